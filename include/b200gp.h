@@ -1,0 +1,195 @@
+/* b200gp.h -- C-ABI of the B200-native solver backend for tinygp-style Gaussian processes.
+ *
+ * The reference (dfm/tinygp @ 5302d5a) has no FFI: its boundary is the Python `Solver`
+ * protocol (src/tinygp/solvers/solver.py:15-82) that `GaussianProcess.__init__` calls as a
+ * constructor (src/tinygp/gp.py:106-112).  The host package `tinygp_b200` re-declares that
+ * protocol and binds every method to one of the entry points below through ctypes.  Each
+ * entry point names the reference call it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; b200gp_last_error(ctx) gives
+ *     the message.  No exception crosses the ABI.
+ *   - all matrices are row-major fp64.  Pointers are HOST pointers unless the name ends in
+ *     `_dev` (then they are device pointers on the context's device).
+ *   - a context owns one device, one stream and a cache of device buffers; objects created
+ *     from a context (`b200gp_dense`, `b200gp_qs`) own their device-resident factor until freed.
+ *   - calls are host-synchronous (equivalent to jax's .block_until_ready()); a context is
+ *     single-threaded.  ctypes releases the GIL for the duration of a call.
+ *   - non positive-definite input never fails a call: `info` > 0 is the 1-based index of the
+ *     first bad pivot and the factor holds NaNs, which the host maps to log_probability = -inf
+ *     (src/tinygp/gp.py:316).
+ */
+#ifndef B200GP_H
+#define B200GP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200gp_ctx b200gp_ctx;
+typedef struct b200gp_dense b200gp_dense;
+typedef struct b200gp_qs b200gp_qs;
+
+/* ---- kernel programs -------------------------------------------------------------------
+ * A stationary kernel expression (kernels/base.py:170-209 Sum/Product/Constant over the leaves
+ * of kernels/stationary.py:76-235) is lowered by the host to a postfix program of
+ * B200GP_PROG_STRIDE doubles per instruction: {opcode, distance, p0, p1}.
+ */
+#define B200GP_PROG_STRIDE 4
+#define B200GP_PROG_MAX_INSTR 32
+enum {
+    B200GP_OP_CONST = 0,          /* p0 = value                      base.py:190-209        */
+    B200GP_OP_EXP = 1,            /* p0 = scale                      stationary.py:76-82    */
+    B200GP_OP_EXPSQUARED = 2,     /* p0 = scale                      stationary.py:104-106  */
+    B200GP_OP_MATERN32 = 3,       /* p0 = scale                      stationary.py:126-129  */
+    B200GP_OP_MATERN52 = 4,       /* p0 = scale                      stationary.py:150-153  */
+    B200GP_OP_COSINE = 5,         /* p0 = scale                      stationary.py:173-175  */
+    B200GP_OP_EXPSINESQUARED = 6, /* p0 = scale, p1 = gamma          stationary.py:202-205  */
+    B200GP_OP_RATIONALQUADRATIC = 7, /* p0 = scale, p1 = alpha       stationary.py:232-235  */
+    B200GP_OP_ADD = 16,           /* pops two, pushes sum            base.py:170-177        */
+    B200GP_OP_MUL = 17            /* pops two, pushes product        base.py:180-187        */
+};
+enum { B200GP_DIST_L1 = 0, B200GP_DIST_L2 = 1 }; /* kernels/distance.py:41-59 */
+
+/* ---- context ---------------------------------------------------------------------------- */
+int b200gp_version(void);
+/* stream: a cudaStream_t to launch on (e.g. torch's current stream) or NULL for a private one. */
+int b200gp_create(int device, void* stream, b200gp_ctx** out);
+int b200gp_destroy(b200gp_ctx* ctx);
+const char* b200gp_last_error(b200gp_ctx* ctx);
+/* number of kernel launches issued by this context since creation (bench "gpu_launches"). */
+int64_t b200gp_launch_count(b200gp_ctx* ctx);
+/* tunables: "nb" (outer panel width, multiple of 128), "profile" (0/1: per-kernel CUDA-event timers) */
+int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value);
+
+/* per-kernel device timings accumulated while option "profile"=1 (ms, CUDA events on ctx stream) */
+typedef struct {
+    double syrk_ms;     /* trailing-update DMMA GEMM launches             */
+    double syrk_flop;   /* useful flop issued by those launches (2*M*N*K over computed tiles) */
+    int64_t syrk_launches;
+    double panel_ms;    /* potf2 + panel GEMMs                            */
+    double build_ms;    /* stand-alone kernel-matrix build launches       */
+    double build_bytes; /* bytes written by those launches                */
+    double solve_ms;    /* triangular solves                              */
+    double qs_ms;       /* quasiseparable scan kernels                    */
+    double qs_bytes;    /* algorithmic bytes moved by them                */
+    int64_t qs_launches;
+} b200gp_profile;
+int b200gp_get_profile(b200gp_ctx* ctx, b200gp_profile* out, int reset);
+
+/* fp64 tensor (DMMA) peak micro-benchmark on this device: returns achieved TFLOP/s of a
+ * register-resident mma.sync.m8n8k4.f64 loop on all SMs, and of a DFMA loop. */
+int b200gp_measure_fp64_peak(b200gp_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+
+/* ---- kernels.Kernel.__call__  (kernels/base.py:84-103) ---------------------------------- */
+/* out[n1*n2] = k(X1_i, X2_j);  X1 (n1, ndim), X2 (n2, ndim) row-major. */
+int b200gp_kernel_matrix(b200gp_ctx* ctx, const double* prog, int n_instr,
+                         const double* X1, int64_t n1, const double* X2, int64_t n2, int ndim,
+                         double* out);
+/* out[n] = k(X_i, X_i)  (evaluate_diag, base.py:59-66) */
+int b200gp_kernel_diag(b200gp_ctx* ctx, const double* prog, int n_instr,
+                       const double* X, int64_t n, int ndim, double* out);
+/* out[n1] = k(X1, X2) @ y  (Kernel.matmul, base.py:68-82) without materialising K on the host */
+int b200gp_kernel_matvec(b200gp_ctx* ctx, const double* prog, int n_instr,
+                         const double* X1, int64_t n1, const double* X2, int64_t n2, int ndim,
+                         const double* y, double* out);
+
+/* ---- solvers.DirectSolver  (solvers/direct.py:17-95) ------------------------------------ */
+/* __init__ (direct.py:30-53): K = k(X,X) + diag generated tile-by-tile on the device and
+ * factored in place, L L^T = K.  `info` as described above. */
+int b200gp_dense_create(b200gp_ctx* ctx, const double* prog, int n_instr,
+                        const double* X, int64_t n, int ndim, const double* diag,
+                        b200gp_dense** out, int* info);
+/* same with X/diag already resident on the device (bench `value` leg) */
+int b200gp_dense_create_dev(b200gp_ctx* ctx, const double* prog, int n_instr,
+                            const double* X_dev, int64_t n, int ndim, const double* diag_dev,
+                            b200gp_dense** out, int* info);
+/* __init__ with covariance= given (direct.py:50-53): factor a host n x n matrix. */
+int b200gp_dense_create_from_cov(b200gp_ctx* ctx, const double* cov, int64_t n,
+                                 b200gp_dense** out, int* info);
+int b200gp_dense_free(b200gp_dense* s);
+/* normalization() - n/2 log(2 pi) = sum_i log L_ii   (direct.py:61-64) */
+int b200gp_dense_logdet_half(b200gp_dense* s, double* out);
+/* solve_triangular (direct.py:66-70): Y (n, nrhs) row-major, in place. */
+int b200gp_dense_solve_triangular(b200gp_dense* s, double* Y, int64_t nrhs, int transpose);
+/* dot_triangular (direct.py:72-73): Y <- L @ Y, Y (n, nrhs). */
+int b200gp_dense_dot_triangular(b200gp_dense* s, double* Y, int64_t nrhs);
+/* condition (direct.py:75-95): out (m, m) = Kss - A^T A, A = L^-1 Ks; Xtest NULL => X. */
+int b200gp_dense_condition(b200gp_dense* s, const double* prog, int n_instr,
+                           const double* Xtest, int64_t m, const double* diag_test, double* out);
+/* covariance() (direct.py:58-59): regenerated by the build kernel; only valid for objects
+ * created from a program.  out (n, n). */
+int b200gp_dense_covariance(b200gp_dense* s, double* out);
+/* scale_tril (direct.py:28): lower factor, zeros above the diagonal.  out (n, n). */
+int b200gp_dense_get_factor(b200gp_dense* s, double* out);
+/* GaussianProcess.log_probability (gp.py:126-138,313-320) for a fresh factor, fused:
+ * logp = -0.5 |L^-1 r|^2 - sum log L_ii - n/2 log 2pi ; non-finite -> -inf.  r = y - mean. */
+int b200gp_dense_log_probability(b200gp_ctx* ctx, const double* prog, int n_instr,
+                                 const double* X, int64_t n, int ndim, const double* diag,
+                                 const double* resid, double* logp);
+int b200gp_dense_log_probability_dev(b200gp_ctx* ctx, const double* prog, int n_instr,
+                                     const double* X_dev, int64_t n, int ndim,
+                                     const double* diag_dev, const double* resid_dev, double* logp);
+/* batched hyper-parameter grid (BASELINE config 5): nbatch programs of equal length over one X;
+ * diag (n) and resid (n) shared.  logp[nbatch]. */
+int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const double* progs, int n_instr,
+                                         int64_t nbatch, const double* X, int64_t n, int ndim,
+                                         const double* diag, const double* resid, double* logp);
+
+/* ---- solvers.QuasisepSolver  (solvers/quasisep/solver.py:19-139) ------------------------- */
+/* Quasiseparable kernels (kernels/quasisep.py) are lowered to a list of `ncomp` components
+ * (a Sum is block-diagonal, quasisep.py:241-295), each B200GP_QS_STRIDE doubles:
+ * {kind, sigma_scale, p0, p1, p2, p3, 0, 0}.  sigma_scale multiplies Pinf (Scale, :334-340). */
+#define B200GP_QS_STRIDE 8
+#define B200GP_QS_MAX_COMP 8
+#define B200GP_QS_MAX_J 8
+enum {
+    B200GP_QS_EXP = 0,      /* p0 = scale, p1 = sigma                 quasisep.py:491-525 */
+    B200GP_QS_MATERN32 = 1, /* p0 = scale, p1 = sigma                 quasisep.py:528-569 */
+    B200GP_QS_MATERN52 = 2, /* p0 = scale, p1 = sigma                 quasisep.py:572-633 */
+    B200GP_QS_SHO = 3,      /* p0 = omega, p1 = quality, p2 = sigma   quasisep.py:404-488 */
+    B200GP_QS_CELERITE = 4, /* p0..p3 = a, b, c, d                    quasisep.py:343-401 */
+    B200GP_QS_COSINE = 5    /* p0 = scale, p1 = sigma                 quasisep.py:636-673 */
+};
+/* _check_sorted (solver.py:142-146): *unsorted = any(diff(t) < 0), bit-exact boolean. */
+int b200gp_qs_check_sorted(b200gp_ctx* ctx, const double* t, int64_t n, int* unsorted);
+/* __init__ (solver.py:35-82): generators (quasisep.py:102-116) + noise + Cholesky (ops.py:352-365).
+ * `unsorted` is set (and nothing factored, rc=0) if assume_sorted==0 and t is not sorted. */
+int b200gp_qs_create(b200gp_ctx* ctx, const double* comps, int ncomp,
+                     const double* t, int64_t n, const double* diag, int assume_sorted,
+                     b200gp_qs** out, int* unsorted, int* info);
+int b200gp_qs_create_dev(b200gp_ctx* ctx, const double* comps, int ncomp,
+                         const double* t_dev, int64_t n, const double* diag_dev, int assume_sorted,
+                         b200gp_qs** out, int* unsorted, int* info);
+int b200gp_qs_free(b200gp_qs* s);
+int b200gp_qs_state_dim(b200gp_qs* s, int* J);
+int b200gp_qs_logdet_half(b200gp_qs* s, double* out);     /* sum log c   (solver.py:90-93) */
+int b200gp_qs_variance(b200gp_qs* s, double* out);        /* d (n)       (solver.py:84-85) */
+/* factor generators: c (n), w (n, J)  (LowerTriQSM(diag=c, lower=(p, w, a)), core.py:524-539) */
+int b200gp_qs_get_factor(b200gp_qs* s, double* c, double* w);
+/* symmetric generators d (n), p (n,J), q (n,J), a (n,J,J)  (quasisep.py:102-116) */
+int b200gp_qs_get_generators(b200gp_qs* s, double* d, double* p, double* q, double* a);
+/* solve_triangular (solver.py:95-99; ops.py:463-472 / 489-498): Y (n, nrhs) in place */
+int b200gp_qs_solve_triangular(b200gp_qs* s, double* Y, int64_t nrhs, int transpose);
+/* dot_triangular (solver.py:101-102; core.py:303-305, ops.py:308-316) */
+int b200gp_qs_dot_triangular(b200gp_qs* s, double* Y, int64_t nrhs);
+/* SymmQSM @ y (core.py:499-505): Y <- K Y with K the covariance incl. noise */
+int b200gp_qs_matmul(b200gp_qs* s, double* Y, int64_t nrhs);
+/* fused log_probability for a fresh factor (gp.py:313-320 through solver.py:73-99) */
+int b200gp_qs_log_probability(b200gp_ctx* ctx, const double* comps, int ncomp,
+                              const double* t, int64_t n, const double* diag, const double* resid,
+                              int assume_sorted, int* unsorted, double* logp);
+int b200gp_qs_log_probability_dev(b200gp_ctx* ctx, const double* comps, int ncomp,
+                                  const double* t_dev, int64_t n, const double* diag_dev,
+                                  const double* resid_dev, int assume_sorted, int* unsorted,
+                                  double* logp);
+/* jnp.searchsorted(X2, X1, side="right") - 1  (kernels/quasisep.py:121): bit-exact indices */
+int b200gp_searchsorted_right_m1(b200gp_ctx* ctx, const double* sorted, int64_t n,
+                                 const double* query, int64_t m, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GP_H */

@@ -1,0 +1,213 @@
+"""Parity of the CUDA DirectSolver path against the oracle (run with -m gpu on the B200 box).
+Everything goes through the C-ABI (ctypes) exactly as a user of the plugin surface would."""
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+from oracle import tinygp_np as o
+from tinygp_b200 import GaussianProcess, kernels, noise, solvers
+from util import LOGP_RTOL, assert_close, rel, to_oracle
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = {
+    "expsq": lambda: kernels.ExpSquared(1.5),
+    "exp": lambda: kernels.Exp(0.7),
+    "m32": lambda: kernels.Matern32(1.5),
+    "m32_l2": lambda: kernels.Matern32(1.5, kernels.L2Distance()),
+    "m52": lambda: kernels.Matern52(2.5),
+    "cos": lambda: kernels.Cosine(2.3),
+    "ess": lambda: kernels.ExpSineSquared(2.3, gamma=1.3),
+    "rq": lambda: kernels.RationalQuadratic(1.2, alpha=1.7),
+    "rq_l2": lambda: kernels.RationalQuadratic(1.2, kernels.L2Distance(), alpha=1.7),
+    "expsq_l1": lambda: kernels.ExpSquared(1.5, kernels.L1Distance()),
+    "combo": lambda: 1.8 * kernels.ExpSquared(0.9) + kernels.Matern32(3.0) * kernels.Constant(0.4) + 0.1,
+    "c3": lambda: 1.5 * kernels.Matern52(2.0) + 0.7 * kernels.RationalQuadratic(1.5, alpha=1.5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(KERNELS))
+@pytest.mark.parametrize("ndim", [1, 3])
+def test_kernel_matrix_parity(name, ndim):
+    rng = np.random.default_rng(1234 + ndim)
+    X1 = rng.uniform(-3, 3, (137, ndim)) if ndim > 1 else rng.uniform(-3, 3, 137)
+    X2 = rng.uniform(-3, 3, (61, ndim)) if ndim > 1 else rng.uniform(-3, 3, 61)
+    k = KERNELS[name]()
+    ko = to_oracle(k)
+    np.testing.assert_allclose(k(X1, X2), ko(X1, X2), rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(k(X1, X1), ko(X1, X1), rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(k(X1), ko(X1), rtol=1e-15)
+    y = rng.normal(size=61)
+    np.testing.assert_allclose(k.matmul(X1, X2, y), ko(X1, X2) @ y, rtol=1e-11, atol=1e-12)
+    # the diagonal of a stationary kernel is exact (explicit differences, distance.py:58-59)
+    if name not in ("combo", "c3"):
+        assert np.all(np.diag(k(X1, X1)) == np.diag(ko(X1, X1)))
+
+
+def test_scalar_evaluate_and_edge_shapes():
+    k = kernels.Matern52(1.3)
+    assert np.isclose(k.evaluate(0.3, 1.1), to_oracle(k)(np.array([0.3]), np.array([1.1]))[0, 0], rtol=1e-14)
+    one = k(np.array([0.5]), np.array([0.5, 0.7]))
+    assert one.shape == (1, 2) and one[0, 0] == 1.0
+    with pytest.raises(ValueError):
+        k(np.zeros((3, 2)), np.zeros((3, 3)))
+    with pytest.raises(Exception):
+        k(np.zeros((0,)), np.zeros((3,)))
+
+
+@pytest.mark.parametrize("n", [1, 50, 128, 300, 1100])
+def test_factor_parity(n, ctx):
+    rng = np.random.default_rng(n)
+    X = rng.uniform(0, 6, (n, 2))
+    k = 1.3 * kernels.ExpSquared(0.8)
+    diag = rng.uniform(0.05, 0.2, n)
+    for nb in (128, 512):
+        ctx.set_option("nb", nb)
+        s = solvers.DirectSolver(k, X, noise.Diagonal(diag))
+        so = o.DirectSolver(to_oracle(k), X, o.Diagonal(diag))
+        assert s.info == 0
+        np.testing.assert_allclose(s.scale_tril, so.scale_tril, rtol=1e-10, atol=1e-12)
+        assert rel(s.normalization(), so.normalization()) < 1e-12
+        assert_close(s.variance(), so.variance(), 1e-14, 1e-14)
+        np.testing.assert_allclose(s.covariance(), so.covariance(), rtol=1e-13, atol=1e-15)
+    ctx.set_option("nb", 512)
+
+
+@pytest.mark.parametrize("n,ndim,name", [(256, 1, "expsq"), (777, 3, "c3"), (2048, 3, "expsq"), (1500, 2, "combo")])
+def test_log_probability_parity(n, ndim, name):
+    rng = np.random.default_rng(84930)
+    if ndim == 1:
+        X = np.sort(rng.uniform(-3, 3, n))  # BASELINE config 1 (test_solver.py:19-24)
+        y = np.sin(X)
+    else:
+        X = rng.uniform(0, 8, (n, ndim))
+        y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    k = KERNELS[name]()
+    lp = GaussianProcess(k, X, diag=0.1).log_probability(y)
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+    assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+    # mean handling (gp.py:81-88)
+    lp = GaussianProcess(k, X, diag=0.1, mean=0.3).log_probability(y)
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1, mean=0.3).log_probability(y)
+    assert rel(lp, lpo) < LOGP_RTOL
+
+
+def test_fused_log_probability_entry_point(ctx):
+    from ctypes import byref, c_double
+    from tinygp_b200 import _cabi
+    rng = np.random.default_rng(5)
+    n = 900
+    X = np.ascontiguousarray(rng.uniform(0, 8, (n, 3)))
+    y = np.sin(X[:, 0])
+    diag = np.full(n, 0.1)
+    k = kernels.ExpSquared(1.0)
+    prog = k.program()
+    lp = c_double()
+    ctx.check(ctx.lib.b200gp_dense_log_probability(ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(X), n, 3,
+                                                   _cabi.ptr(diag), _cabi.ptr(y), byref(lp)))
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+    assert rel(lp.value, lpo) < LOGP_RTOL
+
+
+def test_solves_and_products():
+    rng = np.random.default_rng(7)
+    n = 700
+    X = rng.uniform(0, 8, (n, 3))
+    k = kernels.Matern32(2.0)
+    s = solvers.DirectSolver(k, X, noise.Diagonal(np.full(n, 0.1)))
+    L = np.linalg.cholesky(to_oracle(k)(X, X) + 0.1 * np.eye(n))
+    y = rng.normal(size=n)
+    Y = rng.normal(size=(n, 5))
+    np.testing.assert_allclose(s.solve_triangular(y), scipy.linalg.solve_triangular(L, y, lower=True),
+                               rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(s.solve_triangular(y, transpose=True),
+                               scipy.linalg.solve_triangular(L, y, lower=True, trans=1), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(s.solve_triangular(Y), scipy.linalg.solve_triangular(L, Y, lower=True),
+                               rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(s.solve_triangular(Y, transpose=True),
+                               scipy.linalg.solve_triangular(L, Y, lower=True, trans=1), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(s.dot_triangular(y), L @ y, rtol=1e-11, atol=1e-12)
+    Z = rng.normal(size=(n, 3, 2))
+    np.testing.assert_allclose(s.dot_triangular(Z), np.einsum("ij,j...->i...", L, Z), rtol=1e-11, atol=1e-12)
+    # tests/test_kernels/test_kernels.py:72-83
+    Kinv_y = s.solve_triangular(s.solve_triangular(y), transpose=True)
+    np.testing.assert_allclose(Kinv_y, np.linalg.solve(L @ L.T, y), rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("n,m", [(300, 40), (500, 200)])
+def test_condition_and_predict(n, m):
+    rng = np.random.default_rng(11)
+    X = rng.uniform(0, 6, (n, 2))
+    Xt = rng.uniform(0, 6, (m, 2))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    k = 1.5 * kernels.Matern52(2.0)
+    gp = GaussianProcess(k, X, diag=0.1, mean=0.2)
+    gpo = o.GaussianProcess(to_oracle(k), X, diag=0.1, mean=0.2)
+    lp, cond = gp.condition(y, Xt, diag=0.05)
+    lpo, condo = gpo.condition(y, Xt, diag=0.05)
+    assert rel(lp, lpo) < LOGP_RTOL
+    assert_close(cond.loc, condo.loc)
+    assert_close(cond.covariance, condo.covariance)
+    assert_close(cond.variance, condo.variance)
+    # conditioned GP is itself a working GP (second M x M Cholesky, gp.py:208-221)
+    yt = rng.normal(size=m)
+    assert rel(cond.log_probability(yt), condo.log_probability(yt)) < 1e-7
+    # predict at the inputs (noise shortcut) and with return_var / return_cov
+    assert_close(gp.predict(y), gpo.predict(y))
+    mu, var = gp.predict(y, Xt, return_var=True)
+    muo, varo = gpo.predict(y, Xt, return_var=True)
+    assert_close(mu, muo)
+    assert_close(var, varo)
+    mu, cov = gp.predict(y, return_cov=True, include_mean=False)
+    muo, covo = gpo.predict(y, return_cov=True, include_mean=False)
+    assert_close(mu, muo)
+    assert_close(cov, covo)
+    with pytest.raises(ValueError):
+        gp.condition(y, np.zeros((4, 3)))
+
+
+def test_non_pd_gives_minus_inf():
+    X = np.zeros((200, 1))
+    gp = GaussianProcess(kernels.ExpSquared(1.0), X, diag=-2.0)
+    assert gp.solver.info > 0
+    assert gp.log_probability(np.ones(200)) == -np.inf
+    # default jitter (gp.py:388-393) on distinct points is fine
+    X = np.linspace(0, 100, 200)
+    gp = GaussianProcess(kernels.Exp(1.0), X)
+    gpo = o.GaussianProcess(o.Exp(1.0), X)
+    assert rel(gp.log_probability(np.sin(X)), gpo.log_probability(np.sin(X))) < 1e-7
+
+
+def test_sampling_statistics():
+    # tests/test_gp.py:24-38 (statistical parity only: the RNG stream differs from JAX's)
+    rng = np.random.default_rng(1058390)
+    X = np.sort(rng.uniform(-3, 3, 30))
+    gp = GaussianProcess(kernels.Matern32(1.5), X, diag=0.01, mean=0.5)
+    y = gp.sample(123, shape=(50_000,))
+    assert y.shape == (50_000, 30)
+    assert np.allclose(np.mean(y, axis=0), 0.5, atol=0.02)
+    assert np.allclose(np.cov(y, rowvar=False), gp.covariance, atol=0.03)
+    assert gp.sample(1).shape == (30,)
+
+
+def test_large_n_properties():
+    """N = 8192: parity against the oracle (LAPACK dpotrf, ~3 s) plus size-independent identities."""
+    rng = np.random.default_rng(49382)
+    n = 8192
+    X = rng.uniform(0, 10, (n, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    k = 1.0 * kernels.ExpSquared(1.0)
+    gp = GaussianProcess(k, X, diag=0.1)
+    lp = gp.log_probability(y)
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+    assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+    # L (L^T (L^-T (L^-1 y))) == y   and   |L z|^2 == z^T K z
+    a = gp.solver.solve_triangular(gp.solver.solve_triangular(y), transpose=True)
+    back = gp.solver.dot_triangular(gp.solver.solve_triangular(y))
+    np.testing.assert_allclose(back, y, rtol=1e-9, atol=1e-10)
+    z = rng.normal(size=n)
+    Lz = gp.solver.dot_triangular(z)
+    Kz = k.matmul(X, X, z) + 0.1 * z
+    assert rel(Lz @ Lz, z @ Kz) < 1e-10
+    assert rel(y @ a, np.sum(gp.solver.solve_triangular(y) ** 2)) < 1e-10

@@ -1,0 +1,100 @@
+"""Host logic and the C-ABI surface without a GPU."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tinygp_b200 import _cabi, kernels, noise
+from tinygp_b200.kernels import quasisep as Q
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = _cabi.load_library()
+    header = open(os.path.join(ROOT, "include", "b200gp.h")).read()
+    declared = set(re.findall(r"\b(b200gp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"b200gp_ctx", "b200gp_dense", "b200gp_qs", "b200gp_profile"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200gp.h but not exported"
+        assert name in _cabi.SIGNATURES, f"{name} has no ctypes prototype"
+    assert lib.b200gp_version() >= 100
+
+
+def test_no_cpu_fallback_when_no_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_cabi.B200Error, match="no CPU fallback"):
+        _cabi.Context()
+
+
+def test_kernel_program_lowering():
+    k = 1.5 * kernels.ExpSquared(scale=1.2) + kernels.Matern32(2.0) * kernels.RationalQuadratic(alpha=1.5)
+    prog = k.program()
+    assert prog.shape == (7, 4)
+    assert prog[:, 0].tolist() == [0, 2, 17, 3, 7, 17, 16]
+    assert prog[1, 1] == 1 and prog[3, 1] == 0 and prog[4, 1] == 0   # L2 default only for ExpSquared
+    assert prog[4, 3] == 1.5
+    assert sum([kernels.Exp(1.0), kernels.Exp(2.0)]).program().shape == (3, 4)   # __radd__ with 0
+    assert (kernels.Exp(1.0) + 2.0).program()[1].tolist() == [0, 0, 2.0, 0]
+
+
+def test_unsupported_kernels_raise():
+    for k in (kernels.DotProduct(), kernels.Polynomial(order=2), kernels.Custom(lambda a, b: a * b)):
+        with pytest.raises(NotImplementedError, match="B200"):
+            k.program()
+
+    class MyDist(kernels.Distance):
+        pass
+
+    with pytest.raises(NotImplementedError, match="B200"):
+        kernels.Matern32(1.0, distance=MyDist()).program()
+    with pytest.raises(ValueError, match="scalar"):
+        kernels.Exp(scale=np.ones(2)).program()
+    with pytest.raises(ValueError, match="alpha"):
+        kernels.RationalQuadratic()
+    with pytest.raises(ValueError, match="gamma"):
+        kernels.ExpSineSquared()
+    with pytest.raises(ValueError):
+        kernels.Constant(np.ones(3))
+    with pytest.raises(NotImplementedError):
+        noise.Dense(np.eye(3))
+
+
+def test_quasisep_components():
+    k = Q.SHO(omega=1.5, quality=3.0, sigma=1.8) + 0.7 * Q.Matern32(scale=1.5, sigma=0.9)
+    c = k.component_array()
+    assert c.shape == (2, 8)
+    assert c[0, :5].tolist() == [3, 1.0, 1.5, 3.0, 1.8]
+    assert c[1, :4].tolist() == [1, 0.7, 1.5, 0.9]
+    assert k.state_dim() == 4
+    with pytest.raises(ValueError):
+        Q.Matern32(1.0) + kernels.Exp(1.0)
+    with pytest.raises(NotImplementedError):
+        (Q.Matern32(1.0) * Q.Exp(1.0)).components()
+    # closed forms used for dense evaluation agree with the oracle's state-space evaluation
+    from oracle import tinygp_np as o
+    X = np.linspace(0, 3, 7)
+    ko = o.qs.SHO(1.5, 3.0, 1.8) + o.qs.Scale(o.qs.Matern32(1.5, 0.9), 0.7)
+    np.testing.assert_allclose(k(X, X), ko(X, X), rtol=1e-12, atol=1e-14)
+    for kk, oo in [(Q.SHO(1.5, 0.3), o.qs.SHO(1.5, 0.3)), (Q.SHO(1.5, 0.5), o.qs.SHO(1.5, 0.5)),
+                   (Q.Matern52(1.3, 0.8), o.qs.Matern52(1.3, 0.8)), (Q.Exp(1.3, 0.8), o.qs.Exp(1.3, 0.8)),
+                   (Q.Cosine(1.3, 0.8), o.qs.Cosine(1.3, 0.8)),
+                   (Q.Celerite(1.1, 0.8, 0.9, 0.1), o.qs.Celerite(1.1, 0.8, 0.9, 0.1))]:
+        np.testing.assert_allclose(kk(X, X), oo(X, X), rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(kk(X), oo(X), rtol=1e-12)
+
+
+def test_noise_diagonal():
+    d = noise.Diagonal(np.array([1.0, 2.0]))
+    assert (d + np.zeros((2, 2))).tolist() == [[1, 0], [0, 2]]
+    assert (np.ones((2, 2)) + d).tolist() == [[2, 1], [1, 3]]
+    assert (d @ np.array([3.0, 4.0])).tolist() == [3, 8]
+    with pytest.raises(ValueError):
+        noise.Diagonal(1.0)

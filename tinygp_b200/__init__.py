@@ -1,0 +1,11 @@
+"""tinygp_b200 -- a B200-native solver backend behind tinygp's plugin surface.
+
+``GaussianProcess`` / ``kernels`` / ``noise`` / ``solvers`` mirror ``tinygp``'s names
+(src/tinygp/__init__.py); the arithmetic runs in hand-written sm_100a CUDA behind the C-ABI of
+``include/b200gp.h``.  There is no CPU fallback.
+"""
+
+__version__ = "0.1.0"
+
+from tinygp_b200 import kernels as kernels, means as means, noise as noise, solvers as solvers
+from tinygp_b200.gp import ConditionResult as ConditionResult, GaussianProcess as GaussianProcess

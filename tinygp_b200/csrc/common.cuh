@@ -1,0 +1,121 @@
+// Shared internals of libb200gp: context, error handling, device buffer cache, kernel programs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/b200gp.h"
+
+#define TILE 128  // diagonal-block / tile edge used throughout the dense path
+
+struct GpError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CUDA_CHECK(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            char _buf[512];                                                                \
+            snprintf(_buf, sizeof(_buf), "%s failed at %s:%d: %s", #expr, __FILE__,        \
+                     __LINE__, cudaGetErrorString(_e));                                    \
+            throw GpError(_buf);                                                           \
+        }                                                                                  \
+    } while (0)
+
+// ---- kernel program (device-side copy passed by value as a kernel parameter) -------------
+struct KProg {
+    int n;
+    int op[B200GP_PROG_MAX_INSTR];
+    int dist[B200GP_PROG_MAX_INSTR];
+    double p0[B200GP_PROG_MAX_INSTR];
+    double p1[B200GP_PROG_MAX_INSTR];
+};
+
+KProg parse_prog(const double* prog, int n_instr);
+
+struct CachedBuf {
+    void* ptr;
+    size_t bytes;
+};
+
+struct b200gp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+    int64_t nb = 512;  // outer panel width of the blocked Cholesky
+    bool profile = false;
+    b200gp_profile prof{};
+    std::vector<CachedBuf> cache;  // freed big buffers kept for reuse
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int num_sms = 148;
+
+    void* alloc(size_t bytes);
+    void release(void* p, size_t bytes);  // return to cache
+    void trim();                          // cudaFree everything cached
+};
+
+// RAII timer that accumulates into a profile field when ctx->profile is on.
+struct ProfTimer {
+    b200gp_ctx* c;
+    double* acc;
+    ProfTimer(b200gp_ctx* ctx, double* field) : c(ctx), acc(field) {
+        if (c->profile) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~ProfTimer() {
+        if (c->profile) {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            *acc += ms;
+        }
+    }
+};
+
+#define API_BEGIN(ctxptr)            \
+    b200gp_ctx* _ctx = (ctxptr);     \
+    if (!_ctx) return 1;             \
+    try {                            \
+        CUDA_CHECK(cudaSetDevice(_ctx->device));
+#define API_END                      \
+        return 0;                    \
+    } catch (const std::exception& e) { \
+        _ctx->err = e.what();        \
+        return 2;                    \
+    }
+
+// ---- dense path (dense.cu) -----------------------------------------------------------------
+struct b200gp_dense {
+    b200gp_ctx* ctx = nullptr;
+    int64_t n = 0;    // logical size
+    int64_t np = 0;   // padded to a multiple of TILE (= leading dimension)
+    double* mat = nullptr;   // np x np row-major; lower triangle holds L after factorisation
+    double* linv = nullptr;  // np/TILE inverses of the diagonal blocks, each TILE x TILE
+    int* info_dev = nullptr;
+    int info = 0;
+    // what is needed to regenerate covariance() / run condition()
+    bool has_prog = false;
+    KProg prog{};
+    int ndim = 0;
+    double* X_dev = nullptr;     // n x ndim
+    double* diag_dev = nullptr;  // n
+    bool owns_inputs = false;
+};
+
+void dense_build_rect(b200gp_ctx* ctx, const KProg& prog, const double* X1, int64_t n1,
+                      const double* X2, int64_t n2, int ndim, const double* diag_or_null,
+                      double* out, int64_t ld, int64_t rows_pad, int64_t cols_pad);
+b200gp_dense* dense_factor_from_prog(b200gp_ctx* ctx, const KProg& prog, const double* X_dev,
+                                     int64_t n, int ndim, const double* diag_dev, bool copy_inputs);
+void dense_factor_inplace(b200gp_dense* s, bool generate);
+void dense_destroy(b200gp_dense* s);
+double dense_logdet_half(b200gp_dense* s);
+void dense_solve_vec_dev(b200gp_dense* s, double* y_dev /* np, destroyed */, double* x_dev /* np */,
+                         bool transpose);
+double dense_sumsq_dev(b200gp_ctx* ctx, const double* x_dev, int64_t n);

@@ -1,0 +1,187 @@
+// Context, device-buffer cache, options, profile counters and the fp64 peak micro-benchmarks.
+#include "common.cuh"
+#include <string.h>
+
+void* b200gp_ctx::alloc(size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    // best fit from the cache: smallest cached buffer that is large enough and not > 1.25x
+    int best = -1;
+    for (int i = 0; i < (int)cache.size(); ++i) {
+        if (cache[i].bytes >= bytes && (double)cache[i].bytes <= 1.25 * (double)bytes + 4096.0) {
+            if (best < 0 || cache[i].bytes < cache[best].bytes) best = i;
+        }
+    }
+    if (best >= 0) {
+        void* p = cache[best].ptr;
+        cache.erase(cache.begin() + best);
+        return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        trim();  // drop cached buffers and retry once
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        char buf[256];
+        snprintf(buf, sizeof(buf), "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        throw GpError(buf);
+    }
+    return p;
+}
+
+void b200gp_ctx::release(void* p, size_t bytes) {
+    if (!p) return;
+    if (bytes == 0) bytes = 8;
+    // the stream may still be using p: all frees go through the cache, and a cached buffer is only
+    // ever handed to work enqueued later on the same stream, so ordering is preserved.
+    cache.push_back({p, bytes});
+    size_t total = 0;
+    for (auto& c : cache) total += c.bytes;
+    // keep at most ~48 GiB or 64 entries cached
+    while (cache.size() > 64 || total > ((size_t)48 << 30)) {
+        cudaStreamSynchronize(stream);
+        total -= cache.front().bytes;
+        cudaFree(cache.front().ptr);
+        cache.erase(cache.begin());
+    }
+}
+
+void b200gp_ctx::trim() {
+    cudaStreamSynchronize(stream);
+    for (auto& c : cache) cudaFree(c.ptr);
+    cache.clear();
+}
+
+// ---- fp64 peak micro-benchmarks ----------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[i][0]), "+d"(c[i][1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = i * 1e-3;
+    const double a = 1.0 + threadIdx.x * 1e-12, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" {
+
+int b200gp_version(void) { return 100; }
+
+int b200gp_create(int device, void* stream, b200gp_ctx** out) {
+    if (!out) return 1;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return 3;  // no usable CUDA device: the host raises, there is no CPU fallback
+    }
+    b200gp_ctx* c = new b200gp_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return 3; }
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 3; }
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    memset(&c->prof, 0, sizeof(c->prof));
+    *out = c;
+    return 0;
+}
+
+int b200gp_destroy(b200gp_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    ctx->trim();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+const char* b200gp_last_error(b200gp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t b200gp_launch_count(b200gp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
+    API_BEGIN(ctx)
+    if (!strcmp(key, "nb")) {
+        if (value < TILE || value % TILE) throw GpError("option nb must be a positive multiple of 128");
+        _ctx->nb = value;
+    } else if (!strcmp(key, "profile")) {
+        _ctx->profile = (value != 0);
+    } else if (!strcmp(key, "trim")) {
+        _ctx->trim();
+    } else {
+        throw GpError(std::string("unknown option ") + key);
+    }
+    API_END
+}
+
+int b200gp_get_profile(b200gp_ctx* ctx, b200gp_profile* out, int reset) {
+    API_BEGIN(ctx)
+    *out = _ctx->prof;
+    if (reset) memset(&_ctx->prof, 0, sizeof(_ctx->prof));
+    API_END
+}
+
+int b200gp_measure_fp64_peak(b200gp_ctx* ctx, double* dmma_tflops, double* dfma_tflops) {
+    API_BEGIN(ctx)
+    const int blocks = _ctx->num_sms * 4, threads = 256, iters = 4096;
+    double* buf = (double*)_ctx->alloc((size_t)blocks * threads * 8);
+    float ms = 0;
+    for (int rep = 0; rep < 2; ++rep) {  // first pass warms up
+        cudaEventRecord(_ctx->ev0, _ctx->stream);
+        dmma_peak_kernel<<<blocks, threads, 0, _ctx->stream>>>(buf, iters);
+        cudaEventRecord(_ctx->ev1, _ctx->stream);
+        CUDA_CHECK(cudaEventSynchronize(_ctx->ev1));
+        cudaEventElapsedTime(&ms, _ctx->ev0, _ctx->ev1);
+    }
+    // per warp per instruction: 8*8*4 FMA = 512 flop
+    *dmma_tflops = (double)blocks * (threads / 32) * (double)iters * 16.0 * 512.0 / (ms * 1e-3) / 1e12;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(_ctx->ev0, _ctx->stream);
+        dfma_peak_kernel<<<blocks, threads, 0, _ctx->stream>>>(buf, iters);
+        cudaEventRecord(_ctx->ev1, _ctx->stream);
+        CUDA_CHECK(cudaEventSynchronize(_ctx->ev1));
+        cudaEventElapsedTime(&ms, _ctx->ev0, _ctx->ev1);
+    }
+    *dfma_tflops = (double)blocks * threads * (double)iters * 16.0 * 2.0 / (ms * 1e-3) / 1e12;
+    _ctx->launches += 4;
+    _ctx->release(buf, (size_t)blocks * threads * 8);
+    API_END
+}
+
+}  // extern "C"

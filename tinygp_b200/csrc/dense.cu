@@ -1,0 +1,1132 @@
+// Dense DirectSolver path for sm_100a: pairwise kernel build (K1), blocked right-looking Cholesky
+// whose panel/trailing updates run on the fp64 tensor pipe (DMMA, mma.sync.m8n8k4.f64) (K2),
+// triangular solves + reductions behind log_probability (K3), L@z (K4).
+//
+// Reference behaviour being replaced: src/tinygp/solvers/direct.py:30-95 (DirectSolver),
+// src/tinygp/kernels/base.py:84-103 (Kernel.__call__), src/tinygp/kernels/stationary.py:76-235,
+// src/tinygp/kernels/distance.py:41-59, src/tinygp/noise.py:77-78.
+//
+// Data layout in HBM: one np x np row-major fp64 matrix (np = n rounded up to 128; the pad is an
+// identity block so it contributes log 1 = 0 to the determinant), lower triangle significant.
+// Row-major makes BOTH operands of every update  C_ij -= P_i P_j^T  K-contiguous (a panel row is
+// a contiguous run of doubles), which is exactly the row.col operand form of mma.m8n8k4.f64.
+#include "common.cuh"
+#include <limits.h>
+
+// =============================================================================================
+// kernel-program evaluation (device)
+// =============================================================================================
+#define MAX_NDIM 16
+#define SQRT3 1.7320508075688772
+#define SQRT5 2.23606797749979
+#define PI_D 3.141592653589793
+
+// l1 = sum_d |x1_d - x2_d| ; l2sq = sum_d (x1_d - x2_d)^2   (explicit differences, distance.py:45,59)
+__device__ __forceinline__ double kprog_eval(const KProg& P, double l1, double l2sq) {
+    double st[8];
+    int sp = 0;
+    for (int i = 0; i < P.n; ++i) {
+        const int op = P.op[i];
+        if (op == B200GP_OP_ADD) {
+            --sp;
+            st[sp - 1] = st[sp - 1] + st[sp];
+            continue;
+        }
+        if (op == B200GP_OP_MUL) {
+            --sp;
+            st[sp - 1] = st[sp - 1] * st[sp];
+            continue;
+        }
+        const double p0 = P.p0[i], p1 = P.p1[i];
+        double v;
+        if (op == B200GP_OP_CONST) {
+            v = p0;
+        } else {
+            const bool l2 = (P.dist[i] == B200GP_DIST_L2);
+            if (op == B200GP_OP_EXPSQUARED || op == B200GP_OP_RATIONALQUADRATIC) {
+                // squared_distance / square(scale)   (stationary.py:105,234 ; distance.py:30-38,58-59)
+                const double sq = l2 ? l2sq : l1 * l1;
+                const double r2 = sq / (p0 * p0);
+                if (op == B200GP_OP_EXPSQUARED)
+                    v = exp(-0.5 * r2);
+                else
+                    v = pow(1.0 + 0.5 * r2 / p1, -p1);
+            } else {
+                // distance (distance.py:44-45 / 51-56: sqrt with the r2==0 guard)
+                const double dist = l2 ? ((l2sq == 0.0) ? l1 : sqrt(l2sq)) : l1;
+                const double r = dist / p0;
+                if (op == B200GP_OP_EXP) {
+                    v = exp(-r);
+                } else if (op == B200GP_OP_MATERN32) {
+                    const double arg = SQRT3 * r;
+                    v = (1.0 + arg) * exp(-arg);
+                } else if (op == B200GP_OP_MATERN52) {
+                    const double arg = SQRT5 * r;
+                    v = (1.0 + arg + arg * arg / 3.0) * exp(-arg);
+                } else if (op == B200GP_OP_COSINE) {
+                    v = cos(2.0 * PI_D * r);
+                } else {  // EXPSINESQUARED
+                    const double s = sin(PI_D * r);
+                    v = exp(-p1 * (s * s));
+                }
+            }
+        }
+        st[sp++] = v;
+    }
+    return st[0];
+}
+
+KProg parse_prog(const double* prog, int n_instr) {
+    if (n_instr <= 0 || n_instr > B200GP_PROG_MAX_INSTR) throw GpError("kernel program: bad length");
+    KProg P{};
+    P.n = n_instr;
+    int depth = 0;
+    for (int i = 0; i < n_instr; ++i) {
+        const double* q = prog + (size_t)i * B200GP_PROG_STRIDE;
+        P.op[i] = (int)q[0];
+        P.dist[i] = (int)q[1];
+        P.p0[i] = q[2];
+        P.p1[i] = q[3];
+        const int op = P.op[i];
+        if (op == B200GP_OP_ADD || op == B200GP_OP_MUL) {
+            if (depth < 2) throw GpError("kernel program: stack underflow");
+            --depth;
+        } else if (op >= B200GP_OP_CONST && op <= B200GP_OP_RATIONALQUADRATIC) {
+            ++depth;
+            if (depth > 8) throw GpError("kernel program: expression too deep (max 8)");
+        } else {
+            throw GpError("kernel program: unknown opcode");
+        }
+    }
+    if (depth != 1) throw GpError("kernel program: malformed expression");
+    return P;
+}
+
+// =============================================================================================
+// K1: pairwise kernel build.  out[(i)*ld + j] for i < rows_pad, j < cols_pad.
+// =============================================================================================
+struct BuildArgs {
+    const double* X1;   // n1 x ndim
+    const double* X2;   // n2 x ndim
+    const double* diag; // indexed by global row, or null
+    double* out;
+    int64_t ld;
+    int64_t n1, n2;          // valid extents (in units of out rows / cols, relative to row_off/col_off)
+    int64_t rows_pad, cols_pad;
+    int64_t row_off, col_off;  // global indices of out(0,0), used for the diagonal / identity pad
+    int ndim;
+    int pad_identity;  // padded entries: (grow==gcol) ? 1 : 0 instead of 0
+};
+
+#define BUILD_ROWS 32
+#define BUILD_COLS 128
+__global__ void __launch_bounds__(256) build_rect_kernel(const __grid_constant__ KProg P, const BuildArgs a) {
+    __shared__ double x1s[BUILD_ROWS * MAX_NDIM];
+    __shared__ double x2s[BUILD_COLS * MAX_NDIM];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * BUILD_ROWS;
+    const int64_t c0 = (int64_t)blockIdx.x * BUILD_COLS;
+    const int nd = a.ndim;
+    for (int i = tid; i < BUILD_ROWS * nd; i += 256) {
+        const int64_t r = r0 + i / nd;
+        x1s[i] = (r < a.n1) ? a.X1[r * nd + (i % nd)] : 0.0;
+    }
+    for (int i = tid; i < BUILD_COLS * nd; i += 256) {
+        const int64_t c = c0 + i / nd;
+        x2s[i] = (c < a.n2) ? a.X2[c * nd + (i % nd)] : 0.0;
+    }
+    __syncthreads();
+    const int cl = (tid & 63) * 2;  // two consecutive columns per thread -> 16-byte stores, 512 B per warp
+    const int rl0 = tid >> 6;       // 0..3
+#pragma unroll 2
+    for (int rr = 0; rr < BUILD_ROWS / 4; ++rr) {
+        const int rl = rl0 + rr * 4;
+        const int64_t r = r0 + rl;
+        if (r >= a.rows_pad) break;
+        double v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int64_t c = c0 + cl + e;
+            const int64_t gr = r + a.row_off, gc = c + a.col_off;
+            if (r < a.n1 && c < a.n2) {
+                double l1 = 0.0, l2 = 0.0;
+                for (int d = 0; d < nd; ++d) {
+                    const double df = x1s[rl * nd + d] - x2s[(cl + e) * nd + d];
+                    l1 += fabs(df);
+                    l2 += df * df;
+                }
+                double k = kprog_eval(P, l1, l2);
+                if (a.diag != nullptr && gr == gc) k += a.diag[gr];
+                v[e] = k;
+            } else {
+                v[e] = (a.pad_identity && gr == gc) ? 1.0 : 0.0;
+            }
+        }
+        const int64_t c = c0 + cl;
+        if (c + 1 < a.cols_pad) {
+            *reinterpret_cast<double2*>(a.out + r * a.ld + c) = make_double2(v[0], v[1]);
+        } else if (c < a.cols_pad) {
+            a.out[r * a.ld + c] = v[0];
+        }
+    }
+}
+
+// diag: out[i] = k(x_i, x_i)
+__global__ void build_diag_kernel(const __grid_constant__ KProg P, int64_t n, double* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = kprog_eval(P, 0.0, 0.0);
+}
+
+// out[i] = sum_j k(X1_i, X2_j) y_j   (Kernel.matmul, base.py:68-82) -- one warp per row
+__global__ void __launch_bounds__(256) kernel_matvec_kernel(const __grid_constant__ KProg P, const double* X1, int64_t n1,
+                                                            const double* X2, int64_t n2, int ndim,
+                                                            const double* y, double* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+    if (i >= n1) return;
+    double xi[MAX_NDIM];
+    for (int d = 0; d < ndim; ++d) xi[d] = X1[i * ndim + d];
+    double acc = 0.0;
+    for (int64_t j = lane; j < n2; j += 32) {
+        double l1 = 0.0, l2 = 0.0;
+        for (int d = 0; d < ndim; ++d) {
+            const double df = xi[d] - X2[j * ndim + d];
+            l1 += fabs(df);
+            l2 += df * df;
+        }
+        acc += kprog_eval(P, l1, l2) * y[j];
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[i] = acc;
+}
+
+void dense_build_rect(b200gp_ctx* ctx, const KProg& prog, const double* X1, int64_t n1,
+                      const double* X2, int64_t n2, int ndim, const double* diag_or_null,
+                      double* out, int64_t ld, int64_t rows_pad, int64_t cols_pad) {
+    BuildArgs a{};
+    a.X1 = X1; a.X2 = X2; a.diag = diag_or_null; a.out = out; a.ld = ld;
+    a.n1 = n1; a.n2 = n2; a.rows_pad = rows_pad; a.cols_pad = cols_pad;
+    a.row_off = 0; a.col_off = 0; a.ndim = ndim; a.pad_identity = (diag_or_null != nullptr);
+    dim3 grid((unsigned)((cols_pad + BUILD_COLS - 1) / BUILD_COLS), (unsigned)((rows_pad + BUILD_ROWS - 1) / BUILD_ROWS));
+    ProfTimer t(ctx, &ctx->prof.build_ms);
+    build_rect_kernel<<<grid, 256, 0, ctx->stream>>>(prog, a);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    ctx->prof.build_bytes += 8.0 * (double)rows_pad * (double)cols_pad;
+}
+
+// =============================================================================================
+// K2 core: NT GEMM on the fp64 tensor pipe.   C (op)= alpha * A(MxK) * B(NxK)^T
+// 128x128 CTA tile, 8 warps (2 x 4), warp tile 64 x 32 = 8 x 4 DMMA m8n8k4 atoms,
+// BK = 16 doubles (one 128-byte line per row per stage), 4-stage cp.async pipeline.
+// Shared-memory rows are padded 16 -> 20 doubles so that the (8 rows x 4 k) fragment loads of a
+// half-warp hit 16 distinct 8-byte bank pairs (row stride 40 words = 8 mod 32).
+// =============================================================================================
+namespace gemm {
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, LDS = 20, THREADS = 256;
+constexpr int STAGE_DOUBLES = (BM + BN) * LDS;
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);  // 163840
+constexpr int BAND = 16;  // tile rows per rasterisation band (L2 reuse of the panel operands)
+
+struct Args {
+    const double* A; int64_t lda;
+    const double* B; int64_t ldb;
+    double* C; int64_t ldc;
+    int tiles_m, tiles_n, K;
+    double alpha;
+    int beta_mode;  // 0: C = alpha AB ; 1: C += alpha AB ; 2: C = generator + alpha AB
+    int lower;      // 1: square C, only tiles with tj <= ti are computed
+    // generator (beta_mode 2): C(i,j) = k(x_{row0+i}, x_{col0+j}) + [row==col] diag
+    const double* X; const double* diag; int ndim; int64_t n_valid; int64_t row0, col0;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_ptr, const void* gptr) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_ptr);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gptr));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// linear CTA index -> lower-triangular tile (ti, tj), banded so that concurrently resident CTAs
+// share 16 A row-panels and a handful of B row-panels (both stay in L2).
+__device__ __forceinline__ void lower_tile(int b, int T, int& ti, int& tj) {
+    int R = 0;
+    for (;;) {
+        const int h = min(BAND, T - R * BAND);
+        const int cnt = R * BAND * h + h * (h + 1) / 2;
+        if (b < cnt) {
+            const int full = R * BAND * h;
+            if (b < full) {
+                tj = b / h;
+                ti = R * BAND + b % h;
+            } else {
+                b -= full;
+                int r = 0;
+                while (b >= r + 1) { b -= r + 1; ++r; }
+                ti = R * BAND + r;
+                tj = R * BAND + b;
+            }
+            return;
+        }
+        b -= cnt;
+        ++R;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_constant__ KProg P, const Args g) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+
+    int ti, tj;
+    if (g.lower) {
+        lower_tile((int)blockIdx.x, g.tiles_m, ti, tj);
+    } else {
+        ti = (int)blockIdx.x % g.tiles_m;
+        tj = (int)blockIdx.x / g.tiles_m;
+    }
+    const double* Ag = g.A + (int64_t)ti * BM * g.lda;
+    const double* Bg = g.B + (int64_t)tj * BN * g.ldb;
+
+    // each thread copies 4 x 16 B of A and 4 x 16 B of B per stage
+    const int lrow = tid >> 3;        // 0..31  (+32 per i)
+    const int lc16 = (tid & 7) * 2;   // double offset of the 16-byte chunk within the 128-byte row
+    auto load_stage = [&](int stage, int kc) {
+        double* as = smem + stage * STAGE_DOUBLES;
+        double* bs = as + BM * LDS;
+        const int64_t koff = (int64_t)kc * BK + lc16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = lrow + i * 32;
+            cp_async16(as + r * LDS + lc16, Ag + (int64_t)r * g.lda + koff);
+            cp_async16(bs + r * LDS + lc16, Bg + (int64_t)r * g.ldb + koff);
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    const int KT = g.K / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kc = 0; kc < KT; ++kc) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nk = kc + STAGES - 1;
+        if (nk < KT) load_stage(nk % STAGES, nk);
+        cp_async_commit();
+        const double* as = smem + (kc % STAGES) * STAGE_DOUBLES + (wm * 64 + gq) * LDS + tq;
+        const double* bs = smem + (kc % STAGES) * STAGE_DOUBLES + BM * LDS + (wn * 32 + gq) * LDS + tq;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) a[mi] = as[mi * 8 * LDS + kk * 4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = bs[ni * 8 * LDS + kk * 4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+
+    // epilogue: thread owns rows (wm*64 + mi*8 + gq), column pairs (wn*32 + ni*8 + 2*tq)
+    const int64_t crow0 = (int64_t)ti * BM + wm * 64 + gq;
+    const int64_t ccol0 = (int64_t)tj * BN + wn * 32 + 2 * tq;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        const int64_t r = crow0 + mi * 8;
+        double* crow = g.C + r * g.ldc;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int64_t c = ccol0 + ni * 8;
+            double2 v;
+            if (g.beta_mode == 1) {
+                v = *reinterpret_cast<const double2*>(crow + c);
+            } else if (g.beta_mode == 2) {
+                const int64_t gr = g.row0 + r;
+                double e[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int64_t gc = g.col0 + c + q;
+                    if (gr < g.n_valid && gc < g.n_valid) {
+                        double l1 = 0.0, l2 = 0.0;
+                        for (int d = 0; d < g.ndim; ++d) {
+                            const double df = g.X[gr * g.ndim + d] - g.X[gc * g.ndim + d];
+                            l1 += fabs(df);
+                            l2 += df * df;
+                        }
+                        e[q] = kprog_eval(P, l1, l2);
+                        if (gr == gc) e[q] += g.diag[gr];
+                    } else {
+                        e[q] = (gr == gc) ? 1.0 : 0.0;
+                    }
+                }
+                v = make_double2(e[0], e[1]);
+            } else {
+                v = make_double2(0.0, 0.0);
+            }
+            v.x += g.alpha * acc[mi][ni][0];
+            v.y += g.alpha * acc[mi][ni][1];
+            *reinterpret_cast<double2*>(crow + c) = v;
+        }
+    }
+}
+
+static bool g_attr_set = false;
+static void launch(b200gp_ctx* ctx, const KProg& P, const Args& g) {
+    if (!g_attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        g_attr_set = true;
+    }
+    int64_t ntiles;
+    if (g.lower)
+        ntiles = (int64_t)g.tiles_m * (g.tiles_m + 1) / 2;
+    else
+        ntiles = (int64_t)g.tiles_m * g.tiles_n;
+    if (ntiles <= 0) return;
+    gemm_nt_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(P, g);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+}  // namespace gemm
+
+static const KProg& empty_prog() {
+    static KProg p{};
+    return p;
+}
+
+static void gemm_nt(b200gp_ctx* ctx, double* C, int64_t ldc, const double* A, int64_t lda,
+                    const double* B, int64_t ldb, int tiles_m, int tiles_n, int K, double alpha,
+                    int beta_mode, int lower) {
+    gemm::Args g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.tiles_m = tiles_m; g.tiles_n = tiles_n; g.K = K; g.alpha = alpha;
+    g.beta_mode = beta_mode; g.lower = lower;
+    gemm::launch(ctx, empty_prog(), g);
+}
+
+// =============================================================================================
+// diagonal block: Cholesky of a 128x128 block in shared memory + its triangular inverse.
+// Left-looking column Cholesky; thread (part = tid/128, i = tid%128) owns row i and a quarter of
+// every dot product, so shared-memory accesses are conflict-free (row stride 129 doubles).
+// =============================================================================================
+#define PF_LD 129
+#define PF_THREADS 512
+constexpr int PF_SMEM = (TILE * PF_LD + 4 * TILE + TILE) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel(double* A, int64_t lda, double* linv,
+                                                                    int* info, int global_off) {
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                     // TILE x PF_LD
+    double* red = sm + TILE * PF_LD;    // 4 x TILE partial sums
+    double* tmp = red + 4 * TILE;       // TILE
+    const int tid = threadIdx.x;
+    const int i = tid & (TILE - 1);
+    const int part = tid >> 7;  // 0..3
+
+    // load lower triangle (coalesced along rows), zero the strict upper part
+    for (int e = tid; e < TILE * TILE; e += PF_THREADS) {
+        const int r = e >> 7, c = e & (TILE - 1);
+        S[r * PF_LD + c] = (c <= r) ? A[(int64_t)r * lda + c] : 0.0;
+    }
+    __syncthreads();
+
+    for (int j = 0; j < TILE; ++j) {
+        // partial dots  sum_{k<j, k = part mod 4} L[i][k] L[j][k]   for rows i >= j
+        double s = 0.0;
+        const double ajj = S[j * PF_LD + j];  // read before anyone overwrites column j
+        const double aij = S[i * PF_LD + j];
+        if (i >= j) {
+            const double* ri = S + i * PF_LD;
+            const double* rj = S + j * PF_LD;
+            for (int k = part; k < j; k += 4) s += ri[k] * rj[k];
+        }
+        red[part * TILE + i] = s;
+        __syncthreads();
+        if (part == 0 && i >= j) {
+            const double vj = ajj - (red[j] + red[TILE + j] + red[2 * TILE + j] + red[3 * TILE + j]);
+            if (i == j) {
+                if (!(vj > 0.0)) atomicMin(info, global_off + j + 1);  // NaN or <= 0: first bad pivot
+                S[j * PF_LD + j] = sqrt(vj);
+            } else {
+                const double vi = aij - (red[i] + red[TILE + i] + red[2 * TILE + i] + red[3 * TILE + i]);
+                S[i * PF_LD + j] = vi / sqrt(vj);
+            }
+        }
+        __syncthreads();
+    }
+
+    // write L back (lower triangle only)
+    for (int e = tid; e < TILE * TILE; e += PF_THREADS) {
+        const int r = e >> 7, c = e & (TILE - 1);
+        if (c <= r) A[(int64_t)r * lda + c] = S[r * PF_LD + c];
+    }
+    __syncthreads();
+
+    // in-place inverse of the lower-triangular S (column sweep from the right, LAPACK dtrti2 order):
+    //   inv[j][j] = 1/L[j][j];  inv[i][j] = -inv[j][j] * sum_{k=j+1..i} inv[i][k] L[k][j],  i > j
+    for (int j = TILE - 1; j >= 0; --j) {
+        if (tid < TILE) tmp[tid] = S[tid * PF_LD + j];  // column j of L (rows >= j valid)
+        __syncthreads();
+        const double dj = 1.0 / tmp[j];
+        double s = 0.0;
+        if (i > j) {
+            const double* ri = S + i * PF_LD;
+            for (int k = j + 1 + part; k <= i; k += 4) s += ri[k] * tmp[k];
+        }
+        red[part * TILE + i] = s;
+        __syncthreads();
+        if (part == 0) {
+            if (i == j)
+                S[j * PF_LD + j] = dj;
+            else if (i > j)
+                S[i * PF_LD + j] = -dj * (red[i] + red[TILE + i] + red[2 * TILE + i] + red[3 * TILE + i]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < TILE * TILE; e += PF_THREADS) {
+        const int r = e >> 7, c = e & (TILE - 1);
+        linv[e] = (c <= r) ? S[r * PF_LD + c] : 0.0;
+    }
+}
+
+static void potf2(b200gp_ctx* ctx, double* A, int64_t lda, double* linv, int* info, int global_off) {
+    static bool attr = false;
+    if (!attr) {
+        CUDA_CHECK(cudaFuncSetAttribute(potf2_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+        attr = true;
+    }
+    potf2_trtri_kernel<<<1, PF_THREADS, PF_SMEM, ctx->stream>>>(A, lda, linv, info, global_off);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// =============================================================================================
+// blocked right-looking Cholesky driver (outer panel nb, inner 128-wide left-looking sweep)
+// =============================================================================================
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+void dense_factor_inplace(b200gp_dense* s, bool generate) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t np = s->np, ld = s->np;
+    int64_t NB = ctx->nb;
+    if (NB < TILE) NB = TILE;
+    NB = (NB / TILE) * TILE;
+    double* M = s->mat;
+
+    set_int_kernel<<<1, 1, 0, ctx->stream>>>(s->info_dev, INT_MAX);
+    ctx->launches++;
+
+    if (generate) {
+        // panel 0 (all rows, first NB columns) is the only part of K ever written by a stand-alone
+        // build; every other tile is generated inside the first trailing update's epilogue.
+        const int64_t kb0 = (NB < np) ? NB : np;
+        BuildArgs a{};
+        a.X1 = s->X_dev; a.X2 = s->X_dev; a.diag = s->diag_dev; a.out = M; a.ld = ld;
+        a.n1 = s->n; a.n2 = (s->n < kb0) ? s->n : kb0; a.rows_pad = np; a.cols_pad = kb0;
+        a.row_off = 0; a.col_off = 0; a.ndim = s->ndim; a.pad_identity = 1;
+        dim3 grid((unsigned)((kb0 + BUILD_COLS - 1) / BUILD_COLS), (unsigned)((np + BUILD_ROWS - 1) / BUILD_ROWS));
+        ProfTimer t(ctx, &ctx->prof.build_ms);
+        build_rect_kernel<<<grid, 256, 0, ctx->stream>>>(s->prog, a);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+        ctx->prof.build_bytes += 8.0 * (double)np * (double)kb0;
+    }
+
+    for (int64_t k0 = 0; k0 < np; k0 += NB) {
+        const int64_t kb = (NB < np - k0) ? NB : (np - k0);
+        {
+            ProfTimer t(ctx, &ctx->prof.panel_ms);
+            for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
+                const int64_t c0 = k0 + j0;
+                if (j0 > 0) {
+                    // column block c0 -= (already factored panel columns) x (rows c0.. of them)^T
+                    gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld,
+                            (int)((np - c0) / TILE), 1, (int)j0, -1.0, 1, 0);
+                }
+                potf2(ctx, M + c0 * ld + c0, ld, s->linv + (c0 / TILE) * TILE * TILE, s->info_dev, (int)c0);
+                if (c0 + TILE < np) {
+                    // rows below: X = A * inv(L_jj)^T, in place (one tile column, K = 128)
+                    gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld,
+                            s->linv + (c0 / TILE) * TILE * TILE, TILE, (int)((np - c0 - TILE) / TILE), 1, TILE,
+                            1.0, 0, 0);
+                }
+            }
+        }
+        const int64_t r0 = k0 + kb;
+        if (r0 < np) {
+            gemm::Args g{};
+            g.A = M + r0 * ld + k0; g.lda = ld;
+            g.B = M + r0 * ld + k0; g.ldb = ld;
+            g.C = M + r0 * ld + r0; g.ldc = ld;
+            g.tiles_m = g.tiles_n = (int)((np - r0) / TILE);
+            g.K = (int)kb; g.alpha = -1.0; g.lower = 1;
+            g.beta_mode = (generate && k0 == 0) ? 2 : 1;
+            g.X = s->X_dev; g.diag = s->diag_dev; g.ndim = s->ndim; g.n_valid = s->n;
+            g.row0 = r0; g.col0 = r0;
+            ProfTimer t(ctx, &ctx->prof.syrk_ms);
+            gemm::launch(ctx, (g.beta_mode == 2) ? s->prog : empty_prog(), g);
+            const double T = (double)g.tiles_m;
+            ctx->prof.syrk_flop += T * (T + 1.0) / 2.0 * 2.0 * TILE * TILE * (double)kb;
+            ctx->prof.syrk_launches++;
+        }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(&s->info, s->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (s->info == INT_MAX) s->info = 0;
+    if (s->info > s->n) s->info = 0;  // cannot happen (pad is identity), defensive
+}
+
+// =============================================================================================
+// reductions
+// =============================================================================================
+// out[0] = sum_{i<n} f(v[i*stride]) with f = log (mode 0) or square (mode 1); single block,
+// fixed-shape tree so the result is deterministic.
+__global__ void __launch_bounds__(1024) reduce_kernel(const double* v, int64_t stride, int64_t n, int mode, double* out) {
+    __shared__ double sh[1024];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        const double x = v[i * stride];
+        acc += (mode == 0) ? log(x) : x * x;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+static double reduce_to_host(b200gp_ctx* ctx, const double* v, int64_t stride, int64_t n, int mode) {
+    double* d = (double*)ctx->alloc(sizeof(double));
+    reduce_kernel<<<1, 1024, 0, ctx->stream>>>(v, stride, n, mode, d);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    double h = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(&h, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->release(d, sizeof(double));
+    return h;
+}
+
+double dense_logdet_half(b200gp_dense* s) { return reduce_to_host(s->ctx, s->mat, s->np + 1, s->n, 0); }
+double dense_sumsq_dev(b200gp_ctx* ctx, const double* x_dev, int64_t n) { return reduce_to_host(ctx, x_dev, 1, n, 1); }
+
+// =============================================================================================
+// K3: triangular solves with a vector right-hand side, one launch per 128-block.
+// forward  (L x = y): every CTA recomputes x_j = inv(L_jj) y_j, then updates its rows below.
+// backward (L^T x = y): x_j = inv(L_jj)^T y_j, then y[c] -= sum_r L[jr][c] x_j[r] for columns left.
+// =============================================================================================
+__global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ mat, int64_t ld,
+                                                      const double* __restrict__ linv_j, double* y, double* x,
+                                                      int j, int64_t np) {
+    __shared__ __align__(32) double ys[TILE];
+    __shared__ __align__(32) double xs[TILE];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < TILE) ys[tid] = y[(int64_t)j * TILE + tid];
+    __syncthreads();
+    for (int r = warp; r < TILE; r += 8) {
+        const double* row = linv_j + r * TILE;
+        double s = 0.0;
+        for (int c = lane; c <= r; c += 32) s += row[c] * ys[c];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) xs[r] = s;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < TILE) x[(int64_t)j * TILE + tid] = xs[tid];
+    const int64_t rbase = (int64_t)(j + 1) * TILE + (int64_t)blockIdx.x * 64 + warp * 8;
+    const double4 xv = *reinterpret_cast<const double4*>(xs + lane * 4);
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+        const int64_t r = rbase + rr;
+        if (r >= np) break;
+        const double4 lv = *reinterpret_cast<const double4*>(mat + r * ld + (int64_t)j * TILE + lane * 4);
+        double s = lv.x * xv.x + lv.y * xv.y + lv.z * xv.z + lv.w * xv.w;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[r] -= s;
+    }
+}
+
+__global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ mat, int64_t ld,
+                                                      const double* __restrict__ linv_j, double* y, double* x, int j) {
+    __shared__ double ys[TILE];
+    __shared__ double xs[TILE];
+    __shared__ double part[TILE];
+    const int tid = threadIdx.x;
+    if (tid < TILE) ys[tid] = y[(int64_t)j * TILE + tid];
+    __syncthreads();
+    {
+        // x[c] = sum_{r >= c} linv[r][c] y[r] ; two half-ranges of r per column
+        const int c = tid & (TILE - 1), half = tid >> 7;
+        double s = 0.0;
+        const int rbeg = half ? 64 : 0, rend = half ? TILE : 64;
+        for (int r = max(rbeg, c); r < rend; ++r) s += linv_j[r * TILE + c] * ys[r];
+        if (half) part[c] = s;
+        __syncthreads();
+        if (!half) xs[c] = s + part[c];
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < TILE) x[(int64_t)j * TILE + tid] = xs[tid];
+    const int64_t c = (int64_t)blockIdx.x * 256 + tid;
+    if (c < (int64_t)j * TILE) {
+        const double* base = mat + (int64_t)j * TILE * ld + c;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < TILE; r += 2) {
+            s0 += base[(int64_t)r * ld] * xs[r];
+            s1 += base[(int64_t)(r + 1) * ld] * xs[r + 1];
+        }
+        y[c] -= s0 + s1;
+    }
+}
+
+void dense_solve_vec_dev(b200gp_dense* s, double* y_dev, double* x_dev, bool transpose) {
+    b200gp_ctx* ctx = s->ctx;
+    const int nblk = (int)(s->np / TILE);
+    ProfTimer t(ctx, &ctx->prof.solve_ms);
+    if (!transpose) {
+        for (int j = 0; j < nblk; ++j) {
+            const int64_t rows_below = s->np - (int64_t)(j + 1) * TILE;
+            const unsigned grid = (unsigned)((rows_below + 63) / 64);
+            trsv_fwd_step<<<grid ? grid : 1, 256, 0, ctx->stream>>>(s->mat, s->np, s->linv + (int64_t)j * TILE * TILE,
+                                                                    y_dev, x_dev, j, s->np);
+            ctx->launches++;
+        }
+    } else {
+        for (int j = nblk - 1; j >= 0; --j) {
+            const unsigned grid = (unsigned)(((int64_t)j * TILE + 255) / 256);
+            trsv_bwd_step<<<grid ? grid : 1, 256, 0, ctx->stream>>>(s->mat, s->np, s->linv + (int64_t)j * TILE * TILE,
+                                                                    y_dev, x_dev, j);
+            ctx->launches++;
+        }
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// =============================================================================================
+// K4: out = L z  (direct.py:72-73), one warp per row
+// =============================================================================================
+__global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ mat, int64_t ld, int64_t n,
+                                                          const double* __restrict__ z, double* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+    if (i >= n) return;
+    const double* row = mat + i * ld;
+    double s = 0.0;
+    for (int64_t c = lane; c <= i; c += 32) s += row[c] * z[c];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[i] = s;
+}
+
+// small layout helpers -----------------------------------------------------------------------
+// dst (rows_dst x ld_dst) <- transpose of src (n x m, row-major), zero padded
+__global__ void transpose_pad_kernel(const double* src, int64_t n, int64_t m, double* dst, int64_t rows_dst, int64_t ld_dst) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows_dst * ld_dst) return;
+    const int64_t r = idx / ld_dst, c = idx % ld_dst;  // dst[r][c] = src[c][r]
+    dst[idx] = (r < m && c < n) ? src[c * m + r] : 0.0;
+}
+__global__ void transpose_unpad_kernel(const double* src, int64_t ld_src, double* dst, int64_t n, int64_t m) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * m) return;
+    const int64_t i = idx / m, r = idx % m;  // dst[i][r] = src[r][i]
+    dst[idx] = src[r * ld_src + i];
+}
+__global__ void copy_pad_kernel(const double* src, int64_t n, double* dst, int64_t np) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) dst[i] = (i < n) ? src[i] : 0.0;
+}
+// load an n x n host-layout matrix into the padded np x np buffer with an identity pad
+__global__ void pad_cov_kernel(const double* src, int64_t n, double* dst, int64_t np) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= np * np) return;
+    const int64_t r = idx / np, c = idx % np;
+    dst[idx] = (r < n && c < n) ? src[r * n + c] : ((r == c) ? 1.0 : 0.0);
+}
+__global__ void extract_lower_kernel(const double* src, int64_t ld, double* dst, int64_t n) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int64_t r = idx / n, c = idx % n;
+    dst[idx] = (c <= r) ? src[r * ld + c] : 0.0;
+}
+__global__ void extract_rect_kernel(const double* src, int64_t ld, double* dst, int64_t n, int64_t m) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * m) return;
+    dst[idx] = src[(idx / m) * ld + (idx % m)];
+}
+
+static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// =============================================================================================
+// object lifecycle
+// =============================================================================================
+static b200gp_dense* dense_alloc(b200gp_ctx* ctx, int64_t n) {
+    if (n <= 0) throw GpError("dense: n must be positive");
+    b200gp_dense* s = new b200gp_dense();
+    s->ctx = ctx;
+    s->n = n;
+    s->np = ((n + TILE - 1) / TILE) * TILE;
+    try {
+        s->mat = (double*)ctx->alloc((size_t)s->np * s->np * sizeof(double));
+        s->linv = (double*)ctx->alloc((size_t)(s->np / TILE) * TILE * TILE * sizeof(double));
+        s->info_dev = (int*)ctx->alloc(sizeof(int));
+    } catch (...) {
+        dense_destroy(s);
+        throw;
+    }
+    return s;
+}
+
+void dense_destroy(b200gp_dense* s) {
+    if (!s) return;
+    b200gp_ctx* ctx = s->ctx;
+    if (s->mat) ctx->release(s->mat, (size_t)s->np * s->np * sizeof(double));
+    if (s->linv) ctx->release(s->linv, (size_t)(s->np / TILE) * TILE * TILE * sizeof(double));
+    if (s->info_dev) ctx->release(s->info_dev, sizeof(int));
+    if (s->owns_inputs) {
+        if (s->X_dev) ctx->release(s->X_dev, (size_t)s->n * s->ndim * sizeof(double));
+        if (s->diag_dev) ctx->release(s->diag_dev, (size_t)s->n * sizeof(double));
+    }
+    delete s;
+}
+
+b200gp_dense* dense_factor_from_prog(b200gp_ctx* ctx, const KProg& prog, const double* X_dev, int64_t n,
+                                     int ndim, const double* diag_dev, bool copy_inputs) {
+    if (ndim < 1 || ndim > MAX_NDIM) throw GpError("dense: ndim must be in [1, 16]");
+    b200gp_dense* s = dense_alloc(ctx, n);
+    try {
+        s->has_prog = true;
+        s->prog = prog;
+        s->ndim = ndim;
+        if (copy_inputs) {
+            s->owns_inputs = true;
+            s->X_dev = (double*)ctx->alloc((size_t)n * ndim * sizeof(double));
+            s->diag_dev = (double*)ctx->alloc((size_t)n * sizeof(double));
+            CUDA_CHECK(cudaMemcpyAsync(s->X_dev, X_dev, (size_t)n * ndim * sizeof(double), cudaMemcpyDefault, ctx->stream));
+            CUDA_CHECK(cudaMemcpyAsync(s->diag_dev, diag_dev, (size_t)n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        } else {
+            s->X_dev = const_cast<double*>(X_dev);
+            s->diag_dev = const_cast<double*>(diag_dev);
+        }
+        dense_factor_inplace(s, true);
+    } catch (...) {
+        dense_destroy(s);
+        throw;
+    }
+    return s;
+}
+
+// =============================================================================================
+// C-ABI: dense
+// =============================================================================================
+extern "C" {
+
+int b200gp_kernel_matrix(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X1, int64_t n1,
+                         const double* X2, int64_t n2, int ndim, double* out) {
+    API_BEGIN(ctx)
+    if (ndim < 1 || ndim > MAX_NDIM) throw GpError("kernel_matrix: ndim must be in [1, 16]");
+    if (n1 <= 0 || n2 <= 0) throw GpError("kernel_matrix: empty input");
+    KProg P = parse_prog(prog, n_instr);
+    double* x1 = (double*)_ctx->alloc((size_t)n1 * ndim * 8);
+    double* x2 = (double*)_ctx->alloc((size_t)n2 * ndim * 8);
+    double* o = (double*)_ctx->alloc((size_t)n1 * n2 * 8);
+    CUDA_CHECK(cudaMemcpyAsync(x1, X1, (size_t)n1 * ndim * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(x2, X2, (size_t)n2 * ndim * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    dense_build_rect(_ctx, P, x1, n1, x2, n2, ndim, nullptr, o, n2, n1, n2);
+    CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n1 * n2 * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(x1, (size_t)n1 * ndim * 8);
+    _ctx->release(x2, (size_t)n2 * ndim * 8);
+    _ctx->release(o, (size_t)n1 * n2 * 8);
+    API_END
+}
+
+int b200gp_kernel_diag(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
+                       double* out) {
+    API_BEGIN(ctx)
+    (void)X; (void)ndim;  // stationary kernels: k(x, x) does not depend on x
+    if (n <= 0) throw GpError("kernel_diag: empty input");
+    KProg P = parse_prog(prog, n_instr);
+    double* o = (double*)_ctx->alloc((size_t)n * 8);
+    build_diag_kernel<<<nblocks(n, 256), 256, 0, _ctx->stream>>>(P, n, o);
+    CUDA_CHECK(cudaGetLastError());
+    _ctx->launches++;
+    CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(o, (size_t)n * 8);
+    API_END
+}
+
+int b200gp_kernel_matvec(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X1, int64_t n1,
+                         const double* X2, int64_t n2, int ndim, const double* y, double* out) {
+    API_BEGIN(ctx)
+    if (ndim < 1 || ndim > MAX_NDIM) throw GpError("kernel_matvec: ndim must be in [1, 16]");
+    if (n1 <= 0 || n2 <= 0) throw GpError("kernel_matvec: empty input");
+    KProg P = parse_prog(prog, n_instr);
+    double* x1 = (double*)_ctx->alloc((size_t)n1 * ndim * 8);
+    double* x2 = (double*)_ctx->alloc((size_t)n2 * ndim * 8);
+    double* yd = (double*)_ctx->alloc((size_t)n2 * 8);
+    double* o = (double*)_ctx->alloc((size_t)n1 * 8);
+    CUDA_CHECK(cudaMemcpyAsync(x1, X1, (size_t)n1 * ndim * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(x2, X2, (size_t)n2 * ndim * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(yd, y, (size_t)n2 * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    kernel_matvec_kernel<<<nblocks(n1, 8), 256, 0, _ctx->stream>>>(P, x1, n1, x2, n2, ndim, yd, o);
+    CUDA_CHECK(cudaGetLastError());
+    _ctx->launches++;
+    CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n1 * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(x1, (size_t)n1 * ndim * 8);
+    _ctx->release(x2, (size_t)n2 * ndim * 8);
+    _ctx->release(yd, (size_t)n2 * 8);
+    _ctx->release(o, (size_t)n1 * 8);
+    API_END
+}
+
+int b200gp_dense_create(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
+                        const double* diag, b200gp_dense** out, int* info) {
+    API_BEGIN(ctx)
+    KProg P = parse_prog(prog, n_instr);
+    b200gp_dense* s = dense_factor_from_prog(_ctx, P, X, n, ndim, diag, true);
+    *out = s;
+    if (info) *info = s->info;
+    API_END
+}
+
+int b200gp_dense_create_dev(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X_dev, int64_t n,
+                            int ndim, const double* diag_dev, b200gp_dense** out, int* info) {
+    return b200gp_dense_create(ctx, prog, n_instr, X_dev, n, ndim, diag_dev, out, info);  // cudaMemcpyDefault
+}
+
+int b200gp_dense_create_from_cov(b200gp_ctx* ctx, const double* cov, int64_t n, b200gp_dense** out, int* info) {
+    API_BEGIN(ctx)
+    b200gp_dense* s = dense_alloc(_ctx, n);
+    try {
+        double* tmp = (double*)_ctx->alloc((size_t)n * n * 8);
+        CUDA_CHECK(cudaMemcpyAsync(tmp, cov, (size_t)n * n * 8, cudaMemcpyDefault, _ctx->stream));
+        pad_cov_kernel<<<nblocks(s->np * s->np, 256), 256, 0, _ctx->stream>>>(tmp, n, s->mat, s->np);
+        CUDA_CHECK(cudaGetLastError());
+        _ctx->launches++;
+        dense_factor_inplace(s, false);
+        _ctx->release(tmp, (size_t)n * n * 8);
+    } catch (...) {
+        dense_destroy(s);
+        throw;
+    }
+    *out = s;
+    if (info) *info = s->info;
+    API_END
+}
+
+int b200gp_dense_free(b200gp_dense* s) {
+    if (!s) return 0;
+    API_BEGIN(s->ctx)
+    dense_destroy(s);
+    API_END
+}
+
+int b200gp_dense_logdet_half(b200gp_dense* s, double* out) {
+    API_BEGIN(s->ctx)
+    *out = dense_logdet_half(s);
+    API_END
+}
+
+int b200gp_dense_solve_triangular(b200gp_dense* s, double* Y, int64_t nrhs, int transpose) {
+    API_BEGIN(s->ctx)
+    if (nrhs <= 0) throw GpError("solve_triangular: nrhs must be positive");
+    const int64_t n = s->n, np = s->np;
+    double* yh = (double*)_ctx->alloc((size_t)n * nrhs * 8);
+    double* yt = (double*)_ctx->alloc((size_t)nrhs * np * 8);
+    double* xt = (double*)_ctx->alloc((size_t)nrhs * np * 8);
+    CUDA_CHECK(cudaMemcpyAsync(yh, Y, (size_t)n * nrhs * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    transpose_pad_kernel<<<nblocks(nrhs * np, 256), 256, 0, _ctx->stream>>>(yh, n, nrhs, yt, nrhs, np);
+    _ctx->launches++;
+    for (int64_t r = 0; r < nrhs; ++r) dense_solve_vec_dev(s, yt + r * np, xt + r * np, transpose != 0);
+    transpose_unpad_kernel<<<nblocks(n * nrhs, 256), 256, 0, _ctx->stream>>>(xt, np, yh, n, nrhs);
+    _ctx->launches++;
+    CUDA_CHECK(cudaMemcpyAsync(Y, yh, (size_t)n * nrhs * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(yh, (size_t)n * nrhs * 8);
+    _ctx->release(yt, (size_t)nrhs * np * 8);
+    _ctx->release(xt, (size_t)nrhs * np * 8);
+    API_END
+}
+
+int b200gp_dense_dot_triangular(b200gp_dense* s, double* Y, int64_t nrhs) {
+    API_BEGIN(s->ctx)
+    if (nrhs <= 0) throw GpError("dot_triangular: nrhs must be positive");
+    const int64_t n = s->n, np = s->np;
+    double* yh = (double*)_ctx->alloc((size_t)n * nrhs * 8);
+    double* yt = (double*)_ctx->alloc((size_t)nrhs * np * 8);
+    double* xt = (double*)_ctx->alloc((size_t)nrhs * np * 8);
+    CUDA_CHECK(cudaMemcpyAsync(yh, Y, (size_t)n * nrhs * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    transpose_pad_kernel<<<nblocks(nrhs * np, 256), 256, 0, _ctx->stream>>>(yh, n, nrhs, yt, nrhs, np);
+    _ctx->launches++;
+    for (int64_t r = 0; r < nrhs; ++r) {
+        trmv_lower_kernel<<<nblocks(np, 8), 256, 0, _ctx->stream>>>(s->mat, np, np, yt + r * np, xt + r * np);
+        _ctx->launches++;
+    }
+    transpose_unpad_kernel<<<nblocks(n * nrhs, 256), 256, 0, _ctx->stream>>>(xt, np, yh, n, nrhs);
+    _ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(Y, yh, (size_t)n * nrhs * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(yh, (size_t)n * nrhs * 8);
+    _ctx->release(yt, (size_t)nrhs * np * 8);
+    _ctx->release(xt, (size_t)nrhs * np * 8);
+    API_END
+}
+
+// condition (direct.py:75-95), all on the tensor pipe:  with rows = test points,
+//   At (mp x np) = Ks^T = k(X*, X);  forward substitution block by block on At (NT GEMMs);
+//   out = Kss + diag* - At At^T  (NT GEMM with K = np, C generated in the epilogue).
+int b200gp_dense_condition(b200gp_dense* s, const double* prog, int n_instr, const double* Xtest, int64_t m,
+                           const double* diag_test, double* out) {
+    API_BEGIN(s->ctx)
+    if (!s->has_prog) throw GpError("condition: solver was built from a precomputed covariance (no coordinates)");
+    KProg P = parse_prog(prog, n_instr);
+    const int64_t n = s->n, np = s->np;
+    const int nd = s->ndim;
+    double* xt_dev;
+    bool own_xt = false;
+    if (Xtest == nullptr) {
+        m = n;
+        xt_dev = s->X_dev;
+    } else {
+        if (m <= 0) throw GpError("condition: empty X_test");
+        xt_dev = (double*)_ctx->alloc((size_t)m * nd * 8);
+        own_xt = true;
+        CUDA_CHECK(cudaMemcpyAsync(xt_dev, Xtest, (size_t)m * nd * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    }
+    const int64_t mp = ((m + TILE - 1) / TILE) * TILE;
+    double* dt = (double*)_ctx->alloc((size_t)mp * 8);
+    CUDA_CHECK(cudaMemsetAsync(dt, 0, (size_t)mp * 8, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dt, diag_test, (size_t)m * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    double* At = (double*)_ctx->alloc((size_t)mp * np * 8);
+    // Ks^T, zero padded
+    dense_build_rect(_ctx, P, xt_dev, m, s->X_dev, n, nd, nullptr, At, np, mp, np);
+    const int nblk = (int)(np / TILE), tm = (int)(mp / TILE);
+    {
+        ProfTimer t(_ctx, &_ctx->prof.solve_ms);
+        for (int j = 0; j < nblk; ++j) {
+            double* Aj = At + (int64_t)j * TILE;
+            gemm_nt(_ctx, Aj, np, Aj, np, s->linv + (int64_t)j * TILE * TILE, TILE, tm, 1, TILE, 1.0, 0, 0);
+            if (j + 1 < nblk)
+                gemm_nt(_ctx, Aj + TILE, np, Aj, np, s->mat + (int64_t)(j + 1) * TILE * np + (int64_t)j * TILE, np,
+                        tm, nblk - j - 1, TILE, -1.0, 1, 0);
+        }
+    }
+    double* C = (double*)_ctx->alloc((size_t)mp * mp * 8);
+    {
+        gemm::Args g{};
+        g.A = At; g.lda = np; g.B = At; g.ldb = np; g.C = C; g.ldc = mp;
+        g.tiles_m = g.tiles_n = tm; g.K = (int)np; g.alpha = -1.0; g.beta_mode = 2; g.lower = 0;
+        g.X = xt_dev; g.diag = dt; g.ndim = nd; g.n_valid = m; g.row0 = 0; g.col0 = 0;
+        gemm::launch(_ctx, P, g);
+    }
+    double* o = (double*)_ctx->alloc((size_t)m * m * 8);
+    extract_rect_kernel<<<nblocks(m * m, 256), 256, 0, _ctx->stream>>>(C, mp, o, m, m);
+    _ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)m * m * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(o, (size_t)m * m * 8);
+    _ctx->release(C, (size_t)mp * mp * 8);
+    _ctx->release(At, (size_t)mp * np * 8);
+    _ctx->release(dt, (size_t)mp * 8);
+    if (own_xt) _ctx->release(xt_dev, (size_t)m * nd * 8);
+    API_END
+}
+
+int b200gp_dense_covariance(b200gp_dense* s, double* out) {
+    API_BEGIN(s->ctx)
+    if (!s->has_prog) throw GpError("covariance: solver was built from a precomputed covariance; the host keeps it");
+    const int64_t n = s->n;
+    double* o = (double*)_ctx->alloc((size_t)n * n * 8);
+    BuildArgs a{};
+    a.X1 = s->X_dev; a.X2 = s->X_dev; a.diag = s->diag_dev; a.out = o; a.ld = n;
+    a.n1 = n; a.n2 = n; a.rows_pad = n; a.cols_pad = n; a.ndim = s->ndim; a.pad_identity = 0;
+    dim3 grid((unsigned)((n + BUILD_COLS - 1) / BUILD_COLS), (unsigned)((n + BUILD_ROWS - 1) / BUILD_ROWS));
+    {
+        ProfTimer t(_ctx, &_ctx->prof.build_ms);
+        build_rect_kernel<<<grid, 256, 0, _ctx->stream>>>(s->prog, a);
+        CUDA_CHECK(cudaGetLastError());
+        _ctx->launches++;
+        _ctx->prof.build_bytes += 8.0 * (double)n * (double)n;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n * n * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(o, (size_t)n * n * 8);
+    API_END
+}
+
+int b200gp_dense_get_factor(b200gp_dense* s, double* out) {
+    API_BEGIN(s->ctx)
+    const int64_t n = s->n;
+    double* o = (double*)_ctx->alloc((size_t)n * n * 8);
+    extract_lower_kernel<<<nblocks(n * n, 256), 256, 0, _ctx->stream>>>(s->mat, s->np, o, n);
+    CUDA_CHECK(cudaGetLastError());
+    _ctx->launches++;
+    CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n * n * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(o, (size_t)n * n * 8);
+    API_END
+}
+
+static double dense_logp_impl(b200gp_ctx* ctx, const KProg& P, const double* X, int64_t n, int ndim,
+                              const double* diag, const double* resid) {
+    // X / diag / resid may be host or device pointers (cudaMemcpyDefault resolves them)
+    b200gp_dense* s = dense_factor_from_prog(ctx, P, X, n, ndim, diag, true);
+    double logp;
+    try {
+        const int64_t np = s->np;
+        double* y = (double*)ctx->alloc((size_t)np * 8);
+        double* x = (double*)ctx->alloc((size_t)np * 8);
+        CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)np * 8, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(y, resid, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
+        dense_solve_vec_dev(s, y, x, false);
+        const double ss = dense_sumsq_dev(ctx, x, n);
+        const double ld = dense_logdet_half(s);
+        logp = -0.5 * ss - (ld + 0.5 * (double)n * log(2.0 * M_PI));   // gp.py:313-316, direct.py:61-64
+        if (s->info != 0 || !isfinite(logp)) logp = -INFINITY;
+        ctx->release(y, (size_t)np * 8);
+        ctx->release(x, (size_t)np * 8);
+    } catch (...) {
+        dense_destroy(s);
+        throw;
+    }
+    dense_destroy(s);
+    return logp;
+}
+
+int b200gp_dense_log_probability(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n,
+                                 int ndim, const double* diag, const double* resid, double* logp) {
+    API_BEGIN(ctx)
+    KProg P = parse_prog(prog, n_instr);
+    *logp = dense_logp_impl(_ctx, P, X, n, ndim, diag, resid);
+    API_END
+}
+
+int b200gp_dense_log_probability_dev(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X_dev,
+                                     int64_t n, int ndim, const double* diag_dev, const double* resid_dev,
+                                     double* logp) {
+    return b200gp_dense_log_probability(ctx, prog, n_instr, X_dev, n, ndim, diag_dev, resid_dev, logp);
+}
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+"""``GaussianProcess`` re-declared without JAX (reference: src/tinygp/gp.py:30-393).
+
+Same constructor and method signatures, so ``solver=`` drops in; all linear algebra goes through
+the six ``Solver`` methods exactly where the reference calls them (gp.py:120,124,201,310,315,320,334).
+"""
+
+from __future__ import annotations
+
+__all__ = ["GaussianProcess", "ConditionResult"]
+
+from typing import Any, NamedTuple
+
+import numpy as np
+
+from tinygp_b200 import kernels, means
+from tinygp_b200.kernels.quasisep import Quasisep
+from tinygp_b200.noise import Diagonal, Noise
+from tinygp_b200.solvers import DirectSolver, QuasisepSolver
+
+
+class GaussianProcess:
+    def __init__(self, kernel, X, *, diag=None, noise: Noise | None = None, mean=None, solver: Any | None = None,
+                 mean_value=None, covariance_value: Any | None = None, **solver_kwargs: Any):
+        self.kernel = kernel
+        self.X = X
+        if isinstance(mean, means.MeanBase):  # gp.py:81-86
+            self.mean_function = mean
+        elif mean is None:
+            self.mean_function = means.Mean(0.0)
+        else:
+            self.mean_function = means.Mean(mean)
+        if mean_value is None:
+            mean_value = self.mean_function.vmap(self.X)  # gp.py:87-88
+        mean_value = np.asarray(mean_value, dtype=np.float64)
+        if mean_value.ndim != 1:
+            raise ValueError(f"Invalid mean shape: expected ndim = 1, got ndim={mean_value.ndim}")
+        self.num_data = mean_value.shape[0]
+        self.dtype = mean_value.dtype
+        self.mean = mean_value
+        if noise is None:  # gp.py:96-99
+            diag = _default_diag(self.mean) if diag is None else diag
+            noise = Diagonal(diag=np.broadcast_to(np.asarray(diag, dtype=np.float64), self.mean.shape).copy())
+        self.noise = noise
+        if solver is None:  # gp.py:101-105
+            solver = QuasisepSolver if isinstance(kernel, Quasisep) else DirectSolver
+        self.solver = solver(kernel, self.X, self.noise, covariance=covariance_value, **solver_kwargs)
+
+    @property
+    def loc(self):
+        return self.mean
+
+    @property
+    def variance(self):
+        return self.solver.variance()
+
+    @property
+    def covariance(self):
+        return self.solver.covariance()
+
+    def log_probability(self, y):  # gp.py:126-138
+        return self._compute_log_prob(self._get_alpha(y))
+
+    def condition(self, y, X_test=None, *, diag=None, noise: Noise | None = None, include_mean: bool = True,
+                  kernel=None) -> "ConditionResult":
+        """gp.py:140-223"""
+        if X_test is not None:  # gp.py:180-191
+            a, b = np.asarray(self.X), np.asarray(X_test)
+            if a.ndim != b.ndim or a.shape[1:] != b.shape[1:]:
+                raise ValueError(
+                    "`X_test` must have the same tree structure as the input `X`, "
+                    "and all but the leading dimension must have matching sizes"
+                )
+        alpha, log_prob, mean_value = self._condition(y, X_test, include_mean, kernel)
+        if kernel is None:
+            kernel = self.kernel
+        if noise is None:
+            diag = _default_diag(mean_value) if diag is None else diag
+            noise = Diagonal(diag=np.broadcast_to(np.asarray(diag, dtype=np.float64), mean_value.shape).copy())
+        covariance_value = self.solver.condition(kernel, X_test, noise)  # gp.py:201
+        if X_test is None:
+            X_test = self.X
+        gp = GaussianProcess(  # gp.py:208-221: the conditional GP factors the M x M covariance again
+            kernels.Conditioned(self.X, self.solver, kernel),
+            X_test,
+            noise=noise,
+            mean=means.Conditioned(self.X, alpha, kernel, include_mean=include_mean,
+                                   mean_function=self.mean_function),
+            mean_value=mean_value,
+            covariance_value=covariance_value,
+            solver=DirectSolver,
+        )
+        return ConditionResult(log_prob, gp)
+
+    def predict(self, y, X_test=None, *, kernel=None, include_mean: bool = True, return_var: bool = False,
+                return_cov: bool = False):
+        """gp.py:225-271"""
+        _, cond = self.condition(y, X_test, kernel=kernel, include_mean=include_mean)
+        if return_var:
+            return cond.loc, cond.variance
+        if return_cov:
+            return cond.loc, cond.covariance
+        return cond.loc
+
+    def sample(self, key, shape=None):
+        """gp.py:273-311.  ``key`` seeds numpy's Generator (JAX's threefry stream is not reproducible
+        without JAX -- sample-value parity is statistical only, as in tests/test_gp.py:24-38)."""
+        rng = key if isinstance(key, np.random.Generator) else np.random.default_rng(key)
+        shape = (self.num_data,) if shape is None else (self.num_data,) + tuple(shape)
+        normal_samples = rng.standard_normal(shape)
+        return self.mean + np.moveaxis(self.solver.dot_triangular(normal_samples), 0, -1)
+
+    # -- internals (gp.py:313-361) -------------------------------------------------------------
+    def _compute_log_prob(self, alpha):
+        with np.errstate(all="ignore"):
+            loglike = -0.5 * np.sum(np.square(alpha)) - self.solver.normalization()
+        return loglike if np.isfinite(loglike) else -np.inf
+
+    def _get_alpha(self, y):
+        return self.solver.solve_triangular(np.asarray(y, dtype=np.float64) - self.loc)
+
+    def _condition(self, y, X_test, include_mean, kernel=None):
+        y = np.asarray(y, dtype=np.float64)
+        alpha = self._get_alpha(y)
+        log_prob = self._compute_log_prob(alpha)
+        alpha = self.solver.solve_triangular(alpha, transpose=True)  # gp.py:334
+        if X_test is None:
+            if kernel is None:
+                delta = self.noise @ alpha  # gp.py:342-346
+                mean_value = y - delta
+                if not include_mean:
+                    mean_value = mean_value - self.loc
+            else:
+                mean_value = kernel.matmul(self.X, y=alpha)
+                if include_mean:
+                    mean_value = mean_value + self.loc
+        else:
+            if kernel is None:
+                kernel = self.kernel
+            mean_value = kernel.matmul(X_test, self.X, alpha)  # gp.py:357
+            if include_mean:
+                mean_value = mean_value + self.mean_function.vmap(X_test)
+        return alpha, log_prob, mean_value
+
+
+class ConditionResult(NamedTuple):
+    """gp.py:364-385"""
+    log_probability: Any
+    gp: GaussianProcess
+
+
+def _default_diag(reference):  # gp.py:388-393
+    return np.sqrt(np.finfo(np.asarray(reference).dtype).eps)

@@ -1,0 +1,118 @@
+"""B200 DirectSolver: same six-method contract as src/tinygp/solvers/direct.py:17-95, every method
+bound to a C-ABI entry point of libb200gp.so.  The factor lives in HBM for the object's lifetime."""
+
+from __future__ import annotations
+
+__all__ = ["DirectSolver"]
+
+from ctypes import byref, c_double, c_int, c_void_p
+from typing import Any
+
+import numpy as np
+
+from tinygp_b200 import _cabi
+from tinygp_b200.kernels.base import Kernel, _as_coords
+from tinygp_b200.solvers.solver import Solver
+
+
+class DirectSolver(Solver):
+    """Dense build fused into a blocked Cholesky on the fp64 tensor pipe (direct.py:30-53)."""
+
+    def __init__(self, kernel: Kernel, X, noise, *, covariance: Any | None = None):
+        self._ctx = _cabi.get_context()
+        self._h = c_void_p()
+        self.X = X
+        self.kernel = kernel
+        self.noise = noise
+        info = c_int(0)
+        lib = self._ctx.lib
+        if covariance is None:
+            x, _ = _as_coords(X)
+            diag = _cabi.f64(noise.diagonal())
+            if diag.shape != (x.shape[0],):
+                raise ValueError("noise diagonal must have shape (N,)")
+            prog = kernel.program()
+            self._n = x.shape[0]
+            self.variance_value = kernel(X) + diag                              # direct.py:49
+            self._cov = None
+            self._ctx.check(lib.b200gp_dense_create(self._ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(x),
+                                                    x.shape[0], x.shape[1], _cabi.ptr(diag), byref(self._h),
+                                                    byref(info)))
+        else:
+            cov = _cabi.f64(covariance)
+            if cov.ndim != 2 or cov.shape[0] != cov.shape[1]:
+                raise ValueError("covariance must be a square matrix")
+            self._n = cov.shape[0]
+            self._cov = cov
+            # kernel(X) + noise.diagonal() of the conditioned kernel == diag(covariance) (direct.py:49-52)
+            self.variance_value = np.diag(cov).copy()
+            self._ctx.check(lib.b200gp_dense_create_from_cov(self._ctx.handle, _cabi.ptr(cov), cov.shape[0],
+                                                             byref(self._h), byref(info)))
+        self.info = info.value
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._ctx.lib.b200gp_dense_free(h)
+            except Exception:
+                pass
+            self._h = c_void_p()
+
+    # -- the Solver contract --------------------------------------------------------------
+    def variance(self):
+        return self.variance_value
+
+    def covariance(self):  # direct.py:58-59, regenerated lazily by the build kernel
+        if self._cov is None:
+            out = np.empty((self._n, self._n))
+            self._ctx.check(self._ctx.lib.b200gp_dense_covariance(self._h, _cabi.ptr(out)))
+            self._cov = out
+        return self._cov
+
+    @property
+    def scale_tril(self):
+        out = np.empty((self._n, self._n))
+        self._ctx.check(self._ctx.lib.b200gp_dense_get_factor(self._h, _cabi.ptr(out)))
+        return out
+
+    def normalization(self):  # direct.py:61-64
+        ld = c_double()
+        self._ctx.check(self._ctx.lib.b200gp_dense_logdet_half(self._h, byref(ld)))
+        if self.info != 0:
+            return np.nan
+        return ld.value + 0.5 * self._n * np.log(2 * np.pi)
+
+    def solve_triangular(self, y, *, transpose: bool = False):  # direct.py:66-70
+        y = np.asarray(y, dtype=np.float64)
+        if y.shape[0] != self._n:
+            raise ValueError("dimension mismatch")
+        buf = np.array(y.reshape(self._n, -1), dtype=np.float64, order="C", copy=True)
+        self._ctx.check(self._ctx.lib.b200gp_dense_solve_triangular(self._h, _cabi.ptr(buf), buf.shape[1],
+                                                                    int(bool(transpose))))
+        return buf.reshape(y.shape)
+
+    def dot_triangular(self, y):  # direct.py:72-73
+        y = np.asarray(y, dtype=np.float64)
+        if y.shape[0] != self._n:
+            raise ValueError("dimension mismatch")
+        buf = np.array(y.reshape(self._n, -1), dtype=np.float64, order="C", copy=True)
+        self._ctx.check(self._ctx.lib.b200gp_dense_dot_triangular(self._h, _cabi.ptr(buf), buf.shape[1]))
+        return buf.reshape(y.shape)
+
+    def condition(self, kernel: Kernel, X_test, noise) -> Any:  # direct.py:75-95
+        prog = kernel.program()
+        diag = _cabi.f64(noise.diagonal())
+        if X_test is None:
+            m = self._n
+            xt_ptr = None
+        else:
+            xt, _ = _as_coords(X_test)
+            m = xt.shape[0]
+            xt_ptr = _cabi.ptr(xt)
+        if diag.shape != (m,):
+            raise ValueError("noise diagonal must match the number of test points")
+        out = np.empty((m, m))
+        self._ctx.check(self._ctx.lib.b200gp_dense_condition(self._h, _cabi.ptr(prog), prog.shape[0], xt_ptr, m,
+                                                             _cabi.ptr(diag), _cabi.ptr(out)))
+        return out

@@ -1,0 +1,119 @@
+"""B200 QuasisepSolver: the contract of src/tinygp/solvers/quasisep/solver.py:19-139 over the chunked
+scan kernels of libb200gp.so.  The factor (c, w) lives in HBM for the object's lifetime."""
+
+from __future__ import annotations
+
+__all__ = ["QuasisepSolver"]
+
+from ctypes import byref, c_double, c_int, c_void_p
+from typing import Any
+
+import numpy as np
+
+from tinygp_b200 import _cabi
+from tinygp_b200.kernels.quasisep import Quasisep
+from tinygp_b200.solvers.solver import Solver
+
+_UNSORTED_MSG = "Input coordinates must be sorted in order to use the QuasisepSolver"  # solver.py:142-146
+
+
+class QuasisepSolver(Solver):
+    def __init__(self, kernel, X, noise, *, covariance: Any | None = None, assume_sorted: bool = False,
+                 parallel: bool = False):
+        """``parallel`` is accepted for API compatibility (solver.py:33,60-64); the device scans are
+        always the chunked parallel form, and give the sequential recursion's values."""
+        if covariance is not None:
+            raise NotImplementedError("QuasisepSolver(covariance=SymmQSM) is unsupported by the B200 backend")
+        if not isinstance(kernel, Quasisep):
+            raise ValueError("QuasisepSolver requires a tinygp_b200.kernels.quasisep.Quasisep kernel")
+        self._ctx = _cabi.get_context()
+        self._h = c_void_p()
+        self.kernel, self.noise, self.parallel = kernel, noise, parallel
+        t = _cabi.f64(kernel.coord_to_sortable(X))
+        if t.ndim != 1:
+            raise ValueError("QuasisepSolver takes 1-D sortable coordinates")
+        self.X = t
+        self._n = t.shape[0]
+        diag = _cabi.f64(noise.diagonal())
+        if diag.shape != t.shape:
+            raise ValueError("noise diagonal must have shape (N,)")
+        comps = kernel.component_array()
+        unsorted, info = c_int(0), c_int(0)
+        lib = self._ctx.lib
+        self._ctx.check(lib.b200gp_qs_create(self._ctx.handle, _cabi.ptr(comps), comps.shape[0], _cabi.ptr(t),
+                                             self._n, _cabi.ptr(diag), int(bool(assume_sorted)), byref(self._h),
+                                             byref(unsorted), byref(info)))
+        if unsorted.value:
+            raise ValueError(_UNSORTED_MSG)
+        self.info = info.value
+        J = c_int(0)
+        self._ctx.check(lib.b200gp_qs_state_dim(self._h, byref(J)))
+        self._J = J.value
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._ctx.lib.b200gp_qs_free(h)
+            except Exception:
+                pass
+            self._h = c_void_p()
+
+    # -- Solver contract ------------------------------------------------------------------
+    def variance(self):  # solver.py:84-85
+        out = np.empty(self._n)
+        self._ctx.check(self._ctx.lib.b200gp_qs_variance(self._h, _cabi.ptr(out)))
+        return out
+
+    def covariance(self):  # solver.py:87-88: to_dense() = matmul with the identity (core.py:84-90)
+        eye = np.eye(self._n)
+        self._ctx.check(self._ctx.lib.b200gp_qs_matmul(self._h, _cabi.ptr(eye), self._n))
+        return eye
+
+    def normalization(self):  # solver.py:90-93
+        ld = c_double()
+        self._ctx.check(self._ctx.lib.b200gp_qs_logdet_half(self._h, byref(ld)))
+        return ld.value + 0.5 * self._n * np.log(2 * np.pi)
+
+    def _apply(self, fn, y, *extra):
+        y = np.asarray(y, dtype=np.float64)
+        if y.shape[0] != self._n:
+            raise ValueError("dimension mismatch")
+        buf = np.array(y.reshape(self._n, -1), dtype=np.float64, order="C", copy=True)  # core.py:35-44
+        self._ctx.check(fn(self._h, _cabi.ptr(buf), buf.shape[1], *extra))
+        return buf.reshape(y.shape)
+
+    def solve_triangular(self, y, *, transpose: bool = False):  # solver.py:95-99
+        return self._apply(self._ctx.lib.b200gp_qs_solve_triangular, y, int(bool(transpose)))
+
+    def dot_triangular(self, y):  # solver.py:101-102
+        return self._apply(self._ctx.lib.b200gp_qs_dot_triangular, y)
+
+    def matmul(self, y):
+        """covariance @ y without densifying (core.py:499-505)."""
+        return self._apply(self._ctx.lib.b200gp_qs_matmul, y)
+
+    def factor(self):
+        """(c, w) of the LowerTriQSM factor (core.py:524-539)."""
+        c, w = np.empty(self._n), np.empty((self._n, self._J))
+        self._ctx.check(self._ctx.lib.b200gp_qs_get_factor(self._h, _cabi.ptr(c), _cabi.ptr(w)))
+        return c, w
+
+    def generators(self):
+        """(d, p, q, a) of the SymmQSM incl. the noise diagonal (kernels/quasisep.py:102-116)."""
+        n, J = self._n, self._J
+        d, p, q, a = np.empty(n), np.empty((n, J)), np.empty((n, J)), np.empty((n, J, J))
+        self._ctx.check(self._ctx.lib.b200gp_qs_get_generators(self._h, _cabi.ptr(d), _cabi.ptr(p), _cabi.ptr(q),
+                                                               _cabi.ptr(a)))
+        return d, p, q, a
+
+    def condition(self, kernel, X_test, noise) -> Any:
+        """solver.py:104-139, dense branch (:131-139).  The QSM-valued branch (:124-129) needs qsm_mul /
+        inv / gram and is a 'next' row; predicting at the inputs returns the dense matrix instead."""
+        if X_test is None:
+            Kss = Ks = kernel(self.X, self.X)
+        else:
+            Kss = kernel(X_test, X_test)
+            Ks = kernel(self.X, X_test)
+        A = self.solve_triangular(Ks)
+        return Kss - A.T @ A

@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (contract: see the task statement / DESIGN.md section 6).
+
+Metric (BASELINE.json): GP log_probability/sec at N=65536, dense ExpSquared 3-D, fp64.
+A "step" is one full ``log_probability``: kernel-matrix build fused into the blocked Cholesky,
+forward triangular solve, log-determinant and |alpha|^2 reductions.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload dense|quasisep]
+
+* ``value``  : device-timed throughput with X / diag / y already resident in HBM.
+* ``e2e``    : the same metric through the public API ``GaussianProcess(kernel, X, diag=...).log_probability(y)``
+               with HOST numpy buffers (host->device copies and device->host reads inside the timed region).
+* ``roofline``: trailing-update DMMA kernel, algorithmic flop / summed CUDA-event time of its launches,
+               against the fp64 tensor (DMMA) peak measured by our own micro-benchmark on this GPU
+               (MEASURED_PEAKS.json carries only bf16/HBM peaks; fp64 has no entry there).
+* ``cpu_baseline`` / ``--impl reference``: the NumPy/SciPy oracle port (the reference needs JAX, which is not
+               installed here or on the box) on the host cores, on a bounded sample, extrapolated as stated.
+N > 1: one process per GPU; the dense path runs as independent replicas (one hyper-parameter point per
+rank, no data-path collective) -> "scaling": "weak".
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_DENSE = 65536
+NDIM = 3
+SEED = 49382
+
+
+def make_dense_problem(n, rank=0):
+    """X ~ U(0,20)^3 at N=65536 (same point density for other N), y = sin(x0) + 0.1 N(0,1),
+    1.0 * ExpSquared(scale=1.0), diag=0.1.  Ranks > 0 evaluate a neighbouring length scale."""
+    rng = np.random.default_rng(SEED)
+    side = 20.0 * (n / 65536.0) ** (1.0 / 3.0)
+    X = np.ascontiguousarray(rng.uniform(0.0, side, (n, NDIM)))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    diag = np.full(n, 0.1)
+    scale = 1.0 + 0.01 * rank
+    return X, y, diag, scale
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(np.min(sm)), "sm_max_mhz": float(np.max(mx)),
+                "power_w_median": float(np.median(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def oracle_dense_logp_seconds(n):
+    from oracle import tinygp_np as o
+    X, y, diag, scale = make_dense_problem(n)
+    t0 = time.perf_counter()
+    lp = o.GaussianProcess(o.Constant(1.0) * o.ExpSquared(scale), X, diag=diag).log_probability(y)
+    return time.perf_counter() - t0, lp
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def pick_sample_n(budget_s_per_step):
+    """Calibrate on N=4096 and pick the largest sample whose step fits the budget (time ~ N^3 + N^2 build)."""
+    t, _ = oracle_dense_logp_seconds(4096)
+    for n in (16384, 12288, 8192):
+        if t * (n / 4096.0) ** 3 <= budget_s_per_step:
+            return n
+    return 8192
+
+
+def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path: tinygp needs jax + equinox, neither of which is
+    installed here or on the GPU box (no network), so this is the NumPy/SciPy/LAPACK oracle port
+    (oracle/tinygp_np.py: same formulas, LAPACK dpotrf = what XLA:CPU calls), all host threads."""
+    if rank != 0:
+        return
+    np.random.seed(0)
+    total_budget = 150.0
+    n_s = pick_sample_n(total_budget / max(1, args.steps + args.warmup))
+    for _ in range(args.warmup):
+        oracle_dense_logp_seconds(n_s)
+    ts = []
+    for _ in range(args.steps):
+        t, lp = oracle_dense_logp_seconds(n_s)
+        ts.append(t)
+    t_step = float(np.sum(ts)) / max(1, len(ts))
+    scale_up = (N_DENSE / n_s) ** 3
+    value = 1.0 / (t_step * scale_up)
+    cores = cpu_threads()
+    sample = (f"N={n_s} of the same workload per step ({t_step:.2f} s measured), extrapolated x{scale_up:.0f} "
+              f"(N^3) to N={N_DENSE}")
+    line = {
+        "impl": "reference", "metric": "log_probability/sec", "value": value, "unit": "logp/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * scale_up * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"dense ExpSquared 3-D N={N_DENSE} log_probability (build + Cholesky + solve)",
+                   "kernel": "1.0*ExpSquared(scale=1.0), L2", "diag": 0.1, "seed": SEED},
+        "cpu_baseline": {"value": value, "unit": "logp/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "logp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from tinygp_b200 import GaussianProcess, _cabi, kernels
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the B200 solver has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    stream = torch.cuda.current_stream()
+    ctx = _cabi.Context(device=local_rank, stream=stream.cuda_stream)
+    _cabi.set_context(ctx)
+    ctx.set_option("nb", args.nb)
+
+    n = args.n
+    X, y, diag, scale = make_dense_problem(n, rank)
+    kernel = 1.0 * kernels.ExpSquared(scale=scale)
+    prog = kernel.program()
+    from ctypes import byref, c_double
+    dX = torch.from_numpy(X).cuda()
+    dy = torch.from_numpy(y).cuda()
+    ddiag = torch.from_numpy(diag).cuda()
+    lp = c_double()
+
+    def step_device():
+        ctx.check(ctx.lib.b200gp_dense_log_probability_dev(
+            ctx.handle, _cabi.ptr(prog), prog.shape[0], dX.data_ptr(), n, NDIM, ddiag.data_ptr(), dy.data_ptr(),
+            byref(lp)))
+        return lp.value
+
+    def step_e2e():
+        return GaussianProcess(kernel, X, diag=diag).log_probability(y)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    # fp64 tensor peak on this GPU: burst (short loop) and sustained (~2 s loop, the denominator for a kernel
+    # timed inside a multi-second step)
+    peak_burst = max(ctx.measure_fp64_peak()[0] for _ in range(3))
+    ctx.set_option("peak_iters", 1_500_000)
+    peak_sustained, dfma_sustained = ctx.measure_fp64_peak()
+    ctx.set_option("peak_iters", 4096)
+
+    for _ in range(args.warmup):
+        step_device()
+    l0 = ctx.launch_count()
+    ctx.set_option("profile", 1)
+    ctx.profile(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, logp = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ctx.profile(reset=True)
+    ctx.set_option("profile", 0)
+    launches = ctx.launch_count() - l0
+
+    # e2e through the public API with host buffers
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    ms_e2e, logp_e2e = timed(step_e2e, e2e_steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * args.steps / (ms * 1e-3)
+    e2e_value = world * e2e_steps / (ms_e2e * 1e-3)
+    flop_alg = n ** 3 / 3.0
+    syrk_tf = prof["syrk_flop"] / max(prof["syrk_ms"], 1e-9) / 1e9
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_nt_kernel (trailing SYRK/GEMM update, DMMA m8n8k4 f64)",
+        "achieved": syrk_tf, "peak": peak_sustained, "unit": "TFLOP/s", "frac": syrk_tf / peak_sustained,
+        "peak_source": "measured on this GPU by b200gp_measure_fp64_peak (sustained ~2 s DMMA loop); "
+                       "MEASURED_PEAKS.json has no fp64 entry",
+        "peak_burst": peak_burst, "dfma_sustained": dfma_sustained,
+        "launches": int(prof["syrk_launches"]), "ms_total": prof["syrk_ms"],
+        "whole_step_tflops_n3_over_3": flop_alg * args.steps / (ms * 1e-3) / 1e12,
+        "traffic": _read_traffic(),
+    }
+    # CPU baseline on a bounded sample
+    n_s = pick_sample_n(25.0)
+    t_cpu, lp_cpu = oracle_dense_logp_seconds(n_s)
+    cpu_value = 1.0 / (t_cpu * (n / n_s) ** 3)
+    cpu_baseline = {"value": cpu_value, "unit": "logp/s", "cores": cpu_threads(), "kind": "port",
+                    "sample": f"N={n_s} timed ({t_cpu:.2f} s), extrapolated x{(n / n_s) ** 3:.0f} (N^3) to N={n}"}
+
+    line = {
+        "metric": "log_probability/sec", "value": value, "unit": "logp/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"dense ExpSquared 3-D N={n} log_probability (fused build + blocked Cholesky + solve)",
+                   "kernel": "1.0*ExpSquared(scale=1.0), L2", "diag": 0.1, "seed": SEED, "nb": args.nb,
+                   "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                   "l2": "working set 34 GB >> 126 MB L2 (no flush needed)"},
+        "logp": logp, "logp_e2e": logp_e2e,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "logp/s", "steps": e2e_steps,
+                "h2d_bytes_per_step": int(n * NDIM * 8 + n * 8 + n * 8),
+                "d2h_bytes_per_step": int(n * 8 + n * 8 + 8 + 4)},
+        "gpu_launches": int(launches),
+        "kernel_ms_per_step": {"syrk": prof["syrk_ms"] / args.steps, "panel": prof["panel_ms"] / args.steps,
+                               "build": prof["build_ms"] / args.steps, "solve": prof["solve_ms"] / args.steps},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _read_traffic():
+    p = os.path.join(ROOT, "profiles", "syrk_traffic.json")
+    try:
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_DENSE)
+    ap.add_argument("--nb", type=int, default=1024)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,11 @@ KERNELS = {
     "expsq_l1": lambda: kernels.ExpSquared(1.5, kernels.L1Distance()),
     "combo": lambda: 1.8 * kernels.ExpSquared(0.9) + kernels.Matern32(3.0) * kernels.Constant(0.4) + 0.1,
     "c3": lambda: 1.5 * kernels.Matern52(2.0) + 0.7 * kernels.RationalQuadratic(1.5, alpha=1.5),
+    # BASELINE config 3 with Euclidean metrics (the L1 defaults are not positive definite for D > 1)
+    "c3_l2": lambda: (1.5 * kernels.Matern52(2.0, kernels.L2Distance())
+                      + 0.7 * kernels.RationalQuadratic(1.5, kernels.L2Distance(), alpha=1.5)),
+    "combo_l2": lambda: (1.8 * kernels.ExpSquared(0.9)
+                         + kernels.Matern32(3.0, kernels.L2Distance()) * kernels.Constant(0.4) + 0.1),
 }
 
 
@@ -41,7 +46,7 @@ def test_kernel_matrix_parity(name, ndim):
     y = rng.normal(size=61)
     np.testing.assert_allclose(k.matmul(X1, X2, y), ko(X1, X2) @ y, rtol=1e-11, atol=1e-12)
     # the diagonal of a stationary kernel is exact (explicit differences, distance.py:58-59)
-    if name not in ("combo", "c3"):
+    if name not in ("combo", "c3", "c3_l2", "combo_l2"):
         assert np.all(np.diag(k(X1, X1)) == np.diag(ko(X1, X1)))
 
 
@@ -74,7 +79,8 @@ def test_factor_parity(n, ctx):
     ctx.set_option("nb", 512)
 
 
-@pytest.mark.parametrize("n,ndim,name", [(256, 1, "expsq"), (777, 3, "c3"), (2048, 3, "expsq"), (1500, 2, "combo")])
+@pytest.mark.parametrize("n,ndim,name", [(256, 1, "expsq"), (777, 3, "c3_l2"), (2048, 3, "expsq"),
+                                         (1500, 2, "combo_l2"), (640, 1, "c3"), (900, 1, "combo")])
 def test_log_probability_parity(n, ndim, name):
     rng = np.random.default_rng(84930)
     if ndim == 1:
@@ -114,7 +120,7 @@ def test_solves_and_products():
     rng = np.random.default_rng(7)
     n = 700
     X = rng.uniform(0, 8, (n, 3))
-    k = kernels.Matern32(2.0)
+    k = kernels.Matern32(2.0, kernels.L2Distance())
     s = solvers.DirectSolver(k, X, noise.Diagonal(np.full(n, 0.1)))
     L = np.linalg.cholesky(to_oracle(k)(X, X) + 0.1 * np.eye(n))
     y = rng.normal(size=n)
@@ -141,7 +147,7 @@ def test_condition_and_predict(n, m):
     X = rng.uniform(0, 6, (n, 2))
     Xt = rng.uniform(0, 6, (m, 2))
     y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
-    k = 1.5 * kernels.Matern52(2.0)
+    k = 1.5 * kernels.Matern52(2.0, kernels.L2Distance())
     gp = GaussianProcess(k, X, diag=0.1, mean=0.2)
     gpo = o.GaussianProcess(to_oracle(k), X, diag=0.1, mean=0.2)
     lp, cond = gp.condition(y, Xt, diag=0.05)
@@ -179,6 +185,19 @@ def test_non_pd_gives_minus_inf():
     assert rel(gp.log_probability(np.sin(X)), gpo.log_probability(np.sin(X))) < 1e-7
 
 
+def test_reference_default_l1_metric_is_indefinite_in_3d():
+    """Matern/RationalQuadratic default to the L1 metric (stationary.py:56); for D > 1 that matrix is
+    not positive definite.  Reference behaviour: NaN factor -> log_probability = -inf (gp.py:316)."""
+    rng = np.random.default_rng(7)
+    X = rng.uniform(0, 8, (700, 3))
+    y = np.sin(X[:, 0])
+    k = kernels.Matern32(2.0)
+    gp = GaussianProcess(k, X, diag=0.1)
+    gpo = o.GaussianProcess(to_oracle(k), X, diag=0.1)
+    assert gpo.log_probability(y) == -np.inf
+    assert gp.solver.info > 0 and gp.log_probability(y) == -np.inf
+
+
 def test_sampling_statistics():
     # tests/test_gp.py:24-38 (statistical parity only: the RNG stream differs from JAX's)
     rng = np.random.default_rng(1058390)
@@ -206,8 +225,6 @@ def test_large_n_properties():
     a = gp.solver.solve_triangular(gp.solver.solve_triangular(y), transpose=True)
     back = gp.solver.dot_triangular(gp.solver.solve_triangular(y))
     np.testing.assert_allclose(back, y, rtol=1e-9, atol=1e-10)
-    z = rng.normal(size=n)
-    Lz = gp.solver.dot_triangular(z)
-    Kz = k.matmul(X, X, z) + 0.1 * z
-    assert rel(Lz @ Lz, z @ Kz) < 1e-10
+    # K (K^-1 y) == y with K applied by the matrix-free kernel matvec
+    np.testing.assert_allclose(k.matmul(X, X, a) + 0.1 * a, y, rtol=1e-8, atol=1e-9)
     assert rel(y @ a, np.sum(gp.solver.solve_triangular(y) ** 2)) < 1e-10

@@ -100,3 +100,20 @@ def test_fast_generators_equal_loop(data):
     k = o.qs.SHO(1.5, 3.0, 1.8) + 0.7 * o.qs.Matern32(1.5, 0.9)
     for a, b in zip(k.to_symm_qsm(X), o.qs_generators_fast(k, X)):
         np.testing.assert_array_equal(a, b)
+
+
+def test_c_restatement_equals_numpy(data):
+    from oracle import cref
+    X, y = data
+    k = o.qs.SHO(1.5, 3.0, 1.8) + o.qs.Matern32(1.5, 0.9)
+    d, p, q, a = k.to_symm_qsm(X)
+    d = d + 0.1
+    c, w, bad = cref.qs_cholesky(d, p, q, a)
+    c2, w2 = o.qs_cholesky(d, p, q, a)
+    assert bad == 0
+    np.testing.assert_allclose(c, c2, rtol=1e-14)
+    np.testing.assert_allclose(w, w2, rtol=1e-12, atol=1e-15)
+    lp = cref.qs_log_probability(d, p, q, a, y)
+    lp2 = o.GaussianProcess(k, X, diag=0.1).log_probability(y)
+    assert abs(lp - lp2) <= 1e-12 * abs(lp2)
+    assert cref.qs_log_probability(d - 10.0, p, q, a, y) == -np.inf

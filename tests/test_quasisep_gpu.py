@@ -1,0 +1,150 @@
+"""Parity of the CUDA QuasisepSolver path against the oracle (run with -m gpu on the B200 box)."""
+
+from ctypes import byref, c_int, c_void_p
+
+import numpy as np
+import pytest
+
+from oracle import tinygp_np as o
+from tinygp_b200 import GaussianProcess, _cabi, noise, solvers
+from tinygp_b200.kernels import quasisep as Q
+from util import LOGP_RTOL, rel, to_oracle
+
+pytestmark = pytest.mark.gpu
+
+QS = {
+    "m32": lambda: Q.Matern32(1.5),                                   # test_solver.py:30
+    "m52+exp": lambda: 1.5 * Q.Matern52(1.5) + 0.3 * Q.Exp(1.5),      # test_solver.py:31
+    "sho+m32": lambda: Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9),   # BASELINE config 4
+    "sho_over": lambda: Q.SHO(1.5, 0.3),
+    "sho_crit": lambda: Q.SHO(1.5, 0.5, 1.3),
+    "celerite": lambda: Q.Celerite(1.1, 0.8, 0.9, 0.1),
+    "cos+exp": lambda: Q.Cosine(2.5) + Q.Exp(0.7, 1.3),
+    "j6": lambda: Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9) + 0.5 * Q.SHO(0.4, 1.2),
+    "exp": lambda: Q.Exp(2.0, 0.8),
+}
+
+
+def _data(n, seed=84930):
+    rng = np.random.default_rng(seed)
+    X = np.sort(rng.uniform(-3, 3, n))
+    return X, np.sin(X), rng
+
+
+@pytest.mark.parametrize("name", sorted(QS))
+@pytest.mark.parametrize("n", [1, 50, 333])
+def test_factor_and_ops_parity(name, n):
+    X, y, rng = _data(n)
+    k = QS[name]()
+    ko = to_oracle(k)
+    diag = rng.uniform(0.05, 0.2, n)
+    s = solvers.QuasisepSolver(k, X, noise.Diagonal(diag))
+    so = o.QuasisepSolver(ko, X, o.Diagonal(diag))
+    # generators (kernels/quasisep.py:102-116)
+    for got, want in zip(s.generators(), (so.d, so.p, so.q, so.a)):
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+    c, w = s.factor()
+    np.testing.assert_allclose(c, so.c, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(w, so.w, rtol=1e-9, atol=1e-11)
+    assert rel(s.normalization(), so.normalization()) < 1e-11
+    np.testing.assert_allclose(s.variance(), so.variance(), rtol=1e-14)
+    Y = rng.normal(size=(n, 3))
+    np.testing.assert_allclose(s.solve_triangular(y), so.solve_triangular(y), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(s.solve_triangular(Y), so.solve_triangular(Y), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(s.solve_triangular(Y, transpose=True), so.solve_triangular(Y, transpose=True),
+                               rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(s.dot_triangular(Y), so.dot_triangular(Y), rtol=1e-10, atol=1e-12)
+    if n <= 60:
+        np.testing.assert_allclose(s.covariance(), so.covariance(), rtol=1e-10, atol=1e-12)
+        # Quasisep == Direct on the covariance (test_solver.py:34-47)
+        np.testing.assert_allclose(s.covariance(), k(X, X) + np.diag(diag), rtol=5e-7, atol=5e-7)
+
+
+@pytest.mark.parametrize("name", sorted(QS))
+def test_logp_quasisep_equals_oracle_and_dense(name):
+    # test_solver.py:59-79: QuasisepSolver vs DirectSolver log-probability
+    X, y, _ = _data(700)
+    k = QS[name]()
+    gp = GaussianProcess(k, X, diag=0.1)
+    lp = gp.log_probability(y)
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+    assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+    K = k(X, X) + 0.1 * np.eye(len(X))
+    Lc = np.linalg.cholesky(K)
+    lpd = -0.5 * np.sum(np.linalg.solve(Lc, y) ** 2) - np.sum(np.log(np.diag(Lc))) - 0.5 * len(X) * np.log(2 * np.pi)
+    assert rel(lp, lpd) < 1e-7
+    # parallel flag is accepted and gives the same numbers (test_solver.py:62-68)
+    lp2 = GaussianProcess(k, X, diag=0.1, parallel=True, assume_sorted=True).log_probability(y)
+    assert lp2 == lp
+
+
+def test_condition_dense_branch():
+    # solver.py:131-139 via gp.condition with X_test
+    X, y, rng = _data(120)
+    Xt = np.sort(rng.uniform(-3, 3, 30))
+    k = Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9)
+    lp, cond = GaussianProcess(k, X, diag=0.1).condition(y, Xt)
+    ko = to_oracle(k)
+    lpo, condo = o.GaussianProcess(ko, X, diag=0.1).condition(y, Xt)
+    assert rel(lp, lpo) < LOGP_RTOL
+    np.testing.assert_allclose(cond.loc, condo.loc, rtol=5e-7, atol=5e-7)
+    np.testing.assert_allclose(cond.covariance, condo.covariance, rtol=5e-7, atol=5e-7)
+
+
+def test_unsorted_raises_and_ties_allowed(ctx):
+    # test_solver.py:127-143 ; _check_sorted is a bit-exact boolean
+    X, y, _ = _data(500)
+    with pytest.raises(ValueError, match="sorted"):
+        GaussianProcess(Q.Matern32(1.0), X[::-1].copy(), diag=0.1)
+    Xs = X.copy()
+    Xs[250], Xs[251] = Xs[251], Xs[250]
+    with pytest.raises(ValueError, match="sorted"):
+        GaussianProcess(Q.Matern32(1.0), Xs, diag=0.1)
+    GaussianProcess(Q.Matern32(1.0), Xs, diag=0.1, assume_sorted=True)   # unchecked
+    Xt = X.copy()
+    Xt[10] = Xt[9]
+    GaussianProcess(Q.Matern32(1.0), Xt, diag=0.1).log_probability(y)    # ties allowed
+    flag = c_int(-1)
+    for arr, want in ((X, 0), (Xs, 1), (Xt, 0), (np.array([1.0]), 0), (np.array([2.0, 1.0]), 1)):
+        a = _cabi.f64(arr)
+        ctx.check(ctx.lib.b200gp_qs_check_sorted(ctx.handle, _cabi.ptr(a), a.shape[0], byref(flag)))
+        assert flag.value == want == int(np.any(np.diff(arr) < 0.0))
+
+
+def test_searchsorted_bit_exact(ctx):
+    # kernels/quasisep.py:121 : searchsorted(X2, X1, side="right") - 1
+    rng = np.random.default_rng(3)
+    a = np.sort(rng.uniform(0, 10, 10_000))
+    a[100:105] = a[100]                       # repeated values
+    v = np.concatenate([rng.uniform(-1, 11, 5000), a[::7], [a[0], a[-1], -5.0, 50.0]])
+    out = np.empty(v.shape[0], dtype=np.int64)
+    ctx.check(ctx.lib.b200gp_searchsorted_right_m1(ctx.handle, _cabi.ptr(a), a.shape[0], _cabi.ptr(v), v.shape[0],
+                                                   c_void_p(out.ctypes.data)))
+    assert np.array_equal(out, np.searchsorted(a, v, side="right") - 1)
+
+
+def test_non_pd_gives_minus_inf():
+    X = np.linspace(0, 1, 300)
+    gp = GaussianProcess(Q.Matern32(1.0), X, diag=-0.5)
+    assert gp.solver.info > 0
+    assert gp.log_probability(np.ones(300)) == -np.inf
+
+
+def test_large_n_against_c_oracle_and_properties():
+    """N = 1e6 (many chunks, several tree levels): vs the C oracle, plus size-independent round trips."""
+    from oracle import cref
+    rng = np.random.default_rng(49384)
+    n = 1_000_000
+    t = np.sort(rng.uniform(0, 1e5, n))
+    y = np.sin(t) + 0.1 * rng.normal(size=n)
+    k = Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9)
+    gp = GaussianProcess(k, t, diag=0.1, assume_sorted=True)
+    lp = gp.log_probability(y)
+    d, p, q, a = o.qs_generators_fast(to_oracle(k), t)
+    lpo = cref.qs_log_probability(d + 0.1, p, q, a, y)
+    assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+    s = gp.solver
+    z = rng.normal(size=n)
+    np.testing.assert_allclose(s.dot_triangular(s.solve_triangular(z)), z, rtol=1e-8, atol=1e-9)
+    a1 = s.solve_triangular(s.solve_triangular(y), transpose=True)
+    np.testing.assert_allclose(s.matmul(a1), y, rtol=1e-7, atol=1e-8)     # K K^-1 y == y

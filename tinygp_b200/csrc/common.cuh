@@ -54,26 +54,36 @@ struct b200gp_ctx {
     std::vector<CachedBuf> cache;  // freed big buffers kept for reuse
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int num_sms = 148;
+    int64_t peak_iters = 4096;  // loop length of the fp64 peak micro-benchmarks
+    // deferred (non-blocking) kernel timers: event pairs resolved at the next flush_timers()
+    struct Pending { cudaEvent_t a, b; double* acc; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t get_event();
+    void flush_timers();  // synchronises the stream
 
     void* alloc(size_t bytes);
     void release(void* p, size_t bytes);  // return to cache
     void trim();                          // cudaFree everything cached
 };
 
-// RAII timer that accumulates into a profile field when ctx->profile is on.
+// RAII timer that accumulates into a profile field when ctx->profile is on.  It only records two
+// events on the stream (no host synchronisation); elapsed times are resolved by flush_timers().
 struct ProfTimer {
     b200gp_ctx* c;
     double* acc;
+    cudaEvent_t a = nullptr;
     ProfTimer(b200gp_ctx* ctx, double* field) : c(ctx), acc(field) {
-        if (c->profile) cudaEventRecord(c->ev0, c->stream);
+        if (c->profile) {
+            a = c->get_event();
+            cudaEventRecord(a, c->stream);
+        }
     }
     ~ProfTimer() {
         if (c->profile) {
-            cudaEventRecord(c->ev1, c->stream);
-            cudaEventSynchronize(c->ev1);
-            float ms = 0;
-            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-            *acc += ms;
+            cudaEvent_t b = c->get_event();
+            cudaEventRecord(b, c->stream);
+            c->pending.push_back({a, b, acc});
         }
     }
 };

@@ -49,6 +49,30 @@ void b200gp_ctx::release(void* p, size_t bytes) {
     }
 }
 
+cudaEvent_t b200gp_ctx::get_event() {
+    if (!event_pool.empty()) {
+        cudaEvent_t e = event_pool.back();
+        event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void b200gp_ctx::flush_timers() {
+    if (pending.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto& p : pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) *p.acc += ms;
+        event_pool.push_back(p.a);
+        event_pool.push_back(p.b);
+    }
+    pending.clear();
+    cudaGetLastError();
+}
+
 void b200gp_ctx::trim() {
     cudaStreamSynchronize(stream);
     for (auto& c : cache) cudaFree(c.ptr);
@@ -123,6 +147,8 @@ int b200gp_create(int device, void* stream, b200gp_ctx** out) {
 int b200gp_destroy(b200gp_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
+    ctx->flush_timers();
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     ctx->trim();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -141,7 +167,11 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
         if (value < TILE || value % TILE) throw GpError("option nb must be a positive multiple of 128");
         _ctx->nb = value;
     } else if (!strcmp(key, "profile")) {
+        _ctx->flush_timers();
         _ctx->profile = (value != 0);
+    } else if (!strcmp(key, "peak_iters")) {
+        if (value < 16) throw GpError("option peak_iters must be >= 16");
+        _ctx->peak_iters = value;
     } else if (!strcmp(key, "trim")) {
         _ctx->trim();
     } else {
@@ -152,6 +182,7 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
 
 int b200gp_get_profile(b200gp_ctx* ctx, b200gp_profile* out, int reset) {
     API_BEGIN(ctx)
+    _ctx->flush_timers();
     *out = _ctx->prof;
     if (reset) memset(&_ctx->prof, 0, sizeof(_ctx->prof));
     API_END
@@ -159,7 +190,8 @@ int b200gp_get_profile(b200gp_ctx* ctx, b200gp_profile* out, int reset) {
 
 int b200gp_measure_fp64_peak(b200gp_ctx* ctx, double* dmma_tflops, double* dfma_tflops) {
     API_BEGIN(ctx)
-    const int blocks = _ctx->num_sms * 4, threads = 256, iters = 4096;
+    const int blocks = _ctx->num_sms * 4, threads = 256;
+    const int iters = (int)_ctx->peak_iters;
     double* buf = (double*)_ctx->alloc((size_t)blocks * threads * 8);
     float ms = 0;
     for (int rep = 0; rep < 2; ++rep) {  // first pass warms up

@@ -163,10 +163,12 @@ __global__ void __launch_bounds__(256) build_rect_kernel(const __grid_constant__
             }
         }
         const int64_t c = c0 + cl;
-        if (c + 1 < a.cols_pad) {
-            *reinterpret_cast<double2*>(a.out + r * a.ld + c) = make_double2(v[0], v[1]);
-        } else if (c < a.cols_pad) {
-            a.out[r * a.ld + c] = v[0];
+        double* dst = a.out + r * a.ld + c;
+        if (c + 1 < a.cols_pad && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+        } else {
+            if (c < a.cols_pad) dst[0] = v[0];
+            if (c + 1 < a.cols_pad) dst[1] = v[1];
         }
     }
 }

@@ -1,25 +1,1269 @@
-// placeholder until the scan kernels land (next commit): every entry point fails loudly.
+// QuasisepSolver path for sm_100a: the celerite recursions as chunked three-phase scans.
+//
+// Reference behaviour being replaced: src/tinygp/solvers/quasisep/solver.py:35-139,
+// src/tinygp/solvers/quasisep/ops.py:308-365,463-512 (sequential scans; the parallel forms :319-399,
+// :475-512 are the algebra the chunk composites come from), src/tinygp/kernels/quasisep.py:102-116
+// (generators) and :343-673 (state-space models).
+//
+// Scheme (every scan): one thread owns a chunk of CHUNK consecutive points and
+//   (1) folds its chunk into a composite starting from the identity,
+//   (2) a small tree (fan-in TREE_R) combines chunk composites and hands each chunk the state at
+//       its left edge,
+//   (3) the thread replays its chunk from that state with the *sequential reference recursion*,
+//       so emitted values follow ops.py:354-361 / :465-468 operation for operation.
+// Generators (a_k, p_k) are recomputed in registers from t[k] - t[k-1]; q and the kernel part of d
+// are constants of the model.  Cholesky composites are the (A, F, G) triples of ops.py:368-385; since
+// each point is a rank-one element the in-chunk fold needs no linear solve:
+//     u = F p, s = d - p.u, v = A^T p, w = q - a u
+//     F <- a F a^T + w w^T / s,   A <- a A - w v^T / s,   G <- G - v v^T / s
+// HBM traffic per point: read t, diag (and y) ; write c, w  -- 8(3 + 1 + J) bytes for log_probability.
 #include "common.cuh"
-#define QS_NI(ctxexpr)                                              \
-    b200gp_ctx* c_ = (ctxexpr);                                     \
-    if (c_) c_->err = "quasisep path not implemented yet";          \
-    return 4;
-struct b200gp_qs { b200gp_ctx* ctx; };
-extern "C" {
-int b200gp_qs_check_sorted(b200gp_ctx* ctx, const double*, int64_t, int*) { QS_NI(ctx) }
-int b200gp_qs_create(b200gp_ctx* ctx, const double*, int, const double*, int64_t, const double*, int, b200gp_qs**, int*, int*) { QS_NI(ctx) }
-int b200gp_qs_create_dev(b200gp_ctx* ctx, const double*, int, const double*, int64_t, const double*, int, b200gp_qs**, int*, int*) { QS_NI(ctx) }
-int b200gp_qs_free(b200gp_qs* s) { (void)s; return 0; }
-int b200gp_qs_state_dim(b200gp_qs* s, int*) { QS_NI(s ? s->ctx : nullptr) }
-int b200gp_qs_logdet_half(b200gp_qs* s, double*) { QS_NI(s ? s->ctx : nullptr) }
-int b200gp_qs_variance(b200gp_qs* s, double*) { QS_NI(s ? s->ctx : nullptr) }
-int b200gp_qs_get_factor(b200gp_qs* s, double*, double*) { QS_NI(s ? s->ctx : nullptr) }
-int b200gp_qs_get_generators(b200gp_qs* s, double*, double*, double*, double*) { QS_NI(s ? s->ctx : nullptr) }
-int b200gp_qs_solve_triangular(b200gp_qs* s, double*, int64_t, int) { QS_NI(s ? s->ctx : nullptr) }
-int b200gp_qs_dot_triangular(b200gp_qs* s, double*, int64_t) { QS_NI(s ? s->ctx : nullptr) }
-int b200gp_qs_matmul(b200gp_qs* s, double*, int64_t) { QS_NI(s ? s->ctx : nullptr) }
-int b200gp_qs_log_probability(b200gp_ctx* ctx, const double*, int, const double*, int64_t, const double*, const double*, int, int*, double*) { QS_NI(ctx) }
-int b200gp_qs_log_probability_dev(b200gp_ctx* ctx, const double*, int, const double*, int64_t, const double*, const double*, int, int*, double*) { QS_NI(ctx) }
-int b200gp_searchsorted_right_m1(b200gp_ctx* ctx, const double*, int64_t, const double*, int64_t, int64_t*) { QS_NI(ctx) }
-int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const double*, int, int64_t, const double*, int64_t, int, const double*, const double*, double*) { QS_NI(ctx) }
+#include <limits.h>
+
+#define QS_CHUNK 64
+#define TREE_R 16
+#define QS_THREADS 128
+
+struct QsModel {
+    int ncomp, J;
+    int kind[B200GP_QS_MAX_COMP];
+    int off[B200GP_QS_MAX_COMP];
+    int mode[B200GP_QS_MAX_COMP];  // SHO: 0 critical, 1 underdamped, 2 overdamped
+    double c0[B200GP_QS_MAX_COMP], c1[B200GP_QS_MAX_COMP], c2[B200GP_QS_MAX_COMP];
+    double h[B200GP_QS_MAX_J];  // observation model (constant for all supported kernels)
+    double q[B200GP_QS_MAX_J];  // h Pinf
+    double d0;                  // h Pinf h
+};
+
+struct b200gp_qs {
+    b200gp_ctx* ctx = nullptr;
+    int64_t n = 0;
+    int J = 0;
+    QsModel model{};
+    double* t = nullptr;     // n
+    double* diag = nullptr;  // n
+    double* c = nullptr;     // n
+    double* w = nullptr;     // n x J
+    int info = 0;
+    double logdet_half = 0.0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// host: lower the component list to a QsModel (constants follow kernels/quasisep.py)
+// ---------------------------------------------------------------------------------------------
+static QsModel build_model(const double* comps, int ncomp) {
+    if (ncomp <= 0 || ncomp > B200GP_QS_MAX_COMP) throw GpError("quasisep: bad component count");
+    QsModel m{};
+    m.ncomp = ncomp;
+    int J = 0;
+    double Pinf[B200GP_QS_MAX_J][B200GP_QS_MAX_J] = {};
+    for (int i = 0; i < ncomp; ++i) {
+        const double* cc = comps + (size_t)i * B200GP_QS_STRIDE;
+        const int kind = (int)cc[0];
+        const double ps = cc[1], p0 = cc[2], p1 = cc[3], p2 = cc[4], p3 = cc[5];
+        int sz;
+        switch (kind) {
+            case B200GP_QS_EXP: sz = 1; break;
+            case B200GP_QS_MATERN52: sz = 3; break;
+            case B200GP_QS_MATERN32: case B200GP_QS_SHO: case B200GP_QS_CELERITE: case B200GP_QS_COSINE: sz = 2; break;
+            default: throw GpError("quasisep: unknown component kind");
+        }
+        if (J + sz > B200GP_QS_MAX_J) throw GpError("quasisep: state dimension exceeds 8");
+        m.kind[i] = kind;
+        m.off[i] = J;
+        double P[3][3] = {};
+        double h[3] = {0, 0, 0};
+        switch (kind) {
+            case B200GP_QS_EXP:  // quasisep.py:491-525
+                m.c0[i] = p0; h[0] = p1; P[0][0] = 1.0; break;
+            case B200GP_QS_MATERN32: {  // quasisep.py:528-569
+                const double f = sqrt(3.0) / p0;
+                m.c0[i] = f; m.c1[i] = f * f; h[0] = p1;
+                P[0][0] = 1.0; P[1][1] = 3.0 / (p0 * p0); break;
+            }
+            case B200GP_QS_MATERN52: {  // quasisep.py:572-633
+                const double f = sqrt(5.0) / p0, f2 = f * f, f2o3 = f2 / 3.0;
+                m.c0[i] = f; m.c1[i] = f2; h[0] = p1;
+                P[0][0] = 1.0; P[0][2] = -f2o3; P[1][1] = f2o3; P[2][0] = -f2o3; P[2][2] = f2 * f2; break;
+            }
+            case B200GP_QS_SHO: {  // quasisep.py:404-488
+                const double w = p0, q = p1;
+                m.c0[i] = w; m.c1[i] = q; h[0] = p2;
+                P[0][0] = 1.0; P[1][1] = w * w;
+                if (fabs(q - 0.5) <= 1e-8 + 1e-5 * 0.5) {  // jnp.allclose(q, 0.5)
+                    m.mode[i] = 0;
+                } else if (q > 0.5) {
+                    m.mode[i] = 1; m.c2[i] = sqrt(fmax(4.0 * (q * q) - 1.0, 0.0));
+                } else {
+                    m.mode[i] = 2; m.c2[i] = sqrt(fmax(1.0 - 4.0 * (q * q), 0.0));
+                }
+                break;
+            }
+            case B200GP_QS_CELERITE: {  // quasisep.py:343-401
+                const double a = p0, b = p1, c = p2, d = p3;
+                const double c2 = c * c, d2 = d * d, s2 = c2 + d2;
+                const double h2_2 = d2 * (a * c - b * d) / (2.0 * c * s2);
+                const double h2 = sqrt(h2_2);
+                const double h1 = (c * h2 - sqrt(a * d2 - s2 * h2_2)) / d;
+                m.c0[i] = c; m.c1[i] = d; h[0] = h1; h[1] = h2;
+                P[0][0] = 1.0; P[0][1] = P[1][0] = -c / d; P[1][1] = 1.0 + 2.0 * c2 / d2; break;
+            }
+            case B200GP_QS_COSINE:  // quasisep.py:636-673
+                m.c0[i] = 2.0 * M_PI / p0; h[0] = p1; P[0][0] = P[1][1] = 1.0; break;
+        }
+        for (int r = 0; r < sz; ++r) {
+            m.h[J + r] = h[r];
+            for (int s = 0; s < sz; ++s) Pinf[J + r][J + s] = ps * P[r][s];  // Scale: quasisep.py:334-340
+        }
+        J += sz;
+    }
+    m.J = J;
+    m.d0 = 0.0;
+    for (int j = 0; j < J; ++j) {  // q = h Pinf ; d = sum(hP * h)   (quasisep.py:109-111)
+        double s = 0.0;
+        for (int i = 0; i < J; ++i) s += m.h[i] * Pinf[i][j];
+        m.q[j] = s;
+    }
+    for (int j = 0; j < J; ++j) m.d0 += m.q[j] * m.h[j];
+    return m;
 }
+
+// ---------------------------------------------------------------------------------------------
+// device: per-point generators  a = T(t_{k-1}, t_k)^T,  p = h a      (quasisep.py:102-116)
+// ---------------------------------------------------------------------------------------------
+template <int J>
+__device__ __forceinline__ void qs_gen(const QsModel& m, const double dt, double (&a)[J][J], double (&p)[J]) {
+    double al[J * J];  // scratch with runtime offsets; copied to registers below
+#pragma unroll
+    for (int i = 0; i < J * J; ++i) al[i] = 0.0;
+    for (int ci = 0; ci < m.ncomp; ++ci) {
+        const int o = m.off[ci];
+        double T[3][3];  // transition_matrix(X1, X2) as written in the reference
+        int sz = 2;
+        switch (m.kind[ci]) {
+            case B200GP_QS_EXP:
+                sz = 1;
+                T[0][0] = exp(-dt / m.c0[ci]);
+                break;
+            case B200GP_QS_MATERN32: {
+                const double f = m.c0[ci], e = exp(-f * dt);
+                T[0][0] = e * (1.0 + f * dt); T[0][1] = e * (-m.c1[ci] * dt);
+                T[1][0] = e * dt;             T[1][1] = e * (1.0 - f * dt);
+                break;
+            }
+            case B200GP_QS_MATERN52: {
+                sz = 3;
+                const double f = m.c0[ci], f2 = m.c1[ci], d2 = dt * dt, e = exp(-f * dt);
+                T[0][0] = e * (0.5 * f2 * d2 + f * dt + 1.0);
+                T[0][1] = e * (-0.5 * f * f2 * d2);
+                T[0][2] = e * (0.5 * f2 * f * dt * (f * dt - 2.0));
+                T[1][0] = e * (dt * (f * dt + 1.0));
+                T[1][1] = e * (-f2 * d2 + f * dt + 1.0);
+                T[1][2] = e * (f2 * dt * (f * dt - 3.0));
+                T[2][0] = e * (0.5 * d2);
+                T[2][1] = e * (0.5 * dt * (2.0 - f * dt));
+                T[2][2] = e * (0.5 * f2 * d2 - 2.0 * f * dt + 1.0);
+                break;
+            }
+            case B200GP_QS_SHO: {
+                const double w = m.c0[ci], q = m.c1[ci];
+                if (m.mode[ci] == 0) {
+                    const double e = exp(-w * dt);
+                    T[0][0] = e * (1.0 + w * dt); T[0][1] = e * (-(w * w) * dt);
+                    T[1][0] = e * dt;             T[1][1] = e * (1.0 - w * dt);
+                } else {
+                    const double f = m.c2[ci];
+                    const double arg = 0.5 * f * w * dt / q;
+                    const double e = exp(-0.5 * w * dt / q);
+                    double sn, cs;
+                    if (m.mode[ci] == 1) {
+                        sincos(arg, &sn, &cs);
+                    } else {
+                        sn = sinh(arg);
+                        cs = cosh(arg);
+                    }
+                    T[0][0] = e * (cs + sn / f);           T[0][1] = e * (-2.0 * q * w * sn / f);
+                    T[1][0] = e * (2.0 * q * sn / (w * f)); T[1][1] = e * (cs - sn / f);
+                }
+                break;
+            }
+            case B200GP_QS_CELERITE: {
+                double sn, cs;
+                sincos(m.c1[ci] * dt, &sn, &cs);
+                const double e = exp(-m.c0[ci] * dt);
+                // exp(-c dt) * [[cos, -sin], [sin, cos]].T
+                T[0][0] = e * cs; T[0][1] = e * sn;
+                T[1][0] = e * -sn; T[1][1] = e * cs;
+                break;
+            }
+            default: {  // COSINE
+                double sn, cs;
+                sincos(m.c0[ci] * dt, &sn, &cs);
+                T[0][0] = cs; T[0][1] = sn;
+                T[1][0] = -sn; T[1][1] = cs;
+                break;
+            }
+        }
+        for (int r = 0; r < sz; ++r)
+            for (int s = 0; s < sz; ++s) al[(o + r) * J + (o + s)] = T[s][r];  // a = T^T
+    }
+#pragma unroll
+    for (int i = 0; i < J; ++i)
+#pragma unroll
+        for (int j = 0; j < J; ++j) a[i][j] = al[i * J + j];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {  // p = h a
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < J; ++i) s += m.h[i] * a[i][j];
+        p[j] = s;
+    }
+}
+
+// small dense helpers ---------------------------------------------------------------------------
+template <int J>
+__device__ __forceinline__ void matmul(const double (&x)[J][J], const double (&y)[J][J], double (&o)[J][J]) {
+#pragma unroll
+    for (int i = 0; i < J; ++i)
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < J; ++k) s += x[i][k] * y[k][j];
+            o[i][j] = s;
+        }
+}
+template <int J>
+__device__ __forceinline__ void matmul_nt(const double (&x)[J][J], const double (&y)[J][J], double (&o)[J][J]) {
+#pragma unroll
+    for (int i = 0; i < J; ++i)
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < J; ++k) s += x[i][k] * y[j][k];
+            o[i][j] = s;
+        }
+}
+// solve M X = B in place (B overwritten by X); Gaussian elimination with partial pivoting
+template <int J>
+__device__ __forceinline__ void solve_inplace(double (&M)[J][J], double (&B)[J][J]) {
+#pragma unroll
+    for (int c = 0; c < J; ++c) {
+        int piv = c;
+        double best = fabs(M[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < J; ++r) {
+            const double v = fabs(M[r][c]);
+            if (v > best) { best = v; piv = r; }
+        }
+#pragma unroll
+        for (int r = c + 1; r < J; ++r) {
+            if (r == piv) {
+#pragma unroll
+                for (int k = 0; k < J; ++k) {
+                    double tmp = M[c][k]; M[c][k] = M[r][k]; M[r][k] = tmp;
+                    tmp = B[c][k]; B[c][k] = B[r][k]; B[r][k] = tmp;
+                }
+            }
+        }
+        const double inv = 1.0 / M[c][c];
+#pragma unroll
+        for (int r = c + 1; r < J; ++r) {
+            const double f = M[r][c] * inv;
+#pragma unroll
+            for (int k = 0; k < J; ++k) {
+                M[r][k] -= f * M[c][k];
+                B[r][k] -= f * B[c][k];
+            }
+        }
+    }
+#pragma unroll
+    for (int c = J - 1; c >= 0; --c) {
+        const double inv = 1.0 / M[c][c];
+#pragma unroll
+        for (int k = 0; k < J; ++k) {
+            double s = B[c][k];
+#pragma unroll
+            for (int r = c + 1; r < J; ++r) s -= M[c][r] * B[r][k];
+            B[c][k] = s * inv;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan monoids.  Storage is structure-of-arrays: element e of item i at buf[e * count + i].
+// ---------------------------------------------------------------------------------------------
+template <int J>
+struct Riccati {
+    static constexpr int SIZE = 3 * J * J;   // A, F, G
+    static constexpr int STATE = J * J;      // f
+    double A[J][J], F[J][J], G[J][J];
+    __device__ void identity() {
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) { A[i][j] = (i == j) ? 1.0 : 0.0; F[i][j] = 0.0; G[i][j] = 0.0; }
+    }
+    __device__ void load(const double* buf, int64_t count, int64_t i) {
+#pragma unroll
+        for (int e = 0; e < J * J; ++e) {
+            A[e / J][e % J] = buf[(int64_t)e * count + i];
+            F[e / J][e % J] = buf[(int64_t)(J * J + e) * count + i];
+            G[e / J][e % J] = buf[(int64_t)(2 * J * J + e) * count + i];
+        }
+    }
+    __device__ void store(double* buf, int64_t count, int64_t i) const {
+#pragma unroll
+        for (int e = 0; e < J * J; ++e) {
+            buf[(int64_t)e * count + i] = A[e / J][e % J];
+            buf[(int64_t)(J * J + e) * count + i] = F[e / J][e % J];
+            buf[(int64_t)(2 * J * J + e) * count + i] = G[e / J][e % J];
+        }
+    }
+    // this <- this (left) combined with r (right)      (ops.py:376-383)
+    __device__ void combine(const Riccati& r) {
+        double M[J][J], X[J][J], T1[J][J], T2[J][J];
+        // M = I + F_l G_r
+        matmul<J>(F, r.G, M);
+#pragma unroll
+        for (int i = 0; i < J; ++i) M[i][i] += 1.0;
+        // [M^-1 A_l | M^-1 F_l] share the factorisation: solve twice on copies
+        double Mc[J][J];
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) { Mc[i][j] = M[i][j]; X[i][j] = A[i][j]; }
+        solve_inplace<J>(Mc, X);        // X = M^-1 A_l
+        double newA[J][J];
+        matmul<J>(r.A, X, newA);        // A_r M^-1 A_l
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) { Mc[i][j] = M[i][j]; X[i][j] = F[i][j]; }
+        solve_inplace<J>(Mc, X);        // X = M^-1 F_l
+        matmul<J>(r.A, X, T1);          // A_r M^-1 F_l
+        matmul_nt<J>(T1, r.A, T2);      // ... A_r^T
+        double newF[J][J];
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) newF[i][j] = r.F[i][j] + T2[i][j];
+        // G_l + A_l^T M^-T G_r A_l : solve M^T Y = G_r
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) { Mc[i][j] = M[j][i]; X[i][j] = r.G[i][j]; }
+        solve_inplace<J>(Mc, X);        // X = M^-T G_r
+        matmul<J>(X, A, T1);            // M^-T G_r A_l
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < J; ++k) s += A[k][i] * T1[k][j];  // A_l^T (...)
+                T2[i][j] = s;
+            }
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) { G[i][j] += T2[i][j]; A[i][j] = newA[i][j]; F[i][j] = newF[i][j]; }
+    }
+    // f <- F + A (I + f G)^-1 f A^T
+    __device__ void apply(double (&f)[J][J]) const {
+        double M[J][J], X[J][J], T1[J][J];
+        matmul<J>(f, G, M);
+#pragma unroll
+        for (int i = 0; i < J; ++i) M[i][i] += 1.0;
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) X[i][j] = f[i][j];
+        solve_inplace<J>(M, X);
+        matmul<J>(A, X, T1);
+        matmul_nt<J>(T1, A, X);
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) f[i][j] = F[i][j] + X[i][j];
+    }
+};
+
+template <int J>
+struct Affine {
+    static constexpr int SIZE = J * J + J;  // A, b
+    static constexpr int STATE = J;         // g
+    double A[J][J], b[J];
+    __device__ void identity() {
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            b[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) A[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    }
+    __device__ void load(const double* buf, int64_t count, int64_t i) {
+#pragma unroll
+        for (int e = 0; e < J * J; ++e) A[e / J][e % J] = buf[(int64_t)e * count + i];
+#pragma unroll
+        for (int e = 0; e < J; ++e) b[e] = buf[(int64_t)(J * J + e) * count + i];
+    }
+    __device__ void store(double* buf, int64_t count, int64_t i) const {
+#pragma unroll
+        for (int e = 0; e < J * J; ++e) buf[(int64_t)e * count + i] = A[e / J][e % J];
+#pragma unroll
+        for (int e = 0; e < J; ++e) buf[(int64_t)(J * J + e) * count + i] = b[e];
+    }
+    __device__ void combine(const Affine& r) {  // (A_r A_l, A_r b_l + b_r)   (ops.py:322-324)
+        double nA[J][J], nb[J];
+        matmul<J>(r.A, A, nA);
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            double s = r.b[i];
+#pragma unroll
+            for (int k = 0; k < J; ++k) s += r.A[i][k] * b[k];
+            nb[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            b[i] = nb[i];
+#pragma unroll
+            for (int j = 0; j < J; ++j) A[i][j] = nA[i][j];
+        }
+    }
+    __device__ void apply(double (&g)[J]) const {
+        double o[J];
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            double s = b[i];
+#pragma unroll
+            for (int k = 0; k < J; ++k) s += A[i][k] * g[k];
+            o[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < J; ++i) g[i] = o[i];
+    }
+};
+
+template <int J> __device__ __forceinline__ void state_load(double (&f)[J][J], const double* buf, int64_t count, int64_t i) {
+#pragma unroll
+    for (int e = 0; e < J * J; ++e) f[e / J][e % J] = buf[(int64_t)e * count + i];
+}
+template <int J> __device__ __forceinline__ void state_store(const double (&f)[J][J], double* buf, int64_t count, int64_t i) {
+#pragma unroll
+    for (int e = 0; e < J * J; ++e) buf[(int64_t)e * count + i] = f[e / J][e % J];
+}
+template <int J> __device__ __forceinline__ void state_load(double (&g)[J], const double* buf, int64_t count, int64_t i) {
+#pragma unroll
+    for (int e = 0; e < J; ++e) g[e] = buf[(int64_t)e * count + i];
+}
+template <int J> __device__ __forceinline__ void state_store(const double (&g)[J], double* buf, int64_t count, int64_t i) {
+#pragma unroll
+    for (int e = 0; e < J; ++e) buf[(int64_t)e * count + i] = g[e];
+}
+template <int J> __device__ __forceinline__ void state_zero(double (&f)[J][J]) {
+#pragma unroll
+    for (int i = 0; i < J; ++i)
+#pragma unroll
+        for (int j = 0; j < J; ++j) f[i][j] = 0.0;
+}
+template <int J> __device__ __forceinline__ void state_zero(double (&g)[J]) {
+#pragma unroll
+    for (int i = 0; i < J; ++i) g[i] = 0.0;
+}
+
+template <class Op> struct StateOf;
+template <int J> struct StateOf<Riccati<J>> { typedef double type[J][J]; };
+template <int J> struct StateOf<Affine<J>> { typedef double type[J]; };
+
+// up-sweep: parent[i] = fold of child[i*R .. i*R+R-1]
+template <class Op>
+__global__ void __launch_bounds__(QS_THREADS) tree_up_kernel(const double* child, int64_t nchild, double* parent, int64_t nparent) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nparent) return;
+    Op acc, e;
+    const int64_t b = i * TREE_R;
+    acc.load(child, nchild, b);
+    for (int64_t j = b + 1; j < b + TREE_R && j < nchild; ++j) {
+        e.load(child, nchild, j);
+        acc.combine(e);
+    }
+    acc.store(parent, nparent, i);
+}
+// top: a single thread walks the (<= TREE_R) top items and emits the state at each item's left edge
+template <class Op>
+__global__ void tree_top_kernel(const double* items, int64_t n, double* start) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    typename StateOf<Op>::type s;
+    state_zero(s);
+    Op e;
+    for (int64_t i = 0; i < n; ++i) {
+        state_store(s, start, n, i);
+        e.load(items, n, i);
+        e.apply(s);
+    }
+}
+// down-sweep: child start states from the parent's start state
+template <class Op>
+__global__ void __launch_bounds__(QS_THREADS) tree_down_kernel(const double* child, int64_t nchild, const double* pstart,
+                                                               int64_t nparent, double* cstart) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nparent) return;
+    typename StateOf<Op>::type s;
+    state_load(s, pstart, nparent, i);
+    Op e;
+    const int64_t b = i * TREE_R;
+    for (int64_t j = b; j < b + TREE_R && j < nchild; ++j) {
+        state_store(s, cstart, nchild, j);
+        if (j + 1 < b + TREE_R && j + 1 < nchild) {
+            e.load(child, nchild, j);
+            e.apply(s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cholesky: chunk composites and replay
+// ---------------------------------------------------------------------------------------------
+template <int J>
+__global__ void __launch_bounds__(QS_THREADS) chol_chunk_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
+                                                                const double* __restrict__ diag, int64_t n,
+                                                                double* comp, int64_t nchunks) {
+    const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= nchunks) return;
+    const int64_t k0 = ch * QS_CHUNK, k1 = min(n, k0 + QS_CHUNK);
+    Riccati<J> R;
+    R.identity();
+    double tp = (k0 == 0) ? t[0] : t[k0 - 1];
+    for (int64_t k = k0; k < k1; ++k) {
+        const double tk = t[k];
+        double a[J][J], p[J];
+        qs_gen<J>(m, tk - tp, a, p);
+        tp = tk;
+        const double d = m.d0 + diag[k];
+        double u[J], v[J], w[J];
+        double s = d;
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            double x = 0.0, y = 0.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) { x += R.F[i][j] * p[j]; y += R.A[j][i] * p[j]; }
+            u[i] = x; v[i] = y;
+        }
+#pragma unroll
+        for (int i = 0; i < J; ++i) s -= p[i] * u[i];
+        const double is = 1.0 / s;
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            double x = m.q[i];
+#pragma unroll
+            for (int j = 0; j < J; ++j) x -= a[i][j] * u[j];
+            w[i] = x;
+        }
+        double T1[J][J], T2[J][J];
+        matmul<J>(a, R.F, T1);
+        matmul_nt<J>(T1, a, T2);
+        matmul<J>(a, R.A, T1);
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                R.F[i][j] = T2[i][j] + w[i] * w[j] * is;
+                R.A[i][j] = T1[i][j] - w[i] * v[j] * is;
+                R.G[i][j] -= v[i] * v[j] * is;
+            }
+    }
+    R.store(comp, nchunks, ch);
+}
+
+// replay with the sequential recursion of ops.py:354-361; writes c, w, per-chunk sum(log c)
+template <int J>
+__global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
+                                                                 const double* __restrict__ diag, int64_t n,
+                                                                 const double* fstart, int64_t nchunks, double* c_out,
+                                                                 double* w_out, double* logc_part, int* info) {
+    const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= nchunks) return;
+    const int64_t k0 = ch * QS_CHUNK, k1 = min(n, k0 + QS_CHUNK);
+    double f[J][J];
+    state_load<J>(f, fstart, nchunks, ch);
+    double tp = (k0 == 0) ? t[0] : t[k0 - 1];
+    double lsum = 0.0;
+    for (int64_t k = k0; k < k1; ++k) {
+        const double tk = t[k];
+        double a[J][J], p[J];
+        qs_gen<J>(m, tk - tp, a, p);
+        tp = tk;
+        const double d = m.d0 + diag[k];
+        // ck = sqrt(dk - pk @ fp @ pk)
+        double pf[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < J; ++i) s += p[i] * f[i][j];
+            pf[j] = s;
+        }
+        double quad = 0.0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) quad += pf[j] * p[j];
+        const double c2 = d - quad;
+        if (!(c2 > 0.0)) atomicMin(info, (int)min((int64_t)INT_MAX - 1, k) + 1);
+        const double ck = sqrt(c2);
+        // tmp = fp @ ak.T ; wk = (qk - pk @ tmp) / ck ; fk = ak @ tmp + outer(wk, wk)
+        double tmp[J][J];
+        matmul_nt<J>(f, a, tmp);
+        double w[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < J; ++i) s += p[i] * tmp[i][j];
+            w[j] = (m.q[j] - s) / ck;
+        }
+        matmul<J>(a, tmp, f);
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) f[i][j] += w[i] * w[j];
+        c_out[k] = ck;
+#pragma unroll
+        for (int j = 0; j < J; ++j) w_out[k * J + j] = w[j];
+        lsum += log(ck);
+    }
+    logc_part[ch] = lsum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// affine scans: triangular solves and products
+// ---------------------------------------------------------------------------------------------
+enum { OP_LOWER_SOLVE = 0, OP_UPPER_SOLVE = 1, OP_LOWER_DOT = 2, OP_SYMM_LOWER = 3, OP_SYMM_UPPER = 4 };
+__host__ __device__ constexpr bool op_reverse(int op) { return op == OP_UPPER_SOLVE || op == OP_SYMM_UPPER; }
+
+// logical position i of a reverse scan is physical index n-1-i
+template <int J, int OP>
+__global__ void __launch_bounds__(QS_THREADS) affine_chunk_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
+                                                                  const double* __restrict__ c, const double* __restrict__ w,
+                                                                  const double* __restrict__ x, int64_t n, double* comp,
+                                                                  int64_t nchunks) {
+    const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= nchunks) return;
+    const int64_t l0 = ch * QS_CHUNK, l1 = min(n, l0 + QS_CHUNK);
+    Affine<J> R;
+    R.identity();
+    for (int64_t l = l0; l < l1; ++l) {
+        const int64_t k = op_reverse(OP) ? (n - 1 - l) : l;
+        const double dt = (k == 0) ? 0.0 : (t[k] - t[k - 1]);
+        double a[J][J], p[J];
+        qs_gen<J>(m, dt, a, p);
+        const double xk = x[k];
+        double Ak[J][J], bk[J];
+        if (OP == OP_LOWER_SOLVE) {  // g' = (a - w p^T / c) g + w x / c
+            const double ic = 1.0 / c[k];
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                const double wi = w[k * J + i] * ic;
+                bk[i] = wi * xk;
+#pragma unroll
+                for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j] - wi * p[j];
+            }
+        } else if (OP == OP_UPPER_SOLVE) {  // g' = (a^T - p w^T / c) g + p x / c
+            const double ic = 1.0 / c[k];
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                const double pi = p[i] * ic;
+                bk[i] = pi * xk;
+#pragma unroll
+                for (int j = 0; j < J; ++j) Ak[i][j] = a[j][i] - pi * w[k * J + j];
+            }
+        } else if (OP == OP_LOWER_DOT) {  // g' = a g + w x
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                bk[i] = w[k * J + i] * xk;
+#pragma unroll
+                for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j];
+            }
+        } else if (OP == OP_SYMM_LOWER) {  // g' = a g + q x
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                bk[i] = m.q[i] * xk;
+#pragma unroll
+                for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j];
+            }
+        } else {  // OP_SYMM_UPPER: g' = a^T g + p x
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                bk[i] = p[i] * xk;
+#pragma unroll
+                for (int j = 0; j < J; ++j) Ak[i][j] = a[j][i];
+            }
+        }
+        double nA[J][J], nb[J];
+        matmul<J>(Ak, R.A, nA);
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            double s = bk[i];
+#pragma unroll
+            for (int j = 0; j < J; ++j) s += Ak[i][j] * R.b[j];
+            nb[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            R.b[i] = nb[i];
+#pragma unroll
+            for (int j = 0; j < J; ++j) R.A[i][j] = nA[i][j];
+        }
+    }
+    R.store(comp, nchunks, ch);
+}
+
+// replay; out may alias x only if accumulate == 0 (each thread reads x[k] before writing out[k])
+template <int J, int OP>
+__global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
+                                                                   const double* __restrict__ diag, const double* __restrict__ c,
+                                                                   const double* __restrict__ w, const double* x, int64_t n,
+                                                                   const double* gstart, int64_t nchunks, double* out,
+                                                                   double* sq_part) {
+    const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= nchunks) return;
+    const int64_t l0 = ch * QS_CHUNK, l1 = min(n, l0 + QS_CHUNK);
+    double g[J];
+    state_load<J>(g, gstart, nchunks, ch);
+    double ssum = 0.0;
+    for (int64_t l = l0; l < l1; ++l) {
+        const int64_t k = op_reverse(OP) ? (n - 1 - l) : l;
+        const double dt = (k == 0) ? 0.0 : (t[k] - t[k - 1]);
+        double a[J][J], p[J];
+        qs_gen<J>(m, dt, a, p);
+        const double xk = x[k];
+        double y, ng[J];
+        if (OP == OP_LOWER_SOLVE) {  // ops.py:465-468: y = (x - p@f)/d ; f = a@f + outer(q, y)
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) s += p[j] * g[j];
+            y = (xk - s) / c[k];
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
+                ng[i] = v + w[k * J + i] * y;
+            }
+            out[k] = y;
+        } else if (OP == OP_UPPER_SOLVE) {  // ops.py:491-494: y = (x - q@f)/d ; f = a.T@f + outer(p, y)
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) s += w[k * J + j] * g[j];
+            y = (xk - s) / c[k];
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) v += a[j][i] * g[j];
+                ng[i] = v + p[i] * y;
+            }
+            out[k] = y;
+        } else if (OP == OP_LOWER_DOT) {  // core.py:303-305 + ops.py:310-316: c x + p . f ; f = a f + w x
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) s += p[j] * g[j];
+            y = c[k] * xk + s;
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
+                ng[i] = v + w[k * J + i] * xk;
+            }
+            out[k] = y;
+        } else if (OP == OP_SYMM_LOWER) {  // core.py:499-505: d x + lower part
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) s += p[j] * g[j];
+            y = (m.d0 + diag[k]) * xk + s;
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
+                ng[i] = v + m.q[i] * xk;
+            }
+            out[k] = y;
+        } else {  // OP_SYMM_UPPER (ops.py:332-338): out += q . f ; f = a^T f + p x
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) s += m.q[j] * g[j];
+            y = s;
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) v += a[j][i] * g[j];
+                ng[i] = v + p[i] * xk;
+            }
+            out[k] += y;
+        }
+#pragma unroll
+        for (int i = 0; i < J; ++i) g[i] = ng[i];
+        ssum += y * y;
+    }
+    if (sq_part) sq_part[ch] = ssum;
+}
+
+// misc kernels -----------------------------------------------------------------------------------
+__global__ void sorted_check_kernel(const double* t, int64_t n, int* flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n && (t[i + 1] - t[i]) < 0.0) atomicOr(flag, 1);  // np.any(np.diff(X) < 0.0)
+}
+__global__ void searchsorted_kernel(const double* a, int64_t n, const double* v, int64_t m, int64_t* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double x = v[i];
+    int64_t lo = 0, hi = n;  // first index with a[idx] > x   (side="right")
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    out[i] = lo - 1;
+}
+__global__ void sum_partials_kernel(const double* part, int64_t n, double* out) {
+    __shared__ double sh[1024];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) acc += part[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+__global__ void add_const_kernel(const double* in, double c0, double* out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + c0;
+}
+__global__ void strided_gather_kernel(const double* src, int64_t stride, int64_t off, double* dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i * stride + off];
+}
+__global__ void strided_scatter_kernel(const double* src, double* dst, int64_t stride, int64_t off, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i * stride + off] = src[i];
+}
+template <int J>
+__global__ void generators_kernel(const __grid_constant__ QsModel m, const double* t, const double* diag, int64_t n,
+                                  double* d, double* p, double* q, double* a) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double aa[J][J], pp[J];
+    qs_gen<J>(m, (k == 0) ? 0.0 : (t[k] - t[k - 1]), aa, pp);
+    d[k] = m.d0 + diag[k];
+    for (int i = 0; i < J; ++i) {
+        p[k * J + i] = pp[i];
+        q[k * J + i] = m.q[i];
+        for (int j = 0; j < J; ++j) a[(k * J + i) * J + j] = aa[i][j];
+    }
+}
+
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// ---------------------------------------------------------------------------------------------
+// host-side tree driver: chunk composites -> start state per chunk
+// ---------------------------------------------------------------------------------------------
+template <class Op>
+static void run_tree(b200gp_ctx* ctx, double* comp0, int64_t n0, double* start0) {
+    std::vector<double*> comps{comp0};
+    std::vector<int64_t> counts{n0};
+    std::vector<size_t> bytes{0};
+    while (counts.back() > TREE_R) {
+        const int64_t nc = counts.back(), np_ = (nc + TREE_R - 1) / TREE_R;
+        const size_t b = (size_t)Op::SIZE * np_ * 8;
+        double* parent = (double*)ctx->alloc(b);
+        tree_up_kernel<Op><<<nblk(np_, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(comps.back(), nc, parent, np_);
+        ctx->launches++;
+        comps.push_back(parent);
+        counts.push_back(np_);
+        bytes.push_back(b);
+    }
+    const int L = (int)counts.size();
+    std::vector<double*> starts(L, nullptr);
+    std::vector<size_t> sbytes(L, 0);
+    for (int l = 0; l < L; ++l) {
+        if (l == 0) {
+            starts[l] = start0;
+        } else {
+            sbytes[l] = (size_t)Op::STATE * counts[l] * 8;
+            starts[l] = (double*)ctx->alloc(sbytes[l]);
+        }
+    }
+    tree_top_kernel<Op><<<1, 32, 0, ctx->stream>>>(comps[L - 1], counts[L - 1], starts[L - 1]);
+    ctx->launches++;
+    for (int l = L - 2; l >= 0; --l) {
+        tree_down_kernel<Op><<<nblk(counts[l + 1], QS_THREADS), QS_THREADS, 0, ctx->stream>>>(
+            comps[l], counts[l], starts[l + 1], counts[l + 1], starts[l]);
+        ctx->launches++;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    for (int l = 1; l < L; ++l) {
+        ctx->release(comps[l], bytes[l]);
+        ctx->release(starts[l], sbytes[l]);
+    }
+}
+
+template <int J>
+static void qs_factor_J(b200gp_qs* s, int* info_dev, double* logdet_dev) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t n = s->n, nch = (n + QS_CHUNK - 1) / QS_CHUNK;
+    const size_t cb = (size_t)Riccati<J>::SIZE * nch * 8, sb = (size_t)J * J * nch * 8;
+    double* comp = (double*)ctx->alloc(cb);
+    double* fstart = (double*)ctx->alloc(sb);
+    double* part = (double*)ctx->alloc((size_t)nch * 8);
+    chol_chunk_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->diag, n, comp, nch);
+    ctx->launches++;
+    run_tree<Riccati<J>>(ctx, comp, nch, fstart);
+    chol_replay_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->diag, n, fstart, nch,
+                                                                                 s->c, s->w, part, info_dev);
+    ctx->launches++;
+    sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part, nch, logdet_dev);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    ctx->release(comp, cb);
+    ctx->release(fstart, sb);
+    ctx->release(part, (size_t)nch * 8);
+}
+
+// one affine scan over a device vector x -> out ; optional sum of squares of the emitted values
+template <int J, int OP>
+static void qs_affine_J(b200gp_qs* s, const double* x, double* out, double* sumsq_dev) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t n = s->n, nch = (n + QS_CHUNK - 1) / QS_CHUNK;
+    const size_t cb = (size_t)Affine<J>::SIZE * nch * 8, sb = (size_t)J * nch * 8;
+    double* comp = (double*)ctx->alloc(cb);
+    double* gstart = (double*)ctx->alloc(sb);
+    double* part = sumsq_dev ? (double*)ctx->alloc((size_t)nch * 8) : nullptr;
+    affine_chunk_kernel<J, OP><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->c, s->w, x, n, comp, nch);
+    ctx->launches++;
+    run_tree<Affine<J>>(ctx, comp, nch, gstart);
+    affine_replay_kernel<J, OP><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->diag, s->c, s->w, x, n,
+                                                                                       gstart, nch, out, part);
+    ctx->launches++;
+    if (sumsq_dev) {
+        sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part, nch, sumsq_dev);
+        ctx->launches++;
+        ctx->release(part, (size_t)nch * 8);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    ctx->release(comp, cb);
+    ctx->release(gstart, sb);
+}
+
+#define QS_DISPATCH_J(Jv, CALL)                                          \
+    switch (Jv) {                                                        \
+        case 1: { constexpr int JJ = 1; CALL; } break;                   \
+        case 2: { constexpr int JJ = 2; CALL; } break;                   \
+        case 3: { constexpr int JJ = 3; CALL; } break;                   \
+        case 4: { constexpr int JJ = 4; CALL; } break;                   \
+        case 5: { constexpr int JJ = 5; CALL; } break;                   \
+        case 6: { constexpr int JJ = 6; CALL; } break;                   \
+        default: throw GpError("quasisep: state dimension > 6 is not compiled in"); \
+    }
+
+static void qs_affine(b200gp_qs* s, int op, const double* x, double* out, double* sumsq_dev) {
+    ProfTimer tm(s->ctx, &s->ctx->prof.qs_ms);
+    s->ctx->prof.qs_launches++;
+    s->ctx->prof.qs_bytes += 8.0 * (double)s->n * (3.0 + 2.0 * (1.0 + s->J));  // 2 passes read t,c,w,x ; write out
+    switch (op) {
+        case OP_LOWER_SOLVE: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_LOWER_SOLVE>(s, x, out, sumsq_dev))) break;
+        case OP_UPPER_SOLVE: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_UPPER_SOLVE>(s, x, out, sumsq_dev))) break;
+        case OP_LOWER_DOT: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_LOWER_DOT>(s, x, out, sumsq_dev))) break;
+        case OP_SYMM_LOWER: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_SYMM_LOWER>(s, x, out, sumsq_dev))) break;
+        case OP_SYMM_UPPER: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_SYMM_UPPER>(s, x, out, sumsq_dev))) break;
+        default: throw GpError("quasisep: bad op");
+    }
+}
+
+static void qs_destroy(b200gp_qs* s) {
+    if (!s) return;
+    b200gp_ctx* ctx = s->ctx;
+    const size_t nb = (size_t)s->n * 8;
+    if (s->t) ctx->release(s->t, nb);
+    if (s->diag) ctx->release(s->diag, nb);
+    if (s->c) ctx->release(s->c, nb);
+    if (s->w) ctx->release(s->w, nb * s->J);
+    delete s;
+}
+
+static bool qs_is_unsorted(b200gp_ctx* ctx, const double* t_dev, int64_t n) {
+    int* flag = (int*)ctx->alloc(sizeof(int));
+    CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    if (n > 1) {
+        sorted_check_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(t_dev, n, flag);
+        ctx->launches++;
+    }
+    int h = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->release(flag, sizeof(int));
+    return h != 0;
+}
+
+// t / diag may be host or device pointers
+static b200gp_qs* qs_create_impl(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n,
+                                 const double* diag, int assume_sorted, int* unsorted) {
+    if (n <= 0) throw GpError("quasisep: n must be positive");
+    QsModel model = build_model(comps, ncomp);
+    b200gp_qs* s = new b200gp_qs();
+    s->ctx = ctx;
+    s->n = n;
+    s->J = model.J;
+    s->model = model;
+    try {
+        const size_t nb = (size_t)n * 8;
+        s->t = (double*)ctx->alloc(nb);
+        s->diag = (double*)ctx->alloc(nb);
+        CUDA_CHECK(cudaMemcpyAsync(s->t, t, nb, cudaMemcpyDefault, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(s->diag, diag, nb, cudaMemcpyDefault, ctx->stream));
+        if (unsorted) *unsorted = 0;
+        if (!assume_sorted && qs_is_unsorted(ctx, s->t, n)) {
+            if (unsorted) *unsorted = 1;
+            qs_destroy(s);
+            return nullptr;
+        }
+        s->c = (double*)ctx->alloc(nb);
+        s->w = (double*)ctx->alloc(nb * s->J);
+        int* info_dev = (int*)ctx->alloc(sizeof(int));
+        double* ld_dev = (double*)ctx->alloc(sizeof(double));
+        int big = INT_MAX;
+        CUDA_CHECK(cudaMemcpyAsync(info_dev, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        {
+            ProfTimer tm(ctx, &ctx->prof.qs_ms);
+            ctx->prof.qs_launches++;
+            ctx->prof.qs_bytes += 8.0 * (double)n * (2.0 * 2.0 + 1.0 + s->J);  // two passes read t,diag ; write c,w
+            QS_DISPATCH_J(s->J, (qs_factor_J<JJ>(s, info_dev, ld_dev)))
+        }
+        CUDA_CHECK(cudaMemcpyAsync(&s->info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&s->logdet_half, ld_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (s->info == INT_MAX) s->info = 0;
+        ctx->release(info_dev, sizeof(int));
+        ctx->release(ld_dev, sizeof(double));
+    } catch (...) {
+        qs_destroy(s);
+        throw;
+    }
+    return s;
+}
+
+// apply `op` column by column to a host matrix Y (n, nrhs)
+static void qs_apply_host(b200gp_qs* s, int op, double* Y, int64_t nrhs, int op2 = -1) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t n = s->n;
+    if (nrhs <= 0) throw GpError("quasisep: nrhs must be positive");
+    double* yh = (double*)ctx->alloc((size_t)n * nrhs * 8);
+    double* x = (double*)ctx->alloc((size_t)n * 8);
+    double* o = (double*)ctx->alloc((size_t)n * 8);
+    CUDA_CHECK(cudaMemcpyAsync(yh, Y, (size_t)n * nrhs * 8, cudaMemcpyHostToDevice, ctx->stream));
+    for (int64_t r = 0; r < nrhs; ++r) {
+        if (nrhs == 1) {
+            CUDA_CHECK(cudaMemcpyAsync(x, yh, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            strided_gather_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(yh, nrhs, r, x, n);
+            ctx->launches++;
+        }
+        qs_affine(s, op, x, o, nullptr);
+        if (op2 >= 0) qs_affine(s, op2, x, o, nullptr);
+        strided_scatter_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>(o, yh, nrhs, r, n);
+        ctx->launches++;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(Y, yh, (size_t)n * nrhs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->release(yh, (size_t)n * nrhs * 8);
+    ctx->release(x, (size_t)n * 8);
+    ctx->release(o, (size_t)n * 8);
+}
+
+static double qs_logp_impl(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n,
+                           const double* diag, const double* resid, int assume_sorted, int* unsorted) {
+    b200gp_qs* s = qs_create_impl(ctx, comps, ncomp, t, n, diag, assume_sorted, unsorted);
+    if (!s) return NAN;
+    double logp;
+    try {
+        double* x = (double*)ctx->alloc((size_t)n * 8);
+        double* o = (double*)ctx->alloc((size_t)n * 8);
+        double* ss_dev = (double*)ctx->alloc(8);
+        CUDA_CHECK(cudaMemcpyAsync(x, resid, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
+        qs_affine(s, OP_LOWER_SOLVE, x, o, ss_dev);
+        double ss = 0.0;
+        CUDA_CHECK(cudaMemcpyAsync(&ss, ss_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        logp = -0.5 * ss - (s->logdet_half + 0.5 * (double)n * log(2.0 * M_PI));  // gp.py:313-316 ; solver.py:90-93
+        if (s->info != 0 || !isfinite(logp)) logp = -INFINITY;
+        ctx->release(x, (size_t)n * 8);
+        ctx->release(o, (size_t)n * 8);
+        ctx->release(ss_dev, 8);
+    } catch (...) {
+        qs_destroy(s);
+        throw;
+    }
+    qs_destroy(s);
+    return logp;
+}
+
+// =============================================================================================
+// C-ABI: quasisep
+// =============================================================================================
+extern "C" {
+
+int b200gp_qs_check_sorted(b200gp_ctx* ctx, const double* t, int64_t n, int* unsorted) {
+    API_BEGIN(ctx)
+    if (n <= 0) throw GpError("check_sorted: empty input");
+    double* td = (double*)_ctx->alloc((size_t)n * 8);
+    CUDA_CHECK(cudaMemcpyAsync(td, t, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
+    *unsorted = qs_is_unsorted(_ctx, td, n) ? 1 : 0;
+    _ctx->release(td, (size_t)n * 8);
+    API_END
+}
+
+int b200gp_qs_create(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n, const double* diag,
+                     int assume_sorted, b200gp_qs** out, int* unsorted, int* info) {
+    API_BEGIN(ctx)
+    *out = nullptr;
+    b200gp_qs* s = qs_create_impl(_ctx, comps, ncomp, t, n, diag, assume_sorted, unsorted);
+    *out = s;
+    if (info) *info = s ? s->info : 0;
+    API_END
+}
+
+int b200gp_qs_create_dev(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t_dev, int64_t n,
+                         const double* diag_dev, int assume_sorted, b200gp_qs** out, int* unsorted, int* info) {
+    return b200gp_qs_create(ctx, comps, ncomp, t_dev, n, diag_dev, assume_sorted, out, unsorted, info);
+}
+
+int b200gp_qs_free(b200gp_qs* s) {
+    if (!s) return 0;
+    API_BEGIN(s->ctx)
+    qs_destroy(s);
+    API_END
+}
+
+int b200gp_qs_state_dim(b200gp_qs* s, int* J) {
+    API_BEGIN(s->ctx)
+    *J = s->J;
+    API_END
+}
+
+int b200gp_qs_logdet_half(b200gp_qs* s, double* out) {
+    API_BEGIN(s->ctx)
+    *out = (s->info != 0) ? NAN : s->logdet_half;
+    API_END
+}
+
+int b200gp_qs_variance(b200gp_qs* s, double* out) {
+    API_BEGIN(s->ctx)
+    double* o = (double*)_ctx->alloc((size_t)s->n * 8);
+    add_const_kernel<<<nblk(s->n, 256), 256, 0, _ctx->stream>>>(s->diag, s->model.d0, o, s->n);
+    _ctx->launches++;
+    CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)s->n * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(o, (size_t)s->n * 8);
+    API_END
+}
+
+int b200gp_qs_get_factor(b200gp_qs* s, double* c, double* w) {
+    API_BEGIN(s->ctx)
+    CUDA_CHECK(cudaMemcpyAsync(c, s->c, (size_t)s->n * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(w, s->w, (size_t)s->n * s->J * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    API_END
+}
+
+int b200gp_qs_get_generators(b200gp_qs* s, double* d, double* p, double* q, double* a) {
+    API_BEGIN(s->ctx)
+    const int64_t n = s->n;
+    const int J = s->J;
+    double* dd = (double*)_ctx->alloc((size_t)n * 8);
+    double* pd = (double*)_ctx->alloc((size_t)n * J * 8);
+    double* qd = (double*)_ctx->alloc((size_t)n * J * 8);
+    double* ad = (double*)_ctx->alloc((size_t)n * J * J * 8);
+    QS_DISPATCH_J(J, (generators_kernel<JJ><<<nblk(n, 128), 128, 0, _ctx->stream>>>(s->model, s->t, s->diag, n, dd, pd, qd, ad)))
+    _ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(d, dd, (size_t)n * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(p, pd, (size_t)n * J * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(q, qd, (size_t)n * J * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(a, ad, (size_t)n * J * J * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(dd, (size_t)n * 8);
+    _ctx->release(pd, (size_t)n * J * 8);
+    _ctx->release(qd, (size_t)n * J * 8);
+    _ctx->release(ad, (size_t)n * J * J * 8);
+    API_END
+}
+
+int b200gp_qs_solve_triangular(b200gp_qs* s, double* Y, int64_t nrhs, int transpose) {
+    API_BEGIN(s->ctx)
+    qs_apply_host(s, transpose ? OP_UPPER_SOLVE : OP_LOWER_SOLVE, Y, nrhs);
+    API_END
+}
+
+int b200gp_qs_dot_triangular(b200gp_qs* s, double* Y, int64_t nrhs) {
+    API_BEGIN(s->ctx)
+    qs_apply_host(s, OP_LOWER_DOT, Y, nrhs);
+    API_END
+}
+
+int b200gp_qs_matmul(b200gp_qs* s, double* Y, int64_t nrhs) {
+    API_BEGIN(s->ctx)
+    qs_apply_host(s, OP_SYMM_LOWER, Y, nrhs, OP_SYMM_UPPER);
+    API_END
+}
+
+int b200gp_qs_log_probability(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n,
+                              const double* diag, const double* resid, int assume_sorted, int* unsorted, double* logp) {
+    API_BEGIN(ctx)
+    *logp = qs_logp_impl(_ctx, comps, ncomp, t, n, diag, resid, assume_sorted, unsorted);
+    API_END
+}
+
+int b200gp_qs_log_probability_dev(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t_dev, int64_t n,
+                                  const double* diag_dev, const double* resid_dev, int assume_sorted, int* unsorted,
+                                  double* logp) {
+    return b200gp_qs_log_probability(ctx, comps, ncomp, t_dev, n, diag_dev, resid_dev, assume_sorted, unsorted, logp);
+}
+
+int b200gp_searchsorted_right_m1(b200gp_ctx* ctx, const double* sorted, int64_t n, const double* query, int64_t m,
+                                 int64_t* out) {
+    API_BEGIN(ctx)
+    if (n <= 0 || m <= 0) throw GpError("searchsorted: empty input");
+    double* a = (double*)_ctx->alloc((size_t)n * 8);
+    double* v = (double*)_ctx->alloc((size_t)m * 8);
+    int64_t* o = (int64_t*)_ctx->alloc((size_t)m * 8);
+    CUDA_CHECK(cudaMemcpyAsync(a, sorted, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(v, query, (size_t)m * 8, cudaMemcpyDefault, _ctx->stream));
+    searchsorted_kernel<<<nblk(m, 256), 256, 0, _ctx->stream>>>(a, n, v, m, o);
+    _ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)m * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(a, (size_t)n * 8);
+    _ctx->release(v, (size_t)m * 8);
+    _ctx->release(o, (size_t)m * 8);
+    API_END
+}
+
+// batched dense log_probability lives in dense_batched.cu (placeholder until then)
+int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const double* progs, int n_instr, int64_t nbatch,
+                                         const double* X, int64_t n, int ndim, const double* diag, const double* resid,
+                                         double* logp) {
+    API_BEGIN(ctx)
+    for (int64_t b = 0; b < nbatch; ++b) {
+        int rc = b200gp_dense_log_probability(ctx, progs + (size_t)b * n_instr * B200GP_PROG_STRIDE, n_instr, X, n, ndim,
+                                              diag, resid, logp + b);
+        if (rc) return rc;
+    }
+    API_END
+}
+
+}  // extern "C"

@@ -347,6 +347,14 @@ class qs:
                 return h2 @ self.transition_matrix(X1, X2).T @ Pinf @ h1
             return h1 @ self.transition_matrix(X2, X1).T @ Pinf @ h2
 
+        def matmul(self, X1, X2=None, y=None):
+            """quasisep.py:147-163 (to_general_qsm @ y); evaluated densely here -- same values."""
+            if y is None:
+                y, X2 = X2, None
+            if X2 is None:
+                X2 = X1
+            return self(X1, X2) @ np.asarray(y, dtype=np.float64)
+
         def __call__(self, X1, X2=None):
             X1 = np.asarray(X1, dtype=np.float64)
             if X2 is None:

@@ -83,6 +83,14 @@ int b200gp_get_profile(b200gp_ctx* ctx, b200gp_profile* out, int reset);
  * register-resident mma.sync.m8n8k4.f64 loop on all SMs, and of a DFMA loop. */
 int b200gp_measure_fp64_peak(b200gp_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 
+/* diagnostics for the int8 fixed-point tensor-core update (tcgen05.mma kind::i8, ozaki.cu):
+ * C (rows x rows, host, in/out) -= sum_{s+t<S} 2^-(12+7(s+t)) rs_i rs_j Q_s Q_t^T with Q_s the S int8 digit planes
+ * (each rows x K, row-major, host).  rows % 256 == 0, K % 128 == 0.  Used by the parity tests only. */
+int b200gp_i8_update_test(b200gp_ctx* ctx, const int8_t* planes, int S, int64_t rows, int64_t K,
+                          const double* rs, double* C);
+/* option keys for b200gp_set_option: "nb", "profile", "peak_iters", "trim",
+ * "ozaki_slices" (0 = native fp64 DMMA trailing update; 2..8 = int8 digit planes), "ozaki_min_n". */
+
 /* ---- kernels.Kernel.__call__  (kernels/base.py:84-103) ---------------------------------- */
 /* out[n1*n2] = k(X1_i, X2_j);  X1 (n1, ndim), X2 (n2, ndim) row-major. */
 int b200gp_kernel_matrix(b200gp_ctx* ctx, const double* prog, int n_instr,

@@ -228,3 +228,33 @@ def test_large_n_properties():
     # K (K^-1 y) == y with K applied by the matrix-free kernel matvec
     np.testing.assert_allclose(k.matmul(X, X, a) + 0.1 * a, y, rtol=1e-8, atol=1e-9)
     assert rel(y @ a, np.sum(gp.solver.solve_triangular(y) ** 2)) < 1e-10
+
+
+def test_batched_hyperparameter_grid(ctx):
+    """BASELINE config 5 in miniature: B kernels over one (X, y); each entry equals its own log_probability."""
+    from ctypes import c_void_p
+    from tinygp_b200 import _cabi
+    rng = np.random.default_rng(49385)
+    n = 900
+    X = np.ascontiguousarray(rng.uniform(0, 8, (n, 3)))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    diag = np.full(n, 0.1)
+    grid = [(s, a) for s in (0.5, 1.0, 2.0) for a in (0.3, 1.0, 4.0)]
+    ks = [a * kernels.ExpSquared(scale=s) for s, a in grid]
+    progs = np.ascontiguousarray(np.stack([k.program() for k in ks]))
+    out = np.empty(len(ks))
+    for nb in (128, 512):
+        ctx.set_option("nb_batched", nb)
+        ctx.check(ctx.lib.b200gp_dense_log_probability_batched(
+            ctx.handle, _cabi.ptr(progs), progs.shape[1], len(ks), _cabi.ptr(X), n, 3, _cabi.ptr(diag), _cabi.ptr(y),
+            _cabi.ptr(out)))
+        for k, got in zip(ks, out):
+            want = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+            assert rel(got, want) < LOGP_RTOL, (got, want)
+    ctx.set_option("nb_batched", 512)
+    # a non-PD member of the batch gives -inf without disturbing the others
+    bad = np.ascontiguousarray(np.stack([ks[0].program(), (-1.0 * kernels.ExpSquared(1.0)).program()]))
+    out2 = np.empty(2)
+    ctx.check(ctx.lib.b200gp_dense_log_probability_batched(
+        ctx.handle, _cabi.ptr(bad), bad.shape[1], 2, _cabi.ptr(X), n, 3, _cabi.ptr(diag), _cabi.ptr(y), _cabi.ptr(out2)))
+    assert out2[1] == -np.inf and rel(out2[0], out[0]) < 1e-12

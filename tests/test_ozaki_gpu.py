@@ -1,0 +1,85 @@
+"""The int8 fixed-point (Ozaki-style) trailing update on tcgen05: exactness of the integer products, digit
+cutting, and parity of the full factorisation against the oracle (run with -m gpu on the B200 box)."""
+
+import numpy as np
+import pytest
+
+from oracle import tinygp_np as o
+from tinygp_b200 import GaussianProcess, _cabi, kernels, noise, solvers
+from util import LOGP_RTOL, rel, to_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_update(C, planes, rs, S):
+    out = C.copy()
+    P = planes.astype(np.float64)
+    for s in range(S):
+        for t in range(S - s):
+            out -= 2.0 ** -(12 + 7 * (s + t)) * (rs[:, None] * rs[None, :]) * (P[s] @ P[t].T)
+    return out
+
+
+@pytest.mark.parametrize("rows,K,S", [(256, 128, 1), (256, 512, 3), (512, 1024, 8), (768, 384, 7)])
+def test_i8_update_kernel_is_exact(ctx, rows, K, S):
+    rng = np.random.default_rng(rows + K + S)
+    planes = rng.integers(-64, 65, size=(S, rows, K), dtype=np.int8)
+    rs = 2.0 ** rng.integers(-2, 3, size=rows).astype(np.float64)
+    C = rng.normal(size=(rows, rows))
+    got = np.ascontiguousarray(C.copy())
+    pl = np.ascontiguousarray(planes)
+    ctx.check(ctx.lib.b200gp_i8_update_test(ctx.handle, _cabi.ptr(pl), S, rows, K, _cabi.ptr(rs), _cabi.ptr(got)))
+    want = _ref_update(C, planes, rs, S)
+    # integer dot products are exact; the only rounding is one fp64 fma per group
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
+
+
+@pytest.mark.parametrize("slices", [8, 7, 6])
+@pytest.mark.parametrize("n,nb", [(1024, 256), (3000, 512), (6144, 1024)])
+def test_ozaki_factor_parity(ctx, n, nb, slices):
+    rng = np.random.default_rng(n)
+    X = rng.uniform(0, 20.0 * (n / 65536.0) ** (1 / 3), (n, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    k = 1.3 * kernels.ExpSquared(0.8)
+    diag = rng.uniform(0.05, 0.2, n)
+    ctx.set_option("nb", nb)
+    ctx.set_option("ozaki_slices", slices)
+    ctx.set_option("ozaki_min_n", 0)
+    try:
+        s = solvers.DirectSolver(k, X, noise.Diagonal(diag))
+        lp = GaussianProcess(k, X, diag=diag).log_probability(y)
+    finally:
+        ctx.set_option("ozaki_slices", 0)
+        ctx.set_option("ozaki_min_n", 4096)
+        ctx.set_option("nb", 512)
+    so = o.DirectSolver(to_oracle(k), X, o.Diagonal(diag))
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=diag).log_probability(y)
+    assert s.info == 0
+    tol = {8: 1e-10, 7: 1e-9, 6: 1e-7}[slices]
+    np.testing.assert_allclose(s.scale_tril, so.scale_tril, rtol=tol, atol=tol)
+    assert rel(s.normalization(), so.normalization()) < 1e-10
+    assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+
+
+def test_ozaki_non_pd_and_large_scales(ctx):
+    """Row scales span orders of magnitude (heteroscedastic diag); an indefinite matrix still yields -inf."""
+    rng = np.random.default_rng(2)
+    n = 2048
+    X = rng.uniform(0, 6, (n, 2))
+    y = rng.normal(size=n)
+    diag = 10.0 ** rng.uniform(-2, 3, n)
+    k = 50.0 * kernels.ExpSquared(1.1)
+    ctx.set_option("nb", 256)
+    ctx.set_option("ozaki_slices", 8)
+    ctx.set_option("ozaki_min_n", 0)
+    try:
+        lp = GaussianProcess(k, X, diag=diag).log_probability(y)
+        bad = GaussianProcess(kernels.Matern32(2.0), rng.uniform(0, 8, (n, 3)), diag=0.1)   # L1 in 3-D: indefinite
+        lpbad = bad.log_probability(y)
+    finally:
+        ctx.set_option("ozaki_slices", 0)
+        ctx.set_option("ozaki_min_n", 4096)
+        ctx.set_option("nb", 512)
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=diag).log_probability(y)
+    assert rel(lp, lpo) < LOGP_RTOL
+    assert bad.solver.info > 0 and lpbad == -np.inf

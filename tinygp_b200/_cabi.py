@@ -48,6 +48,7 @@ SIGNATURES = {
     "b200gp_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
     "b200gp_get_profile": (c_int, [c_void_p, POINTER(Profile), c_int]),
     "b200gp_measure_fp64_peak": (c_int, [c_void_p, c_double_p, c_double_p]),
+    "b200gp_i8_update_test": (c_int, [_V, _D, _I, _L, _L, _D, _D]),
     "b200gp_kernel_matrix": (c_int, [_V, _D, _I, _D, _L, _D, _L, _I, _D]),
     "b200gp_kernel_diag": (c_int, [_V, _D, _I, _D, _L, _I, _D]),
     "b200gp_kernel_matvec": (c_int, [_V, _D, _I, _D, _L, _D, _L, _I, _D, _D]),

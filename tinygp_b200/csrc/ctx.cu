@@ -172,6 +172,14 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
     } else if (!strcmp(key, "peak_iters")) {
         if (value < 16) throw GpError("option peak_iters must be >= 16");
         _ctx->peak_iters = value;
+    } else if (!strcmp(key, "nb_batched")) {
+        if (value < TILE || value % TILE) throw GpError("option nb_batched must be a positive multiple of 128");
+        _ctx->nb_batched = value;
+    } else if (!strcmp(key, "ozaki_slices")) {
+        if (value < 0 || value > 8) throw GpError("option ozaki_slices must be in [0, 8]");
+        _ctx->oz_slices = value;
+    } else if (!strcmp(key, "ozaki_min_n")) {
+        _ctx->oz_min_n = value;
     } else if (!strcmp(key, "trim")) {
         _ctx->trim();
     } else {

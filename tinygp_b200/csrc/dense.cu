@@ -22,7 +22,7 @@
 #define PI_D 3.141592653589793
 
 // l1 = sum_d |x1_d - x2_d| ; l2sq = sum_d (x1_d - x2_d)^2   (explicit differences, distance.py:45,59)
-__device__ __forceinline__ double kprog_eval(const KProg& P, double l1, double l2sq) {
+__host__ __device__ __forceinline__ double kprog_eval(const KProg& P, double l1, double l2sq) {
     double st[8];
     int sp = 0;
     for (int i = 0; i < P.n; ++i) {
@@ -116,14 +116,25 @@ struct BuildArgs {
     int64_t row_off, col_off;  // global indices of out(0,0), used for the diagonal / identity pad
     int ndim;
     int pad_identity;  // padded entries: (grow==gcol) ? 1 : 0 instead of 0
+    // batched build (blockIdx.z = problem): one program per problem, outputs batch_stride apart
+    const KProg* progs;
+    int64_t batch_stride;
 };
 
 #define BUILD_ROWS 32
 #define BUILD_COLS 128
-__global__ void __launch_bounds__(256) build_rect_kernel(const __grid_constant__ KProg P, const BuildArgs a) {
+__global__ void __launch_bounds__(256) build_rect_kernel(const __grid_constant__ KProg P0, const BuildArgs a) {
     __shared__ double x1s[BUILD_ROWS * MAX_NDIM];
     __shared__ double x2s[BUILD_COLS * MAX_NDIM];
+    __shared__ KProg Pb;
     const int tid = threadIdx.x;
+    if (a.progs != nullptr) {
+        const int* src = reinterpret_cast<const int*>(a.progs + blockIdx.z);
+        int* dst = reinterpret_cast<int*>(&Pb);
+        for (int i = tid; i < (int)(sizeof(KProg) / sizeof(int)); i += 256) dst[i] = src[i];
+    }
+    const KProg& P = (a.progs != nullptr) ? Pb : P0;
+    double* const outb = a.out + (int64_t)blockIdx.z * a.batch_stride;
     const int64_t r0 = (int64_t)blockIdx.y * BUILD_ROWS;
     const int64_t c0 = (int64_t)blockIdx.x * BUILD_COLS;
     const int nd = a.ndim;
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(256) build_rect_kernel(const __grid_constant__
             }
         }
         const int64_t c = c0 + cl;
-        double* dst = a.out + r * a.ld + c;
+        double* dst = outb + r * a.ld + c;
         if (c + 1 < a.cols_pad && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
             *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
         } else {
@@ -240,6 +251,8 @@ struct Args {
     int lower;      // 1: square C, only tiles with tj <= ti are computed
     // generator (beta_mode 2): C(i,j) = k(x_{row0+i}, x_{col0+j}) + [row==col] diag
     const double* X; const double* diag; int ndim; int64_t n_valid; int64_t row0, col0;
+    // batched launch (blockIdx.y = problem): element strides between problems
+    int batch; int64_t strideA, strideB, strideC;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_ptr, const void* gptr) {
@@ -295,8 +308,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
         ti = (int)blockIdx.x % g.tiles_m;
         tj = (int)blockIdx.x / g.tiles_m;
     }
-    const double* Ag = g.A + (int64_t)ti * BM * g.lda;
-    const double* Bg = g.B + (int64_t)tj * BN * g.ldb;
+    const int64_t bz = blockIdx.y;
+    const double* Ag = g.A + bz * g.strideA + (int64_t)ti * BM * g.lda;
+    const double* Bg = g.B + bz * g.strideB + (int64_t)tj * BN * g.ldb;
 
     // each thread copies 4 x 16 B of A and 4 x 16 B of B per stage
     const int lrow = tid >> 3;        // 0..31  (+32 per i)
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
         const int64_t r = crow0 + mi * 8;
-        double* crow = g.C + r * g.ldc;
+        double* crow = g.C + bz * g.strideC + r * g.ldc;
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
             const int64_t c = ccol0 + ni * 8;
@@ -402,7 +416,8 @@ static void launch(b200gp_ctx* ctx, const KProg& P, const Args& g) {
     else
         ntiles = (int64_t)g.tiles_m * g.tiles_n;
     if (ntiles <= 0) return;
-    gemm_nt_kernel<<<(unsigned)ntiles, THREADS, SMEM_BYTES, ctx->stream>>>(P, g);
+    dim3 grid((unsigned)ntiles, (unsigned)(g.batch > 0 ? g.batch : 1));
+    gemm_nt_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(P, g);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -415,11 +430,13 @@ static const KProg& empty_prog() {
 
 static void gemm_nt(b200gp_ctx* ctx, double* C, int64_t ldc, const double* A, int64_t lda,
                     const double* B, int64_t ldb, int tiles_m, int tiles_n, int K, double alpha,
-                    int beta_mode, int lower) {
+                    int beta_mode, int lower, int batch = 1, int64_t strideA = 0, int64_t strideB = 0,
+                    int64_t strideC = 0) {
     gemm::Args g{};
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
     g.tiles_m = tiles_m; g.tiles_n = tiles_n; g.K = K; g.alpha = alpha;
     g.beta_mode = beta_mode; g.lower = lower;
+    g.batch = batch; g.strideA = strideA; g.strideB = strideB; g.strideC = strideC;
     gemm::launch(ctx, empty_prog(), g);
 }
 
@@ -433,8 +450,12 @@ static void gemm_nt(b200gp_ctx* ctx, double* C, int64_t ldc, const double* A, in
 constexpr int PF_SMEM = (TILE * PF_LD + 4 * TILE + TILE) * (int)sizeof(double);
 
 __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel(double* A, int64_t lda, double* linv,
-                                                                    int* info, int global_off) {
+                                                                    int* info, int global_off, int64_t strideA,
+                                                                    int64_t stride_linv) {
     extern __shared__ __align__(16) double sm[];
+    A += (int64_t)blockIdx.x * strideA;          // batched launch: one CTA per problem
+    linv += (int64_t)blockIdx.x * stride_linv;
+    info += blockIdx.x;
     double* S = sm;                     // TILE x PF_LD
     double* red = sm + TILE * PF_LD;    // 4 x TILE partial sums
     double* tmp = red + 4 * TILE;       // TILE
@@ -508,13 +529,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel(double* A, i
     }
 }
 
-static void potf2(b200gp_ctx* ctx, double* A, int64_t lda, double* linv, int* info, int global_off) {
+static void potf2(b200gp_ctx* ctx, double* A, int64_t lda, double* linv, int* info, int global_off, int batch = 1,
+                  int64_t strideA = 0, int64_t stride_linv = 0) {
     static bool attr = false;
     if (!attr) {
         CUDA_CHECK(cudaFuncSetAttribute(potf2_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
         attr = true;
     }
-    potf2_trtri_kernel<<<1, PF_THREADS, PF_SMEM, ctx->stream>>>(A, lda, linv, info, global_off);
+    potf2_trtri_kernel<<<batch, PF_THREADS, PF_SMEM, ctx->stream>>>(A, lda, linv, info, global_off, strideA, stride_linv);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -524,6 +546,52 @@ static void potf2(b200gp_ctx* ctx, double* A, int64_t lda, double* linv, int* in
 // =============================================================================================
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
 
+// factor the panel of columns [k0, k0+kb) over all rows >= k0: inner 128-wide left-looking sweep
+void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t np = s->np, ld = s->np;
+    double* M = s->mat;
+    for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
+        const int64_t c0 = k0 + j0;
+        if (j0 > 0) {
+            // column block c0 -= (already factored panel columns) x (rows c0.. of them)^T
+            gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld,
+                    (int)((np - c0) / TILE), 1, (int)j0, -1.0, 1, 0);
+        }
+        potf2(ctx, M + c0 * ld + c0, ld, s->linv + (c0 / TILE) * TILE * TILE, s->info_dev, (int)c0);
+        if (c0 + TILE < np) {
+            // rows below: X = A * inv(L_jj)^T, in place (one tile column, K = 128)
+            gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld,
+                    s->linv + (c0 / TILE) * TILE * TILE, TILE, (int)((np - c0 - TILE) / TILE), 1, TILE,
+                    1.0, 0, 0);
+        }
+    }
+}
+
+// generate K (+ diag, identity pad) for rows [r0, np), columns [c0, c0+ncols) straight into the matrix
+void dense_build_region(b200gp_dense* s, int64_t r0, int64_t c0, int64_t ncols) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t np = s->np, ld = s->np;
+    BuildArgs a{};
+    a.X1 = s->X_dev + r0 * s->ndim;
+    a.X2 = s->X_dev + c0 * s->ndim;
+    a.diag = s->diag_dev; a.out = s->mat + r0 * ld + c0; a.ld = ld;
+    a.n1 = (s->n > r0) ? (s->n - r0) : 0;
+    a.n2 = (s->n > c0) ? ((s->n - c0 < ncols) ? (s->n - c0) : ncols) : 0;
+    a.rows_pad = np - r0; a.cols_pad = ncols;
+    a.row_off = r0; a.col_off = c0; a.ndim = s->ndim; a.pad_identity = 1;
+    dim3 grid((unsigned)((ncols + BUILD_COLS - 1) / BUILD_COLS), (unsigned)((np - r0 + BUILD_ROWS - 1) / BUILD_ROWS));
+    ProfTimer t(ctx, &ctx->prof.build_ms);
+    build_rect_kernel<<<grid, 256, 0, ctx->stream>>>(s->prog, a);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    ctx->prof.build_bytes += 8.0 * (double)(np - r0) * (double)ncols;
+}
+
+double dense_kernel_diag_value(const KProg& P) { return kprog_eval(P, 0.0, 0.0); }
+
+void dense_factor_ozaki(b200gp_dense* s, int S);  // ozaki.cu
+
 void dense_factor_inplace(b200gp_dense* s, bool generate) {
     b200gp_ctx* ctx = s->ctx;
     const int64_t np = s->np, ld = s->np;
@@ -532,44 +600,25 @@ void dense_factor_inplace(b200gp_dense* s, bool generate) {
     NB = (NB / TILE) * TILE;
     double* M = s->mat;
 
+    if (generate && ctx->oz_slices > 0 && np >= ctx->oz_min_n) {
+        dense_factor_ozaki(s, (int)ctx->oz_slices);
+        return;
+    }
+
     set_int_kernel<<<1, 1, 0, ctx->stream>>>(s->info_dev, INT_MAX);
     ctx->launches++;
 
     if (generate) {
         // panel 0 (all rows, first NB columns) is the only part of K ever written by a stand-alone
         // build; every other tile is generated inside the first trailing update's epilogue.
-        const int64_t kb0 = (NB < np) ? NB : np;
-        BuildArgs a{};
-        a.X1 = s->X_dev; a.X2 = s->X_dev; a.diag = s->diag_dev; a.out = M; a.ld = ld;
-        a.n1 = s->n; a.n2 = (s->n < kb0) ? s->n : kb0; a.rows_pad = np; a.cols_pad = kb0;
-        a.row_off = 0; a.col_off = 0; a.ndim = s->ndim; a.pad_identity = 1;
-        dim3 grid((unsigned)((kb0 + BUILD_COLS - 1) / BUILD_COLS), (unsigned)((np + BUILD_ROWS - 1) / BUILD_ROWS));
-        ProfTimer t(ctx, &ctx->prof.build_ms);
-        build_rect_kernel<<<grid, 256, 0, ctx->stream>>>(s->prog, a);
-        CUDA_CHECK(cudaGetLastError());
-        ctx->launches++;
-        ctx->prof.build_bytes += 8.0 * (double)np * (double)kb0;
+        dense_build_region(s, 0, 0, (NB < np) ? NB : np);
     }
 
     for (int64_t k0 = 0; k0 < np; k0 += NB) {
         const int64_t kb = (NB < np - k0) ? NB : (np - k0);
         {
             ProfTimer t(ctx, &ctx->prof.panel_ms);
-            for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
-                const int64_t c0 = k0 + j0;
-                if (j0 > 0) {
-                    // column block c0 -= (already factored panel columns) x (rows c0.. of them)^T
-                    gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld,
-                            (int)((np - c0) / TILE), 1, (int)j0, -1.0, 1, 0);
-                }
-                potf2(ctx, M + c0 * ld + c0, ld, s->linv + (c0 / TILE) * TILE * TILE, s->info_dev, (int)c0);
-                if (c0 + TILE < np) {
-                    // rows below: X = A * inv(L_jj)^T, in place (one tile column, K = 128)
-                    gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld,
-                            s->linv + (c0 / TILE) * TILE * TILE, TILE, (int)((np - c0 - TILE) / TILE), 1, TILE,
-                            1.0, 0, 0);
-                }
-            }
+            dense_panel_factor(s, k0, kb);
         }
         const int64_t r0 = k0 + kb;
         if (r0 < np) {
@@ -600,8 +649,11 @@ void dense_factor_inplace(b200gp_dense* s, bool generate) {
 // =============================================================================================
 // out[0] = sum_{i<n} f(v[i*stride]) with f = log (mode 0) or square (mode 1); single block,
 // fixed-shape tree so the result is deterministic.
-__global__ void __launch_bounds__(1024) reduce_kernel(const double* v, int64_t stride, int64_t n, int mode, double* out) {
+__global__ void __launch_bounds__(1024) reduce_kernel(const double* v, int64_t stride, int64_t n, int mode, double* out,
+                                                      int64_t batch_stride) {
     __shared__ double sh[1024];
+    v += (int64_t)blockIdx.x * batch_stride;
+    out += blockIdx.x;
     double acc = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += 1024) {
         const double x = v[i * stride];
@@ -618,7 +670,7 @@ __global__ void __launch_bounds__(1024) reduce_kernel(const double* v, int64_t s
 
 static double reduce_to_host(b200gp_ctx* ctx, const double* v, int64_t stride, int64_t n, int mode) {
     double* d = (double*)ctx->alloc(sizeof(double));
-    reduce_kernel<<<1, 1024, 0, ctx->stream>>>(v, stride, n, mode, d);
+    reduce_kernel<<<1, 1024, 0, ctx->stream>>>(v, stride, n, mode, d, 0);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     double h = 0.0;
@@ -638,10 +690,14 @@ double dense_sumsq_dev(b200gp_ctx* ctx, const double* x_dev, int64_t n) { return
 // =============================================================================================
 __global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ mat, int64_t ld,
                                                       const double* __restrict__ linv_j, double* y, double* x,
-                                                      int j, int64_t np) {
+                                                      int j, int64_t np, int64_t stride_mat, int64_t stride_linv) {
     __shared__ __align__(32) double ys[TILE];
     __shared__ __align__(32) double xs[TILE];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    mat += (int64_t)blockIdx.y * stride_mat;      // batched launch
+    linv_j += (int64_t)blockIdx.y * stride_linv;
+    y += (int64_t)blockIdx.y * np;
+    x += (int64_t)blockIdx.y * np;
     if (tid < TILE) ys[tid] = y[(int64_t)j * TILE + tid];
     __syncthreads();
     for (int r = warp; r < TILE; r += 8) {
@@ -708,7 +764,7 @@ void dense_solve_vec_dev(b200gp_dense* s, double* y_dev, double* x_dev, bool tra
             const int64_t rows_below = s->np - (int64_t)(j + 1) * TILE;
             const unsigned grid = (unsigned)((rows_below + 63) / 64);
             trsv_fwd_step<<<grid ? grid : 1, 256, 0, ctx->stream>>>(s->mat, s->np, s->linv + (int64_t)j * TILE * TILE,
-                                                                    y_dev, x_dev, j, s->np);
+                                                                    y_dev, x_dev, j, s->np, 0, 0);
             ctx->launches++;
         }
     } else {
@@ -1132,3 +1188,140 @@ int b200gp_dense_log_probability_dev(b200gp_ctx* ctx, const double* prog, int n_
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// batched log_probability over a hyper-parameter grid (BASELINE config 5): B problems share X, diag, y and
+// differ in their kernel program.  Every kernel of the blocked factorisation is launched once for the
+// whole batch (grid.y / grid.x = problem), so the launch chain is paid once per batch, not per problem.
+// =============================================================================================
+__global__ void finish_logp_kernel(const double* ld_half, const double* sumsq, const int* info, int64_t n, int64_t nb,
+                                   double* logp) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    double lp = -0.5 * sumsq[b] - (ld_half[b] + 0.5 * (double)n * log(2.0 * M_PI));   // gp.py:313-316
+    if (info[b] != INT_MAX || !isfinite(lp)) lp = -INFINITY;
+    logp[b] = lp;
+}
+__global__ void fill_int_kernel(int* p, int v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void replicate_pad_kernel(const double* src, int64_t n, double* dst, int64_t np, int64_t nbatch) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= np * nbatch) return;
+    const int64_t i = idx % np;
+    dst[idx] = (i < n) ? src[i] : 0.0;
+}
+
+static void dense_logp_batched_chunk(b200gp_ctx* ctx, const KProg* progs_dev, int64_t B, const double* X_dev, int64_t n,
+                                     int ndim, const double* diag_dev, const double* resid_dev, double* logp_dev) {
+    const int64_t np = ((n + TILE - 1) / TILE) * TILE, ld = np;
+    const int nblk = (int)(np / TILE);
+    const int64_t smat = np * np, slinv = (int64_t)nblk * TILE * TILE;
+    double* M = (double*)ctx->alloc((size_t)B * smat * 8);
+    double* linv = (double*)ctx->alloc((size_t)B * slinv * 8);
+    int* info = (int*)ctx->alloc((size_t)B * sizeof(int));
+    double* y = (double*)ctx->alloc((size_t)B * np * 8);
+    double* x = (double*)ctx->alloc((size_t)B * np * 8);
+    double* red = (double*)ctx->alloc((size_t)2 * B * 8);
+    fill_int_kernel<<<nblocks(B, 256), 256, 0, ctx->stream>>>(info, INT_MAX, B);
+    ctx->launches++;
+    {   // K_b = k_b(X, X) + diag for every problem (lower triangle is what the factorisation reads)
+        BuildArgs a{};
+        a.X1 = X_dev; a.X2 = X_dev; a.diag = diag_dev; a.out = M; a.ld = ld;
+        a.n1 = n; a.n2 = n; a.rows_pad = np; a.cols_pad = np; a.ndim = ndim; a.pad_identity = 1;
+        a.progs = progs_dev; a.batch_stride = smat;
+        dim3 grid((unsigned)((np + BUILD_COLS - 1) / BUILD_COLS), (unsigned)((np + BUILD_ROWS - 1) / BUILD_ROWS), (unsigned)B);
+        ProfTimer t(ctx, &ctx->prof.build_ms);
+        build_rect_kernel<<<grid, 256, 0, ctx->stream>>>(empty_prog(), a);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+        ctx->prof.build_bytes += 8.0 * (double)B * (double)np * (double)np;
+    }
+    int64_t NB = ctx->nb_batched;
+    for (int64_t k0 = 0; k0 < np; k0 += NB) {
+        const int64_t kb = (NB < np - k0) ? NB : (np - k0);
+        {
+            ProfTimer t(ctx, &ctx->prof.panel_ms);
+            for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
+                const int64_t c0 = k0 + j0;
+                if (j0 > 0)
+                    gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld, (int)((np - c0) / TILE), 1,
+                            (int)j0, -1.0, 1, 0, (int)B, smat, smat, smat);
+                potf2(ctx, M + c0 * ld + c0, ld, linv + (c0 / TILE) * TILE * TILE, info, (int)c0, (int)B, smat, slinv);
+                if (c0 + TILE < np)
+                    gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld, linv + (c0 / TILE) * TILE * TILE,
+                            TILE, (int)((np - c0 - TILE) / TILE), 1, TILE, 1.0, 0, 0, (int)B, smat, slinv, smat);
+            }
+        }
+        const int64_t r0 = k0 + kb;
+        if (r0 < np) {
+            const int T = (int)((np - r0) / TILE);
+            ProfTimer t(ctx, &ctx->prof.syrk_ms);
+            gemm_nt(ctx, M + r0 * ld + r0, ld, M + r0 * ld + k0, ld, M + r0 * ld + k0, ld, T, T, (int)kb, -1.0, 1, 1, (int)B,
+                    smat, smat, smat);
+            ctx->prof.syrk_flop += (double)B * T * (T + 1.0) / 2.0 * 2.0 * TILE * TILE * (double)kb;
+            ctx->prof.syrk_launches++;
+        }
+    }
+    // forward solves for all problems at once
+    replicate_pad_kernel<<<nblocks(B * np, 256), 256, 0, ctx->stream>>>(resid_dev, n, y, np, B);
+    ctx->launches++;
+    {
+        ProfTimer t(ctx, &ctx->prof.solve_ms);
+        for (int j = 0; j < nblk; ++j) {
+            const int64_t rows_below = np - (int64_t)(j + 1) * TILE;
+            const unsigned gx = (unsigned)((rows_below + 63) / 64);
+            dim3 grid(gx ? gx : 1, (unsigned)B);
+            trsv_fwd_step<<<grid, 256, 0, ctx->stream>>>(M, np, linv + (int64_t)j * TILE * TILE, y, x, j, np, smat, slinv);
+            ctx->launches++;
+        }
+    }
+    reduce_kernel<<<(unsigned)B, 1024, 0, ctx->stream>>>(M, np + 1, n, 0, red, smat);       // sum log L_ii
+    reduce_kernel<<<(unsigned)B, 1024, 0, ctx->stream>>>(x, 1, n, 1, red + B, np);          // |alpha|^2
+    finish_logp_kernel<<<nblocks(B, 256), 256, 0, ctx->stream>>>(red, red + B, info, n, B, logp_dev);
+    ctx->launches += 3;
+    CUDA_CHECK(cudaGetLastError());
+    ctx->release(M, (size_t)B * smat * 8);
+    ctx->release(linv, (size_t)B * slinv * 8);
+    ctx->release(info, (size_t)B * sizeof(int));
+    ctx->release(y, (size_t)B * np * 8);
+    ctx->release(x, (size_t)B * np * 8);
+    ctx->release(red, (size_t)2 * B * 8);
+}
+
+extern "C" int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const double* progs, int n_instr, int64_t nbatch,
+                                                    const double* X, int64_t n, int ndim, const double* diag,
+                                                    const double* resid, double* logp) {
+    API_BEGIN(ctx)
+    if (nbatch <= 0 || n <= 0) throw GpError("batched log_probability: empty batch");
+    if (ndim < 1 || ndim > MAX_NDIM) throw GpError("batched log_probability: ndim must be in [1, 16]");
+    std::vector<KProg> hp((size_t)nbatch);
+    for (int64_t b = 0; b < nbatch; ++b) hp[b] = parse_prog(progs + (size_t)b * n_instr * B200GP_PROG_STRIDE, n_instr);
+    KProg* dp = (KProg*)_ctx->alloc((size_t)nbatch * sizeof(KProg));
+    double* dX = (double*)_ctx->alloc((size_t)n * ndim * 8);
+    double* dd = (double*)_ctx->alloc((size_t)n * 8);
+    double* dr = (double*)_ctx->alloc((size_t)n * 8);
+    double* dl = (double*)_ctx->alloc((size_t)nbatch * 8);
+    CUDA_CHECK(cudaMemcpyAsync(dp, hp.data(), (size_t)nbatch * sizeof(KProg), cudaMemcpyHostToDevice, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dX, X, (size_t)n * ndim * 8, cudaMemcpyDefault, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dd, diag, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dr, resid, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));  // hp is host-stack memory
+    const int64_t np = ((n + TILE - 1) / TILE) * TILE;
+    int64_t chunk = (int64_t)(((size_t)40 << 30) / ((size_t)np * np * 8));   // <= 40 GiB of matrices per chunk
+    if (chunk < 1) chunk = 1;
+    if (chunk > 4096) chunk = 4096;
+    for (int64_t b0 = 0; b0 < nbatch; b0 += chunk) {
+        const int64_t B = (chunk < nbatch - b0) ? chunk : (nbatch - b0);
+        dense_logp_batched_chunk(_ctx, dp + b0, B, dX, n, ndim, dd, dr, dl + b0);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(logp, dl, (size_t)nbatch * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(dp, (size_t)nbatch * sizeof(KProg));
+    _ctx->release(dX, (size_t)n * ndim * 8);
+    _ctx->release(dd, (size_t)n * 8);
+    _ctx->release(dr, (size_t)n * 8);
+    _ctx->release(dl, (size_t)nbatch * 8);
+    API_END
+}

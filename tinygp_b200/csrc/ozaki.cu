@@ -1,0 +1,481 @@
+// Fixed-point (Ozaki-style) Cholesky update on the 5th-gen tensor cores: tcgen05.mma kind::i8, TMA-fed
+// operands, int32 accumulators in TMEM.
+//
+// tcgen05 has no f64 kind, and the DMMA pipe sustains only ~30 TFLOP/s, so the N^3/3 flop of
+// `linalg.cholesky` (src/tinygp/solvers/direct.py:53) are moved onto the int8 tensor pipe:
+//
+//   * |L_ik| <= sqrt(K_ii) for a Cholesky factor, so every row of L has the a-priori scale
+//     rs_i = 2^ceil(log2 sqrt(K_ii)) and  x_ik = L_ik / rs_i  lies in [-1, 1].
+//   * x is cut into S signed 7-bit digits (first digit 6 bits):  x = sum_s q_s 2^-(6+7s) , q_s in int8,
+//     with exact remainders (every step is exact in fp64).  Digits are stored as S int8 planes.
+//   * sum_k L_ik L_jk = rs_i rs_j sum_{s,t} 2^-(12+7(s+t)) (q_s[i,:] . q_t[j,:])  where each integer dot
+//     product is EXACT in int32; pairs with equal s+t = g share one TMEM accumulator, pairs with
+//     s+t >= S are dropped (<= 2^-(6+7(S-1)) relative to the row scale: 2^-55 for S = 8).
+//   * left-looking block columns: column block J is generated (K tiles), then
+//     C -= L[rows, 0:c0] L[c0:c0+nb, 0:c0]^T runs with K = c0 (all previous panels at once), so each C tile
+//     is converted int32 -> fp64 only S times in total; then the panel is factored in fp64 on the DMMA
+//     path (dense.cu) and its digits are cut.
+//
+// Kernel (one CTA per 128 x 256 tile of C, 192 threads):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor.2d, 128-byte swizzle, 4-stage mbarrier ring)
+//   warp 1   : TMEM alloc + single-thread tcgen05.mma issuer (M=128, N=256, K=32 per instruction)
+//   warps 2-5: epilogue: tcgen05.ld 32x32b -> cvt -> C -= rs_i rs_j 2^-(12+7g) G_g  (fp64 RMW on the tile)
+// Two 256-column accumulators ping-pong so the epilogue of group g overlaps the MMAs of group g+1.
+#include "common.cuh"
+#include <cuda.h>
+#include <limits.h>
+
+namespace oz {
+
+constexpr int TM = 128;          // tile rows  (UMMA M)
+constexpr int TN = 256;          // tile cols  (UMMA N)
+constexpr int KC = 128;          // int8 K elements per pipeline stage (= one 128-byte swizzle row)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TM * KC;             // 16 KiB
+constexpr int B_BYTES = TN * KC;             // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;    // bounded waits: a protocol bug must not hang the GPU
+
+// instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): c=S32, a=b=INT8, K-major, N=256, M=128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+struct Args {
+    double* C; int64_t ldc;            // fp64 tile base: C[(row0 + i) * ldc + col0 + j]
+    const double* rs;                  // row scales (power of two), indexed by global row
+    int64_t row0, col0;                // global row / col of tile (0,0)
+    int tiles_m, tiles_n;
+    int K;                             // int8 K extent (multiple of KC), operands start at k = 0
+    int S;                             // number of digit planes used
+    int64_t b_row0;                    // first global row of the B operand (= col0 for the Cholesky update)
+    int64_t n_rows;                    // rows of the matrix (for masking the last column tile)
+    int skip_upper;                    // skip tiles entirely above the diagonal
+    int* error_flag;
+};
+
+struct Maps { CUtensorMap plane[8]; };
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// returns false on timeout (the caller raises the abort flag)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+    for (uint32_t it = 0; it < SPIN_LIMIT; ++it) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if ((it & 1023u) == 1023u && *abort_flag) return false;
+    }
+    *abort_flag = 1;
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+// K-major operand, 128-byte swizzle: SBO = 1024 B between 8-row groups, LBO unused (=1), version 1 (sm100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// ---- the tile kernel ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_constant__ Maps maps, const Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;                  // [STAGES]
+    uint64_t* empty = bars + STAGES;        // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;    // [2]
+    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = (int)blockIdx.x % g.tiles_m, tj = (int)blockIdx.x / g.tiles_m;
+    const int64_t grow0 = g.row0 + (int64_t)ti * TM;   // global row of tile row 0
+    const int64_t gcol0 = g.col0 + (int64_t)tj * TN;   // global col of tile col 0
+    if (g.skip_upper && grow0 + TM - 1 < gcol0) return;  // whole tile above the diagonal (uniform per CTA)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tfull + 0, 1); mbar_init(tfull + 1, 1);
+        mbar_init(tempty + 0, 4); mbar_init(tempty + 1, 4);
+        *abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (two 256-column int32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int KT = g.K / KC;
+    const int S = g.S;
+    const int64_t brow0 = g.b_row0 + (int64_t)tj * TN;  // global row of the B operand's first row
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int gi = 0; gi < S && ok; ++gi) {
+                for (int s = 0; s <= gi && ok; ++s) {
+                    const int t = gi - s;
+                    for (int kc = 0; kc < KT; ++kc) {
+                        if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; break; }
+                        uint8_t* a_dst = smem + stage * STAGE_BYTES;
+                        uint8_t* b_dst = a_dst + A_BYTES;
+                        mbar_expect_tx(full + stage, STAGE_BYTES);
+                        tma_load_2d(a_dst, &maps.plane[s], full + stage, kc * KC, (int)grow0);
+                        tma_load_2d(b_dst, &maps.plane[t], full + stage, kc * KC, (int)brow0);
+                        tma_load_2d(b_dst + A_BYTES, &maps.plane[t], full + stage, kc * KC, (int)brow0 + 128);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int gi = 0; gi < S && ok; ++gi) {
+                const int acc = gi & 1;
+                if (gi >= 2) {  // the epilogue must have drained this accumulator (group gi-2)
+                    if (!mbar_wait(tempty + acc, ((gi >> 1) - 1) & 1, abort_flag)) { ok = false; break; }
+                    tc_fence_after();
+                }
+                const uint32_t tacc = tmem_base + (uint32_t)acc * TN;
+                uint32_t accumulate = 0;
+                for (int s = 0; s <= gi && ok; ++s) {
+                    for (int kc = 0; kc < KT; ++kc) {
+                        if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < KC / 32; ++kk) {
+                            umma_i8(tacc, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), accumulate);
+                            accumulate = 1;
+                        }
+                        tc_commit(empty + stage);  // frees the smem slot when these MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                if (ok) tc_commit(tfull + acc);    // accumulator of group gi complete
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;            // tile row owned by this thread
+        const int64_t gr = grow0 + row;
+        const double rsi = g.rs[gr];
+        double* crow = g.C + gr * g.ldc;
+        bool ok = true;
+        for (int gi = 0; gi < S && ok; ++gi) {
+            const int acc = gi & 1;
+            if (!mbar_wait(tfull + acc, (gi >> 1) & 1, abort_flag)) { ok = false; break; }
+            tc_fence_after();
+            // weight 2^-(12 + 7 gi), exact power of two
+            const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
+            const double sc = -(rsi * wg);
+#pragma unroll 1
+            for (int cb = 0; cb < TN / 32; ++cb) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb * 32), r);
+                const int64_t gc = gcol0 + cb * 32;
+                if (gc < g.n_rows) {  // column tiles may stick out past the matrix on the last panel
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
+                        double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
+                        cv.x = fma(sc * rj.x, (double)(int)r[j], cv.x);
+                        cv.y = fma(sc * rj.y, (double)(int)r[j + 1], cv.y);
+                        *reinterpret_cast<double2*>(crow + gc + j) = cv;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && *abort_flag) atomicExch(g.error_flag, 1);
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---- digit cutting -------------------------------------------------------------------------------
+// planes[s][row * ldq + col] for rows [r0, np), cols [c0, c0 + ncols); 16 columns per thread
+__global__ void __launch_bounds__(256) cut_digits_kernel(const double* __restrict__ mat, int64_t ld, const double* __restrict__ rs,
+                                                         int64_t r0, int64_t nrows, int64_t c0, int64_t ncols,
+                                                         int8_t* planes, int64_t plane_stride, int64_t ldq, int S) {
+    const int64_t groups_per_row = ncols / 16;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * groups_per_row) return;
+    const int64_t row = r0 + idx / groups_per_row;
+    const int64_t col = c0 + (idx % groups_per_row) * 16;
+    const double inv = 1.0 / rs[row];  // power of two: exact
+    double x[16];
+    const double4* src = reinterpret_cast<const double4*>(mat + row * ld + col);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const double4 d = src[v];
+        x[4 * v + 0] = d.x * inv * 64.0; x[4 * v + 1] = d.y * inv * 64.0;
+        x[4 * v + 2] = d.z * inv * 64.0; x[4 * v + 3] = d.w * inv * 64.0;
+    }
+    for (int s = 0; s < S; ++s) {
+        uint32_t packed[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            uint32_t wv = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                double& xx = x[4 * v + e];
+                double qd = rint(xx);
+                qd = fmin(fmax(qd, -127.0), 127.0);   // |x| <= 64 (+ rounding) by construction
+                xx = (xx - qd) * 128.0;               // exact
+                wv |= ((uint32_t)(uint8_t)(int8_t)(int)qd) << (8 * e);
+            }
+            packed[v] = wv;
+        }
+        *reinterpret_cast<uint4*>(planes + (int64_t)s * plane_stride + row * ldq + col) =
+            make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+
+// rs[i] = 2^ceil(log2 sqrt(K_ii)), K_ii = kdiag + diag[i]; identity pad rows get 1
+__global__ void row_scale_kernel(double kdiag, const double* __restrict__ diag, int64_t n, int64_t np, double* rs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    double v = 1.0;
+    if (i < n) {
+        const double kii = kdiag + diag[i];
+        if (kii > 0.0 && isfinite(kii)) {
+            const int e = ilogb(kii);                        // 2^e <= kii < 2^(e+1)
+            const int h = (e + 1 >= 0) ? (e + 2) / 2 : -((-(e + 1)) / 2);  // ceil((e+1)/2)
+            v = scalbn(1.0, h);
+        }
+    }
+    rs[i] = v;
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p)
+            throw GpError("cuTensorMapEncodeTiled is not available from the driver");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// planes: S contiguous int8 matrices [rows][ldq]; box = 128 bytes (k) x 128 rows, 128-byte swizzle
+Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, int S) {
+    Maps m{};
+    EncodeTiledFn enc = get_encode();
+    for (int s = 0; s < 8; ++s) {
+        const int sp = (s < S) ? s : 0;
+        cuuint64_t dims[2] = {(cuuint64_t)ldq, (cuuint64_t)rows};
+        cuuint64_t strides[1] = {(cuuint64_t)ldq};
+        cuuint32_t box[2] = {(cuuint32_t)KC, 128u};
+        cuuint32_t estr[2] = {1u, 1u};
+        CUresult r = enc(&m.plane[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes + (int64_t)sp * plane_stride, dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) throw GpError("cuTensorMapEncodeTiled failed");
+    }
+    return m;
+}
+
+void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
+    static bool attr = false;
+    if (!attr) {
+        CUDA_CHECK(cudaFuncSetAttribute(i8_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr = true;
+    }
+    const int64_t nt = (int64_t)a.tiles_m * a.tiles_n;
+    if (nt <= 0 || a.K <= 0) return;
+    i8_update_kernel<<<(unsigned)nt, THREADS, SMEM_BYTES, ctx->stream>>>(maps, a);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+}  // namespace oz
+
+// ================================================================================================
+// left-looking factorisation driver
+// ================================================================================================
+void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb);                       // dense.cu
+void dense_build_region(b200gp_dense* s, int64_t r0, int64_t c0, int64_t ncols);          // dense.cu
+double dense_kernel_diag_value(const KProg& P);                                           // dense.cu
+
+void dense_factor_ozaki(b200gp_dense* s, int S) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t np = s->np, ld = np;
+    int64_t NB = ctx->nb;
+    if (NB < 256) NB = 256;
+    NB = (NB / 256) * 256;
+    if (S < 2) S = 2;
+    if (S > 8) S = 8;
+
+    const size_t plane_stride = (size_t)np * np;
+    int8_t* planes = (int8_t*)ctx->alloc(plane_stride * S);
+    double* rs = (double*)ctx->alloc((size_t)np * 8);
+    int* err = (int*)ctx->alloc(sizeof(int));
+    CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), ctx->stream));
+    int big = INT_MAX;
+    CUDA_CHECK(cudaMemcpyAsync(s->info_dev, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    oz::row_scale_kernel<<<(unsigned)((np + 255) / 256), 256, 0, ctx->stream>>>(dense_kernel_diag_value(s->prog), s->diag_dev,
+                                                                               s->n, np, rs);
+    ctx->launches++;
+    oz::Maps maps = oz::make_maps(planes, (int64_t)plane_stride, np, np, S);
+
+    for (int64_t c0 = 0; c0 < np; c0 += NB) {
+        const int64_t kb = (NB < np - c0) ? NB : (np - c0);
+        // (1) generate this block column of K (rows c0.., cols c0..c0+kb)
+        dense_build_region(s, c0, c0, kb);
+        // (2) C -= L[c0:, 0:c0] L[c0:c0+kb, 0:c0]^T on the int8 tensor pipe
+        if (c0 > 0) {
+            oz::Args a{};
+            a.C = s->mat; a.ldc = ld; a.rs = rs;
+            a.row0 = c0; a.col0 = c0; a.b_row0 = c0;
+            a.tiles_m = (int)((np - c0) / oz::TM);
+            a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
+            a.K = (int)c0; a.S = S; a.n_rows = np; a.skip_upper = 1; a.error_flag = err;
+            ProfTimer t(ctx, &ctx->prof.syrk_ms);
+            oz::launch_update(ctx, maps, a);
+            const double rows = (double)(np - c0);
+            ctx->prof.syrk_flop += 2.0 * rows * (double)kb * (double)c0;  // fp64-equivalent flop of this update
+            ctx->prof.syrk_launches++;
+        }
+        // (3) factor the panel in fp64 (DMMA path)
+        {
+            ProfTimer t(ctx, &ctx->prof.panel_ms);
+            dense_panel_factor(s, c0, kb);
+        }
+        // (4) cut the digits of the rows below the diagonal block
+        if (c0 + kb < np) {
+            const int64_t nrows = np - (c0 + kb);
+            const int64_t nthreads = nrows * (kb / 16);
+            ProfTimer t(ctx, &ctx->prof.build_ms);
+            oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
+                s->mat, ld, rs, c0 + kb, nrows, c0, kb, planes, (int64_t)plane_stride, np, S);
+            ctx->launches++;
+        }
+    }
+    CUDA_CHECK(cudaGetLastError());
+    int herr = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&s->info, s->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->release(planes, plane_stride * S);
+    ctx->release(rs, (size_t)np * 8);
+    ctx->release(err, sizeof(int));
+    if (herr) throw GpError("int8 tensor update: pipeline wait timed out (internal protocol error)");
+    if (s->info == INT_MAX) s->info = 0;
+    if (s->info > s->n) s->info = 0;
+}
+
+// ---- diagnostics entry point: C -= sum_{s+t<S} 2^-(12+7(s+t)) rs_i rs_j Q_s[rows] Q_t[rows_b]^T ----------
+extern "C" int b200gp_i8_update_test(b200gp_ctx* ctx, const int8_t* planes_host, int S, int64_t rows, int64_t K,
+                                     const double* rs_host, double* C_host /* rows x rows, in/out */) {
+    API_BEGIN(ctx)
+    if (rows % 256 || K % 128 || S < 1 || S > 8) throw GpError("i8 test: rows % 256 == 0, K % 128 == 0, 1 <= S <= 8");
+    const size_t pstride = (size_t)rows * K;
+    int8_t* planes = (int8_t*)_ctx->alloc(pstride * S);
+    double* rs = (double*)_ctx->alloc((size_t)rows * 8);
+    double* C = (double*)_ctx->alloc((size_t)rows * rows * 8);
+    int* err = (int*)_ctx->alloc(sizeof(int));
+    CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(planes, planes_host, pstride * S, cudaMemcpyHostToDevice, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(rs, rs_host, (size_t)rows * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(C, C_host, (size_t)rows * rows * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    oz::Maps maps = oz::make_maps(planes, (int64_t)pstride, rows, K, S);
+    oz::Args a{};
+    a.C = C; a.ldc = rows; a.rs = rs; a.row0 = 0; a.col0 = 0; a.b_row0 = 0;
+    a.tiles_m = (int)(rows / oz::TM); a.tiles_n = (int)(rows / oz::TN);
+    a.K = (int)K; a.S = S; a.n_rows = rows; a.skip_upper = 0; a.error_flag = err;
+    oz::launch_update(_ctx, maps, a);
+    int herr = 0;
+    CUDA_CHECK(cudaMemcpyAsync(C_host, C, (size_t)rows * rows * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(planes, pstride * S);
+    _ctx->release(rs, (size_t)rows * 8);
+    _ctx->release(C, (size_t)rows * rows * 8);
+    _ctx->release(err, sizeof(int));
+    if (herr) throw GpError("i8 test: pipeline wait timed out");
+    API_END
+}

@@ -1253,17 +1253,4 @@ int b200gp_searchsorted_right_m1(b200gp_ctx* ctx, const double* sorted, int64_t 
     API_END
 }
 
-// batched dense log_probability lives in dense_batched.cu (placeholder until then)
-int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const double* progs, int n_instr, int64_t nbatch,
-                                         const double* X, int64_t n, int ndim, const double* diag, const double* resid,
-                                         double* logp) {
-    API_BEGIN(ctx)
-    for (int64_t b = 0; b < nbatch; ++b) {
-        int rc = b200gp_dense_log_probability(ctx, progs + (size_t)b * n_instr * B200GP_PROG_STRIDE, n_instr, X, n, ndim,
-                                              diag, resid, logp + b);
-        if (rc) return rc;
-    }
-    API_END
-}
-
 }  // extern "C"

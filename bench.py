@@ -185,6 +185,7 @@ def run_ours(args, rank, local_rank, world):
     ctx = _cabi.Context(device=local_rank, stream=stream.cuda_stream)
     _cabi.set_context(ctx)
     ctx.set_option("nb", args.nb)
+    ctx.set_option("ozaki_slices", args.slices)
 
     n = args.n
     X, y, diag, scale = make_dense_problem(n, rank)
@@ -282,6 +283,8 @@ def run_ours(args, rank, local_rank, world):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"dense ExpSquared 3-D N={n} log_probability (fused build + blocked Cholesky + solve)",
                    "kernel": "1.0*ExpSquared(scale=1.0), L2", "diag": 0.1, "seed": SEED, "nb": args.nb,
+                   "trailing_update": (f"int8 fixed-point, {args.slices} digit planes (tcgen05 kind::i8)" if args.slices
+                                       else "native fp64 DMMA"),
                    "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                    "l2": "working set 34 GB >> 126 MB L2 (no flush needed)"},
         "logp": logp, "logp_e2e": logp_e2e,
@@ -296,6 +299,97 @@ def run_ours(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_quasisep(args, rank, local_rank, world):
+    """BASELINE config 4: SHO + Matern-3/2 (J = 4) on a sorted 1-D series; non-default workload."""
+    import torch
+    from ctypes import byref, c_double, c_int
+    from tinygp_b200 import GaussianProcess, _cabi
+    from tinygp_b200.kernels import quasisep as Q
+
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx = _cabi.Context(device=local_rank, stream=stream.cuda_stream)
+    _cabi.set_context(ctx)
+    n = args.n if args.n != N_DENSE else 10_000_000
+    rng = np.random.default_rng(49384)
+    t = np.sort(rng.uniform(0, n / 10.0, n))
+    y = np.sin(t) + 0.1 * rng.normal(size=n)
+    diag = np.full(n, 0.1)
+    kernel = Q.SHO(omega=1.5, quality=3.0, sigma=1.8) + Q.Matern32(scale=1.5, sigma=0.9)
+    comps = kernel.component_array()
+    dt, dy, dd = (torch.from_numpy(a).cuda() for a in (t, y, diag))
+    lp, uns = c_double(), c_int()
+
+    def step_device():
+        ctx.check(ctx.lib.b200gp_qs_log_probability_dev(ctx.handle, _cabi.ptr(comps), comps.shape[0], dt.data_ptr(), n,
+                                                        dd.data_ptr(), dy.data_ptr(), 1, byref(uns), byref(lp)))
+        return lp.value
+
+    def step_e2e():
+        return GaussianProcess(kernel, t, diag=diag, assume_sorted=True).log_probability(y)
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), out
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.set_option("profile", 1)
+    ctx.profile(reset=True)
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, logp = timed(step_device, args.steps)
+    clocks = sampler.stop()
+    prof = ctx.profile(reset=True)
+    ctx.set_option("profile", 0)
+    launches = ctx.launch_count() - l0
+    step_e2e()
+    ms_e2e, logp_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
+    e2e_steps = max(1, min(args.steps, 3))
+    J = kernel.state_dim()
+    alg_bytes = 8.0 * n * (3 + 1 + J)          # read t, diag, y ; write c, w   (SURVEY 8d: 64 B/point at J=4)
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        hbm_peak, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = alg_bytes * args.steps / (prof["qs_ms"] * 1e-3) / 1e9
+    # CPU baseline: C restatement of the sequential recursion on a bounded sample (1 core, scalar port)
+    from oracle import cref, tinygp_np as o
+    ns = min(n, 1_000_000)
+    ko = o.qs.SHO(1.5, 3.0, 1.8) + o.qs.Matern32(1.5, 0.9)
+    d_, p_, q_, a_ = o.qs_generators_fast(ko, t[:ns])
+    t0 = time.perf_counter()
+    lpo = cref.qs_log_probability(d_ + 0.1, p_, q_, a_, y[:ns])
+    t_cpu = time.perf_counter() - t0
+    line = {
+        "metric": "log_probability/sec", "value": args.steps / (ms * 1e-3), "unit": "logp/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"quasisep SHO+Matern32 (J=4) N={n} log_probability", "diag": 0.1, "seed": 49384,
+                   "l2": "working set 0.64 GB > 126 MB L2"},
+        "logp": logp, "logp_e2e": logp_e2e,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "peak_source": src, "traffic": None,
+                     "note": "kernel is fp64-ALU bound (Riccati composites), see DESIGN.md section 4"},
+        "cpu_baseline": {"value": 1.0 / (t_cpu * n / ns), "unit": "logp/s", "cores": 1, "kind": "port",
+                         "sample": f"first {ns} points, C restatement of ops.py:352-365,463-472 ({t_cpu:.2f} s; generators "
+                                   f"precomputed, not timed), scaled x{n / ns:.0f} (O(N))"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_steps / (ms_e2e * 1e-3), "unit": "logp/s", "h2d_bytes_per_step": int(3 * 8 * n),
+                "d2h_bytes_per_step": int(8 * n + 8)},
+        "gpu_launches": int(launches), "kernel_ms_per_step": {"qs": prof["qs_ms"] / args.steps},
+    }
+    print(json.dumps(line), flush=True)
 
 
 def _read_traffic():
@@ -314,12 +408,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_DENSE)
     ap.add_argument("--nb", type=int, default=1024)
+    ap.add_argument("--workload", default="dense", choices=["dense", "quasisep"])
+    ap.add_argument("--slices", type=int, default=0, help="int8 digit planes of the fixed-point update (0 = native DMMA)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+    elif args.workload == "quasisep":
+        if rank == 0:
+            run_quasisep(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -57,7 +57,7 @@ def test_ozaki_factor_parity(ctx, n, nb, slices):
     assert s.info == 0
     tol = {8: 1e-10, 7: 1e-9, 6: 1e-7}[slices]
     np.testing.assert_allclose(s.scale_tril, so.scale_tril, rtol=tol, atol=tol)
-    assert rel(s.normalization(), so.normalization()) < 1e-10
+    assert rel(s.normalization(), so.normalization()) < {8: 1e-10, 7: 1e-10, 6: 1e-8}[slices]
     assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
 
 

@@ -295,6 +295,9 @@ __device__ __forceinline__ void lower_tile(int b, int T, int& ti, int& tj) {
     }
 }
 
+// LOWER = true is the trailing SYRK update (the N^3/3 kernel); false = panel / rectangular GEMMs.  Two
+// instantiations so that profilers list them separately.
+template <bool LOWER>
 __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_constant__ KProg P, const Args g) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
     const int wm = warp >> 2, wn = warp & 3;
 
     int ti, tj;
-    if (g.lower) {
+    if (LOWER) {
         lower_tile((int)blockIdx.x, g.tiles_m, ti, tj);
     } else {
         ti = (int)blockIdx.x % g.tiles_m;
@@ -407,7 +410,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
 static bool g_attr_set = false;
 static void launch(b200gp_ctx* ctx, const KProg& P, const Args& g) {
     if (!g_attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         g_attr_set = true;
     }
     int64_t ntiles;
@@ -417,7 +421,10 @@ static void launch(b200gp_ctx* ctx, const KProg& P, const Args& g) {
         ntiles = (int64_t)g.tiles_m * g.tiles_n;
     if (ntiles <= 0) return;
     dim3 grid((unsigned)ntiles, (unsigned)(g.batch > 0 ? g.batch : 1));
-    gemm_nt_kernel<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(P, g);
+    if (g.lower)
+        gemm_nt_kernel<true><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(P, g);
+    else
+        gemm_nt_kernel<false><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(P, g);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }

@@ -19,12 +19,13 @@ ctx = _cabi.get_context()
 tag = sys.argv[1] if len(sys.argv) > 1 else "run"
 sizes = [int(s) for s in (sys.argv[2].split(",") if len(sys.argv) > 2 else "4096,16384,32768,65536".split(","))]
 nbs = [int(s) for s in (sys.argv[3].split(",") if len(sys.argv) > 3 else "512".split(","))]
+slices_list = [int(s) for s in (sys.argv[4].split(",") if len(sys.argv) > 4 else "0".split(","))]
 
 out["fp64_peak"] = [ctx.measure_fp64_peak() for _ in range(3)]
 print("fp64 peak (dmma, dfma) TF/s:", out["fp64_peak"], flush=True)
 
 
-def logp_dev(n, nb, profile):
+def logp_dev(n, nb, profile, slices=0):
     rng = np.random.default_rng(49382)
     X = np.ascontiguousarray(rng.uniform(0, 20.0 * (n / 65536.0) ** (1 / 3), (n, 3)))
     y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
@@ -32,6 +33,8 @@ def logp_dev(n, nb, profile):
     k = 1.0 * kernels.ExpSquared(1.0)
     prog = k.program()
     ctx.set_option("nb", nb)
+    ctx.set_option("ozaki_slices", slices)
+    ctx.set_option("ozaki_min_n", 0)
     ctx.set_option("profile", int(profile))
     ctx.profile(reset=True)
     lp = c_double()
@@ -46,19 +49,23 @@ def logp_dev(n, nb, profile):
 
 res = []
 for n in sizes:
+  oracle_cache = {}
+  for sl in slices_list:
     for nb in nbs:
-        lp, dt, _, _ = logp_dev(n, nb, False)       # warm-up (allocations)
-        lp, dt, _, data = logp_dev(n, nb, False)
-        lp2, dt2, prof, _ = logp_dev(n, nb, True)
+        lp, dt, _, _ = logp_dev(n, nb, False, sl)       # warm-up (allocations)
+        lp, dt, _, data = logp_dev(n, nb, False, sl)
+        lp2, dt2, prof, _ = logp_dev(n, nb, True, sl)
         tf = n**3 / 3 / dt / 1e12
-        row = {"n": n, "nb": nb, "logp": lp, "sec": dt, "tflops_n3_3": tf, "profile": prof,
+        row = {"n": n, "nb": nb, "slices": sl, "logp": lp, "sec": dt, "tflops_n3_3": tf, "profile": prof,
                "syrk_tflops": prof["syrk_flop"] / max(prof["syrk_ms"], 1e-9) / 1e9}
         if n <= 16384:
             X, y = data
-            t0 = time.perf_counter()
-            lpo = o.GaussianProcess(o.Constant(1.0) * o.ExpSquared(1.0), X, diag=0.1).log_probability(y)
+            if n not in oracle_cache:
+                t0 = time.perf_counter()
+                lpo = o.GaussianProcess(o.Constant(1.0) * o.ExpSquared(1.0), X, diag=0.1).log_probability(y)
+                oracle_cache[n] = (lpo, time.perf_counter() - t0)
+            lpo, row["oracle_sec"] = oracle_cache[n]
             row["oracle_logp"] = lpo
-            row["oracle_sec"] = time.perf_counter() - t0
             row["rel_err"] = abs(lp - lpo) / abs(lpo)
         print(json.dumps(row), flush=True)
         res.append(row)

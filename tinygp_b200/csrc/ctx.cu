@@ -152,6 +152,7 @@ int b200gp_destroy(b200gp_ctx* ctx) {
     ctx->trim();
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -178,6 +179,10 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
     } else if (!strcmp(key, "ozaki_slices")) {
         if (value < 0 || value > 8) throw GpError("option ozaki_slices must be in [0, 8]");
         _ctx->oz_slices = value;
+    } else if (!strcmp(key, "ozaki_lookahead")) {
+        _ctx->oz_lookahead = value;
+    } else if (!strcmp(key, "ozaki_cluster")) {
+        _ctx->oz_cluster = value;
     } else if (!strcmp(key, "ozaki_min_n")) {
         _ctx->oz_min_n = value;
     } else if (!strcmp(key, "trim")) {

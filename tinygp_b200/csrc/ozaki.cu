@@ -46,7 +46,8 @@ struct Args {
     const double* rs;                  // row scales (power of two), indexed by global row
     int64_t row0, col0;                // global row / col of tile (0,0)
     int tiles_m, tiles_n;
-    int K;                             // int8 K extent (multiple of KC), operands start at k = 0
+    int K;                             // int8 K extent (multiple of KC)
+    int k_begin;                       // first K column (multiple of KC)
     int S;                             // number of digit planes used
     int64_t b_row0;                    // first global row of the B operand (= col0 for the Cholesky update)
     int64_t n_rows;                    // rows of the matrix (for masking the last column tile)
@@ -132,7 +133,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---- the tile kernel ----------------------------------------------------------------------------
+// Cluster of CM x CN CTAs (cluster rank r: cm = r % CM, cn = r / CM) working on CM x CN neighbouring tiles.
+// The A tile (rows of ti) is needed by the CN CTAs of a cluster row and the B tile (rows of tj) by the CM
+// CTAs of a cluster column: every CTA fetches only its 1/CN slice of A and 1/CM slice of B and TMA-multicasts
+// it to its mates, which divides the L2 -> SM traffic (the measured bottleneck of the 1 x 1 version).
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+constexpr int BOXR = 64;  // rows per TMA box
+
+template <int CM, int CN>
 __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_constant__ Maps maps, const Args g) {
+    static_assert((TM / CN) % BOXR == 0 && (TN / CM) % BOXR == 0, "slice must be whole TMA boxes");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -143,14 +171,36 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
 
+    constexpr int CS = CM * CN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ti = (int)blockIdx.x % g.tiles_m, tj = (int)blockIdx.x / g.tiles_m;
-    const int64_t grow0 = g.row0 + (int64_t)ti * TM;   // global row of tile row 0
-    const int64_t gcol0 = g.col0 + (int64_t)tj * TN;   // global col of tile col 0
-    if (g.skip_upper && grow0 + TM - 1 < gcol0) return;  // whole tile above the diagonal (uniform per CTA)
+    int crank = 0;
+    if (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
+    const int cm = crank % CM, cn = crank / CM;
+    const int cluster_id = (int)blockIdx.x / CS;
+    const int ctm = (g.tiles_m + CM - 1) / CM;            // cluster tiles along M
+    const int ci = cluster_id % ctm, cj = cluster_id / ctm;
+    const int ti = ci * CM + cm, tj = cj * CN + cn;
+    const int64_t grow0 = g.row0 + (int64_t)ti * TM;      // global row of tile row 0
+    const int64_t gcol0 = g.col0 + (int64_t)tj * TN;      // global col of tile col 0
+    // cluster-uniform decisions
+    const int64_t crow_lo = g.row0 + (int64_t)ci * CM * TM, crow_hi = crow_lo + (int64_t)CM * TM - 1;
+    const int64_t ccol_lo = g.col0 + (int64_t)cj * CN * TN, ccol_hi = ccol_lo + (int64_t)CN * TN - 1;
+    if (g.skip_upper && crow_hi < ccol_lo) return;        // every tile of the cluster lies above the diagonal
+    // tiles that contain diagonal elements get ALL S^2 digit pairs: the dropped pairs s+t >= S are zero-mean
+    // off the diagonal but a sum of squares (systematic bias) on it
+    const bool diag_cluster = g.skip_upper && !(crow_lo > ccol_hi) ;
+    const int S = g.S;
+    const int NG = diag_cluster ? (2 * S - 1) : S;
+
+    uint16_t mask_a = 0, mask_b = 0;
+#pragma unroll
+    for (int c = 0; c < CN; ++c) mask_a |= (uint16_t)(1u << (cm + CM * c));
+#pragma unroll
+    for (int m = 0; m < CM; ++m) mask_b |= (uint16_t)(1u << (m + CM * cn));
+    const uint16_t mask_all = mask_a | mask_b;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CM + CN - 1); }
         mbar_init(tfull + 0, 1); mbar_init(tfull + 1, 1);
         mbar_init(tempty + 0, 4); mbar_init(tempty + 1, 4);
         *abort_flag = 0;
@@ -162,11 +212,11 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();   // mates' barriers must be initialised before any multicast lands
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     const int KT = g.K / KC;
-    const int S = g.S;
     const int64_t brow0 = g.b_row0 + (int64_t)tj * TN;  // global row of the B operand's first row
 
     if (warp == 0) {
@@ -175,17 +225,32 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            for (int gi = 0; gi < S && ok; ++gi) {
-                for (int s = 0; s <= gi && ok; ++s) {
+            for (int gi = 0; gi < NG && ok; ++gi) {
+                const int s_lo = (gi - (S - 1) > 0) ? gi - (S - 1) : 0, s_hi = (gi < S - 1) ? gi : S - 1;
+                for (int s = s_lo; s <= s_hi && ok; ++s) {
                     const int t = gi - s;
                     for (int kc = 0; kc < KT; ++kc) {
                         if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; break; }
                         uint8_t* a_dst = smem + stage * STAGE_BYTES;
                         uint8_t* b_dst = a_dst + A_BYTES;
-                        mbar_expect_tx(full + stage, STAGE_BYTES);
-                        tma_load_2d(a_dst, &maps.plane[s], full + stage, kc * KC, (int)grow0);
-                        tma_load_2d(b_dst, &maps.plane[t], full + stage, kc * KC, (int)brow0);
-                        tma_load_2d(b_dst + A_BYTES, &maps.plane[t], full + stage, kc * KC, (int)brow0 + 128);
+                        mbar_expect_tx(full + stage, STAGE_BYTES);   // own + mates' slices land on this barrier
+                        constexpr int A_ROWS = TM / CN, B_ROWS = TN / CM;
+#pragma unroll
+                        for (int bx = 0; bx < A_ROWS / BOXR; ++bx) {
+                            const int r = cn * A_ROWS + bx * BOXR;
+                            if (CN > 1)
+                                tma_load_2d_mc(a_dst + r * KC, &maps.plane[s], full + stage, g.k_begin + kc * KC, (int)grow0 + r, mask_a);
+                            else
+                                tma_load_2d(a_dst + r * KC, &maps.plane[s], full + stage, g.k_begin + kc * KC, (int)grow0 + r);
+                        }
+#pragma unroll
+                        for (int bx = 0; bx < B_ROWS / BOXR; ++bx) {
+                            const int r = cm * B_ROWS + bx * BOXR;
+                            if (CM > 1)
+                                tma_load_2d_mc(b_dst + r * KC, &maps.plane[t], full + stage, g.k_begin + kc * KC, (int)brow0 + r, mask_b);
+                            else
+                                tma_load_2d(b_dst + r * KC, &maps.plane[t], full + stage, g.k_begin + kc * KC, (int)brow0 + r);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -197,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            for (int gi = 0; gi < S && ok; ++gi) {
+            for (int gi = 0; gi < NG && ok; ++gi) {
                 const int acc = gi & 1;
                 if (gi >= 2) {  // the epilogue must have drained this accumulator (group gi-2)
                     if (!mbar_wait(tempty + acc, ((gi >> 1) - 1) & 1, abort_flag)) { ok = false; break; }
@@ -205,7 +270,8 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                 }
                 const uint32_t tacc = tmem_base + (uint32_t)acc * TN;
                 uint32_t accumulate = 0;
-                for (int s = 0; s <= gi && ok; ++s) {
+                const int s_lo = (gi - (S - 1) > 0) ? gi - (S - 1) : 0, s_hi = (gi < S - 1) ? gi : S - 1;
+                for (int s = s_lo; s <= s_hi && ok; ++s) {
                     for (int kc = 0; kc < KT; ++kc) {
                         if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
                         tc_fence_after();
@@ -216,7 +282,8 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                             umma_i8(tacc, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), accumulate);
                             accumulate = 1;
                         }
-                        tc_commit(empty + stage);  // frees the smem slot when these MMAs retire
+                        // free the slot in every CTA whose producer writes into it (row- and column-mates)
+                        if (CS > 1) tc_commit_mc(empty + stage, mask_all); else tc_commit(empty + stage);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -228,10 +295,11 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
         const int q = warp & 3;
         const int row = q * 32 + lane;            // tile row owned by this thread
         const int64_t gr = grow0 + row;
-        const double rsi = g.rs[gr];
-        double* crow = g.C + gr * g.ldc;
+        const bool row_ok = gr < g.n_rows;        // padding tiles of an incomplete cluster do no stores
+        const double rsi = row_ok ? g.rs[gr] : 0.0;
+        double* crow = g.C + (row_ok ? gr : 0) * g.ldc;
         bool ok = true;
-        for (int gi = 0; gi < S && ok; ++gi) {
+        for (int gi = 0; gi < NG && ok; ++gi) {
             const int acc = gi & 1;
             if (!mbar_wait(tfull + acc, (gi >> 1) & 1, abort_flag)) { ok = false; break; }
             tc_fence_after();
@@ -243,7 +311,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb * 32), r);
                 const int64_t gc = gcol0 + cb * 32;
-                if (gc < g.n_rows) {  // column tiles may stick out past the matrix on the last panel
+                if (row_ok && gc < g.n_rows) {  // column tiles may stick out past the matrix on the last panel
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
@@ -262,6 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
 
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();   // no CTA may exit while mates still multicast into it / arrive on its barriers
     if (threadIdx.x == 0 && *abort_flag) atomicExch(g.error_flag, 1);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
@@ -349,7 +418,7 @@ Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, 
         const int sp = (s < S) ? s : 0;
         cuuint64_t dims[2] = {(cuuint64_t)ldq, (cuuint64_t)rows};
         cuuint64_t strides[1] = {(cuuint64_t)ldq};
-        cuuint32_t box[2] = {(cuuint32_t)KC, 128u};
+        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BOXR};
         cuuint32_t estr[2] = {1u, 1u};
         CUresult r = enc(&m.plane[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes + (int64_t)sp * plane_stride, dims, strides,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -359,17 +428,42 @@ Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, 
     return m;
 }
 
-void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
+template <int CM, int CN>
+static void launch_cfg(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     static bool attr = false;
     if (!attr) {
-        CUDA_CHECK(cudaFuncSetAttribute(i8_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(i8_update_kernel<CM, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
-    const int64_t nt = (int64_t)a.tiles_m * a.tiles_n;
-    if (nt <= 0 || a.K <= 0) return;
-    i8_update_kernel<<<(unsigned)nt, THREADS, SMEM_BYTES, ctx->stream>>>(maps, a);
-    CUDA_CHECK(cudaGetLastError());
+    const int ctm = (a.tiles_m + CM - 1) / CM, ctn = (a.tiles_n + CN - 1) / CN;
+    const int64_t nclusters = (int64_t)ctm * ctn;
+    if (nclusters <= 0 || a.K <= 0) return;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(nclusters * CM * CN));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CM * CN;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, i8_update_kernel<CM, CN>, maps, a));
     ctx->launches++;
+}
+
+// cluster shape code: 11 = 1x1 (no multicast), 21 = 2x1, 12 = 1x2, 22 = 2x2, 41 = 4x1, 42 = 4x2
+void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
+    switch ((int)ctx->oz_cluster) {
+        case 11: launch_cfg<1, 1>(ctx, maps, a); break;
+        case 21: launch_cfg<2, 1>(ctx, maps, a); break;
+        case 12: launch_cfg<1, 2>(ctx, maps, a); break;
+        case 41: launch_cfg<4, 1>(ctx, maps, a); break;
+        case 42: launch_cfg<4, 2>(ctx, maps, a); break;
+        default: launch_cfg<2, 2>(ctx, maps, a); break;
+    }
 }
 
 }  // namespace oz
@@ -389,6 +483,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
     NB = (NB / 256) * 256;
     if (S < 2) S = 2;
     if (S > 8) S = 8;
+    const bool lookahead = ctx->oz_lookahead != 0;
 
     const size_t plane_stride = (size_t)np * np;
     int8_t* planes = (int8_t*)ctx->alloc(plane_stride * S);
@@ -402,40 +497,81 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
     ctx->launches++;
     oz::Maps maps = oz::make_maps(planes, (int64_t)plane_stride, np, np, S);
 
-    for (int64_t c0 = 0; c0 < np; c0 += NB) {
-        const int64_t kb = (NB < np - c0) ? NB : (np - c0);
-        // (1) generate this block column of K (rows c0.., cols c0..c0+kb)
-        dense_build_region(s, c0, c0, kb);
-        // (2) C -= L[c0:, 0:c0] L[c0:c0+kb, 0:c0]^T on the int8 tensor pipe
-        if (c0 > 0) {
-            oz::Args a{};
-            a.C = s->mat; a.ldc = ld; a.rs = rs;
-            a.row0 = c0; a.col0 = c0; a.b_row0 = c0;
-            a.tiles_m = (int)((np - c0) / oz::TM);
-            a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
-            a.K = (int)c0; a.S = S; a.n_rows = np; a.skip_upper = 1; a.error_flag = err;
-            ProfTimer t(ctx, &ctx->prof.syrk_ms);
-            oz::launch_update(ctx, maps, a);
-            const double rows = (double)(np - c0);
-            ctx->prof.syrk_flop += 2.0 * rows * (double)kb * (double)c0;  // fp64-equivalent flop of this update
-            ctx->prof.syrk_launches++;
+    // Two streams: `upd` (the context stream) runs build + int8 updates, `pan` (high priority) runs the fp64
+    // panel factorisation and the digit cutting.  Update J is split into the part that only needs panels
+    // < J-1 (runs UNDER the factorisation of panel J-1) and the short K = nb part that needs panel J-1.
+    cudaStream_t upd = ctx->stream, pan = ctx->stream;
+    if (lookahead) {
+        if (!ctx->stream2) {
+            int lo = 0, hi = 0;
+            CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
         }
-        // (3) factor the panel in fp64 (DMMA path)
+        pan = ctx->stream2;
+    }
+    const int ncol = (int)((np + NB - 1) / NB);
+    std::vector<cudaEvent_t> ev_upd(ncol), ev_cut(ncol);
+    if (lookahead) {
+        for (int j = 0; j < ncol; ++j) { ev_upd[j] = ctx->get_event(); ev_cut[j] = ctx->get_event(); }
+        cudaEvent_t e0 = ctx->get_event();   // pan must see the row scales / info reset issued on upd
+        CUDA_CHECK(cudaEventRecord(e0, upd));
+        CUDA_CHECK(cudaStreamWaitEvent(pan, e0, 0));
+        ctx->event_pool.push_back(e0);
+    }
+
+    auto update = [&](int64_t c0, int64_t kb, int64_t k_begin, int64_t k_len) {
+        if (k_len <= 0) return;
+        oz::Args a{};
+        a.C = s->mat; a.ldc = ld; a.rs = rs;
+        a.row0 = c0; a.col0 = c0; a.b_row0 = c0;
+        a.tiles_m = (int)((np - c0) / oz::TM);
+        a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
+        a.K = (int)k_len; a.k_begin = (int)k_begin; a.S = S; a.n_rows = np; a.skip_upper = 1; a.error_flag = err;
+        ProfTimer t(ctx, &ctx->prof.syrk_ms);
+        oz::launch_update(ctx, maps, a);
+        ctx->prof.syrk_flop += 2.0 * (double)(np - c0) * (double)kb * (double)k_len;  // fp64-equivalent flop
+        ctx->prof.syrk_launches++;
+    };
+
+    for (int J = 0; J < ncol; ++J) {
+        const int64_t c0 = (int64_t)J * NB;
+        const int64_t kb = (NB < np - c0) ? NB : (np - c0);
+        // ---- stream upd: generate the block column, then C -= L[c0:, 0:c0] L[c0:c0+kb, 0:c0]^T on the int8 pipe
+        ctx->stream = upd;
+        dense_build_region(s, c0, c0, kb);
+        if (lookahead) {
+            if (J >= 2) update(c0, kb, 0, (int64_t)(J - 1) * NB);                 // panels 0 .. J-2
+            if (J >= 1) {
+                CUDA_CHECK(cudaStreamWaitEvent(upd, ev_cut[J - 1], 0));
+                update(c0, kb, (int64_t)(J - 1) * NB, NB);                        // panel J-1
+            }
+            CUDA_CHECK(cudaEventRecord(ev_upd[J], upd));
+            CUDA_CHECK(cudaStreamWaitEvent(pan, ev_upd[J], 0));
+        } else if (J >= 1) {
+            update(c0, kb, 0, c0);
+        }
+        // ---- stream pan: factor the panel in fp64 (DMMA path), then cut the digits of the rows below it
+        ctx->stream = pan;
         {
             ProfTimer t(ctx, &ctx->prof.panel_ms);
             dense_panel_factor(s, c0, kb);
         }
-        // (4) cut the digits of the rows below the diagonal block
         if (c0 + kb < np) {
             const int64_t nrows = np - (c0 + kb);
             const int64_t nthreads = nrows * (kb / 16);
             ProfTimer t(ctx, &ctx->prof.build_ms);
-            oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, ctx->stream>>>(
+            oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, pan>>>(
                 s->mat, ld, rs, c0 + kb, nrows, c0, kb, planes, (int64_t)plane_stride, np, S);
             ctx->launches++;
         }
+        if (lookahead) CUDA_CHECK(cudaEventRecord(ev_cut[J], pan));
     }
+    ctx->stream = upd;
     CUDA_CHECK(cudaGetLastError());
+    if (lookahead) {
+        CUDA_CHECK(cudaStreamWaitEvent(upd, ev_cut[ncol - 1], 0));   // join
+        for (int j = 0; j < ncol; ++j) { ctx->event_pool.push_back(ev_upd[j]); ctx->event_pool.push_back(ev_cut[j]); }
+    }
     int herr = 0;
     CUDA_CHECK(cudaMemcpyAsync(&s->info, s->info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -466,7 +602,7 @@ extern "C" int b200gp_i8_update_test(b200gp_ctx* ctx, const int8_t* planes_host,
     oz::Args a{};
     a.C = C; a.ldc = rows; a.rs = rs; a.row0 = 0; a.col0 = 0; a.b_row0 = 0;
     a.tiles_m = (int)(rows / oz::TM); a.tiles_n = (int)(rows / oz::TN);
-    a.K = (int)K; a.S = S; a.n_rows = rows; a.skip_upper = 0; a.error_flag = err;
+    a.K = (int)K; a.k_begin = 0; a.S = S; a.n_rows = rows; a.skip_upper = 0; a.error_flag = err;
     oz::launch_update(_ctx, maps, a);
     int herr = 0;
     CUDA_CHECK(cudaMemcpyAsync(C_host, C, (size_t)rows * rows * 8, cudaMemcpyDeviceToHost, _ctx->stream));

@@ -20,6 +20,8 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "run"
 sizes = [int(s) for s in (sys.argv[2].split(",") if len(sys.argv) > 2 else "4096,16384,32768,65536".split(","))]
 nbs = [int(s) for s in (sys.argv[3].split(",") if len(sys.argv) > 3 else "512".split(","))]
 slices_list = [int(s) for s in (sys.argv[4].split(",") if len(sys.argv) > 4 else "0".split(","))]
+clusters = [int(s) for s in (sys.argv[5].split(",") if len(sys.argv) > 5 else "22".split(","))]
+lookaheads = [int(s) for s in (sys.argv[6].split(",") if len(sys.argv) > 6 else "1".split(","))]
 
 out["fp64_peak"] = [ctx.measure_fp64_peak() for _ in range(3)]
 print("fp64 peak (dmma, dfma) TF/s:", out["fp64_peak"], flush=True)
@@ -50,13 +52,15 @@ def logp_dev(n, nb, profile, slices=0):
 res = []
 for n in sizes:
   oracle_cache = {}
-  for sl in slices_list:
+  for sl, cl, la in [(a, b, c) for a in slices_list for b in (clusters if a else [22]) for c in (lookaheads if a else [1])]:
+    ctx.set_option("ozaki_cluster", cl)
+    ctx.set_option("ozaki_lookahead", la)
     for nb in nbs:
         lp, dt, _, _ = logp_dev(n, nb, False, sl)       # warm-up (allocations)
         lp, dt, _, data = logp_dev(n, nb, False, sl)
         lp2, dt2, prof, _ = logp_dev(n, nb, True, sl)
         tf = n**3 / 3 / dt / 1e12
-        row = {"n": n, "nb": nb, "slices": sl, "logp": lp, "sec": dt, "tflops_n3_3": tf, "profile": prof,
+        row = {"n": n, "nb": nb, "slices": sl, "cluster": cl, "lookahead": la, "logp": lp, "sec": dt, "tflops_n3_3": tf, "profile": prof,
                "syrk_tflops": prof["syrk_flop"] / max(prof["syrk_ms"], 1e-9) / 1e9}
         if n <= 16384:
             X, y = data

@@ -231,6 +231,10 @@ def run_ours(args, rank, local_rank, world):
     ctx.set_option("peak_iters", 1_500_000)
     peak_sustained, dfma_sustained = ctx.measure_fp64_peak()
     ctx.set_option("peak_iters", 4096)
+    i8_peak_burst = max(ctx.measure_i8_peak() for _ in range(2))
+    ctx.set_option("peak_iters", 200000)
+    i8_peak_sustained = ctx.measure_i8_peak()
+    ctx.set_option("peak_iters", 4096)
 
     for _ in range(args.warmup):
         step_device()
@@ -260,8 +264,27 @@ def run_ours(args, rank, local_rank, world):
     e2e_value = world * e2e_steps / (ms_e2e * 1e-3)
     flop_alg = n ** 3 / 3.0
     syrk_tf = prof["syrk_flop"] / max(prof["syrk_ms"], 1e-9) / 1e9
-    roofline = {
-        "bound": "tensor", "kernel": "gemm_nt_kernel (trailing SYRK/GEMM update, DMMA m8n8k4 f64)",
+    if args.slices:
+        i8_tops = prof["i8_ops"] / max(prof["syrk_ms"], 1e-9) / 1e9
+        try:
+            bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            bf16 = {}
+        roofline = {
+            "bound": "tensor", "kernel": "i8_update_kernel (tcgen05.mma kind::i8, TMA multicast, TMEM int32 accumulators)",
+            "achieved": i8_tops, "peak": i8_peak_sustained, "unit": "TFLOP/s", "frac": i8_tops / i8_peak_sustained,
+            "peak_source": "int8 tensor TOP/s measured on this GPU by b200gp_measure_i8_peak (resident-operand "
+                           "tcgen05 loop, ~1 s); MEASURED_PEAKS.json has bf16 only (int8 nominal = 2x bf16)",
+            "peak_burst": i8_peak_burst, "bf16_measured_peaks": {k: bf16.get(k) for k in ("bf16_tflops", "bf16_tflops_sustained")},
+            "int8_ops_per_step": prof["i8_ops"] / args.steps, "digit_planes": args.slices,
+            "fp64_equivalent_tflops": syrk_tf, "fp64_dmma_peak_sustained": peak_sustained, "fp64_dmma_peak_burst": peak_burst,
+            "launches": int(prof["syrk_launches"]), "ms_total": prof["syrk_ms"],
+            "whole_step_tflops_n3_over_3": flop_alg * args.steps / (ms * 1e-3) / 1e12,
+            "traffic": _read_traffic(),
+        }
+    else:
+      roofline = {
+        "bound": "tensor", "kernel": "gemm_nt_kernel<true> (trailing SYRK/GEMM update, DMMA m8n8k4 f64)",
         "achieved": syrk_tf, "peak": peak_sustained, "unit": "TFLOP/s", "frac": syrk_tf / peak_sustained,
         "peak_source": "measured on this GPU by b200gp_measure_fp64_peak (sustained ~2 s DMMA loop); "
                        "MEASURED_PEAKS.json has no fp64 entry",
@@ -269,7 +292,7 @@ def run_ours(args, rank, local_rank, world):
         "launches": int(prof["syrk_launches"]), "ms_total": prof["syrk_ms"],
         "whole_step_tflops_n3_over_3": flop_alg * args.steps / (ms * 1e-3) / 1e12,
         "traffic": _read_traffic(),
-    }
+      }
     # CPU baseline on a bounded sample
     n_s = pick_sample_n(25.0)
     t_cpu, lp_cpu = oracle_dense_logp_seconds(n_s)

@@ -76,12 +76,16 @@ typedef struct {
     double qs_ms;       /* quasiseparable scan kernels                    */
     double qs_bytes;    /* algorithmic bytes moved by them                */
     int64_t qs_launches;
+    double i8_ops;      /* int8 tensor ops (2 x MAC) issued by the fixed-point update launches (time: syrk_ms) */
 } b200gp_profile;
 int b200gp_get_profile(b200gp_ctx* ctx, b200gp_profile* out, int reset);
 
 /* fp64 tensor (DMMA) peak micro-benchmark on this device: returns achieved TFLOP/s of a
  * register-resident mma.sync.m8n8k4.f64 loop on all SMs, and of a DFMA loop. */
 int b200gp_measure_fp64_peak(b200gp_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+/* int8 tensor peak micro-benchmark: tcgen05.mma kind::i8 (M=128, N=256, K=32) issued back to back on every SM
+ * from resident shared-memory operands (no TMA traffic); returns TOP/s (2 x MAC). */
+int b200gp_measure_i8_peak(b200gp_ctx* ctx, double* tops);
 
 /* diagnostics for the int8 fixed-point tensor-core update (tcgen05.mma kind::i8, ozaki.cu):
  * C (rows x rows, host, in/out) -= sum_{s+t<S} 2^-(12+7(s+t)) rs_i rs_j Q_s Q_t^T with Q_s the S int8 digit planes

@@ -63,7 +63,7 @@ def test_ozaki_factor_parity(ctx, n, nb, slices, lookahead):
     assert s.info == 0
     tol = {8: 1e-10, 7: 1e-10, 6: 1e-9}[slices]
     np.testing.assert_allclose(s.scale_tril, so.scale_tril, rtol=tol, atol=tol)
-    assert rel(s.normalization(), so.normalization()) < 1e-10
+    assert rel(s.normalization(), so.normalization()) < (1e-9 if slices == 6 else 1e-10)
     assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
 
 

@@ -33,7 +33,7 @@ class Profile(ctypes.Structure):
         ("syrk_ms", c_double), ("syrk_flop", c_double), ("syrk_launches", c_int64),
         ("panel_ms", c_double), ("build_ms", c_double), ("build_bytes", c_double),
         ("solve_ms", c_double), ("qs_ms", c_double), ("qs_bytes", c_double),
-        ("qs_launches", c_int64),
+        ("qs_launches", c_int64), ("i8_ops", c_double),
     ]
 
 
@@ -48,6 +48,7 @@ SIGNATURES = {
     "b200gp_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
     "b200gp_get_profile": (c_int, [c_void_p, POINTER(Profile), c_int]),
     "b200gp_measure_fp64_peak": (c_int, [c_void_p, c_double_p, c_double_p]),
+    "b200gp_measure_i8_peak": (c_int, [c_void_p, c_double_p]),
     "b200gp_i8_update_test": (c_int, [_V, _D, _I, _L, _L, _D, _D]),
     "b200gp_kernel_matrix": (c_int, [_V, _D, _I, _D, _L, _D, _L, _I, _D]),
     "b200gp_kernel_diag": (c_int, [_V, _D, _I, _D, _L, _I, _D]),
@@ -145,6 +146,11 @@ class Context:
         a, b = c_double(), c_double()
         self.check(self.lib.b200gp_measure_fp64_peak(self.handle, byref(a), byref(b)))
         return a.value, b.value
+
+    def measure_i8_peak(self):
+        a = c_double()
+        self.check(self.lib.b200gp_measure_i8_peak(self.handle, byref(a)))
+        return a.value
 
     def close(self):
         if self.handle:

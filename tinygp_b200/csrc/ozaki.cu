@@ -452,6 +452,17 @@ static void launch_cfg(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     cfg.numAttrs = 1;
     CUDA_CHECK(cudaLaunchKernelEx(&cfg, i8_update_kernel<CM, CN>, maps, a));
     ctx->launches++;
+    // int8 ops issued (mirrors the kernel's cluster-uniform decisions)
+    double pairs_tiles = 0.0;
+    for (int cj = 0; cj < ctn; ++cj)
+        for (int ci = 0; ci < ctm; ++ci) {
+            const int64_t rlo = a.row0 + (int64_t)ci * CM * TM, rhi = rlo + (int64_t)CM * TM - 1;
+            const int64_t clo = a.col0 + (int64_t)cj * CN * TN, chi = clo + (int64_t)CN * TN - 1;
+            if (a.skip_upper && rhi < clo) continue;
+            const bool dg = a.skip_upper && !(rlo > chi);
+            pairs_tiles += (double)(CM * CN) * (dg ? (double)a.S * a.S : 0.5 * a.S * (a.S + 1));
+        }
+    ctx->prof.i8_ops += 2.0 * pairs_tiles * (double)TM * TN * (double)a.K;
 }
 
 // cluster shape code: 11 = 1x1 (no multicast), 21 = 2x1, 12 = 1x2, 22 = 2x2, 41 = 4x1, 42 = 4x2
@@ -464,6 +475,44 @@ void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
         case 42: launch_cfg<4, 2>(ctx, maps, a); break;
         default: launch_cfg<2, 2>(ctx, maps, a); break;
     }
+}
+
+// ---- int8 tensor peak: MMAs back to back from resident smem operands --------------------------------------
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int* sink) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + STAGE_BYTES);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
+    for (int i = threadIdx.x; i < STAGE_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        *abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy smem writes -> async proxy (UMMA)
+    if ((threadIdx.x >> 5) == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    if (threadIdx.x == 32) {
+        const uint32_t a_addr = smem_u32(smem), b_addr = a_addr + A_BYTES;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                umma_i8(tmem_base + (uint32_t)((it & 1) * TN), make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), 1u);
+        }
+        tc_commit(bar);
+        if (!mbar_wait(bar, 0, abort_flag)) atomicExch(sink, 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
 }
 
 }  // namespace oz
@@ -613,5 +662,27 @@ extern "C" int b200gp_i8_update_test(b200gp_ctx* ctx, const int8_t* planes_host,
     _ctx->release(C, (size_t)rows * rows * 8);
     _ctx->release(err, sizeof(int));
     if (herr) throw GpError("i8 test: pipeline wait timed out");
+    API_END
+}
+
+extern "C" int b200gp_measure_i8_peak(b200gp_ctx* ctx, double* tops) {
+    API_BEGIN(ctx)
+    const int smem_bytes = oz::STAGE_BYTES + 1024 + 64;
+    CUDA_CHECK(cudaFuncSetAttribute(oz::i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int* sink = (int*)_ctx->alloc(sizeof(int));
+    CUDA_CHECK(cudaMemsetAsync(sink, 0, sizeof(int), _ctx->stream));
+    const int iters = (int)((_ctx->peak_iters < 200000) ? _ctx->peak_iters * 4 : 800000);
+    float ms = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(_ctx->ev0, _ctx->stream);
+        oz::i8_peak_kernel<<<_ctx->num_sms, 128, smem_bytes, _ctx->stream>>>(iters, sink);
+        cudaEventRecord(_ctx->ev1, _ctx->stream);
+        CUDA_CHECK(cudaEventSynchronize(_ctx->ev1));
+        cudaEventElapsedTime(&ms, _ctx->ev0, _ctx->ev1);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    _ctx->launches += 2;
+    *tops = (double)_ctx->num_sms * (double)iters * 4.0 * 2.0 * oz::TM * oz::TN * 32.0 / (ms * 1e-3) / 1e12;
+    _ctx->release(sink, sizeof(int));
     API_END
 }

@@ -184,13 +184,13 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
     const int64_t gcol0 = g.col0 + (int64_t)tj * TN;      // global col of tile col 0
     // cluster-uniform decisions
     const int64_t crow_lo = g.row0 + (int64_t)ci * CM * TM, crow_hi = crow_lo + (int64_t)CM * TM - 1;
-    const int64_t ccol_lo = g.col0 + (int64_t)cj * CN * TN, ccol_hi = ccol_lo + (int64_t)CN * TN - 1;
+    const int64_t ccol_lo = g.col0 + (int64_t)cj * CN * TN;
     if (g.skip_upper && crow_hi < ccol_lo) return;        // every tile of the cluster lies above the diagonal
-    // tiles that contain diagonal elements get ALL S^2 digit pairs: the dropped pairs s+t >= S are zero-mean
-    // off the diagonal but a sum of squares (systematic bias) on it
-    const bool diag_cluster = g.skip_upper && !(crow_lo > ccol_hi) ;
+    // Pairs with s + t >= S are dropped everywhere.  Off the diagonal they are zero-mean; on the diagonal they
+    // are sums of squares (a systematic bias), which cut_digits_kernel accumulates exactly per row and
+    // diag_correct_kernel subtracts from C_ii -- so every tile does the same S(S+1)/2 products.
     const int S = g.S;
-    const int NG = diag_cluster ? (2 * S - 1) : S;
+    const int NG = S;
 
     uint16_t mask_a = 0, mask_b = 0;
 #pragma unroll
@@ -338,42 +338,79 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
 }
 
 // ---- digit cutting -------------------------------------------------------------------------------
-// planes[s][row * ldq + col] for rows [r0, np), cols [c0, c0 + ncols); 16 columns per thread
+// planes[s][row * ldq + col] for rows [r0, np), cols [c0, c0 + ncols); 16 columns per thread.
+// Also accumulates, per row, the dropped diagonal pairs  sum_{s+t>=S} 2^-(12+7(s+t)) sum_k q_s q_t  (exact integer
+// sums, fp64 weights) into corr[slot][row] with slot = 512-column group: two warps -> two commutative adds.
 __global__ void __launch_bounds__(256) cut_digits_kernel(const double* __restrict__ mat, int64_t ld, const double* __restrict__ rs,
                                                          int64_t r0, int64_t nrows, int64_t c0, int64_t ncols,
-                                                         int8_t* planes, int64_t plane_stride, int64_t ldq, int S) {
+                                                         int8_t* planes, int64_t plane_stride, int64_t ldq, int S,
+                                                         double* corr /* [ncols/512 slots][np] for this panel */, int64_t np) {
     const int64_t groups_per_row = ncols / 16;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nrows * groups_per_row) return;
-    const int64_t row = r0 + idx / groups_per_row;
-    const int64_t col = c0 + (idx % groups_per_row) * 16;
-    const double inv = 1.0 / rs[row];  // power of two: exact
-    double x[16];
-    const double4* src = reinterpret_cast<const double4*>(mat + row * ld + col);
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        const double4 d = src[v];
-        x[4 * v + 0] = d.x * inv * 64.0; x[4 * v + 1] = d.y * inv * 64.0;
-        x[4 * v + 2] = d.z * inv * 64.0; x[4 * v + 3] = d.w * inv * 64.0;
-    }
-    for (int s = 0; s < S; ++s) {
-        uint32_t packed[4];
+    const bool active = idx < nrows * groups_per_row;
+    const int64_t row = r0 + (active ? idx / groups_per_row : 0);
+    const int64_t col = c0 + (active ? (idx % groups_per_row) * 16 : 0);
+    double dropped = 0.0;
+    if (active) {
+        const double inv = 1.0 / rs[row];  // power of two: exact
+        double x[16];
+        const double4* src = reinterpret_cast<const double4*>(mat + row * ld + col);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            uint32_t wv = 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                double& xx = x[4 * v + e];
-                double qd = rint(xx);
-                qd = fmin(fmax(qd, -127.0), 127.0);   // |x| <= 64 (+ rounding) by construction
-                xx = (xx - qd) * 128.0;               // exact
-                wv |= ((uint32_t)(uint8_t)(int8_t)(int)qd) << (8 * e);
-            }
-            packed[v] = wv;
+            const double4 d = src[v];
+            x[4 * v + 0] = d.x * inv * 64.0; x[4 * v + 1] = d.y * inv * 64.0;
+            x[4 * v + 2] = d.z * inv * 64.0; x[4 * v + 3] = d.w * inv * 64.0;
         }
-        *reinterpret_cast<uint4*>(planes + (int64_t)s * plane_stride + row * ldq + col) =
-            make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        int q[8][16];
+        for (int s = 0; s < S; ++s) {
+            uint32_t packed[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                uint32_t wv = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    double& xx = x[4 * v + e];
+                    double qd = rint(xx);
+                    qd = fmin(fmax(qd, -127.0), 127.0);   // |x| <= 64 (+ rounding) by construction
+                    xx = (xx - qd) * 128.0;               // exact
+                    const int qi = (int)qd;
+                    q[s][4 * v + e] = qi;
+                    wv |= ((uint32_t)(uint8_t)(int8_t)qi) << (8 * e);
+                }
+                packed[v] = wv;
+            }
+            *reinterpret_cast<uint4*>(planes + (int64_t)s * plane_stride + row * ldq + col) =
+                make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        // dropped pairs (s + t >= S), grouped by g = s + t so each group is one exact integer sum
+        for (int gsum = S; gsum <= 2 * (S - 1); ++gsum) {
+            int acc = 0;
+            for (int sdig = gsum - (S - 1); sdig <= S - 1; ++sdig) {
+                const int tdig = gsum - sdig;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc += q[sdig][e] * q[tdig][e];
+            }
+            dropped += (double)acc * __longlong_as_double((long long)(1023 - (12 + 7 * gsum)) << 52);
+        }
     }
+    // 32 threads (one warp) cover 512 columns of one row when ncols >= 512; reduce and add once per warp
+    const int lanes_per_row = (groups_per_row < 32) ? (int)groups_per_row : 32;
+    for (int o = lanes_per_row >> 1; o > 0; o >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
+    if (active && ((threadIdx.x & 31) % lanes_per_row) == 0) {
+        const int64_t slot = (col - c0) / 512;
+        const double r2 = rs[row] * rs[row];
+        corr[slot * np + row] = r2 * dropped;   // one writer per (slot, row)
+    }
+}
+
+// C_ii -= sum over previous panels/slots of corr[.][i] for the rows of block column [c0, c0+kb)
+__global__ void diag_correct_kernel(double* mat, int64_t ld, const double* corr, int64_t nslots, int64_t np, int64_t c0,
+                                    int64_t kb) {
+    const int64_t i = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c0 + kb) return;
+    double s = 0.0;
+    for (int64_t t = 0; t < nslots; ++t) s += corr[t * np + i];   // fixed order: deterministic
+    mat[i * ld + i] -= s;
 }
 
 // rs[i] = 2^ceil(log2 sqrt(K_ii)), K_ii = kdiag + diag[i]; identity pad rows get 1
@@ -459,8 +496,8 @@ static void launch_cfg(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
             const int64_t rlo = a.row0 + (int64_t)ci * CM * TM, rhi = rlo + (int64_t)CM * TM - 1;
             const int64_t clo = a.col0 + (int64_t)cj * CN * TN, chi = clo + (int64_t)CN * TN - 1;
             if (a.skip_upper && rhi < clo) continue;
-            const bool dg = a.skip_upper && !(rlo > chi);
-            pairs_tiles += (double)(CM * CN) * (dg ? (double)a.S * a.S : 0.5 * a.S * (a.S + 1));
+            (void)chi;
+            pairs_tiles += (double)(CM * CN) * 0.5 * a.S * (a.S + 1);
         }
     ctx->prof.i8_ops += 2.0 * pairs_tiles * (double)TM * TN * (double)a.K;
 }
@@ -528,8 +565,11 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
     b200gp_ctx* ctx = s->ctx;
     const int64_t np = s->np, ld = np;
     int64_t NB = ctx->nb;
-    if (NB < 256) NB = 256;
-    NB = (NB / 256) * 256;
+    {   // power of two >= 256 (the digit-cutting kernel reduces per 512-column group with warp shuffles)
+        int64_t p2 = 256;
+        while (p2 * 2 <= NB) p2 *= 2;
+        NB = p2;
+    }
     if (S < 2) S = 2;
     if (S > 8) S = 8;
     const bool lookahead = ctx->oz_lookahead != 0;
@@ -539,6 +579,11 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
     double* rs = (double*)ctx->alloc((size_t)np * 8);
     int* err = (int*)ctx->alloc(sizeof(int));
     CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), ctx->stream));
+    const int64_t slots_per_panel = (NB + 511) / 512;
+    const int64_t ncol_all = (np + NB - 1) / NB;
+    const size_t corr_bytes = (size_t)ncol_all * slots_per_panel * np * 8;
+    double* corr = (double*)ctx->alloc(corr_bytes);
+    CUDA_CHECK(cudaMemsetAsync(corr, 0, corr_bytes, ctx->stream));
     int big = INT_MAX;
     CUDA_CHECK(cudaMemcpyAsync(s->info_dev, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     oz::row_scale_kernel<<<(unsigned)((np + 255) / 256), 256, 0, ctx->stream>>>(dense_kernel_diag_value(s->prog), s->diag_dev,
@@ -594,10 +639,17 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
                 CUDA_CHECK(cudaStreamWaitEvent(upd, ev_cut[J - 1], 0));
                 update(c0, kb, (int64_t)(J - 1) * NB, NB);                        // panel J-1
             }
-            CUDA_CHECK(cudaEventRecord(ev_upd[J], upd));
-            CUDA_CHECK(cudaStreamWaitEvent(pan, ev_upd[J], 0));
         } else if (J >= 1) {
             update(c0, kb, 0, c0);
+        }
+        if (J >= 1) {   // exact diagonal part of the dropped digit pairs (all previous panels)
+            oz::diag_correct_kernel<<<(unsigned)((kb + 255) / 256), 256, 0, upd>>>(s->mat, ld, corr, (int64_t)J * slots_per_panel,
+                                                                                  np, c0, kb);
+            ctx->launches++;
+        }
+        if (lookahead) {
+            CUDA_CHECK(cudaEventRecord(ev_upd[J], upd));
+            CUDA_CHECK(cudaStreamWaitEvent(pan, ev_upd[J], 0));
         }
         // ---- stream pan: factor the panel in fp64 (DMMA path), then cut the digits of the rows below it
         ctx->stream = pan;
@@ -610,7 +662,8 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
             const int64_t nthreads = nrows * (kb / 16);
             ProfTimer t(ctx, &ctx->prof.build_ms);
             oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, pan>>>(
-                s->mat, ld, rs, c0 + kb, nrows, c0, kb, planes, (int64_t)plane_stride, np, S);
+                s->mat, ld, rs, c0 + kb, nrows, c0, kb, planes, (int64_t)plane_stride, np, S,
+                corr + (size_t)J * slots_per_panel * np, np);
             ctx->launches++;
         }
         if (lookahead) CUDA_CHECK(cudaEventRecord(ev_cut[J], pan));
@@ -628,6 +681,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
     ctx->release(planes, plane_stride * S);
     ctx->release(rs, (size_t)np * 8);
     ctx->release(err, sizeof(int));
+    ctx->release(corr, corr_bytes);
     if (herr) throw GpError("int8 tensor update: pipeline wait timed out (internal protocol error)");
     if (s->info == INT_MAX) s->info = 0;
     if (s->info > s->n) s->info = 0;

@@ -54,7 +54,7 @@ def test_ozaki_factor_parity(ctx, n, nb, slices, lookahead):
         s = solvers.DirectSolver(k, X, noise.Diagonal(diag))
         lp = GaussianProcess(k, X, diag=diag).log_probability(y)
     finally:
-        ctx.set_option("ozaki_lookahead", 1)
+        ctx.set_option("ozaki_lookahead", 0)
         ctx.set_option("ozaki_slices", 0)
         ctx.set_option("ozaki_min_n", 4096)
         ctx.set_option("nb", 512)

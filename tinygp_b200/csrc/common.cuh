@@ -57,7 +57,7 @@ struct b200gp_ctx {
     int64_t peak_iters = 4096;  // loop length of the fp64 peak micro-benchmarks
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
     int64_t oz_slices = 0;      // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu)
-    int64_t oz_lookahead = 1;   // overlap the fp64 panel factorisation with the int8 update on a second stream
+    int64_t oz_lookahead = 0;   // overlap the fp64 panel factorisation with the int8 update on a second stream
     cudaStream_t stream2 = nullptr;
     int64_t oz_cluster = 22;    // cluster shape of the int8 update kernel (CM*10 + CN), see ozaki.cu
     int64_t oz_min_n = 4096;    // below this size the native DMMA path is used

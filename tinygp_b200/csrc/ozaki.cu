@@ -177,8 +177,11 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
     if (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
     const int cm = crank % CM, cn = crank / CM;
     const int cluster_id = (int)blockIdx.x / CS;
-    const int ctm = (g.tiles_m + CM - 1) / CM;            // cluster tiles along M
-    const int ci = cluster_id % ctm, cj = cluster_id / ctm;
+    // tj fastest: the tiles_n (= nb/256, e.g. 4) column tiles of one row panel are adjacent in launch order, so
+    // co-resident CTAs share every A row panel (and all share the few B panels) in L2 instead of each streaming
+    // its own A panel from DRAM (ncu, round 1: 8.1 GB DRAM reads per launch, 62 % L2 hit rate with ti fastest)
+    const int ctn = (g.tiles_n + CN - 1) / CN;            // cluster tiles along N
+    const int ci = cluster_id / ctn, cj = cluster_id % ctn;
     const int ti = ci * CM + cm, tj = cj * CN + cn;
     const int64_t grow0 = g.row0 + (int64_t)ti * TM;      // global row of tile row 0
     const int64_t gcol0 = g.col0 + (int64_t)tj * TN;      // global col of tile col 0

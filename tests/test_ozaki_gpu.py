@@ -20,7 +20,7 @@ def _ref_update(C, planes, rs, S):
     return out
 
 
-@pytest.mark.parametrize("cluster", [11, 21, 12, 22, 41, 42])
+@pytest.mark.parametrize("cluster", [2, 11, 21, 12, 22, 41, 42])
 @pytest.mark.parametrize("rows,K,S", [(256, 128, 1), (256, 512, 3), (512, 1024, 8), (768, 384, 7)])
 def test_i8_update_kernel_is_exact(ctx, rows, K, S, cluster):
     ctx.set_option("ozaki_cluster", cluster)

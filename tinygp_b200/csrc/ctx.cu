@@ -40,8 +40,8 @@ void b200gp_ctx::release(void* p, size_t bytes) {
     cache.push_back({p, bytes});
     size_t total = 0;
     for (auto& c : cache) total += c.bytes;
-    // keep at most ~48 GiB or 64 entries cached
-    while (cache.size() > 64 || total > ((size_t)48 << 30)) {
+    // keep at most ~110 GiB or 64 entries cached (N = 65536: 34 GB matrix + up to 34 GB of int8 digit planes)
+    while (cache.size() > 64 || total > ((size_t)110 << 30)) {
         cudaStreamSynchronize(stream);
         total -= cache.front().bytes;
         cudaFree(cache.front().ptr);

@@ -340,6 +340,197 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
     }
 }
 
+// ---- 2-SM variant: tcgen05.mma.cta_group::2, one 256 x 256 tile per CTA pair -------------------------------
+// Each CTA of the pair fetches its own 128 A rows and only HALF of the B tile (128 of 256 rows); the MMA reads
+// the other half from the peer's shared memory.  Per-SM operand ingest drops from 48 KB to 32 KB per K = 128
+// stage, which is what bounds the 1-SM kernel (ncu: tensor pipe ~50 % with nothing else saturated), and the
+// freed shared memory buys two more pipeline stages.
+constexpr int STAGES2 = 6;
+constexpr int STAGE2_BYTES = A_BYTES + A_BYTES;             // A 128 rows + B half 128 rows = 32 KiB
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t local_addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;\n" : "=r"(r) : "r"(local_addr));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(IDESC2), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_constant__ Maps maps, const Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* full = bars;                     // [STAGES2]  (used in the leader CTA only)
+    uint64_t* empty = bars + STAGES2;          // [STAGES2]  (one per CTA, signalled by the MMA commit multicast)
+    uint64_t* tfull = bars + 2 * STAGES2;      // [2]        (one per CTA)
+    uint64_t* tempty = bars + 2 * STAGES2 + 2; // [2]        (leader only; 8 arrivals: 4 epilogue warps x 2 CTAs)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
+    const bool leader = (crank == 0);
+    const int pair_id = (int)blockIdx.x >> 1;
+    const int ptm = (g.tiles_m + 1) / 2;                     // row pairs
+    const int pi = pair_id / g.tiles_n, tj = pair_id % g.tiles_n;   // tj fastest (L2 sharing of A panels)
+    (void)ptm;
+    const int64_t prow0 = g.row0 + (int64_t)pi * 2 * TM;     // first row of the 256-row pair tile
+    const int64_t grow0 = prow0 + (int64_t)crank * TM;       // this CTA's 128 rows
+    const int64_t gcol0 = g.col0 + (int64_t)tj * TN;
+    if (g.skip_upper && prow0 + 2 * TM - 1 < gcol0) return;  // pair-uniform
+
+    const int S = g.S;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tfull + 0, 1); mbar_init(tfull + 1, 1);
+        mbar_init(tempty + 0, 8); mbar_init(tempty + 1, 8);
+        *abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int KT = g.K / KC;
+    const int64_t brow0 = g.b_row0 + (int64_t)tj * TN + (int64_t)crank * 128;  // this CTA's half of the B rows
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; completion is signalled on the LEADER's full barrier) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int gi = 0; gi < S && ok; ++gi) {
+                for (int s = 0; s <= gi && ok; ++s) {
+                    const int t = gi - s;
+                    for (int kc = 0; kc < KT; ++kc) {
+                        if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; break; }
+                        uint8_t* a_dst = smem + stage * STAGE2_BYTES;
+                        uint8_t* b_dst = a_dst + A_BYTES;
+                        if (leader) mbar_expect_tx(full + stage, 2 * STAGE2_BYTES);   // both CTAs' bytes
+                        const uint32_t lbar = mapa_rank0(smem_u32(full + stage));
+                        const int kx = g.k_begin + kc * KC;
+#pragma unroll
+                        for (int bx = 0; bx < TM / BOXR; ++bx) {
+                            tma_load_2d_2sm(a_dst + bx * BOXR * KC, &maps.plane[s], lbar, kx, (int)grow0 + bx * BOXR);
+                            tma_load_2d_2sm(b_dst + bx * BOXR * KC, &maps.plane[t], lbar, kx, (int)brow0 + bx * BOXR);
+                        }
+                        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives both SMs =====
+        if (leader && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int gi = 0; gi < S && ok; ++gi) {
+                const int acc = gi & 1;
+                if (gi >= 2) {
+                    if (!mbar_wait(tempty + acc, ((gi >> 1) - 1) & 1, abort_flag)) { ok = false; break; }
+                    tc_fence_after();
+                }
+                const uint32_t tacc = tmem_base + (uint32_t)acc * TN;
+                uint32_t accumulate = 0;
+                for (int s = 0; s <= gi && ok; ++s) {
+                    for (int kc = 0; kc < KT; ++kc) {
+                        if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
+                        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < KC / 32; ++kk) {
+                            umma_i8_2sm(tacc, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), accumulate);
+                            accumulate = 1;
+                        }
+                        tc_commit_2sm(empty + stage, 0x3);   // free the slot in both CTAs
+                        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                    }
+                }
+                if (ok) tc_commit_2sm(tfull + acc, 0x3);     // accumulators (both CTAs) of group gi complete
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): this CTA's 128 rows x 256 columns =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int64_t gr = grow0 + row;
+        const bool row_ok = gr < g.n_rows;
+        const double rsi = row_ok ? g.rs[gr] : 0.0;
+        double* crow = g.C + (row_ok ? gr : 0) * g.ldc;
+        const uint32_t tempty_leader0 = mapa_rank0(smem_u32(tempty + 0));
+        const uint32_t tempty_leader1 = mapa_rank0(smem_u32(tempty + 1));
+        bool ok = true;
+        for (int gi = 0; gi < S && ok; ++gi) {
+            const int acc = gi & 1;
+            if (!mbar_wait(tfull + acc, (gi >> 1) & 1, abort_flag)) { ok = false; break; }
+            tc_fence_after();
+            const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
+            const double sc = -(rsi * wg);
+#pragma unroll 1
+            for (int cb = 0; cb < TN / 32; ++cb) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb * 32), r);
+                const int64_t gc = gcol0 + cb * 32;
+                if (row_ok && gc < g.n_rows) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
+                        double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
+                        cv.x = fma(sc * rj.x, (double)(int)r[j], cv.x);
+                        cv.y = fma(sc * rj.y, (double)(int)r[j + 1], cv.y);
+                        *reinterpret_cast<double2*>(crow + gc + j) = cv;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (threadIdx.x == 0 && *abort_flag) atomicExch(g.error_flag, 1);
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // ---- digit cutting -------------------------------------------------------------------------------
 // planes[s][row * ldq + col] for rows [r0, np), cols [c0, c0 + ncols); 16 columns per thread.
 // Also accumulates, per row, the dropped diagonal pairs  sum_{s+t>=S} 2^-(12+7(s+t)) sum_k q_s q_t  (exact integer
@@ -505,9 +696,44 @@ static void launch_cfg(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     ctx->prof.i8_ops += 2.0 * pairs_tiles * (double)TM * TN * (double)a.K;
 }
 
-// cluster shape code: 11 = 1x1 (no multicast), 21 = 2x1, 12 = 1x2, 22 = 2x2, 41 = 4x1, 42 = 4x2
+static void launch_2sm(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
+    static bool attr = false;
+    if (!attr) {
+        CUDA_CHECK(cudaFuncSetAttribute(i8_update_kernel_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+        attr = true;
+    }
+    const int ptm = (a.tiles_m + 1) / 2;
+    const int64_t npairs = (int64_t)ptm * a.tiles_n;
+    if (npairs <= 0 || a.K <= 0) return;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(npairs * 2));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM2_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, i8_update_kernel_2sm, maps, a));
+    ctx->launches++;
+    double pairs_tiles = 0.0;
+    for (int pi = 0; pi < ptm; ++pi)
+        for (int tj = 0; tj < a.tiles_n; ++tj) {
+            const int64_t rlo = a.row0 + (int64_t)pi * 2 * TM, clo = a.col0 + (int64_t)tj * TN;
+            if (a.skip_upper && rlo + 2 * TM - 1 < clo) continue;
+            pairs_tiles += 2.0 * 0.5 * a.S * (a.S + 1);
+        }
+    ctx->prof.i8_ops += 2.0 * pairs_tiles * (double)TM * TN * (double)a.K;
+}
+
+// cluster shape code: 2 = CTA pair with tcgen05 cta_group::2 (256 x 256 tile per pair);
+// 11 = 1x1 (no multicast), 21 = 2x1, 12 = 1x2, 22 = 2x2, 41 = 4x1, 42 = 4x2 (cta_group::1 + TMA multicast)
 void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     switch ((int)ctx->oz_cluster) {
+        case 2: launch_2sm(ctx, maps, a); break;
         case 11: launch_cfg<1, 1>(ctx, maps, a); break;
         case 21: launch_cfg<2, 1>(ctx, maps, a); break;
         case 12: launch_cfg<1, 2>(ctx, maps, a); break;

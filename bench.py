@@ -186,6 +186,7 @@ def run_ours(args, rank, local_rank, world):
     _cabi.set_context(ctx)
     ctx.set_option("nb", args.nb)
     ctx.set_option("ozaki_slices", args.slices)
+    ctx.set_option("ozaki_min_n", 0 if args.slices else 1 << 40)
 
     n = args.n
     X, y, diag, scale = make_dense_problem(n, rank)
@@ -415,6 +416,64 @@ def run_quasisep(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_batched(args, rank, local_rank, world):
+    """BASELINE config 5: 1024 independent N=4096 ExpSquared problems (32 x 32 hyper-parameter grid), sharded
+    128 per GPU at 8 GPUs -- replicas only, no data-path collective.  Non-default workload."""
+    import torch
+    import torch.distributed as dist
+    from tinygp_b200 import _cabi, kernels
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+    ctx = _cabi.Context(device=local_rank, stream=stream.cuda_stream)
+    _cabi.set_context(ctx)
+    n = 4096 if args.n == N_DENSE else args.n
+    nprob = 1024
+    rng = np.random.default_rng(49385)
+    X = np.ascontiguousarray(rng.uniform(0, 8, (n, 3)))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    diag = np.full(n, 0.1)
+    grid = [(s, a) for s in np.logspace(-0.5, 0.5, 32) for a in np.logspace(-1, 1, 32)]
+    mine = grid[rank::world]
+    progs = np.ascontiguousarray(np.stack([(a * kernels.ExpSquared(scale=s)).program() for s, a in mine]))
+    out = np.empty(len(mine))
+
+    def step():
+        ctx.check(ctx.lib.b200gp_dense_log_probability_batched(
+            ctx.handle, _cabi.ptr(progs), progs.shape[1], len(mine), _cabi.ptr(X), n, 3, _cabi.ptr(diag), _cabi.ptr(y),
+            _cabi.ptr(out)))
+
+    for _ in range(args.warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        t = float(ms.item()) * 1e-3
+        print(json.dumps({
+            "metric": "log_probability/sec", "value": nprob * args.steps / t, "unit": "logp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "strong", "dtype": "f64", "data": "synthetic", "vs_baseline": None,
+            "config": {"workload": f"batched: {nprob} x (N={n}) ExpSquared log_probability, hyper-parameter grid, "
+                                   f"{len(mine)} problems per GPU (host buffers, end to end)"},
+            "tflops_n3_over_3": nprob * args.steps * n ** 3 / 3 / t / 1e12,
+            "logp_first": float(out[0]),
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def _read_traffic():
     p = os.path.join(ROOT, "profiles", "syrk_traffic.json")
     try:
@@ -431,14 +490,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_DENSE)
     ap.add_argument("--nb", type=int, default=1024)
-    ap.add_argument("--workload", default="dense", choices=["dense", "quasisep"])
-    ap.add_argument("--slices", type=int, default=0, help="int8 digit planes of the fixed-point update (0 = native DMMA)")
+    ap.add_argument("--workload", default="dense", choices=["dense", "quasisep", "batched"])
+    ap.add_argument("--slices", type=int, default=8,
+                    help="int8 digit planes of the fixed-point trailing update: 8 = 55-bit digits (fp64-equivalent, "
+                         "default), 7 = 48-bit, 0 = native fp64 DMMA")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+    elif args.workload == "batched":
+        run_batched(args, rank, local_rank, world)
     elif args.workload == "quasisep":
         if rank == 0:
             run_quasisep(args, rank, local_rank, world)

@@ -69,6 +69,7 @@ def test_factor_parity(n, ctx):
     diag = rng.uniform(0.05, 0.2, n)
     for nb in (128, 512):
         ctx.set_option("nb", nb)
+        ctx.set_option("ozaki_slices", 0)      # the native fp64 DMMA path is the one under test here
         s = solvers.DirectSolver(k, X, noise.Diagonal(diag))
         so = o.DirectSolver(to_oracle(k), X, o.Diagonal(diag))
         assert s.info == 0
@@ -76,7 +77,8 @@ def test_factor_parity(n, ctx):
         assert rel(s.normalization(), so.normalization()) < 1e-12
         assert_close(s.variance(), so.variance(), 1e-14, 1e-14)
         np.testing.assert_allclose(s.covariance(), so.covariance(), rtol=1e-13, atol=1e-15)
-    ctx.set_option("nb", 512)
+    ctx.set_option("nb", 1024)
+    ctx.set_option("ozaki_slices", 8)
 
 
 @pytest.mark.parametrize("n,ndim,name", [(256, 1, "expsq"), (777, 3, "c3_l2"), (2048, 3, "expsq"),
@@ -210,8 +212,11 @@ def test_sampling_statistics():
     assert gp.sample(1).shape == (30,)
 
 
-def test_large_n_properties():
-    """N = 8192: parity against the oracle (LAPACK dpotrf, ~3 s) plus size-independent identities."""
+@pytest.mark.parametrize("slices", [8, 0])
+def test_large_n_properties(ctx, slices):
+    """N = 8192: parity against the oracle (LAPACK dpotrf, ~3 s) plus size-independent identities, for the
+    default int8 fixed-point trailing update (8 digit planes) and for the native fp64 DMMA path."""
+    ctx.set_option("ozaki_slices", slices)
     rng = np.random.default_rng(49382)
     n = 8192
     X = rng.uniform(0, 10, (n, 3))
@@ -228,6 +233,7 @@ def test_large_n_properties():
     # K (K^-1 y) == y with K applied by the matrix-free kernel matvec
     np.testing.assert_allclose(k.matmul(X, X, a) + 0.1 * a, y, rtol=1e-8, atol=1e-9)
     assert rel(y @ a, np.sum(gp.solver.solve_triangular(y) ** 2)) < 1e-10
+    ctx.set_option("ozaki_slices", 8)
 
 
 def test_batched_hyperparameter_grid(ctx):

@@ -31,7 +31,7 @@ def test_i8_update_kernel_is_exact(ctx, rows, K, S, cluster):
     got = np.ascontiguousarray(C.copy())
     pl = np.ascontiguousarray(planes)
     ctx.check(ctx.lib.b200gp_i8_update_test(ctx.handle, _cabi.ptr(pl), S, rows, K, _cabi.ptr(rs), _cabi.ptr(got)))
-    ctx.set_option("ozaki_cluster", 22)
+    ctx.set_option("ozaki_cluster", 21)
     want = _ref_update(C, planes, rs, S)
     # integer dot products are exact; the only rounding is one fp64 fma per group
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
@@ -55,9 +55,9 @@ def test_ozaki_factor_parity(ctx, n, nb, slices, lookahead):
         lp = GaussianProcess(k, X, diag=diag).log_probability(y)
     finally:
         ctx.set_option("ozaki_lookahead", 0)
-        ctx.set_option("ozaki_slices", 0)
-        ctx.set_option("ozaki_min_n", 4096)
-        ctx.set_option("nb", 512)
+        ctx.set_option("ozaki_slices", 8)
+        ctx.set_option("ozaki_min_n", 8192)
+        ctx.set_option("nb", 1024)
     so = o.DirectSolver(to_oracle(k), X, o.Diagonal(diag))
     lpo = o.GaussianProcess(to_oracle(k), X, diag=diag).log_probability(y)
     assert s.info == 0
@@ -83,9 +83,9 @@ def test_ozaki_non_pd_and_large_scales(ctx):
         bad = GaussianProcess(kernels.Matern32(2.0), rng.uniform(0, 8, (n, 3)), diag=0.1)   # L1 in 3-D: indefinite
         lpbad = bad.log_probability(y)
     finally:
-        ctx.set_option("ozaki_slices", 0)
-        ctx.set_option("ozaki_min_n", 4096)
-        ctx.set_option("nb", 512)
+        ctx.set_option("ozaki_slices", 8)
+        ctx.set_option("ozaki_min_n", 8192)
+        ctx.set_option("nb", 1024)
     lpo = o.GaussianProcess(to_oracle(k), X, diag=diag).log_probability(y)
     assert rel(lp, lpo) < LOGP_RTOL
     assert bad.solver.info > 0 and lpbad == -np.inf

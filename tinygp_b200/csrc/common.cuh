@@ -48,7 +48,7 @@ struct b200gp_ctx {
     bool own_stream = false;
     std::string err;
     int64_t launches = 0;
-    int64_t nb = 512;  // outer panel width of the blocked Cholesky
+    int64_t nb = 1024;  // outer panel width of the blocked Cholesky
     bool profile = false;
     b200gp_profile prof{};
     std::vector<CachedBuf> cache;  // freed big buffers kept for reuse
@@ -56,11 +56,11 @@ struct b200gp_ctx {
     int num_sms = 148;
     int64_t peak_iters = 4096;  // loop length of the fp64 peak micro-benchmarks
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
-    int64_t oz_slices = 0;      // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu)
+    int64_t oz_slices = 8;      // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA
     int64_t oz_lookahead = 0;   // overlap the fp64 panel factorisation with the int8 update on a second stream
     cudaStream_t stream2 = nullptr;
-    int64_t oz_cluster = 22;    // cluster shape of the int8 update kernel (CM*10 + CN), see ozaki.cu
-    int64_t oz_min_n = 4096;    // below this size the native DMMA path is used
+    int64_t oz_cluster = 21;    // cluster shape of the int8 update kernel (CM*10 + CN), see ozaki.cu
+    int64_t oz_min_n = 8192;    // below this size the native DMMA path is used
     // deferred (non-blocking) kernel timers: event pairs resolved at the next flush_timers()
     struct Pending { cudaEvent_t a, b; double* acc; };
     std::vector<Pending> pending;

@@ -221,10 +221,8 @@ def run_ours(args, rank, local_rank, world):
             out = fn()
         e1.record(stream)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out
+        from tinygp_b200.parallel import max_over_ranks
+        return max_over_ranks(e0.elapsed_time(e1), device="cuda"), out
 
     # fp64 tensor peak on this GPU: burst (short loop) and sustained (~2 s loop, the denominator for a kernel
     # timed inside a multi-second step)
@@ -436,7 +434,8 @@ def run_batched(args, rank, local_rank, world):
     y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
     diag = np.full(n, 0.1)
     grid = [(s, a) for s in np.logspace(-0.5, 0.5, 32) for a in np.logspace(-1, 1, 32)]
-    mine = grid[rank::world]
+    from tinygp_b200.parallel import shard_indices
+    mine = [grid[i] for i in shard_indices(len(grid), rank, world)]
     progs = np.ascontiguousarray(np.stack([(a * kernels.ExpSquared(scale=s)).program() for s, a in mine]))
     out = np.empty(len(mine))
 

@@ -1,0 +1,57 @@
+"""The N > 1 host logic (problem sharding, max-over-ranks timing, result gather) on CPU with gloo, world_size 2.
+The data path itself has no collective (replicas); see DESIGN.md section 5."""
+
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tinygp_b200 import parallel
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, nprob, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        idx = parallel.shard_indices(nprob, rank, world)
+        # stand-in for the per-problem log-probabilities computed by this rank's GPU
+        vals = np.sin(idx.astype(np.float64)) - 3.0 * idx
+        full = parallel.gather_results(idx, vals, nprob)
+        tmax = parallel.max_over_ranks(10.0 + rank)
+        q.put((rank, idx.tolist(), full.tolist(), tmax))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharding_is_a_partition():
+    for nprob, world in [(1024, 8), (7, 2), (3, 4), (1, 1)]:
+        seen = np.concatenate([parallel.shard_indices(nprob, r, world) for r in range(world)])
+        assert sorted(seen.tolist()) == list(range(nprob))
+
+
+def test_world_size_2_gloo():
+    world, nprob = 2, 11
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nprob, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.sin(np.arange(nprob, dtype=np.float64)) - 3.0 * np.arange(nprob)
+    for rank, idx, full, tmax in res:
+        assert idx == list(range(rank, nprob, world))
+        np.testing.assert_allclose(full, want, rtol=0, atol=0)
+        assert tmax == 11.0          # max over ranks of (10 + rank)

@@ -86,6 +86,8 @@ int b200gp_measure_fp64_peak(b200gp_ctx* ctx, double* dmma_tflops, double* dfma_
 /* int8 tensor peak micro-benchmark: tcgen05.mma kind::i8 (M=128, N=256, K=32) issued back to back on every SM
  * from resident shared-memory operands (no TMA traffic); returns TOP/s (2 x MAC). */
 int b200gp_measure_i8_peak(b200gp_ctx* ctx, double* tops);
+/* same with tcgen05.mma.cta_group::2 on CTA pairs (M = 256) */
+int b200gp_measure_i8_peak_2sm(b200gp_ctx* ctx, double* tops);
 
 /* diagnostics for the int8 fixed-point tensor-core update (tcgen05.mma kind::i8, ozaki.cu):
  * C (rows x rows, host, in/out) -= sum_{s+t<S} 2^-(12+7(s+t)) rs_i rs_j Q_s Q_t^T with Q_s the S int8 digit planes
@@ -149,6 +151,21 @@ int b200gp_dense_log_probability_dev(b200gp_ctx* ctx, const double* prog, int n_
 int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const double* progs, int n_instr,
                                          int64_t nbatch, const double* X, int64_t n, int ndim,
                                          const double* diag, const double* resid, double* logp);
+
+/* ---- one dense log_probability sharded over several GPUs (one process per GPU) ---------------------------
+ * Step API driven by the host (tinygp_b200/multigpu.py) with ONE all-gather per block column in between
+ * (torch.distributed / NCCL): for J in 0..ncol-1: update_rows(J, my rows) -> pack -> [all_gather] -> unpack ->
+ * panel(J); then finish().  Every rank ends up with the complete factor. */
+typedef struct b200gp_mg b200gp_mg;
+int b200gp_mg_create(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
+                     const double* diag, int slices, b200gp_mg** out);
+int b200gp_mg_free(b200gp_mg* m);
+int b200gp_mg_geometry(b200gp_mg* m, int64_t* np, int64_t* nb, int* ncol);
+int b200gp_mg_update_rows(b200gp_mg* m, int J, int64_t r0, int64_t r1);
+int b200gp_mg_pack(b200gp_mg* m, int J, int64_t r0, int64_t r1, double* buf_dev);
+int b200gp_mg_unpack(b200gp_mg* m, int J, int64_t r0, int64_t r1, const double* buf_dev);
+int b200gp_mg_panel(b200gp_mg* m, int J);
+int b200gp_mg_finish(b200gp_mg* m, const double* resid, double* logp);
 
 /* ---- solvers.QuasisepSolver  (solvers/quasisep/solver.py:19-139) ------------------------- */
 /* Quasiseparable kernels (kernels/quasisep.py) are lowered to a list of `ncomp` components

@@ -20,7 +20,7 @@ def _ref_update(C, planes, rs, S):
     return out
 
 
-@pytest.mark.parametrize("cluster", [2, 11, 21, 12, 22, 41, 42])
+@pytest.mark.parametrize("cluster", [1, 2, 11, 21, 12, 22, 41, 42])
 @pytest.mark.parametrize("rows,K,S", [(256, 128, 1), (256, 512, 3), (512, 1024, 8), (768, 384, 7)])
 def test_i8_update_kernel_is_exact(ctx, rows, K, S, cluster):
     ctx.set_option("ozaki_cluster", cluster)
@@ -89,3 +89,22 @@ def test_ozaki_non_pd_and_large_scales(ctx):
     lpo = o.GaussianProcess(to_oracle(k), X, diag=diag).log_probability(y)
     assert rel(lp, lpo) < LOGP_RTOL
     assert bad.solver.info > 0 and lpbad == -np.inf
+
+
+def test_sharded_step_api_single_rank():
+    """The multi-GPU step API (update_rows / pack / unpack / panel / finish) with world_size 1."""
+    from tinygp_b200 import multigpu
+    rng = np.random.default_rng(77)
+    n = 3000
+    X = rng.uniform(0, 7, (n, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    k = 1.3 * kernels.ExpSquared(0.8)
+    ctx = _cabi.get_context()
+    ctx.set_option("nb", 512)
+    try:
+        for slices in (8, 7):
+            lp = multigpu.log_probability_sharded(k, X, np.full(n, 0.1), y, slices=slices)
+            lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+            assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+    finally:
+        ctx.set_option("nb", 1024)

@@ -55,3 +55,21 @@ def test_world_size_2_gloo():
         assert idx == list(range(rank, nprob, world))
         np.testing.assert_allclose(full, want, rtol=0, atol=0)
         assert tmax == 11.0          # max over ranks of (10 + rank)
+
+
+def test_row_chunks_partition_every_block_column():
+    from tinygp_b200 import multigpu
+    for np_, nb, world in [(65536, 1024, 8), (131072, 1024, 8), (3072, 256, 2), (1280, 256, 4), (256, 256, 2)]:
+        for c0 in range(0, np_, nb):
+            ch = multigpu.row_chunk(np_, c0, world)
+            assert ch % multigpu.ALIGN == 0
+            cover = []
+            for r in range(world):
+                r0, r1 = multigpu.my_rows(np_, c0, world, r)
+                assert c0 <= r0 <= r1 <= np_ and r0 % 128 == 0 and (r1 - r0) <= ch
+                cover.append((r0, r1))
+            # contiguous, disjoint, complete
+            assert cover[0][0] == c0
+            for (a0, a1), (b0, b1) in zip(cover, cover[1:]):
+                assert a1 == b0 or (a1 == np_ and b0 == np_)
+            assert max(r1 for _, r1 in cover) == np_

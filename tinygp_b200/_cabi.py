@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200gp_get_profile": (c_int, [c_void_p, POINTER(Profile), c_int]),
     "b200gp_measure_fp64_peak": (c_int, [c_void_p, c_double_p, c_double_p]),
     "b200gp_measure_i8_peak": (c_int, [c_void_p, c_double_p]),
+    "b200gp_measure_i8_peak_2sm": (c_int, [c_void_p, c_double_p]),
     "b200gp_i8_update_test": (c_int, [_V, _D, _I, _L, _L, _D, _D]),
     "b200gp_kernel_matrix": (c_int, [_V, _D, _I, _D, _L, _D, _L, _I, _D]),
     "b200gp_kernel_diag": (c_int, [_V, _D, _I, _D, _L, _I, _D]),
@@ -66,6 +67,14 @@ SIGNATURES = {
     "b200gp_dense_log_probability": (c_int, [_V, _D, _I, _D, _L, _I, _D, _D, c_double_p]),
     "b200gp_dense_log_probability_dev": (c_int, [_V, _D, _I, _D, _L, _I, _D, _D, c_double_p]),
     "b200gp_dense_log_probability_batched": (c_int, [_V, _D, _I, _L, _D, _L, _I, _D, _D, _D]),
+    "b200gp_mg_create": (c_int, [_V, _D, _I, _D, _L, _I, _D, _I, POINTER(c_void_p)]),
+    "b200gp_mg_free": (c_int, [_V]),
+    "b200gp_mg_geometry": (c_int, [_V, POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]),
+    "b200gp_mg_update_rows": (c_int, [_V, _I, _L, _L]),
+    "b200gp_mg_pack": (c_int, [_V, _I, _L, _L, _D]),
+    "b200gp_mg_unpack": (c_int, [_V, _I, _L, _L, _D]),
+    "b200gp_mg_panel": (c_int, [_V, _I]),
+    "b200gp_mg_finish": (c_int, [_V, _D, c_double_p]),
     "b200gp_qs_check_sorted": (c_int, [_V, _D, _L, POINTER(c_int)]),
     "b200gp_qs_create": (c_int, [_V, _D, _I, _D, _L, _D, _I, POINTER(c_void_p), POINTER(c_int), POINTER(c_int)]),
     "b200gp_qs_create_dev": (c_int, [_V, _D, _I, _D, _L, _D, _I, POINTER(c_void_p), POINTER(c_int), POINTER(c_int)]),

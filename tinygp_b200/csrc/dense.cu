@@ -597,6 +597,27 @@ void dense_build_region(b200gp_dense* s, int64_t r0, int64_t c0, int64_t ncols) 
 
 double dense_kernel_diag_value(const KProg& P) { return kprog_eval(P, 0.0, 0.0); }
 
+// rows [r0, r1) x columns [c0, c0+ncols) only (multi-GPU row sharding)
+struct BuildRegionArgs { int64_t r0, r1, c0, ncols; };
+void dense_build_rows(b200gp_dense* s, const BuildRegionArgs& q) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t ld = s->np;
+    BuildArgs a{};
+    a.X1 = s->X_dev + q.r0 * s->ndim;
+    a.X2 = s->X_dev + q.c0 * s->ndim;
+    a.diag = s->diag_dev; a.out = s->mat + q.r0 * ld + q.c0; a.ld = ld;
+    a.n1 = (s->n > q.r0) ? ((s->n - q.r0 < q.r1 - q.r0) ? (s->n - q.r0) : (q.r1 - q.r0)) : 0;
+    a.n2 = (s->n > q.c0) ? ((s->n - q.c0 < q.ncols) ? (s->n - q.c0) : q.ncols) : 0;
+    a.rows_pad = q.r1 - q.r0; a.cols_pad = q.ncols;
+    a.row_off = q.r0; a.col_off = q.c0; a.ndim = s->ndim; a.pad_identity = 1;
+    dim3 grid((unsigned)((q.ncols + BUILD_COLS - 1) / BUILD_COLS), (unsigned)((q.r1 - q.r0 + BUILD_ROWS - 1) / BUILD_ROWS));
+    ProfTimer t(ctx, &ctx->prof.build_ms);
+    build_rect_kernel<<<grid, 256, 0, ctx->stream>>>(s->prog, a);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    ctx->prof.build_bytes += 8.0 * (double)(q.r1 - q.r0) * (double)q.ncols;
+}
+
 void dense_factor_ozaki(b200gp_dense* s, int S);  // ozaki.cu
 
 void dense_factor_inplace(b200gp_dense* s, bool generate) {
@@ -842,6 +863,7 @@ static inline unsigned nblocks(int64_t n, int t) { return (unsigned)((n + t - 1)
 // =============================================================================================
 // object lifecycle
 // =============================================================================================
+static b200gp_dense* dense_alloc(b200gp_ctx* ctx, int64_t n);
 static b200gp_dense* dense_alloc(b200gp_ctx* ctx, int64_t n) {
     if (n <= 0) throw GpError("dense: n must be positive");
     b200gp_dense* s = new b200gp_dense();
@@ -870,6 +892,27 @@ void dense_destroy(b200gp_dense* s) {
         if (s->diag_dev) ctx->release(s->diag_dev, (size_t)s->n * sizeof(double));
     }
     delete s;
+}
+
+// allocate the dense object and copy X / diag to the device, WITHOUT factoring (multi-GPU step API)
+b200gp_dense* dense_alloc_for_prog(b200gp_ctx* ctx, const KProg& prog, const double* X, int64_t n, int ndim,
+                                   const double* diag) {
+    if (ndim < 1 || ndim > MAX_NDIM) throw GpError("dense: ndim must be in [1, 16]");
+    b200gp_dense* s = dense_alloc(ctx, n);
+    try {
+        s->has_prog = true;
+        s->prog = prog;
+        s->ndim = ndim;
+        s->owns_inputs = true;
+        s->X_dev = (double*)ctx->alloc((size_t)n * ndim * sizeof(double));
+        s->diag_dev = (double*)ctx->alloc((size_t)n * sizeof(double));
+        CUDA_CHECK(cudaMemcpyAsync(s->X_dev, X, (size_t)n * ndim * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(s->diag_dev, diag, (size_t)n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    } catch (...) {
+        dense_destroy(s);
+        throw;
+    }
+    return s;
 }
 
 b200gp_dense* dense_factor_from_prog(b200gp_ctx* ctx, const KProg& prog, const double* X_dev, int64_t n,

@@ -531,6 +531,145 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
     }
 }
 
+// ---- wide-tile variant: one CTA computes 256 x 256 (two M = 128 MMAs share every B stage) -------------------
+// Same per-SM operand ingest as the 2-SM pair kernel (64 KB per 2 x 128x256x128 MACs instead of 48 KB per one)
+// without a cluster.  TMEM holds the two 256-column accumulators of ONE digit group, so the epilogue of group g
+// is not overlapped with the MMAs of group g+1 (negligible once K is a few thousand).
+constexpr int STAGES_W = 3;
+constexpr int STAGE_W_BYTES = 2 * A_BYTES + B_BYTES;        // 64 KiB
+constexpr int SMEM_W_BYTES = STAGES_W * STAGE_W_BYTES + 1024 + 256;
+constexpr int THREADS_W = 320;                               // producer warp, MMA warp, 8 epilogue warps
+
+__global__ void __launch_bounds__(THREADS_W, 1) i8_update_kernel_wide(const __grid_constant__ Maps maps, const Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES_W * STAGE_W_BYTES);
+    uint64_t* full = bars;                    // [STAGES_W]
+    uint64_t* empty = bars + STAGES_W;        // [STAGES_W]
+    uint64_t* tfull = bars + 2 * STAGES_W;    // [1]
+    uint64_t* tempty = bars + 2 * STAGES_W + 1;  // [1], 8 arrivals
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES_W + 2);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pi = (int)blockIdx.x / g.tiles_n, tj = (int)blockIdx.x % g.tiles_n;   // tj fastest
+    const int64_t prow0 = g.row0 + (int64_t)pi * 2 * TM;
+    const int64_t gcol0 = g.col0 + (int64_t)tj * TN;
+    if (g.skip_upper && prow0 + 2 * TM - 1 < gcol0) return;
+    const int S = g.S;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES_W; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 8);
+        *abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int KT = g.K / KC;
+    const int64_t brow0 = g.b_row0 + (int64_t)tj * TN;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int gi = 0; gi < S && ok; ++gi)
+                for (int s = 0; s <= gi && ok; ++s) {
+                    const int t = gi - s;
+                    for (int kc = 0; kc < KT; ++kc) {
+                        if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; break; }
+                        uint8_t* a_dst = smem + stage * STAGE_W_BYTES;
+                        uint8_t* b_dst = a_dst + 2 * A_BYTES;
+                        mbar_expect_tx(full + stage, STAGE_W_BYTES);
+                        const int kx = g.k_begin + kc * KC;
+#pragma unroll
+                        for (int bx = 0; bx < (2 * TM) / BOXR; ++bx)
+                            tma_load_2d(a_dst + bx * BOXR * KC, &maps.plane[s], full + stage, kx, (int)prow0 + bx * BOXR);
+#pragma unroll
+                        for (int bx = 0; bx < TN / BOXR; ++bx)
+                            tma_load_2d(b_dst + bx * BOXR * KC, &maps.plane[t], full + stage, kx, (int)brow0 + bx * BOXR);
+                        if (++stage == STAGES_W) { stage = 0; phase ^= 1; }
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int gi = 0; gi < S && ok; ++gi) {
+                if (gi >= 1) {  // both accumulators must have been drained (group gi-1)
+                    if (!mbar_wait(tempty, (gi - 1) & 1, abort_flag)) { ok = false; break; }
+                    tc_fence_after();
+                }
+                uint32_t accumulate = 0;
+                for (int s = 0; s <= gi && ok; ++s)
+                    for (int kc = 0; kc < KT; ++kc) {
+                        if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(smem + stage * STAGE_W_BYTES);
+                        const uint32_t a1 = a0 + A_BYTES, b = a0 + 2 * A_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < KC / 32; ++kk) {
+                            const uint64_t db = make_desc(b + kk * 32);
+                            umma_i8(tmem_base, make_desc(a0 + kk * 32), db, accumulate);
+                            umma_i8(tmem_base + TN, make_desc(a1 + kk * 32), db, accumulate);
+                            accumulate = 1;
+                        }
+                        tc_commit(empty + stage);
+                        if (++stage == STAGES_W) { stage = 0; phase ^= 1; }
+                    }
+                if (ok) tc_commit(tfull);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp >= 6) ? 1 : 0;                 // which 128-row sub-tile / accumulator
+        const int64_t gr = prow0 + half * TM + q * 32 + lane;
+        const bool row_ok = gr < g.n_rows;
+        const double rsi = row_ok ? g.rs[gr] : 0.0;
+        double* crow = g.C + (row_ok ? gr : 0) * g.ldc;
+        bool ok = true;
+        for (int gi = 0; gi < S && ok; ++gi) {
+            if (!mbar_wait(tfull, gi & 1, abort_flag)) { ok = false; break; }
+            tc_fence_after();
+            const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
+            const double sc = -(rsi * wg);
+#pragma unroll 1
+            for (int cb = 0; cb < TN / 32; ++cb) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * TN + cb * 32), r);
+                const int64_t gc = gcol0 + cb * 32;
+                if (row_ok && gc < g.n_rows) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
+                        double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
+                        cv.x = fma(sc * rj.x, (double)(int)r[j], cv.x);
+                        cv.y = fma(sc * rj.y, (double)(int)r[j + 1], cv.y);
+                        *reinterpret_cast<double2*>(crow + gc + j) = cv;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && *abort_flag) atomicExch(g.error_flag, 1);
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+}
+
 // ---- digit cutting -------------------------------------------------------------------------------
 // planes[s][row * ldq + col] for rows [r0, np), cols [c0, c0 + ncols); 16 columns per thread.
 // Also accumulates, per row, the dropped diagonal pairs  sum_{s+t>=S} 2^-(12+7(s+t)) sum_k q_s q_t  (exact integer
@@ -729,10 +868,34 @@ static void launch_2sm(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     ctx->prof.i8_ops += 2.0 * pairs_tiles * (double)TM * TN * (double)a.K;
 }
 
-// cluster shape code: 2 = CTA pair with tcgen05 cta_group::2 (256 x 256 tile per pair);
+static void launch_wide(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
+    static bool attr = false;
+    if (!attr) {
+        CUDA_CHECK(cudaFuncSetAttribute(i8_update_kernel_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_BYTES));
+        attr = true;
+    }
+    const int ptm = (a.tiles_m + 1) / 2;
+    const int64_t nt = (int64_t)ptm * a.tiles_n;
+    if (nt <= 0 || a.K <= 0) return;
+    i8_update_kernel_wide<<<(unsigned)nt, THREADS_W, SMEM_W_BYTES, ctx->stream>>>(maps, a);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    double pairs_tiles = 0.0;
+    for (int pi = 0; pi < ptm; ++pi)
+        for (int tj = 0; tj < a.tiles_n; ++tj) {
+            const int64_t rlo = a.row0 + (int64_t)pi * 2 * TM, clo = a.col0 + (int64_t)tj * TN;
+            if (a.skip_upper && rlo + 2 * TM - 1 < clo) continue;
+            pairs_tiles += 2.0 * 0.5 * a.S * (a.S + 1);
+        }
+    ctx->prof.i8_ops += 2.0 * pairs_tiles * (double)TM * TN * (double)a.K;
+}
+
+// cluster shape code: 1 = wide 256 x 256 tile per CTA (two MMAs per B stage, no cluster);
+// 2 = CTA pair with tcgen05 cta_group::2 (256 x 256 tile per pair);
 // 11 = 1x1 (no multicast), 21 = 2x1, 12 = 1x2, 22 = 2x2, 41 = 4x1, 42 = 4x2 (cta_group::1 + TMA multicast)
 void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     switch ((int)ctx->oz_cluster) {
+        case 1: launch_wide(ctx, maps, a); break;
         case 2: launch_2sm(ctx, maps, a); break;
         case 11: launch_cfg<1, 1>(ctx, maps, a); break;
         case 21: launch_cfg<2, 1>(ctx, maps, a); break;
@@ -781,12 +944,56 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int* sink) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
 }
 
+// same with cta_group::2 (CTA pair, M = 256): does the 2-SM MMA itself run at full rate?
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel_2sm(int iters, int* sink) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + STAGE2_BYTES);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
+    int crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
+    for (int i = threadIdx.x; i < STAGE2_BYTES / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        *abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if ((threadIdx.x >> 5) == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    if (crank == 0 && threadIdx.x == 32) {
+        const uint32_t a_addr = smem_u32(smem), b_addr = a_addr + A_BYTES;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                umma_i8_2sm(tmem_base + (uint32_t)((it & 1) * TN), make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), 1u);
+        }
+        tc_commit_2sm(bar, 0x1);
+        if (!mbar_wait(bar, 0, abort_flag)) atomicExch(sink, 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if ((threadIdx.x >> 5) == 1)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
+}
+
 }  // namespace oz
 
 // ================================================================================================
 // left-looking factorisation driver
 // ================================================================================================
 void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb);                       // dense.cu
+struct BuildRegionArgs { int64_t r0, r1, c0, ncols; };
+void dense_build_rows(b200gp_dense* s, const BuildRegionArgs& a);                        // dense.cu
 void dense_build_region(b200gp_dense* s, int64_t r0, int64_t c0, int64_t ncols);          // dense.cu
 double dense_kernel_diag_value(const KProg& P);                                           // dense.cu
 
@@ -969,3 +1176,223 @@ extern "C" int b200gp_measure_i8_peak(b200gp_ctx* ctx, double* tops) {
     _ctx->release(sink, sizeof(int));
     API_END
 }
+
+extern "C" int b200gp_measure_i8_peak_2sm(b200gp_ctx* ctx, double* tops) {
+    API_BEGIN(ctx)
+    const int smem_bytes = oz::STAGE2_BYTES + 1024 + 64;
+    CUDA_CHECK(cudaFuncSetAttribute(oz::i8_peak_kernel_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int* sink = (int*)_ctx->alloc(sizeof(int));
+    CUDA_CHECK(cudaMemsetAsync(sink, 0, sizeof(int), _ctx->stream));
+    const int iters = (int)((_ctx->peak_iters < 200000) ? _ctx->peak_iters * 4 : 800000);
+    const int npairs = _ctx->num_sms / 2;
+    float ms = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(npairs * 2));
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = _ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaEventRecord(_ctx->ev0, _ctx->stream);
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, oz::i8_peak_kernel_2sm, iters, sink));
+        cudaEventRecord(_ctx->ev1, _ctx->stream);
+        CUDA_CHECK(cudaEventSynchronize(_ctx->ev1));
+        cudaEventElapsedTime(&ms, _ctx->ev0, _ctx->ev1);
+    }
+    _ctx->launches += 2;
+    // per pair per instruction: 256 x 256 x 32 MAC
+    *tops = (double)npairs * (double)iters * 4.0 * 2.0 * 256.0 * 256.0 * 32.0 / (ms * 1e-3) / 1e12;
+    _ctx->release(sink, sizeof(int));
+    API_END
+}
+
+// ================================================================================================
+// Multi-GPU (one process per GPU) step API for ONE dense factorisation sharded over ranks.
+//
+// Every rank holds the full matrix buffer and all digit planes.  For block column J the rows [c0, np) are
+// split into equal chunks; rank r generates + int8-updates only ITS chunk of C_J, the chunks are all-gathered
+// by the host (torch.distributed / NCCL over NVLink, one collective per block column:
+// rows x nb x 8 bytes), and every rank then runs the (cheap, deterministic) fp64 panel factorisation and the
+// digit cutting redundantly -- so there is no owner, no panel broadcast and no second collective.
+// The N^3/3 part (the int8 update) is divided by the number of GPUs; communication totals 8 N^2/2 bytes.
+// ================================================================================================
+struct b200gp_mg {
+    b200gp_ctx* ctx = nullptr;
+    b200gp_dense* s = nullptr;
+    int S = 8;
+    int64_t NB = 1024;
+    int ncol = 0;
+    int8_t* planes = nullptr;
+    size_t plane_stride = 0;
+    double* rs = nullptr;
+    double* corr = nullptr;
+    size_t corr_bytes = 0;
+    int64_t slots_per_panel = 0;
+    int* err = nullptr;
+    oz::Maps maps{};
+};
+
+b200gp_dense* dense_alloc_for_prog(b200gp_ctx* ctx, const KProg& prog, const double* X, int64_t n, int ndim,
+                                   const double* diag);   // dense.cu
+
+extern "C" {
+
+int b200gp_mg_create(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
+                     const double* diag, int slices, b200gp_mg** out) {
+    API_BEGIN(ctx)
+    KProg P = parse_prog(prog, n_instr);
+    b200gp_mg* m = new b200gp_mg();
+    m->ctx = _ctx;
+    m->s = dense_alloc_for_prog(_ctx, P, X, n, ndim, diag);
+    const int64_t np = m->s->np;
+    m->S = (slices < 2) ? 2 : (slices > 8 ? 8 : slices);
+    int64_t p2 = 256;
+    while (p2 * 2 <= _ctx->nb) p2 *= 2;
+    m->NB = p2;
+    m->ncol = (int)((np + m->NB - 1) / m->NB);
+    m->plane_stride = (size_t)np * np;
+    m->planes = (int8_t*)_ctx->alloc(m->plane_stride * m->S);
+    m->rs = (double*)_ctx->alloc((size_t)np * 8);
+    m->err = (int*)_ctx->alloc(sizeof(int));
+    m->slots_per_panel = (m->NB + 511) / 512;
+    m->corr_bytes = (size_t)m->ncol * m->slots_per_panel * np * 8;
+    m->corr = (double*)_ctx->alloc(m->corr_bytes);
+    CUDA_CHECK(cudaMemsetAsync(m->err, 0, sizeof(int), _ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(m->corr, 0, m->corr_bytes, _ctx->stream));
+    int big = INT_MAX;
+    CUDA_CHECK(cudaMemcpyAsync(m->s->info_dev, &big, sizeof(int), cudaMemcpyHostToDevice, _ctx->stream));
+    oz::row_scale_kernel<<<(unsigned)((np + 255) / 256), 256, 0, _ctx->stream>>>(dense_kernel_diag_value(m->s->prog),
+                                                                                m->s->diag_dev, m->s->n, np, m->rs);
+    _ctx->launches++;
+    m->maps = oz::make_maps(m->planes, (int64_t)m->plane_stride, np, np, m->S);
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    *out = m;
+    API_END
+}
+
+int b200gp_mg_free(b200gp_mg* m) {
+    if (!m) return 0;
+    API_BEGIN(m->ctx)
+    _ctx->release(m->planes, m->plane_stride * m->S);
+    _ctx->release(m->rs, (size_t)m->s->np * 8);
+    _ctx->release(m->err, sizeof(int));
+    _ctx->release(m->corr, m->corr_bytes);
+    dense_destroy(m->s);
+    delete m;
+    API_END
+}
+
+int b200gp_mg_geometry(b200gp_mg* m, int64_t* np, int64_t* nb, int* ncol) {
+    API_BEGIN(m->ctx)
+    *np = m->s->np; *nb = m->NB; *ncol = m->ncol;
+    API_END
+}
+
+// generate rows [r0, r1) of block column J and subtract L[r0:r1, 0:c0] L[c0:c0+kb, 0:c0]^T (int8 tensor update)
+int b200gp_mg_update_rows(b200gp_mg* m, int J, int64_t r0, int64_t r1) {
+    API_BEGIN(m->ctx)
+    b200gp_dense* s = m->s;
+    const int64_t np = s->np, c0 = (int64_t)J * m->NB;
+    const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
+    if (r1 > np) r1 = np;
+    if (r0 < c0 || r0 % oz::TM || r1 % oz::TM) throw GpError("mg_update_rows: rows must be 128-aligned and >= c0");
+    if (r1 <= r0) return 0;
+    {   // build only my rows
+        BuildRegionArgs br{r0, r1, c0, kb};
+        dense_build_rows(s, br);
+    }
+    if (J >= 1) {
+        oz::Args a{};
+        a.C = s->mat; a.ldc = np; a.rs = m->rs;
+        a.row0 = r0; a.col0 = c0; a.b_row0 = c0;
+        a.tiles_m = (int)((r1 - r0) / oz::TM);
+        a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
+        a.K = (int)c0; a.k_begin = 0; a.S = m->S; a.n_rows = np; a.skip_upper = 1; a.error_flag = m->err;
+        ProfTimer t(_ctx, &_ctx->prof.syrk_ms);
+        oz::launch_update(_ctx, m->maps, a);
+        _ctx->prof.syrk_flop += 2.0 * (double)(r1 - r0) * (double)kb * (double)c0;
+        _ctx->prof.syrk_launches++;
+    }
+    API_END
+}
+
+// mat[r0:r1, c0:c0+kb] <-> contiguous device buffer [(r1-r0)][nb] (torch-owned, NCCL-visible)
+int b200gp_mg_pack(b200gp_mg* m, int J, int64_t r0, int64_t r1, double* buf_dev) {
+    API_BEGIN(m->ctx)
+    const int64_t np = m->s->np, c0 = (int64_t)J * m->NB;
+    const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
+    if (r1 > np) r1 = np;
+    if (r1 <= r0) return 0;
+    CUDA_CHECK(cudaMemcpy2DAsync(buf_dev, (size_t)m->NB * 8, m->s->mat + r0 * np + c0, (size_t)np * 8, (size_t)kb * 8,
+                                 (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, _ctx->stream));
+    API_END
+}
+int b200gp_mg_unpack(b200gp_mg* m, int J, int64_t r0, int64_t r1, const double* buf_dev) {
+    API_BEGIN(m->ctx)
+    const int64_t np = m->s->np, c0 = (int64_t)J * m->NB;
+    const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
+    if (r1 > np) r1 = np;
+    if (r1 <= r0) return 0;
+    CUDA_CHECK(cudaMemcpy2DAsync(m->s->mat + r0 * np + c0, (size_t)np * 8, buf_dev, (size_t)m->NB * 8, (size_t)kb * 8,
+                                 (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, _ctx->stream));
+    API_END
+}
+
+// after the all-gather: diagonal correction, fp64 panel factorisation, digit cutting (identical on every rank)
+int b200gp_mg_panel(b200gp_mg* m, int J) {
+    API_BEGIN(m->ctx)
+    b200gp_dense* s = m->s;
+    const int64_t np = s->np, c0 = (int64_t)J * m->NB;
+    const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
+    if (J >= 1) {
+        oz::diag_correct_kernel<<<(unsigned)((kb + 255) / 256), 256, 0, _ctx->stream>>>(
+            s->mat, np, m->corr, (int64_t)J * m->slots_per_panel, np, c0, kb);
+        _ctx->launches++;
+    }
+    {
+        ProfTimer t(_ctx, &_ctx->prof.panel_ms);
+        dense_panel_factor(s, c0, kb);
+    }
+    if (c0 + kb < np) {
+        const int64_t nrows = np - (c0 + kb);
+        const int64_t nthreads = nrows * (kb / 16);
+        ProfTimer t(_ctx, &_ctx->prof.build_ms);
+        oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, _ctx->stream>>>(
+            s->mat, np, m->rs, c0 + kb, nrows, c0, kb, m->planes, (int64_t)m->plane_stride, np, m->S,
+            m->corr + (size_t)J * m->slots_per_panel * np, np);
+        _ctx->launches++;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    API_END
+}
+
+// forward solve + reductions on this rank's (complete) factor: gp.py:313-320
+int b200gp_mg_finish(b200gp_mg* m, const double* resid, double* logp) {
+    API_BEGIN(m->ctx)
+    b200gp_dense* s = m->s;
+    const int64_t np = s->np, n = s->n;
+    int herr = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&s->info, s->info_dev, sizeof(int), cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&herr, m->err, sizeof(int), cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    if (herr) throw GpError("int8 tensor update: pipeline wait timed out (internal protocol error)");
+    if (s->info == INT_MAX) s->info = 0;
+    double* y = (double*)_ctx->alloc((size_t)np * 8);
+    double* x = (double*)_ctx->alloc((size_t)np * 8);
+    CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)np * 8, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(y, resid, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
+    dense_solve_vec_dev(s, y, x, false);
+    const double ss = dense_sumsq_dev(_ctx, x, n);
+    const double ld = dense_logdet_half(s);
+    double lp = -0.5 * ss - (ld + 0.5 * (double)n * log(2.0 * M_PI));
+    if (s->info != 0 || !isfinite(lp)) lp = -INFINITY;
+    *logp = lp;
+    _ctx->release(y, (size_t)np * 8);
+    _ctx->release(x, (size_t)np * 8);
+    API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+"""One dense ``log_probability`` sharded over several GPUs (one process per GPU, ``torch.distributed``).
+
+The int8 tensor-core trailing update of block column J is split by ROWS over the ranks; one
+``all_gather_into_tensor`` per block column (NCCL over NVLink, rows x nb x 8 bytes) gives every rank the whole
+updated column, and every rank then factors the panel and cuts its digits redundantly (cheap, deterministic),
+so there is no panel broadcast.  See ``include/b200gp.h`` (b200gp_mg_*) and DESIGN.md section 5.
+"""
+
+from __future__ import annotations
+
+from ctypes import byref, c_double, c_int, c_int64, c_void_p
+
+import numpy as np
+
+from tinygp_b200 import _cabi
+from tinygp_b200.kernels.base import _as_coords
+
+ALIGN = 256  # row chunks are whole 256-row tile pairs
+
+
+def row_chunk(np_: int, c0: int, world: int) -> int:
+    """Rows per rank for the column block starting at c0 (equal chunks, ALIGN-aligned, last ones may be short)."""
+    rows = np_ - c0
+    return max(ALIGN, -(-rows // (ALIGN * world)) * ALIGN)
+
+
+def my_rows(np_: int, c0: int, world: int, rank: int) -> tuple[int, int]:
+    ch = row_chunk(np_, c0, world)
+    r0 = min(np_, c0 + rank * ch)
+    return r0, min(np_, r0 + ch)
+
+
+def make_context(local_rank: int = 0) -> _cabi.Context:
+    """A library context on torch's current CUDA stream (so NCCL collectives order with our kernels)."""
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    ctx = _cabi.Context(device=local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    ctx.on_torch_stream = True
+    _cabi.set_context(ctx)
+    return ctx
+
+
+def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, ctx: _cabi.Context | None = None,
+                            X_dev=None, diag_dev=None, resid_dev=None) -> float:
+    """log N(resid | 0, k(X,X) + diag) with the factorisation sharded over the default process group.
+    `*_dev` may be given as CUDA tensors (device-resident inputs, bench `value` leg)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    ctx = ctx or _cabi.get_context()
+    if world > 1 and not getattr(ctx, "on_torch_stream", False):
+        raise _cabi.B200Error("sharded runs need a context created by multigpu.make_context()")
+    lib = ctx.lib
+    prog = kernel.program()
+    if X_dev is None:
+        x, _ = _as_coords(X)
+        n, ndim = x.shape
+        xp, dp, rp = _cabi.ptr(x), _cabi.ptr(_cabi.f64(diag)), _cabi.ptr(_cabi.f64(resid))
+        keep = (x,)
+    else:
+        n, ndim = X_dev.shape
+        xp, dp, rp = X_dev.data_ptr(), diag_dev.data_ptr(), resid_dev.data_ptr()
+        keep = ()
+    mg = c_void_p()
+    ctx.check(lib.b200gp_mg_create(ctx.handle, _cabi.ptr(prog), prog.shape[0], xp, n, ndim, dp, int(slices), byref(mg)))
+    try:
+        np_, nb, ncol = c_int64(), c_int64(), c_int()
+        ctx.check(lib.b200gp_mg_geometry(mg, byref(np_), byref(nb), byref(ncol)))
+        np_, nb, ncol = np_.value, nb.value, ncol.value
+        if world > 1:
+            chmax = row_chunk(np_, 0, world)
+            mine_buf = torch.empty(chmax * nb, dtype=torch.float64, device="cuda")
+            full_buf = torch.empty(world * chmax * nb, dtype=torch.float64, device="cuda")
+        for J in range(ncol):
+            c0 = J * nb
+            ch = row_chunk(np_, c0, world)
+            r0, r1 = my_rows(np_, c0, world, rank)
+            ctx.check(lib.b200gp_mg_update_rows(mg, J, r0, r1))
+            if world > 1:
+                mine = mine_buf[: ch * nb]
+                full = full_buf[: world * ch * nb]
+                ctx.check(lib.b200gp_mg_pack(mg, J, r0, r1, mine.data_ptr()))
+                dist.all_gather_into_tensor(full, mine)
+                for r in range(world):
+                    if r == rank:
+                        continue
+                    q0 = min(np_, c0 + r * ch)
+                    q1 = min(np_, q0 + ch)
+                    if q1 > q0:
+                        ctx.check(lib.b200gp_mg_unpack(mg, J, q0, q1, full.data_ptr() + r * ch * nb * 8))
+            ctx.check(lib.b200gp_mg_panel(mg, J))
+        lp = c_double()
+        ctx.check(lib.b200gp_mg_finish(mg, rp, byref(lp)))
+        del keep
+        return lp.value
+    finally:
+        lib.b200gp_mg_free(mg)

@@ -181,9 +181,9 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from tinygp_b200 import multigpu
+    ctx = multigpu.make_context(local_rank)      # library + torch share one (non-default) CUDA stream
     stream = torch.cuda.current_stream()
-    ctx = _cabi.Context(device=local_rank, stream=stream.cuda_stream)
-    _cabi.set_context(ctx)
     ctx.set_option("nb", args.nb)
     ctx.set_option("ozaki_slices", args.slices)
     ctx.set_option("ozaki_min_n", 0 if args.slices else 1 << 40)
@@ -330,10 +330,9 @@ def run_quasisep(args, rank, local_rank, world):
     from tinygp_b200 import GaussianProcess, _cabi
     from tinygp_b200.kernels import quasisep as Q
 
-    torch.cuda.set_device(local_rank)
+    from tinygp_b200 import multigpu
+    ctx = multigpu.make_context(local_rank)
     stream = torch.cuda.current_stream()
-    ctx = _cabi.Context(device=local_rank, stream=stream.cuda_stream)
-    _cabi.set_context(ctx)
     n = args.n if args.n != N_DENSE else 10_000_000
     rng = np.random.default_rng(49384)
     t = np.sort(rng.uniform(0, n / 10.0, n))
@@ -424,9 +423,9 @@ def run_batched(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from tinygp_b200 import multigpu
+    ctx = multigpu.make_context(local_rank)
     stream = torch.cuda.current_stream()
-    ctx = _cabi.Context(device=local_rank, stream=stream.cuda_stream)
-    _cabi.set_context(ctx)
     n = 4096 if args.n == N_DENSE else args.n
     nprob = 1024
     rng = np.random.default_rng(49385)

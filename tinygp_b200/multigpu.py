@@ -31,11 +31,16 @@ def my_rows(np_: int, c0: int, world: int, rank: int) -> tuple[int, int]:
 
 
 def make_context(local_rank: int = 0) -> _cabi.Context:
-    """A library context on torch's current CUDA stream (so NCCL collectives order with our kernels)."""
+    """A library context on torch's current CUDA stream (so NCCL collectives order with our kernels).
+    The legacy default stream has handle 0, which the C-ABI reads as "make a private stream", so a dedicated
+    torch stream is created and made current for this process."""
     import torch
 
     torch.cuda.set_device(local_rank)
-    ctx = _cabi.Context(device=local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    ctx = _cabi.Context(device=local_rank, stream=stream.cuda_stream)
+    ctx.torch_stream = stream          # keep it alive
     ctx.on_torch_stream = True
     _cabi.set_context(ctx)
     return ctx

@@ -558,7 +558,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_DENSE)
+    ap.add_argument("--size", "--n", dest="n", type=int, default=N_DENSE, help="problem size N (use --size under torchrun)")
     ap.add_argument("--nb", type=int, default=1024)
     ap.add_argument("--workload", default="dense", choices=["dense", "quasisep", "batched", "sharded"])
     ap.add_argument("--slices", type=int, default=8,

@@ -157,15 +157,17 @@ int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const double* progs, i
  * (torch.distributed / NCCL): for J in 0..ncol-1: update_rows(J, my rows) -> pack -> [all_gather] -> unpack ->
  * panel(J); then finish().  Every rank ends up with the complete factor. */
 typedef struct b200gp_mg b200gp_mg;
+/* streaming != 0: keep no np x np fp64 matrix (rolling np x nb column buffer; the forward solve and log-det
+ * are folded into each panel step) -- only the int8 digit planes stay resident (N = 131072 fits one B200). */
 int b200gp_mg_create(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
-                     const double* diag, int slices, b200gp_mg** out);
+                     const double* diag, const double* resid, int slices, int streaming, b200gp_mg** out);
 int b200gp_mg_free(b200gp_mg* m);
 int b200gp_mg_geometry(b200gp_mg* m, int64_t* np, int64_t* nb, int* ncol);
 int b200gp_mg_update_rows(b200gp_mg* m, int J, int64_t r0, int64_t r1);
 int b200gp_mg_pack(b200gp_mg* m, int J, int64_t r0, int64_t r1, double* buf_dev);
 int b200gp_mg_unpack(b200gp_mg* m, int J, int64_t r0, int64_t r1, const double* buf_dev);
 int b200gp_mg_panel(b200gp_mg* m, int J);
-int b200gp_mg_finish(b200gp_mg* m, const double* resid, double* logp);
+int b200gp_mg_finish(b200gp_mg* m, double* logp);
 
 /* ---- solvers.QuasisepSolver  (solvers/quasisep/solver.py:19-139) ------------------------- */
 /* Quasiseparable kernels (kernels/quasisep.py) are lowered to a list of `ncomp` components

@@ -102,9 +102,10 @@ def test_sharded_step_api_single_rank():
     ctx = _cabi.get_context()
     ctx.set_option("nb", 512)
     try:
+        lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
         for slices in (8, 7):
-            lp = multigpu.log_probability_sharded(k, X, np.full(n, 0.1), y, slices=slices)
-            lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
-            assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+            for streaming in (True, False):
+                lp = multigpu.log_probability_sharded(k, X, np.full(n, 0.1), y, slices=slices, streaming=streaming)
+                assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo, slices, streaming)
     finally:
         ctx.set_option("nb", 1024)

@@ -110,8 +110,12 @@ struct ProfTimer {
 struct b200gp_dense {
     b200gp_ctx* ctx = nullptr;
     int64_t n = 0;    // logical size
-    int64_t np = 0;   // padded to a multiple of TILE (= leading dimension)
-    double* mat = nullptr;   // np x np row-major; lower triangle holds L after factorisation
+    int64_t np = 0;   // padded to a multiple of TILE
+    int64_t ld = 0;   // leading dimension of `mat` (= np, or the panel width in streaming mode)
+    size_t mat_bytes = 0;    // bytes owned behind mat_alloc (0: not owned)
+    double* mat_alloc = nullptr;
+    double* mat = nullptr;   // row-major; element (r, c) at mat[r * ld + c]; lower triangle holds L after factorisation.
+                             // In streaming mode this is a VIRTUAL base (column buffer minus the block-column offset).
     double* linv = nullptr;  // np/TILE inverses of the diagonal blocks, each TILE x TILE
     int* info_dev = nullptr;
     int info = 0;

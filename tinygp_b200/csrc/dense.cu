@@ -556,7 +556,7 @@ __global__ void set_int_kernel(int* p, int v) { *p = v; }
 // factor the panel of columns [k0, k0+kb) over all rows >= k0: inner 128-wide left-looking sweep
 void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb) {
     b200gp_ctx* ctx = s->ctx;
-    const int64_t np = s->np, ld = s->np;
+    const int64_t np = s->np, ld = s->ld;
     double* M = s->mat;
     for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
         const int64_t c0 = k0 + j0;
@@ -601,7 +601,7 @@ double dense_kernel_diag_value(const KProg& P) { return kprog_eval(P, 0.0, 0.0);
 struct BuildRegionArgs { int64_t r0, r1, c0, ncols; };
 void dense_build_rows(b200gp_dense* s, const BuildRegionArgs& q) {
     b200gp_ctx* ctx = s->ctx;
-    const int64_t ld = s->np;
+    const int64_t ld = s->ld;
     BuildArgs a{};
     a.X1 = s->X_dev + q.r0 * s->ndim;
     a.X2 = s->X_dev + q.c0 * s->ndim;
@@ -806,6 +806,26 @@ void dense_solve_vec_dev(b200gp_dense* s, double* y_dev, double* x_dev, bool tra
     CUDA_CHECK(cudaGetLastError());
 }
 
+// streaming helpers (multi-GPU / large-N fused log_probability): forward-substitution steps for the 128-blocks
+// of ONE block column right after it has been factored, and that column's contribution to sum(log L_ii)
+void dense_trsv_fwd_blocks(b200gp_dense* s, double* y_dev, double* x_dev, int j_begin, int j_end) {
+    b200gp_ctx* ctx = s->ctx;
+    ProfTimer t(ctx, &ctx->prof.solve_ms);
+    for (int j = j_begin; j < j_end; ++j) {
+        const int64_t rows_below = s->np - (int64_t)(j + 1) * TILE;
+        const unsigned grid = (unsigned)((rows_below + 63) / 64);
+        trsv_fwd_step<<<grid ? grid : 1, 256, 0, ctx->stream>>>(s->mat, s->ld, s->linv + (int64_t)j * TILE * TILE, y_dev,
+                                                                x_dev, j, s->np, 0, 0);
+        ctx->launches++;
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+void dense_logdiag_partial(b200gp_dense* s, int64_t c0, int64_t count, double* out_dev) {
+    if (count <= 0) return;
+    reduce_kernel<<<1, 1024, 0, s->ctx->stream>>>(s->mat + c0 * s->ld + c0, s->ld + 1, count, 0, out_dev, 0);
+    s->ctx->launches++;
+}
+
 // =============================================================================================
 // K4: out = L z  (direct.py:72-73), one warp per row
 // =============================================================================================
@@ -870,8 +890,11 @@ static b200gp_dense* dense_alloc(b200gp_ctx* ctx, int64_t n) {
     s->ctx = ctx;
     s->n = n;
     s->np = ((n + TILE - 1) / TILE) * TILE;
+    s->ld = s->np;
     try {
-        s->mat = (double*)ctx->alloc((size_t)s->np * s->np * sizeof(double));
+        s->mat_bytes = (size_t)s->np * s->np * sizeof(double);
+        s->mat_alloc = (double*)ctx->alloc(s->mat_bytes);
+        s->mat = s->mat_alloc;
         s->linv = (double*)ctx->alloc((size_t)(s->np / TILE) * TILE * TILE * sizeof(double));
         s->info_dev = (int*)ctx->alloc(sizeof(int));
     } catch (...) {
@@ -884,7 +907,7 @@ static b200gp_dense* dense_alloc(b200gp_ctx* ctx, int64_t n) {
 void dense_destroy(b200gp_dense* s) {
     if (!s) return;
     b200gp_ctx* ctx = s->ctx;
-    if (s->mat) ctx->release(s->mat, (size_t)s->np * s->np * sizeof(double));
+    if (s->mat_alloc) ctx->release(s->mat_alloc, s->mat_bytes);
     if (s->linv) ctx->release(s->linv, (size_t)(s->np / TILE) * TILE * TILE * sizeof(double));
     if (s->info_dev) ctx->release(s->info_dev, sizeof(int));
     if (s->owns_inputs) {

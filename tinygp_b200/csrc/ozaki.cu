@@ -1233,25 +1233,54 @@ struct b200gp_mg {
     int64_t slots_per_panel = 0;
     int* err = nullptr;
     oz::Maps maps{};
+    // streaming mode: no full fp64 matrix; a rolling np x NB column buffer, forward solve + log-det per panel
+    bool streaming = false;
+    double* colbuf = nullptr;
+    double* y = nullptr;       // np, right-hand side being reduced
+    double* x = nullptr;       // np, alpha
+    double* logparts = nullptr;  // ncol partial sums of log L_ii
 };
 
+void dense_trsv_fwd_blocks(b200gp_dense* s, double* y_dev, double* x_dev, int j_begin, int j_end);   // dense.cu
+void dense_logdiag_partial(b200gp_dense* s, int64_t c0, int64_t count, double* out_dev);             // dense.cu
 b200gp_dense* dense_alloc_for_prog(b200gp_ctx* ctx, const KProg& prog, const double* X, int64_t n, int ndim,
                                    const double* diag);   // dense.cu
 
 extern "C" {
 
 int b200gp_mg_create(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
-                     const double* diag, int slices, b200gp_mg** out) {
+                     const double* diag, const double* resid, int slices, int streaming, b200gp_mg** out) {
     API_BEGIN(ctx)
     KProg P = parse_prog(prog, n_instr);
     b200gp_mg* m = new b200gp_mg();
     m->ctx = _ctx;
-    m->s = dense_alloc_for_prog(_ctx, P, X, n, ndim, diag);
-    const int64_t np = m->s->np;
-    m->S = (slices < 2) ? 2 : (slices > 8 ? 8 : slices);
+    m->streaming = (streaming != 0);
     int64_t p2 = 256;
     while (p2 * 2 <= _ctx->nb) p2 *= 2;
     m->NB = p2;
+    if (!m->streaming) {
+        m->s = dense_alloc_for_prog(_ctx, P, X, n, ndim, diag);
+    } else {
+        // hand-built dense object without the np x np matrix
+        if (ndim < 1 || ndim > 16) throw GpError("dense: ndim must be in [1, 16]");
+        b200gp_dense* s = new b200gp_dense();
+        s->ctx = _ctx; s->n = n; s->np = ((n + TILE - 1) / TILE) * TILE; s->ld = m->NB;
+        s->has_prog = true; s->prog = P; s->ndim = ndim; s->owns_inputs = true;
+        s->linv = (double*)_ctx->alloc((size_t)(s->np / TILE) * TILE * TILE * sizeof(double));
+        s->info_dev = (int*)_ctx->alloc(sizeof(int));
+        s->X_dev = (double*)_ctx->alloc((size_t)n * ndim * sizeof(double));
+        s->diag_dev = (double*)_ctx->alloc((size_t)n * sizeof(double));
+        CUDA_CHECK(cudaMemcpyAsync(s->X_dev, X, (size_t)n * ndim * sizeof(double), cudaMemcpyDefault, _ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(s->diag_dev, diag, (size_t)n * sizeof(double), cudaMemcpyDefault, _ctx->stream));
+        m->s = s;
+        m->colbuf = (double*)_ctx->alloc((size_t)s->np * m->NB * 8);
+    }
+    const int64_t np = m->s->np;
+    m->S = (slices < 2) ? 2 : (slices > 8 ? 8 : slices);
+    m->y = (double*)_ctx->alloc((size_t)np * 8);
+    m->x = (double*)_ctx->alloc((size_t)np * 8);
+    CUDA_CHECK(cudaMemsetAsync(m->y, 0, (size_t)np * 8, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(m->y, resid, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
     m->ncol = (int)((np + m->NB - 1) / m->NB);
     m->plane_stride = (size_t)np * np;
     m->planes = (int8_t*)_ctx->alloc(m->plane_stride * m->S);
@@ -1260,6 +1289,8 @@ int b200gp_mg_create(b200gp_ctx* ctx, const double* prog, int n_instr, const dou
     m->slots_per_panel = (m->NB + 511) / 512;
     m->corr_bytes = (size_t)m->ncol * m->slots_per_panel * np * 8;
     m->corr = (double*)_ctx->alloc(m->corr_bytes);
+    m->logparts = (double*)_ctx->alloc((size_t)m->ncol * 8);
+    CUDA_CHECK(cudaMemsetAsync(m->logparts, 0, (size_t)m->ncol * 8, _ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(m->err, 0, sizeof(int), _ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(m->corr, 0, m->corr_bytes, _ctx->stream));
     int big = INT_MAX;
@@ -1280,6 +1311,13 @@ int b200gp_mg_free(b200gp_mg* m) {
     _ctx->release(m->rs, (size_t)m->s->np * 8);
     _ctx->release(m->err, sizeof(int));
     _ctx->release(m->corr, m->corr_bytes);
+    _ctx->release(m->logparts, (size_t)m->ncol * 8);
+    _ctx->release(m->y, (size_t)m->s->np * 8);
+    _ctx->release(m->x, (size_t)m->s->np * 8);
+    if (m->streaming) {
+        _ctx->release(m->colbuf, (size_t)m->s->np * m->NB * 8);
+        m->s->mat = nullptr;
+    }
     dense_destroy(m->s);
     delete m;
     API_END
@@ -1299,6 +1337,7 @@ int b200gp_mg_update_rows(b200gp_mg* m, int J, int64_t r0, int64_t r1) {
     const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
     if (r1 > np) r1 = np;
     if (r0 < c0 || r0 % oz::TM || r1 % oz::TM) throw GpError("mg_update_rows: rows must be 128-aligned and >= c0");
+    if (m->streaming) s->mat = m->colbuf - c0;   // virtual base: (r, c) of this block column -> colbuf[r * NB + (c - c0)]
     if (r1 <= r0) return 0;
     {   // build only my rows
         BuildRegionArgs br{r0, r1, c0, kb};
@@ -1306,7 +1345,7 @@ int b200gp_mg_update_rows(b200gp_mg* m, int J, int64_t r0, int64_t r1) {
     }
     if (J >= 1) {
         oz::Args a{};
-        a.C = s->mat; a.ldc = np; a.rs = m->rs;
+        a.C = s->mat; a.ldc = s->ld; a.rs = m->rs;
         a.row0 = r0; a.col0 = c0; a.b_row0 = c0;
         a.tiles_m = (int)((r1 - r0) / oz::TM);
         a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
@@ -1326,8 +1365,8 @@ int b200gp_mg_pack(b200gp_mg* m, int J, int64_t r0, int64_t r1, double* buf_dev)
     const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
     if (r1 > np) r1 = np;
     if (r1 <= r0) return 0;
-    CUDA_CHECK(cudaMemcpy2DAsync(buf_dev, (size_t)m->NB * 8, m->s->mat + r0 * np + c0, (size_t)np * 8, (size_t)kb * 8,
-                                 (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, _ctx->stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(buf_dev, (size_t)m->NB * 8, m->s->mat + r0 * m->s->ld + c0, (size_t)m->s->ld * 8,
+                                 (size_t)kb * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, _ctx->stream));
     API_END
 }
 int b200gp_mg_unpack(b200gp_mg* m, int J, int64_t r0, int64_t r1, const double* buf_dev) {
@@ -1336,8 +1375,8 @@ int b200gp_mg_unpack(b200gp_mg* m, int J, int64_t r0, int64_t r1, const double* 
     const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
     if (r1 > np) r1 = np;
     if (r1 <= r0) return 0;
-    CUDA_CHECK(cudaMemcpy2DAsync(m->s->mat + r0 * np + c0, (size_t)np * 8, buf_dev, (size_t)m->NB * 8, (size_t)kb * 8,
-                                 (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, _ctx->stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(m->s->mat + r0 * m->s->ld + c0, (size_t)m->s->ld * 8, buf_dev, (size_t)m->NB * 8,
+                                 (size_t)kb * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, _ctx->stream));
     API_END
 }
 
@@ -1349,7 +1388,7 @@ int b200gp_mg_panel(b200gp_mg* m, int J) {
     const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
     if (J >= 1) {
         oz::diag_correct_kernel<<<(unsigned)((kb + 255) / 256), 256, 0, _ctx->stream>>>(
-            s->mat, np, m->corr, (int64_t)J * m->slots_per_panel, np, c0, kb);
+            s->mat, s->ld, m->corr, (int64_t)J * m->slots_per_panel, np, c0, kb);
         _ctx->launches++;
     }
     {
@@ -1361,16 +1400,22 @@ int b200gp_mg_panel(b200gp_mg* m, int J) {
         const int64_t nthreads = nrows * (kb / 16);
         ProfTimer t(_ctx, &_ctx->prof.build_ms);
         oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, _ctx->stream>>>(
-            s->mat, np, m->rs, c0 + kb, nrows, c0, kb, m->planes, (int64_t)m->plane_stride, np, m->S,
+            s->mat, s->ld, m->rs, c0 + kb, nrows, c0, kb, m->planes, (int64_t)m->plane_stride, np, m->S,
             m->corr + (size_t)J * m->slots_per_panel * np, np);
         _ctx->launches++;
+    }
+    if (m->streaming) {
+        // this block column of L is about to be overwritten: consume it now (forward substitution + log-det)
+        dense_trsv_fwd_blocks(s, m->y, m->x, (int)(c0 / TILE), (int)((c0 + kb) / TILE));
+        const int64_t valid = (s->n > c0) ? ((s->n - c0 < kb) ? (s->n - c0) : kb) : 0;
+        dense_logdiag_partial(s, c0, valid, m->logparts + J);
     }
     CUDA_CHECK(cudaGetLastError());
     API_END
 }
 
 // forward solve + reductions on this rank's (complete) factor: gp.py:313-320
-int b200gp_mg_finish(b200gp_mg* m, const double* resid, double* logp) {
+int b200gp_mg_finish(b200gp_mg* m, double* logp) {
     API_BEGIN(m->ctx)
     b200gp_dense* s = m->s;
     const int64_t np = s->np, n = s->n;
@@ -1380,18 +1425,22 @@ int b200gp_mg_finish(b200gp_mg* m, const double* resid, double* logp) {
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
     if (herr) throw GpError("int8 tensor update: pipeline wait timed out (internal protocol error)");
     if (s->info == INT_MAX) s->info = 0;
-    double* y = (double*)_ctx->alloc((size_t)np * 8);
-    double* x = (double*)_ctx->alloc((size_t)np * 8);
-    CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)np * 8, _ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(y, resid, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
-    dense_solve_vec_dev(s, y, x, false);
-    const double ss = dense_sumsq_dev(_ctx, x, n);
-    const double ld = dense_logdet_half(s);
+    (void)np;
+    double ld;
+    if (m->streaming) {
+        std::vector<double> parts((size_t)m->ncol);
+        CUDA_CHECK(cudaMemcpyAsync(parts.data(), m->logparts, (size_t)m->ncol * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+        ld = 0.0;
+        for (double p : parts) ld += p;   // fixed order
+    } else {
+        dense_solve_vec_dev(s, m->y, m->x, false);
+        ld = dense_logdet_half(s);
+    }
+    const double ss = dense_sumsq_dev(_ctx, m->x, n);
     double lp = -0.5 * ss - (ld + 0.5 * (double)n * log(2.0 * M_PI));
     if (s->info != 0 || !isfinite(lp)) lp = -INFINITY;
     *logp = lp;
-    _ctx->release(y, (size_t)np * 8);
-    _ctx->release(x, (size_t)np * 8);
     API_END
 }
 

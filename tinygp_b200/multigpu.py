@@ -46,10 +46,11 @@ def make_context(local_rank: int = 0) -> _cabi.Context:
     return ctx
 
 
-def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, ctx: _cabi.Context | None = None,
-                            X_dev=None, diag_dev=None, resid_dev=None) -> float:
+def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streaming: bool = True,
+                            ctx: _cabi.Context | None = None, X_dev=None, diag_dev=None, resid_dev=None) -> float:
     """log N(resid | 0, k(X,X) + diag) with the factorisation sharded over the default process group.
-    `*_dev` may be given as CUDA tensors (device-resident inputs, bench `value` leg)."""
+    `*_dev` may be given as CUDA tensors (device-resident inputs, bench `value` leg).  `streaming=True` keeps no
+    np x np fp64 matrix (forward solve and log-det are folded into the panel steps)."""
     import torch
     import torch.distributed as dist
 
@@ -70,7 +71,8 @@ def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, ctx: _ca
         xp, dp, rp = X_dev.data_ptr(), diag_dev.data_ptr(), resid_dev.data_ptr()
         keep = ()
     mg = c_void_p()
-    ctx.check(lib.b200gp_mg_create(ctx.handle, _cabi.ptr(prog), prog.shape[0], xp, n, ndim, dp, int(slices), byref(mg)))
+    ctx.check(lib.b200gp_mg_create(ctx.handle, _cabi.ptr(prog), prog.shape[0], xp, n, ndim, dp, rp, int(slices),
+                                   int(bool(streaming)), byref(mg)))
     try:
         np_, nb, ncol = c_int64(), c_int64(), c_int()
         ctx.check(lib.b200gp_mg_geometry(mg, byref(np_), byref(nb), byref(ncol)))
@@ -98,7 +100,7 @@ def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, ctx: _ca
                         ctx.check(lib.b200gp_mg_unpack(mg, J, q0, q1, full.data_ptr() + r * ch * nb * 8))
             ctx.check(lib.b200gp_mg_panel(mg, J))
         lp = c_double()
-        ctx.check(lib.b200gp_mg_finish(mg, rp, byref(lp)))
+        ctx.check(lib.b200gp_mg_finish(mg, byref(lp)))
         del keep
         return lp.value
     finally:

@@ -61,8 +61,10 @@ def test_scalar_evaluate_and_edge_shapes():
         k(np.zeros((0,)), np.zeros((3,)))
 
 
+@pytest.mark.parametrize("potf2", [2, 1])
 @pytest.mark.parametrize("n", [1, 50, 128, 300, 1100])
-def test_factor_parity(n, ctx):
+def test_factor_parity(n, ctx, potf2):
+    ctx.set_option("potf2_version", potf2)
     rng = np.random.default_rng(n)
     X = rng.uniform(0, 6, (n, 2))
     k = 1.3 * kernels.ExpSquared(0.8)
@@ -79,6 +81,7 @@ def test_factor_parity(n, ctx):
         np.testing.assert_allclose(s.covariance(), so.covariance(), rtol=1e-13, atol=1e-15)
     ctx.set_option("nb", 1024)
     ctx.set_option("ozaki_slices", 8)
+    ctx.set_option("potf2_version", 2)
 
 
 @pytest.mark.parametrize("n,ndim,name", [(256, 1, "expsq"), (777, 3, "c3_l2"), (2048, 3, "expsq"),

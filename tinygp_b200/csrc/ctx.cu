@@ -173,6 +173,8 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
     } else if (!strcmp(key, "peak_iters")) {
         if (value < 16) throw GpError("option peak_iters must be >= 16");
         _ctx->peak_iters = value;
+    } else if (!strcmp(key, "potf2_version")) {
+        _ctx->potf2_version = value;
     } else if (!strcmp(key, "nb_batched")) {
         if (value < TILE || value % TILE) throw GpError("option nb_batched must be a positive multiple of 128");
         _ctx->nb_batched = value;

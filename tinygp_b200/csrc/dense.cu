@@ -536,6 +536,190 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel(double* A, i
     }
 }
 
+// ---- v2: rank-8 blocked right-looking Cholesky + 8-column blocked inverse, register tiles -------------------
+// v1 does 2 shared-memory loads per FMA (no register reuse) and 2-3 barriers per column: 186 us per block (ncu).
+// Here every 8-column panel is factored redundantly in registers by the threads that own its rows (no barrier
+// inside), the rank-8 trailing update uses 4x4 register tiles (2 FMA per load) and the inverse is built 8 columns
+// at a time: 32 + 48 barriers instead of 640.
+constexpr int PF2_SMEM = (TILE * PF_LD + TILE * 8 + 4 * TILE * 8) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel_v2(double* A, int64_t lda, double* linv, int* info,
+                                                                       int global_off, int64_t strideA,
+                                                                       int64_t stride_linv) {
+    extern __shared__ __align__(16) double sm[];
+    A += (int64_t)blockIdx.x * strideA;
+    linv += (int64_t)blockIdx.x * stride_linv;
+    info += blockIdx.x;
+    double* S = sm;                       // TILE x PF_LD
+    double* T = sm + TILE * PF_LD;        // TILE x 8 : column block of L being inverted
+    double* red = T + TILE * 8;           // 4 x TILE x 8 partial sums
+    const int tid = threadIdx.x;
+    const int i = tid & (TILE - 1);
+    const int part = tid >> 7;
+
+    for (int e = tid; e < TILE * TILE; e += PF_THREADS) {
+        const int r = e >> 7, c = e & (TILE - 1);
+        S[r * PF_LD + c] = (c <= r) ? A[(int64_t)r * lda + c] : 0.0;
+    }
+    __syncthreads();
+
+    // ---------------- phase 1: Cholesky ----------------
+    for (int jb = 0; jb < TILE / 8; ++jb) {
+        const int j0 = jb * 8;
+        if (tid < TILE && tid >= j0) {
+            const int r = tid;
+            double D[8][8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) D[a][b] = S[(j0 + a) * PF_LD + j0 + b];
+            int firstbad = -1;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double v = D[c][c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) v -= D[c][k] * D[c][k];
+                if (!(v > 0.0) && firstbad < 0) firstbad = c;
+                const double sq = sqrt(v);
+                D[c][c] = sq;
+#pragma unroll
+                for (int a = c + 1; a < 8; ++a) {
+                    double w = D[a][c];
+#pragma unroll
+                    for (int k = 0; k < c; ++k) w -= D[a][k] * D[c][k];
+                    D[a][c] = w / sq;
+                }
+            }
+            if (r == j0 && firstbad >= 0) atomicMin(info, global_off + j0 + firstbad + 1);
+            if (r < j0 + 8) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (a == r - j0) {
+#pragma unroll
+                        for (int b = 0; b <= a; ++b) S[r * PF_LD + j0 + b] = D[a][b];
+                    }
+            } else {
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double w = S[r * PF_LD + j0 + c];
+#pragma unroll
+                    for (int k = 0; k < c; ++k) w -= x[k] * D[c][k];
+                    x[c] = w / D[c][c];
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) S[r * PF_LD + j0 + c] = x[c];
+            }
+        }
+        __syncthreads();
+        const int m = TILE - j0 - 8;
+        if (m > 0) {
+            const int nt = m >> 2, ntiles = nt * (nt + 1) / 2;
+            for (int e = tid; e < ntiles; e += PF_THREADS) {
+                int ti = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+                while (ti * (ti + 1) / 2 > e) --ti;
+                const int tj = e - ti * (ti + 1) / 2;
+                const int i0 = j0 + 8 + 4 * ti, c0 = j0 + 8 + 4 * tj;
+                double Lr[4][8], Lc[4][8], acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        Lr[a][k] = S[(i0 + a) * PF_LD + j0 + k];
+                        Lc[a][k] = S[(c0 + a) * PF_LD + j0 + k];
+                    }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) sacc += Lr[a][k] * Lc[b][k];
+                        acc[a][b] = sacc;
+                    }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (c0 + b <= i0 + a) S[(i0 + a) * PF_LD + c0 + b] -= acc[a][b];
+            }
+        }
+        __syncthreads();
+    }
+
+    for (int e = tid; e < TILE * TILE; e += PF_THREADS) {
+        const int r = e >> 7, c = e & (TILE - 1);
+        if (c <= r) A[(int64_t)r * lda + c] = S[r * PF_LD + c];
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: X = L^-1 in place, 8 columns at a time from the right ----------------
+    //   X[i, jb] = -( sum_{k > jb-block, k <= i} X[i,k] L[k, jb] ) inv(L[jb,jb]) ,   X[jb,jb] = inv(L[jb,jb])
+    for (int jb = TILE / 8 - 1; jb >= 0; --jb) {
+        const int j0 = jb * 8;
+        for (int e = tid; e < TILE * 8; e += PF_THREADS) {
+            const int k = e >> 3, c = e & 7;
+            T[e] = (k >= j0) ? S[k * PF_LD + j0 + c] : 0.0;
+        }
+        __syncthreads();
+        double acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+        if (i >= j0 + 8) {
+            const double* ri = S + i * PF_LD;
+            for (int k = j0 + 8 + part; k <= i; k += 4) {
+                const double xik = ri[k];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] += xik * T[k * 8 + c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) red[(part * TILE + i) * 8 + c] = acc[c];
+        __syncthreads();
+        if (part == 0 && i >= j0) {
+            // inverse of the 8x8 lower diagonal block (rows j0..j0+7 of T), in registers
+            double Di[8][8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                Di[c][c] = 1.0 / T[(j0 + c) * 8 + c];
+#pragma unroll
+                for (int a = c + 1; a < 8; ++a) {
+                    double w = 0.0;
+#pragma unroll
+                    for (int k = c; k < a; ++k) w += T[(j0 + a) * 8 + k] * Di[k][c];
+                    Di[a][c] = -w / T[(j0 + a) * 8 + a];
+                }
+            }
+            if (i < j0 + 8) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (a == i - j0) {
+#pragma unroll
+                        for (int c = 0; c <= a; ++c) S[i * PF_LD + j0 + c] = Di[a][c];
+                    }
+            } else {
+                double v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    v[c] = red[i * 8 + c] + red[(TILE + i) * 8 + c] + red[(2 * TILE + i) * 8 + c] + red[(3 * TILE + i) * 8 + c];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double w = 0.0;
+#pragma unroll
+                    for (int cp = c; cp < 8; ++cp) w += v[cp] * Di[cp][c];
+                    S[i * PF_LD + j0 + c] = -w;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < TILE * TILE; e += PF_THREADS) {
+        const int r = e >> 7, c = e & (TILE - 1);
+        linv[e] = (c <= r) ? S[r * PF_LD + c] : 0.0;
+    }
+}
+
 static void potf2(b200gp_ctx* ctx, double* A, int64_t lda, double* linv, int* info, int global_off, int batch = 1,
                   int64_t strideA = 0, int64_t stride_linv = 0) {
     static bool attr = false;
@@ -543,7 +727,17 @@ static void potf2(b200gp_ctx* ctx, double* A, int64_t lda, double* linv, int* in
         CUDA_CHECK(cudaFuncSetAttribute(potf2_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
         attr = true;
     }
-    potf2_trtri_kernel<<<batch, PF_THREADS, PF_SMEM, ctx->stream>>>(A, lda, linv, info, global_off, strideA, stride_linv);
+    if (ctx->potf2_version == 1) {
+        potf2_trtri_kernel<<<batch, PF_THREADS, PF_SMEM, ctx->stream>>>(A, lda, linv, info, global_off, strideA, stride_linv);
+    } else {
+        static bool attr2 = false;
+        if (!attr2) {
+            CUDA_CHECK(cudaFuncSetAttribute(potf2_trtri_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, PF2_SMEM));
+            attr2 = true;
+        }
+        potf2_trtri_kernel_v2<<<batch, PF_THREADS, PF2_SMEM, ctx->stream>>>(A, lda, linv, info, global_off, strideA,
+                                                                          stride_linv);
+    }
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -1220,9 +1414,16 @@ int b200gp_dense_get_factor(b200gp_dense* s, double* out) {
     API_END
 }
 
+extern "C++" double ozaki_logp_streaming(b200gp_ctx* ctx, const KProg& P, const double* X, int64_t n, int ndim,
+                                         const double* diag, const double* resid, int S);   // ozaki.cu
+
 static double dense_logp_impl(b200gp_ctx* ctx, const KProg& P, const double* X, int64_t n, int ndim,
                               const double* diag, const double* resid) {
     // X / diag / resid may be host or device pointers (cudaMemcpyDefault resolves them)
+    if (ctx->oz_slices > 0 && ((n + TILE - 1) / TILE) * TILE >= ctx->oz_min_n && ctx->oz_lookahead == 0) {
+        // no factor is retained by this entry point: stream the block columns (no N x N fp64 matrix at all)
+        return ozaki_logp_streaming(ctx, P, X, n, ndim, diag, resid, (int)ctx->oz_slices);
+    }
     b200gp_dense* s = dense_factor_from_prog(ctx, P, X, n, ndim, diag, true);
     double logp;
     try {

@@ -1445,3 +1445,27 @@ int b200gp_mg_finish(b200gp_mg* m, double* logp) {
 }
 
 }  // extern "C"
+
+// single-GPU fused log_probability through the same step functions (world size 1, streaming)
+double ozaki_logp_streaming(b200gp_ctx* ctx, const KProg& P, const double* X, int64_t n, int ndim, const double* diag,
+                            const double* resid, int S) {
+    // re-encode the program for the C entry point
+    std::vector<double> prog((size_t)P.n * B200GP_PROG_STRIDE);
+    for (int i = 0; i < P.n; ++i) {
+        prog[4 * i + 0] = P.op[i]; prog[4 * i + 1] = P.dist[i]; prog[4 * i + 2] = P.p0[i]; prog[4 * i + 3] = P.p1[i];
+    }
+    b200gp_mg* m = nullptr;
+    if (b200gp_mg_create(ctx, prog.data(), P.n, X, n, ndim, diag, resid, S, 1, &m)) throw GpError(ctx->err);
+    double lp = 0.0;
+    int rc = 0;
+    const int64_t np = m->s->np;
+    for (int J = 0; J < m->ncol && !rc; ++J) {
+        rc = b200gp_mg_update_rows(m, J, (int64_t)J * m->NB, np);
+        if (!rc) rc = b200gp_mg_panel(m, J);
+    }
+    if (!rc) rc = b200gp_mg_finish(m, &lp);
+    std::string err = ctx->err;
+    b200gp_mg_free(m);
+    if (rc) throw GpError(err);
+    return lp;
+}

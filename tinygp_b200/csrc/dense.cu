@@ -566,13 +566,20 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel_v2(double* A
     // ---------------- phase 1: Cholesky ----------------
     for (int jb = 0; jb < TILE / 8; ++jb) {
         const int j0 = jb * 8;
-        if (tid < TILE && tid >= j0) {
-            const int r = tid;
-            double D[8][8];
+        // load phase (diagonal block + own row), then a barrier: the stores below overwrite what others read here
+        const bool owner = (tid < TILE && tid >= j0);
+        double D[8][8], arow[8];
+        if (owner) {
 #pragma unroll
             for (int a = 0; a < 8; ++a)
 #pragma unroll
                 for (int b = 0; b <= a; ++b) D[a][b] = S[(j0 + a) * PF_LD + j0 + b];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) arow[c] = S[tid * PF_LD + j0 + c];
+        }
+        __syncthreads();
+        if (owner) {
+            const int r = tid;
             int firstbad = -1;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -592,17 +599,19 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel_v2(double* A
             }
             if (r == j0 && firstbad >= 0) atomicMin(info, global_off + j0 + firstbad + 1);
             if (r < j0 + 8) {
+                // every owner of a diagonal-block row holds the same factored block: one of them stores it all
+                // (static register indices; a per-row select would push D into local memory)
+                if (r == j0) {
 #pragma unroll
-                for (int a = 0; a < 8; ++a)
-                    if (a == r - j0) {
+                    for (int a = 0; a < 8; ++a)
 #pragma unroll
-                        for (int b = 0; b <= a; ++b) S[r * PF_LD + j0 + b] = D[a][b];
-                    }
+                        for (int b = 0; b <= a; ++b) S[(j0 + a) * PF_LD + j0 + b] = D[a][b];
+                }
             } else {
                 double x[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    double w = S[r * PF_LD + j0 + c];
+                    double w = arow[c];
 #pragma unroll
                     for (int k = 0; k < c; ++k) w -= x[k] * D[c][k];
                     x[c] = w / D[c][c];
@@ -621,23 +630,24 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel_v2(double* A
                 while (ti * (ti + 1) / 2 > e) --ti;
                 const int tj = e - ti * (ti + 1) / 2;
                 const int i0 = j0 + 8 + 4 * ti, c0 = j0 + 8 + 4 * tj;
-                double Lr[4][8], Lc[4][8], acc[4][4];
+                double acc[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        Lr[a][k] = S[(i0 + a) * PF_LD + j0 + k];
-                        Lc[a][k] = S[(c0 + a) * PF_LD + j0 + k];
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // 8 loads feed 16 FMAs; no big register arrays
+                    double lr[4], lc[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        lr[a] = S[(i0 + a) * PF_LD + j0 + k];
+                        lc[a] = S[(c0 + a) * PF_LD + j0 + k];
                     }
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        double sacc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) sacc += Lr[a][k] * Lc[b][k];
-                        acc[a][b] = sacc;
-                    }
+                        for (int b = 0; b < 4; ++b) acc[a][b] += lr[a] * lc[b];
+                }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -692,12 +702,12 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel_v2(double* A
                 }
             }
             if (i < j0 + 8) {
+                if (i == j0) {
 #pragma unroll
-                for (int a = 0; a < 8; ++a)
-                    if (a == i - j0) {
+                    for (int a = 0; a < 8; ++a)
 #pragma unroll
-                        for (int c = 0; c <= a; ++c) S[i * PF_LD + j0 + c] = Di[a][c];
-                    }
+                        for (int c = 0; c <= a; ++c) S[(j0 + a) * PF_LD + j0 + c] = Di[a][c];
+                }
             } else {
                 double v[8];
 #pragma unroll
@@ -1420,9 +1430,14 @@ extern "C++" double ozaki_logp_streaming(b200gp_ctx* ctx, const KProg& P, const 
 static double dense_logp_impl(b200gp_ctx* ctx, const KProg& P, const double* X, int64_t n, int ndim,
                               const double* diag, const double* resid) {
     // X / diag / resid may be host or device pointers (cudaMemcpyDefault resolves them)
-    if (ctx->oz_slices > 0 && ((n + TILE - 1) / TILE) * TILE >= ctx->oz_min_n && ctx->oz_lookahead == 0) {
-        // no factor is retained by this entry point: stream the block columns (no N x N fp64 matrix at all)
-        return ozaki_logp_streaming(ctx, P, X, n, ndim, diag, resid, (int)ctx->oz_slices);
+    {
+        // no factor is retained by this entry point, so very large problems stream their block columns (no N x N
+        // fp64 matrix: only the digit planes stay resident).  Smaller ones keep the matrix: the rolling column
+        // buffer competes with the operand planes for L2 and costs ~10 % (measured at N = 65536).
+        const int64_t npad = ((n + TILE - 1) / TILE) * TILE;
+        const double need = (double)npad * (double)npad * (8.0 + (double)ctx->oz_slices);
+        if (ctx->oz_slices > 0 && npad >= ctx->oz_min_n && need > 150e9)
+            return ozaki_logp_streaming(ctx, P, X, n, ndim, diag, resid, (int)ctx->oz_slices);
     }
     b200gp_dense* s = dense_factor_from_prog(ctx, P, X, n, ndim, diag, true);
     double logp;

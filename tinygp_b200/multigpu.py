@@ -46,7 +46,7 @@ def make_context(local_rank: int = 0) -> _cabi.Context:
     return ctx
 
 
-def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streaming: bool = True,
+def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streaming: bool | None = None,
                             ctx: _cabi.Context | None = None, X_dev=None, diag_dev=None, resid_dev=None) -> float:
     """log N(resid | 0, k(X,X) + diag) with the factorisation sharded over the default process group.
     `*_dev` may be given as CUDA tensors (device-resident inputs, bench `value` leg).  `streaming=True` keeps no
@@ -70,6 +70,9 @@ def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streamin
         n, ndim = X_dev.shape
         xp, dp, rp = X_dev.data_ptr(), diag_dev.data_ptr(), resid_dev.data_ptr()
         keep = ()
+    if streaming is None:   # stream only when matrix + digit planes would not fit comfortably in HBM
+        npad = -(-n // 128) * 128
+        streaming = npad * npad * (8.0 + slices) > 150e9
     mg = c_void_p()
     ctx.check(lib.b200gp_mg_create(ctx.handle, _cabi.ptr(prog), prog.shape[0], xp, n, ndim, dp, rp, int(slices),
                                    int(bool(streaming)), byref(mg)))

@@ -107,20 +107,34 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------
+_USED_THREADS = [1]
+
+
 def oracle_dense_logp_seconds(n):
+    """One oracle log_probability on ALL host cores (torchrun exports OMP_NUM_THREADS=1; undo that here)."""
     from oracle import tinygp_np as o
     X, y, diag, scale = make_dense_problem(n)
-    t0 = time.perf_counter()
-    lp = o.GaussianProcess(o.Constant(1.0) * o.ExpSquared(scale), X, diag=diag).log_probability(y)
-    return time.perf_counter() - t0, lp
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        limiter = threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        limiter = None
+    try:
+        t0 = time.perf_counter()
+        lp = o.GaussianProcess(o.Constant(1.0) * o.ExpSquared(scale), X, diag=diag).log_probability(y)
+        dt = time.perf_counter() - t0
+        try:
+            _USED_THREADS[0] = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        except Exception:
+            pass
+    finally:
+        if limiter is not None:
+            limiter.restore_original_limits()
+    return dt, lp
 
 
 def cpu_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        return os.cpu_count() or 1
+    return int(_USED_THREADS[0])
 
 
 def pick_sample_n(budget_s_per_step):
@@ -292,12 +306,15 @@ def run_ours(args, rank, local_rank, world):
         "whole_step_tflops_n3_over_3": flop_alg * args.steps / (ms * 1e-3) / 1e12,
         "traffic": _read_traffic(),
       }
-    # CPU baseline on a bounded sample
-    n_s = pick_sample_n(25.0)
-    t_cpu, lp_cpu = oracle_dense_logp_seconds(n_s)
-    cpu_value = 1.0 / (t_cpu * (n / n_s) ** 3)
-    cpu_baseline = {"value": cpu_value, "unit": "logp/s", "cores": cpu_threads(), "kind": "port",
-                    "sample": f"N={n_s} timed ({t_cpu:.2f} s), extrapolated x{(n / n_s) ** 3:.0f} (N^3) to N={n}"}
+    # CPU baseline on a bounded sample (rank 0 at N=1 only)
+    if world == 1:
+        n_s = pick_sample_n(25.0)
+        t_cpu, lp_cpu = oracle_dense_logp_seconds(n_s)
+        cpu_value = 1.0 / (t_cpu * (n / n_s) ** 3)
+        cpu_baseline = {"value": cpu_value, "unit": "logp/s", "cores": cpu_threads(), "kind": "port",
+                        "sample": f"N={n_s} timed ({t_cpu:.2f} s), extrapolated x{(n / n_s) ** 3:.0f} (N^3) to N={n}"}
+    else:
+        cpu_baseline = None
 
     line = {
         "metric": "log_probability/sec", "value": value, "unit": "logp/s", "n_gpus": world, "steps": args.steps,

@@ -46,6 +46,9 @@ struct b200gp_qs {
     double* w = nullptr;     // n x J
     int info = 0;
     double logdet_half = 0.0;
+    // fused log_probability: forward-solve chunk composites accumulated inside the Cholesky replay pass
+    double* fused_comp = nullptr;
+    size_t fused_comp_bytes = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -582,12 +585,16 @@ template <int J>
 __global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
                                                                  const double* __restrict__ diag, int64_t n,
                                                                  const double* fstart, int64_t nchunks, double* c_out,
-                                                                 double* w_out, double* logc_part, int* info) {
+                                                                 double* w_out, double* logc_part, int* info,
+                                                                 const double* __restrict__ x_fuse, double* aff_comp) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= nchunks) return;
     const int64_t k0 = ch * QS_CHUNK, k1 = min(n, k0 + QS_CHUNK);
     double f[J][J];
     state_load<J>(f, fstart, nchunks, ch);
+    const bool fuse = (x_fuse != nullptr);
+    Affine<J> R;      // forward-solve composite of this chunk (ops.py:475-486 elements), only when fusing
+    R.identity();
     double tp = (k0 == 0) ? t[0] : t[k0 - 1];
     double lsum = 0.0;
     for (int64_t k = k0; k < k1; ++k) {
@@ -631,8 +638,30 @@ __global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < J; ++j) w_out[k * J + j] = w[j];
         lsum += log(ck);
+        if (fuse) {   // g' = (a - w p^T / c) g + w x / c, folded while c, w, a, p are still in registers
+            const double ic = 1.0 / ck, xk = x_fuse[k];
+            double Ak[J][J], nA[J][J], nb[J];
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                const double wi = w[i] * ic;
+#pragma unroll
+                for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j] - wi * p[j];
+                double sb = wi * xk;
+#pragma unroll
+                for (int j = 0; j < J; ++j) sb += Ak[i][j] * R.b[j];
+                nb[i] = sb;
+            }
+            matmul<J>(Ak, R.A, nA);
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                R.b[i] = nb[i];
+#pragma unroll
+                for (int j = 0; j < J; ++j) R.A[i][j] = nA[i][j];
+            }
+        }
     }
     logc_part[ch] = lsum;
+    if (fuse) R.store(aff_comp, nchunks, ch);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -912,7 +941,7 @@ static void run_tree(b200gp_ctx* ctx, double* comp0, int64_t n0, double* start0)
 }
 
 template <int J>
-static void qs_factor_J(b200gp_qs* s, int* info_dev, double* logdet_dev) {
+static void qs_factor_J(b200gp_qs* s, int* info_dev, double* logdet_dev, const double* x_fuse) {
     b200gp_ctx* ctx = s->ctx;
     const int64_t n = s->n, nch = (n + QS_CHUNK - 1) / QS_CHUNK;
     const size_t cb = (size_t)Riccati<J>::SIZE * nch * 8, sb = (size_t)J * J * nch * 8;
@@ -922,8 +951,13 @@ static void qs_factor_J(b200gp_qs* s, int* info_dev, double* logdet_dev) {
     chol_chunk_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->diag, n, comp, nch);
     ctx->launches++;
     run_tree<Riccati<J>>(ctx, comp, nch, fstart);
+    if (x_fuse) {
+        s->fused_comp_bytes = (size_t)Affine<J>::SIZE * nch * 8;
+        s->fused_comp = (double*)ctx->alloc(s->fused_comp_bytes);
+    }
     chol_replay_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->diag, n, fstart, nch,
-                                                                                 s->c, s->w, part, info_dev);
+                                                                                 s->c, s->w, part, info_dev, x_fuse,
+                                                                                 s->fused_comp);
     ctx->launches++;
     sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part, nch, logdet_dev);
     ctx->launches++;
@@ -935,15 +969,17 @@ static void qs_factor_J(b200gp_qs* s, int* info_dev, double* logdet_dev) {
 
 // one affine scan over a device vector x -> out ; optional sum of squares of the emitted values
 template <int J, int OP>
-static void qs_affine_J(b200gp_qs* s, const double* x, double* out, double* sumsq_dev) {
+static void qs_affine_J(b200gp_qs* s, const double* x, double* out, double* sumsq_dev, double* precomputed_comp = nullptr) {
     b200gp_ctx* ctx = s->ctx;
     const int64_t n = s->n, nch = (n + QS_CHUNK - 1) / QS_CHUNK;
     const size_t cb = (size_t)Affine<J>::SIZE * nch * 8, sb = (size_t)J * nch * 8;
-    double* comp = (double*)ctx->alloc(cb);
+    double* comp = precomputed_comp ? precomputed_comp : (double*)ctx->alloc(cb);
     double* gstart = (double*)ctx->alloc(sb);
     double* part = sumsq_dev ? (double*)ctx->alloc((size_t)nch * 8) : nullptr;
-    affine_chunk_kernel<J, OP><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->c, s->w, x, n, comp, nch);
-    ctx->launches++;
+    if (!precomputed_comp) {
+        affine_chunk_kernel<J, OP><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->c, s->w, x, n, comp, nch);
+        ctx->launches++;
+    }
     run_tree<Affine<J>>(ctx, comp, nch, gstart);
     affine_replay_kernel<J, OP><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->diag, s->c, s->w, x, n,
                                                                                        gstart, nch, out, part);
@@ -954,7 +990,7 @@ static void qs_affine_J(b200gp_qs* s, const double* x, double* out, double* sums
         ctx->release(part, (size_t)nch * 8);
     }
     CUDA_CHECK(cudaGetLastError());
-    ctx->release(comp, cb);
+    if (!precomputed_comp) ctx->release(comp, cb);
     ctx->release(gstart, sb);
 }
 
@@ -991,6 +1027,7 @@ static void qs_destroy(b200gp_qs* s) {
     if (s->diag) ctx->release(s->diag, nb);
     if (s->c) ctx->release(s->c, nb);
     if (s->w) ctx->release(s->w, nb * s->J);
+    if (s->fused_comp) ctx->release(s->fused_comp, s->fused_comp_bytes);
     delete s;
 }
 
@@ -1010,7 +1047,7 @@ static bool qs_is_unsorted(b200gp_ctx* ctx, const double* t_dev, int64_t n) {
 
 // t / diag may be host or device pointers
 static b200gp_qs* qs_create_impl(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n,
-                                 const double* diag, int assume_sorted, int* unsorted) {
+                                 const double* diag, int assume_sorted, int* unsorted, const double* x_fuse_dev = nullptr) {
     if (n <= 0) throw GpError("quasisep: n must be positive");
     QsModel model = build_model(comps, ncomp);
     b200gp_qs* s = new b200gp_qs();
@@ -1040,7 +1077,7 @@ static b200gp_qs* qs_create_impl(b200gp_ctx* ctx, const double* comps, int ncomp
             ProfTimer tm(ctx, &ctx->prof.qs_ms);
             ctx->prof.qs_launches++;
             ctx->prof.qs_bytes += 8.0 * (double)n * (2.0 * 2.0 + 1.0 + s->J);  // two passes read t,diag ; write c,w
-            QS_DISPATCH_J(s->J, (qs_factor_J<JJ>(s, info_dev, ld_dev)))
+            QS_DISPATCH_J(s->J, (qs_factor_J<JJ>(s, info_dev, ld_dev, x_fuse_dev)))
         }
         CUDA_CHECK(cudaMemcpyAsync(&s->info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaMemcpyAsync(&s->logdet_half, ld_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1086,15 +1123,29 @@ static void qs_apply_host(b200gp_qs* s, int op, double* Y, int64_t nrhs, int op2
 
 static double qs_logp_impl(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n,
                            const double* diag, const double* resid, int assume_sorted, int* unsorted) {
-    b200gp_qs* s = qs_create_impl(ctx, comps, ncomp, t, n, diag, assume_sorted, unsorted);
-    if (!s) return NAN;
+    double* x = (double*)ctx->alloc((size_t)n * 8);
+    CUDA_CHECK(cudaMemcpyAsync(x, resid, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
+    b200gp_qs* s = nullptr;
+    try {
+        s = qs_create_impl(ctx, comps, ncomp, t, n, diag, assume_sorted, unsorted, x);
+    } catch (...) {
+        ctx->release(x, (size_t)n * 8);
+        throw;
+    }
+    if (!s) {
+        ctx->release(x, (size_t)n * 8);
+        return NAN;
+    }
     double logp;
     try {
-        double* x = (double*)ctx->alloc((size_t)n * 8);
         double* o = (double*)ctx->alloc((size_t)n * 8);
         double* ss_dev = (double*)ctx->alloc(8);
-        CUDA_CHECK(cudaMemcpyAsync(x, resid, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
-        qs_affine(s, OP_LOWER_SOLVE, x, o, ss_dev);
+        {   // tree + replay only: the chunk composites were accumulated inside the Cholesky replay
+            ProfTimer tm(ctx, &ctx->prof.qs_ms);
+            ctx->prof.qs_launches++;
+            ctx->prof.qs_bytes += 8.0 * (double)n * (4.0 + s->J);
+            QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_LOWER_SOLVE>(s, x, o, ss_dev, s->fused_comp)))
+        }
         double ss = 0.0;
         CUDA_CHECK(cudaMemcpyAsync(&ss, ss_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

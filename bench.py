@@ -350,6 +350,8 @@ def run_quasisep(args, rank, local_rank, world):
     from tinygp_b200 import multigpu
     ctx = multigpu.make_context(local_rank)
     stream = torch.cuda.current_stream()
+    if args.qs_chunk:
+        ctx.set_option("qs_chunk", args.qs_chunk)
     n = args.n if args.n != N_DENSE else 10_000_000
     rng = np.random.default_rng(49384)
     t = np.sort(rng.uniform(0, n / 10.0, n))
@@ -577,6 +579,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", "--n", dest="n", type=int, default=N_DENSE, help="problem size N (use --size under torchrun)")
     ap.add_argument("--nb", type=int, default=1024)
+    ap.add_argument("--qs-chunk", type=int, default=0)
     ap.add_argument("--workload", default="dense", choices=["dense", "quasisep", "batched", "sharded"])
     ap.add_argument("--slices", type=int, default=8,
                     help="int8 digit planes of the fixed-point trailing update: 8 = 55-bit digits (fp64-equivalent, "

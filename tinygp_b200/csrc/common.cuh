@@ -55,6 +55,7 @@ struct b200gp_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int num_sms = 148;
     int64_t peak_iters = 4096;  // loop length of the fp64 peak micro-benchmarks
+    int64_t qs_chunk = 64;      // points per thread in the quasiseparable scans
     int64_t potf2_version = 2;  // 1: column-at-a-time diagonal-block kernel, 2: rank-8 blocked with register tiles
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
     int64_t oz_slices = 8;      // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA

@@ -26,6 +26,7 @@
 
 struct QsModel {
     int ncomp, J;
+    int chunk;   // points per thread (runtime tunable, option "qs_chunk")
     int kind[B200GP_QS_MAX_COMP];
     int off[B200GP_QS_MAX_COMP];
     int mode[B200GP_QS_MAX_COMP];  // SHO: 0 critical, 1 underdamped, 2 overdamped
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(QS_THREADS) chol_chunk_kernel(const __grid_con
                                                                 double* comp, int64_t nchunks) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= nchunks) return;
-    const int64_t k0 = ch * QS_CHUNK, k1 = min(n, k0 + QS_CHUNK);
+    const int64_t k0 = ch * m.chunk, k1 = min(n, k0 + m.chunk);
     Riccati<J> R;
     R.identity();
     double tp = (k0 == 0) ? t[0] : t[k0 - 1];
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_co
                                                                  const double* __restrict__ x_fuse, double* aff_comp) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= nchunks) return;
-    const int64_t k0 = ch * QS_CHUNK, k1 = min(n, k0 + QS_CHUNK);
+    const int64_t k0 = ch * m.chunk, k1 = min(n, k0 + m.chunk);
     double f[J][J];
     state_load<J>(f, fstart, nchunks, ch);
     const bool fuse = (x_fuse != nullptr);
@@ -678,7 +679,7 @@ __global__ void __launch_bounds__(QS_THREADS) affine_chunk_kernel(const __grid_c
                                                                   int64_t nchunks) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= nchunks) return;
-    const int64_t l0 = ch * QS_CHUNK, l1 = min(n, l0 + QS_CHUNK);
+    const int64_t l0 = ch * m.chunk, l1 = min(n, l0 + m.chunk);
     Affine<J> R;
     R.identity();
     for (int64_t l = l0; l < l1; ++l) {
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_
                                                                    double* sq_part) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= nchunks) return;
-    const int64_t l0 = ch * QS_CHUNK, l1 = min(n, l0 + QS_CHUNK);
+    const int64_t l0 = ch * m.chunk, l1 = min(n, l0 + m.chunk);
     double g[J];
     state_load<J>(g, gstart, nchunks, ch);
     double ssum = 0.0;
@@ -943,7 +944,7 @@ static void run_tree(b200gp_ctx* ctx, double* comp0, int64_t n0, double* start0)
 template <int J>
 static void qs_factor_J(b200gp_qs* s, int* info_dev, double* logdet_dev, const double* x_fuse) {
     b200gp_ctx* ctx = s->ctx;
-    const int64_t n = s->n, nch = (n + QS_CHUNK - 1) / QS_CHUNK;
+    const int64_t n = s->n, nch = (n + s->model.chunk - 1) / s->model.chunk;
     const size_t cb = (size_t)Riccati<J>::SIZE * nch * 8, sb = (size_t)J * J * nch * 8;
     double* comp = (double*)ctx->alloc(cb);
     double* fstart = (double*)ctx->alloc(sb);
@@ -971,7 +972,7 @@ static void qs_factor_J(b200gp_qs* s, int* info_dev, double* logdet_dev, const d
 template <int J, int OP>
 static void qs_affine_J(b200gp_qs* s, const double* x, double* out, double* sumsq_dev, double* precomputed_comp = nullptr) {
     b200gp_ctx* ctx = s->ctx;
-    const int64_t n = s->n, nch = (n + QS_CHUNK - 1) / QS_CHUNK;
+    const int64_t n = s->n, nch = (n + s->model.chunk - 1) / s->model.chunk;
     const size_t cb = (size_t)Affine<J>::SIZE * nch * 8, sb = (size_t)J * nch * 8;
     double* comp = precomputed_comp ? precomputed_comp : (double*)ctx->alloc(cb);
     double* gstart = (double*)ctx->alloc(sb);
@@ -1055,6 +1056,7 @@ static b200gp_qs* qs_create_impl(b200gp_ctx* ctx, const double* comps, int ncomp
     s->n = n;
     s->J = model.J;
     s->model = model;
+    s->model.chunk = (int)ctx->qs_chunk;
     try {
         const size_t nb = (size_t)n * 8;
         s->t = (double*)ctx->alloc(nb);

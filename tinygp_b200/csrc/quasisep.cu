@@ -528,6 +528,51 @@ __global__ void __launch_bounds__(QS_THREADS) tree_down_kernel(const double* chi
 }
 
 // ---------------------------------------------------------------------------------------------
+// 32-byte per-thread vector accesses.  One thread walks `chunk` consecutive points, so neighbouring threads are
+// chunk*8 bytes apart and nothing coalesces across the warp; with scalar loads every thread keeps ~5 cache
+// lines "hot" and 1024 resident threads thrash L1 (ncu, round 1: all four scan kernels cost ~0.65 ms regardless
+// of their flop count).  Loading/storing 4 points (one full 32-byte sector) per access makes every sector move
+// exactly once.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld4(const double* __restrict__ p, int64_t kb, int64_t k1, double (&v)[4]) {
+    if (kb + 3 < k1 && ((reinterpret_cast<uintptr_t>(p + kb) & 31) == 0)) {
+        const double4 q = *reinterpret_cast<const double4*>(p + kb);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (kb + u < k1) ? p[kb + u] : 0.0;
+    }
+}
+__device__ __forceinline__ void st4(double* p, int64_t kb, int64_t k1, const double (&v)[4]) {
+    if (kb + 3 < k1 && ((reinterpret_cast<uintptr_t>(p + kb) & 31) == 0)) {
+        *reinterpret_cast<double4*>(p + kb) = make_double4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (kb + u < k1) p[kb + u] = v[u];
+    }
+}
+template <int J>
+__device__ __forceinline__ void ldrow(const double* __restrict__ p, int64_t k, double (&v)[J]) {
+    if (J == 4 && ((reinterpret_cast<uintptr_t>(p + k * J) & 31) == 0)) {
+        const double4 q = *reinterpret_cast<const double4*>(p + k * J);
+        v[0] = q.x; v[1 % J] = q.y; v[2 % J] = q.z; v[3 % J] = q.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j] = p[k * J + j];
+    }
+}
+template <int J>
+__device__ __forceinline__ void strow(double* p, int64_t k, const double (&v)[J]) {
+    if (J == 4 && ((reinterpret_cast<uintptr_t>(p + k * J) & 31) == 0)) {
+        *reinterpret_cast<double4*>(p + k * J) = make_double4(v[0], v[1 % J], v[2 % J], v[3 % J]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) p[k * J + j] = v[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cholesky: chunk composites and replay
 // ---------------------------------------------------------------------------------------------
 template <int J>
@@ -540,12 +585,18 @@ __global__ void __launch_bounds__(QS_THREADS) chol_chunk_kernel(const __grid_con
     Riccati<J> R;
     R.identity();
     double tp = (k0 == 0) ? t[0] : t[k0 - 1];
-    for (int64_t k = k0; k < k1; ++k) {
-        const double tk = t[k];
+    for (int64_t kb = k0; kb < k1; kb += 4) {
+      double t4[4], g4[4];
+      ld4(t, kb, k1, t4);
+      ld4(diag, kb, k1, g4);
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        if (kb + uu >= k1) break;
+        const double tk = t4[uu];
         double a[J][J], p[J];
         qs_gen<J>(m, tk - tp, a, p);
         tp = tk;
-        const double d = m.d0 + diag[k];
+        const double d = m.d0 + g4[uu];
         double u[J], v[J], w[J];
         double s = d;
 #pragma unroll
@@ -577,6 +628,7 @@ __global__ void __launch_bounds__(QS_THREADS) chol_chunk_kernel(const __grid_con
                 R.A[i][j] = T1[i][j] - w[i] * v[j] * is;
                 R.G[i][j] -= v[i] * v[j] * is;
             }
+      }
     }
     R.store(comp, nchunks, ch);
 }
@@ -598,12 +650,20 @@ __global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_co
     R.identity();
     double tp = (k0 == 0) ? t[0] : t[k0 - 1];
     double lsum = 0.0;
-    for (int64_t k = k0; k < k1; ++k) {
-        const double tk = t[k];
+    for (int64_t kb = k0; kb < k1; kb += 4) {
+      double t4[4], g4[4], x4[4], c4[4];
+      ld4(t, kb, k1, t4);
+      ld4(diag, kb, k1, g4);
+      if (fuse) ld4(x_fuse, kb, k1, x4);
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        const int64_t k = kb + uu;
+        if (k >= k1) break;
+        const double tk = t4[uu];
         double a[J][J], p[J];
         qs_gen<J>(m, tk - tp, a, p);
         tp = tk;
-        const double d = m.d0 + diag[k];
+        const double d = m.d0 + g4[uu];
         // ck = sqrt(dk - pk @ fp @ pk)
         double pf[J];
 #pragma unroll
@@ -635,12 +695,11 @@ __global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_co
         for (int i = 0; i < J; ++i)
 #pragma unroll
             for (int j = 0; j < J; ++j) f[i][j] += w[i] * w[j];
-        c_out[k] = ck;
-#pragma unroll
-        for (int j = 0; j < J; ++j) w_out[k * J + j] = w[j];
+        c4[uu] = ck;
+        strow<J>(w_out, k, w);
         lsum += log(ck);
         if (fuse) {   // g' = (a - w p^T / c) g + w x / c, folded while c, w, a, p are still in registers
-            const double ic = 1.0 / ck, xk = x_fuse[k];
+            const double ic = 1.0 / ck, xk = x4[uu];
             double Ak[J][J], nA[J][J], nb[J];
 #pragma unroll
             for (int i = 0; i < J; ++i) {
@@ -660,6 +719,8 @@ __global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_co
                 for (int j = 0; j < J; ++j) R.A[i][j] = nA[i][j];
             }
         }
+      }
+      st4(c_out, kb, k1, c4);
     }
     logc_part[ch] = lsum;
     if (fuse) R.store(aff_comp, nchunks, ch);
@@ -682,35 +743,52 @@ __global__ void __launch_bounds__(QS_THREADS) affine_chunk_kernel(const __grid_c
     const int64_t l0 = ch * m.chunk, l1 = min(n, l0 + m.chunk);
     Affine<J> R;
     R.identity();
-    for (int64_t l = l0; l < l1; ++l) {
+    double tprev = 0.0;
+    if (!op_reverse(OP)) tprev = (l0 == 0) ? t[0] : t[l0 - 1];
+    for (int64_t lb = l0; lb < l1; lb += 4) {
+      double t4[4], x4[4], c4[4];
+      if (!op_reverse(OP)) {   // forward scans: one 32-byte sector per array per 4 points
+          ld4(t, lb, l1, t4);
+          ld4(x, lb, l1, x4);
+          if (OP == OP_LOWER_SOLVE) ld4(c, lb, l1, c4);
+      }
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        const int64_t l = lb + uu;
+        if (l >= l1) break;
         const int64_t k = op_reverse(OP) ? (n - 1 - l) : l;
-        const double dt = (k == 0) ? 0.0 : (t[k] - t[k - 1]);
+        double dt;
+        if (!op_reverse(OP)) { dt = t4[uu] - tprev; tprev = t4[uu]; }
+        else dt = (k == 0) ? 0.0 : (t[k] - t[k - 1]);
         double a[J][J], p[J];
         qs_gen<J>(m, dt, a, p);
-        const double xk = x[k];
+        const double xk = op_reverse(OP) ? x[k] : x4[uu];
+        const double ck_in = (OP == OP_LOWER_SOLVE) ? c4[uu] : ((OP == OP_UPPER_SOLVE) ? c[k] : 1.0);
+        double wk[J];
+        if (OP == OP_LOWER_SOLVE || OP == OP_UPPER_SOLVE || OP == OP_LOWER_DOT) ldrow<J>(w, k, wk);
         double Ak[J][J], bk[J];
         if (OP == OP_LOWER_SOLVE) {  // g' = (a - w p^T / c) g + w x / c
-            const double ic = 1.0 / c[k];
+            const double ic = 1.0 / ck_in;
 #pragma unroll
             for (int i = 0; i < J; ++i) {
-                const double wi = w[k * J + i] * ic;
+                const double wi = wk[i] * ic;
                 bk[i] = wi * xk;
 #pragma unroll
                 for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j] - wi * p[j];
             }
         } else if (OP == OP_UPPER_SOLVE) {  // g' = (a^T - p w^T / c) g + p x / c
-            const double ic = 1.0 / c[k];
+            const double ic = 1.0 / ck_in;
 #pragma unroll
             for (int i = 0; i < J; ++i) {
                 const double pi = p[i] * ic;
                 bk[i] = pi * xk;
 #pragma unroll
-                for (int j = 0; j < J; ++j) Ak[i][j] = a[j][i] - pi * w[k * J + j];
+                for (int j = 0; j < J; ++j) Ak[i][j] = a[j][i] - pi * wk[j];
             }
         } else if (OP == OP_LOWER_DOT) {  // g' = a g + w x
 #pragma unroll
             for (int i = 0; i < J; ++i) {
-                bk[i] = w[k * J + i] * xk;
+                bk[i] = wk[i] * xk;
 #pragma unroll
                 for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j];
             }
@@ -745,6 +823,7 @@ __global__ void __launch_bounds__(QS_THREADS) affine_chunk_kernel(const __grid_c
             for (int j = 0; j < J; ++j) R.A[i][j] = nA[i][j];
         }
     }
+    }
     R.store(comp, nchunks, ch);
 }
 
@@ -761,31 +840,50 @@ __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_
     double g[J];
     state_load<J>(g, gstart, nchunks, ch);
     double ssum = 0.0;
-    for (int64_t l = l0; l < l1; ++l) {
+    double tprev = 0.0;
+    if (!op_reverse(OP)) tprev = (l0 == 0) ? t[0] : t[l0 - 1];
+    for (int64_t lb = l0; lb < l1; lb += 4) {
+      double t4[4], x4[4], c4[4], d4[4], o4[4];
+      if (!op_reverse(OP)) {   // forward scans: 32-byte vector accesses (see ld4)
+          ld4(t, lb, l1, t4);
+          ld4(x, lb, l1, x4);
+          if (OP == OP_LOWER_SOLVE || OP == OP_LOWER_DOT) ld4(c, lb, l1, c4);
+          if (OP == OP_SYMM_LOWER) ld4(diag, lb, l1, d4);
+      }
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        const int64_t l = lb + uu;
+        if (l >= l1) break;
         const int64_t k = op_reverse(OP) ? (n - 1 - l) : l;
-        const double dt = (k == 0) ? 0.0 : (t[k] - t[k - 1]);
+        double dt;
+        if (!op_reverse(OP)) { dt = t4[uu] - tprev; tprev = t4[uu]; }
+        else dt = (k == 0) ? 0.0 : (t[k] - t[k - 1]);
         double a[J][J], p[J];
         qs_gen<J>(m, dt, a, p);
-        const double xk = x[k];
+        const double xk = op_reverse(OP) ? x[k] : x4[uu];
+        const double ck_in = op_reverse(OP) ? ((OP == OP_UPPER_SOLVE) ? c[k] : 1.0) : c4[uu];
+        const double dk_in = (OP == OP_SYMM_LOWER) ? d4[uu] : 0.0;
+        double wk[J];
+        if (OP == OP_LOWER_SOLVE || OP == OP_UPPER_SOLVE || OP == OP_LOWER_DOT) ldrow<J>(w, k, wk);
         double y, ng[J];
         if (OP == OP_LOWER_SOLVE) {  // ops.py:465-468: y = (x - p@f)/d ; f = a@f + outer(q, y)
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < J; ++j) s += p[j] * g[j];
-            y = (xk - s) / c[k];
+            y = (xk - s) / ck_in;
 #pragma unroll
             for (int i = 0; i < J; ++i) {
                 double v = 0.0;
 #pragma unroll
                 for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
-                ng[i] = v + w[k * J + i] * y;
+                ng[i] = v + wk[i] * y;
             }
-            out[k] = y;
+            o4[uu] = y;
         } else if (OP == OP_UPPER_SOLVE) {  // ops.py:491-494: y = (x - q@f)/d ; f = a.T@f + outer(p, y)
             double s = 0.0;
 #pragma unroll
-            for (int j = 0; j < J; ++j) s += w[k * J + j] * g[j];
-            y = (xk - s) / c[k];
+            for (int j = 0; j < J; ++j) s += wk[j] * g[j];
+            y = (xk - s) / ck_in;
 #pragma unroll
             for (int i = 0; i < J; ++i) {
                 double v = 0.0;
@@ -798,20 +896,20 @@ __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < J; ++j) s += p[j] * g[j];
-            y = c[k] * xk + s;
+            y = ck_in * xk + s;
 #pragma unroll
             for (int i = 0; i < J; ++i) {
                 double v = 0.0;
 #pragma unroll
                 for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
-                ng[i] = v + w[k * J + i] * xk;
+                ng[i] = v + wk[i] * xk;
             }
-            out[k] = y;
+            o4[uu] = y;
         } else if (OP == OP_SYMM_LOWER) {  // core.py:499-505: d x + lower part
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < J; ++j) s += p[j] * g[j];
-            y = (m.d0 + diag[k]) * xk + s;
+            y = (m.d0 + dk_in) * xk + s;
 #pragma unroll
             for (int i = 0; i < J; ++i) {
                 double v = 0.0;
@@ -819,7 +917,7 @@ __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_
                 for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
                 ng[i] = v + m.q[i] * xk;
             }
-            out[k] = y;
+            o4[uu] = y;
         } else {  // OP_SYMM_UPPER (ops.py:332-338): out += q . f ; f = a^T f + p x
             double s = 0.0;
 #pragma unroll
@@ -837,6 +935,8 @@ __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < J; ++i) g[i] = ng[i];
         ssum += y * y;
+      }
+      if (!op_reverse(OP)) st4(out, lb, l1, o4);
     }
     if (sq_part) sq_part[ch] = ssum;
 }

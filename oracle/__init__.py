@@ -15,7 +15,9 @@ therefore pinned by (i) the reference's own test *relations*, restated in
 test_solver.py:27-103, test_kalman.py:47-69; QSM Cholesky == dense Cholesky,
 test_core.py:308-323; generators == dense kernel and transition == expm(F^T dt),
 test_quasisep.py:53-72; Celerite closed form, test_quasisep.py:83-97) and
-(ii) the multivariate-normal definition via scipy.stats.  Absolute values are
-"parity unpinned" in the sense of the task statement: no reference-produced
-number exists to compare against.
+(ii) the multivariate-normal definition via scipy.stats, and (iii) the known-answer
+vectors of tests/golden/known_answers.json, produced by tests/golden/make_golden.py
+from an independent scalar-formula + scipy.stats formulation (NOT by the reference).
+Absolute values are "parity unpinned" in the sense of the task statement: no
+reference-produced number exists to compare against.
 """

@@ -61,6 +61,7 @@ struct b200gp_ctx {
     int64_t oz_slices = 8;      // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA
     int64_t oz_lookahead = 0;   // overlap the fp64 panel factorisation with the int8 update on a second stream
     cudaStream_t stream2 = nullptr;
+    int64_t oz_prefetch = 0;    // L2 prefetch distance (K-chunks of 128) of the int8 update's TMA producer
     int64_t oz_cluster = 21;    // cluster shape of the int8 update kernel (CM*10 + CN), see ozaki.cu
     int64_t oz_min_n = 8192;    // below this size the native DMMA path is used
     // deferred (non-blocking) kernel timers: event pairs resolved at the next flush_timers()

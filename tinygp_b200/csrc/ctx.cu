@@ -184,6 +184,8 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
     } else if (!strcmp(key, "ozaki_slices")) {
         if (value < 0 || value > 8) throw GpError("option ozaki_slices must be in [0, 8]");
         _ctx->oz_slices = value;
+    } else if (!strcmp(key, "ozaki_prefetch")) {
+        _ctx->oz_prefetch = value;
     } else if (!strcmp(key, "ozaki_lookahead")) {
         _ctx->oz_lookahead = value;
     } else if (!strcmp(key, "ozaki_cluster")) {

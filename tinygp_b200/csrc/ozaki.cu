@@ -51,6 +51,7 @@ struct Args {
     int S;                             // number of digit planes used
     int64_t b_row0;                    // first global row of the B operand (= col0 for the Cholesky update)
     int64_t n_rows;                    // rows of the matrix (for masking the last column tile)
+    int prefetch;                      // L2 prefetch distance in K-chunks (0 = off)
     int skip_upper;                    // skip tiles entirely above the diagonal
     int* error_flag;
 };
@@ -94,6 +95,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
             smem_u32(smem_dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// fire-and-forget L2 prefetch of a TMA box: the demand loads of the shared-memory ring then see L2-hit latency
+// instead of loaded DRAM latency (the ring holds only 192 KB; ncu showed the kernel latency-bound)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -238,6 +244,15 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                         uint8_t* b_dst = a_dst + A_BYTES;
                         mbar_expect_tx(full + stage, STAGE_BYTES);   // own + mates' slices land on this barrier
                         constexpr int A_ROWS = TM / CN, B_ROWS = TN / CM;
+                        if (g.prefetch > 0 && kc + g.prefetch < KT) {   // own slices, `prefetch` K-chunks ahead, into L2
+                            const int kp = g.k_begin + (kc + g.prefetch) * KC;
+#pragma unroll
+                            for (int bx = 0; bx < A_ROWS / BOXR; ++bx)
+                                tma_prefetch_2d(&maps.plane[s], kp, (int)grow0 + cn * A_ROWS + bx * BOXR);
+#pragma unroll
+                            for (int bx = 0; bx < B_ROWS / BOXR; ++bx)
+                                tma_prefetch_2d(&maps.plane[t], kp, (int)brow0 + cm * B_ROWS + bx * BOXR);
+                        }
 #pragma unroll
                         for (int bx = 0; bx < A_ROWS / BOXR; ++bx) {
                             const int r = cn * A_ROWS + bx * BOXR;
@@ -1057,6 +1072,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
         a.tiles_m = (int)((np - c0) / oz::TM);
         a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
         a.K = (int)k_len; a.k_begin = (int)k_begin; a.S = S; a.n_rows = np; a.skip_upper = 1; a.error_flag = err;
+        a.prefetch = (int)ctx->oz_prefetch;
         ProfTimer t(ctx, &ctx->prof.syrk_ms);
         oz::launch_update(ctx, maps, a);
         ctx->prof.syrk_flop += 2.0 * (double)(np - c0) * (double)kb * (double)k_len;  // fp64-equivalent flop
@@ -1142,6 +1158,7 @@ extern "C" int b200gp_i8_update_test(b200gp_ctx* ctx, const int8_t* planes_host,
     a.C = C; a.ldc = rows; a.rs = rs; a.row0 = 0; a.col0 = 0; a.b_row0 = 0;
     a.tiles_m = (int)(rows / oz::TM); a.tiles_n = (int)(rows / oz::TN);
     a.K = (int)K; a.k_begin = 0; a.S = S; a.n_rows = rows; a.skip_upper = 0; a.error_flag = err;
+    a.prefetch = (int)_ctx->oz_prefetch;
     oz::launch_update(_ctx, maps, a);
     int herr = 0;
     CUDA_CHECK(cudaMemcpyAsync(C_host, C, (size_t)rows * rows * 8, cudaMemcpyDeviceToHost, _ctx->stream));
@@ -1350,6 +1367,7 @@ int b200gp_mg_update_rows(b200gp_mg* m, int J, int64_t r0, int64_t r1) {
         a.tiles_m = (int)((r1 - r0) / oz::TM);
         a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
         a.K = (int)c0; a.k_begin = 0; a.S = m->S; a.n_rows = np; a.skip_upper = 1; a.error_flag = m->err;
+        a.prefetch = (int)_ctx->oz_prefetch;
         ProfTimer t(_ctx, &_ctx->prof.syrk_ms);
         oz::launch_update(_ctx, m->maps, a);
         _ctx->prof.syrk_flop += 2.0 * (double)(r1 - r0) * (double)kb * (double)c0;

@@ -23,6 +23,8 @@ slices_list = [int(s) for s in (sys.argv[4].split(",") if len(sys.argv) > 4 else
 clusters = [int(s) for s in (sys.argv[5].split(",") if len(sys.argv) > 5 else "22".split(","))]
 lookaheads = [int(s) for s in (sys.argv[6].split(",") if len(sys.argv) > 6 else "1".split(","))]
 
+if os.environ.get("PREFETCH"):
+    ctx.set_option("ozaki_prefetch", int(os.environ["PREFETCH"]))
 if os.environ.get("POTF2"):
     ctx.set_option("potf2_version", int(os.environ["POTF2"]))
 out["fp64_peak"] = [ctx.measure_fp64_peak() for _ in range(1)]

@@ -39,6 +39,17 @@ typedef struct b200gp_qs b200gp_qs;
  */
 #define B200GP_PROG_STRIDE 4
 #define B200GP_PROG_MAX_INSTR 32
+/* Input transforms (transforms.py:23-161 Transform/Linear/Cholesky/Subspace).  Linear, Cholesky and
+ * Subspace are linear maps z = M x, and a stationary leaf only sees differences, so a transformed
+ * leaf evaluates its distance on M (x1 - x2).  A program may start with up to B200GP_PROG_MAX_METRICS
+ * metric definitions: one header row {B200GP_OP_METRIC, id (1-based), rows, cols} followed by
+ * ceil(rows*cols/4) rows holding M row-major (zero padded); rows, cols <= B200GP_METRIC_MAX_DIM and
+ * cols must equal ndim of the call.  A leaf selects metric `id` by adding 2*id to its distance code
+ * (id 0 = untransformed coordinates).  Metric rows count towards n_instr (<= B200GP_PROG_MAX_ROWS) but
+ * not towards B200GP_PROG_MAX_INSTR. */
+#define B200GP_PROG_MAX_METRICS 3
+#define B200GP_METRIC_MAX_DIM 8
+#define B200GP_PROG_MAX_ROWS (B200GP_PROG_MAX_INSTR + B200GP_PROG_MAX_METRICS * 17)
 enum {
     B200GP_OP_CONST = 0,          /* p0 = value                      base.py:190-209        */
     B200GP_OP_EXP = 1,            /* p0 = scale                      stationary.py:76-82    */
@@ -49,7 +60,8 @@ enum {
     B200GP_OP_EXPSINESQUARED = 6, /* p0 = scale, p1 = gamma          stationary.py:202-205  */
     B200GP_OP_RATIONALQUADRATIC = 7, /* p0 = scale, p1 = alpha       stationary.py:232-235  */
     B200GP_OP_ADD = 16,           /* pops two, pushes sum            base.py:170-177        */
-    B200GP_OP_MUL = 17            /* pops two, pushes product        base.py:180-187        */
+    B200GP_OP_MUL = 17,           /* pops two, pushes product        base.py:180-187        */
+    B200GP_OP_METRIC = 32         /* metric definition header (see above)  transforms.py:57-161 */
 };
 enum { B200GP_DIST_L1 = 0, B200GP_DIST_L2 = 1 }; /* kernels/distance.py:41-59 */
 

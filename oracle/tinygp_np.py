@@ -15,6 +15,7 @@ __all__ = [
     "Constant", "Sum", "Product",
     "Exp", "ExpSquared", "Matern32", "Matern52", "Cosine", "ExpSineSquared",
     "RationalQuadratic",
+    "Transform", "Linear", "Cholesky", "Subspace",
     "Diagonal", "DirectSolver", "GaussianProcess",
     "qs", "QuasisepSolver", "KalmanLogp",
 ]
@@ -66,17 +67,26 @@ class Kernel:
     def evaluate_diff(self, d):  # d: (..., D) explicit differences
         raise NotImplementedError
 
+    def evaluate_pts(self, A, B):
+        """kernel between broadcastable point arrays (..., D); stationary kernels only need A - B, the
+        transforms of transforms.py map the points first."""
+        return self.evaluate_diff(A - B)
+
     def __call__(self, X1, X2=None, chunk=2048):
         """kernels/base.py:84-103"""
         if X2 is None:
             # evaluate_diag(X) = evaluate(X, X)  (base.py:59-66,85-86)
             X1 = np.asarray(X1, dtype=np.float64).reshape(np.shape(X1)[0], -1)
-            return self.evaluate_diff(X1 - X1)
+            return self.evaluate_pts(X1, X1)
         X1 = np.asarray(X1, dtype=np.float64)
         X2 = np.asarray(X2, dtype=np.float64)
+        if X1.ndim == 1:
+            X1 = X1[:, None]
+        if X2.ndim == 1:
+            X2 = X2[:, None]
         out = np.empty((X1.shape[0], X2.shape[0]))
         for s in range(0, X1.shape[0], chunk):
-            out[s:s + chunk] = self.evaluate_diff(_diff(X1[s:s + chunk], X2))
+            out[s:s + chunk] = self.evaluate_pts(X1[s:s + chunk, None, :], X2[None, :, :])
         return out
 
     def matmul(self, X1, X2=None, y=None):
@@ -112,6 +122,9 @@ class Sum(Kernel):
     def evaluate_diff(self, d):
         return self.kernel1.evaluate_diff(d) + self.kernel2.evaluate_diff(d)
 
+    def evaluate_pts(self, A, B):
+        return self.kernel1.evaluate_pts(A, B) + self.kernel2.evaluate_pts(A, B)
+
 
 class Product(Kernel):
     """kernels/base.py:180-187"""
@@ -121,6 +134,9 @@ class Product(Kernel):
 
     def evaluate_diff(self, d):
         return self.kernel1.evaluate_diff(d) * self.kernel2.evaluate_diff(d)
+
+    def evaluate_pts(self, A, B):
+        return self.kernel1.evaluate_pts(A, B) * self.kernel2.evaluate_pts(A, B)
 
 
 class Constant(Kernel):
@@ -217,6 +233,87 @@ class RationalQuadratic(Stationary):
     def evaluate_diff(self, d):
         r2 = self.distance.squared_distance(d) / np.square(self.scale)
         return (1.0 + 0.5 * r2 / self.alpha) ** -self.alpha
+
+
+# ----------------------------------------------------------------------------
+# transforms.py
+# ----------------------------------------------------------------------------
+class _PointTransform(Kernel):
+    """kernel.evaluate(t(X1), t(X2)) with t applied to every point (last axis)."""
+
+    def _map(self, A):
+        raise NotImplementedError
+
+    def evaluate_pts(self, A, B):
+        return self.kernel.evaluate_pts(self._map(np.asarray(A, dtype=np.float64)),
+                                        self._map(np.asarray(B, dtype=np.float64)))
+
+    def evaluate_diff(self, d):
+        raise TypeError("a transformed kernel is not a function of the raw coordinate difference")
+
+
+class Transform(_PointTransform):
+    """transforms.py:23-37"""
+
+    def __init__(self, transform, kernel):
+        self.transform, self.kernel = transform, kernel
+
+    def _map(self, A):
+        flat = A.reshape(-1, A.shape[-1])
+        out = np.asarray([np.atleast_1d(self.transform(p[0] if p.size == 1 else p)) for p in flat], dtype=np.float64)
+        return out.reshape(A.shape[:-1] + (-1,))
+
+
+class Linear(_PointTransform):
+    """transforms.py:40-74"""
+
+    def __init__(self, scale, kernel):
+        self.scale, self.kernel = np.asarray(scale, dtype=np.float64), kernel
+
+    def _map(self, A):
+        if self.scale.ndim < 2:
+            return self.scale * A                       # jnp.multiply(scale, X)
+        if self.scale.ndim == 2:
+            return A @ self.scale.T                     # jnp.dot(scale, X) for every point X
+        raise ValueError("'scale' must be 0-, 1-, or 2-dimensional")
+
+
+class Cholesky(_PointTransform):
+    """transforms.py:77-136"""
+
+    def __init__(self, factor, kernel):
+        self.factor, self.kernel = np.asarray(factor, dtype=np.float64), kernel
+
+    def _map(self, A):
+        if self.factor.ndim < 2:
+            return (1.0 / self.factor) * A
+        if self.factor.ndim == 2:
+            flat = A.reshape(-1, A.shape[-1])
+            out = sla.solve_triangular(self.factor, flat.T, lower=True).T
+            return out.reshape(A.shape)
+        raise ValueError("'scale' must be 0-, 1-, or 2-dimensional")
+
+    @classmethod
+    def from_parameters(cls, diagonal, off_diagonal, kernel):
+        diagonal, off_diagonal = np.asarray(diagonal, float), np.asarray(off_diagonal, float)
+        ndim = diagonal.size
+        if off_diagonal.size != ((ndim - 1) * ndim) // 2:
+            raise ValueError("Dimension mismatch")
+        factor = np.zeros((ndim, ndim))
+        factor[np.diag_indices(ndim)] += diagonal
+        factor[np.tril_indices(ndim, -1)] += off_diagonal
+        return cls(factor, kernel)
+
+
+class Subspace(_PointTransform):
+    """transforms.py:139-161"""
+
+    def __init__(self, axis, kernel):
+        self.axis, self.kernel = axis, kernel
+
+    def _map(self, A):
+        out = A[..., self.axis] if np.ndim(self.axis) == 0 else A[..., list(self.axis)]
+        return out[..., None] if np.ndim(self.axis) == 0 else out
 
 
 # ----------------------------------------------------------------------------

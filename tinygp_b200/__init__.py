@@ -7,5 +7,11 @@
 
 __version__ = "0.1.0"
 
-from tinygp_b200 import kernels as kernels, means as means, noise as noise, solvers as solvers
+from tinygp_b200 import (
+    kernels as kernels,
+    means as means,
+    noise as noise,
+    solvers as solvers,
+    transforms as transforms,
+)
 from tinygp_b200.gp import ConditionResult as ConditionResult, GaussianProcess as GaussianProcess

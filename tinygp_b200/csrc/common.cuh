@@ -33,9 +33,15 @@ struct KProg {
     int dist[B200GP_PROG_MAX_INSTR];
     double p0[B200GP_PROG_MAX_INSTR];
     double p1[B200GP_PROG_MAX_INSTR];
+    // linear input transforms (transforms.py): metric[i] = 0 (identity) or 1-based index into M
+    int metric[B200GP_PROG_MAX_INSTR];
+    int nmetric;
+    int mcols;  // = ndim of the coordinates every metric applies to (0 if no metrics)
+    int mrows[B200GP_PROG_MAX_METRICS];
+    double M[B200GP_PROG_MAX_METRICS][B200GP_METRIC_MAX_DIM * B200GP_METRIC_MAX_DIM];
 };
 
-KProg parse_prog(const double* prog, int n_instr);
+KProg parse_prog(const double* prog, int n_rows, int ndim);
 
 struct CachedBuf {
     void* ptr;

@@ -22,7 +22,17 @@
 #define PI_D 3.141592653589793
 
 // l1 = sum_d |x1_d - x2_d| ; l2sq = sum_d (x1_d - x2_d)^2   (explicit differences, distance.py:45,59)
-__host__ __device__ __forceinline__ double kprog_eval(const KProg& P, double l1, double l2sq) {
+// `diff(d)` returns x1_d - x2_d; it is re-evaluated (not cached in a register array) so that the DMMA
+// GEMM epilogue, which inlines this, keeps its register budget.  Leaves that carry a linear input
+// transform (transforms.py:57-161) measure their distance on M (x1 - x2).
+template <typename F>
+__host__ __device__ __forceinline__ double kprog_eval(const KProg& P, int ndim, F diff) {
+    double l1_id = 0.0, l2_id = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+        const double df = diff(d);
+        l1_id += fabs(df);
+        l2_id += df * df;
+    }
     double st[8];
     int sp = 0;
     for (int i = 0; i < P.n; ++i) {
@@ -42,6 +52,19 @@ __host__ __device__ __forceinline__ double kprog_eval(const KProg& P, double l1,
         if (op == B200GP_OP_CONST) {
             v = p0;
         } else {
+            double l1 = l1_id, l2sq = l2_id;
+            const int m = P.metric[i];
+            if (m > 0) {
+                l1 = 0.0;
+                l2sq = 0.0;
+                const double* Mm = P.M[m - 1];
+                for (int r = 0; r < P.mrows[m - 1]; ++r) {
+                    double z = 0.0;
+                    for (int c = 0; c < ndim; ++c) z += Mm[r * B200GP_METRIC_MAX_DIM + c] * diff(c);
+                    l1 += fabs(z);
+                    l2sq += z * z;
+                }
+            }
             const bool l2 = (P.dist[i] == B200GP_DIST_L2);
             if (op == B200GP_OP_EXPSQUARED || op == B200GP_OP_RATIONALQUADRATIC) {
                 // squared_distance / square(scale)   (stationary.py:105,234 ; distance.py:30-38,58-59)
@@ -76,15 +99,47 @@ __host__ __device__ __forceinline__ double kprog_eval(const KProg& P, double l1,
     return st[0];
 }
 
-KProg parse_prog(const double* prog, int n_instr) {
-    if (n_instr <= 0 || n_instr > B200GP_PROG_MAX_INSTR) throw GpError("kernel program: bad length");
+// k(x, x): every difference is zero, with or without a transform
+__host__ __device__ __forceinline__ double kprog_eval_zero(const KProg& P) {
+    return kprog_eval(P, 0, [](int) { return 0.0; });
+}
+
+// ndim < 0: the caller has no coordinates (k(x, x) only) and metrics are accepted for any width
+KProg parse_prog(const double* prog, int n_rows, int ndim) {
+    if (n_rows <= 0 || n_rows > B200GP_PROG_MAX_ROWS) throw GpError("kernel program: bad length");
     KProg P{};
+    int depth = 0, row = 0;
+    // metric definitions come first
+    while (row < n_rows && (int)prog[(size_t)row * B200GP_PROG_STRIDE] == B200GP_OP_METRIC) {
+        const double* q = prog + (size_t)row * B200GP_PROG_STRIDE;
+        const int id = (int)q[1], r = (int)q[2], c = (int)q[3];
+        if (id != P.nmetric + 1 || id > B200GP_PROG_MAX_METRICS)
+            throw GpError("kernel program: metric ids must be 1..3 in order (at most 3 distinct input transforms)");
+        if (r < 1 || r > B200GP_METRIC_MAX_DIM || c < 1 || c > B200GP_METRIC_MAX_DIM)
+            throw GpError("kernel program: transformed kernels support at most 8 input / output dimensions");
+        if (ndim >= 0 && c != ndim) throw GpError("kernel program: transform width does not match ndim");
+        if (P.nmetric > 0 && c != P.mcols) throw GpError("kernel program: inconsistent transform widths");
+        const int nd_rows = (r * c + B200GP_PROG_STRIDE - 1) / B200GP_PROG_STRIDE;
+        if (row + 1 + nd_rows > n_rows) throw GpError("kernel program: truncated metric definition");
+        const double* data = q + B200GP_PROG_STRIDE;
+        for (int i = 0; i < r; ++i)
+            for (int j = 0; j < c; ++j) {
+                const double v = data[i * c + j];
+                if (!(v == v) || v - v != 0.0) throw GpError("kernel program: non-finite transform matrix");
+                P.M[id - 1][i * B200GP_METRIC_MAX_DIM + j] = v;
+            }
+        P.mrows[id - 1] = r;
+        P.mcols = c;
+        P.nmetric = id;
+        row += 1 + nd_rows;
+    }
+    const int n_instr = n_rows - row;
+    if (n_instr <= 0 || n_instr > B200GP_PROG_MAX_INSTR) throw GpError("kernel program: bad length");
     P.n = n_instr;
-    int depth = 0;
     for (int i = 0; i < n_instr; ++i) {
-        const double* q = prog + (size_t)i * B200GP_PROG_STRIDE;
+        const double* q = prog + (size_t)(row + i) * B200GP_PROG_STRIDE;
         P.op[i] = (int)q[0];
-        P.dist[i] = (int)q[1];
+        const int dcode = (int)q[1];
         P.p0[i] = q[2];
         P.p1[i] = q[3];
         const int op = P.op[i];
@@ -92,6 +147,9 @@ KProg parse_prog(const double* prog, int n_instr) {
             if (depth < 2) throw GpError("kernel program: stack underflow");
             --depth;
         } else if (op >= B200GP_OP_CONST && op <= B200GP_OP_RATIONALQUADRATIC) {
+            if (dcode < 0 || (dcode >> 1) > P.nmetric) throw GpError("kernel program: leaf refers to an undefined metric");
+            P.dist[i] = dcode & 1;
+            P.metric[i] = (op == B200GP_OP_CONST) ? 0 : (dcode >> 1);
             ++depth;
             if (depth > 8) throw GpError("kernel program: expression too deep (max 8)");
         } else {
@@ -123,7 +181,7 @@ struct BuildArgs {
 
 #define BUILD_ROWS 32
 #define BUILD_COLS 128
-__global__ void __launch_bounds__(256) build_rect_kernel(const __grid_constant__ KProg P0, const BuildArgs a) {
+__global__ void __launch_bounds__(256, 3) build_rect_kernel(const __grid_constant__ KProg P0, const BuildArgs a) {
     __shared__ double x1s[BUILD_ROWS * MAX_NDIM];
     __shared__ double x2s[BUILD_COLS * MAX_NDIM];
     __shared__ KProg Pb;
@@ -160,13 +218,9 @@ __global__ void __launch_bounds__(256) build_rect_kernel(const __grid_constant__
             const int64_t c = c0 + cl + e;
             const int64_t gr = r + a.row_off, gc = c + a.col_off;
             if (r < a.n1 && c < a.n2) {
-                double l1 = 0.0, l2 = 0.0;
-                for (int d = 0; d < nd; ++d) {
-                    const double df = x1s[rl * nd + d] - x2s[(cl + e) * nd + d];
-                    l1 += fabs(df);
-                    l2 += df * df;
-                }
-                double k = kprog_eval(P, l1, l2);
+                const double* xa = x1s + rl * nd;
+                const double* xb = x2s + (cl + e) * nd;
+                double k = kprog_eval(P, nd, [&](int d) { return xa[d] - xb[d]; });
                 if (a.diag != nullptr && gr == gc) k += a.diag[gr];
                 v[e] = k;
             } else {
@@ -187,7 +241,7 @@ __global__ void __launch_bounds__(256) build_rect_kernel(const __grid_constant__
 // diag: out[i] = k(x_i, x_i)
 __global__ void build_diag_kernel(const __grid_constant__ KProg P, int64_t n, double* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = kprog_eval(P, 0.0, 0.0);
+    if (i < n) out[i] = kprog_eval_zero(P);
 }
 
 // out[i] = sum_j k(X1_i, X2_j) y_j   (Kernel.matmul, base.py:68-82) -- one warp per row
@@ -201,13 +255,8 @@ __global__ void __launch_bounds__(256) kernel_matvec_kernel(const __grid_constan
     for (int d = 0; d < ndim; ++d) xi[d] = X1[i * ndim + d];
     double acc = 0.0;
     for (int64_t j = lane; j < n2; j += 32) {
-        double l1 = 0.0, l2 = 0.0;
-        for (int d = 0; d < ndim; ++d) {
-            const double df = xi[d] - X2[j * ndim + d];
-            l1 += fabs(df);
-            l2 += df * df;
-        }
-        acc += kprog_eval(P, l1, l2) * y[j];
+        const double* xj = X2 + j * ndim;
+        acc += kprog_eval(P, ndim, [&](int d) { return xi[d] - xj[d]; }) * y[j];
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) out[i] = acc;
@@ -384,13 +433,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(const __grid_consta
                 for (int q = 0; q < 2; ++q) {
                     const int64_t gc = g.col0 + c + q;
                     if (gr < g.n_valid && gc < g.n_valid) {
-                        double l1 = 0.0, l2 = 0.0;
-                        for (int d = 0; d < g.ndim; ++d) {
-                            const double df = g.X[gr * g.ndim + d] - g.X[gc * g.ndim + d];
-                            l1 += fabs(df);
-                            l2 += df * df;
-                        }
-                        e[q] = kprog_eval(P, l1, l2);
+                        const double* xa = g.X + gr * g.ndim;
+                        const double* xb = g.X + gc * g.ndim;
+                        e[q] = kprog_eval(P, g.ndim, [&](int d) { return xa[d] - xb[d]; });
                         if (gr == gc) e[q] += g.diag[gr];
                     } else {
                         e[q] = (gr == gc) ? 1.0 : 0.0;
@@ -799,7 +844,7 @@ void dense_build_region(b200gp_dense* s, int64_t r0, int64_t c0, int64_t ncols) 
     ctx->prof.build_bytes += 8.0 * (double)(np - r0) * (double)ncols;
 }
 
-double dense_kernel_diag_value(const KProg& P) { return kprog_eval(P, 0.0, 0.0); }
+double dense_kernel_diag_value(const KProg& P) { return kprog_eval_zero(P); }
 
 // rows [r0, r1) x columns [c0, c0+ncols) only (multi-GPU row sharding)
 struct BuildRegionArgs { int64_t r0, r1, c0, ncols; };
@@ -1178,7 +1223,7 @@ int b200gp_kernel_matrix(b200gp_ctx* ctx, const double* prog, int n_instr, const
     API_BEGIN(ctx)
     if (ndim < 1 || ndim > MAX_NDIM) throw GpError("kernel_matrix: ndim must be in [1, 16]");
     if (n1 <= 0 || n2 <= 0) throw GpError("kernel_matrix: empty input");
-    KProg P = parse_prog(prog, n_instr);
+    KProg P = parse_prog(prog, n_instr, ndim);
     double* x1 = (double*)_ctx->alloc((size_t)n1 * ndim * 8);
     double* x2 = (double*)_ctx->alloc((size_t)n2 * ndim * 8);
     double* o = (double*)_ctx->alloc((size_t)n1 * n2 * 8);
@@ -1196,9 +1241,9 @@ int b200gp_kernel_matrix(b200gp_ctx* ctx, const double* prog, int n_instr, const
 int b200gp_kernel_diag(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
                        double* out) {
     API_BEGIN(ctx)
-    (void)X; (void)ndim;  // stationary kernels: k(x, x) does not depend on x
+    (void)X;  // stationary kernels: k(x, x) does not depend on x (nor on a linear input transform)
     if (n <= 0) throw GpError("kernel_diag: empty input");
-    KProg P = parse_prog(prog, n_instr);
+    KProg P = parse_prog(prog, n_instr, ndim);
     double* o = (double*)_ctx->alloc((size_t)n * 8);
     build_diag_kernel<<<nblocks(n, 256), 256, 0, _ctx->stream>>>(P, n, o);
     CUDA_CHECK(cudaGetLastError());
@@ -1214,7 +1259,7 @@ int b200gp_kernel_matvec(b200gp_ctx* ctx, const double* prog, int n_instr, const
     API_BEGIN(ctx)
     if (ndim < 1 || ndim > MAX_NDIM) throw GpError("kernel_matvec: ndim must be in [1, 16]");
     if (n1 <= 0 || n2 <= 0) throw GpError("kernel_matvec: empty input");
-    KProg P = parse_prog(prog, n_instr);
+    KProg P = parse_prog(prog, n_instr, ndim);
     double* x1 = (double*)_ctx->alloc((size_t)n1 * ndim * 8);
     double* x2 = (double*)_ctx->alloc((size_t)n2 * ndim * 8);
     double* yd = (double*)_ctx->alloc((size_t)n2 * 8);
@@ -1237,7 +1282,7 @@ int b200gp_kernel_matvec(b200gp_ctx* ctx, const double* prog, int n_instr, const
 int b200gp_dense_create(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
                         const double* diag, b200gp_dense** out, int* info) {
     API_BEGIN(ctx)
-    KProg P = parse_prog(prog, n_instr);
+    KProg P = parse_prog(prog, n_instr, ndim);
     b200gp_dense* s = dense_factor_from_prog(_ctx, P, X, n, ndim, diag, true);
     *out = s;
     if (info) *info = s->info;
@@ -1335,7 +1380,7 @@ int b200gp_dense_condition(b200gp_dense* s, const double* prog, int n_instr, con
                            const double* diag_test, double* out) {
     API_BEGIN(s->ctx)
     if (!s->has_prog) throw GpError("condition: solver was built from a precomputed covariance (no coordinates)");
-    KProg P = parse_prog(prog, n_instr);
+    KProg P = parse_prog(prog, n_instr, s->ndim);
     const int64_t n = s->n, np = s->np;
     const int nd = s->ndim;
     double* xt_dev;
@@ -1465,7 +1510,7 @@ static double dense_logp_impl(b200gp_ctx* ctx, const KProg& P, const double* X, 
 int b200gp_dense_log_probability(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n,
                                  int ndim, const double* diag, const double* resid, double* logp) {
     API_BEGIN(ctx)
-    KProg P = parse_prog(prog, n_instr);
+    KProg P = parse_prog(prog, n_instr, ndim);
     *logp = dense_logp_impl(_ctx, P, X, n, ndim, diag, resid);
     API_END
 }
@@ -1586,7 +1631,7 @@ extern "C" int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const doubl
     if (nbatch <= 0 || n <= 0) throw GpError("batched log_probability: empty batch");
     if (ndim < 1 || ndim > MAX_NDIM) throw GpError("batched log_probability: ndim must be in [1, 16]");
     std::vector<KProg> hp((size_t)nbatch);
-    for (int64_t b = 0; b < nbatch; ++b) hp[b] = parse_prog(progs + (size_t)b * n_instr * B200GP_PROG_STRIDE, n_instr);
+    for (int64_t b = 0; b < nbatch; ++b) hp[b] = parse_prog(progs + (size_t)b * n_instr * B200GP_PROG_STRIDE, n_instr, ndim);
     KProg* dp = (KProg*)_ctx->alloc((size_t)nbatch * sizeof(KProg));
     double* dX = (double*)_ctx->alloc((size_t)n * ndim * 8);
     double* dd = (double*)_ctx->alloc((size_t)n * 8);

@@ -1268,7 +1268,7 @@ extern "C" {
 int b200gp_mg_create(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
                      const double* diag, const double* resid, int slices, int streaming, b200gp_mg** out) {
     API_BEGIN(ctx)
-    KProg P = parse_prog(prog, n_instr);
+    KProg P = parse_prog(prog, n_instr, ndim);
     b200gp_mg* m = new b200gp_mg();
     m->ctx = _ctx;
     m->streaming = (streaming != 0);

@@ -7,13 +7,13 @@ program* (include/b200gp.h) and runs the pairwise-build CUDA kernel.
 
 from __future__ import annotations
 
-__all__ = ["Kernel", "Conditioned", "Custom", "Sum", "Product", "Constant", "DotProduct", "Polynomial"]
+__all__ = ["Kernel", "Conditioned", "Custom", "Sum", "Product", "Constant", "DotProduct", "Polynomial", "Lowering"]
 
 import numpy as np
 
 from tinygp_b200 import _cabi
 
-OP_CONST, OP_ADD, OP_MUL = 0, 16, 17
+OP_CONST, OP_ADD, OP_MUL, OP_METRIC = 0, 16, 17, 32
 
 
 def _as_coords(X):
@@ -25,18 +25,118 @@ def _as_coords(X):
     raise ValueError("coordinates must have shape (N,) or (N, D); pytrees are not supported by the B200 backend")
 
 
+class Lowering:
+    """State threaded through ``Kernel.lower``: the input transform in force at the current node.
+
+    The device interpreter evaluates a stationary leaf on ``M (x1 - x2)`` for a per-leaf matrix ``M``
+    (include/b200gp.h, B200GP_OP_METRIC).  ``transforms.Linear/Cholesky/Subspace`` (transforms.py:57-161)
+    compose into ``M`` directly.  A general ``transforms.Transform(callable)`` (transforms.py:23-37) is
+    applied on the host, point by point, and its output is appended to the coordinates as extra columns
+    which the leaf's matrix then selects -- so a program is always lowered *for* a coordinate array and the
+    (possibly augmented) coordinates are what goes to the device.
+    """
+
+    MAX_METRICS = 3
+    MAX_DIM = 8
+
+    def __init__(self, X=None, scalar_coords=False):
+        self.X = X                    # (N, D) or None when lowering without coordinates
+        self.ndim0 = None if X is None else X.shape[1]   # width before any host-computed columns are appended
+        self.scalar_coords = scalar_coords
+        self.matrix = None            # None = untransformed coordinates
+        self.metrics: list[np.ndarray] = []
+
+    # -- used by transform nodes ----------------------------------------------------------
+    def width(self) -> int:
+        if self.X is None:
+            raise ValueError("a kernel with input transforms can only be lowered for given coordinates "
+                             "(use Kernel.lower_for(X))")
+        return self.X.shape[1]
+
+    def current(self) -> np.ndarray:
+        return np.eye(self.ndim0, self.width()) if self.matrix is None else self.matrix
+
+    def coords(self) -> np.ndarray:
+        """coordinates seen by the current node, one row per point"""
+        self.width()
+        if self.matrix is None:
+            return self.X[:, :self.ndim0]
+        return self.X[:, :self.matrix.shape[1]] @ self.matrix.T   # columns appended later are not seen
+
+    def append_columns(self, Z: np.ndarray) -> np.ndarray:
+        """augment the coordinates with host-computed columns; returns the matrix selecting them"""
+        w0 = self.width()
+        self.X = np.ascontiguousarray(np.concatenate([self.X, Z], axis=1))
+        sel = np.zeros((Z.shape[1], self.X.shape[1]))
+        sel[np.arange(Z.shape[1]), w0 + np.arange(Z.shape[1])] = 1.0
+        if self.matrix is not None:  # the enclosing matrix refers to the old, narrower coordinates
+            self.matrix = np.pad(self.matrix, ((0, 0), (0, Z.shape[1])))
+        return sel
+
+    # -- used by leaves -------------------------------------------------------------------
+    def metric_code(self) -> int:
+        if self.matrix is None:
+            return 0
+        M = np.asarray(self.matrix, dtype=np.float64)
+        for i, other in enumerate(self.metrics):
+            k = min(other.shape[1], M.shape[1])
+            if other.shape[0] == M.shape[0] and np.array_equal(other[:, :k], M[:, :k]) \
+                    and not other[:, k:].any() and not M[:, k:].any():
+                return 2 * (i + 1)
+        if len(self.metrics) == self.MAX_METRICS:
+            raise NotImplementedError(f"at most {self.MAX_METRICS} distinct input transforms per kernel expression")
+        self.metrics.append(M.copy())
+        return 2 * len(self.metrics)
+
+    def metric_rows(self) -> list[tuple[float, float, float, float]]:
+        rows: list[tuple[float, float, float, float]] = []
+        if not self.metrics:
+            return rows
+        w = self.width()
+        for i, M in enumerate(self.metrics):
+            M = np.pad(M, ((0, 0), (0, w - M.shape[1])))
+            if M.shape[0] > self.MAX_DIM or w > self.MAX_DIM:
+                raise NotImplementedError(f"transformed kernels support at most {self.MAX_DIM} (augmented) input "
+                                          "dimensions on the B200 backend")
+            if not np.all(np.isfinite(M)):
+                raise ValueError("non-finite input transform")
+            rows.append((float(OP_METRIC), float(i + 1), float(M.shape[0]), float(w)))
+            flat = np.zeros(-(-M.size // 4) * 4)
+            flat[:M.size] = M.ravel()
+            rows.extend(tuple(r) for r in flat.reshape(-1, 4))
+        return rows
+
+
 class Kernel:
     """Base class (base.py:29-126)."""
 
-    def lower(self) -> list[tuple[int, int, float, float]]:
+    def lower(self, lc: Lowering) -> list[tuple[int, int, float, float]]:
         raise NotImplementedError(
             f"{type(self).__name__} cannot be lowered to a device kernel program: "
-            "unsupported by the B200 solver backend (only stationary kernels and their sums/products)"
+            "unsupported by the B200 solver backend (only stationary kernels, their sums/products and "
+            "input transforms of them)"
         )
 
     def program(self) -> np.ndarray:
-        instr = self.lower()
+        """the kernel program of an expression without input transforms"""
+        lc = Lowering()
+        instr = self.lower(lc)
         return np.ascontiguousarray(np.array(instr, dtype=np.float64).reshape(-1, _cabi.PROG_STRIDE))
+
+    def lower_for(self, X) -> tuple[np.ndarray, np.ndarray]:
+        """(program, device coordinates) for the coordinates X; the coordinates are X itself unless the
+        expression holds a general ``transforms.Transform``, whose output is appended as extra columns."""
+        x, scalar = _as_coords(X)
+        lc = Lowering(x, scalar)
+        instr = self.lower(lc)
+        if lc.X.shape[1] != lc.ndim0:
+            # columns were appended: leaves on the untransformed coordinates must not see them
+            lc.matrix = np.eye(lc.ndim0, lc.X.shape[1])
+            instr = [(op, d + lc.metric_code(), p0, p1) if (0 < op < OP_ADD and d < 2) else (op, d, p0, p1)
+                     for (op, d, p0, p1) in instr]
+        rows = lc.metric_rows() + instr
+        prog = np.ascontiguousarray(np.array(rows, dtype=np.float64).reshape(-1, _cabi.PROG_STRIDE))
+        return prog, np.ascontiguousarray(lc.X)
 
     # -- evaluation ---------------------------------------------------------------------
     def evaluate(self, X1, X2):
@@ -50,14 +150,13 @@ class Kernel:
 
     def __call__(self, X1, X2=None):
         ctx = _cabi.get_context()
-        prog = self.program()
-        x1, _ = _as_coords(X1)
+        prog, x1 = self.lower_for(X1)
         if X2 is None:  # base.py:85-93
             out = np.empty(x1.shape[0])
             ctx.check(ctx.lib.b200gp_kernel_diag(ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(x1),
                                                  x1.shape[0], x1.shape[1], _cabi.ptr(out)))
             return out
-        x2, _ = _as_coords(X2)
+        _, x2 = self.lower_for(X2)
         if x1.shape[1] != x2.shape[1]:
             raise ValueError("X1 and X2 must have the same number of input dimensions")
         out = np.empty((x1.shape[0], x2.shape[0]))
@@ -77,9 +176,10 @@ class Kernel:
         if y.ndim != 1:
             return np.dot(self(X1, X2), y)
         ctx = _cabi.get_context()
-        prog = self.program()
-        x1, _ = _as_coords(X1)
-        x2, _ = _as_coords(X2)
+        prog, x1 = self.lower_for(X1)
+        _, x2 = self.lower_for(X2)
+        if x1.shape[1] != x2.shape[1]:
+            raise ValueError("X1 and X2 must have the same number of input dimensions")
         yy = _cabi.f64(y)
         out = np.empty(x1.shape[0])
         ctx.check(ctx.lib.b200gp_kernel_matvec(ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(x1), x1.shape[0],
@@ -117,8 +217,8 @@ class Sum(Kernel):
     def __init__(self, kernel1: Kernel, kernel2: Kernel):
         self.kernel1, self.kernel2 = kernel1, kernel2
 
-    def lower(self):
-        return self.kernel1.lower() + self.kernel2.lower() + [(OP_ADD, 0, 0.0, 0.0)]
+    def lower(self, lc):
+        return self.kernel1.lower(lc) + self.kernel2.lower(lc) + [(OP_ADD, 0, 0.0, 0.0)]
 
 
 class Product(Kernel):
@@ -127,8 +227,8 @@ class Product(Kernel):
     def __init__(self, kernel1: Kernel, kernel2: Kernel):
         self.kernel1, self.kernel2 = kernel1, kernel2
 
-    def lower(self):
-        return self.kernel1.lower() + self.kernel2.lower() + [(OP_MUL, 0, 0.0, 0.0)]
+    def lower(self, lc):
+        return self.kernel1.lower(lc) + self.kernel2.lower(lc) + [(OP_MUL, 0, 0.0, 0.0)]
 
 
 class Constant(Kernel):
@@ -139,7 +239,7 @@ class Constant(Kernel):
             raise ValueError("The value of a constant kernel must be a scalar")
         self.value = float(value)
 
-    def lower(self):
+    def lower(self, lc):
         return [(OP_CONST, 0, self.value, 0.0)]
 
 

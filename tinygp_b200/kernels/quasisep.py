@@ -62,7 +62,7 @@ class Quasisep(Kernel):
             X2 = X1
         return self(X1, X2) @ np.asarray(y, dtype=np.float64)
 
-    def lower(self):
+    def lower(self, lc=None):
         raise NotImplementedError(
             "quasiseparable kernels are handled by QuasisepSolver; they do not lower to a dense kernel program")
 

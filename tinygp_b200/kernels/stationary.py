@@ -36,10 +36,10 @@ class Stationary(Kernel):
     def _params(self):
         return float(self.scale), 0.0
 
-    def lower(self):
+    def lower(self, lc):
         self._check()
         p0, p1 = self._params()
-        return [(self.opcode, self.distance.code, p0, p1)]
+        return [(self.opcode, self.distance.code + lc.metric_code(), p0, p1)]
 
 
 class Exp(Stationary):

@@ -60,13 +60,13 @@ def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streamin
     if world > 1 and not getattr(ctx, "on_torch_stream", False):
         raise _cabi.B200Error("sharded runs need a context created by multigpu.make_context()")
     lib = ctx.lib
-    prog = kernel.program()
     if X_dev is None:
-        x, _ = _as_coords(X)
+        prog, x = kernel.lower_for(X)
         n, ndim = x.shape
         xp, dp, rp = _cabi.ptr(x), _cabi.ptr(_cabi.f64(diag)), _cabi.ptr(_cabi.f64(resid))
         keep = (x,)
     else:
+        prog = kernel.program()   # device-resident coordinates: no host-side transforms
         n, ndim = X_dev.shape
         xp, dp, rp = X_dev.data_ptr(), diag_dev.data_ptr(), resid_dev.data_ptr()
         keep = ()

@@ -27,11 +27,10 @@ class DirectSolver(Solver):
         info = c_int(0)
         lib = self._ctx.lib
         if covariance is None:
-            x, _ = _as_coords(X)
+            prog, x = kernel.lower_for(X)   # x = X, plus host-computed columns of any transforms.Transform
             diag = _cabi.f64(noise.diagonal())
             if diag.shape != (x.shape[0],):
                 raise ValueError("noise diagonal must have shape (N,)")
-            prog = kernel.program()
             self._n = x.shape[0]
             self.variance_value = kernel(X) + diag                              # direct.py:49
             self._cov = None
@@ -101,13 +100,13 @@ class DirectSolver(Solver):
         return buf.reshape(y.shape)
 
     def condition(self, kernel: Kernel, X_test, noise) -> Any:  # direct.py:75-95
-        prog = kernel.program()
         diag = _cabi.f64(noise.diagonal())
         if X_test is None:
+            prog, _ = kernel.lower_for(self.X)
             m = self._n
             xt_ptr = None
         else:
-            xt, _ = _as_coords(X_test)
+            prog, xt = kernel.lower_for(X_test)
             m = xt.shape[0]
             xt_ptr = _cabi.ptr(xt)
         if diag.shape != (m,):

@@ -59,6 +59,10 @@ enum {
     B200GP_OP_COSINE = 5,         /* p0 = scale                      stationary.py:173-175  */
     B200GP_OP_EXPSINESQUARED = 6, /* p0 = scale, p1 = gamma          stationary.py:202-205  */
     B200GP_OP_RATIONALQUADRATIC = 7, /* p0 = scale, p1 = alpha       stationary.py:232-235  */
+    /* closed forms k(tau) of the quasiseparable kernels, used when one is evaluated densely
+     * (kernels/quasisep.py:118-163 evaluate / condition at test points); r = distance (unscaled) */
+    B200GP_OP_EXPCOS = 8,         /* exp(-p0 r) cos(p1 r)            quasisep.py:343-488    */
+    B200GP_OP_EXPSIN = 9,         /* exp(-p0 r) sin(p1 r)            quasisep.py:343-488    */
     B200GP_OP_ADD = 16,           /* pops two, pushes sum            base.py:170-177        */
     B200GP_OP_MUL = 17,           /* pops two, pushes product        base.py:180-187        */
     B200GP_OP_METRIC = 32         /* metric definition header (see above)  transforms.py:57-161 */
@@ -228,6 +232,13 @@ int b200gp_qs_log_probability_dev(b200gp_ctx* ctx, const double* comps, int ncom
                                   const double* t_dev, int64_t n, const double* diag_dev,
                                   const double* resid_dev, int assume_sorted, int* unsorted,
                                   double* logp);
+/* Quasisep.matmul(X1, X2, y) = to_general_qsm(X1, X2) @ y  (kernels/quasisep.py:118-163, solvers/quasisep/
+ * general.py:66-106) in O((n + m) J^2): a forward and a backward state scan over the n sorted training
+ * coordinates, then one searchsorted + two transition matrices per test point.  Host buffers; Y is n x nrhs and
+ * out is m x nrhs, row-major.  This is the predictive mean at arbitrary test points (gp.py:357). */
+int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t_test,
+                            int64_t m, const double* t_train, int64_t n, const double* Y, int64_t nrhs,
+                            double* out);
 /* jnp.searchsorted(X2, X1, side="right") - 1  (kernels/quasisep.py:121): bit-exact indices */
 int b200gp_searchsorted_right_m1(b200gp_ctx* ctx, const double* sorted, int64_t n,
                                  const double* query, int64_t m, int64_t* out);

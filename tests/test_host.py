@@ -78,17 +78,32 @@ def test_quasisep_components():
         Q.Matern32(1.0) + kernels.Exp(1.0)
     with pytest.raises(NotImplementedError):
         (Q.Matern32(1.0) * Q.Exp(1.0)).components()
-    # closed forms used for dense evaluation agree with the oracle's state-space evaluation
+
+
+QS_PAIRS = [
+    (lambda: Q.SHO(1.5, 3.0, 1.8) + 0.7 * Q.Matern32(1.5, 0.9),
+     lambda o: o.qs.SHO(1.5, 3.0, 1.8) + o.qs.Scale(o.qs.Matern32(1.5, 0.9), 0.7)),
+    (lambda: Q.SHO(1.5, 0.3), lambda o: o.qs.SHO(1.5, 0.3)),
+    (lambda: Q.SHO(1.5, 0.5), lambda o: o.qs.SHO(1.5, 0.5)),
+    (lambda: Q.Matern52(1.3, 0.8), lambda o: o.qs.Matern52(1.3, 0.8)),
+    (lambda: Q.Exp(1.3, 0.8), lambda o: o.qs.Exp(1.3, 0.8)),
+    (lambda: Q.Cosine(1.3, 0.8), lambda o: o.qs.Cosine(1.3, 0.8)),
+    (lambda: Q.Celerite(1.1, 0.8, 0.9, 0.1), lambda o: o.qs.Celerite(1.1, 0.8, 0.9, 0.1)),
+]
+
+
+@pytest.mark.parametrize("case", range(len(QS_PAIRS)))
+def test_quasisep_dense_lowering(case):
+    """the closed-form k(tau) programs that evaluate a quasiseparable kernel densely on the device agree with the
+    oracle's state-space evaluation (kernels/quasisep.py:118-145); checked here through the Python restatement of
+    the device interpreter, on the GPU in tests/test_quasisep_gpu.py"""
     from oracle import tinygp_np as o
+    from test_transforms import _interp
+    kk, oo = QS_PAIRS[case][0](), QS_PAIRS[case][1](o)
     X = np.linspace(0, 3, 7)
-    ko = o.qs.SHO(1.5, 3.0, 1.8) + o.qs.Scale(o.qs.Matern32(1.5, 0.9), 0.7)
-    np.testing.assert_allclose(k(X, X), ko(X, X), rtol=1e-12, atol=1e-14)
-    for kk, oo in [(Q.SHO(1.5, 0.3), o.qs.SHO(1.5, 0.3)), (Q.SHO(1.5, 0.5), o.qs.SHO(1.5, 0.5)),
-                   (Q.Matern52(1.3, 0.8), o.qs.Matern52(1.3, 0.8)), (Q.Exp(1.3, 0.8), o.qs.Exp(1.3, 0.8)),
-                   (Q.Cosine(1.3, 0.8), o.qs.Cosine(1.3, 0.8)),
-                   (Q.Celerite(1.1, 0.8, 0.9, 0.1), o.qs.Celerite(1.1, 0.8, 0.9, 0.1))]:
-        np.testing.assert_allclose(kk(X, X), oo(X, X), rtol=1e-11, atol=1e-13)
-        np.testing.assert_allclose(kk(X), oo(X), rtol=1e-12)
+    prog, x = kk.lower_for(X)
+    got = np.array([[_interp(prog, a, b) for b in x] for a in x])
+    np.testing.assert_allclose(got, oo(X, X), rtol=1e-11, atol=1e-13)
 
 
 def test_noise_diagonal():

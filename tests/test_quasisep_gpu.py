@@ -148,3 +148,72 @@ def test_large_n_against_c_oracle_and_properties():
     np.testing.assert_allclose(s.dot_triangular(s.solve_triangular(z)), z, rtol=1e-8, atol=1e-9)
     a1 = s.solve_triangular(s.solve_triangular(y), transpose=True)
     np.testing.assert_allclose(s.matmul(a1), y, rtol=1e-7, atol=1e-8)     # K K^-1 y == y
+
+
+# ------------------------------------------------------------------------------------------------
+# row f2: dense evaluation and the GeneralQSM product on the device (kernels/quasisep.py:118-163)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(QS))
+def test_dense_evaluation_on_device(name):
+    """k(X1, X2) of a quasiseparable kernel: closed form in the CUDA build kernel vs the oracle's
+    state-space evaluate (h Pinf T h)."""
+    k, ko = QS[name](), to_oracle(QS[name]())
+    rng = np.random.default_rng(5)
+    X1, X2 = rng.uniform(-3, 3, 90), rng.uniform(-3, 3, 60)
+    X2[:5] = X1[:5]                                  # tau = 0 pairs
+    np.testing.assert_allclose(k(X1, X2), ko(X1, X2), rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(k(X1), ko(X1), rtol=1e-12)
+    with pytest.raises(ValueError):
+        k(np.zeros((4, 2)), np.zeros((4, 2)))
+
+
+@pytest.mark.parametrize("name", sorted(QS))
+@pytest.mark.parametrize("n,m", [(1, 3), (60, 45), (300, 40)])
+def test_general_matmul_parity(name, n, m):
+    """Quasisep.matmul(X1, X2, y) (general.py:66-106) vs the dense product; test points unsorted, outside the
+    training range on both sides, and coinciding with training points.  (Sizes are bounded by the oracle, whose
+    dense evaluate is a Python loop per pair; n = 300 spans 5 scan chunks, the large test below the tree.)"""
+    k, ko = QS[name](), to_oracle(QS[name]())
+    rng = np.random.default_rng(n + m)
+    X2 = np.sort(rng.uniform(-3, 3, n))
+    X1 = rng.uniform(-4, 4, m)
+    X1[0], X1[1], X1[2] = X2[0], X2[-1], X2[n // 2]
+    if n > 10:
+        X2[7] = X2[6]                                # a repeated training coordinate
+    y = rng.normal(size=n)
+    Kd = ko(X1, X2)
+    np.testing.assert_allclose(k.matmul(X1, X2, y), Kd @ y, rtol=1e-9, atol=1e-10)
+    Y = rng.normal(size=(n, 3))
+    np.testing.assert_allclose(k.matmul(X1, X2, Y), Kd @ Y, rtol=1e-9, atol=1e-10)
+    if n <= 60:
+        np.testing.assert_allclose(k.matmul(X2, y), ko(X2, X2) @ y, rtol=1e-9, atol=1e-10)   # symmetric form
+
+
+def test_predict_at_test_points_parity():
+    """gp.predict(y, X_test) through QuasisepSolver: mean by the O(n + m) general product (gp.py:357), variance by
+    the dense branch (solver.py:131-139) with the kernel evaluated on the device."""
+    X, y, rng = _data(200)
+    Xt = rng.uniform(-3.5, 3.5, 60)                  # unsorted, partly extrapolating
+    k = Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9)
+    mu, var = GaussianProcess(k, X, diag=0.1).predict(y, Xt, return_var=True)
+    muo, varo = o.GaussianProcess(to_oracle(k), X, diag=0.1).predict(y, Xt, return_var=True)
+    np.testing.assert_allclose(mu, muo, rtol=5e-7, atol=5e-7)
+    np.testing.assert_allclose(var, varo, rtol=5e-7, atol=5e-7)
+
+
+def test_general_matmul_large_consistency():
+    """N = 3e5 training points, M = 1e5 test points: rows at training coordinates equal the symmetric product
+    (core.py:499-505) minus the noise term, and far-away test points decouple."""
+    n, m = 300_000, 100_000
+    rng = np.random.default_rng(9)
+    X = np.sort(rng.uniform(0, 3e4, n))
+    y = np.sin(X) + 0.1 * rng.normal(size=n)
+    k = Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9)
+    diag = np.full(n, 0.1)
+    gp = GaussianProcess(k, X, diag=diag)
+    sym = gp.solver.matmul(y) - diag * y
+    pick = rng.integers(0, n, m)
+    got = k.matmul(X[pick], X, y)
+    np.testing.assert_allclose(got, sym[pick], rtol=1e-9, atol=1e-9)
+    far = k.matmul(np.array([-1e5, 1e6]), X, y)     # exp(-tau) underflows: no coupling (Matern/SHO decay)
+    assert np.all(np.abs(far) < 1e-300)

@@ -43,7 +43,11 @@ def _interp(prog, x1, x2):
             r2 = (l2sq if l2 else l1 * l1) / (p0 * p0)
             st.append(np.exp(-0.5 * r2) if op == 2 else (1 + 0.5 * r2 / p1) ** (-p1))
             continue
-        r = ((l1 if l2sq == 0 else np.sqrt(l2sq)) if l2 else l1) / p0
+        dist = (l1 if l2sq == 0 else np.sqrt(l2sq)) if l2 else l1
+        if op in (8, 9):
+            st.append(np.exp(-p0 * dist) * (np.cos(p1 * dist) if op == 8 else np.sin(p1 * dist)))
+            continue
+        r = dist / p0
         if op == 1:
             v = np.exp(-r)
         elif op == 3:

@@ -77,6 +77,12 @@ __host__ __device__ __forceinline__ double kprog_eval(const KProg& P, int ndim, 
             } else {
                 // distance (distance.py:44-45 / 51-56: sqrt with the r2==0 guard)
                 const double dist = l2 ? ((l2sq == 0.0) ? l1 : sqrt(l2sq)) : l1;
+                if (op == B200GP_OP_EXPCOS || op == B200GP_OP_EXPSIN) {
+                    double sn, cs;
+                    sincos(p1 * dist, &sn, &cs);
+                    st[sp++] = exp(-p0 * dist) * ((op == B200GP_OP_EXPCOS) ? cs : sn);
+                    continue;
+                }
                 const double r = dist / p0;
                 if (op == B200GP_OP_EXP) {
                     v = exp(-r);
@@ -146,7 +152,7 @@ KProg parse_prog(const double* prog, int n_rows, int ndim) {
         if (op == B200GP_OP_ADD || op == B200GP_OP_MUL) {
             if (depth < 2) throw GpError("kernel program: stack underflow");
             --depth;
-        } else if (op >= B200GP_OP_CONST && op <= B200GP_OP_RATIONALQUADRATIC) {
+        } else if (op >= B200GP_OP_CONST && op <= B200GP_OP_EXPSIN) {
             if (dcode < 0 || (dcode >> 1) > P.nmetric) throw GpError("kernel program: leaf refers to an undefined metric");
             P.dist[i] = dcode & 1;
             P.metric[i] = (op == B200GP_OP_CONST) ? 0 : (dcode >> 1);

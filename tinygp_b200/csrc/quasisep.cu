@@ -729,8 +729,13 @@ __global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_co
 // ---------------------------------------------------------------------------------------------
 // affine scans: triangular solves and products
 // ---------------------------------------------------------------------------------------------
-enum { OP_LOWER_SOLVE = 0, OP_UPPER_SOLVE = 1, OP_LOWER_DOT = 2, OP_SYMM_LOWER = 3, OP_SYMM_UPPER = 4 };
-__host__ __device__ constexpr bool op_reverse(int op) { return op == OP_UPPER_SOLVE || op == OP_SYMM_UPPER; }
+// OP_GEN_LOWER / OP_GEN_UPPER: the two state scans of GeneralQSM.matmul (general.py:75-104).  Same recursions as
+// the symmetric product, but the replay pass stores the n x J STATES (forward f_k, backward g_k) instead of outputs.
+enum { OP_LOWER_SOLVE = 0, OP_UPPER_SOLVE = 1, OP_LOWER_DOT = 2, OP_SYMM_LOWER = 3, OP_SYMM_UPPER = 4,
+       OP_GEN_LOWER = 5, OP_GEN_UPPER = 6 };
+__host__ __device__ constexpr bool op_reverse(int op) {
+    return op == OP_UPPER_SOLVE || op == OP_SYMM_UPPER || op == OP_GEN_UPPER;
+}
 
 // logical position i of a reverse scan is physical index n-1-i
 template <int J, int OP>
@@ -792,14 +797,14 @@ __global__ void __launch_bounds__(QS_THREADS) affine_chunk_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j];
             }
-        } else if (OP == OP_SYMM_LOWER) {  // g' = a g + q x
+        } else if (OP == OP_SYMM_LOWER || OP == OP_GEN_LOWER) {  // g' = a g + q x
 #pragma unroll
             for (int i = 0; i < J; ++i) {
                 bk[i] = m.q[i] * xk;
 #pragma unroll
                 for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j];
             }
-        } else {  // OP_SYMM_UPPER: g' = a^T g + p x
+        } else {  // OP_SYMM_UPPER, OP_GEN_UPPER: g' = a^T g + p x
 #pragma unroll
             for (int i = 0; i < J; ++i) {
                 bk[i] = p[i] * xk;
@@ -918,6 +923,30 @@ __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_
                 ng[i] = v + m.q[i] * xk;
             }
             o4[uu] = y;
+        } else if (OP == OP_GEN_LOWER) {  // general.py:77-83: f_k = a_k f_{k-1} + ql_k x_k, every f_k kept
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
+                ng[i] = v + m.q[i] * xk;
+            }
+            strow<J>(out, k, ng);
+            y = 0.0;
+        } else if (OP == OP_GEN_UPPER) {  // general.py:89-101: g_k = a_{k+1}^T g_{k+1} + pu_k x_k, every g_k kept.
+            // The carried state here is a_{k+1}^T g_{k+1} (this scan folds a_k^T in when it LEAVES point k).
+            double gk[J];
+#pragma unroll
+            for (int i = 0; i < J; ++i) gk[i] = g[i] + m.h[i] * xk;
+            strow<J>(out, k, gk);
+#pragma unroll
+            for (int i = 0; i < J; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) v += a[j][i] * g[j];
+                ng[i] = v + p[i] * xk;
+            }
+            y = 0.0;
         } else {  // OP_SYMM_UPPER (ops.py:332-338): out += q . f ; f = a^T f + p x
             double s = 0.0;
 #pragma unroll
@@ -936,7 +965,7 @@ __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_
         for (int i = 0; i < J; ++i) g[i] = ng[i];
         ssum += y * y;
       }
-      if (!op_reverse(OP)) st4(out, lb, l1, o4);
+      if (!op_reverse(OP) && OP != OP_GEN_LOWER) st4(out, lb, l1, o4);
     }
     if (sq_part) sq_part[ch] = ssum;
 }
@@ -956,6 +985,46 @@ __global__ void searchsorted_kernel(const double* a, int64_t n, const double* v,
         if (a[mid] <= x) lo = mid + 1; else hi = mid;
     }
     out[i] = lo - 1;
+}
+// GeneralQSM.matmul epilogue (kernels/quasisep.py:118-145 + general.py:84-104), one thread per test point:
+//   idx = searchsorted(t2, x, right) - 1;
+//   lower = [h T(t2[idx], x)^T] . f[idx]           if 0 <= idx < n
+//   upper = [(h Pinf) T(x, t2[idx+1])] . g[idx+1]  if -1 <= idx < n-1
+template <int J>
+__global__ void general_gather_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t2, int64_t n,
+                                      const double* __restrict__ t1, int64_t mtest, const double* __restrict__ F,
+                                      const double* __restrict__ G, double* out, int64_t out_stride) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mtest) return;
+    const double x = t1[i];
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (t2[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    const int64_t idx = lo - 1;
+    double acc = 0.0;
+    double a[J][J], p[J], st[J];
+    if (idx >= 0) {
+        qs_gen<J>(m, x - t2[idx], a, p);   // a = T(t2[idx], x)^T, p = h a = pl
+        ldrow<J>(F, idx, st);
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc += p[j] * st[j];
+    }
+    if (idx < n - 1) {
+        qs_gen<J>(m, t2[idx + 1] - x, a, p);   // a = T(x, t2[idx+1])^T ; qu = q T = q a^T
+        ldrow<J>(G, idx + 1, st);
+        double up = 0.0;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            double qu = 0.0;
+#pragma unroll
+            for (int k = 0; k < J; ++k) qu += m.q[k] * a[j][k];
+            up += qu * st[j];
+        }
+        acc += up;
+    }
+    out[i * out_stride] = acc;
 }
 __global__ void sum_partials_kernel(const double* part, int64_t n, double* out) {
     __shared__ double sh[1024];
@@ -1116,6 +1185,8 @@ static void qs_affine(b200gp_qs* s, int op, const double* x, double* out, double
         case OP_LOWER_DOT: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_LOWER_DOT>(s, x, out, sumsq_dev))) break;
         case OP_SYMM_LOWER: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_SYMM_LOWER>(s, x, out, sumsq_dev))) break;
         case OP_SYMM_UPPER: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_SYMM_UPPER>(s, x, out, sumsq_dev))) break;
+        case OP_GEN_LOWER: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_GEN_LOWER>(s, x, out, sumsq_dev))) break;
+        case OP_GEN_UPPER: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_GEN_UPPER>(s, x, out, sumsq_dev))) break;
         default: throw GpError("quasisep: bad op");
     }
 }
@@ -1384,6 +1455,48 @@ int b200gp_qs_log_probability_dev(b200gp_ctx* ctx, const double* comps, int ncom
                                   const double* diag_dev, const double* resid_dev, int assume_sorted, int* unsorted,
                                   double* logp) {
     return b200gp_qs_log_probability(ctx, comps, ncomp, t_dev, n, diag_dev, resid_dev, assume_sorted, unsorted, logp);
+}
+
+// kernel.matmul(X1, X2, y) for a quasiseparable kernel in O((n + m) J^2): kernels/quasisep.py:147-163
+// (to_general_qsm(X1, X2) @ y).  t_train must be sorted; t_test need not be.
+int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t_test, int64_t m,
+                            const double* t_train, int64_t n, const double* Y, int64_t nrhs, double* out) {
+    API_BEGIN(ctx)
+    if (n <= 0 || m <= 0 || nrhs <= 0) throw GpError("qs_kernel_matmul: empty input");
+    b200gp_qs s;   // scan-only view: no factor, no noise diagonal
+    s.ctx = _ctx;
+    s.n = n;
+    s.model = build_model(comps, ncomp);
+    s.model.chunk = _ctx->qs_chunk;
+    s.J = s.model.J;
+    const size_t nb8 = (size_t)n * 8, mb8 = (size_t)m * 8, sb = (size_t)n * s.J * 8;
+    double* t2 = (double*)_ctx->alloc(nb8);
+    double* t1 = (double*)_ctx->alloc(mb8);
+    double* yh = (double*)_ctx->alloc(nb8 * nrhs);
+    double* x = (double*)_ctx->alloc(nb8);
+    double* F = (double*)_ctx->alloc(sb);
+    double* G = (double*)_ctx->alloc(sb);
+    double* o = (double*)_ctx->alloc(mb8 * nrhs);
+    CUDA_CHECK(cudaMemcpyAsync(t2, t_train, nb8, cudaMemcpyDefault, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(t1, t_test, mb8, cudaMemcpyDefault, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(yh, Y, nb8 * nrhs, cudaMemcpyDefault, _ctx->stream));
+    s.t = t2;
+    for (int64_t r = 0; r < nrhs; ++r) {
+        strided_gather_kernel<<<nblk(n, 256), 256, 0, _ctx->stream>>>(yh, nrhs, r, x, n);
+        _ctx->launches++;
+        qs_affine(&s, OP_GEN_LOWER, x, F, nullptr);
+        qs_affine(&s, OP_GEN_UPPER, x, G, nullptr);
+        QS_DISPATCH_J(s.J, (general_gather_kernel<JJ><<<nblk(m, 128), 128, 0, _ctx->stream>>>(s.model, t2, n, t1, m, F, G,
+                                                                                              o + r, nrhs)))
+        _ctx->launches++;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out, o, mb8 * nrhs, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    s.t = nullptr;
+    _ctx->release(t2, nb8); _ctx->release(t1, mb8); _ctx->release(yh, nb8 * nrhs); _ctx->release(x, nb8);
+    _ctx->release(F, sb); _ctx->release(G, sb); _ctx->release(o, mb8 * nrhs);
+    API_END
 }
 
 int b200gp_searchsorted_right_m1(b200gp_ctx* ctx, const double* sorted, int64_t n, const double* query, int64_t m,

@@ -17,6 +17,9 @@ import numpy as np
 
 from tinygp_b200.kernels.base import Kernel
 
+# dense kernel-program opcodes (include/b200gp.h)
+OP_CONST, OP_EXP, OP_MATERN32, OP_MATERN52, OP_COSINE, OP_EXPCOS, OP_EXPSIN, OP_ADD, OP_MUL = 0, 1, 3, 4, 5, 8, 9, 16, 17
+
 QS_EXP, QS_MATERN32, QS_MATERN52, QS_SHO, QS_CELERITE, QS_COSINE = range(6)
 STATE_DIM = {QS_EXP: 1, QS_MATERN32: 2, QS_MATERN52: 3, QS_SHO: 2, QS_CELERITE: 2, QS_COSINE: 2}
 
@@ -42,29 +45,46 @@ class Quasisep(Kernel):
     def coord_to_sortable(self, X):
         return X
 
-    # dense evaluation of a quasiseparable kernel goes through its closed form k(tau)
-    def _ktau(self, tau):
-        raise NotImplementedError
+    # Dense evaluation (quasisep.py:118-145 ``evaluate``; used by ``condition`` at test points,
+    # solver.py:131-139): the closed form k(tau), tau = |t1 - t2|, lowered to the same device kernel program as
+    # the stationary kernels and evaluated by the CUDA build kernel (Kernel.__call__).
+    def tau_program(self, dist: int) -> list[tuple]:
+        raise NotImplementedError(
+            f"{type(self).__name__} has no dense closed form on the B200 backend")
+
+    def lower(self, lc):
+        return self.tau_program(lc.metric_code())   # distance code 0 = L1 = |t1 - t2| in one dimension
 
     def __call__(self, X1, X2=None):
         X1 = np.asarray(X1, dtype=np.float64)
-        if X2 is None:
-            return self._ktau(np.zeros_like(X1))
-        X2 = np.asarray(X2, dtype=np.float64)
-        if X1.ndim != 1 or X2.ndim != 1:
+        if X1.ndim != 1 or (X2 is not None and np.ndim(X2) != 1):
             raise ValueError("quasiseparable kernels take 1-D sortable coordinates")
-        return self._ktau(np.abs(X1[:, None] - X2[None, :]))
+        return super().__call__(X1, X2)
 
     def matmul(self, X1, X2=None, y=None):
+        """quasisep.py:147-163: ``to_general_qsm(X1, X2) @ y`` in O((n + m) J^2) on the device (two state scans
+        over the sorted X2, a searchsorted and two transition matrices per row of X1).  With X2 omitted the
+        general form is used with X1 for both (reference: ``to_symm_qsm(X1) @ y``, the same matrix)."""
+        from tinygp_b200 import _cabi
         if y is None:
             y, X2 = X2, None
         if X2 is None:
             X2 = X1
-        return self(X1, X2) @ np.asarray(y, dtype=np.float64)
-
-    def lower(self, lc=None):
-        raise NotImplementedError(
-            "quasiseparable kernels are handled by QuasisepSolver; they do not lower to a dense kernel program")
+        t1 = _cabi.f64(np.asarray(self.coord_to_sortable(X1), dtype=np.float64))
+        t2 = _cabi.f64(np.asarray(self.coord_to_sortable(X2), dtype=np.float64))
+        y = np.asarray(y, dtype=np.float64)
+        if t1.ndim != 1 or t2.ndim != 1:
+            raise ValueError("quasiseparable kernels take 1-D sortable coordinates")
+        if y.shape[0] != t2.shape[0]:
+            raise ValueError("dimension mismatch")
+        comps = self.component_array()
+        yy = np.ascontiguousarray(y.reshape(t2.shape[0], -1))
+        out = np.empty((t1.shape[0], yy.shape[1]))
+        ctx = _cabi.get_context()
+        ctx.check(ctx.lib.b200gp_qs_kernel_matmul(ctx.handle, _cabi.ptr(comps), comps.shape[0], _cabi.ptr(t1),
+                                                  t1.shape[0], _cabi.ptr(t2), t2.shape[0], _cabi.ptr(yy),
+                                                  yy.shape[1], _cabi.ptr(out)))
+        return out.reshape((t1.shape[0],) + y.shape[1:])
 
     # algebra (quasisep.py:165-199)
     def __add__(self, other):
@@ -103,8 +123,8 @@ class Sum(Quasisep):
     def components(self):
         return self.kernel1.components() + self.kernel2.components()
 
-    def _ktau(self, tau):
-        return self.kernel1._ktau(tau) + self.kernel2._ktau(tau)
+    def tau_program(self, dist):
+        return self.kernel1.tau_program(dist) + self.kernel2.tau_program(dist) + [(OP_ADD, 0, 0.0, 0.0)]
 
 
 class Scale(Quasisep):
@@ -117,8 +137,8 @@ class Scale(Quasisep):
         s = float(self.scale)
         return [(c[0], c[1] * s) + tuple(c[2:]) for c in self.kernel.components()]
 
-    def _ktau(self, tau):
-        return float(self.scale) * self.kernel._ktau(tau)
+    def tau_program(self, dist):
+        return self.kernel.tau_program(dist) + [(OP_CONST, 0, float(self.scale), 0.0), (OP_MUL, 0, 0.0, 0.0)]
 
 
 class Product(Quasisep):
@@ -127,8 +147,8 @@ class Product(Quasisep):
     def __init__(self, kernel1, kernel2):
         self.kernel1, self.kernel2 = kernel1, kernel2
 
-    def _ktau(self, tau):
-        return self.kernel1._ktau(tau) * self.kernel2._ktau(tau)
+    def tau_program(self, dist):
+        return self.kernel1.tau_program(dist) + self.kernel2.tau_program(dist) + [(OP_MUL, 0, 0.0, 0.0)]
 
 
 class Celerite(Quasisep):
@@ -140,8 +160,10 @@ class Celerite(Quasisep):
     def components(self):
         return [(QS_CELERITE, 1.0, float(self.a), float(self.b), float(self.c), float(self.d))]
 
-    def _ktau(self, tau):
-        return np.exp(-self.c * tau) * (self.a * np.cos(self.d * tau) + self.b * np.sin(self.d * tau))
+    def tau_program(self, dist):
+        a, b, c, d = float(self.a), float(self.b), float(self.c), float(self.d)
+        return [(OP_EXPCOS, dist, c, d), (OP_CONST, 0, a, 0.0), (OP_MUL, 0, 0.0, 0.0),
+                (OP_EXPSIN, dist, c, d), (OP_CONST, 0, b, 0.0), (OP_MUL, 0, 0.0, 0.0), (OP_ADD, 0, 0.0, 0.0)]
 
 
 class SHO(Quasisep):
@@ -153,18 +175,22 @@ class SHO(Quasisep):
     def components(self):
         return [(QS_SHO, 1.0, float(self.omega), float(self.quality), float(self.sigma), 0.0)]
 
-    def _ktau(self, tau):
+    def tau_program(self, dist):
+        """sigma^2 exp(-w tau / 2Q) [cos + sin / g] (Q > 1/2), [cosh + sinh / f] (Q < 1/2, written as two
+        exponentials), (1 + w tau) exp(-w tau) (Q = 1/2): the regimes of quasisep.py:449-488."""
         w, q, s2 = float(self.omega), float(self.quality), float(self.sigma) ** 2
-        e = np.exp(-0.5 * w * tau / q)
+        beta = 0.5 * w / q
+        scale = [(OP_CONST, 0, s2, 0.0), (OP_MUL, 0, 0.0, 0.0)]
         if np.allclose(q, 0.5):
-            return s2 * np.exp(-w * tau) * (1 + w * tau)
+            return [(OP_MATERN32, dist, np.sqrt(3.0) / w, 0.0)] + scale
         if q > 0.5:
             g = np.sqrt(4 * q * q - 1)
-            arg = 0.5 * g * w * tau / q
-            return s2 * e * (np.cos(arg) + np.sin(arg) / g)
+            return [(OP_EXPCOS, dist, beta, g * beta), (OP_EXPSIN, dist, beta, g * beta),
+                    (OP_CONST, 0, 1.0 / g, 0.0), (OP_MUL, 0, 0.0, 0.0), (OP_ADD, 0, 0.0, 0.0)] + scale
         f = np.sqrt(1 - 4 * q * q)
-        arg = 0.5 * f * w * tau / q
-        return s2 * e * (np.cosh(arg) + np.sinh(arg) / f)
+        return [(OP_EXPCOS, dist, beta * (1 - f), 0.0), (OP_CONST, 0, 0.5 * (1 + 1 / f), 0.0), (OP_MUL, 0, 0.0, 0.0),
+                (OP_EXPCOS, dist, beta * (1 + f), 0.0), (OP_CONST, 0, 0.5 * (1 - 1 / f), 0.0), (OP_MUL, 0, 0.0, 0.0),
+                (OP_ADD, 0, 0.0, 0.0)] + scale
 
 
 class Exp(Quasisep):
@@ -176,8 +202,8 @@ class Exp(Quasisep):
     def components(self):
         return [(QS_EXP, 1.0, float(self.scale), float(self.sigma), 0.0, 0.0)]
 
-    def _ktau(self, tau):
-        return float(self.sigma) ** 2 * np.exp(-tau / self.scale)
+    def tau_program(self, dist):
+        return [(OP_EXP, dist, float(self.scale), 0.0), (OP_CONST, 0, float(self.sigma) ** 2, 0.0), (OP_MUL, 0, 0.0, 0.0)]
 
 
 class Matern32(Quasisep):
@@ -189,9 +215,9 @@ class Matern32(Quasisep):
     def components(self):
         return [(QS_MATERN32, 1.0, float(self.scale), float(self.sigma), 0.0, 0.0)]
 
-    def _ktau(self, tau):
-        f = np.sqrt(3) / self.scale
-        return float(self.sigma) ** 2 * (1 + f * tau) * np.exp(-f * tau)
+    def tau_program(self, dist):
+        return [(OP_MATERN32, dist, float(self.scale), 0.0), (OP_CONST, 0, float(self.sigma) ** 2, 0.0),
+                (OP_MUL, 0, 0.0, 0.0)]
 
 
 class Matern52(Quasisep):
@@ -203,9 +229,9 @@ class Matern52(Quasisep):
     def components(self):
         return [(QS_MATERN52, 1.0, float(self.scale), float(self.sigma), 0.0, 0.0)]
 
-    def _ktau(self, tau):
-        f = np.sqrt(5) / self.scale
-        return float(self.sigma) ** 2 * (1 + f * tau + np.square(f * tau) / 3) * np.exp(-f * tau)
+    def tau_program(self, dist):
+        return [(OP_MATERN52, dist, float(self.scale), 0.0), (OP_CONST, 0, float(self.sigma) ** 2, 0.0),
+                (OP_MUL, 0, 0.0, 0.0)]
 
 
 class Cosine(Quasisep):
@@ -217,8 +243,9 @@ class Cosine(Quasisep):
     def components(self):
         return [(QS_COSINE, 1.0, float(self.scale), float(self.sigma), 0.0, 0.0)]
 
-    def _ktau(self, tau):
-        return float(self.sigma) ** 2 * np.cos(2 * np.pi * tau / self.scale)
+    def tau_program(self, dist):
+        return [(OP_COSINE, dist, float(self.scale), 0.0), (OP_CONST, 0, float(self.sigma) ** 2, 0.0),
+                (OP_MUL, 0, 0.0, 0.0)]
 
 
 class CARMA(Quasisep):

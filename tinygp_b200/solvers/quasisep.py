@@ -108,8 +108,10 @@ class QuasisepSolver(Solver):
         return d, p, q, a
 
     def condition(self, kernel, X_test, noise) -> Any:
-        """solver.py:104-139, dense branch (:131-139).  The QSM-valued branch (:124-129) needs qsm_mul /
-        inv / gram and is a 'next' row; predicting at the inputs returns the dense matrix instead."""
+        """solver.py:104-139, dense branch (:131-139): the kernel matrices are built by the CUDA build kernel from
+        the kernel's closed form (kernels/quasisep.py tau_program) and solved against by the device scans.  The
+        QSM-valued branch (:124-129, X_test=None) needs qsm_mul / inv / gram and is a 'next' row; predicting at the
+        inputs returns the same values as a dense matrix instead."""
         if X_test is None:
             Kss = Ks = kernel(self.X, self.X)
         else:

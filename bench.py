@@ -52,6 +52,19 @@ def make_dense_problem(n, rank=0):
     return X, y, diag, scale
 
 
+def golden_check(which, n, logp):
+    """full-size LAPACK known answer (tests/golden/full_size.json, made by tests/golden/make_golden_full.py)"""
+    try:
+        g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden",
+                                        "full_size.json")))[which]
+    except Exception:
+        return None
+    if g["n"] != n:
+        return None
+    return {"log_probability": g["log_probability"], "rel_err": abs(logp - g["log_probability"]) / abs(g["log_probability"]),
+            "source": g["lapack"]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -326,7 +339,7 @@ def run_ours(args, rank, local_rank, world):
                                        else "native fp64 DMMA"),
                    "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                    "l2": "working set 34 GB >> 126 MB L2 (no flush needed)"},
-        "logp": logp, "logp_e2e": logp_e2e,
+        "logp": logp, "logp_e2e": logp_e2e, "golden": golden_check("c2", n, logp),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "logp/s", "steps": e2e_steps,
                 "h2d_bytes_per_step": int(n * NDIM * 8 + n * 8 + n * 8),
@@ -546,7 +559,7 @@ def run_sharded(args, rank, local_rank, world):
             "config": {"workload": f"dense Matern52+RationalQuadratic (L2) 3-D N={n}: ONE log_probability sharded over "
                                    f"{world} GPU(s), int8 fixed-point update ({slices} digit planes), all-gather per block column",
                        "diag": 0.1, "seed": 49383, "nb": args.nb},
-            "logp": lp, "tflops_n3_over_3": n ** 3 / 3.0 * args.steps / t / 1e12,
+            "logp": lp, "golden": golden_check("c3s", n, lp), "tflops_n3_over_3": n ** 3 / 3.0 * args.steps / t / 1e12,
             "kernel_ms_per_step_rank0": {"i8_update": prof["syrk_ms"] / args.steps, "panel": prof["panel_ms"] / args.steps,
                                          "build_cut": prof["build_ms"] / args.steps, "solve": prof["solve_ms"] / args.steps},
             "allgather_bytes_per_step": int(8 * n * (n + args.nb) / 2),

@@ -20,10 +20,19 @@ def _ref_update(C, planes, rs, S):
     return out
 
 
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("pairing", [0, 1, 2])
 @pytest.mark.parametrize("cluster", [1, 2, 11, 21, 12, 22, 41, 42])
-@pytest.mark.parametrize("rows,K,S", [(256, 128, 1), (256, 512, 3), (512, 1024, 8), (768, 384, 7)])
-def test_i8_update_kernel_is_exact(ctx, rows, K, S, cluster):
+@pytest.mark.parametrize("rows,K,S", [(256, 128, 1), (256, 512, 3), (512, 1024, 8), (768, 384, 7), (512, 2048, 2)])
+def test_i8_update_kernel_is_exact(ctx, rows, K, S, cluster, pairing, layout):
+    """pairing: 0 = one digit group per pass (default), 1 = two groups per pass sharing their operand stages,
+    2 = the paired loop structure with single groups (diagnostic).  layout: 0 = plane-major digit planes,
+    1 = chunk-major (all planes of a 128-byte K chunk adjacent; one 4-D tensor map)."""
+    if (pairing or layout) and cluster in (1, 2):
+        pytest.skip("the wide and 2-SM variants have neither switch")
     ctx.set_option("ozaki_cluster", cluster)
+    ctx.set_option("ozaki_pairing", pairing)
+    ctx.set_option("ozaki_layout", layout)
     rng = np.random.default_rng(rows + K + S)
     planes = rng.integers(-64, 65, size=(S, rows, K), dtype=np.int8)
     rs = 2.0 ** rng.integers(-2, 3, size=rows).astype(np.float64)
@@ -32,6 +41,8 @@ def test_i8_update_kernel_is_exact(ctx, rows, K, S, cluster):
     pl = np.ascontiguousarray(planes)
     ctx.check(ctx.lib.b200gp_i8_update_test(ctx.handle, _cabi.ptr(pl), S, rows, K, _cabi.ptr(rs), _cabi.ptr(got)))
     ctx.set_option("ozaki_cluster", 21)
+    ctx.set_option("ozaki_pairing", 0)
+    ctx.set_option("ozaki_layout", 0)
     want = _ref_update(C, planes, rs, S)
     # integer dot products are exact; the only rounding is one fp64 fma per group
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
@@ -64,6 +75,29 @@ def test_ozaki_factor_parity(ctx, n, nb, slices, lookahead):
     tol = {8: 1e-10, 7: 1e-10, 6: 1e-9}[slices]
     np.testing.assert_allclose(s.scale_tril, so.scale_tril, rtol=tol, atol=tol)
     assert rel(s.normalization(), so.normalization()) < (1e-9 if slices == 6 else 1e-10)
+    assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+
+
+@pytest.mark.parametrize("layout,pairing", [(1, 0), (1, 1), (0, 1), (0, 2)])
+def test_ozaki_layout_and_pairing_variants(ctx, layout, pairing):
+    """the whole factorisation with the optional digit-plane layout / group pairing switched on"""
+    n = 3000
+    rng = np.random.default_rng(7)
+    X = rng.uniform(0, 20.0 * (n / 65536.0) ** (1 / 3), (n, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    k = 1.3 * kernels.ExpSquared(0.8)
+    ctx.set_option("nb", 512)
+    ctx.set_option("ozaki_min_n", 0)
+    ctx.set_option("ozaki_layout", layout)
+    ctx.set_option("ozaki_pairing", pairing)
+    try:
+        lp = GaussianProcess(k, X, diag=0.1).log_probability(y)
+    finally:
+        ctx.set_option("ozaki_layout", 0)
+        ctx.set_option("ozaki_pairing", 0)
+        ctx.set_option("ozaki_min_n", 8192)
+        ctx.set_option("nb", 1024)
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
     assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
 
 

@@ -68,6 +68,8 @@ struct b200gp_ctx {
     int64_t oz_lookahead = 0;   // overlap the fp64 panel factorisation with the int8 update on a second stream
     cudaStream_t stream2 = nullptr;
     int64_t oz_prefetch = 0;    // L2 prefetch distance (K-chunks of 128) of the int8 update's TMA producer
+    int64_t oz_pairing = 0;    // int8 update: 1 = accumulate two digit groups at once (1.8x fewer operand loads), 2 = diagnostic
+    int64_t oz_layout = 0;     // digit planes: 0 plane-major, 1 chunk-major (all planes of a K chunk adjacent)
     int64_t oz_cluster = 21;    // cluster shape of the int8 update kernel (CM*10 + CN), see ozaki.cu
     int64_t oz_min_n = 8192;    // below this size the native DMMA path is used
     // deferred (non-blocking) kernel timers: event pairs resolved at the next flush_timers()

@@ -186,6 +186,11 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
         _ctx->oz_slices = value;
     } else if (!strcmp(key, "ozaki_prefetch")) {
         _ctx->oz_prefetch = value;
+    } else if (!strcmp(key, "ozaki_layout")) {
+        if (value != 0 && value != 1) throw GpError("option ozaki_layout must be 0 or 1");
+        _ctx->oz_layout = value;
+    } else if (!strcmp(key, "ozaki_pairing")) {
+        _ctx->oz_pairing = (value == 2) ? 2 : (value ? 1 : 0);
     } else if (!strcmp(key, "ozaki_lookahead")) {
         _ctx->oz_lookahead = value;
     } else if (!strcmp(key, "ozaki_cluster")) {

@@ -53,10 +53,15 @@ struct Args {
     int64_t n_rows;                    // rows of the matrix (for masking the last column tile)
     int prefetch;                      // L2 prefetch distance in K-chunks (0 = off)
     int skip_upper;                    // skip tiles entirely above the diagonal
+    int layout;                        // digit-plane layout: 0 plane-major [s][row][k], 1 chunk-major [k/128][row][s][128]
+    int pg_single;                     // diagnostic: paired-group loop structure (kc outer) with ONE group per pass
     int* error_flag;
 };
 
-struct Maps { CUtensorMap plane[8]; };
+// `all`: ONE 3-D map (k, row, plane) used by the main kernel -- cycling through per-plane descriptors makes every
+// TMA issue miss the descriptor cache (measured: 3x the per-stage cost once stages alternate planes);
+// `plane[s]`: 2-D per-plane maps kept for the wide / 2-SM variants.
+struct Maps { CUtensorMap all; CUtensorMap plane[8]; };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,6 +100,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
             smem_u32(smem_dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 // fire-and-forget L2 prefetch of a TMA box: the demand loads of the shared-memory ring then see L2-hit latency
 // instead of loaded DRAM latency (the ring holds only 192 KB; ncu showed the kernel latency-bound)
@@ -151,6 +167,29 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
                      smem_u32(bar)),
@@ -164,7 +203,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 constexpr int BOXR = 64;  // rows per TMA box
 
-template <int CM, int CN>
+// PG ("paired groups"): two digit groups g0 = 2P, g1 = 2P + 1 are accumulated at once in the two TMEM accumulators.
+// Per K chunk the ring then carries stages i = 0..g1 holding (A plane i, B plane g1 - i); stage i feeds
+//   A_i x B_{g1-i} -> accumulator 1 (group g1)   and   A_{i-1} (previous stage) x B_{g1-i} -> accumulator 0 (group g0),
+// so S = 8 needs 20 stage loads per K chunk instead of 36: the L2 -> shared-memory operand stream, which bounds the
+// unpaired kernel at ~50 % tensor-pipe utilisation (profiles/r1_ncu_i8_update.md), shrinks 1.8x for the same MMAs.
+template <int CM, int CN, bool PG>
 __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_constant__ Maps maps, const Args g) {
     static_assert((TM / CN) % BOXR == 0 && (TN / CM) % BOXR == 0, "slice must be whole TMA boxes");
     extern __shared__ uint8_t smem_raw[];
@@ -231,46 +275,61 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            // one ring stage: (A plane s, B plane t) of K chunk kc
+            // one 128-byte x 64-row box of digit plane `pl` at K chunk kc into this CTA's (and its mates') current stage
+            const int kchunk0 = g.k_begin / KC;
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            for (int gi = 0; gi < NG && ok; ++gi) {
-                const int s_lo = (gi - (S - 1) > 0) ? gi - (S - 1) : 0, s_hi = (gi < S - 1) ? gi : S - 1;
-                for (int s = s_lo; s <= s_hi && ok; ++s) {
-                    const int t = gi - s;
-                    for (int kc = 0; kc < KT; ++kc) {
-                        if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; break; }
+            auto load_box = [&](uint8_t* dst, int kc, int row, int pl, bool mc, uint16_t mask) {
+                if (g.layout == 1) {
+                    if (mc) tma_load_4d_mc(dst, &maps.all, full + stage, 0, pl, row, kchunk0 + kc, mask);
+                    else tma_load_4d(dst, &maps.all, full + stage, 0, pl, row, kchunk0 + kc);
+                } else {
+                    if (mc) tma_load_3d_mc(dst, &maps.all, full + stage, g.k_begin + kc * KC, row, pl, mask);
+                    else tma_load_3d(dst, &maps.all, full + stage, g.k_begin + kc * KC, row, pl);
+                }
+            };
+            auto issue_stage = [&](int s, int t, int kc) {
+                        if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; return; }
                         uint8_t* a_dst = smem + stage * STAGE_BYTES;
                         uint8_t* b_dst = a_dst + A_BYTES;
                         mbar_expect_tx(full + stage, STAGE_BYTES);   // own + mates' slices land on this barrier
                         constexpr int A_ROWS = TM / CN, B_ROWS = TN / CM;
-                        if (g.prefetch > 0 && kc + g.prefetch < KT) {   // own slices, `prefetch` K-chunks ahead, into L2
+                        if (g.prefetch > 0 && g.layout == 0 && kc + g.prefetch < KT) {   // own slices, `prefetch` K-chunks ahead, into L2
                             const int kp = g.k_begin + (kc + g.prefetch) * KC;
 #pragma unroll
                             for (int bx = 0; bx < A_ROWS / BOXR; ++bx)
-                                tma_prefetch_2d(&maps.plane[s], kp, (int)grow0 + cn * A_ROWS + bx * BOXR);
+                                tma_prefetch_3d(&maps.all, kp, (int)grow0 + cn * A_ROWS + bx * BOXR, s);
 #pragma unroll
                             for (int bx = 0; bx < B_ROWS / BOXR; ++bx)
-                                tma_prefetch_2d(&maps.plane[t], kp, (int)brow0 + cm * B_ROWS + bx * BOXR);
+                                tma_prefetch_3d(&maps.all, kp, (int)brow0 + cm * B_ROWS + bx * BOXR, t);
                         }
 #pragma unroll
                         for (int bx = 0; bx < A_ROWS / BOXR; ++bx) {
                             const int r = cn * A_ROWS + bx * BOXR;
-                            if (CN > 1)
-                                tma_load_2d_mc(a_dst + r * KC, &maps.plane[s], full + stage, g.k_begin + kc * KC, (int)grow0 + r, mask_a);
-                            else
-                                tma_load_2d(a_dst + r * KC, &maps.plane[s], full + stage, g.k_begin + kc * KC, (int)grow0 + r);
+                            load_box(a_dst + r * KC, kc, (int)grow0 + r, s, CN > 1, mask_a);
                         }
 #pragma unroll
                         for (int bx = 0; bx < B_ROWS / BOXR; ++bx) {
                             const int r = cm * B_ROWS + bx * BOXR;
-                            if (CM > 1)
-                                tma_load_2d_mc(b_dst + r * KC, &maps.plane[t], full + stage, g.k_begin + kc * KC, (int)brow0 + r, mask_b);
-                            else
-                                tma_load_2d(b_dst + r * KC, &maps.plane[t], full + stage, g.k_begin + kc * KC, (int)brow0 + r);
+                            load_box(b_dst + r * KC, kc, (int)brow0 + r, t, CM > 1, mask_b);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    }
+            };
+            if constexpr (PG) {
+                const int npass = g.pg_single ? S : (S + 1) / 2;
+                for (int P = 0; P < npass && ok; ++P) {
+                    const int g0 = g.pg_single ? P : 2 * P;
+                    const int top = (!g.pg_single && g0 + 1 < S) ? g0 + 1 : g0;
+                    for (int kc = 0; kc < KT && ok; ++kc)
+                        for (int i = 0; i <= top && ok; ++i) issue_stage(i, top - i, kc);
+                }
+            } else {
+                for (int gi = 0; gi < NG && ok; ++gi) {
+                    const int s_lo = (gi - (S - 1) > 0) ? gi - (S - 1) : 0, s_hi = (gi < S - 1) ? gi : S - 1;
+                    for (int s = s_lo; s <= s_hi && ok; ++s)
+                        for (int kc = 0; kc < KT && ok; ++kc) issue_stage(s, gi - s, kc);
                 }
             }
         }
@@ -280,32 +339,85 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            for (int gi = 0; gi < NG && ok; ++gi) {
-                const int acc = gi & 1;
-                if (gi >= 2) {  // the epilogue must have drained this accumulator (group gi-2)
-                    if (!mbar_wait(tempty + acc, ((gi >> 1) - 1) & 1, abort_flag)) { ok = false; break; }
-                    tc_fence_after();
-                }
-                const uint32_t tacc = tmem_base + (uint32_t)acc * TN;
-                uint32_t accumulate = 0;
-                const int s_lo = (gi - (S - 1) > 0) ? gi - (S - 1) : 0, s_hi = (gi < S - 1) ? gi : S - 1;
-                for (int s = s_lo; s <= s_hi && ok; ++s) {
-                    for (int kc = 0; kc < KT; ++kc) {
-                        if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+            if constexpr (PG) {
+                const int npass = g.pg_single ? S : (S + 1) / 2;
+                for (int P = 0; P < npass && ok; ++P) {
+                    const int g0 = g.pg_single ? P : 2 * P;
+                    const bool two = !g.pg_single && (g0 + 1 < S);
+                    const int top = two ? g0 + 1 : g0;
+                    if (P >= 1) {  // the epilogue must have drained both accumulators (pair P-1)
+                        if (!mbar_wait(tempty, (uint32_t)((P - 1) & 1), abort_flag)) { ok = false; break; }
                         tc_fence_after();
-                        const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-                        for (int kk = 0; kk < KC / 32; ++kk) {
-                            umma_i8(tacc, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), accumulate);
-                            accumulate = 1;
-                        }
-                        // free the slot in every CTA whose producer writes into it (row- and column-mates)
-                        if (CS > 1) tc_commit_mc(empty + stage, mask_all); else tc_commit(empty + stage);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
+                    const uint32_t acc0 = tmem_base, acc1 = tmem_base + (uint32_t)TN;
+                    uint32_t accum0 = 0, accum1 = 0;
+                    for (int kc = 0; kc < KT && ok; ++kc) {
+                        uint32_t prev_a = 0;
+                        int prev_stage = 0;
+                        for (int i = 0; i <= top; ++i) {
+                            if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                            tc_fence_after();
+                            const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                            const uint32_t b_addr = a_addr + A_BYTES;
+                            if (two) {
+#pragma unroll
+                                for (int kk = 0; kk < KC / 32; ++kk) {   // A_i x B_{top-i}: group top
+                                    umma_i8(acc1, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), accum1);
+                                    accum1 = 1;
+                                }
+                                if (i >= 1) {
+#pragma unroll
+                                    for (int kk = 0; kk < KC / 32; ++kk) {   // A_{i-1} x B_{top-i}: group top - 1
+                                        umma_i8(acc0, make_desc(prev_a + kk * 32), make_desc(b_addr + kk * 32), accum0);
+                                        accum0 = 1;
+                                    }
+                                    // stage i-1 is now dead: its A was just used for the last time, its B one step ago
+                                    if (CS > 1) tc_commit_mc(empty + prev_stage, mask_all); else tc_commit(empty + prev_stage);
+                                }
+                                if (i == top) { if (CS > 1) tc_commit_mc(empty + stage, mask_all); else tc_commit(empty + stage); }
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < KC / 32; ++kk) {
+                                    umma_i8(acc0, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), accum0);
+                                    accum0 = 1;
+                                }
+                                if (CS > 1) tc_commit_mc(empty + stage, mask_all); else tc_commit(empty + stage);
+                            }
+                            prev_a = a_addr;
+                            prev_stage = stage;
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    if (ok) tc_commit(tfull);    // both accumulators of pair P complete
                 }
-                if (ok) tc_commit(tfull + acc);    // accumulator of group gi complete
+            } else {
+                for (int gi = 0; gi < NG && ok; ++gi) {
+                    const int acc = gi & 1;
+                    if (gi >= 2) {  // the epilogue must have drained this accumulator (group gi-2)
+                        if (!mbar_wait(tempty + acc, ((gi >> 1) - 1) & 1, abort_flag)) { ok = false; break; }
+                        tc_fence_after();
+                    }
+                    const uint32_t tacc = tmem_base + (uint32_t)acc * TN;
+                    uint32_t accumulate = 0;
+                    const int s_lo = (gi - (S - 1) > 0) ? gi - (S - 1) : 0, s_hi = (gi < S - 1) ? gi : S - 1;
+                    for (int s = s_lo; s <= s_hi && ok; ++s) {
+                        for (int kc = 0; kc < KT; ++kc) {
+                            if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                            tc_fence_after();
+                            const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                            const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                            for (int kk = 0; kk < KC / 32; ++kk) {
+                                umma_i8(tacc, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), accumulate);
+                                accumulate = 1;
+                            }
+                            // free the slot in every CTA whose producer writes into it (row- and column-mates)
+                            if (CS > 1) tc_commit_mc(empty + stage, mask_all); else tc_commit(empty + stage);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    if (ok) tc_commit(tfull + acc);    // accumulator of group gi complete
+                }
             }
         }
     } else {
@@ -317,32 +429,71 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
         const double rsi = row_ok ? g.rs[gr] : 0.0;
         double* crow = g.C + (row_ok ? gr : 0) * g.ldc;
         bool ok = true;
-        for (int gi = 0; gi < NG && ok; ++gi) {
-            const int acc = gi & 1;
-            if (!mbar_wait(tfull + acc, (gi >> 1) & 1, abort_flag)) { ok = false; break; }
-            tc_fence_after();
-            // weight 2^-(12 + 7 gi), exact power of two
-            const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
-            const double sc = -(rsi * wg);
+        if constexpr (PG) {
+            const int npass = g.pg_single ? S : (S + 1) / 2;
+            for (int P = 0; P < npass && ok; ++P) {
+                const int g0 = g.pg_single ? P : 2 * P;
+                const bool two = !g.pg_single && (g0 + 1 < S);
+                if (!mbar_wait(tfull, (uint32_t)(P & 1), abort_flag)) { ok = false; break; }
+                tc_fence_after();
+                // group g0 weighs 2^-(12 + 7 g0); group g0 + 1 is 2^-7 of that.  a0 + a1 2^-7 is exact in fp64
+                // (|a| < 2^31), so the pair costs ONE rounding and one read-modify-write of the fp64 tile.
+                const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * g0)) << 52);
+                const double sc = -(rsi * wg);
 #pragma unroll 1
-            for (int cb = 0; cb < TN / 32; ++cb) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb * 32), r);
-                const int64_t gc = gcol0 + cb * 32;
-                if (row_ok && gc < g.n_rows) {  // column tiles may stick out past the matrix on the last panel
+                for (int cb = 0; cb < TN / 32; ++cb) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), r0);
+                    if (two) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TN + cb * 32), r1);
+                    const int64_t gc = gcol0 + cb * 32;
+                    if (row_ok && gc < g.n_rows) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
-                        double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
-                        cv.x = fma(sc * rj.x, (double)(int)r[j], cv.x);
-                        cv.y = fma(sc * rj.y, (double)(int)r[j + 1], cv.y);
-                        *reinterpret_cast<double2*>(crow + gc + j) = cv;
+                        for (int j = 0; j < 32; j += 2) {
+                            const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
+                            double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
+                            double tx = (double)(int)r0[j], ty = (double)(int)r0[j + 1];
+                            if (two) {
+                                tx = fma((double)(int)r1[j], 0.0078125, tx);
+                                ty = fma((double)(int)r1[j + 1], 0.0078125, ty);
+                            }
+                            cv.x = fma(sc * rj.x, tx, cv.x);
+                            cv.y = fma(sc * rj.y, ty, cv.y);
+                            *reinterpret_cast<double2*>(crow + gc + j) = cv;
+                        }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + acc);
+        } else {
+            for (int gi = 0; gi < NG && ok; ++gi) {
+                const int acc = gi & 1;
+                if (!mbar_wait(tfull + acc, (gi >> 1) & 1, abort_flag)) { ok = false; break; }
+                tc_fence_after();
+                // weight 2^-(12 + 7 gi), exact power of two
+                const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
+                const double sc = -(rsi * wg);
+    #pragma unroll 1
+                for (int cb = 0; cb < TN / 32; ++cb) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb * 32), r);
+                    const int64_t gc = gcol0 + cb * 32;
+                    if (row_ok && gc < g.n_rows) {  // column tiles may stick out past the matrix on the last panel
+    #pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
+                            double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
+                            cv.x = fma(sc * rj.x, (double)(int)r[j], cv.x);
+                            cv.y = fma(sc * rj.y, (double)(int)r[j + 1], cv.y);
+                            *reinterpret_cast<double2*>(crow + gc + j) = cv;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + acc);
+            }
         }
     }
 
@@ -692,7 +843,8 @@ __global__ void __launch_bounds__(THREADS_W, 1) i8_update_kernel_wide(const __gr
 __global__ void __launch_bounds__(256) cut_digits_kernel(const double* __restrict__ mat, int64_t ld, const double* __restrict__ rs,
                                                          int64_t r0, int64_t nrows, int64_t c0, int64_t ncols,
                                                          int8_t* planes, int64_t plane_stride, int64_t ldq, int S,
-                                                         double* corr /* [ncols/512 slots][np] for this panel */, int64_t np) {
+                                                         double* corr /* [ncols/512 slots][np] for this panel */, int64_t np,
+                                                         int layout = 0) {
     const int64_t groups_per_row = ncols / 16;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = idx < nrows * groups_per_row;
@@ -727,8 +879,10 @@ __global__ void __launch_bounds__(256) cut_digits_kernel(const double* __restric
                 }
                 packed[v] = wv;
             }
-            *reinterpret_cast<uint4*>(planes + (int64_t)s * plane_stride + row * ldq + col) =
-                make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            // plane-major [s][row][k], or chunk-major [k / 128][row][s][128] (np rows per chunk slab)
+            const int64_t off = (layout == 1) ? (((col >> 7) * np + row) * S + s) * 128 + (col & 127)
+                                              : (int64_t)s * plane_stride + row * ldq + col;
+            *reinterpret_cast<uint4*>(planes + off) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
         // dropped pairs (s + t >= S), grouped by g = s + t so each group is one exact integer sum
         for (int gsum = S; gsum <= 2 * (S - 1); ++gsum) {
@@ -749,6 +903,17 @@ __global__ void __launch_bounds__(256) cut_digits_kernel(const double* __restric
         const double r2 = rs[row] * rs[row];
         corr[slot * np + row] = r2 * dropped;   // one writer per (slot, row)
     }
+}
+
+// test helper: plane-major [s][row][k] -> chunk-major [k / 128][row][s][128], 16 bytes per thread
+__global__ void relayout_chunk_major_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst, int64_t rows, int64_t K, int S) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per_plane = rows * (K / 16);
+    if (idx >= per_plane * S) return;
+    const int s = (int)(idx / per_plane);
+    const int64_t rem = idx % per_plane, row = rem / (K / 16), col = (rem % (K / 16)) * 16;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (int64_t)s * rows * K + row * K + col);
+    *reinterpret_cast<uint4*>(dst + (((col >> 7) * rows + row) * S + s) * 128 + (col & 127)) = v;
 }
 
 // C_ii -= sum over previous panels/slots of corr[.][i] for the rows of block column [c0, c0+kb)
@@ -796,9 +961,30 @@ static EncodeTiledFn get_encode() {
 }
 
 // planes: S contiguous int8 matrices [rows][ldq]; box = 128 bytes (k) x 128 rows, 128-byte swizzle
-Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, int S) {
+Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, int S, int layout = 0) {
     Maps m{};
     EncodeTiledFn enc = get_encode();
+    if (layout == 1) {   // chunk-major: [k / 128][row][plane][128]
+        cuuint64_t dims[4] = {(cuuint64_t)KC, (cuuint64_t)S, (cuuint64_t)rows, (cuuint64_t)(ldq / KC)};
+        cuuint64_t strides[3] = {(cuuint64_t)KC, (cuuint64_t)S * KC, (cuuint64_t)rows * S * KC};
+        cuuint32_t box[4] = {(cuuint32_t)KC, 1u, (cuuint32_t)BOXR, 1u};
+        cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+        CUresult r = enc(&m.all, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, planes, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) throw GpError("cuTensorMapEncodeTiled (4-D) failed");
+        return m;   // the per-plane 2-D maps do not exist in this layout
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)ldq, (cuuint64_t)rows, (cuuint64_t)S};
+        cuuint64_t strides[2] = {(cuuint64_t)ldq, (cuuint64_t)plane_stride};
+        cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BOXR, 1u};
+        cuuint32_t estr[3] = {1u, 1u, 1u};
+        CUresult r = enc(&m.all, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) throw GpError("cuTensorMapEncodeTiled (3-D) failed");
+    }
     for (int s = 0; s < 8; ++s) {
         const int sp = (s < S) ? s : 0;
         cuuint64_t dims[2] = {(cuuint64_t)ldq, (cuuint64_t)rows};
@@ -813,11 +999,11 @@ Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, 
     return m;
 }
 
-template <int CM, int CN>
+template <int CM, int CN, bool PG>
 static void launch_cfg(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     static bool attr = false;
     if (!attr) {
-        CUDA_CHECK(cudaFuncSetAttribute(i8_update_kernel<CM, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(i8_update_kernel<CM, CN, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
     const int ctm = (a.tiles_m + CM - 1) / CM, ctn = (a.tiles_n + CN - 1) / CN;
@@ -835,7 +1021,7 @@ static void launch_cfg(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, i8_update_kernel<CM, CN>, maps, a));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, i8_update_kernel<CM, CN, PG>, maps, a));
     ctx->launches++;
     // int8 ops issued (mirrors the kernel's cluster-uniform decisions)
     double pairs_tiles = 0.0;
@@ -909,15 +1095,20 @@ static void launch_wide(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
 // 2 = CTA pair with tcgen05 cta_group::2 (256 x 256 tile per pair);
 // 11 = 1x1 (no multicast), 21 = 2x1, 12 = 1x2, 22 = 2x2, 41 = 4x1, 42 = 4x2 (cta_group::1 + TMA multicast)
 void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
+    if (a.layout == 1 && (ctx->oz_cluster == 1 || ctx->oz_cluster == 2))
+        throw GpError("ozaki_layout=1 (chunk-major digit planes) is not implemented for the wide / 2-SM kernels");
     switch ((int)ctx->oz_cluster) {
         case 1: launch_wide(ctx, maps, a); break;
         case 2: launch_2sm(ctx, maps, a); break;
-        case 11: launch_cfg<1, 1>(ctx, maps, a); break;
-        case 21: launch_cfg<2, 1>(ctx, maps, a); break;
-        case 12: launch_cfg<1, 2>(ctx, maps, a); break;
-        case 41: launch_cfg<4, 1>(ctx, maps, a); break;
-        case 42: launch_cfg<4, 2>(ctx, maps, a); break;
-        default: launch_cfg<2, 2>(ctx, maps, a); break;
+#define OZ_CFG(CMv, CNv) \
+    do { if (ctx->oz_pairing) launch_cfg<CMv, CNv, true>(ctx, maps, a); else launch_cfg<CMv, CNv, false>(ctx, maps, a); } while (0)
+        case 11: OZ_CFG(1, 1); break;
+        case 21: OZ_CFG(2, 1); break;
+        case 12: OZ_CFG(1, 2); break;
+        case 41: OZ_CFG(4, 1); break;
+        case 42: OZ_CFG(4, 2); break;
+        default: OZ_CFG(2, 2); break;
+#undef OZ_CFG
     }
 }
 
@@ -1040,7 +1231,8 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
     oz::row_scale_kernel<<<(unsigned)((np + 255) / 256), 256, 0, ctx->stream>>>(dense_kernel_diag_value(s->prog), s->diag_dev,
                                                                                s->n, np, rs);
     ctx->launches++;
-    oz::Maps maps = oz::make_maps(planes, (int64_t)plane_stride, np, np, S);
+    const int layout = (int)ctx->oz_layout;
+    oz::Maps maps = oz::make_maps(planes, (int64_t)plane_stride, np, np, S, layout);
 
     // Two streams: `upd` (the context stream) runs build + int8 updates, `pan` (high priority) runs the fp64
     // panel factorisation and the digit cutting.  Update J is split into the part that only needs panels
@@ -1072,7 +1264,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
         a.tiles_m = (int)((np - c0) / oz::TM);
         a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
         a.K = (int)k_len; a.k_begin = (int)k_begin; a.S = S; a.n_rows = np; a.skip_upper = 1; a.error_flag = err;
-        a.prefetch = (int)ctx->oz_prefetch;
+        a.prefetch = (int)ctx->oz_prefetch; a.pg_single = (ctx->oz_pairing == 2); a.layout = layout;
         ProfTimer t(ctx, &ctx->prof.syrk_ms);
         oz::launch_update(ctx, maps, a);
         ctx->prof.syrk_flop += 2.0 * (double)(np - c0) * (double)kb * (double)k_len;  // fp64-equivalent flop
@@ -1115,7 +1307,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
             ProfTimer t(ctx, &ctx->prof.build_ms);
             oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, pan>>>(
                 s->mat, ld, rs, c0 + kb, nrows, c0, kb, planes, (int64_t)plane_stride, np, S,
-                corr + (size_t)J * slots_per_panel * np, np);
+                corr + (size_t)J * slots_per_panel * np, np, layout);
             ctx->launches++;
         }
         if (lookahead) CUDA_CHECK(cudaEventRecord(ev_cut[J], pan));
@@ -1153,18 +1345,28 @@ extern "C" int b200gp_i8_update_test(b200gp_ctx* ctx, const int8_t* planes_host,
     CUDA_CHECK(cudaMemcpyAsync(planes, planes_host, pstride * S, cudaMemcpyHostToDevice, _ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(rs, rs_host, (size_t)rows * 8, cudaMemcpyHostToDevice, _ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(C, C_host, (size_t)rows * rows * 8, cudaMemcpyHostToDevice, _ctx->stream));
-    oz::Maps maps = oz::make_maps(planes, (int64_t)pstride, rows, K, S);
+    const int layout = (int)_ctx->oz_layout;
+    int8_t* planes_cm = nullptr;
+    if (layout == 1) {
+        planes_cm = (int8_t*)_ctx->alloc(pstride * S);
+        const int64_t nthr = (int64_t)S * rows * (K / 16);
+        oz::relayout_chunk_major_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, _ctx->stream>>>(planes, planes_cm, rows, K, S);
+        _ctx->launches++;
+    }
+    oz::Maps maps = oz::make_maps(layout == 1 ? planes_cm : planes, (int64_t)pstride, rows, K, S, layout);
     oz::Args a{};
+    a.layout = layout;
     a.C = C; a.ldc = rows; a.rs = rs; a.row0 = 0; a.col0 = 0; a.b_row0 = 0;
     a.tiles_m = (int)(rows / oz::TM); a.tiles_n = (int)(rows / oz::TN);
     a.K = (int)K; a.k_begin = 0; a.S = S; a.n_rows = rows; a.skip_upper = 0; a.error_flag = err;
-    a.prefetch = (int)_ctx->oz_prefetch;
+    a.prefetch = (int)_ctx->oz_prefetch; a.pg_single = (_ctx->oz_pairing == 2);
     oz::launch_update(_ctx, maps, a);
     int herr = 0;
     CUDA_CHECK(cudaMemcpyAsync(C_host, C, (size_t)rows * rows * 8, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
     _ctx->release(planes, pstride * S);
+    if (planes_cm) _ctx->release(planes_cm, pstride * S);
     _ctx->release(rs, (size_t)rows * 8);
     _ctx->release(C, (size_t)rows * rows * 8);
     _ctx->release(err, sizeof(int));
@@ -1367,7 +1569,7 @@ int b200gp_mg_update_rows(b200gp_mg* m, int J, int64_t r0, int64_t r1) {
         a.tiles_m = (int)((r1 - r0) / oz::TM);
         a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
         a.K = (int)c0; a.k_begin = 0; a.S = m->S; a.n_rows = np; a.skip_upper = 1; a.error_flag = m->err;
-        a.prefetch = (int)_ctx->oz_prefetch;
+        a.prefetch = (int)_ctx->oz_prefetch; a.pg_single = (_ctx->oz_pairing == 2);
         ProfTimer t(_ctx, &_ctx->prof.syrk_ms);
         oz::launch_update(_ctx, m->maps, a);
         _ctx->prof.syrk_flop += 2.0 * (double)(r1 - r0) * (double)kb * (double)c0;

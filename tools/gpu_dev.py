@@ -23,6 +23,10 @@ slices_list = [int(s) for s in (sys.argv[4].split(",") if len(sys.argv) > 4 else
 clusters = [int(s) for s in (sys.argv[5].split(",") if len(sys.argv) > 5 else "22".split(","))]
 lookaheads = [int(s) for s in (sys.argv[6].split(",") if len(sys.argv) > 6 else "1".split(","))]
 
+if os.environ.get("LAYOUT"):
+    ctx.set_option("ozaki_layout", int(os.environ["LAYOUT"]))
+if os.environ.get("PAIRING"):
+    ctx.set_option("ozaki_pairing", int(os.environ["PAIRING"]))
 if os.environ.get("PREFETCH"):
     ctx.set_option("ozaki_prefetch", int(os.environ["PREFETCH"]))
 if os.environ.get("POTF2"):

@@ -918,7 +918,8 @@ class GaussianProcess:
         if X_test is None:
             X_test = self.X
         gp = GaussianProcess(kernel, X_test, noise=noise, mean_value=mean_value,
-                             covariance_value=covariance_value, solver=_PrecomputedDirect)
+                             covariance_value=covariance_value, solver=_PrecomputedDirect,
+                             noise_in_covariance=isinstance(self.solver, DirectSolver))
         return log_prob, gp
 
     def predict(self, y, X_test=None, *, kernel=None, include_mean=True, return_var=False, return_cov=False):
@@ -935,12 +936,18 @@ class GaussianProcess:
 
 
 class _PrecomputedDirect(DirectSolver):
-    """DirectSolver given covariance_value (gp.py:208-221 -> direct.py:50-52).  The variance of the
-    conditioned GP is kernels.Conditioned.evaluate_diag + noise == diag(covariance_value)."""
+    """DirectSolver given covariance_value (gp.py:208-221 -> direct.py:49-52).  The variance of the conditioned GP is
+    kernels.Conditioned.evaluate_diag + noise.diagonal() (direct.py:49 with base.py:149-153), and
+    Conditioned.evaluate_diag == diag(Kss - A^T A).  DirectSolver.condition adds the noise to Kss (direct.py:88-92),
+    QuasisepSolver.condition's dense branch does not (solvers/quasisep/solver.py:131-139) -- so for a quasiseparable
+    parent the conditioned GP's *variance* carries the noise while its *covariance* does not.  Pinned by
+    tests/golden/reference_vectors.json (pred_var vs pred_cov_row0)."""
 
-    def __init__(self, kernel, X, noise, *, covariance=None):
+    def __init__(self, kernel, X, noise, *, covariance=None, noise_in_covariance=True):
         self.X = np.asarray(X, dtype=np.float64)
         self.variance_value = np.diag(covariance).copy()
+        if not noise_in_covariance:
+            self.variance_value = self.variance_value + noise.diagonal()
         self.covariance_value = covariance
         try:
             self.scale_tril = sla.cholesky(covariance, lower=True, check_finite=False)

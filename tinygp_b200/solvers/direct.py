@@ -18,6 +18,8 @@ from tinygp_b200.solvers.solver import Solver
 class DirectSolver(Solver):
     """Dense build fused into a blocked Cholesky on the fp64 tensor pipe (direct.py:30-53)."""
 
+    condition_includes_noise = True   # direct.py:88-92: Kss = kernel(X*, X*) + noise
+
     def __init__(self, kernel: Kernel, X, noise, *, covariance: Any | None = None):
         self._ctx = _cabi.get_context()
         self._h = c_void_p()
@@ -43,8 +45,14 @@ class DirectSolver(Solver):
                 raise ValueError("covariance must be a square matrix")
             self._n = cov.shape[0]
             self._cov = cov
-            # kernel(X) + noise.diagonal() of the conditioned kernel == diag(covariance) (direct.py:49-52)
+            # direct.py:49: variance = kernel(X) + noise.diagonal() with kernel = kernels.Conditioned, whose diagonal is
+            # diag(Kss - A^T A).  DirectSolver.condition put the noise into Kss (direct.py:88-92) so that is diag(cov);
+            # QuasisepSolver.condition's dense branch leaves it out (solvers/quasisep/solver.py:131-139), and the
+            # reference's conditioned variance then still carries it (golden: reference_vectors.json pred_var).
             self.variance_value = np.diag(cov).copy()
+            parent = getattr(kernel, "solver", None)
+            if parent is not None and not getattr(parent, "condition_includes_noise", True):
+                self.variance_value = self.variance_value + _cabi.f64(noise.diagonal())
             self._ctx.check(lib.b200gp_dense_create_from_cov(self._ctx.handle, _cabi.ptr(cov), cov.shape[0],
                                                              byref(self._h), byref(info)))
         self.info = info.value

@@ -18,6 +18,8 @@ _UNSORTED_MSG = "Input coordinates must be sorted in order to use the QuasisepSo
 
 
 class QuasisepSolver(Solver):
+    condition_includes_noise = False  # solver.py:131-139: the dense branch returns Kss - A^T A without the noise
+
     def __init__(self, kernel, X, noise, *, covariance: Any | None = None, assume_sorted: bool = False,
                  parallel: bool = False):
         """``parallel`` is accepted for API compatibility (solver.py:33,60-64); the device scans are

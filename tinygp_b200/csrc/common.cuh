@@ -142,6 +142,9 @@ struct b200gp_dense {
 void dense_build_rect(b200gp_ctx* ctx, const KProg& prog, const double* X1, int64_t n1,
                       const double* X2, int64_t n2, int ndim, const double* diag_or_null,
                       double* out, int64_t ld, int64_t rows_pad, int64_t cols_pad);
+void dense_conditioned_covariance_to_host(b200gp_ctx* ctx, const KProg& P, const double* At, int64_t mp, int64_t kp,
+                                          const double* xt_dev, const double* dt_dev, int nd, int64_t m,
+                                          double* out_host);
 b200gp_dense* dense_factor_from_prog(b200gp_ctx* ctx, const KProg& prog, const double* X_dev,
                                      int64_t n, int ndim, const double* diag_dev, bool copy_inputs);
 void dense_factor_inplace(b200gp_dense* s, bool generate);

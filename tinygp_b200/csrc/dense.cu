@@ -1219,6 +1219,32 @@ b200gp_dense* dense_factor_from_prog(b200gp_ctx* ctx, const KProg& prog, const d
     return s;
 }
 
+// out_host (m x m) = k(X*, X*) + diag* - At At^T for At (mp x kp row-major, zero padded, rows = test points):
+// one NT GEMM on the tensor pipe with K = kp whose C tile is generated in the epilogue (beta_mode 2).  Shared by
+// DirectSolver.condition (direct.py:88-95) and QuasisepSolver.condition's dense branch (solvers/quasisep/solver.py:131-139).
+void dense_conditioned_covariance_to_host(b200gp_ctx* ctx, const KProg& P, const double* At, int64_t mp, int64_t kp,
+                                          const double* xt_dev, const double* dt_dev, int nd, int64_t m,
+                                          double* out_host) {
+    if (mp % TILE != 0 || kp % TILE != 0) throw GpError("conditioned covariance: operands must be padded to 128");
+    const int tm = (int)(mp / TILE);
+    double* C = (double*)ctx->alloc((size_t)mp * mp * 8);
+    {
+        gemm::Args g{};
+        g.A = At; g.lda = kp; g.B = At; g.ldb = kp; g.C = C; g.ldc = mp;
+        g.tiles_m = g.tiles_n = tm; g.K = (int)kp; g.alpha = -1.0; g.beta_mode = 2; g.lower = 0;
+        g.X = xt_dev; g.diag = dt_dev; g.ndim = nd; g.n_valid = m; g.row0 = 0; g.col0 = 0;
+        gemm::launch(ctx, P, g);
+    }
+    double* o = (double*)ctx->alloc((size_t)m * m * 8);
+    extract_rect_kernel<<<nblocks(m * m, 256), 256, 0, ctx->stream>>>(C, mp, o, m, m);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(out_host, o, (size_t)m * m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->release(o, (size_t)m * m * 8);
+    ctx->release(C, (size_t)mp * mp * 8);
+}
+
 // =============================================================================================
 // C-ABI: dense
 // =============================================================================================
@@ -1418,22 +1444,7 @@ int b200gp_dense_condition(b200gp_dense* s, const double* prog, int n_instr, con
                         tm, nblk - j - 1, TILE, -1.0, 1, 0);
         }
     }
-    double* C = (double*)_ctx->alloc((size_t)mp * mp * 8);
-    {
-        gemm::Args g{};
-        g.A = At; g.lda = np; g.B = At; g.ldb = np; g.C = C; g.ldc = mp;
-        g.tiles_m = g.tiles_n = tm; g.K = (int)np; g.alpha = -1.0; g.beta_mode = 2; g.lower = 0;
-        g.X = xt_dev; g.diag = dt; g.ndim = nd; g.n_valid = m; g.row0 = 0; g.col0 = 0;
-        gemm::launch(_ctx, P, g);
-    }
-    double* o = (double*)_ctx->alloc((size_t)m * m * 8);
-    extract_rect_kernel<<<nblocks(m * m, 256), 256, 0, _ctx->stream>>>(C, mp, o, m, m);
-    _ctx->launches++;
-    CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)m * m * 8, cudaMemcpyDeviceToHost, _ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(o, (size_t)m * m * 8);
-    _ctx->release(C, (size_t)mp * mp * 8);
+    dense_conditioned_covariance_to_host(_ctx, P, At, mp, np, xt_dev, dt, nd, m, out);
     _ctx->release(At, (size_t)mp * np * 8);
     _ctx->release(dt, (size_t)mp * 8);
     if (own_xt) _ctx->release(xt_dev, (size_t)m * nd * 8);

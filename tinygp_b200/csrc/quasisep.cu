@@ -1499,6 +1499,42 @@ int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, con
     API_END
 }
 
+// QuasisepSolver.condition, dense branch (solvers/quasisep/solver.py:131-139):  out = Kss - A^T A with
+// A = factor.solve(Ks), Ks = k(X, X*), Kss = k(X*, X*) -- the noise is NOT added here (the reference does not).
+// Everything runs on the device: Ks^T (rows = test points, each row a contiguous n-vector) from the build kernel,
+// one forward-substitution scan per row, then the NT GEMM with the k(X*, X*) generator epilogue shared with
+// DirectSolver.condition.  `prog` is the predictive kernel lowered for 1-D coordinates; t_test == NULL means X* = X.
+int b200gp_qs_condition(b200gp_qs* s, const double* prog, int n_instr, const double* t_test, int64_t m, double* out) {
+    API_BEGIN(s->ctx)
+    KProg P = parse_prog(prog, n_instr, 1);
+    const int64_t n = s->n;
+    double* xt_dev = s->t;
+    bool own_xt = false;
+    if (t_test == nullptr) {
+        m = n;
+    } else {
+        if (m <= 0) throw GpError("qs_condition: empty X_test");
+        xt_dev = (double*)_ctx->alloc((size_t)m * 8);
+        own_xt = true;
+        CUDA_CHECK(cudaMemcpyAsync(xt_dev, t_test, (size_t)m * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    }
+    const int64_t mp = ((m + TILE - 1) / TILE) * TILE, kp = ((n + TILE - 1) / TILE) * TILE;
+    const size_t ab = (size_t)mp * kp * 8;
+    double* Kst = (double*)_ctx->alloc(ab);
+    double* At = (double*)_ctx->alloc(ab);
+    double* dt = (double*)_ctx->alloc((size_t)mp * 8);
+    CUDA_CHECK(cudaMemsetAsync(dt, 0, (size_t)mp * 8, _ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(At, 0, ab, _ctx->stream));   // pad rows / columns of A^T must be zero for the GEMM
+    dense_build_rect(_ctx, P, xt_dev, m, s->t, n, 1, nullptr, Kst, kp, mp, kp);
+    for (int64_t r = 0; r < m; ++r) qs_affine(s, OP_LOWER_SOLVE, Kst + r * kp, At + r * kp, nullptr);
+    dense_conditioned_covariance_to_host(_ctx, P, At, mp, kp, xt_dev, dt, 1, m, out);
+    _ctx->release(Kst, ab);
+    _ctx->release(At, ab);
+    _ctx->release(dt, (size_t)mp * 8);
+    if (own_xt) _ctx->release(xt_dev, (size_t)m * 8);
+    API_END
+}
+
 int b200gp_searchsorted_right_m1(b200gp_ctx* ctx, const double* sorted, int64_t n, const double* query, int64_t m,
                                  int64_t* out) {
     API_BEGIN(ctx)

@@ -110,14 +110,27 @@ class QuasisepSolver(Solver):
         return d, p, q, a
 
     def condition(self, kernel, X_test, noise) -> Any:
-        """solver.py:104-139, dense branch (:131-139): the kernel matrices are built by the CUDA build kernel from
-        the kernel's closed form (kernels/quasisep.py tau_program) and solved against by the device scans.  The
-        QSM-valued branch (:124-129, X_test=None) needs qsm_mul / inv / gram and is a 'next' row; predicting at the
-        inputs returns the same values as a dense matrix instead."""
+        """solver.py:104-139, dense branch (:131-139): ``Kss - A^T A`` with ``A = factor.solve(Ks)`` -- computed
+        entirely on the device by ``b200gp_qs_condition`` (build kernel for ``Ks^T`` from the predictive kernel's
+        program, one forward-substitution scan per test point, NT GEMM on the tensor pipe with ``k(X*, X*)`` generated
+        in its epilogue).  As in the reference, ``noise`` does not enter this matrix (it does enter the conditioned
+        GP's ``variance``, see ``DirectSolver.__init__``).  The QSM-valued branch (:124-129, X_test=None with a
+        Quasisep kernel) needs qsm_mul / inv / gram and is a 'next' row; predicting at the inputs returns the same
+        values as a dense matrix instead."""
         if X_test is None:
-            Kss = Ks = kernel(self.X, self.X)
+            prog, x = kernel.lower_for(self.X)
+            xt_ptr, m = None, self._n
         else:
-            Kss = kernel(X_test, X_test)
-            Ks = kernel(self.X, X_test)
-        A = self.solve_triangular(Ks)
-        return Kss - A.T @ A
+            xt = np.asarray(kernel.coord_to_sortable(X_test) if hasattr(kernel, "coord_to_sortable") else X_test,
+                            dtype=np.float64)
+            if xt.ndim != 1:
+                raise ValueError("QuasisepSolver.condition takes 1-D test coordinates")
+            prog, x = kernel.lower_for(xt)
+            xt_ptr, m = _cabi.ptr(x), x.shape[0]
+        if x.shape[1] != 1:
+            raise NotImplementedError("a predictive kernel with host-side Transform columns is unsupported by the "
+                                      "B200 QuasisepSolver.condition")
+        out = np.empty((m, m))
+        self._ctx.check(self._ctx.lib.b200gp_qs_condition(self._h, _cabi.ptr(prog), prog.shape[0], xt_ptr, m,
+                                                          _cabi.ptr(out)))
+        return out

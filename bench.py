@@ -214,6 +214,9 @@ def run_ours(args, rank, local_rank, world):
     ctx.set_option("nb", args.nb)
     ctx.set_option("ozaki_slices", args.slices)
     ctx.set_option("ozaki_min_n", 0 if args.slices else 1 << 40)
+    for kv in args.opt:                            # tuning experiments: --opt ozaki_pairing=1 --opt ozaki_layout=1 ...
+        key, _, val = kv.partition("=")
+        ctx.set_option(key, int(val))
 
     n = args.n
     X, y, diag, scale = make_dense_problem(n, rank)
@@ -337,6 +340,7 @@ def run_ours(args, rank, local_rank, world):
                    "kernel": "1.0*ExpSquared(scale=1.0), L2", "diag": 0.1, "seed": SEED, "nb": args.nb,
                    "trailing_update": (f"int8 fixed-point, {args.slices} digit planes (tcgen05 kind::i8)" if args.slices
                                        else "native fp64 DMMA"),
+                   "options": args.opt,
                    "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                    "l2": "working set 34 GB >> 126 MB L2 (no flush needed)"},
         "logp": logp, "logp_e2e": logp_e2e, "golden": golden_check("c2", n, logp),
@@ -597,6 +601,8 @@ def main():
     ap.add_argument("--slices", type=int, default=8,
                     help="int8 digit planes of the fixed-point trailing update: 8 = 55-bit digits (fp64-equivalent, "
                          "default), 7 = 48-bit, 0 = native fp64 DMMA")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
+                    help="library option for tuning runs (b200gp_set_option), recorded in config.options; dense workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -173,19 +173,20 @@ class Kernel:
         if X2 is None:
             X2 = X1
         y = np.asarray(y, dtype=np.float64)
-        if y.ndim != 1:
-            return np.dot(self(X1, X2), y)
         ctx = _cabi.get_context()
         prog, x1 = self.lower_for(X1)
         _, x2 = self.lower_for(X2)
         if x1.shape[1] != x2.shape[1]:
             raise ValueError("X1 and X2 must have the same number of input dimensions")
-        yy = _cabi.f64(y)
-        out = np.empty(x1.shape[0])
-        ctx.check(ctx.lib.b200gp_kernel_matvec(ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(x1), x1.shape[0],
-                                               _cabi.ptr(x2), x2.shape[0], x1.shape[1], _cabi.ptr(yy),
-                                               _cabi.ptr(out)))
-        return out
+        if y.shape[0] != x2.shape[0]:
+            raise ValueError("dimension mismatch")
+        cols = np.ascontiguousarray(y.reshape(x2.shape[0], -1).T)   # one device matvec per right-hand side
+        out = np.empty((cols.shape[0], x1.shape[0]))
+        for r in range(cols.shape[0]):
+            ctx.check(ctx.lib.b200gp_kernel_matvec(ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(x1),
+                                                   x1.shape[0], _cabi.ptr(x2), x2.shape[0], x1.shape[1],
+                                                   _cabi.ptr(cols[r]), _cabi.ptr(out[r])))
+        return np.ascontiguousarray(out.T).reshape((x1.shape[0],) + y.shape[1:])
 
     # -- algebra (base.py:105-126) --------------------------------------------------------
     def __add__(self, other):

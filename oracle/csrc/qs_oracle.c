@@ -6,7 +6,8 @@
  *   log-probability  src/tinygp/gp.py:313-320 with solvers/quasisep/solver.py:90-93
  *
  * Generators d (n), p (n,J), q (n,J), a (n,J,J) are supplied by the caller (NumPy restatement of
- * kernels/quasisep.py:102-116), row-major.  "parity unpinned": the reference has no golden vectors.
+ * kernels/quasisep.py:102-116), row-major.  Pinned through the NumPy oracle (tests/test_oracle_quasisep.py compares
+ * the two), which is pinned to reference-generated goldens (oracle/__init__.py).
  */
 #include <math.h>
 #include <stdint.h>

@@ -2,7 +2,8 @@
 
 Every function cites the reference file:line (relative to /root/reference/src/tinygp)
 it follows.  Operation order follows the reference so that differences to XLA are
-limited to libm/LAPACK rounding.  "parity unpinned": see the package docstring.
+limited to libm/LAPACK rounding.  Pinned against reference-generated goldens
+(tests/golden/reference_vectors.json, <= 1e-12): see the package docstring.
 """
 
 from __future__ import annotations

@@ -239,13 +239,14 @@ int b200gp_qs_log_probability_dev(b200gp_ctx* ctx, const double* comps, int ncom
 int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t_test,
                             int64_t m, const double* t_train, int64_t n, const double* Y, int64_t nrhs,
                             double* out);
-/* QuasisepSolver.condition, dense branch (solvers/quasisep/solver.py:131-139): out (m x m, host, row-major) =
- * k(X*, X*) - A^T A with A = factor.solve(k(X, X*)); like the reference, the predictive noise is NOT added here.
- * `prog` is the predictive kernel's program for 1-D coordinates; t_test == NULL means X* = X (then m is ignored and
- * out is n x n).  Build kernel -> one forward-substitution scan per test point -> NT GEMM with the generator
- * epilogue; no host arithmetic. */
+/* QuasisepSolver.condition (solvers/quasisep/solver.py:104-139): out (m x m, host, row-major) =
+ * k(X*, X*) [+ diag] - A^T A with A = factor.solve(k(X, X*)).  The reference adds the predictive noise in its QSM
+ * branch (:124-129: X* = X and a quasiseparable kernel; returned here densified) and NOT in the dense branch
+ * (:131-139), so `diag_or_null` (m values) is passed only for the former.  `prog` is the predictive kernel's
+ * program for 1-D coordinates; t_test == NULL means X* = X (m is ignored, out is n x n).  Build kernel -> one
+ * forward-substitution scan per test point -> NT GEMM with the generator epilogue; no host arithmetic. */
 int b200gp_qs_condition(b200gp_qs* s, const double* prog, int n_instr, const double* t_test, int64_t m,
-                        double* out);
+                        const double* diag_or_null, double* out);
 /* jnp.searchsorted(X2, X1, side="right") - 1  (kernels/quasisep.py:121): bit-exact indices */
 int b200gp_searchsorted_right_m1(b200gp_ctx* ctx, const double* sorted, int64_t n,
                                  const double* query, int64_t m, int64_t* out);

@@ -800,7 +800,17 @@ class QuasisepSolver:
         y2, shape = _as2d(y)
         return (self.c[:, None] * y2 + qs_lower_matmul(self.p, self.w, self.a, y2)).reshape(shape)
 
-    def condition(self, kernel, X_test, noise):  # solver.py:131-139 (dense fallback)
+    def condition(self, kernel, X_test, noise):
+        """solver.py:104-139.  The QSM branch (:124-129, X_test None and a quasiseparable kernel) is
+        ``M + noise - (factor.inv() @ M).gram()``; restated densely -- (L^-1 M)^T (L^-1 M) is the same matrix -- so this
+        branch returns the same VALUES as the reference's SymmQSM, noise included; the dense branch (:131-139) has no
+        noise term.  `last_condition_has_noise` tells GaussianProcess.condition which one ran."""
+        self.last_condition_has_noise = False
+        if X_test is None and isinstance(kernel, qs.Quasisep):
+            M = kernel(self.X, self.X)
+            A = self.solve_triangular(M)
+            self.last_condition_has_noise = True
+            return M + np.diag(noise.diagonal()) - A.T @ A
         if X_test is None:
             Kss = Ks = kernel(self.X, self.X)
         else:
@@ -920,7 +930,7 @@ class GaussianProcess:
             X_test = self.X
         gp = GaussianProcess(kernel, X_test, noise=noise, mean_value=mean_value,
                              covariance_value=covariance_value, solver=_PrecomputedDirect,
-                             noise_in_covariance=isinstance(self.solver, DirectSolver))
+                             noise_in_covariance=getattr(self.solver, "last_condition_has_noise", True))
         return log_prob, gp
 
     def predict(self, y, X_test=None, *, kernel=None, include_mean=True, return_var=False, return_cov=False):

@@ -125,9 +125,13 @@ def run_case(ns, case):
     out["pred_var"] = to_np(cgp.variance).tolist()
     out["pred_cov_row0"] = to_np(cgp.covariance)[0].tolist()
     out["cond_gp_log_probability"] = float(to_np(cgp.log_probability(inp["y_test"])))
-    mu_in, var_in = gp.predict(y, return_var=True)           # X_test=None branch (gp.py:340-346)
-    out["pred_in_mean_norm"] = float(np.linalg.norm(to_np(mu_in)))
-    out["pred_in_var_sum"] = float(np.sum(to_np(var_in)))
+    cond_in = gp.condition(y, diag=0.05)                     # X_test=None branch (gp.py:340-346; solver.py:124-129)
+    out["pred_in_mean_norm"] = float(np.linalg.norm(to_np(cond_in[1].loc)))
+    out["pred_in_var_sum"] = float(np.sum(to_np(cond_in[1].variance)))
+    cov_in = to_np(cond_in[1].covariance)
+    out["pred_in_cov_trace"] = float(np.trace(cov_in))
+    out["pred_in_cov_row0"] = cov_in[0, :8].tolist()
+    out["cond_in_gp_log_probability"] = float(to_np(cond_in[1].log_probability(y + 0.01 * z)))
     if case["kind"] == "dense":
         idx = np.arange(0, case["n"], max(1, case["n"] // 9))[:9]
         X1 = X[idx]

@@ -1500,11 +1500,14 @@ int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, con
 }
 
 // QuasisepSolver.condition, dense branch (solvers/quasisep/solver.py:131-139):  out = Kss - A^T A with
-// A = factor.solve(Ks), Ks = k(X, X*), Kss = k(X*, X*) -- the noise is NOT added here (the reference does not).
+// A = factor.solve(Ks), Ks = k(X, X*), Kss = k(X*, X*).  The reference adds the predictive noise only in its QSM
+// branch (:124-129, X* = X with a quasiseparable kernel) and not in the dense branch: the caller passes
+// diag_or_null accordingly (m values added to the diagonal, or NULL).
 // Everything runs on the device: Ks^T (rows = test points, each row a contiguous n-vector) from the build kernel,
 // one forward-substitution scan per row, then the NT GEMM with the k(X*, X*) generator epilogue shared with
 // DirectSolver.condition.  `prog` is the predictive kernel lowered for 1-D coordinates; t_test == NULL means X* = X.
-int b200gp_qs_condition(b200gp_qs* s, const double* prog, int n_instr, const double* t_test, int64_t m, double* out) {
+int b200gp_qs_condition(b200gp_qs* s, const double* prog, int n_instr, const double* t_test, int64_t m,
+                        const double* diag_or_null, double* out) {
     API_BEGIN(s->ctx)
     KProg P = parse_prog(prog, n_instr, 1);
     const int64_t n = s->n;
@@ -1524,6 +1527,8 @@ int b200gp_qs_condition(b200gp_qs* s, const double* prog, int n_instr, const dou
     double* At = (double*)_ctx->alloc(ab);
     double* dt = (double*)_ctx->alloc((size_t)mp * 8);
     CUDA_CHECK(cudaMemsetAsync(dt, 0, (size_t)mp * 8, _ctx->stream));
+    if (diag_or_null != nullptr)   // solver.py:124-129 adds the noise; the dense branch :131-139 does not
+        CUDA_CHECK(cudaMemcpyAsync(dt, diag_or_null, (size_t)m * 8, cudaMemcpyHostToDevice, _ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(At, 0, ab, _ctx->stream));   // pad rows / columns of A^T must be zero for the GEMM
     dense_build_rect(_ctx, P, xt_dev, m, s->t, n, 1, nullptr, Kst, kp, mp, kp);
     for (int64_t r = 0; r < m; ++r) qs_affine(s, OP_LOWER_SOLVE, Kst + r * kp, At + r * kp, nullptr);

@@ -12,13 +12,11 @@ import numpy as np
 
 from tinygp_b200 import _cabi
 from tinygp_b200.kernels.base import Kernel, _as_coords
-from tinygp_b200.solvers.solver import Solver
+from tinygp_b200.solvers.solver import ConditionedCovariance, Solver
 
 
 class DirectSolver(Solver):
     """Dense build fused into a blocked Cholesky on the fp64 tensor pipe (direct.py:30-53)."""
-
-    condition_includes_noise = True   # direct.py:88-92: Kss = kernel(X*, X*) + noise
 
     def __init__(self, kernel: Kernel, X, noise, *, covariance: Any | None = None):
         self._ctx = _cabi.get_context()
@@ -50,8 +48,7 @@ class DirectSolver(Solver):
             # QuasisepSolver.condition's dense branch leaves it out (solvers/quasisep/solver.py:131-139), and the
             # reference's conditioned variance then still carries it (golden: reference_vectors.json pred_var).
             self.variance_value = np.diag(cov).copy()
-            parent = getattr(kernel, "solver", None)
-            if parent is not None and not getattr(parent, "condition_includes_noise", True):
+            if not getattr(covariance, "includes_noise", True):    # solvers.solver.ConditionedCovariance tag
                 self.variance_value = self.variance_value + _cabi.f64(noise.diagonal())
             self._ctx.check(lib.b200gp_dense_create_from_cov(self._ctx.handle, _cabi.ptr(cov), cov.shape[0],
                                                              byref(self._h), byref(info)))
@@ -122,4 +119,4 @@ class DirectSolver(Solver):
         out = np.empty((m, m))
         self._ctx.check(self._ctx.lib.b200gp_dense_condition(self._h, _cabi.ptr(prog), prog.shape[0], xt_ptr, m,
                                                              _cabi.ptr(diag), _cabi.ptr(out)))
-        return out
+        return ConditionedCovariance.tag(out, True)          # direct.py:88-92: Kss = kernel(X*, X*) + noise

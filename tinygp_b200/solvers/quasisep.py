@@ -12,14 +12,12 @@ import numpy as np
 
 from tinygp_b200 import _cabi
 from tinygp_b200.kernels.quasisep import Quasisep
-from tinygp_b200.solvers.solver import Solver
+from tinygp_b200.solvers.solver import ConditionedCovariance, Solver
 
 _UNSORTED_MSG = "Input coordinates must be sorted in order to use the QuasisepSolver"  # solver.py:142-146
 
 
 class QuasisepSolver(Solver):
-    condition_includes_noise = False  # solver.py:131-139: the dense branch returns Kss - A^T A without the noise
-
     def __init__(self, kernel, X, noise, *, covariance: Any | None = None, assume_sorted: bool = False,
                  parallel: bool = False):
         """``parallel`` is accepted for API compatibility (solver.py:33,60-64); the device scans are
@@ -110,16 +108,22 @@ class QuasisepSolver(Solver):
         return d, p, q, a
 
     def condition(self, kernel, X_test, noise) -> Any:
-        """solver.py:104-139, dense branch (:131-139): ``Kss - A^T A`` with ``A = factor.solve(Ks)`` -- computed
-        entirely on the device by ``b200gp_qs_condition`` (build kernel for ``Ks^T`` from the predictive kernel's
-        program, one forward-substitution scan per test point, NT GEMM on the tensor pipe with ``k(X*, X*)`` generated
-        in its epilogue).  As in the reference, ``noise`` does not enter this matrix (it does enter the conditioned
-        GP's ``variance``, see ``DirectSolver.__init__``).  The QSM-valued branch (:124-129, X_test=None with a
-        Quasisep kernel) needs qsm_mul / inv / gram and is a 'next' row; predicting at the inputs returns the same
-        values as a dense matrix instead."""
+        """solver.py:104-139: ``Kss [+ noise] - A^T A`` with ``A = factor.solve(Ks)`` -- computed entirely on the
+        device by ``b200gp_qs_condition`` (build kernel for ``Ks^T`` from the predictive kernel's program, one
+        forward-substitution scan per test point, NT GEMM on the tensor pipe with ``k(X*, X*)`` generated in its
+        epilogue).  The reference adds the predictive noise in its QSM branch (:124-129: ``X_test is None`` with a
+        quasiseparable kernel) and not in its dense branch (:131-139); the result is tagged accordingly
+        (``ConditionedCovariance.includes_noise``).  The QSM branch's *values* are returned as a dense matrix: a
+        QSM-valued result needs qsm_mul / inv / gram on the device and is a 'next' row."""
+        diag_ptr, with_noise = None, False
         if X_test is None:
             prog, x = kernel.lower_for(self.X)
             xt_ptr, m = None, self._n
+            if isinstance(kernel, Quasisep):                                   # solver.py:124-129
+                diag = _cabi.f64(noise.diagonal())
+                if diag.shape != (m,):
+                    raise ValueError("noise diagonal must match the number of predicted points")
+                diag_ptr, with_noise = _cabi.ptr(diag), True
         else:
             xt = np.asarray(kernel.coord_to_sortable(X_test) if hasattr(kernel, "coord_to_sortable") else X_test,
                             dtype=np.float64)
@@ -132,5 +136,5 @@ class QuasisepSolver(Solver):
                                       "B200 QuasisepSolver.condition")
         out = np.empty((m, m))
         self._ctx.check(self._ctx.lib.b200gp_qs_condition(self._h, _cabi.ptr(prog), prog.shape[0], xt_ptr, m,
-                                                          _cabi.ptr(out)))
-        return out
+                                                          diag_ptr, _cabi.ptr(out)))
+        return ConditionedCovariance.tag(out, with_noise)

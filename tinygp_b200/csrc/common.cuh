@@ -64,7 +64,11 @@ struct b200gp_ctx {
     int64_t qs_chunk = 64;      // points per thread in the quasiseparable scans
     int64_t potf2_version = 2;  // 1: column-at-a-time diagonal-block kernel, 2: rank-8 blocked with register tiles
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
-    int64_t oz_slices = 8;      // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA
+    // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA.  7 planes = 48 bits under the
+    // row scale: at N = 65536 the log-probability differs from the LAPACK golden by 4.7e-12 with 7 AND with 8 planes
+    // (profiles/r1_bench_dense_int8x{7,8}.json vs tests/golden/full_size.json) -- the digit truncation is below the fp64
+    // rounding of the factorisation itself, so the 8th plane buys nothing; 8 stays available (ozaki_slices).
+    int64_t oz_slices = 7;
     int64_t oz_lookahead = 0;   // overlap the fp64 panel factorisation with the int8 update on a second stream
     cudaStream_t stream2 = nullptr;
     int64_t oz_prefetch = 0;    // L2 prefetch distance (K-chunks of 128) of the int8 update's TMA producer

@@ -78,3 +78,32 @@ def test_matrix_rhs_kernel_matmul_runs_on_the_device_entry_point(mocklib):
     assert got.shape == (5, 3) and mocklib.calls.count("kernel_matvec") == 3 and "kernel_matrix" not in mocklib.calls
     from oracle import tinygp_np as o
     np.testing.assert_allclose(got, (1.3 * o.Matern52(0.8))(X1, X2) @ Y, rtol=1e-12, atol=1e-14)
+
+
+def test_mean_only_predict_skips_the_conditioned_covariance(mocklib):
+    """gp.py:225-229: predict is jitted with return_var / return_cov static, so the reference never materialises the
+    conditioned covariance for a mean-only prediction; neither do we (an N x N matrix for a long time series)."""
+    import tinygp_b200 as tg
+    from tinygp_b200.kernels import quasisep
+    from oracle import tinygp_np as o
+    rng = np.random.default_rng(2)
+    t = np.sort(rng.uniform(0, 30, 150)); y = np.sin(t); tt = rng.uniform(-1, 31, 11)
+    k, ko = quasisep.SHO(1.5, 3.0, 1.8) + quasisep.Matern32(1.5, 0.9), o.qs.SHO(1.5, 3.0, 1.8) + o.qs.Matern32(1.5, 0.9)
+    gp, gpo = tg.GaussianProcess(k, t, diag=0.1), o.GaussianProcess(ko, t, diag=0.1)
+    np.testing.assert_allclose(gp.predict(y), gpo.predict(y), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(gp.predict(y, tt), gpo.predict(y, tt), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(gp.predict(y, tt, include_mean=False), gpo.predict(y, tt, include_mean=False),
+                               rtol=1e-10, atol=1e-12)
+    assert "qs_condition" not in mocklib.calls and "kernel_matrix" not in mocklib.calls
+    mu, var = gp.predict(y, tt, return_var=True)
+    muo, varo = gpo.predict(y, tt, return_var=True)
+    np.testing.assert_allclose(var, varo, rtol=1e-9, atol=1e-12)
+    assert "qs_condition" in mocklib.calls
+    Xd = rng.uniform(0, 4, (40, 2)); yd = np.sin(Xd[:, 0])
+    gpd = tg.GaussianProcess(tg.kernels.Matern32(1.2), Xd, diag=0.1, mean=0.4)
+    gpdo = o.GaussianProcess(o.Matern32(1.2), Xd, diag=0.1, mean=0.4)
+    n0 = len(mocklib.calls)
+    np.testing.assert_allclose(gpd.predict(yd, Xd[:5] + 0.1), gpdo.predict(yd, Xd[:5] + 0.1), rtol=1e-10, atol=1e-12)
+    assert "dense_condition" not in mocklib.calls[n0:]
+    with pytest.raises(ValueError):
+        gpd.predict(yd, Xd[0])

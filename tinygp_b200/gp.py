@@ -63,13 +63,7 @@ class GaussianProcess:
     def condition(self, y, X_test=None, *, diag=None, noise: Noise | None = None, include_mean: bool = True,
                   kernel=None) -> "ConditionResult":
         """gp.py:140-223"""
-        if X_test is not None:  # gp.py:180-191
-            a, b = np.asarray(self.X), np.asarray(X_test)
-            if a.ndim != b.ndim or a.shape[1:] != b.shape[1:]:
-                raise ValueError(
-                    "`X_test` must have the same tree structure as the input `X`, "
-                    "and all but the leading dimension must have matching sizes"
-                )
+        self._check_X_test(X_test)
         alpha, log_prob, mean_value = self._condition(y, X_test, include_mean, kernel)
         if kernel is None:
             kernel = self.kernel
@@ -93,7 +87,13 @@ class GaussianProcess:
 
     def predict(self, y, X_test=None, *, kernel=None, include_mean: bool = True, return_var: bool = False,
                 return_cov: bool = False):
-        """gp.py:225-271"""
+        """gp.py:225-271.  The reference's ``predict`` is jitted with ``return_var`` / ``return_cov`` static
+        (gp.py:225-229), so XLA never computes the conditioned covariance when only the mean is asked for; the same
+        holds here explicitly -- the mean needs ``alpha`` and one kernel product, not ``solver.condition`` (which for a
+        quasiseparable N = 10^7 series would be an N x N matrix)."""
+        if not (return_var or return_cov):
+            self._check_X_test(X_test)
+            return self._condition(y, X_test, include_mean, kernel)[2]
         _, cond = self.condition(y, X_test, kernel=kernel, include_mean=include_mean)
         if return_var:
             return cond.loc, cond.variance
@@ -108,6 +108,15 @@ class GaussianProcess:
         shape = (self.num_data,) if shape is None else (self.num_data,) + tuple(shape)
         normal_samples = rng.standard_normal(shape)
         return self.mean + np.moveaxis(self.solver.dot_triangular(normal_samples), 0, -1)
+
+    def _check_X_test(self, X_test):  # gp.py:180-191
+        if X_test is not None:
+            a, b = np.asarray(self.X), np.asarray(X_test)
+            if a.ndim != b.ndim or a.shape[1:] != b.shape[1:]:
+                raise ValueError(
+                    "`X_test` must have the same tree structure as the input `X`, "
+                    "and all but the leading dimension must have matching sizes"
+                )
 
     # -- internals (gp.py:313-361) -------------------------------------------------------------
     def _compute_log_prob(self, alpha):

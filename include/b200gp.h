@@ -239,6 +239,13 @@ int b200gp_qs_log_probability_dev(b200gp_ctx* ctx, const double* comps, int ncom
 int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t_test,
                             int64_t m, const double* t_train, int64_t n, const double* Y, int64_t nrhs,
                             double* out);
+/* diag((K + N)^-1), n values (host): the diagonal of `factor.inv().gram()` (solvers/quasisep/core.py:310-317,
+ * 424-434) by one backward scan in O(n J^3), without forming the matrix.  The conditioned variance at the inputs
+ * (solver.py:124-129 then :84-85) is  noise* + N - N^2 diag((K + N)^-1). */
+int b200gp_qs_inverse_diagonal(b200gp_qs* s, double* out);
+/* variance of the conditioned process at the inputs for the solver's own kernel = diagonal of solver.py:124-129 as
+ * read by solver.py:84-85:  out_i = noise_pred_i + N_i - N_i^2 diag((K + N)^-1)_i  (n values in, n out, host). */
+int b200gp_qs_conditioned_variance(b200gp_qs* s, const double* noise_pred, double* out);
 /* QuasisepSolver.condition (solvers/quasisep/solver.py:104-139): out (m x m, host, row-major) =
  * k(X*, X*) [+ diag] - A^T A with A = factor.solve(k(X, X*)).  The reference adds the predictive noise in its QSM
  * branch (:124-129: X* = X and a quasiseparable kernel; returned here densified) and NOT in the dense branch

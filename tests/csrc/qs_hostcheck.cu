@@ -1,0 +1,111 @@
+// TEST INFRASTRUCTURE: runs the __host__ __device__ pieces of tinygp_b200/csrc/qs_core.cuh on the CPU, one "thread"
+// at a time, so that `-m "not gpu"` tests can compare the SAME source the CUDA kernels execute (model lowering,
+// per-point generators, the GramBack scan monoid, chunk / tree / replay decomposition) with the oracle.
+// Built on demand by tests/test_device_code_on_host.py with nvcc; never linked into libb200gp.so.
+#include "../../tinygp_b200/csrc/qs_core.cuh"
+
+#include <vector>
+
+namespace {
+
+template <class Op, int J>
+void host_tree(const std::vector<double>& comp, int64_t n, std::vector<double>& start) {
+    // the same two-level structure as run_tree<Op> (fan-in TREE_R), recursively, using Op::combine / Op::apply
+    if (n <= TREE_R) {
+        double s[J][J] = {};
+        Op e;
+        for (int64_t i = 0; i < n; ++i) {
+            for (int q = 0; q < J * J; ++q) start[(size_t)q * n + i] = s[q / J][q % J];
+            e.load(comp.data(), n, i);
+            e.apply(s);
+        }
+        return;
+    }
+    const int64_t np_ = (n + TREE_R - 1) / TREE_R;
+    std::vector<double> parent((size_t)Op::SIZE * np_), pstart((size_t)J * J * np_);
+    for (int64_t i = 0; i < np_; ++i) {                       // tree_up_kernel
+        Op acc, e;
+        const int64_t b = i * TREE_R;
+        acc.load(comp.data(), n, b);
+        for (int64_t j = b + 1; j < b + TREE_R && j < n; ++j) { e.load(comp.data(), n, j); acc.combine(e); }
+        acc.store(parent.data(), np_, i);
+    }
+    host_tree<Op, J>(parent, np_, pstart);
+    for (int64_t i = 0; i < np_; ++i) {                       // tree_down_kernel
+        double s[J][J];
+        for (int q = 0; q < J * J; ++q) s[q / J][q % J] = pstart[(size_t)q * np_ + i];
+        Op e;
+        const int64_t b = i * TREE_R;
+        for (int64_t j = b; j < b + TREE_R && j < n; ++j) {
+            for (int q = 0; q < J * J; ++q) start[(size_t)q * n + j] = s[q / J][q % J];
+            if (j + 1 < b + TREE_R && j + 1 < n) { e.load(comp.data(), n, j); e.apply(s); }
+        }
+    }
+}
+
+template <int J>
+void inv_diag_host(const QsModel& m, const double* t, const double* c, const double* w, int64_t n, double* out) {
+    const int64_t nch = (n + m.chunk - 1) / m.chunk;
+    std::vector<double> comp((size_t)GramBack<J>::SIZE * nch), start((size_t)J * J * nch);
+    for (int64_t ch = 0; ch < nch; ++ch) gram_chunk_body<J>(m, t, c, w, n, comp.data(), nch, ch);
+    host_tree<GramBack<J>, J>(comp, nch, start);
+    for (int64_t ch = 0; ch < nch; ++ch) gram_replay_body<J>(m, t, c, w, n, start.data(), nch, out, ch);
+}
+
+template <int J>
+void generators_host(const QsModel& m, const double* t, int64_t n, double* a_out, double* p_out) {
+    for (int64_t k = 0; k < n; ++k) {
+        double a[J][J], p[J];
+        qs_gen<J>(m, (k == 0) ? 0.0 : (t[k] - t[k - 1]), a, p);
+        for (int i = 0; i < J; ++i) {
+            p_out[k * J + i] = p[i];
+            for (int j = 0; j < J; ++j) a_out[(k * J + i) * J + j] = a[i][j];
+        }
+    }
+}
+
+}  // namespace
+
+#define DISPATCH_J(Jv, CALL)                        \
+    switch (Jv) {                                   \
+        case 1: { constexpr int JJ = 1; CALL; } break; \
+        case 2: { constexpr int JJ = 2; CALL; } break; \
+        case 3: { constexpr int JJ = 3; CALL; } break; \
+        case 4: { constexpr int JJ = 4; CALL; } break; \
+        case 5: { constexpr int JJ = 5; CALL; } break; \
+        case 6: { constexpr int JJ = 6; CALL; } break; \
+        default: return 3;                          \
+    }
+
+extern "C" {
+
+// model constants: J, q (h Pinf), h, d0
+int hostcheck_model(const double* comps, int ncomp, int* J, double* q, double* h, double* d0) {
+    try {
+        QsModel m = build_model(comps, ncomp);
+        *J = m.J;
+        *d0 = m.d0;
+        for (int i = 0; i < m.J; ++i) { q[i] = m.q[i]; h[i] = m.h[i]; }
+        return 0;
+    } catch (const std::exception&) { return 2; }
+}
+
+int hostcheck_generators(const double* comps, int ncomp, const double* t, int64_t n, double* a_out, double* p_out) {
+    try {
+        QsModel m = build_model(comps, ncomp);
+        DISPATCH_J(m.J, (generators_host<JJ>(m, t, n, a_out, p_out)))
+        return 0;
+    } catch (const std::exception&) { return 2; }
+}
+
+int hostcheck_inverse_diagonal(const double* comps, int ncomp, const double* t, int64_t n, const double* c,
+                               const double* w, int chunk, double* out) {
+    try {
+        QsModel m = build_model(comps, ncomp);
+        m.chunk = chunk;
+        DISPATCH_J(m.J, (inv_diag_host<JJ>(m, t, c, w, n, out)))
+        return 0;
+    } catch (const std::exception&) { return 2; }
+}
+
+}  // extern "C"

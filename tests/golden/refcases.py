@@ -132,6 +132,9 @@ def run_case(ns, case):
     out["pred_in_cov_trace"] = float(np.trace(cov_in))
     out["pred_in_cov_row0"] = cov_in[0, :8].tolist()
     out["cond_in_gp_log_probability"] = float(to_np(cond_in[1].log_probability(y + 0.01 * z)))
+    mu_p, var_p = gp.predict(y, return_var=True)             # gp.py:225-271 at the inputs, default predictive jitter
+    out["predict_in_mean_norm"] = float(np.linalg.norm(to_np(mu_p)))
+    out["predict_in_var"] = to_np(var_p)[:: max(1, case["n"] // 16)].tolist()
     if case["kind"] == "dense":
         idx = np.arange(0, case["n"], max(1, case["n"] // 9))[:9]
         X1 = X[idx]

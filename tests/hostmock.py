@@ -297,6 +297,21 @@ class MockLib:
         y[:] = s.covariance() @ y
         return 0
 
+    def b200gp_qs_inverse_diagonal(self, h, outp):
+        self.calls.append("qs_inverse_diagonal")
+        s = self._get(h)
+        arr(outp, s.d.shape)[:] = np.diag(np.linalg.inv(s.covariance()))
+        return 0
+
+    def b200gp_qs_conditioned_variance(self, h, noise_pred, outp):
+        self.calls.append("qs_conditioned_variance")
+        s = self._get(h)
+        n = s.d.shape[0]
+        K = s.kernel(s.X, s.X)
+        A = s.solve_triangular(K)
+        arr(outp, (n,))[:] = arr(noise_pred, (n,)) + np.diag(K - A.T @ A)      # solver.py:124-129 read by :84-85
+        return 0
+
     def b200gp_qs_condition(self, h, prog, n_instr, t_test, m, diag, outp):
         self.calls.append("qs_condition")
         s = self._get(h)

@@ -1,0 +1,71 @@
+"""diag((K + N)^-1) and the O(N) conditioned variance of the QuasisepSolver (GramBack backward scan, written after
+round 1's GPU minutes were spent: the same source passes on the CPU in tests/test_device_code_on_host.py; this file
+sorts last so that a launch-geometry problem here cannot hide the other GPU results under `pytest -x`)."""
+
+import numpy as np
+import pytest
+
+from oracle import tinygp_np as o
+from tinygp_b200 import GaussianProcess
+from tinygp_b200.kernels import quasisep as Q
+from util import to_oracle
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = {
+    "sho+m32": Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9),
+    "m52": Q.Matern52(2.5, 1.3),
+    "exp": Q.Exp(1.7, 0.8),
+    "sum3": 2.0 * Q.Matern32(1.2) + Q.SHO(0.8, 4.0, 0.6) + 0.5 * Q.Exp(5.0),
+}
+
+
+def _data(n, seed=3):
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(0, n / 8.0, n))
+    return t, np.sin(t) + 0.1 * rng.normal(size=n), rng.uniform(0.05, 0.2, n)
+
+
+@pytest.mark.parametrize("n", [1, 63, 700, 4099])
+@pytest.mark.parametrize("name", list(KERNELS))
+def test_inverse_diagonal_parity(name, n):
+    t, y, noise = _data(n)
+    gp = GaussianProcess(KERNELS[name], t, diag=noise)
+    got = gp.solver.inverse_diagonal()
+    so = o.QuasisepSolver(to_oracle(KERNELS[name]), t, o.Diagonal(noise))
+    if n <= 700:
+        want = np.diag(np.linalg.inv(so.covariance()))
+    else:
+        idx = np.unique(np.r_[0, 1, n // 2, n - 2, n - 1, np.random.default_rng(1).integers(0, n, 12)])
+        E = np.zeros((n, idx.size)); E[idx, np.arange(idx.size)] = 1.0
+        want = so.solve_triangular(so.solve_triangular(E), transpose=True)[idx, np.arange(idx.size)]
+        got = got[idx]
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("name", list(KERNELS))
+def test_predict_variance_at_the_inputs_is_the_reference_qsm_branch(name):
+    """gp.predict(y, return_var=True): solver.py:124-129 read by :84-85, here by one backward scan"""
+    t, y, noise = _data(300)
+    mu, var = GaussianProcess(KERNELS[name], t, diag=noise).predict(y, return_var=True)
+    muo, varo = o.GaussianProcess(to_oracle(KERNELS[name]), t, diag=noise).predict(y, return_var=True)
+    np.testing.assert_allclose(mu, muo, rtol=5e-7, atol=5e-7)
+    np.testing.assert_allclose(var, varo, rtol=1e-8, atol=1e-12)
+
+
+def test_large_series_smoothing_variance_is_linear_time():
+    """N = 2e6: no N x N matrix anywhere; the variance lies between 0 and the prior variance + jitter and equals
+    the dense value on a window far from the ends (the process decorrelates over a few time scales)."""
+    n = 2_000_000
+    t, y, noise = _data(n, seed=5)
+    k = KERNELS["sho+m32"]
+    gp = GaussianProcess(k, t, diag=noise)
+    mu, var = gp.predict(y, return_var=True)
+    assert mu.shape == var.shape == (n,) and np.all(np.isfinite(var))
+    prior = 1.8 ** 2 + 0.9 ** 2
+    assert var.min() > 0.0 and var.max() < prior + 1e-6
+    lo, hi = n // 2 - 1500, n // 2 + 1500                       # 3000 points ~ 375 time units >> all time scales
+    muw, varw = o.GaussianProcess(to_oracle(k), t[lo:hi], diag=noise[lo:hi]).predict(y[lo:hi], return_var=True)
+    mid = slice(1000, 2000)
+    np.testing.assert_allclose(var[lo:hi][mid], varw[mid], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(mu[lo:hi][mid], muw[mid], rtol=1e-6, atol=1e-8)

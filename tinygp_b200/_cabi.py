@@ -90,6 +90,8 @@ SIGNATURES = {
     "b200gp_qs_log_probability": (c_int, [_V, _D, _I, _D, _L, _D, _D, _I, POINTER(c_int), c_double_p]),
     "b200gp_qs_log_probability_dev": (c_int, [_V, _D, _I, _D, _L, _D, _D, _I, POINTER(c_int), c_double_p]),
     "b200gp_qs_kernel_matmul": (c_int, [_V, _D, c_int, _D, _L, _D, _L, _D, _L, _D]),
+    "b200gp_qs_inverse_diagonal": (c_int, [_V, _D]),
+    "b200gp_qs_conditioned_variance": (c_int, [_V, _D, _D]),
     "b200gp_qs_condition": (c_int, [_V, _D, _I, _D, _L, _D, _D]),
     "b200gp_searchsorted_right_m1": (c_int, [_V, _D, _L, _D, _L, _D]),
 }

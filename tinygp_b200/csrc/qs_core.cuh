@@ -1,0 +1,440 @@
+// Shared core of the quasiseparable path: the state-space model, per-point generators, small dense helpers and the
+// scan pieces that are written as __host__ __device__ functions so that tests/csrc/qs_hostcheck.cu can run the SAME
+// source on the CPU (serially, one "thread" at a time) against the oracle.  Included by quasisep.cu.
+#pragma once
+#include "common.cuh"
+#include <math.h>
+
+#define TREE_R 16
+#define QS_THREADS 128
+
+struct QsModel {
+    int ncomp, J;
+    int chunk;   // points per thread (runtime tunable, option "qs_chunk")
+    int kind[B200GP_QS_MAX_COMP];
+    int off[B200GP_QS_MAX_COMP];
+    int mode[B200GP_QS_MAX_COMP];  // SHO: 0 critical, 1 underdamped, 2 overdamped
+    double c0[B200GP_QS_MAX_COMP], c1[B200GP_QS_MAX_COMP], c2[B200GP_QS_MAX_COMP];
+    double h[B200GP_QS_MAX_J];  // observation model (constant for all supported kernels)
+    double q[B200GP_QS_MAX_J];  // h Pinf
+    double d0;                  // h Pinf h
+};
+
+// ---------------------------------------------------------------------------------------------
+// host: lower the component list to a QsModel (constants follow kernels/quasisep.py)
+// ---------------------------------------------------------------------------------------------
+static inline QsModel build_model(const double* comps, int ncomp) {
+    if (ncomp <= 0 || ncomp > B200GP_QS_MAX_COMP) throw GpError("quasisep: bad component count");
+    QsModel m{};
+    m.ncomp = ncomp;
+    int J = 0;
+    double Pinf[B200GP_QS_MAX_J][B200GP_QS_MAX_J] = {};
+    for (int i = 0; i < ncomp; ++i) {
+        const double* cc = comps + (size_t)i * B200GP_QS_STRIDE;
+        const int kind = (int)cc[0];
+        const double ps = cc[1], p0 = cc[2], p1 = cc[3], p2 = cc[4], p3 = cc[5];
+        int sz;
+        switch (kind) {
+            case B200GP_QS_EXP: sz = 1; break;
+            case B200GP_QS_MATERN52: sz = 3; break;
+            case B200GP_QS_MATERN32: case B200GP_QS_SHO: case B200GP_QS_CELERITE: case B200GP_QS_COSINE: sz = 2; break;
+            default: throw GpError("quasisep: unknown component kind");
+        }
+        if (J + sz > B200GP_QS_MAX_J) throw GpError("quasisep: state dimension exceeds 8");
+        m.kind[i] = kind;
+        m.off[i] = J;
+        double P[3][3] = {};
+        double h[3] = {0, 0, 0};
+        switch (kind) {
+            case B200GP_QS_EXP:  // quasisep.py:491-525
+                m.c0[i] = p0; h[0] = p1; P[0][0] = 1.0; break;
+            case B200GP_QS_MATERN32: {  // quasisep.py:528-569
+                const double f = sqrt(3.0) / p0;
+                m.c0[i] = f; m.c1[i] = f * f; h[0] = p1;
+                P[0][0] = 1.0; P[1][1] = 3.0 / (p0 * p0); break;
+            }
+            case B200GP_QS_MATERN52: {  // quasisep.py:572-633
+                const double f = sqrt(5.0) / p0, f2 = f * f, f2o3 = f2 / 3.0;
+                m.c0[i] = f; m.c1[i] = f2; h[0] = p1;
+                P[0][0] = 1.0; P[0][2] = -f2o3; P[1][1] = f2o3; P[2][0] = -f2o3; P[2][2] = f2 * f2; break;
+            }
+            case B200GP_QS_SHO: {  // quasisep.py:404-488
+                const double w = p0, q = p1;
+                m.c0[i] = w; m.c1[i] = q; h[0] = p2;
+                P[0][0] = 1.0; P[1][1] = w * w;
+                if (fabs(q - 0.5) <= 1e-8 + 1e-5 * 0.5) {  // jnp.allclose(q, 0.5)
+                    m.mode[i] = 0;
+                } else if (q > 0.5) {
+                    m.mode[i] = 1; m.c2[i] = sqrt(fmax(4.0 * (q * q) - 1.0, 0.0));
+                } else {
+                    m.mode[i] = 2; m.c2[i] = sqrt(fmax(1.0 - 4.0 * (q * q), 0.0));
+                }
+                break;
+            }
+            case B200GP_QS_CELERITE: {  // quasisep.py:343-401
+                const double a = p0, b = p1, c = p2, d = p3;
+                const double c2 = c * c, d2 = d * d, s2 = c2 + d2;
+                const double h2_2 = d2 * (a * c - b * d) / (2.0 * c * s2);
+                const double h2 = sqrt(h2_2);
+                const double h1 = (c * h2 - sqrt(a * d2 - s2 * h2_2)) / d;
+                m.c0[i] = c; m.c1[i] = d; h[0] = h1; h[1] = h2;
+                P[0][0] = 1.0; P[0][1] = P[1][0] = -c / d; P[1][1] = 1.0 + 2.0 * c2 / d2; break;
+            }
+            case B200GP_QS_COSINE:  // quasisep.py:636-673
+                m.c0[i] = 2.0 * M_PI / p0; h[0] = p1; P[0][0] = P[1][1] = 1.0; break;
+        }
+        for (int r = 0; r < sz; ++r) {
+            m.h[J + r] = h[r];
+            for (int s = 0; s < sz; ++s) Pinf[J + r][J + s] = ps * P[r][s];  // Scale: quasisep.py:334-340
+        }
+        J += sz;
+    }
+    m.J = J;
+    m.d0 = 0.0;
+    for (int j = 0; j < J; ++j) {  // q = h Pinf ; d = sum(hP * h)   (quasisep.py:109-111)
+        double s = 0.0;
+        for (int i = 0; i < J; ++i) s += m.h[i] * Pinf[i][j];
+        m.q[j] = s;
+    }
+    for (int j = 0; j < J; ++j) m.d0 += m.q[j] * m.h[j];
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device: per-point generators  a = T(t_{k-1}, t_k)^T,  p = h a      (quasisep.py:102-116)
+// ---------------------------------------------------------------------------------------------
+template <int J>
+__host__ __device__ __forceinline__ void qs_gen(const QsModel& m, const double dt, double (&a)[J][J], double (&p)[J]) {
+    double al[J * J];  // scratch with runtime offsets; copied to registers below
+#pragma unroll
+    for (int i = 0; i < J * J; ++i) al[i] = 0.0;
+    for (int ci = 0; ci < m.ncomp; ++ci) {
+        const int o = m.off[ci];
+        double T[3][3];  // transition_matrix(X1, X2) as written in the reference
+        int sz = 2;
+        switch (m.kind[ci]) {
+            case B200GP_QS_EXP:
+                sz = 1;
+                T[0][0] = exp(-dt / m.c0[ci]);
+                break;
+            case B200GP_QS_MATERN32: {
+                const double f = m.c0[ci], e = exp(-f * dt);
+                T[0][0] = e * (1.0 + f * dt); T[0][1] = e * (-m.c1[ci] * dt);
+                T[1][0] = e * dt;             T[1][1] = e * (1.0 - f * dt);
+                break;
+            }
+            case B200GP_QS_MATERN52: {
+                sz = 3;
+                const double f = m.c0[ci], f2 = m.c1[ci], d2 = dt * dt, e = exp(-f * dt);
+                T[0][0] = e * (0.5 * f2 * d2 + f * dt + 1.0);
+                T[0][1] = e * (-0.5 * f * f2 * d2);
+                T[0][2] = e * (0.5 * f2 * f * dt * (f * dt - 2.0));
+                T[1][0] = e * (dt * (f * dt + 1.0));
+                T[1][1] = e * (-f2 * d2 + f * dt + 1.0);
+                T[1][2] = e * (f2 * dt * (f * dt - 3.0));
+                T[2][0] = e * (0.5 * d2);
+                T[2][1] = e * (0.5 * dt * (2.0 - f * dt));
+                T[2][2] = e * (0.5 * f2 * d2 - 2.0 * f * dt + 1.0);
+                break;
+            }
+            case B200GP_QS_SHO: {
+                const double w = m.c0[ci], q = m.c1[ci];
+                if (m.mode[ci] == 0) {
+                    const double e = exp(-w * dt);
+                    T[0][0] = e * (1.0 + w * dt); T[0][1] = e * (-(w * w) * dt);
+                    T[1][0] = e * dt;             T[1][1] = e * (1.0 - w * dt);
+                } else {
+                    const double f = m.c2[ci];
+                    const double arg = 0.5 * f * w * dt / q;
+                    const double e = exp(-0.5 * w * dt / q);
+                    double sn, cs;
+                    if (m.mode[ci] == 1) {
+                        sincos(arg, &sn, &cs);
+                    } else {
+                        sn = sinh(arg);
+                        cs = cosh(arg);
+                    }
+                    T[0][0] = e * (cs + sn / f);           T[0][1] = e * (-2.0 * q * w * sn / f);
+                    T[1][0] = e * (2.0 * q * sn / (w * f)); T[1][1] = e * (cs - sn / f);
+                }
+                break;
+            }
+            case B200GP_QS_CELERITE: {
+                double sn, cs;
+                sincos(m.c1[ci] * dt, &sn, &cs);
+                const double e = exp(-m.c0[ci] * dt);
+                // exp(-c dt) * [[cos, -sin], [sin, cos]].T
+                T[0][0] = e * cs; T[0][1] = e * sn;
+                T[1][0] = e * -sn; T[1][1] = e * cs;
+                break;
+            }
+            default: {  // COSINE
+                double sn, cs;
+                sincos(m.c0[ci] * dt, &sn, &cs);
+                T[0][0] = cs; T[0][1] = sn;
+                T[1][0] = -sn; T[1][1] = cs;
+                break;
+            }
+        }
+        for (int r = 0; r < sz; ++r)
+            for (int s = 0; s < sz; ++s) al[(o + r) * J + (o + s)] = T[s][r];  // a = T^T
+    }
+#pragma unroll
+    for (int i = 0; i < J; ++i)
+#pragma unroll
+        for (int j = 0; j < J; ++j) a[i][j] = al[i * J + j];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {  // p = h a
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < J; ++i) s += m.h[i] * a[i][j];
+        p[j] = s;
+    }
+}
+
+// small dense helpers ---------------------------------------------------------------------------
+template <int J>
+__host__ __device__ __forceinline__ void matmul(const double (&x)[J][J], const double (&y)[J][J], double (&o)[J][J]) {
+#pragma unroll
+    for (int i = 0; i < J; ++i)
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < J; ++k) s += x[i][k] * y[k][j];
+            o[i][j] = s;
+        }
+}
+template <int J>
+__host__ __device__ __forceinline__ void matmul_nt(const double (&x)[J][J], const double (&y)[J][J], double (&o)[J][J]) {
+#pragma unroll
+    for (int i = 0; i < J; ++i)
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < J; ++k) s += x[i][k] * y[j][k];
+            o[i][j] = s;
+        }
+}
+// solve M X = B in place (B overwritten by X); Gaussian elimination with partial pivoting
+template <int J>
+__host__ __device__ __forceinline__ void solve_inplace(double (&M)[J][J], double (&B)[J][J]) {
+#pragma unroll
+    for (int c = 0; c < J; ++c) {
+        int piv = c;
+        double best = fabs(M[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < J; ++r) {
+            const double v = fabs(M[r][c]);
+            if (v > best) { best = v; piv = r; }
+        }
+#pragma unroll
+        for (int r = c + 1; r < J; ++r) {
+            if (r == piv) {
+#pragma unroll
+                for (int k = 0; k < J; ++k) {
+                    double tmp = M[c][k]; M[c][k] = M[r][k]; M[r][k] = tmp;
+                    tmp = B[c][k]; B[c][k] = B[r][k]; B[r][k] = tmp;
+                }
+            }
+        }
+        const double inv = 1.0 / M[c][c];
+#pragma unroll
+        for (int r = c + 1; r < J; ++r) {
+            const double f = M[r][c] * inv;
+#pragma unroll
+            for (int k = 0; k < J; ++k) {
+                M[r][k] -= f * M[c][k];
+                B[r][k] -= f * B[c][k];
+            }
+        }
+    }
+#pragma unroll
+    for (int c = J - 1; c >= 0; --c) {
+        const double inv = 1.0 / M[c][c];
+#pragma unroll
+        for (int k = 0; k < J; ++k) {
+            double s = B[c][k];
+#pragma unroll
+            for (int r = c + 1; r < J; ++r) s -= M[c][r] * B[r][k];
+            B[c][k] = s * inv;
+        }
+    }
+}
+
+template <int J>
+__host__ __device__ __forceinline__ void ldrow(const double* __restrict__ p, int64_t k, double (&v)[J]) {
+    if (J == 4 && ((reinterpret_cast<uintptr_t>(p + k * J) & 31) == 0)) {
+        const double4 q = *reinterpret_cast<const double4*>(p + k * J);
+        v[0] = q.x; v[1 % J] = q.y; v[2 % J] = q.z; v[3 % J] = q.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) v[j] = p[k * J + j];
+    }
+}
+template <int J>
+__host__ __device__ __forceinline__ void strow(double* p, int64_t k, const double (&v)[J]) {
+    if (J == 4 && ((reinterpret_cast<uintptr_t>(p + k * J) & 31) == 0)) {
+        *reinterpret_cast<double4*>(p + k * J) = make_double4(v[0], v[1 % J], v[2 % J], v[3 % J]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) p[k * J + j] = v[j];
+    }
+}
+
+
+// Backward second-moment recursion  T <- B^T T B + U  (T, U symmetric J x J).  Used for diag((L L^T)^-1): with the
+// inverse factor L^-1 = LowerTriQSM(diag = 1/c, lower = (u, v, b)), u = -p/c, v = w/c, b = a - v p^T (core.py:310-317),
+//   (Sigma^-1)_ii = sum_{k >= i} (L^-1)_ki^2 = 1/c_i^2 + v_i^T S_i v_i ,   S_{i-1} = u_i u_i^T + b_i^T S_i b_i ,  S_{n-1} = 0
+// -- the diagonal of the gram of core.py:424-434 without forming the matrix.
+template <int J>
+struct GramBack {
+    static constexpr int SIZE = 2 * J * J;   // B, U
+    static constexpr int STATE = J * J;      // T
+    double B[J][J], U[J][J];
+    __host__ __device__ void identity() {
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) { B[i][j] = (i == j) ? 1.0 : 0.0; U[i][j] = 0.0; }
+    }
+    __host__ __device__ void load(const double* buf, int64_t count, int64_t i) {
+#pragma unroll
+        for (int e = 0; e < J * J; ++e) {
+            B[e / J][e % J] = buf[(int64_t)e * count + i];
+            U[e / J][e % J] = buf[(int64_t)(J * J + e) * count + i];
+        }
+    }
+    __host__ __device__ void store(double* buf, int64_t count, int64_t i) const {
+#pragma unroll
+        for (int e = 0; e < J * J; ++e) {
+            buf[(int64_t)e * count + i] = B[e / J][e % J];
+            buf[(int64_t)(J * J + e) * count + i] = U[e / J][e % J];
+        }
+    }
+    // one point appended on the right of this composite:  U <- b^T U b + u u^T ;  B <- B b
+    __host__ __device__ void push(const double (&b)[J][J], const double (&u)[J]) {
+        double T1[J][J], nB[J][J];
+        matmul<J>(U, b, T1);             // U b
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                double acc = u[i] * u[j];
+#pragma unroll
+                for (int k = 0; k < J; ++k) acc += b[k][i] * T1[k][j];   // b^T (U b)
+                U[i][j] = acc;
+            }
+        matmul<J>(B, b, nB);
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) B[i][j] = nB[i][j];
+    }
+    // this (applied first) followed by r:  U <- B_r^T U B_r + U_r ;  B <- B B_r
+    __host__ __device__ void combine(const GramBack& r) {
+        double T1[J][J], nB[J][J];
+        matmul<J>(U, r.B, T1);
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                double acc = r.U[i][j];
+#pragma unroll
+                for (int k = 0; k < J; ++k) acc += r.B[k][i] * T1[k][j];
+                U[i][j] = acc;
+            }
+        matmul<J>(B, r.B, nB);
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) B[i][j] = nB[i][j];
+    }
+    __host__ __device__ void apply(double (&T)[J][J]) const {   // T <- B^T T B + U
+        double T1[J][J];
+        matmul<J>(T, B, T1);
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                double acc = U[i][j];
+#pragma unroll
+                for (int k = 0; k < J; ++k) acc += B[k][i] * T1[k][j];
+                T[i][j] = acc;
+            }
+    }
+};
+
+
+// ---------------------------------------------------------------------------------------------
+// diag((L L^T)^-1) by a backward scan (see GramBack): logical position l is physical point n-1-l
+// ---------------------------------------------------------------------------------------------
+template <int J>
+__host__ __device__ __forceinline__ void inv_factor_gen(const QsModel& m, const double* __restrict__ t, const double* __restrict__ c,
+                                               const double* __restrict__ w, int64_t k, double& g, double (&u)[J],
+                                               double (&v)[J], double (&b)[J][J]) {
+    const double dt = (k == 0) ? 0.0 : (t[k] - t[k - 1]);
+    double a[J][J], p[J], wk[J];
+    qs_gen<J>(m, dt, a, p);
+    ldrow<J>(w, k, wk);
+    g = 1.0 / c[k];
+#pragma unroll
+    for (int i = 0; i < J; ++i) { u[i] = -g * p[i]; v[i] = g * wk[i]; }
+#pragma unroll
+    for (int i = 0; i < J; ++i)
+#pragma unroll
+        for (int j = 0; j < J; ++j) b[i][j] = a[i][j] - v[i] * p[j];
+}
+
+template <int J>
+__host__ __device__ __forceinline__ void gram_chunk_body(const QsModel& m, const double* __restrict__ t,
+                                                         const double* __restrict__ c, const double* __restrict__ w,
+                                                         int64_t n, double* comp, int64_t nchunks, int64_t ch) {
+    const int64_t l0 = ch * m.chunk, l1 = (l0 + m.chunk < n) ? (l0 + m.chunk) : n;
+    GramBack<J> R;
+    R.identity();
+    for (int64_t l = l0; l < l1; ++l) {
+        double g, u[J], v[J], b[J][J];
+        inv_factor_gen<J>(m, t, c, w, n - 1 - l, g, u, v, b);
+        R.push(b, u);
+    }
+    R.store(comp, nchunks, ch);
+}
+
+template <int J>
+__host__ __device__ __forceinline__ void gram_replay_body(const QsModel& m, const double* __restrict__ t,
+                                                          const double* __restrict__ c, const double* __restrict__ w,
+                                                          int64_t n, const double* tstart, int64_t nchunks, double* out,
+                                                          int64_t ch) {
+    const int64_t l0 = ch * m.chunk, l1 = (l0 + m.chunk < n) ? (l0 + m.chunk) : n;
+    double T[J][J];
+    #pragma unroll
+    for (int e = 0; e < J * J; ++e) T[e / J][e % J] = tstart[(int64_t)e * nchunks + ch];
+    for (int64_t l = l0; l < l1; ++l) {
+        const int64_t k = n - 1 - l;
+        double g, u[J], v[J], b[J][J];
+        inv_factor_gen<J>(m, t, c, w, k, g, u, v, b);
+        double acc = g * g;
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            double r = 0.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) r += T[i][j] * v[j];
+            acc += v[i] * r;
+        }
+        out[k] = acc;
+        double T1[J][J];
+        matmul<J>(T, b, T1);
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                double r = u[i] * u[j];
+#pragma unroll
+                for (int kk = 0; kk < J; ++kk) r += b[kk][i] * T1[kk][j];
+                T[i][j] = r;
+            }
+    }
+}
+

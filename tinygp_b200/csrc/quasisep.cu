@@ -19,22 +19,9 @@
 // HBM traffic per point: read t, diag (and y) ; write c, w  -- 8(3 + 1 + J) bytes for log_probability.
 #include "common.cuh"
 #include <limits.h>
+#include "qs_core.cuh"
 
 #define QS_CHUNK 64
-#define TREE_R 16
-#define QS_THREADS 128
-
-struct QsModel {
-    int ncomp, J;
-    int chunk;   // points per thread (runtime tunable, option "qs_chunk")
-    int kind[B200GP_QS_MAX_COMP];
-    int off[B200GP_QS_MAX_COMP];
-    int mode[B200GP_QS_MAX_COMP];  // SHO: 0 critical, 1 underdamped, 2 overdamped
-    double c0[B200GP_QS_MAX_COMP], c1[B200GP_QS_MAX_COMP], c2[B200GP_QS_MAX_COMP];
-    double h[B200GP_QS_MAX_J];  // observation model (constant for all supported kernels)
-    double q[B200GP_QS_MAX_J];  // h Pinf
-    double d0;                  // h Pinf h
-};
 
 struct b200gp_qs {
     b200gp_ctx* ctx = nullptr;
@@ -51,249 +38,6 @@ struct b200gp_qs {
     double* fused_comp = nullptr;
     size_t fused_comp_bytes = 0;
 };
-
-// ---------------------------------------------------------------------------------------------
-// host: lower the component list to a QsModel (constants follow kernels/quasisep.py)
-// ---------------------------------------------------------------------------------------------
-static QsModel build_model(const double* comps, int ncomp) {
-    if (ncomp <= 0 || ncomp > B200GP_QS_MAX_COMP) throw GpError("quasisep: bad component count");
-    QsModel m{};
-    m.ncomp = ncomp;
-    int J = 0;
-    double Pinf[B200GP_QS_MAX_J][B200GP_QS_MAX_J] = {};
-    for (int i = 0; i < ncomp; ++i) {
-        const double* cc = comps + (size_t)i * B200GP_QS_STRIDE;
-        const int kind = (int)cc[0];
-        const double ps = cc[1], p0 = cc[2], p1 = cc[3], p2 = cc[4], p3 = cc[5];
-        int sz;
-        switch (kind) {
-            case B200GP_QS_EXP: sz = 1; break;
-            case B200GP_QS_MATERN52: sz = 3; break;
-            case B200GP_QS_MATERN32: case B200GP_QS_SHO: case B200GP_QS_CELERITE: case B200GP_QS_COSINE: sz = 2; break;
-            default: throw GpError("quasisep: unknown component kind");
-        }
-        if (J + sz > B200GP_QS_MAX_J) throw GpError("quasisep: state dimension exceeds 8");
-        m.kind[i] = kind;
-        m.off[i] = J;
-        double P[3][3] = {};
-        double h[3] = {0, 0, 0};
-        switch (kind) {
-            case B200GP_QS_EXP:  // quasisep.py:491-525
-                m.c0[i] = p0; h[0] = p1; P[0][0] = 1.0; break;
-            case B200GP_QS_MATERN32: {  // quasisep.py:528-569
-                const double f = sqrt(3.0) / p0;
-                m.c0[i] = f; m.c1[i] = f * f; h[0] = p1;
-                P[0][0] = 1.0; P[1][1] = 3.0 / (p0 * p0); break;
-            }
-            case B200GP_QS_MATERN52: {  // quasisep.py:572-633
-                const double f = sqrt(5.0) / p0, f2 = f * f, f2o3 = f2 / 3.0;
-                m.c0[i] = f; m.c1[i] = f2; h[0] = p1;
-                P[0][0] = 1.0; P[0][2] = -f2o3; P[1][1] = f2o3; P[2][0] = -f2o3; P[2][2] = f2 * f2; break;
-            }
-            case B200GP_QS_SHO: {  // quasisep.py:404-488
-                const double w = p0, q = p1;
-                m.c0[i] = w; m.c1[i] = q; h[0] = p2;
-                P[0][0] = 1.0; P[1][1] = w * w;
-                if (fabs(q - 0.5) <= 1e-8 + 1e-5 * 0.5) {  // jnp.allclose(q, 0.5)
-                    m.mode[i] = 0;
-                } else if (q > 0.5) {
-                    m.mode[i] = 1; m.c2[i] = sqrt(fmax(4.0 * (q * q) - 1.0, 0.0));
-                } else {
-                    m.mode[i] = 2; m.c2[i] = sqrt(fmax(1.0 - 4.0 * (q * q), 0.0));
-                }
-                break;
-            }
-            case B200GP_QS_CELERITE: {  // quasisep.py:343-401
-                const double a = p0, b = p1, c = p2, d = p3;
-                const double c2 = c * c, d2 = d * d, s2 = c2 + d2;
-                const double h2_2 = d2 * (a * c - b * d) / (2.0 * c * s2);
-                const double h2 = sqrt(h2_2);
-                const double h1 = (c * h2 - sqrt(a * d2 - s2 * h2_2)) / d;
-                m.c0[i] = c; m.c1[i] = d; h[0] = h1; h[1] = h2;
-                P[0][0] = 1.0; P[0][1] = P[1][0] = -c / d; P[1][1] = 1.0 + 2.0 * c2 / d2; break;
-            }
-            case B200GP_QS_COSINE:  // quasisep.py:636-673
-                m.c0[i] = 2.0 * M_PI / p0; h[0] = p1; P[0][0] = P[1][1] = 1.0; break;
-        }
-        for (int r = 0; r < sz; ++r) {
-            m.h[J + r] = h[r];
-            for (int s = 0; s < sz; ++s) Pinf[J + r][J + s] = ps * P[r][s];  // Scale: quasisep.py:334-340
-        }
-        J += sz;
-    }
-    m.J = J;
-    m.d0 = 0.0;
-    for (int j = 0; j < J; ++j) {  // q = h Pinf ; d = sum(hP * h)   (quasisep.py:109-111)
-        double s = 0.0;
-        for (int i = 0; i < J; ++i) s += m.h[i] * Pinf[i][j];
-        m.q[j] = s;
-    }
-    for (int j = 0; j < J; ++j) m.d0 += m.q[j] * m.h[j];
-    return m;
-}
-
-// ---------------------------------------------------------------------------------------------
-// device: per-point generators  a = T(t_{k-1}, t_k)^T,  p = h a      (quasisep.py:102-116)
-// ---------------------------------------------------------------------------------------------
-template <int J>
-__device__ __forceinline__ void qs_gen(const QsModel& m, const double dt, double (&a)[J][J], double (&p)[J]) {
-    double al[J * J];  // scratch with runtime offsets; copied to registers below
-#pragma unroll
-    for (int i = 0; i < J * J; ++i) al[i] = 0.0;
-    for (int ci = 0; ci < m.ncomp; ++ci) {
-        const int o = m.off[ci];
-        double T[3][3];  // transition_matrix(X1, X2) as written in the reference
-        int sz = 2;
-        switch (m.kind[ci]) {
-            case B200GP_QS_EXP:
-                sz = 1;
-                T[0][0] = exp(-dt / m.c0[ci]);
-                break;
-            case B200GP_QS_MATERN32: {
-                const double f = m.c0[ci], e = exp(-f * dt);
-                T[0][0] = e * (1.0 + f * dt); T[0][1] = e * (-m.c1[ci] * dt);
-                T[1][0] = e * dt;             T[1][1] = e * (1.0 - f * dt);
-                break;
-            }
-            case B200GP_QS_MATERN52: {
-                sz = 3;
-                const double f = m.c0[ci], f2 = m.c1[ci], d2 = dt * dt, e = exp(-f * dt);
-                T[0][0] = e * (0.5 * f2 * d2 + f * dt + 1.0);
-                T[0][1] = e * (-0.5 * f * f2 * d2);
-                T[0][2] = e * (0.5 * f2 * f * dt * (f * dt - 2.0));
-                T[1][0] = e * (dt * (f * dt + 1.0));
-                T[1][1] = e * (-f2 * d2 + f * dt + 1.0);
-                T[1][2] = e * (f2 * dt * (f * dt - 3.0));
-                T[2][0] = e * (0.5 * d2);
-                T[2][1] = e * (0.5 * dt * (2.0 - f * dt));
-                T[2][2] = e * (0.5 * f2 * d2 - 2.0 * f * dt + 1.0);
-                break;
-            }
-            case B200GP_QS_SHO: {
-                const double w = m.c0[ci], q = m.c1[ci];
-                if (m.mode[ci] == 0) {
-                    const double e = exp(-w * dt);
-                    T[0][0] = e * (1.0 + w * dt); T[0][1] = e * (-(w * w) * dt);
-                    T[1][0] = e * dt;             T[1][1] = e * (1.0 - w * dt);
-                } else {
-                    const double f = m.c2[ci];
-                    const double arg = 0.5 * f * w * dt / q;
-                    const double e = exp(-0.5 * w * dt / q);
-                    double sn, cs;
-                    if (m.mode[ci] == 1) {
-                        sincos(arg, &sn, &cs);
-                    } else {
-                        sn = sinh(arg);
-                        cs = cosh(arg);
-                    }
-                    T[0][0] = e * (cs + sn / f);           T[0][1] = e * (-2.0 * q * w * sn / f);
-                    T[1][0] = e * (2.0 * q * sn / (w * f)); T[1][1] = e * (cs - sn / f);
-                }
-                break;
-            }
-            case B200GP_QS_CELERITE: {
-                double sn, cs;
-                sincos(m.c1[ci] * dt, &sn, &cs);
-                const double e = exp(-m.c0[ci] * dt);
-                // exp(-c dt) * [[cos, -sin], [sin, cos]].T
-                T[0][0] = e * cs; T[0][1] = e * sn;
-                T[1][0] = e * -sn; T[1][1] = e * cs;
-                break;
-            }
-            default: {  // COSINE
-                double sn, cs;
-                sincos(m.c0[ci] * dt, &sn, &cs);
-                T[0][0] = cs; T[0][1] = sn;
-                T[1][0] = -sn; T[1][1] = cs;
-                break;
-            }
-        }
-        for (int r = 0; r < sz; ++r)
-            for (int s = 0; s < sz; ++s) al[(o + r) * J + (o + s)] = T[s][r];  // a = T^T
-    }
-#pragma unroll
-    for (int i = 0; i < J; ++i)
-#pragma unroll
-        for (int j = 0; j < J; ++j) a[i][j] = al[i * J + j];
-#pragma unroll
-    for (int j = 0; j < J; ++j) {  // p = h a
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < J; ++i) s += m.h[i] * a[i][j];
-        p[j] = s;
-    }
-}
-
-// small dense helpers ---------------------------------------------------------------------------
-template <int J>
-__device__ __forceinline__ void matmul(const double (&x)[J][J], const double (&y)[J][J], double (&o)[J][J]) {
-#pragma unroll
-    for (int i = 0; i < J; ++i)
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < J; ++k) s += x[i][k] * y[k][j];
-            o[i][j] = s;
-        }
-}
-template <int J>
-__device__ __forceinline__ void matmul_nt(const double (&x)[J][J], const double (&y)[J][J], double (&o)[J][J]) {
-#pragma unroll
-    for (int i = 0; i < J; ++i)
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < J; ++k) s += x[i][k] * y[j][k];
-            o[i][j] = s;
-        }
-}
-// solve M X = B in place (B overwritten by X); Gaussian elimination with partial pivoting
-template <int J>
-__device__ __forceinline__ void solve_inplace(double (&M)[J][J], double (&B)[J][J]) {
-#pragma unroll
-    for (int c = 0; c < J; ++c) {
-        int piv = c;
-        double best = fabs(M[c][c]);
-#pragma unroll
-        for (int r = c + 1; r < J; ++r) {
-            const double v = fabs(M[r][c]);
-            if (v > best) { best = v; piv = r; }
-        }
-#pragma unroll
-        for (int r = c + 1; r < J; ++r) {
-            if (r == piv) {
-#pragma unroll
-                for (int k = 0; k < J; ++k) {
-                    double tmp = M[c][k]; M[c][k] = M[r][k]; M[r][k] = tmp;
-                    tmp = B[c][k]; B[c][k] = B[r][k]; B[r][k] = tmp;
-                }
-            }
-        }
-        const double inv = 1.0 / M[c][c];
-#pragma unroll
-        for (int r = c + 1; r < J; ++r) {
-            const double f = M[r][c] * inv;
-#pragma unroll
-            for (int k = 0; k < J; ++k) {
-                M[r][k] -= f * M[c][k];
-                B[r][k] -= f * B[c][k];
-            }
-        }
-    }
-#pragma unroll
-    for (int c = J - 1; c >= 0; --c) {
-        const double inv = 1.0 / M[c][c];
-#pragma unroll
-        for (int k = 0; k < J; ++k) {
-            double s = B[c][k];
-#pragma unroll
-            for (int r = c + 1; r < J; ++r) s -= M[c][r] * B[r][k];
-            B[c][k] = s * inv;
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // scan monoids.  Storage is structure-of-arrays: element e of item i at buf[e * count + i].
@@ -480,6 +224,7 @@ template <int J> __device__ __forceinline__ void state_zero(double (&g)[J]) {
 template <class Op> struct StateOf;
 template <int J> struct StateOf<Riccati<J>> { typedef double type[J][J]; };
 template <int J> struct StateOf<Affine<J>> { typedef double type[J]; };
+template <int J> struct StateOf<GramBack<J>> { typedef double type[J][J]; };
 
 // up-sweep: parent[i] = fold of child[i*R .. i*R+R-1]
 template <class Op>
@@ -552,26 +297,6 @@ __device__ __forceinline__ void st4(double* p, int64_t kb, int64_t k1, const dou
             if (kb + u < k1) p[kb + u] = v[u];
     }
 }
-template <int J>
-__device__ __forceinline__ void ldrow(const double* __restrict__ p, int64_t k, double (&v)[J]) {
-    if (J == 4 && ((reinterpret_cast<uintptr_t>(p + k * J) & 31) == 0)) {
-        const double4 q = *reinterpret_cast<const double4*>(p + k * J);
-        v[0] = q.x; v[1 % J] = q.y; v[2 % J] = q.z; v[3 % J] = q.w;
-    } else {
-#pragma unroll
-        for (int j = 0; j < J; ++j) v[j] = p[k * J + j];
-    }
-}
-template <int J>
-__device__ __forceinline__ void strow(double* p, int64_t k, const double (&v)[J]) {
-    if (J == 4 && ((reinterpret_cast<uintptr_t>(p + k * J) & 31) == 0)) {
-        *reinterpret_cast<double4*>(p + k * J) = make_double4(v[0], v[1 % J], v[2 % J], v[3 % J]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < J; ++j) p[k * J + j] = v[j];
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Cholesky: chunk composites and replay
 // ---------------------------------------------------------------------------------------------
@@ -970,6 +695,24 @@ __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_
     if (sq_part) sq_part[ch] = ssum;
 }
 
+// ---------------------------------------------------------------------------------------------
+// diag((L L^T)^-1) by a backward scan: bodies in qs_core.cuh (shared with the host check in tests/csrc)
+// ---------------------------------------------------------------------------------------------
+template <int J>
+__global__ void __launch_bounds__(QS_THREADS) gram_chunk_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
+                                                                const double* __restrict__ c, const double* __restrict__ w,
+                                                                int64_t n, double* comp, int64_t nchunks) {
+    const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < nchunks) gram_chunk_body<J>(m, t, c, w, n, comp, nchunks, ch);
+}
+template <int J>
+__global__ void __launch_bounds__(QS_THREADS) gram_replay_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
+                                                                 const double* __restrict__ c, const double* __restrict__ w,
+                                                                 int64_t n, const double* tstart, int64_t nchunks, double* out) {
+    const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < nchunks) gram_replay_body<J>(m, t, c, w, n, tstart, nchunks, out, ch);
+}
+
 // misc kernels -----------------------------------------------------------------------------------
 __global__ void sorted_check_kernel(const double* t, int64_t n, int* flag) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1189,6 +932,24 @@ static void qs_affine(b200gp_qs* s, int op, const double* x, double* out, double
         case OP_GEN_UPPER: QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_GEN_UPPER>(s, x, out, sumsq_dev))) break;
         default: throw GpError("quasisep: bad op");
     }
+}
+
+template <int J>
+static void qs_inv_diag_J(b200gp_qs* s, double* out_dev) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t n = s->n, nch = (n + s->model.chunk - 1) / s->model.chunk;
+    const size_t cb = (size_t)GramBack<J>::SIZE * nch * 8, sb = (size_t)J * J * nch * 8;
+    double* comp = (double*)ctx->alloc(cb);
+    double* tstart = (double*)ctx->alloc(sb);
+    gram_chunk_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->c, s->w, n, comp, nch);
+    ctx->launches++;
+    run_tree<GramBack<J>>(ctx, comp, nch, tstart);
+    gram_replay_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->c, s->w, n, tstart, nch,
+                                                                               out_dev);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+    ctx->release(comp, cb);
+    ctx->release(tstart, sb);
 }
 
 static void qs_destroy(b200gp_qs* s) {
@@ -1496,6 +1257,60 @@ int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, con
     s.t = nullptr;
     _ctx->release(t2, nb8); _ctx->release(t1, mb8); _ctx->release(yh, nb8 * nrhs); _ctx->release(x, nb8);
     _ctx->release(F, sb); _ctx->release(G, sb); _ctx->release(o, mb8 * nrhs);
+    API_END
+}
+
+// diag((K + N)^-1) in O(n J^3): the diagonal of (factor.inv()).gram() (core.py:310-317, 424-434) by one backward
+// scan, without forming the matrix.  With it the conditioned variance at the inputs (solver.py:124-129 followed by
+// solver.py:84-85) is  noise* + N - N^2 diag((K + N)^-1)  -- what gp.predict(y, return_var=True) needs at N = 10^7.
+int b200gp_qs_inverse_diagonal(b200gp_qs* s, double* out) {
+    API_BEGIN(s->ctx)
+    if (s->info != 0) throw GpError("qs_inverse_diagonal: the factorisation failed (matrix not positive definite)");
+    const size_t nb = (size_t)s->n * 8;
+    double* o = (double*)_ctx->alloc(nb);
+    {
+        ProfTimer tm(_ctx, &_ctx->prof.qs_ms);
+        _ctx->prof.qs_launches++;
+        _ctx->prof.qs_bytes += 8.0 * (double)s->n * (2.0 * (2.0 + s->J) + 1.0);  // two passes read t, c, w ; write out
+        QS_DISPATCH_J(s->J, (qs_inv_diag_J<JJ>(s, o)))
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out, o, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(o, nb);
+    API_END
+}
+
+__global__ void conditioned_variance_kernel(const double* __restrict__ inv_diag, const double* __restrict__ noise,
+                                            const double* __restrict__ noise_pred, int64_t n, double* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = noise_pred[i] + (noise[i] - noise[i] * noise[i] * inv_diag[i]);
+}
+
+// Variance of the process conditioned on the data, at the inputs, for the solver's own kernel: the diagonal of
+// solver.py:124-129 (`M + noise* - (factor.inv() @ M).gram()`) as read by solver.py:84-85.  With Sigma = K + N and
+// M = K = Sigma - N:  K - K Sigma^-1 K = N - N Sigma^-1 N, so the diagonal is  noise* + N - N^2 diag(Sigma^-1)  -- one
+// backward scan, O(n J^3), no n x n matrix (what gp.predict(y, return_var=True) needs for a 10^7-point series).
+int b200gp_qs_conditioned_variance(b200gp_qs* s, const double* noise_pred, double* out) {
+    API_BEGIN(s->ctx)
+    if (s->info != 0) throw GpError("qs_conditioned_variance: the factorisation failed (matrix not positive definite)");
+    const int64_t n = s->n;
+    const size_t nb = (size_t)n * 8;
+    double* o = (double*)_ctx->alloc(nb);
+    double* np_ = (double*)_ctx->alloc(nb);
+    CUDA_CHECK(cudaMemcpyAsync(np_, noise_pred, nb, cudaMemcpyHostToDevice, _ctx->stream));
+    {
+        ProfTimer tm(_ctx, &_ctx->prof.qs_ms);
+        _ctx->prof.qs_launches++;
+        _ctx->prof.qs_bytes += 8.0 * (double)n * (2.0 * (2.0 + s->J) + 4.0);
+        QS_DISPATCH_J(s->J, (qs_inv_diag_J<JJ>(s, o)))
+        conditioned_variance_kernel<<<nblk(n, 256), 256, 0, _ctx->stream>>>(o, s->diag, np_, n, o);
+        _ctx->launches++;
+        CUDA_CHECK(cudaGetLastError());
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out, o, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    _ctx->release(o, nb);
+    _ctx->release(np_, nb);
     API_END
 }
 

@@ -94,6 +94,12 @@ class GaussianProcess:
         if not (return_var or return_cov):
             self._check_X_test(X_test)
             return self._condition(y, X_test, include_mean, kernel)[2]
+        if return_var and X_test is None and kernel is None and hasattr(self.solver, "conditioned_variance"):
+            # QuasisepSolver at the inputs: the reference's QSM branch (solver.py:124-129) keeps this O(N); so does the
+            # backward scan behind conditioned_variance -- same values as cond.variance below
+            mean_value = self._condition(y, None, include_mean, None)[2]
+            noise = Diagonal(diag=np.full(mean_value.shape, _default_diag(mean_value)))
+            return mean_value, self.solver.conditioned_variance(noise)
         _, cond = self.condition(y, X_test, kernel=kernel, include_mean=include_mean)
         if return_var:
             return cond.loc, cond.variance

@@ -107,6 +107,22 @@ class QuasisepSolver(Solver):
                                                                _cabi.ptr(a)))
         return d, p, q, a
 
+    def inverse_diagonal(self):
+        """diag((K + N)^-1): the diagonal of ``factor.inv().gram()`` (core.py:310-317, 424-434) by one backward scan."""
+        out = np.empty(self._n)
+        self._ctx.check(self._ctx.lib.b200gp_qs_inverse_diagonal(self._h, _cabi.ptr(out)))
+        return out
+
+    def conditioned_variance(self, noise):
+        """Variance of the conditioned process at the inputs for this solver's kernel -- the diagonal of
+        solver.py:124-129 as solver.py:84-85 reads it -- in O(N) on the device (no N x N matrix)."""
+        diag = _cabi.f64(noise.diagonal())
+        if diag.shape != (self._n,):
+            raise ValueError("noise diagonal must match the number of predicted points")
+        out = np.empty(self._n)
+        self._ctx.check(self._ctx.lib.b200gp_qs_conditioned_variance(self._h, _cabi.ptr(diag), _cabi.ptr(out)))
+        return out
+
     def condition(self, kernel, X_test, noise) -> Any:
         """solver.py:104-139: ``Kss [+ noise] - A^T A`` with ``A = factor.solve(Ks)`` -- computed entirely on the
         device by ``b200gp_qs_condition`` (build kernel for ``Ks^T`` from the predictive kernel's program, one

@@ -64,8 +64,10 @@ def test_large_series_smoothing_variance_is_linear_time():
     assert mu.shape == var.shape == (n,) and np.all(np.isfinite(var))
     prior = 1.8 ** 2 + 0.9 ** 2
     assert var.min() > 0.0 and var.max() < prior + 1e-6
-    lo, hi = n // 2 - 1500, n // 2 + 1500                       # 3000 points ~ 375 time units >> all time scales
-    muw, varw = o.GaussianProcess(to_oracle(k), t[lo:hi], diag=noise[lo:hi]).predict(y[lo:hi], return_var=True)
+    # a 3000-point window (~375 time units >> every time scale of the kernel) treated as its own GP -- the small-N path,
+    # whose parity with the oracle is the test above -- must agree with the full series away from the window's ends
+    lo, hi = n // 2 - 1500, n // 2 + 1500
+    muw, varw = GaussianProcess(k, t[lo:hi], diag=noise[lo:hi]).predict(y[lo:hi], return_var=True)
     mid = slice(1000, 2000)
     np.testing.assert_allclose(var[lo:hi][mid], varw[mid], rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(mu[lo:hi][mid], muw[mid], rtol=1e-6, atol=1e-8)

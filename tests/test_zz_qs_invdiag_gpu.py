@@ -46,7 +46,7 @@ def test_inverse_diagonal_parity(name, n):
 @pytest.mark.parametrize("name", list(KERNELS))
 def test_predict_variance_at_the_inputs_is_the_reference_qsm_branch(name):
     """gp.predict(y, return_var=True): solver.py:124-129 read by :84-85, here by one backward scan"""
-    t, y, noise = _data(300)
+    t, y, noise = _data(200)
     mu, var = GaussianProcess(KERNELS[name], t, diag=noise).predict(y, return_var=True)
     muo, varo = o.GaussianProcess(to_oracle(KERNELS[name]), t, diag=noise).predict(y, return_var=True)
     np.testing.assert_allclose(mu, muo, rtol=5e-7, atol=5e-7)

@@ -98,3 +98,92 @@ def test_inverse_diagonal_scan_matches_the_oracle(lib, name, n, chunk):
         Z = s.solve_triangular(s.solve_triangular(E), transpose=True)      # Sigma^-1 e_i
         want, out = Z[idx, np.arange(idx.size)], out[idx]
     np.testing.assert_allclose(out, want, rtol=1e-10, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# dense path: the kernel-program interpreter (kprog.cuh) on the CPU against the REFERENCE's kernel values
+# ------------------------------------------------------------------------------------------------
+KSRC = os.path.join(HERE, "csrc", "kprog_hostcheck.cu")
+KOUT = os.path.join(HERE, "csrc", "_build", "libkprog_hostcheck.so")
+KDEPS = [KSRC, os.path.join(HERE, "..", "tinygp_b200", "csrc", "kprog.cuh"),
+         os.path.join(HERE, "..", "tinygp_b200", "csrc", "common.cuh"), os.path.join(HERE, "..", "include", "b200gp.h")]
+
+
+@pytest.fixture(scope="module")
+def klib():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    if not os.path.exists(KOUT) or any(os.path.getmtime(d) > os.path.getmtime(KOUT) for d in KDEPS):
+        os.makedirs(os.path.dirname(KOUT), exist_ok=True)
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-diag-suppress", "20013",
+                        "-Xcompiler", "-fPIC", "-shared", "-o", KOUT, KSRC], check=True)
+    return ctypes.CDLL(KOUT)
+
+
+def _kmat(klib, k, X1, X2):
+    prog, x1 = k.lower_for(X1)
+    _, x2 = k.lower_for(X2)
+    out, err = np.empty((x1.shape[0], x2.shape[0])), ctypes.create_string_buffer(256)
+    rc = klib.hostcheck_kernel_matrix(_p(prog), prog.shape[0], _p(x1), ctypes.c_int64(x1.shape[0]), _p(x2),
+                                      ctypes.c_int64(x2.shape[0]), x1.shape[1], _p(out), err)
+    assert rc == 0, err.value
+    return out
+
+
+def _dense_cases():
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import refcases
+    return [c for c in refcases.CASES if c["kind"] == "dense"], refcases
+
+
+@pytest.mark.parametrize("case", _dense_cases()[0], ids=[c["name"] for c in _dense_cases()[0]])
+def test_kernel_program_interpreter_reproduces_reference_kernel_values(klib, case):
+    """Kernel.__call__ (base.py:84-103) for every stationary leaf / distance default / sum / product / transform of the
+    golden set: host lowering (Kernel.lower_for) + the device interpreter source, against the reference's numbers"""
+    import json
+    from test_reference_golden import product_namespace
+    refcases = _dense_cases()[1]
+    gold = json.load(open(os.path.join(HERE, "golden", "reference_vectors.json")))["cases"][case["name"]]
+    if "K_cross" not in gold:
+        pytest.skip("non-PD case: the reference returned -inf before any kernel values were recorded")
+    inp = refcases._inputs(case)
+    k = product_namespace().kernel(case["kernel"])
+    idx = np.arange(0, case["n"], max(1, case["n"] // 9))[:9]
+    got = _kmat(klib, k, inp["X"][idx], inp["X_test"])
+    np.testing.assert_allclose(got, np.array(gold["K_cross"]), rtol=1e-13, atol=1e-15)
+    prog, x = k.lower_for(inp["X"][idx])
+    d, err = ctypes.c_double(), ctypes.create_string_buffer(256)
+    assert klib.hostcheck_kernel_diag(_p(prog), prog.shape[0], x.shape[1], ctypes.byref(d), err) == 0, err.value
+    np.testing.assert_allclose(np.full(idx.size, d.value), np.array(gold["K_diag"]), rtol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["sho+m32", "sho_critical", "sho_overdamped", "exp", "m52", "celerite", "cosine+exp",
+                                  "scaled_sum3"])
+def test_quasisep_closed_forms_through_the_interpreter(klib, name):
+    """dense evaluation of a quasiseparable kernel (kernels/quasisep.py:118-145) = its tau program in the same
+    interpreter, against the oracle's state-space evaluate"""
+    k, ko = KERNELS[name]
+    rng = np.random.default_rng(4)
+    t1, t2 = rng.uniform(0, 12, 9), rng.uniform(0, 12, 7)
+    t2[0] = t1[0]
+    np.testing.assert_allclose(_kmat(klib, k, t1, t2), ko(t1, t2), rtol=1e-12, atol=1e-14)
+
+
+def test_malformed_programs_are_rejected_by_the_parser(klib):
+    X = np.zeros((2, 2))
+    out, err = np.empty((2, 2)), ctypes.create_string_buffer(256)
+
+    def run(rows):
+        prog = np.ascontiguousarray(np.array(rows, dtype=np.float64))
+        return klib.hostcheck_kernel_matrix(_p(prog), prog.shape[0], _p(X), ctypes.c_int64(2), _p(X), ctypes.c_int64(2), 2,
+                                            _p(out), err), err.value.decode()
+
+    assert run([[2, 1, 1.0, 0]])[0] == 0
+    assert "stack underflow" in run([[16, 0, 0, 0]])[1]
+    assert "malformed" in run([[2, 1, 1.0, 0], [2, 1, 1.0, 0]])[1]
+    assert "unknown opcode" in run([[11, 0, 1.0, 0]])[1]
+    assert "undefined metric" in run([[2, 3, 1.0, 0]])[1]
+    assert "width does not match" in run([[32, 1, 1, 3], [1, 0, 0, 0], [2, 3, 1.0, 0]])[1]
+    assert "non-finite" in run([[32, 1, 1, 2], [np.nan, 0, 0, 0], [2, 3, 1.0, 0]])[1]

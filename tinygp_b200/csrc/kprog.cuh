@@ -1,0 +1,156 @@
+// The kernel-program interpreter (device side of Kernel.__call__, base.py:84-103): evaluation is __host__ __device__
+// so that tests/csrc/kprog_hostcheck.cu can run the SAME source on the CPU against the reference goldens.
+// Included by dense.cu (which exports parse_prog for the other translation units).
+#pragma once
+#include "common.cuh"
+
+#define MAX_NDIM 16
+#define SQRT3 1.7320508075688772
+#define SQRT5 2.23606797749979
+#define PI_D 3.141592653589793
+
+// l1 = sum_d |x1_d - x2_d| ; l2sq = sum_d (x1_d - x2_d)^2   (explicit differences, distance.py:45,59)
+// `diff(d)` returns x1_d - x2_d; it is re-evaluated (not cached in a register array) so that the DMMA
+// GEMM epilogue, which inlines this, keeps its register budget.  Leaves that carry a linear input
+// transform (transforms.py:57-161) measure their distance on M (x1 - x2).
+template <typename F>
+__host__ __device__ __forceinline__ double kprog_eval(const KProg& P, int ndim, F diff) {
+    double l1_id = 0.0, l2_id = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+        const double df = diff(d);
+        l1_id += fabs(df);
+        l2_id += df * df;
+    }
+    double st[8];
+    int sp = 0;
+    for (int i = 0; i < P.n; ++i) {
+        const int op = P.op[i];
+        if (op == B200GP_OP_ADD) {
+            --sp;
+            st[sp - 1] = st[sp - 1] + st[sp];
+            continue;
+        }
+        if (op == B200GP_OP_MUL) {
+            --sp;
+            st[sp - 1] = st[sp - 1] * st[sp];
+            continue;
+        }
+        const double p0 = P.p0[i], p1 = P.p1[i];
+        double v;
+        if (op == B200GP_OP_CONST) {
+            v = p0;
+        } else {
+            double l1 = l1_id, l2sq = l2_id;
+            const int m = P.metric[i];
+            if (m > 0) {
+                l1 = 0.0;
+                l2sq = 0.0;
+                const double* Mm = P.M[m - 1];
+                for (int r = 0; r < P.mrows[m - 1]; ++r) {
+                    double z = 0.0;
+                    for (int c = 0; c < ndim; ++c) z += Mm[r * B200GP_METRIC_MAX_DIM + c] * diff(c);
+                    l1 += fabs(z);
+                    l2sq += z * z;
+                }
+            }
+            const bool l2 = (P.dist[i] == B200GP_DIST_L2);
+            if (op == B200GP_OP_EXPSQUARED || op == B200GP_OP_RATIONALQUADRATIC) {
+                // squared_distance / square(scale)   (stationary.py:105,234 ; distance.py:30-38,58-59)
+                const double sq = l2 ? l2sq : l1 * l1;
+                const double r2 = sq / (p0 * p0);
+                if (op == B200GP_OP_EXPSQUARED)
+                    v = exp(-0.5 * r2);
+                else
+                    v = pow(1.0 + 0.5 * r2 / p1, -p1);
+            } else {
+                // distance (distance.py:44-45 / 51-56: sqrt with the r2==0 guard)
+                const double dist = l2 ? ((l2sq == 0.0) ? l1 : sqrt(l2sq)) : l1;
+                if (op == B200GP_OP_EXPCOS || op == B200GP_OP_EXPSIN) {
+                    double sn, cs;
+                    sincos(p1 * dist, &sn, &cs);
+                    st[sp++] = exp(-p0 * dist) * ((op == B200GP_OP_EXPCOS) ? cs : sn);
+                    continue;
+                }
+                const double r = dist / p0;
+                if (op == B200GP_OP_EXP) {
+                    v = exp(-r);
+                } else if (op == B200GP_OP_MATERN32) {
+                    const double arg = SQRT3 * r;
+                    v = (1.0 + arg) * exp(-arg);
+                } else if (op == B200GP_OP_MATERN52) {
+                    const double arg = SQRT5 * r;
+                    v = (1.0 + arg + arg * arg / 3.0) * exp(-arg);
+                } else if (op == B200GP_OP_COSINE) {
+                    v = cos(2.0 * PI_D * r);
+                } else {  // EXPSINESQUARED
+                    const double s = sin(PI_D * r);
+                    v = exp(-p1 * (s * s));
+                }
+            }
+        }
+        st[sp++] = v;
+    }
+    return st[0];
+}
+
+// k(x, x): every difference is zero, with or without a transform
+__host__ __device__ __forceinline__ double kprog_eval_zero(const KProg& P) {
+    return kprog_eval(P, 0, [](int) { return 0.0; });
+}
+
+// ndim < 0: the caller has no coordinates (k(x, x) only) and metrics are accepted for any width
+static inline KProg parse_prog_impl(const double* prog, int n_rows, int ndim) {
+    if (n_rows <= 0 || n_rows > B200GP_PROG_MAX_ROWS) throw GpError("kernel program: bad length");
+    KProg P{};
+    int depth = 0, row = 0;
+    // metric definitions come first
+    while (row < n_rows && (int)prog[(size_t)row * B200GP_PROG_STRIDE] == B200GP_OP_METRIC) {
+        const double* q = prog + (size_t)row * B200GP_PROG_STRIDE;
+        const int id = (int)q[1], r = (int)q[2], c = (int)q[3];
+        if (id != P.nmetric + 1 || id > B200GP_PROG_MAX_METRICS)
+            throw GpError("kernel program: metric ids must be 1..3 in order (at most 3 distinct input transforms)");
+        if (r < 1 || r > B200GP_METRIC_MAX_DIM || c < 1 || c > B200GP_METRIC_MAX_DIM)
+            throw GpError("kernel program: transformed kernels support at most 8 input / output dimensions");
+        if (ndim >= 0 && c != ndim) throw GpError("kernel program: transform width does not match ndim");
+        if (P.nmetric > 0 && c != P.mcols) throw GpError("kernel program: inconsistent transform widths");
+        const int nd_rows = (r * c + B200GP_PROG_STRIDE - 1) / B200GP_PROG_STRIDE;
+        if (row + 1 + nd_rows > n_rows) throw GpError("kernel program: truncated metric definition");
+        const double* data = q + B200GP_PROG_STRIDE;
+        for (int i = 0; i < r; ++i)
+            for (int j = 0; j < c; ++j) {
+                const double v = data[i * c + j];
+                if (!(v == v) || v - v != 0.0) throw GpError("kernel program: non-finite transform matrix");
+                P.M[id - 1][i * B200GP_METRIC_MAX_DIM + j] = v;
+            }
+        P.mrows[id - 1] = r;
+        P.mcols = c;
+        P.nmetric = id;
+        row += 1 + nd_rows;
+    }
+    const int n_instr = n_rows - row;
+    if (n_instr <= 0 || n_instr > B200GP_PROG_MAX_INSTR) throw GpError("kernel program: bad length");
+    P.n = n_instr;
+    for (int i = 0; i < n_instr; ++i) {
+        const double* q = prog + (size_t)(row + i) * B200GP_PROG_STRIDE;
+        P.op[i] = (int)q[0];
+        const int dcode = (int)q[1];
+        P.p0[i] = q[2];
+        P.p1[i] = q[3];
+        const int op = P.op[i];
+        if (op == B200GP_OP_ADD || op == B200GP_OP_MUL) {
+            if (depth < 2) throw GpError("kernel program: stack underflow");
+            --depth;
+        } else if (op >= B200GP_OP_CONST && op <= B200GP_OP_EXPSIN) {
+            if (dcode < 0 || (dcode >> 1) > P.nmetric) throw GpError("kernel program: leaf refers to an undefined metric");
+            P.dist[i] = dcode & 1;
+            P.metric[i] = (op == B200GP_OP_CONST) ? 0 : (dcode >> 1);
+            ++depth;
+            if (depth > 8) throw GpError("kernel program: expression too deep (max 8)");
+        } else {
+            throw GpError("kernel program: unknown opcode");
+        }
+    }
+    if (depth != 1) throw GpError("kernel program: malformed expression");
+    return P;
+}
+

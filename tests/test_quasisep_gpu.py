@@ -78,19 +78,6 @@ def test_logp_quasisep_equals_oracle_and_dense(name):
     assert lp2 == lp
 
 
-def test_condition_dense_branch():
-    # solver.py:131-139 via gp.condition with X_test
-    X, y, rng = _data(120)
-    Xt = np.sort(rng.uniform(-3, 3, 30))
-    k = Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9)
-    lp, cond = GaussianProcess(k, X, diag=0.1).condition(y, Xt)
-    ko = to_oracle(k)
-    lpo, condo = o.GaussianProcess(ko, X, diag=0.1).condition(y, Xt)
-    assert rel(lp, lpo) < LOGP_RTOL
-    np.testing.assert_allclose(cond.loc, condo.loc, rtol=5e-7, atol=5e-7)
-    np.testing.assert_allclose(cond.covariance, condo.covariance, rtol=5e-7, atol=5e-7)
-
-
 def test_unsorted_raises_and_ties_allowed(ctx):
     # test_solver.py:127-143 ; _check_sorted is a bit-exact boolean
     X, y, _ = _data(500)
@@ -187,18 +174,6 @@ def test_general_matmul_parity(name, n, m):
     np.testing.assert_allclose(k.matmul(X1, X2, Y), Kd @ Y, rtol=1e-9, atol=1e-10)
     if n <= 60:
         np.testing.assert_allclose(k.matmul(X2, y), ko(X2, X2) @ y, rtol=1e-9, atol=1e-10)   # symmetric form
-
-
-def test_predict_at_test_points_parity():
-    """gp.predict(y, X_test) through QuasisepSolver: mean by the O(n + m) general product (gp.py:357), variance by
-    the dense branch (solver.py:131-139) with the kernel evaluated on the device."""
-    X, y, rng = _data(200)
-    Xt = rng.uniform(-3.5, 3.5, 60)                  # unsorted, partly extrapolating
-    k = Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9)
-    mu, var = GaussianProcess(k, X, diag=0.1).predict(y, Xt, return_var=True)
-    muo, varo = o.GaussianProcess(to_oracle(k), X, diag=0.1).predict(y, Xt, return_var=True)
-    np.testing.assert_allclose(mu, muo, rtol=5e-7, atol=5e-7)
-    np.testing.assert_allclose(var, varo, rtol=5e-7, atol=5e-7)
 
 
 def test_general_matmul_large_consistency():

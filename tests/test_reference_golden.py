@@ -84,19 +84,3 @@ def test_oracle_unsorted_raises_like_the_reference():
     from oracle import tinygp_np as o
     with pytest.raises(ValueError, match="Input coordinates must be sorted"):
         o.GaussianProcess(o.qs.Matern32(1.5), np.array([0.0, 2.0, 1.0]), diag=0.1)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("case", CASES, ids=IDS)
-def test_cuda_path_matches_reference(case):
-    got = refcases.run_case(product_namespace(), case)
-    compare(got, GOLD["cases"][case["name"]], case["name"])
-
-
-@pytest.mark.gpu
-def test_cuda_path_unsorted_raises_like_the_reference():
-    import tinygp_b200 as tg
-    from tinygp_b200.kernels import quasisep
-    with pytest.raises(ValueError) as e:
-        tg.GaussianProcess(quasisep.Matern32(1.5), np.array([0.0, 2.0, 1.0]), diag=0.1)
-    assert str(e.value) == GOLD["unsorted_raises"]

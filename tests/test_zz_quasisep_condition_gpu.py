@@ -1,6 +1,8 @@
-"""diag((K + N)^-1) and the O(N) conditioned variance of the QuasisepSolver (GramBack backward scan, written after
-round 1's GPU minutes were spent: the same source passes on the CPU in tests/test_device_code_on_host.py; this file
-sorts last so that a launch-geometry problem here cannot hide the other GPU results under `pytest -x`)."""
+"""QuasisepSolver conditioning on the device: `b200gp_qs_condition` (build kernel + per-point scans + GEMM with generator
+epilogue) and diag((K + N)^-1) / the O(N) conditioned variance (GramBack backward scan).  Both were written after round
+1's GPU minutes were spent (the scan's source passes on the CPU in tests/test_device_code_on_host.py, the host layer in
+tests/test_host_layer_golden.py); this file sorts last so that a first-run problem here cannot hide the other GPU
+results under `pytest -x`."""
 
 import numpy as np
 import pytest
@@ -8,7 +10,7 @@ import pytest
 from oracle import tinygp_np as o
 from tinygp_b200 import GaussianProcess
 from tinygp_b200.kernels import quasisep as Q
-from util import to_oracle
+from util import LOGP_RTOL, rel, to_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -71,3 +73,34 @@ def test_large_series_smoothing_variance_is_linear_time():
     mid = slice(1000, 2000)
     np.testing.assert_allclose(var[lo:hi][mid], varw[mid], rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(mu[lo:hi][mid], muw[mid], rtol=1e-6, atol=1e-8)
+
+
+def _data_sorted(n, seed=84930):
+    rng = np.random.default_rng(seed)
+    X = np.sort(rng.uniform(-3, 3, n))
+    return X, np.sin(X), rng
+
+
+def test_condition_dense_branch():
+    # solver.py:131-139 via gp.condition with X_test
+    X, y, rng = _data_sorted(120)
+    Xt = np.sort(rng.uniform(-3, 3, 30))
+    k = Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9)
+    lp, cond = GaussianProcess(k, X, diag=0.1).condition(y, Xt)
+    ko = to_oracle(k)
+    lpo, condo = o.GaussianProcess(ko, X, diag=0.1).condition(y, Xt)
+    assert rel(lp, lpo) < LOGP_RTOL
+    np.testing.assert_allclose(cond.loc, condo.loc, rtol=5e-7, atol=5e-7)
+    np.testing.assert_allclose(cond.covariance, condo.covariance, rtol=5e-7, atol=5e-7)
+
+
+def test_predict_at_test_points_parity():
+    """gp.predict(y, X_test) through QuasisepSolver: mean by the O(n + m) general product (gp.py:357), variance by
+    the dense branch (solver.py:131-139) with the kernel evaluated on the device."""
+    X, y, rng = _data_sorted(200)
+    Xt = rng.uniform(-3.5, 3.5, 60)                  # unsorted, partly extrapolating
+    k = Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9)
+    mu, var = GaussianProcess(k, X, diag=0.1).predict(y, Xt, return_var=True)
+    muo, varo = o.GaussianProcess(to_oracle(k), X, diag=0.1).predict(y, Xt, return_var=True)
+    np.testing.assert_allclose(mu, muo, rtol=5e-7, atol=5e-7)
+    np.testing.assert_allclose(var, varo, rtol=5e-7, atol=5e-7)

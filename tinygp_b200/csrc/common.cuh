@@ -88,6 +88,18 @@ struct b200gp_ctx {
     void trim();                          // cudaFree everything cached
 };
 
+// RAII device scratch buffer from the context's cache: returned to it on scope exit, also when an error is thrown.
+struct Scratch {
+    b200gp_ctx* c;
+    size_t bytes;
+    void* p;
+    Scratch(b200gp_ctx* ctx, size_t nbytes) : c(ctx), bytes(nbytes), p(ctx->alloc(nbytes)) {}
+    ~Scratch() { c->release(p, bytes); }
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    double* f64() const { return static_cast<double*>(p); }
+};
+
 // RAII timer that accumulates into a profile field when ctx->profile is on.  It only records two
 // events on the stream (no host synchronisation); elapsed times are resolved by flush_timers().
 struct ProfTimer {

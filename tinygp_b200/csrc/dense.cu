@@ -1081,22 +1081,19 @@ void dense_conditioned_covariance_to_host(b200gp_ctx* ctx, const KProg& P, const
                                           double* out_host) {
     if (mp % TILE != 0 || kp % TILE != 0) throw GpError("conditioned covariance: operands must be padded to 128");
     const int tm = (int)(mp / TILE);
-    double* C = (double*)ctx->alloc((size_t)mp * mp * 8);
+    Scratch C(ctx, (size_t)mp * mp * 8), o(ctx, (size_t)m * m * 8);
     {
         gemm::Args g{};
-        g.A = At; g.lda = kp; g.B = At; g.ldb = kp; g.C = C; g.ldc = mp;
+        g.A = At; g.lda = kp; g.B = At; g.ldb = kp; g.C = C.f64(); g.ldc = mp;
         g.tiles_m = g.tiles_n = tm; g.K = (int)kp; g.alpha = -1.0; g.beta_mode = 2; g.lower = 0;
         g.X = xt_dev; g.diag = dt_dev; g.ndim = nd; g.n_valid = m; g.row0 = 0; g.col0 = 0;
         gemm::launch(ctx, P, g);
     }
-    double* o = (double*)ctx->alloc((size_t)m * m * 8);
-    extract_rect_kernel<<<nblocks(m * m, 256), 256, 0, ctx->stream>>>(C, mp, o, m, m);
+    extract_rect_kernel<<<nblocks(m * m, 256), 256, 0, ctx->stream>>>(C.f64(), mp, o.f64(), m, m);
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaMemcpyAsync(out_host, o, (size_t)m * m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(out_host, o.p, (size_t)m * m * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    ctx->release(o, (size_t)m * m * 8);
-    ctx->release(C, (size_t)mp * mp * 8);
 }
 
 // =============================================================================================

@@ -939,17 +939,15 @@ static void qs_inv_diag_J(b200gp_qs* s, double* out_dev) {
     b200gp_ctx* ctx = s->ctx;
     const int64_t n = s->n, nch = (n + s->model.chunk - 1) / s->model.chunk;
     const size_t cb = (size_t)GramBack<J>::SIZE * nch * 8, sb = (size_t)J * J * nch * 8;
-    double* comp = (double*)ctx->alloc(cb);
-    double* tstart = (double*)ctx->alloc(sb);
-    gram_chunk_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->c, s->w, n, comp, nch);
+    Scratch comp(ctx, cb), tstart(ctx, sb);
+    gram_chunk_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->c, s->w, n, comp.f64(),
+                                                                              nch);
     ctx->launches++;
-    run_tree<GramBack<J>>(ctx, comp, nch, tstart);
-    gram_replay_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->c, s->w, n, tstart, nch,
-                                                                               out_dev);
+    run_tree<GramBack<J>>(ctx, comp.f64(), nch, tstart.f64());
+    gram_replay_kernel<J><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, s->t, s->c, s->w, n, tstart.f64(),
+                                                                               nch, out_dev);
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
-    ctx->release(comp, cb);
-    ctx->release(tstart, sb);
 }
 
 static void qs_destroy(b200gp_qs* s) {
@@ -1267,16 +1265,15 @@ int b200gp_qs_inverse_diagonal(b200gp_qs* s, double* out) {
     API_BEGIN(s->ctx)
     if (s->info != 0) throw GpError("qs_inverse_diagonal: the factorisation failed (matrix not positive definite)");
     const size_t nb = (size_t)s->n * 8;
-    double* o = (double*)_ctx->alloc(nb);
+    Scratch o(_ctx, nb);
     {
         ProfTimer tm(_ctx, &_ctx->prof.qs_ms);
         _ctx->prof.qs_launches++;
         _ctx->prof.qs_bytes += 8.0 * (double)s->n * (2.0 * (2.0 + s->J) + 1.0);  // two passes read t, c, w ; write out
-        QS_DISPATCH_J(s->J, (qs_inv_diag_J<JJ>(s, o)))
+        QS_DISPATCH_J(s->J, (qs_inv_diag_J<JJ>(s, o.f64())))
     }
-    CUDA_CHECK(cudaMemcpyAsync(out, o, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(out, o.p, nb, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(o, nb);
     API_END
 }
 
@@ -1295,22 +1292,19 @@ int b200gp_qs_conditioned_variance(b200gp_qs* s, const double* noise_pred, doubl
     if (s->info != 0) throw GpError("qs_conditioned_variance: the factorisation failed (matrix not positive definite)");
     const int64_t n = s->n;
     const size_t nb = (size_t)n * 8;
-    double* o = (double*)_ctx->alloc(nb);
-    double* np_ = (double*)_ctx->alloc(nb);
-    CUDA_CHECK(cudaMemcpyAsync(np_, noise_pred, nb, cudaMemcpyHostToDevice, _ctx->stream));
+    Scratch o(_ctx, nb), np_(_ctx, nb);
+    CUDA_CHECK(cudaMemcpyAsync(np_.p, noise_pred, nb, cudaMemcpyHostToDevice, _ctx->stream));
     {
         ProfTimer tm(_ctx, &_ctx->prof.qs_ms);
         _ctx->prof.qs_launches++;
         _ctx->prof.qs_bytes += 8.0 * (double)n * (2.0 * (2.0 + s->J) + 4.0);
-        QS_DISPATCH_J(s->J, (qs_inv_diag_J<JJ>(s, o)))
-        conditioned_variance_kernel<<<nblk(n, 256), 256, 0, _ctx->stream>>>(o, s->diag, np_, n, o);
+        QS_DISPATCH_J(s->J, (qs_inv_diag_J<JJ>(s, o.f64())))
+        conditioned_variance_kernel<<<nblk(n, 256), 256, 0, _ctx->stream>>>(o.f64(), s->diag, np_.f64(), n, o.f64());
         _ctx->launches++;
         CUDA_CHECK(cudaGetLastError());
     }
-    CUDA_CHECK(cudaMemcpyAsync(out, o, nb, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(out, o.p, nb, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(o, nb);
-    _ctx->release(np_, nb);
     API_END
 }
 
@@ -1326,32 +1320,20 @@ int b200gp_qs_condition(b200gp_qs* s, const double* prog, int n_instr, const dou
     API_BEGIN(s->ctx)
     KProg P = parse_prog(prog, n_instr, 1);
     const int64_t n = s->n;
-    double* xt_dev = s->t;
-    bool own_xt = false;
-    if (t_test == nullptr) {
-        m = n;
-    } else {
-        if (m <= 0) throw GpError("qs_condition: empty X_test");
-        xt_dev = (double*)_ctx->alloc((size_t)m * 8);
-        own_xt = true;
-        CUDA_CHECK(cudaMemcpyAsync(xt_dev, t_test, (size_t)m * 8, cudaMemcpyHostToDevice, _ctx->stream));
-    }
+    if (t_test == nullptr) m = n;
+    else if (m <= 0) throw GpError("qs_condition: empty X_test");
+    Scratch xt(_ctx, (size_t)m * 8);
+    CUDA_CHECK(cudaMemcpyAsync(xt.p, t_test ? t_test : s->t, (size_t)m * 8, cudaMemcpyDefault, _ctx->stream));
     const int64_t mp = ((m + TILE - 1) / TILE) * TILE, kp = ((n + TILE - 1) / TILE) * TILE;
     const size_t ab = (size_t)mp * kp * 8;
-    double* Kst = (double*)_ctx->alloc(ab);
-    double* At = (double*)_ctx->alloc(ab);
-    double* dt = (double*)_ctx->alloc((size_t)mp * 8);
-    CUDA_CHECK(cudaMemsetAsync(dt, 0, (size_t)mp * 8, _ctx->stream));
+    Scratch Kst(_ctx, ab), At(_ctx, ab), dt(_ctx, (size_t)mp * 8);
+    CUDA_CHECK(cudaMemsetAsync(dt.p, 0, (size_t)mp * 8, _ctx->stream));
     if (diag_or_null != nullptr)   // solver.py:124-129 adds the noise; the dense branch :131-139 does not
-        CUDA_CHECK(cudaMemcpyAsync(dt, diag_or_null, (size_t)m * 8, cudaMemcpyHostToDevice, _ctx->stream));
-    CUDA_CHECK(cudaMemsetAsync(At, 0, ab, _ctx->stream));   // pad rows / columns of A^T must be zero for the GEMM
-    dense_build_rect(_ctx, P, xt_dev, m, s->t, n, 1, nullptr, Kst, kp, mp, kp);
-    for (int64_t r = 0; r < m; ++r) qs_affine(s, OP_LOWER_SOLVE, Kst + r * kp, At + r * kp, nullptr);
-    dense_conditioned_covariance_to_host(_ctx, P, At, mp, kp, xt_dev, dt, 1, m, out);
-    _ctx->release(Kst, ab);
-    _ctx->release(At, ab);
-    _ctx->release(dt, (size_t)mp * 8);
-    if (own_xt) _ctx->release(xt_dev, (size_t)m * 8);
+        CUDA_CHECK(cudaMemcpyAsync(dt.p, diag_or_null, (size_t)m * 8, cudaMemcpyHostToDevice, _ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(At.p, 0, ab, _ctx->stream));   // pad rows / columns of A^T must be zero for the GEMM
+    dense_build_rect(_ctx, P, xt.f64(), m, s->t, n, 1, nullptr, Kst.f64(), kp, mp, kp);
+    for (int64_t r = 0; r < m; ++r) qs_affine(s, OP_LOWER_SOLVE, Kst.f64() + r * kp, At.f64() + r * kp, nullptr);
+    dense_conditioned_covariance_to_host(_ctx, P, At.f64(), mp, kp, xt.f64(), dt.f64(), 1, m, out);
     API_END
 }
 

@@ -104,3 +104,26 @@ def test_predict_at_test_points_parity():
     muo, varo = o.GaussianProcess(to_oracle(k), X, diag=0.1).predict(y, Xt, return_var=True)
     np.testing.assert_allclose(mu, muo, rtol=5e-7, atol=5e-7)
     np.testing.assert_allclose(var, varo, rtol=5e-7, atol=5e-7)
+
+
+def test_int8_update_splits_k_ranges_beyond_the_int32_bound(ctx):
+    """|accumulator| <= S * 4096 * K must stay below 2^31: K = 75264 > 74880 (S = 7) is run as two exact segments.
+    Two rows carry +64 in every digit -- the worst case the bound is about -- so a single unsplit launch WOULD wrap
+    (7 * 4096 * 75264 > 2^31 - 1); the result must still equal the integer-exact reference."""
+    from tinygp_b200 import _cabi
+    S, rows, K = 7, 256, 75264
+    rng = np.random.default_rng(11)
+    planes = rng.integers(-64, 65, size=(S, rows, K), dtype=np.int8)
+    planes[:, :2, :] = 64                        # rows 0 and 1: every digit of every plane is +64
+    rs = np.ones(rows)
+    C = rng.normal(size=(rows, rows))
+    got = C.copy()
+    pl = np.ascontiguousarray(planes)
+    ctx.check(ctx.lib.b200gp_i8_update_test(ctx.handle, _cabi.ptr(pl), S, rows, K, _cabi.ptr(rs), _cabi.ptr(got)))
+    want = C.copy()
+    P = planes.astype(np.int64)
+    for s in range(S):
+        for t in range(S - s):
+            want -= 2.0 ** -(12 + 7 * (s + t)) * (P[s] @ P[t].T).astype(np.float64)
+    assert sum(int(P[s][0] @ P[6 - s][1]) for s in range(7)) > 2 ** 31 - 1     # the last digit group, unsplit, wraps
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * max(1.0, np.abs(want).max()))

@@ -1094,7 +1094,7 @@ static void launch_wide(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
 // cluster shape code: 1 = wide 256 x 256 tile per CTA (two MMAs per B stage, no cluster);
 // 2 = CTA pair with tcgen05 cta_group::2 (256 x 256 tile per pair);
 // 11 = 1x1 (no multicast), 21 = 2x1, 12 = 1x2, 22 = 2x2, 41 = 4x1, 42 = 4x2 (cta_group::1 + TMA multicast)
-void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
+static void launch_update_one(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     if (a.layout == 1 && (ctx->oz_cluster == 1 || ctx->oz_cluster == 2))
         throw GpError("ozaki_layout=1 (chunk-major digit planes) is not implemented for the wide / 2-SM kernels");
     switch ((int)ctx->oz_cluster) {
@@ -1109,6 +1109,30 @@ void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
         case 42: OZ_CFG(4, 2); break;
         default: OZ_CFG(2, 2); break;
 #undef OZ_CFG
+    }
+}
+
+// Exactness of the int32 accumulators: every digit satisfies |q| <= 64 (cut_digits_kernel), a digit group g holds at
+// most S pair products, so |accumulator| <= S * 4096 * K and the integer sums are exact while S * 4096 * K < 2^31:
+// K <= 74880 for S = 7, 65408 for S = 8 (multiples of KC).  That covers every block column up to N = 65536 + nb in one
+// launch; longer K ranges (N = 131072) are split into segments, each an independent exact update of the fp64 tile.
+// (Typical sums are ~1e6 -- the bound is about the worst case, not the expected one.)
+int max_exact_k(int S) {
+    const int64_t k = (((int64_t)1 << 31) - 1) / (4096LL * (S > 0 ? S : 1));
+    return (int)((k / KC) * KC);
+}
+
+void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
+    const int kmax = max_exact_k(a.S);
+    if (a.K <= kmax) {
+        launch_update_one(ctx, maps, a);
+        return;
+    }
+    for (int k0 = 0; k0 < a.K; k0 += kmax) {
+        Args b = a;
+        b.k_begin = a.k_begin + k0;
+        b.K = (a.K - k0 < kmax) ? (a.K - k0) : kmax;
+        launch_update_one(ctx, maps, b);
     }
 }
 

@@ -121,9 +121,9 @@ def test_int8_update_splits_k_ranges_beyond_the_int32_bound(ctx):
     pl = np.ascontiguousarray(planes)
     ctx.check(ctx.lib.b200gp_i8_update_test(ctx.handle, _cabi.ptr(pl), S, rows, K, _cabi.ptr(rs), _cabi.ptr(got)))
     want = C.copy()
-    P = planes.astype(np.int64)
+    P = planes.astype(np.float64)                # integer sums < 2^53: the BLAS products below are exact
     for s in range(S):
         for t in range(S - s):
-            want -= 2.0 ** -(12 + 7 * (s + t)) * (P[s] @ P[t].T).astype(np.float64)
-    assert sum(int(P[s][0] @ P[6 - s][1]) for s in range(7)) > 2 ** 31 - 1     # the last digit group, unsplit, wraps
+            want -= 2.0 ** -(12 + 7 * (s + t)) * (P[s] @ P[t].T)
+    assert sum(float(P[s][0] @ P[6 - s][1]) for s in range(7)) > 2 ** 31 - 1   # the last digit group, unsplit, wraps
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * max(1.0, np.abs(want).max()))

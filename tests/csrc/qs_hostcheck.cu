@@ -8,36 +8,39 @@
 
 namespace {
 
-template <class Op, int J>
+// the structure of run_tree<Op> (quasisep.cu): up-sweep with fan-in TREE_R, top walk, down-sweep -- with the same
+// Op::combine / Op::apply / state_* helpers the tree kernels call
+template <class Op>
 void host_tree(const std::vector<double>& comp, int64_t n, std::vector<double>& start) {
-    // the same two-level structure as run_tree<Op> (fan-in TREE_R), recursively, using Op::combine / Op::apply
-    if (n <= TREE_R) {
-        double s[J][J] = {};
+    typedef typename StateOf<Op>::type State;
+    if (n <= TREE_R) {                                         // tree_top_kernel
+        State s;
+        state_zero(s);
         Op e;
         for (int64_t i = 0; i < n; ++i) {
-            for (int q = 0; q < J * J; ++q) start[(size_t)q * n + i] = s[q / J][q % J];
+            state_store(s, start.data(), n, i);
             e.load(comp.data(), n, i);
             e.apply(s);
         }
         return;
     }
     const int64_t np_ = (n + TREE_R - 1) / TREE_R;
-    std::vector<double> parent((size_t)Op::SIZE * np_), pstart((size_t)J * J * np_);
-    for (int64_t i = 0; i < np_; ++i) {                       // tree_up_kernel
+    std::vector<double> parent((size_t)Op::SIZE * np_), pstart((size_t)Op::STATE * np_);
+    for (int64_t i = 0; i < np_; ++i) {                        // tree_up_kernel
         Op acc, e;
         const int64_t b = i * TREE_R;
         acc.load(comp.data(), n, b);
         for (int64_t j = b + 1; j < b + TREE_R && j < n; ++j) { e.load(comp.data(), n, j); acc.combine(e); }
         acc.store(parent.data(), np_, i);
     }
-    host_tree<Op, J>(parent, np_, pstart);
-    for (int64_t i = 0; i < np_; ++i) {                       // tree_down_kernel
-        double s[J][J];
-        for (int q = 0; q < J * J; ++q) s[q / J][q % J] = pstart[(size_t)q * np_ + i];
+    host_tree<Op>(parent, np_, pstart);
+    for (int64_t i = 0; i < np_; ++i) {                        // tree_down_kernel
+        State s;
+        state_load(s, pstart.data(), np_, i);
         Op e;
         const int64_t b = i * TREE_R;
         for (int64_t j = b; j < b + TREE_R && j < n; ++j) {
-            for (int q = 0; q < J * J; ++q) start[(size_t)q * n + j] = s[q / J][q % J];
+            state_store(s, start.data(), n, j);
             if (j + 1 < b + TREE_R && j + 1 < n) { e.load(comp.data(), n, j); e.apply(s); }
         }
     }
@@ -48,8 +51,43 @@ void inv_diag_host(const QsModel& m, const double* t, const double* c, const dou
     const int64_t nch = (n + m.chunk - 1) / m.chunk;
     std::vector<double> comp((size_t)GramBack<J>::SIZE * nch), start((size_t)J * J * nch);
     for (int64_t ch = 0; ch < nch; ++ch) gram_chunk_body<J>(m, t, c, w, n, comp.data(), nch, ch);
-    host_tree<GramBack<J>, J>(comp, nch, start);
+    host_tree<GramBack<J>>(comp, nch, start);
     for (int64_t ch = 0; ch < nch; ++ch) gram_replay_body<J>(m, t, c, w, n, start.data(), nch, out, ch);
+}
+
+// QuasisepSolver.__init__ (solver.py:73-82): chunk composites -> tree -> replay; optionally with the fused forward solve
+template <int J>
+void factor_host(const QsModel& m, const double* t, const double* diag, int64_t n, double* c, double* w,
+                 double* logdet_half, int* info, const double* x_fuse, double* alpha) {
+    const int64_t nch = (n + m.chunk - 1) / m.chunk;
+    std::vector<double> comp((size_t)Riccati<J>::SIZE * nch), fstart((size_t)J * J * nch), part(nch);
+    std::vector<double> acomp((size_t)Affine<J>::SIZE * nch), gstart((size_t)J * nch);
+    for (int64_t ch = 0; ch < nch; ++ch) chol_chunk_body<J>(m, t, diag, n, comp.data(), nch, ch);
+    host_tree<Riccati<J>>(comp, nch, fstart);
+    *info = INT_MAX;
+    for (int64_t ch = 0; ch < nch; ++ch)
+        chol_replay_body<J>(m, t, diag, n, fstart.data(), nch, c, w, part.data(), info, x_fuse,
+                            x_fuse ? acomp.data() : nullptr, ch);
+    if (*info == INT_MAX) *info = 0;
+    double s = 0.0;
+    for (int64_t ch = 0; ch < nch; ++ch) s += part[ch];
+    *logdet_half = s;
+    if (x_fuse) {   // the fused path of qs_logp_impl: tree over the composites accumulated in the Cholesky replay
+        host_tree<Affine<J>>(acomp, nch, gstart);
+        for (int64_t ch = 0; ch < nch; ++ch)
+            affine_replay_body<J, OP_LOWER_SOLVE>(m, t, diag, c, w, x_fuse, n, gstart.data(), nch, alpha, nullptr, ch);
+    }
+}
+
+template <int J, int OP>
+void affine_host(const QsModel& m, const double* t, const double* diag, const double* c, const double* w,
+                 const double* x, int64_t n, double* out) {
+    const int64_t nch = (n + m.chunk - 1) / m.chunk;
+    std::vector<double> comp((size_t)Affine<J>::SIZE * nch), gstart((size_t)J * nch);
+    for (int64_t ch = 0; ch < nch; ++ch) affine_chunk_body<J, OP>(m, t, c, w, x, n, comp.data(), nch, ch);
+    host_tree<Affine<J>>(comp, nch, gstart);
+    for (int64_t ch = 0; ch < nch; ++ch)
+        affine_replay_body<J, OP>(m, t, diag, c, w, x, n, gstart.data(), nch, out, nullptr, ch);
 }
 
 template <int J>
@@ -94,6 +132,34 @@ int hostcheck_generators(const double* comps, int ncomp, const double* t, int64_
     try {
         QsModel m = build_model(comps, ncomp);
         DISPATCH_J(m.J, (generators_host<JJ>(m, t, n, a_out, p_out)))
+        return 0;
+    } catch (const std::exception&) { return 2; }
+}
+
+int hostcheck_factor(const double* comps, int ncomp, const double* t, const double* diag, int64_t n, int chunk,
+                     double* c, double* w, double* logdet_half, int* info, const double* x_fuse, double* alpha) {
+    try {
+        QsModel m = build_model(comps, ncomp);
+        m.chunk = chunk;
+        DISPATCH_J(m.J, (factor_host<JJ>(m, t, diag, n, c, w, logdet_half, info, x_fuse, alpha)))
+        return 0;
+    } catch (const std::exception&) { return 2; }
+}
+
+// op: the OP_* codes of qs_core.cuh (0 lower solve, 1 upper solve, 2 L z, 3 / 4 lower / upper part of K y)
+int hostcheck_affine(const double* comps, int ncomp, int op, const double* t, const double* diag, const double* c,
+                     const double* w, const double* x, int64_t n, int chunk, double* out) {
+    try {
+        QsModel m = build_model(comps, ncomp);
+        m.chunk = chunk;
+        switch (op) {
+            case OP_LOWER_SOLVE: DISPATCH_J(m.J, (affine_host<JJ, OP_LOWER_SOLVE>(m, t, diag, c, w, x, n, out))) break;
+            case OP_UPPER_SOLVE: DISPATCH_J(m.J, (affine_host<JJ, OP_UPPER_SOLVE>(m, t, diag, c, w, x, n, out))) break;
+            case OP_LOWER_DOT: DISPATCH_J(m.J, (affine_host<JJ, OP_LOWER_DOT>(m, t, diag, c, w, x, n, out))) break;
+            case OP_SYMM_LOWER: DISPATCH_J(m.J, (affine_host<JJ, OP_SYMM_LOWER>(m, t, diag, c, w, x, n, out))) break;
+            case OP_SYMM_UPPER: DISPATCH_J(m.J, (affine_host<JJ, OP_SYMM_UPPER>(m, t, diag, c, w, x, n, out))) break;
+            default: return 3;
+        }
         return 0;
     } catch (const std::exception&) { return 2; }
 }

@@ -187,3 +187,82 @@ def test_malformed_programs_are_rejected_by_the_parser(klib):
     assert "undefined metric" in run([[2, 3, 1.0, 0]])[1]
     assert "width does not match" in run([[32, 1, 1, 3], [1, 0, 0, 0], [2, 3, 1.0, 0]])[1]
     assert "non-finite" in run([[32, 1, 1, 2], [np.nan, 0, 0, 0], [2, 3, 1.0, 0]])[1]
+
+
+# ------------------------------------------------------------------------------------------------
+# the Cholesky and affine scans of the quasiseparable path (BASELINE config 4's hot kernels) on the CPU
+# ------------------------------------------------------------------------------------------------
+OPS = {"lower_solve": 0, "upper_solve": 1, "lower_dot": 2, "symm_lower": 3, "symm_upper": 4}
+
+
+def _factor(lib, k, t, noise, chunk, x=None):
+    comps = k.component_array()
+    n, J = t.size, k.state_dim()
+    c, w = np.zeros(n), np.zeros((n, J))
+    ld, info = ctypes.c_double(), ctypes.c_int()
+    alpha = np.zeros(n) if x is not None else None
+    rc = lib.hostcheck_factor(_p(comps), comps.shape[0], _p(t), _p(noise), ctypes.c_int64(n), chunk, _p(c), _p(w),
+                              ctypes.byref(ld), ctypes.byref(info), _p(x) if x is not None else None,
+                              _p(alpha) if x is not None else None)
+    assert rc == 0
+    return c, w, ld.value, info.value, alpha
+
+
+@pytest.mark.parametrize("chunk", [1, 5, 64])
+@pytest.mark.parametrize("n", [1, 3, 257, 4100])
+@pytest.mark.parametrize("name", list(KERNELS))
+def test_cholesky_scan_matches_the_sequential_recursion(lib, name, n, chunk):
+    """chol_chunk_body -> Riccati tree -> chol_replay_body (ops.py:352-399): c, w, sum log c and the fused forward
+    solve equal the oracle's sequential recursion (ops.py:354-361, 465-468)"""
+    k, ko = KERNELS[name]
+    t, noise = _data(n, seed=n + 1)
+    y = np.sin(t)
+    so = o.QuasisepSolver(ko, t, o.Diagonal(noise))
+    c, w, ld, info, alpha = _factor(lib, k, t, noise, chunk, x=y)
+    assert info == 0
+    np.testing.assert_allclose(c, so.c, rtol=1e-11, atol=0)
+    np.testing.assert_allclose(w, so.w, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(ld, np.sum(np.log(so.c)), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(alpha, so.solve_triangular(y), rtol=1e-9, atol=1e-12)
+
+
+def test_cholesky_scan_reports_the_first_bad_pivot(lib):
+    k, ko = KERNELS["sho+m32"]
+    t, noise = _data(300)
+    bad = noise.copy()
+    bad[123] = -50.0
+    c, w, ld, info, _ = _factor(lib, k, t, bad, 16)
+    d, p, q, a = ko.to_symm_qsm(t)
+    _, _, first = __import__("oracle.cref", fromlist=["x"]).qs_cholesky(d + bad, p, q, a)
+    assert info == first and info >= 1
+
+
+@pytest.mark.parametrize("chunk", [1, 7, 64])
+@pytest.mark.parametrize("n", [1, 258, 3000])
+@pytest.mark.parametrize("name", ["sho+m32", "m52", "cosine+exp"])
+def test_affine_scans_match_the_oracle(lib, name, n, chunk):
+    """triangular solves and products (ops.py:308-349, 463-512; core.py:303-305, 499-505) as chunk / tree / replay"""
+    k, ko = KERNELS[name]
+    comps = k.component_array()
+    t, noise = _data(n, seed=n + 2)
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=n)
+    so = o.QuasisepSolver(ko, t, o.Diagonal(noise))
+    c, w = np.ascontiguousarray(so.c), np.ascontiguousarray(so.w)
+
+    def run(op, out=None):
+        out = np.zeros(n) if out is None else out
+        assert lib.hostcheck_affine(_p(comps), comps.shape[0], OPS[op], _p(t), _p(noise), _p(c), _p(w), _p(x),
+                                    ctypes.c_int64(n), chunk, _p(out)) == 0
+        return out
+
+    np.testing.assert_allclose(run("lower_solve"), so.solve_triangular(x), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(run("upper_solve"), so.solve_triangular(x, transpose=True), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(run("lower_dot"), so.dot_triangular(x), rtol=1e-10, atol=1e-12)
+    ky = run("symm_upper", run("symm_lower"))            # K y = (d y + lower part) + upper part
+    if n <= 300:
+        np.testing.assert_allclose(ky, so.covariance() @ x, rtol=1e-10, atol=1e-11)
+    else:
+        lo = o.qs_lower_matmul(so.p, so.q, so.a, x[:, None])[:, 0]
+        up = o.qs_upper_matmul(so.p, so.q, so.a, x[:, None])[:, 0]
+        np.testing.assert_allclose(ky, so.d * x + lo + up, rtol=1e-10, atol=1e-11)

@@ -39,193 +39,6 @@ struct b200gp_qs {
     size_t fused_comp_bytes = 0;
 };
 
-// ---------------------------------------------------------------------------------------------
-// scan monoids.  Storage is structure-of-arrays: element e of item i at buf[e * count + i].
-// ---------------------------------------------------------------------------------------------
-template <int J>
-struct Riccati {
-    static constexpr int SIZE = 3 * J * J;   // A, F, G
-    static constexpr int STATE = J * J;      // f
-    double A[J][J], F[J][J], G[J][J];
-    __device__ void identity() {
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) { A[i][j] = (i == j) ? 1.0 : 0.0; F[i][j] = 0.0; G[i][j] = 0.0; }
-    }
-    __device__ void load(const double* buf, int64_t count, int64_t i) {
-#pragma unroll
-        for (int e = 0; e < J * J; ++e) {
-            A[e / J][e % J] = buf[(int64_t)e * count + i];
-            F[e / J][e % J] = buf[(int64_t)(J * J + e) * count + i];
-            G[e / J][e % J] = buf[(int64_t)(2 * J * J + e) * count + i];
-        }
-    }
-    __device__ void store(double* buf, int64_t count, int64_t i) const {
-#pragma unroll
-        for (int e = 0; e < J * J; ++e) {
-            buf[(int64_t)e * count + i] = A[e / J][e % J];
-            buf[(int64_t)(J * J + e) * count + i] = F[e / J][e % J];
-            buf[(int64_t)(2 * J * J + e) * count + i] = G[e / J][e % J];
-        }
-    }
-    // this <- this (left) combined with r (right)      (ops.py:376-383)
-    __device__ void combine(const Riccati& r) {
-        double M[J][J], X[J][J], T1[J][J], T2[J][J];
-        // M = I + F_l G_r
-        matmul<J>(F, r.G, M);
-#pragma unroll
-        for (int i = 0; i < J; ++i) M[i][i] += 1.0;
-        // [M^-1 A_l | M^-1 F_l] share the factorisation: solve twice on copies
-        double Mc[J][J];
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) { Mc[i][j] = M[i][j]; X[i][j] = A[i][j]; }
-        solve_inplace<J>(Mc, X);        // X = M^-1 A_l
-        double newA[J][J];
-        matmul<J>(r.A, X, newA);        // A_r M^-1 A_l
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) { Mc[i][j] = M[i][j]; X[i][j] = F[i][j]; }
-        solve_inplace<J>(Mc, X);        // X = M^-1 F_l
-        matmul<J>(r.A, X, T1);          // A_r M^-1 F_l
-        matmul_nt<J>(T1, r.A, T2);      // ... A_r^T
-        double newF[J][J];
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) newF[i][j] = r.F[i][j] + T2[i][j];
-        // G_l + A_l^T M^-T G_r A_l : solve M^T Y = G_r
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) { Mc[i][j] = M[j][i]; X[i][j] = r.G[i][j]; }
-        solve_inplace<J>(Mc, X);        // X = M^-T G_r
-        matmul<J>(X, A, T1);            // M^-T G_r A_l
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < J; ++k) s += A[k][i] * T1[k][j];  // A_l^T (...)
-                T2[i][j] = s;
-            }
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) { G[i][j] += T2[i][j]; A[i][j] = newA[i][j]; F[i][j] = newF[i][j]; }
-    }
-    // f <- F + A (I + f G)^-1 f A^T
-    __device__ void apply(double (&f)[J][J]) const {
-        double M[J][J], X[J][J], T1[J][J];
-        matmul<J>(f, G, M);
-#pragma unroll
-        for (int i = 0; i < J; ++i) M[i][i] += 1.0;
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) X[i][j] = f[i][j];
-        solve_inplace<J>(M, X);
-        matmul<J>(A, X, T1);
-        matmul_nt<J>(T1, A, X);
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) f[i][j] = F[i][j] + X[i][j];
-    }
-};
-
-template <int J>
-struct Affine {
-    static constexpr int SIZE = J * J + J;  // A, b
-    static constexpr int STATE = J;         // g
-    double A[J][J], b[J];
-    __device__ void identity() {
-#pragma unroll
-        for (int i = 0; i < J; ++i) {
-            b[i] = 0.0;
-#pragma unroll
-            for (int j = 0; j < J; ++j) A[i][j] = (i == j) ? 1.0 : 0.0;
-        }
-    }
-    __device__ void load(const double* buf, int64_t count, int64_t i) {
-#pragma unroll
-        for (int e = 0; e < J * J; ++e) A[e / J][e % J] = buf[(int64_t)e * count + i];
-#pragma unroll
-        for (int e = 0; e < J; ++e) b[e] = buf[(int64_t)(J * J + e) * count + i];
-    }
-    __device__ void store(double* buf, int64_t count, int64_t i) const {
-#pragma unroll
-        for (int e = 0; e < J * J; ++e) buf[(int64_t)e * count + i] = A[e / J][e % J];
-#pragma unroll
-        for (int e = 0; e < J; ++e) buf[(int64_t)(J * J + e) * count + i] = b[e];
-    }
-    __device__ void combine(const Affine& r) {  // (A_r A_l, A_r b_l + b_r)   (ops.py:322-324)
-        double nA[J][J], nb[J];
-        matmul<J>(r.A, A, nA);
-#pragma unroll
-        for (int i = 0; i < J; ++i) {
-            double s = r.b[i];
-#pragma unroll
-            for (int k = 0; k < J; ++k) s += r.A[i][k] * b[k];
-            nb[i] = s;
-        }
-#pragma unroll
-        for (int i = 0; i < J; ++i) {
-            b[i] = nb[i];
-#pragma unroll
-            for (int j = 0; j < J; ++j) A[i][j] = nA[i][j];
-        }
-    }
-    __device__ void apply(double (&g)[J]) const {
-        double o[J];
-#pragma unroll
-        for (int i = 0; i < J; ++i) {
-            double s = b[i];
-#pragma unroll
-            for (int k = 0; k < J; ++k) s += A[i][k] * g[k];
-            o[i] = s;
-        }
-#pragma unroll
-        for (int i = 0; i < J; ++i) g[i] = o[i];
-    }
-};
-
-template <int J> __device__ __forceinline__ void state_load(double (&f)[J][J], const double* buf, int64_t count, int64_t i) {
-#pragma unroll
-    for (int e = 0; e < J * J; ++e) f[e / J][e % J] = buf[(int64_t)e * count + i];
-}
-template <int J> __device__ __forceinline__ void state_store(const double (&f)[J][J], double* buf, int64_t count, int64_t i) {
-#pragma unroll
-    for (int e = 0; e < J * J; ++e) buf[(int64_t)e * count + i] = f[e / J][e % J];
-}
-template <int J> __device__ __forceinline__ void state_load(double (&g)[J], const double* buf, int64_t count, int64_t i) {
-#pragma unroll
-    for (int e = 0; e < J; ++e) g[e] = buf[(int64_t)e * count + i];
-}
-template <int J> __device__ __forceinline__ void state_store(const double (&g)[J], double* buf, int64_t count, int64_t i) {
-#pragma unroll
-    for (int e = 0; e < J; ++e) buf[(int64_t)e * count + i] = g[e];
-}
-template <int J> __device__ __forceinline__ void state_zero(double (&f)[J][J]) {
-#pragma unroll
-    for (int i = 0; i < J; ++i)
-#pragma unroll
-        for (int j = 0; j < J; ++j) f[i][j] = 0.0;
-}
-template <int J> __device__ __forceinline__ void state_zero(double (&g)[J]) {
-#pragma unroll
-    for (int i = 0; i < J; ++i) g[i] = 0.0;
-}
-
-template <class Op> struct StateOf;
-template <int J> struct StateOf<Riccati<J>> { typedef double type[J][J]; };
-template <int J> struct StateOf<Affine<J>> { typedef double type[J]; };
-template <int J> struct StateOf<GramBack<J>> { typedef double type[J][J]; };
-
 // up-sweep: parent[i] = fold of child[i*R .. i*R+R-1]
 template <class Op>
 __global__ void __launch_bounds__(QS_THREADS) tree_up_kernel(const double* child, int64_t nchild, double* parent, int64_t nparent) {
@@ -273,92 +86,15 @@ __global__ void __launch_bounds__(QS_THREADS) tree_down_kernel(const double* chi
 }
 
 // ---------------------------------------------------------------------------------------------
-// 32-byte per-thread vector accesses.  One thread walks `chunk` consecutive points, so neighbouring threads are
-// chunk*8 bytes apart and nothing coalesces across the warp; with scalar loads every thread keeps ~5 cache
-// lines "hot" and 1024 resident threads thrash L1 (ncu, round 1: all four scan kernels cost ~0.65 ms regardless
-// of their flop count).  Loading/storing 4 points (one full 32-byte sector) per access makes every sector move
-// exactly once.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ld4(const double* __restrict__ p, int64_t kb, int64_t k1, double (&v)[4]) {
-    if (kb + 3 < k1 && ((reinterpret_cast<uintptr_t>(p + kb) & 31) == 0)) {
-        const double4 q = *reinterpret_cast<const double4*>(p + kb);
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = (kb + u < k1) ? p[kb + u] : 0.0;
-    }
-}
-__device__ __forceinline__ void st4(double* p, int64_t kb, int64_t k1, const double (&v)[4]) {
-    if (kb + 3 < k1 && ((reinterpret_cast<uintptr_t>(p + kb) & 31) == 0)) {
-        *reinterpret_cast<double4*>(p + kb) = make_double4(v[0], v[1], v[2], v[3]);
-    } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (kb + u < k1) p[kb + u] = v[u];
-    }
-}
-// ---------------------------------------------------------------------------------------------
-// Cholesky: chunk composites and replay
+// scan kernels: thin wrappers over the __host__ __device__ bodies of qs_core.cuh (one thread = one chunk)
 // ---------------------------------------------------------------------------------------------
 template <int J>
 __global__ void __launch_bounds__(QS_THREADS) chol_chunk_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
                                                                 const double* __restrict__ diag, int64_t n,
                                                                 double* comp, int64_t nchunks) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= nchunks) return;
-    const int64_t k0 = ch * m.chunk, k1 = min(n, k0 + m.chunk);
-    Riccati<J> R;
-    R.identity();
-    double tp = (k0 == 0) ? t[0] : t[k0 - 1];
-    for (int64_t kb = k0; kb < k1; kb += 4) {
-      double t4[4], g4[4];
-      ld4(t, kb, k1, t4);
-      ld4(diag, kb, k1, g4);
-#pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        if (kb + uu >= k1) break;
-        const double tk = t4[uu];
-        double a[J][J], p[J];
-        qs_gen<J>(m, tk - tp, a, p);
-        tp = tk;
-        const double d = m.d0 + g4[uu];
-        double u[J], v[J], w[J];
-        double s = d;
-#pragma unroll
-        for (int i = 0; i < J; ++i) {
-            double x = 0.0, y = 0.0;
-#pragma unroll
-            for (int j = 0; j < J; ++j) { x += R.F[i][j] * p[j]; y += R.A[j][i] * p[j]; }
-            u[i] = x; v[i] = y;
-        }
-#pragma unroll
-        for (int i = 0; i < J; ++i) s -= p[i] * u[i];
-        const double is = 1.0 / s;
-#pragma unroll
-        for (int i = 0; i < J; ++i) {
-            double x = m.q[i];
-#pragma unroll
-            for (int j = 0; j < J; ++j) x -= a[i][j] * u[j];
-            w[i] = x;
-        }
-        double T1[J][J], T2[J][J];
-        matmul<J>(a, R.F, T1);
-        matmul_nt<J>(T1, a, T2);
-        matmul<J>(a, R.A, T1);
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                R.F[i][j] = T2[i][j] + w[i] * w[j] * is;
-                R.A[i][j] = T1[i][j] - w[i] * v[j] * is;
-                R.G[i][j] -= v[i] * v[j] * is;
-            }
-      }
-    }
-    R.store(comp, nchunks, ch);
+    if (ch < nchunks) chol_chunk_body<J>(m, t, diag, n, comp, nchunks, ch);
 }
-
-// replay with the sequential recursion of ops.py:354-361; writes c, w, per-chunk sum(log c)
 template <int J>
 __global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
                                                                  const double* __restrict__ diag, int64_t n,
@@ -366,198 +102,16 @@ __global__ void __launch_bounds__(QS_THREADS) chol_replay_kernel(const __grid_co
                                                                  double* w_out, double* logc_part, int* info,
                                                                  const double* __restrict__ x_fuse, double* aff_comp) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= nchunks) return;
-    const int64_t k0 = ch * m.chunk, k1 = min(n, k0 + m.chunk);
-    double f[J][J];
-    state_load<J>(f, fstart, nchunks, ch);
-    const bool fuse = (x_fuse != nullptr);
-    Affine<J> R;      // forward-solve composite of this chunk (ops.py:475-486 elements), only when fusing
-    R.identity();
-    double tp = (k0 == 0) ? t[0] : t[k0 - 1];
-    double lsum = 0.0;
-    for (int64_t kb = k0; kb < k1; kb += 4) {
-      double t4[4], g4[4], x4[4], c4[4];
-      ld4(t, kb, k1, t4);
-      ld4(diag, kb, k1, g4);
-      if (fuse) ld4(x_fuse, kb, k1, x4);
-#pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        const int64_t k = kb + uu;
-        if (k >= k1) break;
-        const double tk = t4[uu];
-        double a[J][J], p[J];
-        qs_gen<J>(m, tk - tp, a, p);
-        tp = tk;
-        const double d = m.d0 + g4[uu];
-        // ck = sqrt(dk - pk @ fp @ pk)
-        double pf[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i < J; ++i) s += p[i] * f[i][j];
-            pf[j] = s;
-        }
-        double quad = 0.0;
-#pragma unroll
-        for (int j = 0; j < J; ++j) quad += pf[j] * p[j];
-        const double c2 = d - quad;
-        if (!(c2 > 0.0)) atomicMin(info, (int)min((int64_t)INT_MAX - 1, k) + 1);
-        const double ck = sqrt(c2);
-        // tmp = fp @ ak.T ; wk = (qk - pk @ tmp) / ck ; fk = ak @ tmp + outer(wk, wk)
-        double tmp[J][J];
-        matmul_nt<J>(f, a, tmp);
-        double w[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i < J; ++i) s += p[i] * tmp[i][j];
-            w[j] = (m.q[j] - s) / ck;
-        }
-        matmul<J>(a, tmp, f);
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) f[i][j] += w[i] * w[j];
-        c4[uu] = ck;
-        strow<J>(w_out, k, w);
-        lsum += log(ck);
-        if (fuse) {   // g' = (a - w p^T / c) g + w x / c, folded while c, w, a, p are still in registers
-            const double ic = 1.0 / ck, xk = x4[uu];
-            double Ak[J][J], nA[J][J], nb[J];
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                const double wi = w[i] * ic;
-#pragma unroll
-                for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j] - wi * p[j];
-                double sb = wi * xk;
-#pragma unroll
-                for (int j = 0; j < J; ++j) sb += Ak[i][j] * R.b[j];
-                nb[i] = sb;
-            }
-            matmul<J>(Ak, R.A, nA);
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                R.b[i] = nb[i];
-#pragma unroll
-                for (int j = 0; j < J; ++j) R.A[i][j] = nA[i][j];
-            }
-        }
-      }
-      st4(c_out, kb, k1, c4);
-    }
-    logc_part[ch] = lsum;
-    if (fuse) R.store(aff_comp, nchunks, ch);
+    if (ch < nchunks) chol_replay_body<J>(m, t, diag, n, fstart, nchunks, c_out, w_out, logc_part, info, x_fuse, aff_comp, ch);
 }
-
-// ---------------------------------------------------------------------------------------------
-// affine scans: triangular solves and products
-// ---------------------------------------------------------------------------------------------
-// OP_GEN_LOWER / OP_GEN_UPPER: the two state scans of GeneralQSM.matmul (general.py:75-104).  Same recursions as
-// the symmetric product, but the replay pass stores the n x J STATES (forward f_k, backward g_k) instead of outputs.
-enum { OP_LOWER_SOLVE = 0, OP_UPPER_SOLVE = 1, OP_LOWER_DOT = 2, OP_SYMM_LOWER = 3, OP_SYMM_UPPER = 4,
-       OP_GEN_LOWER = 5, OP_GEN_UPPER = 6 };
-__host__ __device__ constexpr bool op_reverse(int op) {
-    return op == OP_UPPER_SOLVE || op == OP_SYMM_UPPER || op == OP_GEN_UPPER;
-}
-
-// logical position i of a reverse scan is physical index n-1-i
 template <int J, int OP>
 __global__ void __launch_bounds__(QS_THREADS) affine_chunk_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
                                                                   const double* __restrict__ c, const double* __restrict__ w,
                                                                   const double* __restrict__ x, int64_t n, double* comp,
                                                                   int64_t nchunks) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= nchunks) return;
-    const int64_t l0 = ch * m.chunk, l1 = min(n, l0 + m.chunk);
-    Affine<J> R;
-    R.identity();
-    double tprev = 0.0;
-    if (!op_reverse(OP)) tprev = (l0 == 0) ? t[0] : t[l0 - 1];
-    for (int64_t lb = l0; lb < l1; lb += 4) {
-      double t4[4], x4[4], c4[4];
-      if (!op_reverse(OP)) {   // forward scans: one 32-byte sector per array per 4 points
-          ld4(t, lb, l1, t4);
-          ld4(x, lb, l1, x4);
-          if (OP == OP_LOWER_SOLVE) ld4(c, lb, l1, c4);
-      }
-#pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        const int64_t l = lb + uu;
-        if (l >= l1) break;
-        const int64_t k = op_reverse(OP) ? (n - 1 - l) : l;
-        double dt;
-        if (!op_reverse(OP)) { dt = t4[uu] - tprev; tprev = t4[uu]; }
-        else dt = (k == 0) ? 0.0 : (t[k] - t[k - 1]);
-        double a[J][J], p[J];
-        qs_gen<J>(m, dt, a, p);
-        const double xk = op_reverse(OP) ? x[k] : x4[uu];
-        const double ck_in = (OP == OP_LOWER_SOLVE) ? c4[uu] : ((OP == OP_UPPER_SOLVE) ? c[k] : 1.0);
-        double wk[J];
-        if (OP == OP_LOWER_SOLVE || OP == OP_UPPER_SOLVE || OP == OP_LOWER_DOT) ldrow<J>(w, k, wk);
-        double Ak[J][J], bk[J];
-        if (OP == OP_LOWER_SOLVE) {  // g' = (a - w p^T / c) g + w x / c
-            const double ic = 1.0 / ck_in;
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                const double wi = wk[i] * ic;
-                bk[i] = wi * xk;
-#pragma unroll
-                for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j] - wi * p[j];
-            }
-        } else if (OP == OP_UPPER_SOLVE) {  // g' = (a^T - p w^T / c) g + p x / c
-            const double ic = 1.0 / ck_in;
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                const double pi = p[i] * ic;
-                bk[i] = pi * xk;
-#pragma unroll
-                for (int j = 0; j < J; ++j) Ak[i][j] = a[j][i] - pi * wk[j];
-            }
-        } else if (OP == OP_LOWER_DOT) {  // g' = a g + w x
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                bk[i] = wk[i] * xk;
-#pragma unroll
-                for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j];
-            }
-        } else if (OP == OP_SYMM_LOWER || OP == OP_GEN_LOWER) {  // g' = a g + q x
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                bk[i] = m.q[i] * xk;
-#pragma unroll
-                for (int j = 0; j < J; ++j) Ak[i][j] = a[i][j];
-            }
-        } else {  // OP_SYMM_UPPER, OP_GEN_UPPER: g' = a^T g + p x
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                bk[i] = p[i] * xk;
-#pragma unroll
-                for (int j = 0; j < J; ++j) Ak[i][j] = a[j][i];
-            }
-        }
-        double nA[J][J], nb[J];
-        matmul<J>(Ak, R.A, nA);
-#pragma unroll
-        for (int i = 0; i < J; ++i) {
-            double s = bk[i];
-#pragma unroll
-            for (int j = 0; j < J; ++j) s += Ak[i][j] * R.b[j];
-            nb[i] = s;
-        }
-#pragma unroll
-        for (int i = 0; i < J; ++i) {
-            R.b[i] = nb[i];
-#pragma unroll
-            for (int j = 0; j < J; ++j) R.A[i][j] = nA[i][j];
-        }
-    }
-    }
-    R.store(comp, nchunks, ch);
+    if (ch < nchunks) affine_chunk_body<J, OP>(m, t, c, w, x, n, comp, nchunks, ch);
 }
-
-// replay; out may alias x only if accumulate == 0 (each thread reads x[k] before writing out[k])
 template <int J, int OP>
 __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_constant__ QsModel m, const double* __restrict__ t,
                                                                    const double* __restrict__ diag, const double* __restrict__ c,
@@ -565,134 +119,7 @@ __global__ void __launch_bounds__(QS_THREADS) affine_replay_kernel(const __grid_
                                                                    const double* gstart, int64_t nchunks, double* out,
                                                                    double* sq_part) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= nchunks) return;
-    const int64_t l0 = ch * m.chunk, l1 = min(n, l0 + m.chunk);
-    double g[J];
-    state_load<J>(g, gstart, nchunks, ch);
-    double ssum = 0.0;
-    double tprev = 0.0;
-    if (!op_reverse(OP)) tprev = (l0 == 0) ? t[0] : t[l0 - 1];
-    for (int64_t lb = l0; lb < l1; lb += 4) {
-      double t4[4], x4[4], c4[4], d4[4], o4[4];
-      if (!op_reverse(OP)) {   // forward scans: 32-byte vector accesses (see ld4)
-          ld4(t, lb, l1, t4);
-          ld4(x, lb, l1, x4);
-          if (OP == OP_LOWER_SOLVE || OP == OP_LOWER_DOT) ld4(c, lb, l1, c4);
-          if (OP == OP_SYMM_LOWER) ld4(diag, lb, l1, d4);
-      }
-#pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
-        const int64_t l = lb + uu;
-        if (l >= l1) break;
-        const int64_t k = op_reverse(OP) ? (n - 1 - l) : l;
-        double dt;
-        if (!op_reverse(OP)) { dt = t4[uu] - tprev; tprev = t4[uu]; }
-        else dt = (k == 0) ? 0.0 : (t[k] - t[k - 1]);
-        double a[J][J], p[J];
-        qs_gen<J>(m, dt, a, p);
-        const double xk = op_reverse(OP) ? x[k] : x4[uu];
-        const double ck_in = op_reverse(OP) ? ((OP == OP_UPPER_SOLVE) ? c[k] : 1.0) : c4[uu];
-        const double dk_in = (OP == OP_SYMM_LOWER) ? d4[uu] : 0.0;
-        double wk[J];
-        if (OP == OP_LOWER_SOLVE || OP == OP_UPPER_SOLVE || OP == OP_LOWER_DOT) ldrow<J>(w, k, wk);
-        double y, ng[J];
-        if (OP == OP_LOWER_SOLVE) {  // ops.py:465-468: y = (x - p@f)/d ; f = a@f + outer(q, y)
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < J; ++j) s += p[j] * g[j];
-            y = (xk - s) / ck_in;
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
-                ng[i] = v + wk[i] * y;
-            }
-            o4[uu] = y;
-        } else if (OP == OP_UPPER_SOLVE) {  // ops.py:491-494: y = (x - q@f)/d ; f = a.T@f + outer(p, y)
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < J; ++j) s += wk[j] * g[j];
-            y = (xk - s) / ck_in;
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int j = 0; j < J; ++j) v += a[j][i] * g[j];
-                ng[i] = v + p[i] * y;
-            }
-            out[k] = y;
-        } else if (OP == OP_LOWER_DOT) {  // core.py:303-305 + ops.py:310-316: c x + p . f ; f = a f + w x
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < J; ++j) s += p[j] * g[j];
-            y = ck_in * xk + s;
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
-                ng[i] = v + wk[i] * xk;
-            }
-            o4[uu] = y;
-        } else if (OP == OP_SYMM_LOWER) {  // core.py:499-505: d x + lower part
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < J; ++j) s += p[j] * g[j];
-            y = (m.d0 + dk_in) * xk + s;
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
-                ng[i] = v + m.q[i] * xk;
-            }
-            o4[uu] = y;
-        } else if (OP == OP_GEN_LOWER) {  // general.py:77-83: f_k = a_k f_{k-1} + ql_k x_k, every f_k kept
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int j = 0; j < J; ++j) v += a[i][j] * g[j];
-                ng[i] = v + m.q[i] * xk;
-            }
-            strow<J>(out, k, ng);
-            y = 0.0;
-        } else if (OP == OP_GEN_UPPER) {  // general.py:89-101: g_k = a_{k+1}^T g_{k+1} + pu_k x_k, every g_k kept.
-            // The carried state here is a_{k+1}^T g_{k+1} (this scan folds a_k^T in when it LEAVES point k).
-            double gk[J];
-#pragma unroll
-            for (int i = 0; i < J; ++i) gk[i] = g[i] + m.h[i] * xk;
-            strow<J>(out, k, gk);
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int j = 0; j < J; ++j) v += a[j][i] * g[j];
-                ng[i] = v + p[i] * xk;
-            }
-            y = 0.0;
-        } else {  // OP_SYMM_UPPER (ops.py:332-338): out += q . f ; f = a^T f + p x
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < J; ++j) s += m.q[j] * g[j];
-            y = s;
-#pragma unroll
-            for (int i = 0; i < J; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int j = 0; j < J; ++j) v += a[j][i] * g[j];
-                ng[i] = v + p[i] * xk;
-            }
-            out[k] += y;
-        }
-#pragma unroll
-        for (int i = 0; i < J; ++i) g[i] = ng[i];
-        ssum += y * y;
-      }
-      if (!op_reverse(OP) && OP != OP_GEN_LOWER) st4(out, lb, l1, o4);
-    }
-    if (sq_part) sq_part[ch] = ssum;
+    if (ch < nchunks) affine_replay_body<J, OP>(m, t, diag, c, w, x, n, gstart, nchunks, out, sq_part, ch);
 }
 
 // ---------------------------------------------------------------------------------------------

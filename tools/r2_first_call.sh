@@ -23,3 +23,7 @@ grep -h -o '"value": [0-9.]*\|"options": \[[^]]*\]\|"rel_err": [0-9.e-]*\|"digit
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:i8_update -s 40 -c 2 -o $O/r2_i8_full -f \
     python bench.py --steps 1 --warmup 1 --slices 7 --size 32768 > $O/r2_ncu.log 2>&1
 ncu -i $O/r2_i8_full.ncu-rep --page raw --csv > $O/r2_i8_full_raw.csv 2>/dev/null
+# 5. why is the CTA-pair kernel slow?  full capture of two of its launches (warp-state and memory tables)
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:i8_update_kernel_2sm -s 20 -c 2 -o $O/r2_i8_2sm_full -f \
+    python bench.py --steps 1 --warmup 1 --slices 7 --size 16384 --opt ozaki_cluster=2 > $O/r2_ncu_2sm.log 2>&1
+ncu -i $O/r2_i8_2sm_full.ncu-rep --page raw --csv > $O/r2_i8_2sm_full_raw.csv 2>/dev/null

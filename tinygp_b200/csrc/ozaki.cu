@@ -208,6 +208,18 @@ constexpr int BOXR = 64;  // rows per TMA box
 //   A_i x B_{g1-i} -> accumulator 1 (group g1)   and   A_{i-1} (previous stage) x B_{g1-i} -> accumulator 0 (group g0),
 // so S = 8 needs 20 stage loads per K chunk instead of 36: the L2 -> shared-memory operand stream, which bounds the
 // unpaired kernel at ~50 % tensor-pipe utilisation (profiles/r1_ncu_i8_update.md), shrinks 1.8x for the same MMAs.
+// Pass P of the paired loop covers digit group g0 and, if `two`, g0 + 1.  A paired pass streams g1 + 1 stages per K chunk
+// and a single pass g0 + 1, so for an odd plane count the UNPAIRED group is the cheap group 0, not the expensive last one:
+// S = 7 -> (0) (1,2) (3,4) (5,6) = 1 + 3 + 5 + 7 = 16 stage loads per K chunk for the 28 pair products (instead of
+// 2 + 4 + 6 + 7 = 19 with the single group last, or 28 unpaired); S = 8 -> (0,1) (2,3) (4,5) (6,7) = 20 for 36.
+__device__ __forceinline__ void pg_pass(int S, int pg_single, int P, int& g0, bool& two) {
+    if (pg_single) { g0 = P; two = false; return; }
+    const int odd = S & 1;
+    if (odd && P == 0) { g0 = 0; two = false; return; }
+    g0 = 2 * P - odd;
+    two = (g0 + 1 < S);
+}
+
 template <int CM, int CN, bool PG>
 __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_constant__ Maps maps, const Args g) {
     static_assert((TM / CN) % BOXR == 0 && (TN / CM) % BOXR == 0, "slice must be whole TMA boxes");
@@ -320,8 +332,9 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
             if constexpr (PG) {
                 const int npass = g.pg_single ? S : (S + 1) / 2;
                 for (int P = 0; P < npass && ok; ++P) {
-                    const int g0 = g.pg_single ? P : 2 * P;
-                    const int top = (!g.pg_single && g0 + 1 < S) ? g0 + 1 : g0;
+                    int g0; bool two;
+                    pg_pass(S, g.pg_single, P, g0, two);
+                    const int top = two ? g0 + 1 : g0;
                     for (int kc = 0; kc < KT && ok; ++kc)
                         for (int i = 0; i <= top && ok; ++i) issue_stage(i, top - i, kc);
                 }
@@ -342,8 +355,8 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
             if constexpr (PG) {
                 const int npass = g.pg_single ? S : (S + 1) / 2;
                 for (int P = 0; P < npass && ok; ++P) {
-                    const int g0 = g.pg_single ? P : 2 * P;
-                    const bool two = !g.pg_single && (g0 + 1 < S);
+                    int g0; bool two;
+                    pg_pass(S, g.pg_single, P, g0, two);
                     const int top = two ? g0 + 1 : g0;
                     if (P >= 1) {  // the epilogue must have drained both accumulators (pair P-1)
                         if (!mbar_wait(tempty, (uint32_t)((P - 1) & 1), abort_flag)) { ok = false; break; }
@@ -432,8 +445,8 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
         if constexpr (PG) {
             const int npass = g.pg_single ? S : (S + 1) / 2;
             for (int P = 0; P < npass && ok; ++P) {
-                const int g0 = g.pg_single ? P : 2 * P;
-                const bool two = !g.pg_single && (g0 + 1 < S);
+                int g0; bool two;
+                pg_pass(S, g.pg_single, P, g0, two);
                 if (!mbar_wait(tfull, (uint32_t)(P & 1), abort_flag)) { ok = false; break; }
                 tc_fence_after();
                 // group g0 weighs 2^-(12 + 7 g0); group g0 + 1 is 2^-7 of that.  a0 + a1 2^-7 is exact in fp64

@@ -127,3 +127,31 @@ def test_int8_update_splits_k_ranges_beyond_the_int32_bound(ctx):
             want -= 2.0 ** -(12 + 7 * (s + t)) * (P[s] @ P[t].T)
     assert sum(float(P[s][0] @ P[6 - s][1]) for s in range(7)) > 2 ** 31 - 1   # the last digit group, unsplit, wraps
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * max(1.0, np.abs(want).max()))
+
+
+@pytest.mark.parametrize("pairing", [1, 2])
+@pytest.mark.parametrize("rows,K,S", [(256, 128, 1), (256, 512, 3), (512, 1024, 8), (768, 384, 7), (512, 2048, 2),
+                                      (1024, 4096, 7)])
+def test_paired_cta_pair_kernel_is_exact(ctx, rows, K, S, pairing):
+    """i8_update_kernel_2sm<true>: tcgen05 cta_group::2 with two digit groups per pass (written after round 1's last GPU
+    run; same exactness harness as tests/test_ozaki_gpu.py::test_i8_update_kernel_is_exact)"""
+    from tinygp_b200 import _cabi
+    ctx.set_option("ozaki_cluster", 2)
+    ctx.set_option("ozaki_pairing", pairing)
+    rng = np.random.default_rng(rows + K + S)
+    planes = rng.integers(-64, 65, size=(S, rows, K), dtype=np.int8)
+    rs = 2.0 ** rng.integers(-2, 3, size=rows).astype(np.float64)
+    C = rng.normal(size=(rows, rows))
+    got = C.copy()
+    pl = np.ascontiguousarray(planes)
+    try:
+        ctx.check(ctx.lib.b200gp_i8_update_test(ctx.handle, _cabi.ptr(pl), S, rows, K, _cabi.ptr(rs), _cabi.ptr(got)))
+    finally:
+        ctx.set_option("ozaki_cluster", 21)
+        ctx.set_option("ozaki_pairing", 0)
+    want = C.copy()
+    P = planes.astype(np.float64)
+    for s in range(S):
+        for t in range(S - s):
+            want -= 2.0 ** -(12 + 7 * (s + t)) * (rs[:, None] * rs[None, :]) * (P[s] @ P[t].T)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))

@@ -541,6 +541,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -559,6 +566,11 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 
+// PG: paired digit groups as in i8_update_kernel<.., true> (one ring stage = (A plane i, B-half plane top - i) feeds
+// group top with A_i and group top - 1 with the previous stage's A): per SM and pair product 21.7 KB from L2 / 19 KB
+// written to shared memory instead of 48 / 48 for the unpaired 1-SM loop, and the operand reads of the tensor core drop
+// from 96 to 64 B/clk -- shared-memory bandwidth (TMA writes + UMMA reads against 128 B/clk/SM) stops being a bound.
+template <bool PG>
 __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_constant__ Maps maps, const Args g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -610,6 +622,29 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
+            if constexpr (PG) {
+                const int npass = g.pg_single ? S : (S + 1) / 2;
+                for (int P = 0; P < npass && ok; ++P) {
+                    int g0; bool two;
+                    pg_pass(S, g.pg_single, P, g0, two);
+                    const int top = two ? g0 + 1 : g0;
+                    for (int kc = 0; kc < KT && ok; ++kc)
+                        for (int i = 0; i <= top; ++i) {     // stage i: (A plane i, B-half plane top - i), one 3-D map
+                            if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; break; }
+                            uint8_t* a_dst = smem + stage * STAGE2_BYTES;
+                            uint8_t* b_dst = a_dst + A_BYTES;
+                            if (leader) mbar_expect_tx(full + stage, 2 * STAGE2_BYTES);
+                            const uint32_t lbar = mapa_rank0(smem_u32(full + stage));
+                            const int kx = g.k_begin + kc * KC;
+#pragma unroll
+                            for (int bx = 0; bx < TM / BOXR; ++bx) {
+                                tma_load_3d_2sm(a_dst + bx * BOXR * KC, &maps.all, lbar, kx, (int)grow0 + bx * BOXR, i);
+                                tma_load_3d_2sm(b_dst + bx * BOXR * KC, &maps.all, lbar, kx, (int)brow0 + bx * BOXR, top - i);
+                            }
+                            if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                        }
+                }
+            } else {
             for (int gi = 0; gi < S && ok; ++gi) {
                 for (int s = 0; s <= gi && ok; ++s) {
                     const int t = gi - s;
@@ -629,6 +664,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                     }
                 }
             }
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA drives both SMs =====
@@ -636,6 +672,57 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
+            if constexpr (PG) {
+                const int npass = g.pg_single ? S : (S + 1) / 2;
+                for (int P = 0; P < npass && ok; ++P) {
+                    int g0; bool two;
+                    pg_pass(S, g.pg_single, P, g0, two);
+                    const int top = two ? g0 + 1 : g0;
+                    if (P >= 1) {   // both accumulators drained by the epilogue of pass P-1 (8 arrivals: 4 warps x 2 CTAs)
+                        if (!mbar_wait(tempty, (uint32_t)((P - 1) & 1), abort_flag)) { ok = false; break; }
+                        tc_fence_after();
+                    }
+                    const uint32_t acc0 = tmem_base, acc1 = tmem_base + (uint32_t)TN;
+                    uint32_t accum0 = 0, accum1 = 0;
+                    for (int kc = 0; kc < KT && ok; ++kc) {
+                        uint32_t prev_a = 0;
+                        int prev_stage = 0;
+                        for (int i = 0; i <= top; ++i) {
+                            if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                            tc_fence_after();
+                            const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
+                            const uint32_t b_addr = a_addr + A_BYTES;
+                            if (two) {
+#pragma unroll
+                                for (int kk = 0; kk < KC / 32; ++kk) {   // A_i x B_{top-i}: group top
+                                    umma_i8_2sm(acc1, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), accum1);
+                                    accum1 = 1;
+                                }
+                                if (i >= 1) {
+#pragma unroll
+                                    for (int kk = 0; kk < KC / 32; ++kk) {   // A_{i-1} x B_{top-i}: group top - 1
+                                        umma_i8_2sm(acc0, make_desc(prev_a + kk * 32), make_desc(b_addr + kk * 32), accum0);
+                                        accum0 = 1;
+                                    }
+                                    tc_commit_2sm(empty + prev_stage, 0x3);   // stage i-1 is dead in both CTAs
+                                }
+                                if (i == top) tc_commit_2sm(empty + stage, 0x3);
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < KC / 32; ++kk) {
+                                    umma_i8_2sm(acc0, make_desc(a_addr + kk * 32), make_desc(b_addr + kk * 32), accum0);
+                                    accum0 = 1;
+                                }
+                                tc_commit_2sm(empty + stage, 0x3);
+                            }
+                            prev_a = a_addr;
+                            prev_stage = stage;
+                            if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    if (ok) tc_commit_2sm(tfull, 0x3);    // both accumulators (in both CTAs) of pass P complete
+                }
+            } else
             for (int gi = 0; gi < S && ok; ++gi) {
                 const int acc = gi & 1;
                 if (gi >= 2) {
@@ -673,6 +760,42 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
         const uint32_t tempty_leader0 = mapa_rank0(smem_u32(tempty + 0));
         const uint32_t tempty_leader1 = mapa_rank0(smem_u32(tempty + 1));
         bool ok = true;
+        if constexpr (PG) {
+            const int npass = g.pg_single ? S : (S + 1) / 2;
+            for (int P = 0; P < npass && ok; ++P) {
+                int g0; bool two;
+                pg_pass(S, g.pg_single, P, g0, two);
+                if (!mbar_wait(tfull, (uint32_t)(P & 1), abort_flag)) { ok = false; break; }
+                tc_fence_after();
+                const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * g0)) << 52);
+                const double sc = -(rsi * wg);
+#pragma unroll 1
+                for (int cb = 0; cb < TN / 32; ++cb) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), r0);
+                    if (two) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TN + cb * 32), r1);
+                    const int64_t gc = gcol0 + cb * 32;
+                    if (row_ok && gc < g.n_rows) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
+                            double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
+                            double tx = (double)(int)r0[j], ty = (double)(int)r0[j + 1];
+                            if (two) {   // group g0 + 1 is 2^-7 of group g0: a0 + a1 2^-7 is exact, one rounding for the pair
+                                tx = fma((double)(int)r1[j], 0.0078125, tx);
+                                ty = fma((double)(int)r1[j + 1], 0.0078125, ty);
+                            }
+                            cv.x = fma(sc * rj.x, tx, cv.x);
+                            cv.y = fma(sc * rj.y, ty, cv.y);
+                            *reinterpret_cast<double2*>(crow + gc + j) = cv;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader0);
+            }
+        } else
         for (int gi = 0; gi < S && ok; ++gi) {
             const int acc = gi & 1;
             if (!mbar_wait(tfull + acc, (gi >> 1) & 1, abort_flag)) { ok = false; break; }
@@ -1049,10 +1172,11 @@ static void launch_cfg(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     ctx->prof.i8_ops += 2.0 * pairs_tiles * (double)TM * TN * (double)a.K;
 }
 
+template <bool PG>
 static void launch_2sm(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     static bool attr = false;
     if (!attr) {
-        CUDA_CHECK(cudaFuncSetAttribute(i8_update_kernel_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(i8_update_kernel_2sm<PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
         attr = true;
     }
     const int ptm = (a.tiles_m + 1) / 2;
@@ -1070,7 +1194,7 @@ static void launch_2sm(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, i8_update_kernel_2sm, maps, a));
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, i8_update_kernel_2sm<PG>, maps, a));
     ctx->launches++;
     double pairs_tiles = 0.0;
     for (int pi = 0; pi < ptm; ++pi)
@@ -1112,7 +1236,7 @@ static void launch_update_one(b200gp_ctx* ctx, const Maps& maps, const Args& a) 
         throw GpError("ozaki_layout=1 (chunk-major digit planes) is not implemented for the wide / 2-SM kernels");
     switch ((int)ctx->oz_cluster) {
         case 1: launch_wide(ctx, maps, a); break;
-        case 2: launch_2sm(ctx, maps, a); break;
+        case 2: if (ctx->oz_pairing) launch_2sm<true>(ctx, maps, a); else launch_2sm<false>(ctx, maps, a); break;
 #define OZ_CFG(CMv, CNv) \
     do { if (ctx->oz_pairing) launch_cfg<CMv, CNv, true>(ctx, maps, a); else launch_cfg<CMv, CNv, false>(ctx, maps, a); } while (0)
         case 11: OZ_CFG(1, 1); break;

@@ -16,6 +16,7 @@ from tinygp_b200 import kernels, means
 from tinygp_b200.kernels.quasisep import Quasisep
 from tinygp_b200.noise import Diagonal, Noise
 from tinygp_b200.solvers import DirectSolver, QuasisepSolver
+from tinygp_b200.solvers.lazy import LazyConditionedSolver
 
 
 class GaussianProcess:
@@ -70,15 +71,25 @@ class GaussianProcess:
         if noise is None:
             diag = _default_diag(mean_value) if diag is None else diag
             noise = Diagonal(diag=np.broadcast_to(np.asarray(diag, dtype=np.float64), mean_value.shape).copy())
+        cond_kernel = kernels.Conditioned(self.X, self.solver, kernel)
+        cond_mean = means.Conditioned(self.X, alpha, kernel, include_mean=include_mean, mean_function=self.mean_function)
+        if X_test is None and kernel is self.kernel and hasattr(self.solver, "conditioned_variance"):
+            # quasiseparable process conditioned at its own inputs (solver.py:124-129): linear in N until a caller
+            # asks for something that needs the matrix (solvers/lazy.py)
+            parent = self.solver
+            gp = GaussianProcess(
+                cond_kernel, self.X, noise=noise, mean=cond_mean, mean_value=mean_value,
+                solver=lambda k, X, n, covariance=None: LazyConditionedSolver(parent, k, kernel, X, n),
+            )
+            return ConditionResult(log_prob, gp)
         covariance_value = self.solver.condition(kernel, X_test, noise)  # gp.py:201
         if X_test is None:
             X_test = self.X
         gp = GaussianProcess(  # gp.py:208-221: the conditional GP factors the M x M covariance again
-            kernels.Conditioned(self.X, self.solver, kernel),
+            cond_kernel,
             X_test,
             noise=noise,
-            mean=means.Conditioned(self.X, alpha, kernel, include_mean=include_mean,
-                                   mean_function=self.mean_function),
+            mean=cond_mean,
             mean_value=mean_value,
             covariance_value=covariance_value,
             solver=DirectSolver,

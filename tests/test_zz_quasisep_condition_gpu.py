@@ -155,3 +155,31 @@ def test_paired_cta_pair_kernel_is_exact(ctx, rows, K, S, pairing):
         for t in range(S - s):
             want -= 2.0 ** -(12 + 7 * (s + t)) * (rs[:, None] * rs[None, :]) * (P[s] @ P[t].T)
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
+
+
+@pytest.mark.parametrize("slices", [0, 7])
+def test_panel_overlap_option_gives_the_same_factorisation(ctx, slices):
+    """option panel_overlap: inside a panel the rows below the diagonal tile are updated on a side stream while potf2
+    runs; a pure reordering of independent work, so the result must be bit-identical to the serial order"""
+    from tinygp_b200 import kernels
+    n = 3000
+    rng = np.random.default_rng(17)
+    X = rng.uniform(0, 20.0 * (n / 65536.0) ** (1 / 3), (n, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    k = 1.3 * kernels.ExpSquared(0.8)
+    ctx.set_option("nb", 512)
+    ctx.set_option("ozaki_min_n", 0 if slices else 1 << 40)
+    ctx.set_option("ozaki_slices", slices if slices else 7)
+    out = []
+    try:
+        for flag in (0, 1, 1):
+            ctx.set_option("panel_overlap", flag)
+            out.append(GaussianProcess(k, X, diag=0.1).log_probability(y))
+    finally:
+        ctx.set_option("panel_overlap", 0)
+        ctx.set_option("ozaki_min_n", 8192)
+        ctx.set_option("ozaki_slices", 7)
+        ctx.set_option("nb", 1024)
+    assert out[0] == out[1] == out[2], out
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+    assert rel(out[0], lpo) < LOGP_RTOL

@@ -153,6 +153,7 @@ int b200gp_destroy(b200gp_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -191,6 +192,8 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
         _ctx->oz_layout = value;
     } else if (!strcmp(key, "ozaki_pairing")) {
         _ctx->oz_pairing = (value == 2) ? 2 : (value ? 1 : 0);
+    } else if (!strcmp(key, "panel_overlap")) {
+        _ctx->panel_overlap = value ? 1 : 0;
     } else if (!strcmp(key, "ozaki_lookahead")) {
         _ctx->oz_lookahead = value;
     } else if (!strcmp(key, "ozaki_cluster")) {

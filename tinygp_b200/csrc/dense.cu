@@ -667,20 +667,55 @@ void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb) {
     b200gp_ctx* ctx = s->ctx;
     const int64_t np = s->np, ld = s->ld;
     double* M = s->mat;
+    // Option "panel_overlap": potf2 runs on ONE SM (a 128 x 128 Cholesky + inverse is a serial chain) while it only
+    // needs the diagonal tile of the column-block update.  So that update is split: the diagonal tile then potf2 stay
+    // on the main stream, the rows below go to a side stream and are joined before the triangular solve that needs both.
+    const bool overlap = ctx->panel_overlap != 0;
+    cudaStream_t main_stream = ctx->stream;
+    cudaEvent_t e_main = nullptr, e_side = nullptr;
+    if (overlap) {
+        if (!ctx->stream3) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+        e_main = ctx->get_event();
+        e_side = ctx->get_event();
+    }
     for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
         const int64_t c0 = k0 + j0;
+        const int rows_below = (int)((np - c0) / TILE) - 1;
+        bool side_pending = false;
         if (j0 > 0) {
             // column block c0 -= (already factored panel columns) x (rows c0.. of them)^T
-            gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld,
-                    (int)((np - c0) / TILE), 1, (int)j0, -1.0, 1, 0);
+            if (overlap && rows_below > 0) {
+                CUDA_CHECK(cudaEventRecord(e_main, main_stream));            // everything up to the previous solve
+                CUDA_CHECK(cudaStreamWaitEvent(ctx->stream3, e_main, 0));
+                ctx->stream = ctx->stream3;
+                try {
+                    gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + k0, ld, M + c0 * ld + k0, ld,
+                            rows_below, 1, (int)j0, -1.0, 1, 0);
+                } catch (...) {
+                    ctx->stream = main_stream;
+                    throw;
+                }
+                ctx->stream = main_stream;
+                CUDA_CHECK(cudaEventRecord(e_side, ctx->stream3));
+                side_pending = true;
+                gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld, 1, 1, (int)j0, -1.0, 1, 0);
+            } else {
+                gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld,
+                        (int)((np - c0) / TILE), 1, (int)j0, -1.0, 1, 0);
+            }
         }
         potf2(ctx, M + c0 * ld + c0, ld, s->linv + (c0 / TILE) * TILE * TILE, s->info_dev, (int)c0);
         if (c0 + TILE < np) {
+            if (side_pending) CUDA_CHECK(cudaStreamWaitEvent(main_stream, e_side, 0));
             // rows below: X = A * inv(L_jj)^T, in place (one tile column, K = 128)
             gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld,
                     s->linv + (c0 / TILE) * TILE * TILE, TILE, (int)((np - c0 - TILE) / TILE), 1, TILE,
                     1.0, 0, 0);
         }
+    }
+    if (overlap) {
+        ctx->event_pool.push_back(e_main);
+        ctx->event_pool.push_back(e_side);
     }
 }
 

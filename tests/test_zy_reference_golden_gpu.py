@@ -6,8 +6,7 @@ hide the results of the files before it."""
 import numpy as np
 import pytest
 
-import refcases  # noqa: F401  (path set up by test_reference_golden)
-from test_reference_golden import CASES, GOLD, IDS, compare, product_namespace
+from test_reference_golden import CASES, GOLD, IDS, compare, product_namespace, refcases  # noqa: F401
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", CASES, ids=IDS)

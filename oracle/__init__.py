@@ -16,7 +16,7 @@ relations at rtol=atol=5e-7, src/tinygp/test_utils.py:9-26).  The oracle is pinn
       (vmap = loop + stack, lax.scan = loop, jit = identity, linalg = LAPACK); every line of
       tinygp's own algorithm runs as written.  The stand-ins are validated by the reference's
       own test-suite (163 tests pass over them, ``tests/golden/run_reference_tests.sh``).
-      30 cases: BASELINE configs 1-4 at oracle sizes, every stationary leaf / distance default /
+      34 cases: BASELINE configs 1-5 at oracle sizes, every stationary leaf / distance default /
       sum / product / transform, every state-space kernel, ties, both scan modes, non-PD -> -inf,
       log_probability / normalization / solves / condition / predict.  The oracle agrees with
       them to <= 1e-12 (``tests/test_reference_golden.py``, asserted at 1e-10).  Caveat, stated

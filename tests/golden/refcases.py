@@ -76,6 +76,11 @@ CASES = [
     dict(name="linear_matrix_3d", kind="dense", kernel="transforms.Linear(np.array([[0.9, 0.1, 0.0], [0.0, 1.2, -0.3], [0.2, 0.0, 0.7]]), kernels.ExpSquared())", n=70, d=3, span=4.0, diag=0.05, seed=13),
     dict(name="cholesky_3d", kind="dense", kernel=f"transforms.Cholesky.from_parameters(np.array([1.1, 0.8, 1.4]), np.array([0.2, -0.1, 0.3]), kernels.Matern52({L2}))", n=70, d=3, span=4.0, diag=0.05, seed=14),
     dict(name="subspace_additive_3d", kind="dense", kernel="transforms.Subspace(0, kernels.ExpSquared(1.2)) + 0.5 * transforms.Subspace(np.array([1, 2]), kernels.Matern32(0.9))", n=70, d=3, span=4.0, diag=0.05, seed=15),
+    # ---- BASELINE config 5: corners of the (scale, amplitude) hyper-parameter grid, same X ~ U(0, 8)^3 density
+    dict(name="c5_grid_scale_lo_amp_lo", kind="dense", kernel="0.1 * kernels.ExpSquared(scale=10 ** -0.5)", n=128, d=3, span=8.0 * (128 / 4096.0) ** (1 / 3.0), diag=0.1, seed=49385),
+    dict(name="c5_grid_scale_lo_amp_hi", kind="dense", kernel="10.0 * kernels.ExpSquared(scale=10 ** -0.5)", n=128, d=3, span=8.0 * (128 / 4096.0) ** (1 / 3.0), diag=0.1, seed=49385),
+    dict(name="c5_grid_scale_hi_amp_lo", kind="dense", kernel="0.1 * kernels.ExpSquared(scale=10 ** 0.5)", n=128, d=3, span=8.0 * (128 / 4096.0) ** (1 / 3.0), diag=0.1, seed=49385),
+    dict(name="c5_grid_scale_hi_amp_hi", kind="dense", kernel="10.0 * kernels.ExpSquared(scale=10 ** 0.5)", n=128, d=3, span=8.0 * (128 / 4096.0) ** (1 / 3.0), diag=0.1, seed=49385),
     # ---- quasiseparable (QuasisepSolver): BASELINE config 4 kernel, every state-space model, ties, both scan modes
     dict(name="c4_sho_m32_n200", kind="quasisep", kernel="quasisep.SHO(omega=1.5, quality=3.0, sigma=1.8) + quasisep.Matern32(scale=1.5, sigma=0.9)", n=200, span=20.0, diag=0.1, seed=49384),
     dict(name="c4_sho_m32_n200_parallel", kind="quasisep", kernel="quasisep.SHO(omega=1.5, quality=3.0, sigma=1.8) + quasisep.Matern32(scale=1.5, sigma=0.9)", n=200, span=20.0, diag=0.1, seed=49384, parallel=True),

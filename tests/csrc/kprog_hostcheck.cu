@@ -24,6 +24,17 @@ int hostcheck_kernel_matrix(const double* prog, int n_rows, const double* X1, in
     }
 }
 
+// parse -> kprog_encode -> rows; returns the number of rows written (<= max_rows) or -1
+int hostcheck_reencode(const double* prog, int n_rows, int ndim, double* out, int max_rows) {
+    try {
+        const std::vector<double> rows = kprog_encode(parse_prog_impl(prog, n_rows, ndim));
+        const int n = (int)(rows.size() / B200GP_PROG_STRIDE);
+        if (n > max_rows) return -1;
+        for (size_t i = 0; i < rows.size(); ++i) out[i] = rows[i];
+        return n;
+    } catch (const std::exception&) { return -1; }
+}
+
 int hostcheck_kernel_diag(const double* prog, int n_rows, int ndim, double* out, char* err) {
     try {
         const KProg P = parse_prog_impl(prog, n_rows, ndim);

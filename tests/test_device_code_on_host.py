@@ -266,3 +266,17 @@ def test_affine_scans_match_the_oracle(lib, name, n, chunk):
         lo = o.qs_lower_matmul(so.p, so.q, so.a, x[:, None])[:, 0]
         up = o.qs_upper_matmul(so.p, so.q, so.a, x[:, None])[:, 0]
         np.testing.assert_allclose(ky, so.d * x + lo + up, rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize("case", _dense_cases()[0], ids=[c["name"] for c in _dense_cases()[0]])
+def test_parsed_programs_re_encode_to_the_same_rows(klib, case):
+    """kprog_encode (used when a parsed program crosses the C-ABI again: the streaming factorisation of very large N)
+    must reproduce the host lowering row for row -- including the metric definitions of input transforms"""
+    from test_reference_golden import product_namespace
+    refcases = _dense_cases()[1]
+    k = product_namespace().kernel(case["kernel"])
+    prog, x = k.lower_for(refcases._inputs(case)["X"][:4])
+    out = np.zeros((prog.shape[0] + 4, 4))
+    n = klib.hostcheck_reencode(_p(prog), prog.shape[0], x.shape[1], _p(out), out.shape[0])
+    assert n == prog.shape[0]
+    np.testing.assert_array_equal(out[:n], prog)

@@ -154,3 +154,24 @@ static inline KProg parse_prog_impl(const double* prog, int n_rows, int ndim) {
     return P;
 }
 
+
+// inverse of parse_prog_impl: the program rows (metric definitions first, then the instructions with the metric index
+// folded back into the distance code) -- used where a parsed program has to cross the C-ABI again
+static inline std::vector<double> kprog_encode(const KProg& P) {
+    std::vector<double> prog;
+    for (int k = 0; k < P.nmetric; ++k) {
+        const int r = P.mrows[k], c = P.mcols;
+        const int nd_rows = (r * c + B200GP_PROG_STRIDE - 1) / B200GP_PROG_STRIDE;
+        prog.push_back((double)B200GP_OP_METRIC); prog.push_back((double)(k + 1));
+        prog.push_back((double)r); prog.push_back((double)c);
+        std::vector<double> flat((size_t)nd_rows * B200GP_PROG_STRIDE, 0.0);
+        for (int i = 0; i < r; ++i)
+            for (int j = 0; j < c; ++j) flat[(size_t)i * c + j] = P.M[k][i * B200GP_METRIC_MAX_DIM + j];
+        prog.insert(prog.end(), flat.begin(), flat.end());
+    }
+    for (int i = 0; i < P.n; ++i) {
+        prog.push_back((double)P.op[i]); prog.push_back((double)(P.dist[i] + 2 * P.metric[i]));
+        prog.push_back(P.p0[i]); prog.push_back(P.p1[i]);
+    }
+    return prog;
+}

@@ -22,6 +22,7 @@
 //   warps 2-5: epilogue: tcgen05.ld 32x32b -> cvt -> C -= rs_i rs_j 2^-(12+7g) G_g  (fp64 RMW on the tile)
 // Two 256-column accumulators ping-pong so the epilogue of group g overlaps the MMAs of group g+1.
 #include "common.cuh"
+#include "kprog.cuh"
 #include <cuda.h>
 #include <limits.h>
 
@@ -1830,13 +1831,10 @@ int b200gp_mg_finish(b200gp_mg* m, double* logp) {
 // single-GPU fused log_probability through the same step functions (world size 1, streaming)
 double ozaki_logp_streaming(b200gp_ctx* ctx, const KProg& P, const double* X, int64_t n, int ndim, const double* diag,
                             const double* resid, int S) {
-    // re-encode the program for the C entry point
-    std::vector<double> prog((size_t)P.n * B200GP_PROG_STRIDE);
-    for (int i = 0; i < P.n; ++i) {
-        prog[4 * i + 0] = P.op[i]; prog[4 * i + 1] = P.dist[i]; prog[4 * i + 2] = P.p0[i]; prog[4 * i + 3] = P.p1[i];
-    }
+    const std::vector<double> prog = kprog_encode(P);   // kprog.cuh: metric definitions + instructions
+    const int n_rows = (int)(prog.size() / B200GP_PROG_STRIDE);
     b200gp_mg* m = nullptr;
-    if (b200gp_mg_create(ctx, prog.data(), P.n, X, n, ndim, diag, resid, S, 1, &m)) throw GpError(ctx->err);
+    if (b200gp_mg_create(ctx, prog.data(), n_rows, X, n, ndim, diag, resid, S, 1, &m)) throw GpError(ctx->err);
     double lp = 0.0;
     int rc = 0;
     const int64_t np = m->s->np;

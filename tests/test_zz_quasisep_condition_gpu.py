@@ -159,8 +159,9 @@ def test_paired_cta_pair_kernel_is_exact(ctx, rows, K, S, pairing):
 
 @pytest.mark.parametrize("slices", [0, 7])
 def test_panel_overlap_option_gives_the_same_factorisation(ctx, slices):
-    """option panel_overlap: inside a panel the rows below the diagonal tile are updated on a side stream while potf2
-    runs; a pure reordering of independent work, so the result must be bit-identical to the serial order"""
+    """options panel_overlap (inside a panel the rows below the diagonal tile are updated on a side stream while potf2
+    runs) and build_ahead (block column J+1 is generated on a side stream under the int8 update of column J): pure
+    reorderings of independent work, so the results must be bit-identical to the serial order"""
     from tinygp_b200 import kernels
     n = 3000
     rng = np.random.default_rng(17)
@@ -172,14 +173,16 @@ def test_panel_overlap_option_gives_the_same_factorisation(ctx, slices):
     ctx.set_option("ozaki_slices", slices if slices else 7)
     out = []
     try:
-        for flag in (0, 1, 1):
-            ctx.set_option("panel_overlap", flag)
+        for overlap, ahead in ((0, 0), (1, 0), (0, 1), (1, 1)):
+            ctx.set_option("panel_overlap", overlap)
+            ctx.set_option("build_ahead", ahead)
             out.append(GaussianProcess(k, X, diag=0.1).log_probability(y))
     finally:
         ctx.set_option("panel_overlap", 0)
+        ctx.set_option("build_ahead", 0)
         ctx.set_option("ozaki_min_n", 8192)
         ctx.set_option("ozaki_slices", 7)
         ctx.set_option("nb", 1024)
-    assert out[0] == out[1] == out[2], out
+    assert out[0] == out[1] == out[2] == out[3], out
     lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
     assert rel(out[0], lpo) < LOGP_RTOL

@@ -71,6 +71,7 @@ struct b200gp_ctx {
     int64_t oz_slices = 7;
     int64_t oz_lookahead = 0;   // overlap the fp64 panel factorisation with the int8 update on a second stream
     cudaStream_t stream2 = nullptr;
+    int64_t build_ahead = 0;    // 1: generate block column J+1 on a side stream under the int8 update of column J
     int64_t panel_overlap = 0;  // 1: inside a panel, update the rows below the diagonal tile on a side stream while potf2 runs
     cudaStream_t stream3 = nullptr;
     int64_t oz_prefetch = 0;    // L2 prefetch distance (K-chunks of 128) of the int8 update's TMA producer

@@ -192,6 +192,8 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
         _ctx->oz_layout = value;
     } else if (!strcmp(key, "ozaki_pairing")) {
         _ctx->oz_pairing = (value == 2) ? 2 : (value ? 1 : 0);
+    } else if (!strcmp(key, "build_ahead")) {
+        _ctx->build_ahead = value ? 1 : 0;
     } else if (!strcmp(key, "panel_overlap")) {
         _ctx->panel_overlap = value ? 1 : 0;
     } else if (!strcmp(key, "ozaki_lookahead")) {

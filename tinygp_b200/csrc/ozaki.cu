@@ -1433,12 +1433,25 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
         ctx->prof.syrk_launches++;
     };
 
+    // Option "build_ahead": the kernel tiles of block column J+1 depend on nothing but X, so they are generated on a side
+    // stream while the int8 update of column J runs (its CTAs leave most issue slots of an SM idle, and its last,
+    // partially filled wave leaves whole SMs idle) instead of serially in front of update J+1.  Same values.
+    const bool build_ahead = (ctx->build_ahead != 0) && !lookahead;
+    cudaEvent_t ev_build = nullptr;
+    if (build_ahead) {
+        if (!ctx->stream2) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        ev_build = ctx->get_event();
+        CUDA_CHECK(cudaEventRecord(ev_build, upd));                  // X / diag uploads and the resets above
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->stream2, ev_build, 0));
+    }
+
     for (int J = 0; J < ncol; ++J) {
         const int64_t c0 = (int64_t)J * NB;
         const int64_t kb = (NB < np - c0) ? NB : (np - c0);
         // ---- stream upd: generate the block column, then C -= L[c0:, 0:c0] L[c0:c0+kb, 0:c0]^T on the int8 pipe
         ctx->stream = upd;
-        dense_build_region(s, c0, c0, kb);
+        if (build_ahead && J >= 1) CUDA_CHECK(cudaStreamWaitEvent(upd, ev_build, 0));   // generated during iteration J-1
+        else dense_build_region(s, c0, c0, kb);
         if (lookahead) {
             if (J >= 2) update(c0, kb, 0, (int64_t)(J - 1) * NB);                 // panels 0 .. J-2
             if (J >= 1) {
@@ -1447,6 +1460,18 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
             }
         } else if (J >= 1) {
             update(c0, kb, 0, c0);
+        }
+        if (build_ahead && J + 1 < ncol) {   // column J+1 is not touched by anything else until its own update
+            const int64_t c1 = c0 + NB, kb1 = (NB < np - c1) ? NB : (np - c1);
+            ctx->stream = ctx->stream2;
+            try {
+                dense_build_region(s, c1, c1, kb1);
+            } catch (...) {
+                ctx->stream = upd;
+                throw;
+            }
+            ctx->stream = upd;
+            CUDA_CHECK(cudaEventRecord(ev_build, ctx->stream2));
         }
         if (J >= 1) {   // exact diagonal part of the dropped digit pairs (all previous panels)
             oz::diag_correct_kernel<<<(unsigned)((kb + 255) / 256), 256, 0, upd>>>(s->mat, ld, corr, (int64_t)J * slots_per_panel,
@@ -1476,6 +1501,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
     }
     ctx->stream = upd;
     CUDA_CHECK(cudaGetLastError());
+    if (ev_build) ctx->event_pool.push_back(ev_build);
     if (lookahead) {
         CUDA_CHECK(cudaStreamWaitEvent(upd, ev_cut[ncol - 1], 0));   // join
         for (int j = 0; j < ncol; ++j) { ctx->event_pool.push_back(ev_upd[j]); ctx->event_pool.push_back(ev_cut[j]); }

@@ -369,6 +369,9 @@ def run_quasisep(args, rank, local_rank, world):
     stream = torch.cuda.current_stream()
     if args.qs_chunk:
         ctx.set_option("qs_chunk", args.qs_chunk)
+    for kv in args.opt:                            # tuning experiments, e.g. --opt qs_tree=1
+        key, _, val = kv.partition("=")
+        ctx.set_option(key, int(val))
     n = args.n if args.n != N_DENSE else 10_000_000
     rng = np.random.default_rng(49384)
     t = np.sort(rng.uniform(0, n / 10.0, n))
@@ -603,7 +606,7 @@ def main():
                          "same 4.7e-12 distance to the LAPACK golden at N=65536 as 8 planes), 8 = 55 bits, "
                          "0 = native fp64 DMMA")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
-                    help="library option for tuning runs (b200gp_set_option), recorded in config.options; dense workload")
+                    help="library option for tuning runs (b200gp_set_option); dense and quasisep workloads")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

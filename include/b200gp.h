@@ -79,7 +79,9 @@ const char* b200gp_last_error(b200gp_ctx* ctx);
 int64_t b200gp_launch_count(b200gp_ctx* ctx);
 /* tunables: "nb" (outer panel width, multiple of 128), "profile" (0/1: per-kernel CUDA-event timers),
  * "panel_overlap" (0/1: inside a panel, update the rows below the diagonal tile on a side stream while potf2 runs),
- * "build_ahead" (0/1: generate block column J+1 on a side stream under the int8 update of column J) */
+ * "build_ahead" (0/1: generate block column J+1 on a side stream under the int8 update of column J),
+ * "qs_chunk" (points per thread in the quasiseparable scans), "qs_tree" (0: thread-sequential fan-in-16 tree over the
+ * chunk composites, 1: warp-shuffle scan kernels, fan-in 32) */
 int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value);
 
 /* per-kernel device timings accumulated while option "profile"=1 (ms, CUDA events on ctx stream) */

@@ -8,11 +8,64 @@
 
 namespace {
 
+int g_tree_mode = 0;   // 0: fan-in-16 thread-sequential tree, 1: warp-shuffle scan (fan-in 32)
+
+// the algorithm of warp_scan_kernel / warp_propagate_kernel / run_tree_warp (quasisep.cu), lane by lane: a "warp" is an
+// array of 32 composites, __shfl_up becomes an indexed read of the previous step's array
+template <class Op>
+void host_tree_warp_top(const std::vector<double>& comp, int64_t n, std::vector<double>& start) {
+    typedef typename StateOf<Op>::type State;
+    const int64_t nw = (n + 31) / 32;
+    std::vector<double> pre((size_t)Op::SIZE * n), totals((size_t)Op::SIZE * nw);
+    for (int64_t w = 0; w < nw; ++w) {                               // warp_scan_kernel
+        Op cur[32], nxt[32];
+        for (int lane = 0; lane < 32; ++lane) {
+            const int64_t i = w * 32 + lane;
+            if (i < n) cur[lane].load(comp.data(), n, i);
+            else cur[lane].identity();
+        }
+        for (int d = 1; d < 32; d <<= 1) {
+            for (int lane = 0; lane < 32; ++lane) {
+                if (lane >= d) { Op left = cur[lane - d]; left.combine(cur[lane]); nxt[lane] = left; }
+                else nxt[lane] = cur[lane];
+            }
+            for (int lane = 0; lane < 32; ++lane) cur[lane] = nxt[lane];
+        }
+        for (int lane = 0; lane < 32; ++lane) {
+            const int64_t i = w * 32 + lane;
+            Op ex;
+            if (lane == 0) ex.identity();
+            else ex = cur[lane - 1];
+            if (i < n) ex.store(pre.data(), n, i);
+        }
+        const int64_t last = ((n - w * 32) < 32 ? (n - w * 32) : 32) - 1;
+        cur[last].store(totals.data(), nw, w);
+    }
+    std::vector<double> pstart;
+    if (n > 32) {
+        pstart.resize((size_t)Op::STATE * nw);
+        host_tree_warp_top<Op>(totals, nw, pstart);
+    }
+    for (int64_t i = 0; i < n; ++i) {                                // warp_propagate_kernel
+        State s;
+        if (n > 32) state_load(s, pstart.data(), nw, i >> 5);
+        else state_zero(s);
+        Op e;
+        e.load(pre.data(), n, i);
+        e.apply(s);
+        state_store(s, start.data(), n, i);
+    }
+}
+
 // the structure of run_tree<Op> (quasisep.cu): up-sweep with fan-in TREE_R, top walk, down-sweep -- with the same
 // Op::combine / Op::apply / state_* helpers the tree kernels call
 template <class Op>
 void host_tree(const std::vector<double>& comp, int64_t n, std::vector<double>& start) {
     typedef typename StateOf<Op>::type State;
+    if (g_tree_mode == 1) {
+        host_tree_warp_top<Op>(comp, n, start);
+        return;
+    }
     if (n <= TREE_R) {                                         // tree_top_kernel
         State s;
         state_zero(s);
@@ -116,6 +169,8 @@ void generators_host(const QsModel& m, const double* t, int64_t n, double* a_out
     }
 
 extern "C" {
+
+void hostcheck_set_tree(int mode) { g_tree_mode = mode; }
 
 // model constants: J, q (h Pinf), h, d0
 int hostcheck_model(const double* comps, int ncomp, int* J, double* q, double* h, double* d0) {

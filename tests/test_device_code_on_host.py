@@ -280,3 +280,35 @@ def test_parsed_programs_re_encode_to_the_same_rows(klib, case):
     n = klib.hostcheck_reencode(_p(prog), prog.shape[0], x.shape[1], _p(out), out.shape[0])
     assert n == prog.shape[0]
     np.testing.assert_array_equal(out[:n], prog)
+
+
+@pytest.mark.parametrize("n,chunk", [(40, 1), (1100, 1), (33000, 1), (5000, 7)])
+def test_warp_scan_tree_gives_the_same_states(lib, n, chunk):
+    """option qs_tree = 1 (warp-shuffle Hillis-Steele scan over the chunk composites, fan-in 32; 1, 2 and 3 levels here):
+    the emulation of that algorithm with the device monoids reproduces the oracle for the Cholesky (Riccati), the solves
+    (Affine) and the inverse diagonal (GramBack)"""
+    k, ko = KERNELS["sho+m32"]
+    comps = k.component_array()
+    t, noise = _data(n, seed=n + 7)
+    x = np.sin(t)
+    so = o.QuasisepSolver(ko, t, o.Diagonal(noise))
+    lib.hostcheck_set_tree(1)
+    try:
+        c, w, ld, info, alpha = _factor(lib, k, t, noise, chunk, x=x)
+        out = np.zeros(n)
+        assert lib.hostcheck_affine(_p(comps), comps.shape[0], OPS["upper_solve"], _p(t), _p(noise), _p(c), _p(w), _p(x),
+                                    ctypes.c_int64(n), chunk, _p(out)) == 0
+        inv = np.zeros(n)
+        assert lib.hostcheck_inverse_diagonal(_p(comps), comps.shape[0], _p(t), ctypes.c_int64(n), _p(c), _p(w), chunk,
+                                              _p(inv)) == 0
+    finally:
+        lib.hostcheck_set_tree(0)
+    assert info == 0
+    np.testing.assert_allclose(c, so.c, rtol=1e-10, atol=0)
+    np.testing.assert_allclose(w, so.w, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(alpha, so.solve_triangular(x), rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(out, so.solve_triangular(x, transpose=True), rtol=1e-8, atol=1e-11)
+    idx = np.unique(np.r_[0, n // 2, n - 1])
+    E = np.zeros((n, idx.size)); E[idx, np.arange(idx.size)] = 1.0
+    want = so.solve_triangular(so.solve_triangular(E), transpose=True)[idx, np.arange(idx.size)]
+    np.testing.assert_allclose(inv[idx], want, rtol=1e-9, atol=0)

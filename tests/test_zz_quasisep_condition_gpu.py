@@ -186,3 +186,36 @@ def test_panel_overlap_option_gives_the_same_factorisation(ctx, slices):
     assert out[0] == out[1] == out[2] == out[3], out
     lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
     assert rel(out[0], lpo) < LOGP_RTOL
+
+
+@pytest.mark.parametrize("n", [40, 700, 40000])
+@pytest.mark.parametrize("name", ["sho+m32", "m52", "sum3"])
+def test_warp_shuffle_tree_option(ctx, name, n):
+    """option qs_tree = 1: the chunk composites are scanned by warp-shuffle (Hillis-Steele, fan-in 32) kernels instead
+    of the thread-sequential fan-in-16 tree; factor, solves, log-probability and the inverse diagonal must keep parity"""
+    t, y, noise = _data(n, seed=n)
+    k = KERNELS[name]
+    so = o.QuasisepSolver(to_oracle(k), t, o.Diagonal(noise))
+    ctx.set_option("qs_tree", 1)
+    ctx.set_option("qs_chunk", 4 if n <= 700 else 64)        # small chunks -> several tree levels at small n
+    try:
+        gp = GaussianProcess(k, t, diag=noise)
+        c, w = gp.solver.factor()
+        lp = gp.log_probability(y)
+        a = gp.solver.solve_triangular(y)
+        at = gp.solver.solve_triangular(a, transpose=True)
+        inv = gp.solver.inverse_diagonal()
+    finally:
+        ctx.set_option("qs_tree", 0)
+        ctx.set_option("qs_chunk", 64)
+    np.testing.assert_allclose(c, so.c, rtol=1e-10, atol=0)
+    np.testing.assert_allclose(w, so.w, rtol=1e-9, atol=1e-12)
+    ao = so.solve_triangular(y)
+    np.testing.assert_allclose(a, ao, rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(at, so.solve_triangular(ao, transpose=True), rtol=1e-8, atol=1e-11)
+    lpo = -0.5 * ao @ ao - so.normalization()
+    assert rel(lp, lpo) < LOGP_RTOL
+    idx = np.unique(np.r_[0, n // 2, n - 1])
+    E = np.zeros((n, idx.size)); E[idx, np.arange(idx.size)] = 1.0
+    want = so.solve_triangular(so.solve_triangular(E), transpose=True)[idx, np.arange(idx.size)]
+    np.testing.assert_allclose(inv[idx], want, rtol=1e-9, atol=0)

@@ -62,6 +62,7 @@ struct b200gp_ctx {
     int num_sms = 148;
     int64_t peak_iters = 4096;  // loop length of the fp64 peak micro-benchmarks
     int64_t qs_chunk = 64;      // points per thread in the quasiseparable scans
+    int64_t qs_tree = 0;        // 0: thread-sequential fan-in-16 tree over the chunk composites, 1: warp-shuffle scan (fan-in 32)
     int64_t potf2_version = 2;  // 1: column-at-a-time diagonal-block kernel, 2: rank-8 blocked with register tiles
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
     // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA.  7 planes = 48 bits under the

@@ -174,6 +174,9 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
     } else if (!strcmp(key, "peak_iters")) {
         if (value < 16) throw GpError("option peak_iters must be >= 16");
         _ctx->peak_iters = value;
+    } else if (!strcmp(key, "qs_tree")) {
+        if (value != 0 && value != 1) throw GpError("option qs_tree must be 0 or 1");
+        _ctx->qs_tree = value;
     } else if (!strcmp(key, "qs_chunk")) {
         if (value < 4 || value > 4096) throw GpError("option qs_chunk must be in [4, 4096]");
         _ctx->qs_chunk = value;

@@ -325,6 +325,12 @@ struct Riccati {
     static constexpr int SIZE = 3 * J * J;   // A, F, G
     static constexpr int STATE = J * J;      // f
     double A[J][J], F[J][J], G[J][J];
+    template <class Fn> __host__ __device__ void assign_map(const Riccati& s, Fn fn) {   // element-wise this = fn(s)
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) { A[i][j] = fn(s.A[i][j]); F[i][j] = fn(s.F[i][j]); G[i][j] = fn(s.G[i][j]); }
+    }
     __host__ __device__ void identity() {
 #pragma unroll
         for (int i = 0; i < J; ++i)
@@ -421,6 +427,14 @@ struct Affine {
     static constexpr int SIZE = J * J + J;  // A, b
     static constexpr int STATE = J;         // g
     double A[J][J], b[J];
+    template <class Fn> __host__ __device__ void assign_map(const Affine& s, Fn fn) {
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+            b[i] = fn(s.b[i]);
+#pragma unroll
+            for (int j = 0; j < J; ++j) A[i][j] = fn(s.A[i][j]);
+        }
+    }
     __host__ __device__ void identity() {
 #pragma unroll
         for (int i = 0; i < J; ++i) {
@@ -513,6 +527,12 @@ struct GramBack {
     static constexpr int SIZE = 2 * J * J;   // B, U
     static constexpr int STATE = J * J;      // T
     double B[J][J], U[J][J];
+    template <class Fn> __host__ __device__ void assign_map(const GramBack& s, Fn fn) {
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) { B[i][j] = fn(s.B[i][j]); U[i][j] = fn(s.U[i][j]); }
+    }
     __host__ __device__ void identity() {
 #pragma unroll
         for (int i = 0; i < J; ++i)

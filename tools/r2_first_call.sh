@@ -27,3 +27,6 @@ ncu -i $O/r2_i8_full.ncu-rep --page raw --csv > $O/r2_i8_full_raw.csv 2>/dev/nul
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:i8_update_kernel_2sm -s 20 -c 2 -o $O/r2_i8_2sm_full -f \
     python bench.py --steps 1 --warmup 1 --slices 7 --size 16384 --opt ozaki_cluster=2 > $O/r2_ncu_2sm.log 2>&1
 ncu -i $O/r2_i8_2sm_full.ncu-rep --page raw --csv > $O/r2_i8_2sm_full_raw.csv 2>/dev/null
+# 6. quasisep (BASELINE config 4): default tree vs the warp-shuffle scan over the chunk composites
+timeout 200 python bench.py --workload quasisep --steps 5 --warmup 3 > $O/r2_bench_qs.json 2> $O/r2_bench_qs.err
+timeout 200 python bench.py --workload quasisep --steps 5 --warmup 3 --opt qs_tree=1 > $O/r2_bench_qs_tree1.json 2> $O/r2_bench_qs_tree1.err

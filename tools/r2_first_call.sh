@@ -14,7 +14,7 @@ tail -3 $O/r2_pytest_gpu.log
 for S in 8 7 6 5; do
   timeout 200 python bench.py --quick --steps 2 --warmup 2 --slices $S > $O/r2_bench_S$S.json 2> $O/r2_bench_S$S.err
 done
-for OPTS in "ozaki_pairing=1" "ozaki_pairing=1 ozaki_layout=1" "ozaki_layout=1" "ozaki_pairing=1 ozaki_cluster=11" "ozaki_pairing=1 ozaki_cluster=22" "ozaki_cluster=2" "ozaki_cluster=2 ozaki_pairing=1" "ozaki_cluster=1" "panel_overlap=1" "build_ahead=1" "ozaki_pairing=1 panel_overlap=1 build_ahead=1"; do
+for OPTS in "ozaki_pairing=1" "ozaki_pairing=1 ozaki_layout=1" "ozaki_layout=1" "ozaki_pairing=1 ozaki_cluster=11" "ozaki_pairing=1 ozaki_cluster=22" "ozaki_cluster=2" "ozaki_cluster=2 ozaki_pairing=1" "ozaki_cluster=2 ozaki_pairing=2" "ozaki_cluster=1" "panel_overlap=1" "build_ahead=1" "ozaki_pairing=1 panel_overlap=1 build_ahead=1"; do
   tag=$(echo "$OPTS" | tr ' =' '__')
   args=""; for o in $OPTS; do args="$args --opt $o"; done
   timeout 200 python bench.py --quick --steps 2 --warmup 2 --slices 7 $args > $O/r2_bench_S7_$tag.json 2> $O/r2_bench_S7_$tag.err

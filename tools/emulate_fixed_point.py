@@ -5,7 +5,7 @@ dot products are done as fp64 BLAS products of integer-valued matrices (exact: e
 Purpose: how does the log-probability error depend on the number of digit planes S?  (The GPU answer at full size is
 the first measurement of the next round; this gives the trend at oracle-friendly sizes with the bench's point density.)
 
-    python tools/emulate_fixed_point.py [N] [nb]        # developer tool, not part of the product or the tests
+    python tools/emulate_fixed_point.py [N] [nb] [S,S,...]   # developer tool, not part of the product or the tests
 """
 
 import sys
@@ -73,7 +73,8 @@ def main():
     exact = -0.5 * ax @ ax - np.sum(np.log(np.diag(Lx))) - 0.5 * n * np.log(2 * np.pi)
     ev = np.linalg.eigvalsh(K)
     print(f"N={n} nb={nb} exact logp={exact!r} cond(K)={ev[-1] / ev[0]:.3g}")
-    for S in (8, 7, 6, 5, 4, 3):
+    planes_list = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [8, 7, 6, 5, 4, 3]
+    for S in planes_list:
         t0 = time.time()
         lp = logp_fixed_point(K, y, S, nb)
         print(f"  S={S}: logp={lp!r} rel_err={abs(lp - exact) / abs(exact):.3e} ({time.time() - t0:.1f}s)", flush=True)

@@ -1,0 +1,212 @@
+"""The reference's own host-level tests (tests/test_gp.py, tests/test_noise.py, tests/test_kernels/test_kernels.py,
+tests/test_kernels/test_distance.py, tests/test_transforms.py of dfm/tinygp), restated against `tinygp_b200` -- same
+data, same assertions, same tolerances (5e-7, src/tinygp/test_utils.py:9-26) -- and run on the CPU with the C-ABI replaced
+by tests/hostmock.py.  What they check is the product's Python layer (algebra, shapes, error behaviour, lowering);
+cases the B200 backend refuses (Custom, DotProduct, Polynomial, noise.Dense/Banded, user Distance) assert the refusal."""
+
+import os
+import sys
+from ctypes import c_void_p
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+import hostmock  # noqa: E402
+import tinygp_b200 as tinygp  # noqa: E402
+from tinygp_b200 import GaussianProcess, _cabi, kernels, noise, transforms  # noqa: E402
+from tinygp_b200.solvers import DirectSolver  # noqa: E402
+
+
+def assert_allclose(a, b, atol=5e-7, rtol=5e-7):
+    np.testing.assert_allclose(np.asarray(a), np.asarray(b), atol=atol, rtol=rtol)
+
+
+@pytest.fixture(autouse=True)
+def mocklib():
+    lib = hostmock.MockLib()
+    ctx = _cabi.Context.__new__(_cabi.Context)
+    ctx.lib, ctx.handle, ctx.device = lib, c_void_p(1), -1
+    previous = _cabi._ctx
+    _cabi.set_context(ctx)
+    try:
+        yield lib
+    finally:
+        _cabi.set_context(previous)
+
+
+@pytest.fixture
+def random():
+    return np.random.default_rng(1058390)
+
+
+# ---- tests/test_gp.py ---------------------------------------------------------------------------------------
+@pytest.fixture
+def gp_data(random):
+    X = random.uniform(-3, 3, (50, 5))
+    y = random.normal(len(X))
+    return X, y
+
+
+def test_sample(gp_data):                                            # test_gp.py:24-38
+    X, _ = gp_data
+    gp = GaussianProcess(kernels.Matern32(1.5), X, diag=0.01, mean=np.sum)
+    y = gp.sample(543)
+    assert y.shape == (len(X),)
+    y = gp.sample(543, shape=(7, 3))
+    assert y.shape == (7, 3, len(X))
+    y = gp.sample(543, shape=(100_000,))
+    assert y.shape == (100_000, len(X))
+    assert_allclose(np.mean(y, axis=0), np.sum(X, axis=1), atol=0.015)
+    assert_allclose(np.cov(y, rowvar=False), gp.covariance, atol=0.015)
+
+
+def test_means(gp_data):                                             # test_gp.py:41-52
+    X, _ = gp_data
+    y = np.sin(X[:, 0])
+    gp1 = GaussianProcess(kernels.Matern32(1.5), X, diag=0.01, mean=lambda x: 0.0)
+    gp2 = GaussianProcess(kernels.Matern32(1.5), X, diag=0.01, mean=0.0)
+    gp3 = GaussianProcess(kernels.Matern32(1.5), X, diag=0.01)
+    assert_allclose(gp1.mean, gp2.mean)
+    assert_allclose(gp1.mean, gp3.mean)
+    assert_allclose(gp1.log_probability(y), gp2.log_probability(y))
+    assert_allclose(gp1.log_probability(y), gp3.log_probability(y))
+
+
+def test_condition_shape_error(gp_data):                             # test_gp.py:55-76 (array branch; pytrees refused)
+    X, _ = gp_data
+    y = np.sin(X[:, 0])
+    gp = GaussianProcess(kernels.ExpSquared(distance=kernels.L2Distance()), X, diag=0.1)
+    gp.condition(y, X[0][None])
+    with pytest.raises(ValueError):
+        gp.condition(y, X[0])
+    with pytest.raises((ValueError, TypeError, NotImplementedError)):
+        GaussianProcess(kernels.ExpSquared(), {"x": X}, diag=0.1)
+
+
+# ---- tests/test_noise.py ------------------------------------------------------------------------------------
+def test_diagonal():                                                 # test_noise.py:10-46
+    N = 50
+    rng = np.random.default_rng(9432)
+    diag = rng.normal(size=N)
+    nz = tinygp.noise.Diagonal(diag=diag)
+    dense = np.diag(diag)
+    rng = np.random.default_rng(6675)
+    assert_allclose(nz.diagonal(), np.diag(dense))
+    assert_allclose(nz + np.zeros_like(dense), dense)
+    y1 = rng.normal(size=dense.shape)
+    assert_allclose(nz + y1, dense + y1)
+    assert_allclose(y1 + nz, y1 + dense)
+    assert_allclose(nz @ y1, dense @ y1)
+    y2 = rng.normal(size=(N, 3))
+    assert_allclose(nz @ y2, dense @ y2)
+    y3 = rng.normal(size=N)
+    assert_allclose(nz @ y3, dense @ y3)
+    with pytest.raises(ValueError):                                  # noise.py:67-72
+        tinygp.noise.Diagonal(diag=np.float64(0.1))
+
+
+def test_banded_and_dense_are_refused():                             # test_noise.py:49-71: unsupported, loudly
+    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
+        tinygp.noise.Dense(value=np.eye(3))
+    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
+        tinygp.noise.Banded(diag=np.ones(3), off_diags=np.zeros((3, 1)))
+
+
+# ---- tests/test_kernels/test_kernels.py -----------------------------------------------------------------------
+@pytest.fixture
+def kdata(random):
+    x1 = random.uniform(-3, 3, (50, 5))
+    x2 = random.uniform(-5, 5, (50, 5))
+    return x1, x2
+
+
+def test_constant(kdata):                                            # test_kernels.py:24-43
+    x1, x2 = kdata
+    v = np.ones(3)
+    with pytest.raises(ValueError):
+        kernels.Constant(np.ones(3)).evaluate(v, v)
+    with pytest.raises(ValueError):
+        (np.ones(3) * kernels.Matern32(1.5)).evaluate(v, v)
+    factor = 2.5
+    k1 = kernels.Matern32(2.5)
+    assert_allclose(factor * k1(x1, x2), (factor * k1)(x1, x2))
+
+
+def test_custom_and_nonstationary_kernels_are_refused(kdata):        # test_kernels.py:46-63, 93-97
+    x1, x2 = kdata
+    for k in (kernels.Custom(lambda a, b: 1.0), kernels.DotProduct(), kernels.Polynomial(order=1.5, scale=0.5, sigma=1.3)):
+        with pytest.raises(NotImplementedError, match="unsupported by the B200"):
+            k(x1, x2)
+
+
+def test_ops(kdata):                                                 # test_kernels.py:66-73
+    x1, x2 = kdata
+    k1 = 1.5 * kernels.Matern32(2.5)
+    k2 = 0.9 * kernels.ExpSineSquared(scale=1.5, gamma=0.3)
+    assert_allclose(k1(x1, x2) + k2(x1, x2), (k1 + k2)(x1, x2))
+    assert_allclose(k1(x1, x2) * k2(x1, x2), (k1 * k2)(x1, x2))
+    assert_allclose(sum([k1, k2])(x1, x2), (k1 + k2)(x1, x2))        # __radd__ with 0 (base.py:110-116)
+
+
+def test_conditioned(kdata):                                         # test_kernels.py:76-90
+    x1, x2 = kdata
+    k1 = 1.5 * kernels.Matern32(2.5, distance=kernels.L2Distance())
+    k2 = 0.9 * kernels.ExpSquared(scale=1.5)
+    K = k1(x1, x1) + 0.1 * np.eye(x1.shape[0])
+    solver = DirectSolver.init(k1, x1, noise.Diagonal(np.full(x1.shape[0], 0.1)))
+    cond = kernels.Conditioned(x1, solver, k2)
+    assert_allclose(cond(x1, x2), k2(x1, x2) - k2(x1, x1) @ np.linalg.solve(K, k2(x1, x2)))
+
+
+@pytest.mark.parametrize("kernel", [kernels.ExpSineSquared, kernels.RationalQuadratic])
+def test_required_parameters(kernel):                                # test_kernels.py:123-133
+    with pytest.raises(ValueError):
+        kernel(0.5)(np.zeros((2, 1)), np.zeros((2, 1)))
+
+
+# ---- tests/test_kernels/test_distance.py ------------------------------------------------------------------------
+def test_distances_through_the_lowering(kdata):
+    """L1 / L2 distance definitions (distance.py:41-59) as seen through the leaves that use them"""
+    x1, x2 = kdata
+    d1 = np.sum(np.abs(x1[:, None, :] - x2[None, :, :]), axis=-1)
+    d2 = np.sqrt(np.sum((x1[:, None, :] - x2[None, :, :]) ** 2, axis=-1))
+    assert_allclose(kernels.Exp(1.0, distance=kernels.L1Distance())(x1, x2), np.exp(-d1))
+    assert_allclose(kernels.Exp(1.0, distance=kernels.L2Distance())(x1, x2), np.exp(-d2))
+    assert_allclose(kernels.ExpSquared(1.0)(x1, x1)[np.arange(50), np.arange(50)], np.ones(50))   # zero distance, no NaN
+    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
+        class Custom(kernels.Distance):
+            def distance(self, X1, X2):
+                return 0.0
+        kernels.Exp(1.0, distance=Custom())(x1, x2)
+
+
+# ---- tests/test_transforms.py -----------------------------------------------------------------------------------
+def test_linear():                                                   # test_transforms.py:9-16
+    kernel0 = kernels.Matern32(4.5)
+    kernel1 = transforms.Linear(1 / 4.5, kernels.Matern32())
+    assert_allclose(kernel0.evaluate(0.5, 0.1), kernel1.evaluate(0.5, 0.1))
+
+
+def test_multivariate_linear(random):                                # test_transforms.py:19-25
+    x1, x2 = random.normal(size=(2, 3))
+    L = np.linalg.cholesky(np.cov(random.normal(size=(3, 100))))
+    kernel1 = transforms.Linear(np.linalg.inv(L), kernels.Matern32(distance=kernels.L2Distance()))
+    r = np.sqrt(np.sum(np.linalg.solve(L, x1 - x2) ** 2))
+    assert_allclose(kernel1.evaluate(x1, x2), (1 + np.sqrt(3) * r) * np.exp(-np.sqrt(3) * r))
+
+
+def test_cholesky_and_subspace(random):                              # test_transforms.py:28-44
+    kernel0 = kernels.Matern32(4.5)
+    kernel1 = transforms.Cholesky(4.5, kernels.Matern32())
+    assert_allclose(kernel0.evaluate(0.5, 0.1), kernel1.evaluate(0.5, 0.1))
+    x1, x2 = random.normal(size=(2, 3))
+    L = np.linalg.cholesky(np.cov(random.normal(size=(3, 100))))
+    kernel2 = transforms.Cholesky(L, kernels.Matern32(distance=kernels.L2Distance()))
+    kernel3 = transforms.Linear(np.linalg.inv(L), kernels.Matern32(distance=kernels.L2Distance()))
+    assert_allclose(kernel2.evaluate(x1, x2), kernel3.evaluate(x1, x2))
+    kernel4 = transforms.Subspace(1, kernels.Matern32())
+    assert_allclose(kernel4.evaluate(np.array([0.5, 0.1]), np.array([-0.4, 0.7])),
+                    kernels.Matern32().evaluate(np.array([0.1]), np.array([0.7])))

@@ -23,6 +23,9 @@ class GaussianProcess:
     def __init__(self, kernel, X, *, diag=None, noise: Noise | None = None, mean=None, solver: Any | None = None,
                  mean_value=None, covariance_value: Any | None = None, **solver_kwargs: Any):
         self.kernel = kernel
+        if isinstance(X, (dict, tuple)) or np.asarray(X).dtype == object or np.ndim(X) not in (1, 2):
+            raise ValueError("coordinates must be an array of shape (N,) or (N, D); pytree coordinates (gp.py:40-44) "
+                             "are unsupported by the B200 solver backend")
         self.X = X
         if isinstance(mean, means.MeanBase):  # gp.py:81-86
             self.mean_function = mean

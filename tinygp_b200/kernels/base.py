@@ -110,6 +110,10 @@ class Lowering:
 class Kernel:
     """Base class (base.py:29-126)."""
 
+    # `ndarray * kernel` must reach Kernel.__rmul__ (as a jax array does, returning NotImplemented) instead of
+    # broadcasting into an object array; the non-scalar Constant it builds then fails in evaluate (base.py:203-209)
+    __array_ufunc__ = None
+
     def lower(self, lc: Lowering) -> list[tuple[int, int, float, float]]:
         raise NotImplementedError(
             f"{type(self).__name__} cannot be lowered to a device kernel program: "

@@ -210,3 +210,63 @@ def test_cholesky_and_subspace(random):                              # test_tran
     kernel4 = transforms.Subspace(1, kernels.Matern32())
     assert_allclose(kernel4.evaluate(np.array([0.5, 0.1]), np.array([-0.4, 0.7])),
                     kernels.Matern32().evaluate(np.array([0.1]), np.array([0.7])))
+
+
+# ---- tests/test_solvers/test_quasisep/test_solver.py -------------------------------------------------------------
+from tinygp_b200.kernels import quasisep  # noqa: E402
+from tinygp_b200.solvers import QuasisepSolver  # noqa: E402
+
+KERNEL_PAIRS = [
+    (lambda: quasisep.Matern32(sigma=1.8, scale=1.5), lambda: 1.8 ** 2 * kernels.Matern32(1.5)),
+    (lambda: 1.8 ** 2 * quasisep.Matern32(1.5), lambda: 1.8 ** 2 * kernels.Matern32(1.5)),
+    (lambda: quasisep.Matern52(sigma=1.8, scale=1.5), lambda: 1.8 ** 2 * kernels.Matern52(1.5)),
+    (lambda: quasisep.Exp(sigma=1.8, scale=1.5), lambda: 1.8 ** 2 * kernels.Exp(1.5)),
+    (lambda: quasisep.Cosine(sigma=1.8, scale=1.5), lambda: 1.8 ** 2 * kernels.Cosine(1.5)),
+    (lambda: quasisep.Matern32(sigma=1.8, scale=1.5) + quasisep.Matern52(sigma=0.9, scale=0.7),
+     lambda: 1.8 ** 2 * kernels.Matern32(1.5) + 0.9 ** 2 * kernels.Matern52(0.7)),
+]
+
+
+@pytest.mark.parametrize("parallel", [False, True], ids=["sequential", "parallel"])
+@pytest.mark.parametrize("pair", range(len(KERNEL_PAIRS)))
+def test_consistent_with_direct(pair, parallel):                     # test_solver.py:62-103
+    rng = np.random.default_rng(84930)
+    x = np.sort(rng.uniform(-3, 3, 50))
+    y = np.sin(x)
+    t = np.sort(rng.uniform(-3, 3, 10))
+    kernel0 = quasisep.Matern32(sigma=3.8, scale=4.5)
+    kernel1, kernel2 = KERNEL_PAIRS[pair][0](), KERNEL_PAIRS[pair][1]()
+    gp1 = GaussianProcess(kernel1, x, diag=0.1, solver=QuasisepSolver, parallel=parallel)
+    gp2 = GaussianProcess(kernel2, x, diag=0.1, solver=DirectSolver)
+    assert_allclose(gp1.covariance, gp2.covariance)
+    assert_allclose(gp1.solver.normalization(), gp2.solver.normalization())
+    assert_allclose(gp1.log_probability(y), gp2.log_probability(y))
+    assert_allclose(gp1.sample(0), gp2.sample(0))
+    assert_allclose(gp1.sample(0, shape=(5, 7)), gp2.sample(0, shape=(5, 7)))
+
+    gp1p, gp2p = gp1.condition(y), gp2.condition(y)
+    assert_allclose(gp1p.log_probability, gp2p.log_probability)
+    assert_allclose(gp1p.gp.loc, gp2p.gp.loc)
+    assert_allclose(gp1p.gp.variance, gp2p.gp.variance)
+    assert_allclose(gp1p.gp.covariance, gp2p.gp.covariance)
+
+    gp1p, gp2p = gp1.condition(y, kernel=kernel0), gp2.condition(y, kernel=kernel0)
+    assert_allclose(gp1p.log_probability, gp2p.log_probability)
+    assert_allclose(gp1p.gp.loc, gp2p.gp.loc)
+    assert_allclose(gp1p.gp.variance, gp2p.gp.variance)
+    assert_allclose(gp1p.gp.covariance, gp2p.gp.covariance)
+
+    gp1p, gp2p = gp1.condition(y, X_test=t, kernel=kernel0), gp2.condition(y, X_test=t, kernel=kernel0)
+    assert not isinstance(gp1p.gp.solver, QuasisepSolver)
+    assert_allclose(gp1p.log_probability, gp2p.log_probability)
+    assert_allclose(gp1p.gp.loc, gp2p.gp.loc)
+    assert_allclose(gp1p.gp.variance, gp2p.gp.variance)
+    assert_allclose(gp1p.gp.covariance, gp2p.gp.covariance)
+
+
+def test_unsorted():                                                 # test_solver.py:127-143
+    rng = np.random.default_rng(0)
+    x_ = rng.uniform(-3, 3, 50)                                      # not sorted
+    kernel = quasisep.Matern32(sigma=1.8, scale=1.5)
+    with pytest.raises(ValueError, match="Input coordinates must be sorted"):
+        GaussianProcess(kernel, x_, diag=0.1)

@@ -1,0 +1,26 @@
+"""The reference's host-level tests as restated in tests/test_host_layer_reference_tests.py, run a second time with the
+REAL backend (CUDA through the C-ABI) instead of the mock: same functions, same data, same 5e-7 tolerances."""
+
+import pytest
+
+import test_host_layer_reference_tests as _cpu
+from test_host_layer_reference_tests import gp_data, kdata, random  # noqa: F401  (fixtures)
+
+pytestmark = pytest.mark.gpu
+
+
+def _clone(fn):
+    def wrapper(*args, **kwargs):
+        return fn(*args, **kwargs)
+    wrapper.__name__ = fn.__name__
+    wrapper.__doc__ = fn.__doc__
+    wrapper.__wrapped__ = fn            # pytest reads the signature (fixtures, parametrize ids) through __wrapped__
+    wrapper.pytestmark = list(getattr(fn, "pytestmark", []))
+    return wrapper
+
+
+# every test of the CPU module except the ones that only assert refusals / pure host behaviour
+_SKIP = {"test_banded_and_dense_are_refused", "test_diagonal"}
+for _name in dir(_cpu):
+    if _name.startswith("test_") and _name not in _SKIP:
+        globals()[_name] = _clone(getattr(_cpu, _name))

@@ -270,3 +270,56 @@ def test_unsorted():                                                 # test_solv
     kernel = quasisep.Matern32(sigma=1.8, scale=1.5)
     with pytest.raises(ValueError, match="Input coordinates must be sorted"):
         GaussianProcess(kernel, x_, diag=0.1)
+
+
+# ---- tests/test_kernels/test_quasisep.py ----------------------------------------------------------------------------
+QS_KERNELS = [
+    lambda: quasisep.Matern32(sigma=1.8, scale=1.5),
+    lambda: quasisep.Matern32(1.5),
+    lambda: quasisep.Matern52(sigma=1.8, scale=1.5),
+    lambda: quasisep.Matern52(1.5),
+    lambda: quasisep.Celerite(1.1, 0.8, 0.9, 0.1),
+    lambda: quasisep.SHO(omega=1.5, quality=0.5, sigma=1.3),
+    lambda: quasisep.SHO(omega=1.5, quality=3.5, sigma=1.3),
+    lambda: quasisep.SHO(omega=1.5, quality=0.1, sigma=1.3),
+    lambda: quasisep.Exp(sigma=1.8, scale=1.5),
+    lambda: quasisep.Exp(1.5),
+    lambda: 1.5 * quasisep.Matern52(1.5) + 0.3 * quasisep.Exp(1.5),
+    lambda: quasisep.Cosine(sigma=1.8, scale=1.5),
+    lambda: 1.8 * quasisep.Cosine(1.5),
+]
+
+
+@pytest.mark.parametrize("which", range(len(QS_KERNELS)))
+def test_quasisep_kernels(which):                                    # test_quasisep.py:53-72 (matrix identities)
+    rng = np.random.default_rng(84930)
+    x = np.sort(rng.uniform(-3, 3, 50))
+    y = np.sin(x)
+    t = np.sort(rng.uniform(-3, 3, 12))
+    kernel = QS_KERNELS[which]()
+    K = kernel(x, x)
+    diag = np.full(50, 0.3)
+    dense = QuasisepSolver(kernel, x, noise.Diagonal(diag)).covariance()      # to_symm_qsm(x).to_dense() + noise
+    assert_allclose(dense - np.diag(diag), K)
+    assert_allclose(kernel.matmul(x, y), K @ y)
+    assert_allclose(kernel.matmul(t, x, y), kernel(t, x) @ y)
+
+
+def test_quasisep_product_and_carma_are_refused():                   # the two kernels of the list the backend lacks
+    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
+        QuasisepSolver(quasisep.Matern52(1.5) * quasisep.SHO(omega=1.5, quality=0.1), np.linspace(0, 1, 5),
+                       noise.Diagonal(np.full(5, 0.1)))
+    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
+        quasisep.CARMA(alpha=np.array([1.4, 2.3, 1.5]), beta=np.array([0.1, 0.5]))
+
+
+def test_celerite():                                                 # test_quasisep.py:83-97
+    a, b, c, d = 1.1, 0.8, 0.9, 0.1
+    kernel = quasisep.Celerite(a, b, c, d)
+    rng = np.random.default_rng(84930)
+    x = np.sort(rng.uniform(-3, 3, 50))
+    t = np.sort(rng.uniform(-3, 3, 12))
+    tau = np.abs(x[:, None] - x[None, :])
+    assert_allclose(kernel(x, x), np.exp(-c * tau) * (a * np.cos(d * tau) + b * np.sin(d * tau)))
+    tau = np.abs(x[:, None] - t[None, :])
+    assert_allclose(kernel(x, t), np.exp(-c * tau) * (a * np.cos(d * tau) + b * np.sin(d * tau)))

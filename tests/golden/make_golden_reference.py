@@ -54,8 +54,16 @@ def main():
         out["unsorted_raises"] = None
     except ValueError as e:
         out["unsorted_raises"] = str(e)
-    with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
-        json.dump(out, f, indent=0, separators=(",", ":"))
+    with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:      # one line per case
+        f.write("{\n")
+        for k in [k for k in out if k != "cases"]:
+            f.write(f" {json.dumps(k)}: {json.dumps(out[k])},\n")
+        f.write(' "cases": {\n')
+        names = list(out["cases"])
+        for i, n in enumerate(names):
+            body = json.dumps(out["cases"][n], separators=(",", ":"))
+            f.write(f"  {json.dumps(n)}: {body}{',' if i + 1 < len(names) else ''}\n")
+        f.write(" }\n}\n")
     print("wrote reference_vectors.json")
 
 

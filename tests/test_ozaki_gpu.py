@@ -21,7 +21,7 @@ def _ref_update(C, planes, rs, S):
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("pairing", [0])      # paired-group kernels: tests/test_zz_quasisep_condition_gpu.py (changed after the last GPU run)
+@pytest.mark.parametrize("pairing", [0])      # paired-group kernels: tests/test_zz_first_run_gpu.py (changed after the last GPU run)
 @pytest.mark.parametrize("cluster", [1, 2, 11, 21, 12, 22, 41, 42])
 @pytest.mark.parametrize("rows,K,S", [(256, 128, 1), (256, 512, 3), (512, 1024, 8), (768, 384, 7), (512, 2048, 2)])
 def test_i8_update_kernel_is_exact(ctx, rows, K, S, cluster, pairing, layout):

@@ -1,8 +1,11 @@
-"""QuasisepSolver conditioning on the device: `b200gp_qs_condition` (build kernel + per-point scans + GEMM with generator
-epilogue) and diag((K + N)^-1) / the O(N) conditioned variance (GramBack backward scan).  Both were written after round
-1's GPU minutes were spent (the scan's source passes on the CPU in tests/test_device_code_on_host.py, the host layer in
-tests/test_host_layer_golden.py); this file sorts last so that a first-run problem here cannot hide the other GPU
-results under `pytest -x`."""
+"""GPU cases that execute device code (or launch logic) written or changed AFTER round 1's last GPU run -- everything else
+in the `-m gpu` suite runs machine code that is byte-identical to what already passed on the B200
+(profiles/r1_head_check.md).  This file sorts last so that a first-run surprise here cannot hide the other results under
+the driver's `pytest -x`:
+  * QuasisepSolver conditioning on the device (`b200gp_qs_condition`), diag((K + N)^-1) and the O(N) conditioned variance
+    (GramBack backward scan; its source passes on the CPU in tests/test_device_code_on_host.py);
+  * the K-range split of the int8 update, the panel-overlap / build-ahead options, the warp-shuffle tree option;
+  * the paired-group int8 kernels (pairing order changed) and, last of all, the new paired CTA-pair kernel."""
 
 import numpy as np
 import pytest

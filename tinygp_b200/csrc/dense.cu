@@ -1142,17 +1142,17 @@ int b200gp_kernel_matrix(b200gp_ctx* ctx, const double* prog, int n_instr, const
     if (ndim < 1 || ndim > MAX_NDIM) throw GpError("kernel_matrix: ndim must be in [1, 16]");
     if (n1 <= 0 || n2 <= 0) throw GpError("kernel_matrix: empty input");
     KProg P = parse_prog(prog, n_instr, ndim);
-    double* x1 = (double*)_ctx->alloc((size_t)n1 * ndim * 8);
-    double* x2 = (double*)_ctx->alloc((size_t)n2 * ndim * 8);
-    double* o = (double*)_ctx->alloc((size_t)n1 * n2 * 8);
+    Scratch x1_buf(_ctx, (size_t)n1 * ndim * 8);
+    double* const x1 = x1_buf.f64();
+    Scratch x2_buf(_ctx, (size_t)n2 * ndim * 8);
+    double* const x2 = x2_buf.f64();
+    Scratch o_buf(_ctx, (size_t)n1 * n2 * 8);
+    double* const o = o_buf.f64();
     CUDA_CHECK(cudaMemcpyAsync(x1, X1, (size_t)n1 * ndim * 8, cudaMemcpyHostToDevice, _ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(x2, X2, (size_t)n2 * ndim * 8, cudaMemcpyHostToDevice, _ctx->stream));
     dense_build_rect(_ctx, P, x1, n1, x2, n2, ndim, nullptr, o, n2, n1, n2);
     CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n1 * n2 * 8, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(x1, (size_t)n1 * ndim * 8);
-    _ctx->release(x2, (size_t)n2 * ndim * 8);
-    _ctx->release(o, (size_t)n1 * n2 * 8);
     API_END
 }
 
@@ -1162,13 +1162,13 @@ int b200gp_kernel_diag(b200gp_ctx* ctx, const double* prog, int n_instr, const d
     (void)X;  // stationary kernels: k(x, x) does not depend on x (nor on a linear input transform)
     if (n <= 0) throw GpError("kernel_diag: empty input");
     KProg P = parse_prog(prog, n_instr, ndim);
-    double* o = (double*)_ctx->alloc((size_t)n * 8);
+    Scratch o_buf(_ctx, (size_t)n * 8);
+    double* const o = o_buf.f64();
     build_diag_kernel<<<nblocks(n, 256), 256, 0, _ctx->stream>>>(P, n, o);
     CUDA_CHECK(cudaGetLastError());
     _ctx->launches++;
     CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n * 8, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(o, (size_t)n * 8);
     API_END
 }
 
@@ -1178,10 +1178,14 @@ int b200gp_kernel_matvec(b200gp_ctx* ctx, const double* prog, int n_instr, const
     if (ndim < 1 || ndim > MAX_NDIM) throw GpError("kernel_matvec: ndim must be in [1, 16]");
     if (n1 <= 0 || n2 <= 0) throw GpError("kernel_matvec: empty input");
     KProg P = parse_prog(prog, n_instr, ndim);
-    double* x1 = (double*)_ctx->alloc((size_t)n1 * ndim * 8);
-    double* x2 = (double*)_ctx->alloc((size_t)n2 * ndim * 8);
-    double* yd = (double*)_ctx->alloc((size_t)n2 * 8);
-    double* o = (double*)_ctx->alloc((size_t)n1 * 8);
+    Scratch x1_buf(_ctx, (size_t)n1 * ndim * 8);
+    double* const x1 = x1_buf.f64();
+    Scratch x2_buf(_ctx, (size_t)n2 * ndim * 8);
+    double* const x2 = x2_buf.f64();
+    Scratch yd_buf(_ctx, (size_t)n2 * 8);
+    double* const yd = yd_buf.f64();
+    Scratch o_buf(_ctx, (size_t)n1 * 8);
+    double* const o = o_buf.f64();
     CUDA_CHECK(cudaMemcpyAsync(x1, X1, (size_t)n1 * ndim * 8, cudaMemcpyHostToDevice, _ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(x2, X2, (size_t)n2 * ndim * 8, cudaMemcpyHostToDevice, _ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(yd, y, (size_t)n2 * 8, cudaMemcpyHostToDevice, _ctx->stream));
@@ -1190,10 +1194,6 @@ int b200gp_kernel_matvec(b200gp_ctx* ctx, const double* prog, int n_instr, const
     _ctx->launches++;
     CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n1 * 8, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(x1, (size_t)n1 * ndim * 8);
-    _ctx->release(x2, (size_t)n2 * ndim * 8);
-    _ctx->release(yd, (size_t)n2 * 8);
-    _ctx->release(o, (size_t)n1 * 8);
     API_END
 }
 
@@ -1249,9 +1249,12 @@ int b200gp_dense_solve_triangular(b200gp_dense* s, double* Y, int64_t nrhs, int 
     API_BEGIN(s->ctx)
     if (nrhs <= 0) throw GpError("solve_triangular: nrhs must be positive");
     const int64_t n = s->n, np = s->np;
-    double* yh = (double*)_ctx->alloc((size_t)n * nrhs * 8);
-    double* yt = (double*)_ctx->alloc((size_t)nrhs * np * 8);
-    double* xt = (double*)_ctx->alloc((size_t)nrhs * np * 8);
+    Scratch yh_buf(_ctx, (size_t)n * nrhs * 8);
+    double* const yh = yh_buf.f64();
+    Scratch yt_buf(_ctx, (size_t)nrhs * np * 8);
+    double* const yt = yt_buf.f64();
+    Scratch xt_buf(_ctx, (size_t)nrhs * np * 8);
+    double* const xt = xt_buf.f64();
     CUDA_CHECK(cudaMemcpyAsync(yh, Y, (size_t)n * nrhs * 8, cudaMemcpyHostToDevice, _ctx->stream));
     transpose_pad_kernel<<<nblocks(nrhs * np, 256), 256, 0, _ctx->stream>>>(yh, n, nrhs, yt, nrhs, np);
     _ctx->launches++;
@@ -1260,9 +1263,6 @@ int b200gp_dense_solve_triangular(b200gp_dense* s, double* Y, int64_t nrhs, int 
     _ctx->launches++;
     CUDA_CHECK(cudaMemcpyAsync(Y, yh, (size_t)n * nrhs * 8, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(yh, (size_t)n * nrhs * 8);
-    _ctx->release(yt, (size_t)nrhs * np * 8);
-    _ctx->release(xt, (size_t)nrhs * np * 8);
     API_END
 }
 
@@ -1270,9 +1270,12 @@ int b200gp_dense_dot_triangular(b200gp_dense* s, double* Y, int64_t nrhs) {
     API_BEGIN(s->ctx)
     if (nrhs <= 0) throw GpError("dot_triangular: nrhs must be positive");
     const int64_t n = s->n, np = s->np;
-    double* yh = (double*)_ctx->alloc((size_t)n * nrhs * 8);
-    double* yt = (double*)_ctx->alloc((size_t)nrhs * np * 8);
-    double* xt = (double*)_ctx->alloc((size_t)nrhs * np * 8);
+    Scratch yh_buf(_ctx, (size_t)n * nrhs * 8);
+    double* const yh = yh_buf.f64();
+    Scratch yt_buf(_ctx, (size_t)nrhs * np * 8);
+    double* const yt = yt_buf.f64();
+    Scratch xt_buf(_ctx, (size_t)nrhs * np * 8);
+    double* const xt = xt_buf.f64();
     CUDA_CHECK(cudaMemcpyAsync(yh, Y, (size_t)n * nrhs * 8, cudaMemcpyHostToDevice, _ctx->stream));
     transpose_pad_kernel<<<nblocks(nrhs * np, 256), 256, 0, _ctx->stream>>>(yh, n, nrhs, yt, nrhs, np);
     _ctx->launches++;
@@ -1285,9 +1288,6 @@ int b200gp_dense_dot_triangular(b200gp_dense* s, double* Y, int64_t nrhs) {
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(Y, yh, (size_t)n * nrhs * 8, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(yh, (size_t)n * nrhs * 8);
-    _ctx->release(yt, (size_t)nrhs * np * 8);
-    _ctx->release(xt, (size_t)nrhs * np * 8);
     API_END
 }
 
@@ -1341,7 +1341,8 @@ int b200gp_dense_covariance(b200gp_dense* s, double* out) {
     API_BEGIN(s->ctx)
     if (!s->has_prog) throw GpError("covariance: solver was built from a precomputed covariance; the host keeps it");
     const int64_t n = s->n;
-    double* o = (double*)_ctx->alloc((size_t)n * n * 8);
+    Scratch o_buf(_ctx, (size_t)n * n * 8);
+    double* const o = o_buf.f64();
     BuildArgs a{};
     a.X1 = s->X_dev; a.X2 = s->X_dev; a.diag = s->diag_dev; a.out = o; a.ld = n;
     a.n1 = n; a.n2 = n; a.rows_pad = n; a.cols_pad = n; a.ndim = s->ndim; a.pad_identity = 0;
@@ -1355,20 +1356,19 @@ int b200gp_dense_covariance(b200gp_dense* s, double* out) {
     }
     CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n * n * 8, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(o, (size_t)n * n * 8);
     API_END
 }
 
 int b200gp_dense_get_factor(b200gp_dense* s, double* out) {
     API_BEGIN(s->ctx)
     const int64_t n = s->n;
-    double* o = (double*)_ctx->alloc((size_t)n * n * 8);
+    Scratch o_buf(_ctx, (size_t)n * n * 8);
+    double* const o = o_buf.f64();
     extract_lower_kernel<<<nblocks(n * n, 256), 256, 0, _ctx->stream>>>(s->mat, s->np, o, n);
     CUDA_CHECK(cudaGetLastError());
     _ctx->launches++;
     CUDA_CHECK(cudaMemcpyAsync(out, o, (size_t)n * n * 8, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
-    _ctx->release(o, (size_t)n * n * 8);
     API_END
 }
 

@@ -546,9 +546,10 @@ static void qs_apply_host(b200gp_qs* s, int op, double* Y, int64_t nrhs, int op2
     b200gp_ctx* ctx = s->ctx;
     const int64_t n = s->n;
     if (nrhs <= 0) throw GpError("quasisep: nrhs must be positive");
-    double* yh = (double*)ctx->alloc((size_t)n * nrhs * 8);
-    double* x = (double*)ctx->alloc((size_t)n * 8);
-    double* o = (double*)ctx->alloc((size_t)n * 8);
+    Scratch yh_buf(ctx, (size_t)n * nrhs * 8), x_buf(ctx, (size_t)n * 8), o_buf(ctx, (size_t)n * 8);
+    double* const yh = yh_buf.f64();
+    double* const x = x_buf.f64();
+    double* const o = o_buf.f64();
     CUDA_CHECK(cudaMemcpyAsync(yh, Y, (size_t)n * nrhs * 8, cudaMemcpyHostToDevice, ctx->stream));
     for (int64_t r = 0; r < nrhs; ++r) {
         if (nrhs == 1) {
@@ -565,9 +566,6 @@ static void qs_apply_host(b200gp_qs* s, int op, double* Y, int64_t nrhs, int op2
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(Y, yh, (size_t)n * nrhs * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    ctx->release(yh, (size_t)n * nrhs * 8);
-    ctx->release(x, (size_t)n * 8);
-    ctx->release(o, (size_t)n * 8);
 }
 
 static double qs_logp_impl(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n,
@@ -746,13 +744,15 @@ int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, con
     s.model.chunk = _ctx->qs_chunk;
     s.J = s.model.J;
     const size_t nb8 = (size_t)n * 8, mb8 = (size_t)m * 8, sb = (size_t)n * s.J * 8;
-    double* t2 = (double*)_ctx->alloc(nb8);
-    double* t1 = (double*)_ctx->alloc(mb8);
-    double* yh = (double*)_ctx->alloc(nb8 * nrhs);
-    double* x = (double*)_ctx->alloc(nb8);
-    double* F = (double*)_ctx->alloc(sb);
-    double* G = (double*)_ctx->alloc(sb);
-    double* o = (double*)_ctx->alloc(mb8 * nrhs);
+    Scratch t2_buf(_ctx, nb8), t1_buf(_ctx, mb8), yh_buf(_ctx, nb8 * nrhs), x_buf(_ctx, nb8), F_buf(_ctx, sb), G_buf(_ctx, sb),
+        o_buf(_ctx, mb8 * nrhs);
+    double* const t2 = t2_buf.f64();
+    double* const t1 = t1_buf.f64();
+    double* const yh = yh_buf.f64();
+    double* const x = x_buf.f64();
+    double* const F = F_buf.f64();
+    double* const G = G_buf.f64();
+    double* const o = o_buf.f64();
     CUDA_CHECK(cudaMemcpyAsync(t2, t_train, nb8, cudaMemcpyDefault, _ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(t1, t_test, mb8, cudaMemcpyDefault, _ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(yh, Y, nb8 * nrhs, cudaMemcpyDefault, _ctx->stream));
@@ -770,8 +770,6 @@ int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, con
     CUDA_CHECK(cudaMemcpyAsync(out, o, mb8 * nrhs, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
     s.t = nullptr;
-    _ctx->release(t2, nb8); _ctx->release(t1, mb8); _ctx->release(yh, nb8 * nrhs); _ctx->release(x, nb8);
-    _ctx->release(F, sb); _ctx->release(G, sb); _ctx->release(o, mb8 * nrhs);
     API_END
 }
 

@@ -83,6 +83,8 @@ int64_t b200gp_launch_count(b200gp_ctx* ctx);
  * "qs_chunk" (points per thread in the quasiseparable scans), "qs_tree" (0: thread-sequential fan-in-16 tree over the
  * chunk composites, 1: warp-shuffle scan kernels, fan-in 32) */
 int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value);
+/* read an option back (tests restore what they change); key "reset" of b200gp_set_option restores every default */
+int b200gp_get_option(b200gp_ctx* ctx, const char* key, int64_t* value);
 
 /* per-kernel device timings accumulated while option "profile"=1 (ms, CUDA events on ctx stream) */
 typedef struct {

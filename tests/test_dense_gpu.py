@@ -80,7 +80,7 @@ def test_factor_parity(n, ctx, potf2):
         assert_close(s.variance(), so.variance(), 1e-14, 1e-14)
         np.testing.assert_allclose(s.covariance(), so.covariance(), rtol=1e-13, atol=1e-15)
     ctx.set_option("nb", 1024)
-    ctx.set_option("ozaki_slices", 8)
+    ctx.reset_options()       # library defaults (NOT a literal: the default plane count is 7)
     ctx.set_option("potf2_version", 2)
 
 
@@ -236,7 +236,7 @@ def test_large_n_properties(ctx, slices):
     # K (K^-1 y) == y with K applied by the matrix-free kernel matvec
     np.testing.assert_allclose(k.matmul(X, X, a) + 0.1 * a, y, rtol=1e-8, atol=1e-9)
     assert rel(y @ a, np.sum(gp.solver.solve_triangular(y) ** 2)) < 1e-10
-    ctx.set_option("ozaki_slices", 8)
+    ctx.reset_options()
 
 
 def test_batched_hyperparameter_grid(ctx):

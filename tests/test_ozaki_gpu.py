@@ -66,7 +66,7 @@ def test_ozaki_factor_parity(ctx, n, nb, slices, lookahead):
         lp = GaussianProcess(k, X, diag=diag).log_probability(y)
     finally:
         ctx.set_option("ozaki_lookahead", 0)
-        ctx.set_option("ozaki_slices", 8)
+        ctx.reset_options()
         ctx.set_option("ozaki_min_n", 8192)
         ctx.set_option("nb", 1024)
     so = o.DirectSolver(to_oracle(k), X, o.Diagonal(diag))
@@ -117,7 +117,7 @@ def test_ozaki_non_pd_and_large_scales(ctx):
         bad = GaussianProcess(kernels.Matern32(2.0), rng.uniform(0, 8, (n, 3)), diag=0.1)   # L1 in 3-D: indefinite
         lpbad = bad.log_probability(y)
     finally:
-        ctx.set_option("ozaki_slices", 8)
+        ctx.reset_options()
         ctx.set_option("ozaki_min_n", 8192)
         ctx.set_option("nb", 1024)
     lpo = o.GaussianProcess(to_oracle(k), X, diag=diag).log_probability(y)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200gp_last_error": (c_char_p, [c_void_p]),
     "b200gp_launch_count": (c_int64, [c_void_p]),
     "b200gp_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
+    "b200gp_get_option": (c_int, [c_void_p, c_char_p, POINTER(c_int64)]),
     "b200gp_get_profile": (c_int, [c_void_p, POINTER(Profile), c_int]),
     "b200gp_measure_fp64_peak": (c_int, [c_void_p, c_double_p, c_double_p]),
     "b200gp_measure_i8_peak": (c_int, [c_void_p, c_double_p]),
@@ -146,6 +147,15 @@ class Context:
 
     def set_option(self, key: str, value: int):
         self.check(self.lib.b200gp_set_option(self.handle, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        v = c_int64()
+        self.check(self.lib.b200gp_get_option(self.handle, key.encode(), byref(v)))
+        return int(v.value)
+
+    def reset_options(self):
+        """every tuning option back to the library default (common.cuh member initialisers)"""
+        self.set_option("reset", 0)
 
     def launch_count(self) -> int:
         return int(self.lib.b200gp_launch_count(self.handle))

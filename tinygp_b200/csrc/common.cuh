@@ -64,6 +64,9 @@ struct b200gp_ctx {
     int64_t qs_chunk = 64;      // points per thread in the quasiseparable scans
     int64_t qs_tree = 0;        // 0: thread-sequential fan-in-16 tree over the chunk composites, 1: warp-shuffle scan (fan-in 32)
     int64_t potf2_version = 2;  // 1: column-at-a-time diagonal-block kernel, 2: rank-8 blocked with register tiles
+    int64_t qs_kernel = 0;      // quasiseparable scan kernels: 0 = one thread per chunk (round 1), 1 = warp-cooperative
+    int64_t panel_fused = 0;    // 1: one launch per 128-column step of the panel factorisation (potf2 + trtri + solve)
+    int64_t oz_persistent = 0;  // int8 update: 1 = persistent tile scheduler (one CTA pair per SM pair, tiles by atomic counter)
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
     // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA.  7 planes = 48 bits under the
     // row scale: at N = 65536 the log-probability differs from the LAPACK golden by 4.7e-12 with 7 AND with 8 planes

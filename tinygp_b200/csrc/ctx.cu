@@ -163,53 +163,77 @@ const char* b200gp_last_error(b200gp_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int64_t b200gp_launch_count(b200gp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
-    API_BEGIN(ctx)
-    if (!strcmp(key, "nb")) {
-        if (value < TILE || value % TILE) throw GpError("option nb must be a positive multiple of 128");
-        _ctx->nb = value;
-    } else if (!strcmp(key, "profile")) {
-        _ctx->flush_timers();
-        _ctx->profile = (value != 0);
+// plain integer options: key -> member (validated in b200gp_set_option); defaults = the member initialisers in common.cuh
+static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kOptions[] = {
+    {"nb", &b200gp_ctx::nb},
+    {"peak_iters", &b200gp_ctx::peak_iters},
+    {"qs_tree", &b200gp_ctx::qs_tree},
+    {"qs_chunk", &b200gp_ctx::qs_chunk},
+    {"qs_kernel", &b200gp_ctx::qs_kernel},
+    {"potf2_version", &b200gp_ctx::potf2_version},
+    {"panel_fused", &b200gp_ctx::panel_fused},
+    {"nb_batched", &b200gp_ctx::nb_batched},
+    {"ozaki_slices", &b200gp_ctx::oz_slices},
+    {"ozaki_prefetch", &b200gp_ctx::oz_prefetch},
+    {"ozaki_layout", &b200gp_ctx::oz_layout},
+    {"ozaki_pairing", &b200gp_ctx::oz_pairing},
+    {"build_ahead", &b200gp_ctx::build_ahead},
+    {"panel_overlap", &b200gp_ctx::panel_overlap},
+    {"ozaki_lookahead", &b200gp_ctx::oz_lookahead},
+    {"ozaki_cluster", &b200gp_ctx::oz_cluster},
+    {"ozaki_min_n", &b200gp_ctx::oz_min_n},
+    {"ozaki_persistent", &b200gp_ctx::oz_persistent},
+};
+
+static void validate_option(const char* key, int64_t value) {
+    if (!strcmp(key, "nb") || !strcmp(key, "nb_batched")) {
+        if (value < TILE || value % TILE) throw GpError(std::string("option ") + key + " must be a positive multiple of 128");
     } else if (!strcmp(key, "peak_iters")) {
         if (value < 16) throw GpError("option peak_iters must be >= 16");
-        _ctx->peak_iters = value;
-    } else if (!strcmp(key, "qs_tree")) {
-        if (value != 0 && value != 1) throw GpError("option qs_tree must be 0 or 1");
-        _ctx->qs_tree = value;
+    } else if (!strcmp(key, "qs_tree") || !strcmp(key, "ozaki_layout")) {
+        if (value != 0 && value != 1) throw GpError(std::string("option ") + key + " must be 0 or 1");
     } else if (!strcmp(key, "qs_chunk")) {
         if (value < 4 || value > 4096) throw GpError("option qs_chunk must be in [4, 4096]");
-        _ctx->qs_chunk = value;
-    } else if (!strcmp(key, "potf2_version")) {
-        _ctx->potf2_version = value;
-    } else if (!strcmp(key, "nb_batched")) {
-        if (value < TILE || value % TILE) throw GpError("option nb_batched must be a positive multiple of 128");
-        _ctx->nb_batched = value;
     } else if (!strcmp(key, "ozaki_slices")) {
         if (value < 0 || value > 8) throw GpError("option ozaki_slices must be in [0, 8]");
-        _ctx->oz_slices = value;
-    } else if (!strcmp(key, "ozaki_prefetch")) {
-        _ctx->oz_prefetch = value;
-    } else if (!strcmp(key, "ozaki_layout")) {
-        if (value != 0 && value != 1) throw GpError("option ozaki_layout must be 0 or 1");
-        _ctx->oz_layout = value;
-    } else if (!strcmp(key, "ozaki_pairing")) {
-        _ctx->oz_pairing = (value == 2) ? 2 : (value ? 1 : 0);
-    } else if (!strcmp(key, "build_ahead")) {
-        _ctx->build_ahead = value ? 1 : 0;
-    } else if (!strcmp(key, "panel_overlap")) {
-        _ctx->panel_overlap = value ? 1 : 0;
-    } else if (!strcmp(key, "ozaki_lookahead")) {
-        _ctx->oz_lookahead = value;
-    } else if (!strcmp(key, "ozaki_cluster")) {
-        _ctx->oz_cluster = value;
-    } else if (!strcmp(key, "ozaki_min_n")) {
-        _ctx->oz_min_n = value;
-    } else if (!strcmp(key, "trim")) {
-        _ctx->trim();
-    } else {
-        throw GpError(std::string("unknown option ") + key);
     }
+}
+
+int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
+    API_BEGIN(ctx)
+    if (!strcmp(key, "profile")) {
+        _ctx->flush_timers();
+        _ctx->profile = (value != 0);
+        return 0;
+    }
+    if (!strcmp(key, "trim")) {
+        _ctx->trim();
+        return 0;
+    }
+    if (!strcmp(key, "reset")) {   // every tuning option back to the library default
+        const b200gp_ctx defaults;
+        for (const OptEntry& o : kOptions) _ctx->*(o.field) = defaults.*(o.field);
+        return 0;
+    }
+    for (const OptEntry& o : kOptions) {
+        if (strcmp(key, o.key)) continue;
+        validate_option(key, value);
+        if (!strcmp(key, "ozaki_pairing")) value = (value == 2) ? 2 : (value ? 1 : 0);
+        else if (!strcmp(key, "build_ahead") || !strcmp(key, "panel_overlap")) value = value ? 1 : 0;
+        _ctx->*(o.field) = value;
+        return 0;
+    }
+    throw GpError(std::string("unknown option ") + key);
+    API_END
+}
+
+int b200gp_get_option(b200gp_ctx* ctx, const char* key, int64_t* value) {
+    API_BEGIN(ctx)
+    if (!value) throw GpError("get_option: null output");
+    if (!strcmp(key, "profile")) { *value = _ctx->profile ? 1 : 0; return 0; }
+    for (const OptEntry& o : kOptions)
+        if (!strcmp(key, o.key)) { *value = _ctx->*(o.field); return 0; }
+    throw GpError(std::string("unknown option ") + key);
     API_END
 }
 

@@ -61,6 +61,16 @@ class Quasisep(Kernel):
             raise ValueError("quasiseparable kernels take 1-D sortable coordinates")
         return super().__call__(X1, X2)
 
+    def evaluate(self, X1, X2):
+        """Scalar evaluation k(t1, t2) (kernels/quasisep.py:118-145): 1-element 1-D coordinates, not the (1, 1) arrays the
+        stationary base class builds."""
+        t1 = np.atleast_1d(np.asarray(X1, dtype=np.float64)).reshape(-1)[:1]
+        t2 = np.atleast_1d(np.asarray(X2, dtype=np.float64)).reshape(-1)[:1]
+        return self(t1, t2)[0, 0]
+
+    def evaluate_diag(self, X):
+        return self.evaluate(X, X)
+
     def matmul(self, X1, X2=None, y=None):
         """quasisep.py:147-163: ``to_general_qsm(X1, X2) @ y`` in O((n + m) J^2) on the device (two state scans
         over the sorted X2, a searchsorted and two transition matrices per row of X1).  With X2 omitted the

@@ -63,8 +63,9 @@ def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streamin
     if X_dev is None:
         prog, x = kernel.lower_for(X)
         n, ndim = x.shape
-        xp, dp, rp = _cabi.ptr(x), _cabi.ptr(_cabi.f64(diag)), _cabi.ptr(_cabi.f64(resid))
-        keep = (x,)
+        d, r = _cabi.f64(diag), _cabi.f64(resid)      # converted copies must outlive b200gp_mg_create
+        xp, dp, rp = _cabi.ptr(x), _cabi.ptr(d), _cabi.ptr(r)
+        keep = (x, d, r)
     else:
         prog = kernel.program()   # device-resident coordinates: no host-side transforms
         n, ndim = X_dev.shape

@@ -32,6 +32,7 @@ class DirectSolver(Solver):
             if diag.shape != (x.shape[0],):
                 raise ValueError("noise diagonal must have shape (N,)")
             self._n = x.shape[0]
+            self._x = x                      # the lowered (possibly transform-augmented) coordinates held on the device
             self.variance_value = kernel(X) + diag                              # direct.py:49
             self._cov = None
             self._ctx.check(lib.b200gp_dense_create(self._ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(x),
@@ -42,6 +43,7 @@ class DirectSolver(Solver):
             if cov.ndim != 2 or cov.shape[0] != cov.shape[1]:
                 raise ValueError("covariance must be a square matrix")
             self._n = cov.shape[0]
+            self._x = None
             self._cov = cov
             # direct.py:49: variance = kernel(X) + noise.diagonal() with kernel = kernels.Conditioned, whose diagonal is
             # diag(Kss - A^T A).  DirectSolver.condition put the noise into Kss (direct.py:88-92) so that is diag(cov);
@@ -106,12 +108,26 @@ class DirectSolver(Solver):
 
     def condition(self, kernel: Kernel, X_test, noise) -> Any:  # direct.py:75-95
         diag = _cabi.f64(noise.diagonal())
+        if self._x is None:
+            raise NotImplementedError("condition() of a solver built from a precomputed covariance is unsupported by the "
+                                      "B200 solver backend (there are no training coordinates on the device)")
+        # b200gp_dense_condition evaluates the predictive kernel on the TRAINING coordinates kept on the device, i.e. in
+        # the training kernel's lowered layout (raw columns + the host-computed columns of any transforms.Transform).
+        # A predictive kernel that lowers the training inputs differently (other width, other transform outputs) would
+        # read those columns wrongly -- or past the test-point buffer -- so it is refused instead of silently mis-evaluated.
+        prog, x_train = kernel.lower_for(self.X)
+        if x_train.shape != self._x.shape or not np.array_equal(x_train, self._x):
+            raise NotImplementedError(
+                f"the predictive kernel lowers the training coordinates to shape {x_train.shape} but the solver holds "
+                f"{self._x.shape} (general transforms.Transform columns differ between the training and the predictive "
+                "kernel): unsupported by the B200 solver backend")
         if X_test is None:
-            prog, _ = kernel.lower_for(self.X)
             m = self._n
             xt_ptr = None
         else:
             prog, xt = kernel.lower_for(X_test)
+            if xt.shape[1] != self._x.shape[1]:
+                raise ValueError("X_test must have the same number of input dimensions as the training inputs")
             m = xt.shape[0]
             xt_ptr = _cabi.ptr(xt)
         if diag.shape != (m,):

@@ -73,6 +73,8 @@ class QuasisepSolver(Solver):
     def normalization(self):  # solver.py:90-93
         ld = c_double()
         self._ctx.check(self._ctx.lib.b200gp_qs_logdet_half(self._h, byref(ld)))
+        if getattr(self, "info", 0) != 0:     # failed factorisation: NaN like the reference's log of a NaN pivot
+            return np.nan
         return ld.value + 0.5 * self._n * np.log(2 * np.pi)
 
     def _apply(self, fn, y, *extra):

@@ -82,6 +82,7 @@ struct b200gp_ctx {
     int64_t oz_pairing = 0;    // int8 update: 1 = accumulate two digit groups at once (1.8x fewer operand loads), 2 = diagnostic
     int64_t oz_layout = 0;     // digit planes: 0 plane-major, 1 chunk-major (all planes of a K chunk adjacent)
     int64_t oz_cluster = 21;    // cluster shape of the int8 update kernel (CM*10 + CN), see ozaki.cu
+    int64_t oz_l2promo = 3;     // TMA L2 promotion of the digit-plane maps: 0 none, 1 64 B, 2 128 B, 3 256 B
     int64_t oz_min_n = 8192;    // below this size the native DMMA path is used
     // deferred (non-blocking) kernel timers: event pairs resolved at the next flush_timers()
     struct Pending { cudaEvent_t a, b; double* acc; };

@@ -182,6 +182,7 @@ static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kO
     {"ozaki_lookahead", &b200gp_ctx::oz_lookahead},
     {"ozaki_cluster", &b200gp_ctx::oz_cluster},
     {"ozaki_min_n", &b200gp_ctx::oz_min_n},
+    {"ozaki_l2promo", &b200gp_ctx::oz_l2promo},
     {"ozaki_persistent", &b200gp_ctx::oz_persistent},
 };
 

@@ -57,7 +57,12 @@ struct Args {
     int layout;                        // digit-plane layout: 0 plane-major [s][row][k], 1 chunk-major [k/128][row][s][128]
     int pg_single;                     // diagnostic: paired-group loop structure (kc outer) with ONE group per pass
     int* error_flag;
+    unsigned long long* dbg;           // optional in-kernel cycle counters (see DBG_* below); nullptr = off
 };
+
+// in-kernel cycle counters (diagnostics, option-free: on when Args.dbg != nullptr).  Sums over CTAs of clock64() deltas.
+enum { DBG_PROD_WAIT = 0, DBG_PROD_TOTAL = 1, DBG_MMA_WAIT_FULL = 2, DBG_MMA_WAIT_TEMPTY = 3, DBG_MMA_TOTAL = 4,
+       DBG_EPI_WAIT_TFULL = 5, DBG_EPI_TOTAL = 6, DBG_CTAS = 7, DBG_CTA_TOTAL = 8, DBG_N = 16 };
 
 // `all`: ONE 3-D map (k, row, plane) used by the main kernel -- cycling through per-plane descriptors makes every
 // TMA issue miss the descriptor cache (measured: 3x the per-stage cost once stages alternate planes);
@@ -94,6 +99,18 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
     }
     *abort_flag = 1;
     return false;
+}
+// mbar_wait with an optional cycle counter around it
+__device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, volatile int* abort_flag, bool prof,
+                                            unsigned long long& acc) {
+    if (!prof) return mbar_wait(bar, parity, abort_flag);
+    const long long t0 = clock64();
+    const bool r = mbar_wait(bar, parity, abort_flag);
+    acc += (unsigned long long)(clock64() - t0);
+    return r;
+}
+__device__ __forceinline__ void dbg_add(unsigned long long* dbg, int slot, unsigned long long v) {
+    if (dbg) atomicAdd(dbg + slot, v);
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
@@ -285,9 +302,13 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
     const int KT = g.K / KC;
     const int64_t brow0 = g.b_row0 + (int64_t)tj * TN;  // global row of the B operand's first row
 
+    const bool prof = (g.dbg != nullptr);
+    const long long t_cta0 = prof ? clock64() : 0;
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            unsigned long long w_prod = 0;
+            const long long t_role0 = prof ? clock64() : 0;
             // one ring stage: (A plane s, B plane t) of K chunk kc
             // one 128-byte x 64-row box of digit plane `pl` at K chunk kc into this CTA's (and its mates') current stage
             const int kchunk0 = g.k_begin / KC;
@@ -304,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                 }
             };
             auto issue_stage = [&](int s, int t, int kc) {
-                        if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; return; }
+                        if (!mbar_wait_t(empty + stage, phase ^ 1, abort_flag, prof, w_prod)) { ok = false; return; }
                         uint8_t* a_dst = smem + stage * STAGE_BYTES;
                         uint8_t* b_dst = a_dst + A_BYTES;
                         mbar_expect_tx(full + stage, STAGE_BYTES);   // own + mates' slices land on this barrier
@@ -346,10 +367,13 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                         for (int kc = 0; kc < KT && ok; ++kc) issue_stage(s, gi - s, kc);
                 }
             }
+            if (prof) { dbg_add(g.dbg, DBG_PROD_WAIT, w_prod); dbg_add(g.dbg, DBG_PROD_TOTAL, (unsigned long long)(clock64() - t_role0)); }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
+            unsigned long long w_full = 0, w_tempty = 0;
+            const long long t_role0 = prof ? clock64() : 0;
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
@@ -360,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                     pg_pass(S, g.pg_single, P, g0, two);
                     const int top = two ? g0 + 1 : g0;
                     if (P >= 1) {  // the epilogue must have drained both accumulators (pair P-1)
-                        if (!mbar_wait(tempty, (uint32_t)((P - 1) & 1), abort_flag)) { ok = false; break; }
+                        if (!mbar_wait_t(tempty, (uint32_t)((P - 1) & 1), abort_flag, prof, w_tempty)) { ok = false; break; }
                         tc_fence_after();
                     }
                     const uint32_t acc0 = tmem_base, acc1 = tmem_base + (uint32_t)TN;
@@ -369,7 +393,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                         uint32_t prev_a = 0;
                         int prev_stage = 0;
                         for (int i = 0; i <= top; ++i) {
-                            if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                            if (!mbar_wait_t(full + stage, phase, abort_flag, prof, w_full)) { ok = false; break; }
                             tc_fence_after();
                             const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
                             const uint32_t b_addr = a_addr + A_BYTES;
@@ -408,7 +432,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                 for (int gi = 0; gi < NG && ok; ++gi) {
                     const int acc = gi & 1;
                     if (gi >= 2) {  // the epilogue must have drained this accumulator (group gi-2)
-                        if (!mbar_wait(tempty + acc, ((gi >> 1) - 1) & 1, abort_flag)) { ok = false; break; }
+                        if (!mbar_wait_t(tempty + acc, ((gi >> 1) - 1) & 1, abort_flag, prof, w_tempty)) { ok = false; break; }
                         tc_fence_after();
                     }
                     const uint32_t tacc = tmem_base + (uint32_t)acc * TN;
@@ -416,7 +440,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                     const int s_lo = (gi - (S - 1) > 0) ? gi - (S - 1) : 0, s_hi = (gi < S - 1) ? gi : S - 1;
                     for (int s = s_lo; s <= s_hi && ok; ++s) {
                         for (int kc = 0; kc < KT; ++kc) {
-                            if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                            if (!mbar_wait_t(full + stage, phase, abort_flag, prof, w_full)) { ok = false; break; }
                             tc_fence_after();
                             const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
                             const uint32_t b_addr = a_addr + A_BYTES;
@@ -433,9 +457,15 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                     if (ok) tc_commit(tfull + acc);    // accumulator of group gi complete
                 }
             }
+            if (prof) {
+                dbg_add(g.dbg, DBG_MMA_WAIT_FULL, w_full); dbg_add(g.dbg, DBG_MMA_WAIT_TEMPTY, w_tempty);
+                dbg_add(g.dbg, DBG_MMA_TOTAL, (unsigned long long)(clock64() - t_role0));
+            }
         }
     } else {
         // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        unsigned long long w_tfull = 0;
+        const long long t_role0 = prof ? clock64() : 0;
         const int q = warp & 3;
         const int row = q * 32 + lane;            // tile row owned by this thread
         const int64_t gr = grow0 + row;
@@ -448,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
             for (int P = 0; P < npass && ok; ++P) {
                 int g0; bool two;
                 pg_pass(S, g.pg_single, P, g0, two);
-                if (!mbar_wait(tfull, (uint32_t)(P & 1), abort_flag)) { ok = false; break; }
+                if (!mbar_wait_t(tfull, (uint32_t)(P & 1), abort_flag, prof, w_tfull)) { ok = false; break; }
                 tc_fence_after();
                 // group g0 weighs 2^-(12 + 7 g0); group g0 + 1 is 2^-7 of that.  a0 + a1 2^-7 is exact in fp64
                 // (|a| < 2^31), so the pair costs ONE rounding and one read-modify-write of the fp64 tile.
@@ -483,7 +513,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
         } else {
             for (int gi = 0; gi < NG && ok; ++gi) {
                 const int acc = gi & 1;
-                if (!mbar_wait(tfull + acc, (gi >> 1) & 1, abort_flag)) { ok = false; break; }
+                if (!mbar_wait_t(tfull + acc, (gi >> 1) & 1, abort_flag, prof, w_tfull)) { ok = false; break; }
                 tc_fence_after();
                 // weight 2^-(12 + 7 gi), exact power of two
                 const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
@@ -509,11 +539,16 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                 if (lane == 0) mbar_arrive(tempty + acc);
             }
         }
+        if (prof && warp == 2 && lane == 0) {
+            dbg_add(g.dbg, DBG_EPI_WAIT_TFULL, w_tfull);
+            dbg_add(g.dbg, DBG_EPI_TOTAL, (unsigned long long)(clock64() - t_role0));
+        }
     }
 
     tc_fence_before();
     __syncthreads();
     if (CS > 1) cluster_sync_all();   // no CTA may exit while mates still multicast into it / arrive on its barriers
+    if (prof && threadIdx.x == 0) { dbg_add(g.dbg, DBG_CTAS, 1ull); dbg_add(g.dbg, DBG_CTA_TOTAL, (unsigned long long)(clock64() - t_cta0)); }
     if (threadIdx.x == 0 && *abort_flag) atomicExch(g.error_flag, 1);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
@@ -617,9 +652,13 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
     const int KT = g.K / KC;
     const int64_t brow0 = g.b_row0 + (int64_t)tj * TN + (int64_t)crank * 128;  // this CTA's half of the B rows
 
+    const bool prof = (g.dbg != nullptr);
+    const long long t_cta0 = prof ? clock64() : 0;
     if (warp == 0) {
         // ===== TMA producer (both CTAs; completion is signalled on the LEADER's full barrier) =====
         if (lane == 0) {
+            unsigned long long w_prod = 0;
+            const long long t_role0 = prof ? clock64() : 0;
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
@@ -631,7 +670,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                     const int top = two ? g0 + 1 : g0;
                     for (int kc = 0; kc < KT && ok; ++kc)
                         for (int i = 0; i <= top; ++i) {     // stage i: (A plane i, B-half plane top - i), one 3-D map
-                            if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; break; }
+                            if (!mbar_wait_t(empty + stage, phase ^ 1, abort_flag, prof, w_prod)) { ok = false; break; }
                             uint8_t* a_dst = smem + stage * STAGE2_BYTES;
                             uint8_t* b_dst = a_dst + A_BYTES;
                             if (leader) mbar_expect_tx(full + stage, 2 * STAGE2_BYTES);
@@ -650,7 +689,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                 for (int s = 0; s <= gi && ok; ++s) {
                     const int t = gi - s;
                     for (int kc = 0; kc < KT; ++kc) {
-                        if (!mbar_wait(empty + stage, phase ^ 1, abort_flag)) { ok = false; break; }
+                        if (!mbar_wait_t(empty + stage, phase ^ 1, abort_flag, prof, w_prod)) { ok = false; break; }
                         uint8_t* a_dst = smem + stage * STAGE2_BYTES;
                         uint8_t* b_dst = a_dst + A_BYTES;
                         if (leader) mbar_expect_tx(full + stage, 2 * STAGE2_BYTES);   // both CTAs' bytes
@@ -658,18 +697,21 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                         const int kx = g.k_begin + kc * KC;
 #pragma unroll
                         for (int bx = 0; bx < TM / BOXR; ++bx) {
-                            tma_load_2d_2sm(a_dst + bx * BOXR * KC, &maps.plane[s], lbar, kx, (int)grow0 + bx * BOXR);
-                            tma_load_2d_2sm(b_dst + bx * BOXR * KC, &maps.plane[t], lbar, kx, (int)brow0 + bx * BOXR);
+                            tma_load_3d_2sm(a_dst + bx * BOXR * KC, &maps.all, lbar, kx, (int)grow0 + bx * BOXR, s);
+                            tma_load_3d_2sm(b_dst + bx * BOXR * KC, &maps.all, lbar, kx, (int)brow0 + bx * BOXR, t);
                         }
                         if (++stage == STAGES2) { stage = 0; phase ^= 1; }
                     }
                 }
             }
             }
+            if (prof && leader) { dbg_add(g.dbg, DBG_PROD_WAIT, w_prod); dbg_add(g.dbg, DBG_PROD_TOTAL, (unsigned long long)(clock64() - t_role0)); }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA drives both SMs =====
         if (leader && lane == 0) {
+            unsigned long long w_full = 0, w_tempty = 0;
+            const long long t_role0 = prof ? clock64() : 0;
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
@@ -680,7 +722,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                     pg_pass(S, g.pg_single, P, g0, two);
                     const int top = two ? g0 + 1 : g0;
                     if (P >= 1) {   // both accumulators drained by the epilogue of pass P-1 (8 arrivals: 4 warps x 2 CTAs)
-                        if (!mbar_wait(tempty, (uint32_t)((P - 1) & 1), abort_flag)) { ok = false; break; }
+                        if (!mbar_wait_t(tempty, (uint32_t)((P - 1) & 1), abort_flag, prof, w_tempty)) { ok = false; break; }
                         tc_fence_after();
                     }
                     const uint32_t acc0 = tmem_base, acc1 = tmem_base + (uint32_t)TN;
@@ -689,7 +731,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                         uint32_t prev_a = 0;
                         int prev_stage = 0;
                         for (int i = 0; i <= top; ++i) {
-                            if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                            if (!mbar_wait_t(full + stage, phase, abort_flag, prof, w_full)) { ok = false; break; }
                             tc_fence_after();
                             const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
                             const uint32_t b_addr = a_addr + A_BYTES;
@@ -727,14 +769,14 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
             for (int gi = 0; gi < S && ok; ++gi) {
                 const int acc = gi & 1;
                 if (gi >= 2) {
-                    if (!mbar_wait(tempty + acc, ((gi >> 1) - 1) & 1, abort_flag)) { ok = false; break; }
+                    if (!mbar_wait_t(tempty + acc, ((gi >> 1) - 1) & 1, abort_flag, prof, w_tempty)) { ok = false; break; }
                     tc_fence_after();
                 }
                 const uint32_t tacc = tmem_base + (uint32_t)acc * TN;
                 uint32_t accumulate = 0;
                 for (int s = 0; s <= gi && ok; ++s) {
                     for (int kc = 0; kc < KT; ++kc) {
-                        if (!mbar_wait(full + stage, phase, abort_flag)) { ok = false; break; }
+                        if (!mbar_wait_t(full + stage, phase, abort_flag, prof, w_full)) { ok = false; break; }
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smem + stage * STAGE2_BYTES);
                         const uint32_t b_addr = a_addr + A_BYTES;
@@ -749,9 +791,15 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                 }
                 if (ok) tc_commit_2sm(tfull + acc, 0x3);     // accumulators (both CTAs) of group gi complete
             }
+            if (prof) {
+                dbg_add(g.dbg, DBG_MMA_WAIT_FULL, w_full); dbg_add(g.dbg, DBG_MMA_WAIT_TEMPTY, w_tempty);
+                dbg_add(g.dbg, DBG_MMA_TOTAL, (unsigned long long)(clock64() - t_role0));
+            }
         }
     } else {
         // ===== epilogue (both CTAs): this CTA's 128 rows x 256 columns =====
+        unsigned long long w_tfull = 0;
+        const long long t_role0 = prof ? clock64() : 0;
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int64_t gr = grow0 + row;
@@ -766,7 +814,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
             for (int P = 0; P < npass && ok; ++P) {
                 int g0; bool two;
                 pg_pass(S, g.pg_single, P, g0, two);
-                if (!mbar_wait(tfull, (uint32_t)(P & 1), abort_flag)) { ok = false; break; }
+                if (!mbar_wait_t(tfull, (uint32_t)(P & 1), abort_flag, prof, w_tfull)) { ok = false; break; }
                 tc_fence_after();
                 const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * g0)) << 52);
                 const double sc = -(rsi * wg);
@@ -799,7 +847,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
         } else
         for (int gi = 0; gi < S && ok; ++gi) {
             const int acc = gi & 1;
-            if (!mbar_wait(tfull + acc, (gi >> 1) & 1, abort_flag)) { ok = false; break; }
+            if (!mbar_wait_t(tfull + acc, (gi >> 1) & 1, abort_flag, prof, w_tfull)) { ok = false; break; }
             tc_fence_after();
             const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
             const double sc = -(rsi * wg);
@@ -823,11 +871,16 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
         }
+        if (prof && leader && warp == 2 && lane == 0) {
+            dbg_add(g.dbg, DBG_EPI_WAIT_TFULL, w_tfull);
+            dbg_add(g.dbg, DBG_EPI_TOTAL, (unsigned long long)(clock64() - t_role0));
+        }
     }
 
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
+    if (prof && leader && threadIdx.x == 0) { dbg_add(g.dbg, DBG_CTAS, 1ull); dbg_add(g.dbg, DBG_CTA_TOTAL, (unsigned long long)(clock64() - t_cta0)); }
     if (threadIdx.x == 0 && *abort_flag) atomicExch(g.error_flag, 1);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;\n" ::"r"(tmem_base) : "memory");
@@ -1098,16 +1151,20 @@ static EncodeTiledFn get_encode() {
 }
 
 // planes: S contiguous int8 matrices [rows][ldq]; box = 128 bytes (k) x 128 rows, 128-byte swizzle
-Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, int S, int layout = 0) {
+Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, int S, int layout = 0, int l2promo = 3) {
     Maps m{};
     EncodeTiledFn enc = get_encode();
+    const CUtensorMapL2promotion promo = (l2promo == 0) ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : (l2promo == 1) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : (l2promo == 2) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     if (layout == 1) {   // chunk-major: [k / 128][row][plane][128]
         cuuint64_t dims[4] = {(cuuint64_t)KC, (cuuint64_t)S, (cuuint64_t)rows, (cuuint64_t)(ldq / KC)};
         cuuint64_t strides[3] = {(cuuint64_t)KC, (cuuint64_t)S * KC, (cuuint64_t)rows * S * KC};
         cuuint32_t box[4] = {(cuuint32_t)KC, 1u, (cuuint32_t)BOXR, 1u};
         cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
         CUresult r = enc(&m.all, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, planes, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) throw GpError("cuTensorMapEncodeTiled (4-D) failed");
         return m;   // the per-plane 2-D maps do not exist in this layout
@@ -1118,7 +1175,7 @@ Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, 
         cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BOXR, 1u};
         cuuint32_t estr[3] = {1u, 1u, 1u};
         CUresult r = enc(&m.all, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) throw GpError("cuTensorMapEncodeTiled (3-D) failed");
     }
@@ -1130,7 +1187,7 @@ Maps make_maps(int8_t* planes, int64_t plane_stride, int64_t rows, int64_t ldq, 
         cuuint32_t estr[2] = {1u, 1u};
         CUresult r = enc(&m.plane[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, planes + (int64_t)sp * plane_stride, dims, strides,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) throw GpError("cuTensorMapEncodeTiled failed");
     }
     return m;
@@ -1394,7 +1451,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
                                                                                s->n, np, rs);
     ctx->launches++;
     const int layout = (int)ctx->oz_layout;
-    oz::Maps maps = oz::make_maps(planes, (int64_t)plane_stride, np, np, S, layout);
+    oz::Maps maps = oz::make_maps(planes, (int64_t)plane_stride, np, np, S, layout, (int)ctx->oz_l2promo);
 
     // Two streams: `upd` (the context stream) runs build + int8 updates, `pan` (high priority) runs the fp64
     // panel factorisation and the digit cutting.  Update J is split into the part that only needs panels
@@ -1559,6 +1616,81 @@ extern "C" int b200gp_i8_update_test(b200gp_ctx* ctx, const int8_t* planes_host,
     _ctx->release(C, (size_t)rows * rows * 8);
     _ctx->release(err, sizeof(int));
     if (herr) throw GpError("i8 test: pipeline wait timed out");
+    API_END
+}
+
+// ---- micro-benchmark of ONE update launch shape (diagnostics): rows x cols fp64 tile block, K int8 columns ----------
+// planes are filled on the device with a hash pattern (|q| <= 64); `variant` = the ozaki_cluster code, the other switches
+// come from the context options.  Returns the mean launch time and, if dbg_out != nullptr, the in-kernel cycle counters
+// of the LAST launch (DBG_* slots).
+__global__ void fill_planes_kernel(int8_t* p, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n / 16; i += stride) {
+        uint32_t w[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            uint32_t h = (uint32_t)(i * 4 + v) * 2654435761u;
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            uint32_t o = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int q = (int)((h >> (8 * e)) & 0x7f) - 63;   // [-63, 64]
+                o |= ((uint32_t)(uint8_t)(int8_t)q) << (8 * e);
+            }
+            w[v] = o;
+        }
+        reinterpret_cast<uint4*>(p)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+extern "C" int b200gp_i8_update_bench(b200gp_ctx* ctx, int64_t rows, int64_t cols, int64_t K, int S, int reps,
+                                      double* ms_out, unsigned long long* dbg_out /* 16 or null */) {
+    API_BEGIN(ctx)
+    if (rows % 256 || cols % 256 || K % 128 || S < 1 || S > 8 || cols > rows || reps < 1)
+        throw GpError("i8 bench: rows % 256 == 0, cols % 256 == 0, cols <= rows, K % 128 == 0, 1 <= S <= 8");
+    const size_t pstride = (size_t)rows * K;
+    Scratch planes_b(_ctx, pstride * S), rs_b(_ctx, (size_t)rows * 8), C_b(_ctx, (size_t)rows * cols * 8);
+    Scratch err_b(_ctx, sizeof(int)), dbg_b(_ctx, oz::DBG_N * 8);
+    int8_t* planes = (int8_t*)planes_b.p;
+    double* rs = rs_b.f64();
+    int* err = (int*)err_b.p;
+    unsigned long long* dbg = (unsigned long long*)dbg_b.p;
+    CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), _ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(C_b.p, 0, (size_t)rows * cols * 8, _ctx->stream));
+    fill_planes_kernel<<<_ctx->num_sms * 8, 256, 0, _ctx->stream>>>(planes, pstride * S);
+    {
+        std::vector<double> ones((size_t)rows, 1.0);
+        CUDA_CHECK(cudaMemcpyAsync(rs, ones.data(), (size_t)rows * 8, cudaMemcpyHostToDevice, _ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    }
+    const int layout = (int)_ctx->oz_layout;   // layout 1 reads the same bytes through the 4-D map (timing only)
+    oz::Maps maps = oz::make_maps(planes, (int64_t)pstride, rows, K, S, layout, (int)_ctx->oz_l2promo);
+    oz::Args a{};
+    a.layout = layout;
+    a.C = C_b.f64(); a.ldc = cols; a.rs = rs; a.row0 = 0; a.col0 = 0; a.b_row0 = 0;
+    a.tiles_m = (int)(rows / oz::TM); a.tiles_n = (int)(cols / oz::TN);
+    a.K = (int)K; a.k_begin = 0; a.S = S; a.n_rows = rows; a.skip_upper = 0; a.error_flag = err;
+    a.prefetch = (int)_ctx->oz_prefetch; a.pg_single = (_ctx->oz_pairing == 2);
+    a.dbg = nullptr;
+    oz::launch_update(_ctx, maps, a);   // warm-up
+    cudaEventRecord(_ctx->ev0, _ctx->stream);
+    for (int r = 0; r < reps; ++r) oz::launch_update(_ctx, maps, a);
+    cudaEventRecord(_ctx->ev1, _ctx->stream);
+    CUDA_CHECK(cudaEventSynchronize(_ctx->ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, _ctx->ev0, _ctx->ev1);
+    *ms_out = (double)ms / reps;
+    if (dbg_out) {
+        CUDA_CHECK(cudaMemsetAsync(dbg, 0, oz::DBG_N * 8, _ctx->stream));
+        a.dbg = dbg;
+        oz::launch_update(_ctx, maps, a);
+        CUDA_CHECK(cudaMemcpyAsync(dbg_out, dbg, oz::DBG_N * 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    }
+    int herr = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    if (herr) throw GpError("i8 bench: pipeline wait timed out");
     API_END
 }
 

@@ -118,9 +118,10 @@ int b200gp_i8_update_test(b200gp_ctx* ctx, const int8_t* planes, int S, int64_t 
                           const double* rs, double* C);
 /* timing diagnostic of ONE update-launch shape: (rows x cols) fp64 block, K int8 columns, S planes filled on the device;
  * mean milliseconds over `reps` launches and (optional, 16 slots) the in-kernel cycle counters of one more launch.
+ * ldq / ldc: row strides of the digit planes / of C (0 = compact), to reproduce the strides of a large factorisation.
  * The kernel variant follows the context options (ozaki_cluster / ozaki_pairing / ozaki_layout / ...). */
 int b200gp_i8_update_bench(b200gp_ctx* ctx, int64_t rows, int64_t cols, int64_t K, int S, int reps,
-                           double* ms_out, unsigned long long* dbg_out);
+                           int64_t ldq, int64_t ldc, double* ms_out, unsigned long long* dbg_out);
 /* option keys for b200gp_set_option: "nb", "profile", "peak_iters", "trim",
  * "ozaki_slices" (0 = native fp64 DMMA trailing update; 2..8 = int8 digit planes), "ozaki_min_n". */
 

@@ -221,6 +221,49 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 constexpr int BOXR = 64;  // rows per TMA box
 
+// ---- epilogue of one digit group (or a pair of groups) for this thread's tile row ----------------------------------
+// C[row, col0 + 0..255] += sc * rs_j * (acc0 + 2^-7 acc1).  The read-modify-write is issued in BATCHES: all loads of a
+// batch first, then the arithmetic, then the stores.  Round 1 had "load, fma, store" per 16 bytes with the row scales read
+// through a plain pointer, so every store could alias the next load and the accesses were serialised at the loaded
+// L2 latency (in-kernel counters, round 2: ~1.4 M cycles per 128 x 256 tile pass, i.e. ~9000 cycles per 16-byte RMW).
+template <bool TWO>
+__device__ __forceinline__ void epi_rmw_row(uint32_t taddr0, uint32_t taddr1, double* __restrict__ crow,
+                                            const double* __restrict__ rs, int64_t gcol0, int64_t n_cols, bool row_ok,
+                                            double sc) {
+#pragma unroll 1
+    for (int cb = 0; cb < TN / 32; ++cb) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr0 + (uint32_t)(cb * 32), r0);
+        if (TWO) tmem_ld32(taddr1 + (uint32_t)(cb * 32), r1);
+        const int64_t gc = gcol0 + cb * 32;
+        if (row_ok && gc < n_cols) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {       // two batches of 16 columns: 8 + 8 independent 16-byte loads in flight
+                double2 cv[8], rj[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    cv[j] = *reinterpret_cast<const double2*>(crow + gc + h * 16 + 2 * j);
+                    rj[j] = __ldg(reinterpret_cast<const double2*>(rs + gc + h * 16 + 2 * j));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = h * 16 + 2 * j;
+                    double tx = (double)(int)r0[e], ty = (double)(int)r0[e + 1];
+                    if (TWO) {   // group g0 + 1 is 2^-7 of group g0: a0 + a1 2^-7 is exact (|a| < 2^31), one rounding per pair
+                        tx = fma((double)(int)r1[e], 0.0078125, tx);
+                        ty = fma((double)(int)r1[e + 1], 0.0078125, ty);
+                    }
+                    cv[j].x = fma(sc * rj[j].x, tx, cv[j].x);
+                    cv[j].y = fma(sc * rj[j].y, ty, cv[j].y);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<double2*>(crow + gc + h * 16 + 2 * j) = cv[j];
+            }
+        }
+    }
+}
+
+
 // PG ("paired groups"): two digit groups g0 = 2P, g1 = 2P + 1 are accumulated at once in the two TMEM accumulators.
 // Per K chunk the ring then carries stages i = 0..g1 holding (A plane i, B plane g1 - i); stage i feeds
 //   A_i x B_{g1-i} -> accumulator 1 (group g1)   and   A_{i-1} (previous stage) x B_{g1-i} -> accumulator 0 (group g0),
@@ -484,27 +527,10 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                 // (|a| < 2^31), so the pair costs ONE rounding and one read-modify-write of the fp64 tile.
                 const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * g0)) << 52);
                 const double sc = -(rsi * wg);
-#pragma unroll 1
-                for (int cb = 0; cb < TN / 32; ++cb) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), r0);
-                    if (two) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TN + cb * 32), r1);
-                    const int64_t gc = gcol0 + cb * 32;
-                    if (row_ok && gc < g.n_rows) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
-                            double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
-                            double tx = (double)(int)r0[j], ty = (double)(int)r0[j + 1];
-                            if (two) {
-                                tx = fma((double)(int)r1[j], 0.0078125, tx);
-                                ty = fma((double)(int)r1[j + 1], 0.0078125, ty);
-                            }
-                            cv.x = fma(sc * rj.x, tx, cv.x);
-                            cv.y = fma(sc * rj.y, ty, cv.y);
-                            *reinterpret_cast<double2*>(crow + gc + j) = cv;
-                        }
-                    }
+                {
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+                    if (two) epi_rmw_row<true>(trow, trow + (uint32_t)TN, crow, g.rs, gcol0, g.n_rows, row_ok, sc);
+                    else epi_rmw_row<false>(trow, trow, crow, g.rs, gcol0, g.n_rows, row_ok, sc);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -518,21 +544,9 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel(const __grid_cons
                 // weight 2^-(12 + 7 gi), exact power of two
                 const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
                 const double sc = -(rsi * wg);
-    #pragma unroll 1
-                for (int cb = 0; cb < TN / 32; ++cb) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb * 32), r);
-                    const int64_t gc = gcol0 + cb * 32;
-                    if (row_ok && gc < g.n_rows) {  // column tiles may stick out past the matrix on the last panel
-    #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
-                            double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
-                            cv.x = fma(sc * rj.x, (double)(int)r[j], cv.x);
-                            cv.y = fma(sc * rj.y, (double)(int)r[j + 1], cv.y);
-                            *reinterpret_cast<double2*>(crow + gc + j) = cv;
-                        }
-                    }
+                {
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN);
+                    epi_rmw_row<false>(trow, trow, crow, g.rs, gcol0, g.n_rows, row_ok, sc);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -818,27 +832,10 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                 tc_fence_after();
                 const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * g0)) << 52);
                 const double sc = -(rsi * wg);
-#pragma unroll 1
-                for (int cb = 0; cb < TN / 32; ++cb) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), r0);
-                    if (two) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TN + cb * 32), r1);
-                    const int64_t gc = gcol0 + cb * 32;
-                    if (row_ok && gc < g.n_rows) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
-                            double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
-                            double tx = (double)(int)r0[j], ty = (double)(int)r0[j + 1];
-                            if (two) {   // group g0 + 1 is 2^-7 of group g0: a0 + a1 2^-7 is exact, one rounding for the pair
-                                tx = fma((double)(int)r1[j], 0.0078125, tx);
-                                ty = fma((double)(int)r1[j + 1], 0.0078125, ty);
-                            }
-                            cv.x = fma(sc * rj.x, tx, cv.x);
-                            cv.y = fma(sc * rj.y, ty, cv.y);
-                            *reinterpret_cast<double2*>(crow + gc + j) = cv;
-                        }
-                    }
+                {
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+                    if (two) epi_rmw_row<true>(trow, trow + (uint32_t)TN, crow, g.rs, gcol0, g.n_rows, row_ok, sc);
+                    else epi_rmw_row<false>(trow, trow, crow, g.rs, gcol0, g.n_rows, row_ok, sc);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -851,21 +848,9 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
             tc_fence_after();
             const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
             const double sc = -(rsi * wg);
-#pragma unroll 1
-            for (int cb = 0; cb < TN / 32; ++cb) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cb * 32), r);
-                const int64_t gc = gcol0 + cb * 32;
-                if (row_ok && gc < g.n_rows) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
-                        double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
-                        cv.x = fma(sc * rj.x, (double)(int)r[j], cv.x);
-                        cv.y = fma(sc * rj.y, (double)(int)r[j + 1], cv.y);
-                        *reinterpret_cast<double2*>(crow + gc + j) = cv;
-                    }
-                }
+            {
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN);
+                epi_rmw_row<false>(trow, trow, crow, g.rs, gcol0, g.n_rows, row_ok, sc);
             }
             tc_fence_before();
             __syncwarp();
@@ -999,21 +984,9 @@ __global__ void __launch_bounds__(THREADS_W, 1) i8_update_kernel_wide(const __gr
             tc_fence_after();
             const double wg = __longlong_as_double((long long)(1023 - (12 + 7 * gi)) << 52);
             const double sc = -(rsi * wg);
-#pragma unroll 1
-            for (int cb = 0; cb < TN / 32; ++cb) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * TN + cb * 32), r);
-                const int64_t gc = gcol0 + cb * 32;
-                if (row_ok && gc < g.n_rows) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const double2 rj = *reinterpret_cast<const double2*>(g.rs + gc + j);
-                        double2 cv = *reinterpret_cast<double2*>(crow + gc + j);
-                        cv.x = fma(sc * rj.x, (double)(int)r[j], cv.x);
-                        cv.y = fma(sc * rj.y, (double)(int)r[j + 1], cv.y);
-                        *reinterpret_cast<double2*>(crow + gc + j) = cv;
-                    }
-                }
+            {
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * TN);
+                epi_rmw_row<false>(trow, trow, crow, g.rs, gcol0, g.n_rows, row_ok, sc);
             }
             tc_fence_before();
             __syncwarp();
@@ -1645,19 +1618,22 @@ __global__ void fill_planes_kernel(int8_t* p, size_t n) {
 }
 
 extern "C" int b200gp_i8_update_bench(b200gp_ctx* ctx, int64_t rows, int64_t cols, int64_t K, int S, int reps,
+                                      int64_t ldq /* row stride of a digit plane, 0 = K */, int64_t ldc /* 0 = cols */,
                                       double* ms_out, unsigned long long* dbg_out /* 16 or null */) {
     API_BEGIN(ctx)
-    if (rows % 256 || cols % 256 || K % 128 || S < 1 || S > 8 || cols > rows || reps < 1)
-        throw GpError("i8 bench: rows % 256 == 0, cols % 256 == 0, cols <= rows, K % 128 == 0, 1 <= S <= 8");
-    const size_t pstride = (size_t)rows * K;
-    Scratch planes_b(_ctx, pstride * S), rs_b(_ctx, (size_t)rows * 8), C_b(_ctx, (size_t)rows * cols * 8);
+    if (ldq <= 0) ldq = K;
+    if (ldc <= 0) ldc = cols;
+    if (rows % 256 || cols % 256 || K % 128 || S < 1 || S > 8 || cols > rows || reps < 1 || ldq < K || ldq % 128 || ldc < cols)
+        throw GpError("i8 bench: rows % 256 == 0, cols % 256 == 0, cols <= rows, K % 128 == 0, 1 <= S <= 8, ldq >= K, ldc >= cols");
+    const size_t pstride = (size_t)rows * ldq;
+    Scratch planes_b(_ctx, pstride * S), rs_b(_ctx, (size_t)rows * 8), C_b(_ctx, (size_t)rows * ldc * 8);
     Scratch err_b(_ctx, sizeof(int)), dbg_b(_ctx, oz::DBG_N * 8);
     int8_t* planes = (int8_t*)planes_b.p;
     double* rs = rs_b.f64();
     int* err = (int*)err_b.p;
     unsigned long long* dbg = (unsigned long long*)dbg_b.p;
     CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), _ctx->stream));
-    CUDA_CHECK(cudaMemsetAsync(C_b.p, 0, (size_t)rows * cols * 8, _ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(C_b.p, 0, (size_t)rows * ldc * 8, _ctx->stream));
     fill_planes_kernel<<<_ctx->num_sms * 8, 256, 0, _ctx->stream>>>(planes, pstride * S);
     {
         std::vector<double> ones((size_t)rows, 1.0);
@@ -1665,10 +1641,10 @@ extern "C" int b200gp_i8_update_bench(b200gp_ctx* ctx, int64_t rows, int64_t col
         CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
     }
     const int layout = (int)_ctx->oz_layout;   // layout 1 reads the same bytes through the 4-D map (timing only)
-    oz::Maps maps = oz::make_maps(planes, (int64_t)pstride, rows, K, S, layout, (int)_ctx->oz_l2promo);
+    oz::Maps maps = oz::make_maps(planes, (int64_t)pstride, rows, ldq, S, layout, (int)_ctx->oz_l2promo);
     oz::Args a{};
     a.layout = layout;
-    a.C = C_b.f64(); a.ldc = cols; a.rs = rs; a.row0 = 0; a.col0 = 0; a.b_row0 = 0;
+    a.C = C_b.f64(); a.ldc = ldc; a.rs = rs; a.row0 = 0; a.col0 = 0; a.b_row0 = 0;
     a.tiles_m = (int)(rows / oz::TM); a.tiles_n = (int)(cols / oz::TN);
     a.K = (int)K; a.k_begin = 0; a.S = S; a.n_rows = rows; a.skip_upper = 0; a.error_flag = err;
     a.prefetch = (int)_ctx->oz_prefetch; a.pg_single = (_ctx->oz_pairing == 2);

@@ -230,6 +230,9 @@ int b200gp_qs_variance(b200gp_qs* s, double* out);        /* d (n)       (solver
 int b200gp_qs_get_factor(b200gp_qs* s, double* c, double* w);
 /* symmetric generators d (n), p (n,J), q (n,J), a (n,J,J)  (quasisep.py:102-116) */
 int b200gp_qs_get_generators(b200gp_qs* s, double* d, double* p, double* q, double* a);
+/* sum_k (L^-1 y)_k^2 -- the data term of gp.py:313-316 (`-0.5 * jnp.sum(jnp.square(alpha))`) reduced on the device, so
+ * log_probability never brings the N-vector alpha back to the host (y: host or device, n doubles). */
+int b200gp_qs_solve_sumsq(b200gp_qs* s, const double* y, double* out);
 /* solve_triangular (solver.py:95-99; ops.py:463-472 / 489-498): Y (n, nrhs) in place */
 int b200gp_qs_solve_triangular(b200gp_qs* s, double* Y, int64_t nrhs, int transpose);
 /* dot_triangular (solver.py:101-102; core.py:303-305, ops.py:308-316) */

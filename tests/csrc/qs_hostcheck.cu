@@ -3,6 +3,7 @@
 // per-point generators, the GramBack scan monoid, chunk / tree / replay decomposition) with the oracle.
 // Built on demand by tests/test_device_code_on_host.py with nvcc; never linked into libb200gp.so.
 #include "../../tinygp_b200/csrc/qs_core.cuh"
+#include "../../tinygp_b200/csrc/qs_fast.cuh"
 
 #include <vector>
 
@@ -132,6 +133,48 @@ void factor_host(const QsModel& m, const double* t, const double* diag, int64_t 
     }
 }
 
+// the layout-specialised path of qs_fast.cu (qsf_run): chunk fold -> tree -> replay with the fused forward substitution and
+// the per-chunk quadratic sums -> tree over the affine composites -> finish
+template <int L>
+void fast_factor_host(const QsModel& m, const double* t, const double* diag, int64_t n, double* c, double* w,
+                      double* logdet_half, int* info, const double* x_fuse, double* sumsq) {
+    constexpr int J = lay_J(L);
+    const QsFastConst fc = qsf_constants(m);
+    const int64_t nch = (n + m.chunk - 1) / m.chunk;
+    std::vector<double> comp((size_t)Riccati<J>::SIZE * nch), fstart((size_t)J * J * nch), part(nch);
+    std::vector<double> acomp((size_t)Affine<J>::SIZE * nch), gstart((size_t)J * nch), quad((size_t)QsfQuad<J>::SIZE * nch);
+    for (int64_t ch = 0; ch < nch; ++ch) qsf_chunk_body<L>(m, fc, t, diag, n, comp.data(), nch, ch);
+    host_tree<Riccati<J>>(comp, nch, fstart);
+    *info = INT_MAX;
+    for (int64_t ch = 0; ch < nch; ++ch)
+        qsf_replay_body<L>(m, fc, t, diag, n, fstart.data(), nch, c, w, part.data(), info, x_fuse,
+                           x_fuse ? acomp.data() : nullptr, x_fuse ? quad.data() : nullptr, ch);
+    if (*info == INT_MAX) *info = 0;
+    double s = 0.0;
+    for (int64_t ch = 0; ch < nch; ++ch) s += part[ch];
+    *logdet_half = s;
+    if (x_fuse) {
+        host_tree<Affine<J>>(acomp, nch, gstart);
+        double ss = 0.0;
+        for (int64_t ch = 0; ch < nch; ++ch) ss += qsf_quad_eval<J>(quad.data(), gstart.data(), nch, ch);
+        *sumsq = ss;
+    }
+}
+
+template <int L>
+void fast_generators_host(const QsModel& m, const double* t, int64_t n, double* a_out, double* p_out) {
+    constexpr int J = lay_J(L);
+    const QsFastConst fc = qsf_constants(m);
+    for (int64_t k = 0; k < n; ++k) {
+        double a[J][J] = {}, p[J];
+        qsf_gen<L>(m, fc, (k == 0) ? 0.0 : (t[k] - t[k - 1]), a, p);
+        for (int i = 0; i < J; ++i) {
+            p_out[k * J + i] = p[i];
+            for (int j = 0; j < J; ++j) a_out[(k * J + i) * J + j] = a[i][j];
+        }
+    }
+}
+
 template <int J, int OP>
 void affine_host(const QsModel& m, const double* t, const double* diag, const double* c, const double* w,
                  const double* x, int64_t n, double* out) {
@@ -216,6 +259,33 @@ int hostcheck_affine(const double* comps, int ncomp, int op, const double* t, co
             default: return 3;
         }
         return 0;
+    } catch (const std::exception&) { return 2; }
+}
+
+// returns 4 if the model's block layout has no specialised code (the product then uses the generic path)
+int hostcheck_fast_factor(const double* comps, int ncomp, const double* t, const double* diag, int64_t n, int chunk,
+                          double* c, double* w, double* logdet_half, int* info, const double* x_fuse, double* sumsq) {
+    try {
+        QsModel m = build_model(comps, ncomp);
+        m.chunk = chunk;
+        switch (qsf_layout_of(m)) {
+#define X(code) case code: fast_factor_host<code>(m, t, diag, n, c, w, logdet_half, info, x_fuse, sumsq); return 0;
+            QSF_LAYOUTS(X)
+#undef X
+            default: return 4;
+        }
+    } catch (const std::exception&) { return 2; }
+}
+
+int hostcheck_fast_generators(const double* comps, int ncomp, const double* t, int64_t n, double* a_out, double* p_out) {
+    try {
+        QsModel m = build_model(comps, ncomp);
+        switch (qsf_layout_of(m)) {
+#define X(code) case code: fast_generators_host<code>(m, t, n, a_out, p_out); return 0;
+            QSF_LAYOUTS(X)
+#undef X
+            default: return 4;
+        }
     } catch (const std::exception&) { return 2; }
 }
 

@@ -285,6 +285,12 @@ class MockLib:
         y[:] = s.solve_triangular(y.copy(), transpose=bool(transpose))
         return 0
 
+    def b200gp_qs_solve_sumsq(self, h, Y, outp):
+        s = self._get(h)
+        y = arr(Y, (s.d.shape[0],))
+        outp._obj.value = float(np.sum(s.solve_triangular(y.copy()) ** 2))
+        return 0
+
     def b200gp_qs_dot_triangular(self, h, Y, nrhs):
         s = self._get(h)
         y = arr(Y, (s.d.shape[0], nrhs))

@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "qs_hostcheck.cu")
 OUT = os.path.join(HERE, "csrc", "_build", "libqs_hostcheck.so")
 DEPS = [SRC, os.path.join(HERE, "..", "tinygp_b200", "csrc", "qs_core.cuh"),
+        os.path.join(HERE, "..", "tinygp_b200", "csrc", "qs_fast.cuh"),
         os.path.join(HERE, "..", "tinygp_b200", "csrc", "common.cuh")]
 
 KERNELS = {
@@ -312,3 +313,74 @@ def test_warp_scan_tree_gives_the_same_states(lib, n, chunk):
     E = np.zeros((n, idx.size)); E[idx, np.arange(idx.size)] = 1.0
     want = so.solve_triangular(so.solve_triangular(E), transpose=True)[idx, np.arange(idx.size)]
     np.testing.assert_allclose(inv[idx], want, rtol=1e-9, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# the layout-specialised fast path (qs_fast.cuh): same checks, plus sum of squares without a third pass
+# ------------------------------------------------------------------------------------------------
+FAST_KERNELS = dict(KERNELS)
+FAST_KERNELS.update({
+    "celerite+m52": (Q.Celerite(1.1, 0.1, 0.3, 1.5) + Q.Matern52(2.5, 1.3),
+                     o.qs.Celerite(1.1, 0.1, 0.3, 1.5) + o.qs.Matern52(2.5, 1.3)),
+    "exp+exp+m32": (Q.Exp(1.7, 0.8) + Q.Exp(0.6, 0.4) + Q.Matern32(2.0, 0.7),
+                    o.qs.Exp(1.7, 0.8) + o.qs.Exp(0.6, 0.4) + o.qs.Matern32(2.0, 0.7)),
+    "sho3": (Q.SHO(1.5, 3.0, 1.8) + Q.SHO(0.4, 0.2, 0.5) + Q.SHO(2.2, 0.5, 0.3),
+             o.qs.SHO(1.5, 3.0, 1.8) + o.qs.SHO(0.4, 0.2, 0.5) + o.qs.SHO(2.2, 0.5, 0.3)),
+})
+
+
+@pytest.mark.parametrize("name", list(FAST_KERNELS))
+def test_fast_generators_match_the_oracle(lib, name):
+    """qsf_gen (compile-time block offsets, host-prepared reciprocals) against kernels/quasisep.py:102-116"""
+    k, ko = FAST_KERNELS[name]
+    comps = k.component_array()
+    t, _ = _data(200)
+    d, p, q, a = ko.to_symm_qsm(t)
+    ad, pd = np.zeros(a.shape), np.zeros(p.shape)
+    assert lib.hostcheck_fast_generators(_p(comps), comps.shape[0], _p(t), ctypes.c_int64(t.size), _p(ad), _p(pd)) == 0
+    np.testing.assert_allclose(ad, a, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(pd, p, rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("tree", [0, 1])
+@pytest.mark.parametrize("chunk", [1, 5, 64])
+@pytest.mark.parametrize("n", [1, 3, 257, 4100])
+@pytest.mark.parametrize("name", list(FAST_KERNELS))
+def test_fast_factor_and_fused_sum_of_squares(lib, name, n, chunk, tree):
+    """qsf_chunk_body -> tree -> qsf_replay_body -> tree -> qsf_quad_eval: c, w, sum log c of ops.py:354-361 and
+    |L^-1 y|^2 (gp.py:313-316) from the per-chunk quadratic sums, no forward-substitution pass over the points"""
+    k, ko = FAST_KERNELS[name]
+    comps = k.component_array()
+    t, noise = _data(n, seed=n + 1)
+    y = np.sin(t) + 0.3 * np.cos(3.1 * t)
+    so = o.QuasisepSolver(ko, t, o.Diagonal(noise))
+    J = k.state_dim()
+    c, w = np.zeros(n), np.zeros((n, J))
+    ld, info, ss = ctypes.c_double(), ctypes.c_int(), ctypes.c_double()
+    lib.hostcheck_set_tree(tree)
+    try:
+        rc = lib.hostcheck_fast_factor(_p(comps), comps.shape[0], _p(t), _p(noise), ctypes.c_int64(n), chunk, _p(c), _p(w),
+                                       ctypes.byref(ld), ctypes.byref(info), _p(y), ctypes.byref(ss))
+    finally:
+        lib.hostcheck_set_tree(0)
+    assert rc == 0 and info.value == 0
+    np.testing.assert_allclose(c, so.c, rtol=1e-11, atol=0)
+    np.testing.assert_allclose(w, so.w, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(ld.value, np.sum(np.log(so.c)), rtol=1e-12, atol=1e-12)
+    alpha = so.solve_triangular(y)
+    np.testing.assert_allclose(ss.value, np.sum(alpha ** 2), rtol=1e-10)
+
+
+def test_fast_factor_reports_the_first_bad_pivot(lib):
+    k = Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9)
+    comps = k.component_array()
+    n = 500
+    t, noise = _data(n, seed=3)
+    noise = noise.copy()
+    noise[321] = -50.0                                     # makes the pivot at 321 negative
+    c, w = np.zeros(n), np.zeros((n, 4))
+    ld, info, ss = ctypes.c_double(), ctypes.c_int(), ctypes.c_double()
+    y = np.sin(t)
+    assert lib.hostcheck_fast_factor(_p(comps), comps.shape[0], _p(t), _p(noise), ctypes.c_int64(n), 64, _p(c), _p(w),
+                                     ctypes.byref(ld), ctypes.byref(info), _p(y), ctypes.byref(ss)) == 0
+    assert info.value == 322                               # 1-based index of the first non-positive pivot

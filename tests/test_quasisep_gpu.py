@@ -31,9 +31,11 @@ def _data(n, seed=84930):
     return X, np.sin(X), rng
 
 
+@pytest.mark.parametrize("qs_kernel", [1, 0])      # 1: layout-specialised kernels (default), 0: generic J x J kernels
 @pytest.mark.parametrize("name", sorted(QS))
 @pytest.mark.parametrize("n", [1, 50, 333])
-def test_factor_and_ops_parity(name, n):
+def test_factor_and_ops_parity(name, n, qs_kernel, ctx):
+    ctx.set_option("qs_kernel", qs_kernel)           # restored by the autouse fixture of conftest.py
     X, y, rng = _data(n)
     k = QS[name]()
     ko = to_oracle(k)
@@ -60,8 +62,11 @@ def test_factor_and_ops_parity(name, n):
         np.testing.assert_allclose(s.covariance(), k(X, X) + np.diag(diag), rtol=5e-7, atol=5e-7)
 
 
+@pytest.mark.parametrize("qs_kernel,qs_tree", [(1, 0), (1, 1), (0, 0)])
 @pytest.mark.parametrize("name", sorted(QS))
-def test_logp_quasisep_equals_oracle_and_dense(name):
+def test_logp_quasisep_equals_oracle_and_dense(name, qs_kernel, qs_tree, ctx):
+    ctx.set_option("qs_kernel", qs_kernel)
+    ctx.set_option("qs_tree", qs_tree)
     # test_solver.py:59-79: QuasisepSolver vs DirectSolver log-probability
     X, y, _ = _data(700)
     k = QS[name]()

@@ -35,9 +35,7 @@ def test_paired_group_kernels_are_exact(ctx, rows, K, S, cluster, pairing, layou
     try:
         ctx.check(ctx.lib.b200gp_i8_update_test(ctx.handle, _cabi.ptr(pl), S, rows, K, _cabi.ptr(rs), _cabi.ptr(got)))
     finally:
-        ctx.set_option("ozaki_cluster", 21)
-        ctx.set_option("ozaki_pairing", 0)
-        ctx.set_option("ozaki_layout", 0)
+        ctx.reset_options()
     want = _ref_update(C, planes, rs, S)
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
 
@@ -52,15 +50,13 @@ def test_factorisation_with_paired_groups(ctx, layout, pairing):
     k = 1.3 * kernels.ExpSquared(0.8)
     ctx.set_option("nb", 512)
     ctx.set_option("ozaki_min_n", 0)
+    ctx.set_option("ozaki_cluster", 21)       # the chunk-major layout exists for the cta_group::1 kernels only
     ctx.set_option("ozaki_layout", layout)
     ctx.set_option("ozaki_pairing", pairing)
     try:
         lp = GaussianProcess(k, X, diag=0.1).log_probability(y)
     finally:
-        ctx.set_option("ozaki_layout", 0)
-        ctx.set_option("ozaki_pairing", 0)
-        ctx.set_option("ozaki_min_n", 8192)
-        ctx.set_option("nb", 1024)
+        ctx.reset_options()
     lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
     assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
 
@@ -84,8 +80,7 @@ def test_paired_cta_pair_kernel_is_exact(ctx, rows, K, S, pairing):
     try:
         ctx.check(ctx.lib.b200gp_i8_update_test(ctx.handle, _cabi.ptr(pl), S, rows, K, _cabi.ptr(rs), _cabi.ptr(got)))
     finally:
-        ctx.set_option("ozaki_cluster", 21)
-        ctx.set_option("ozaki_pairing", 0)
+        ctx.reset_options()
     want = C.copy()
     P = planes.astype(np.float64)
     for s in range(S):

@@ -87,6 +87,7 @@ SIGNATURES = {
     "b200gp_qs_get_factor": (c_int, [_V, _D, _D]),
     "b200gp_qs_get_generators": (c_int, [_V, _D, _D, _D, _D]),
     "b200gp_qs_solve_triangular": (c_int, [_V, _D, _L, _I]),
+    "b200gp_qs_solve_sumsq": (c_int, [_V, _D, c_double_p]),
     "b200gp_qs_dot_triangular": (c_int, [_V, _D, _L]),
     "b200gp_qs_matmul": (c_int, [_V, _D, _L]),
     "b200gp_qs_log_probability": (c_int, [_V, _D, _I, _D, _L, _D, _D, _I, POINTER(c_int), c_double_p]),

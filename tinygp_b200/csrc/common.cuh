@@ -64,7 +64,8 @@ struct b200gp_ctx {
     int64_t qs_chunk = 64;      // points per thread in the quasiseparable scans
     int64_t qs_tree = 0;        // 0: thread-sequential fan-in-16 tree over the chunk composites, 1: warp-shuffle scan (fan-in 32)
     int64_t potf2_version = 2;  // 1: column-at-a-time diagonal-block kernel, 2: rank-8 blocked with register tiles
-    int64_t qs_kernel = 0;      // quasiseparable scan kernels: 0 = one thread per chunk (round 1), 1 = warp-cooperative
+    int64_t qs_kernel = 1;      // quasiseparable factorisation: 1 = layout-specialised kernels (qs_fast.cuh) when the model's block
+                                // layout is compiled in, 0 = always the generic J x J kernels of qs_core.cuh
     int64_t panel_fused = 0;    // 1: one launch per 128-column step of the panel factorisation (potf2 + trtri + solve)
     int64_t oz_persistent = 0;  // int8 update: 1 = persistent tile scheduler (one CTA pair per SM pair, tiles by atomic counter)
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
@@ -79,9 +80,11 @@ struct b200gp_ctx {
     int64_t panel_overlap = 0;  // 1: inside a panel, update the rows below the diagonal tile on a side stream while potf2 runs
     cudaStream_t stream3 = nullptr;
     int64_t oz_prefetch = 0;    // L2 prefetch distance (K-chunks of 128) of the int8 update's TMA producer
-    int64_t oz_pairing = 0;    // int8 update: 1 = accumulate two digit groups at once (1.8x fewer operand loads), 2 = diagnostic
+    int64_t oz_pairing = 1;    // int8 update: 1 = accumulate two digit groups at once (default: 16 instead of 28 operand-stage loads
+                               // per K chunk at 7 planes), 0 = one group per pass, 2 = diagnostic (paired loop order, single groups)
     int64_t oz_layout = 0;     // digit planes: 0 plane-major, 1 chunk-major (all planes of a K chunk adjacent)
-    int64_t oz_cluster = 21;    // cluster shape of the int8 update kernel (CM*10 + CN), see ozaki.cu
+    int64_t oz_cluster = 2;     // int8 update kernel: 2 = CTA pair with tcgen05 cta_group::2 (default: 256 x 256 tile per pair, B halves
+                                // shared through the peer's shared memory), 1 = wide 1-SM tile, CM*10 + CN = cta_group::1 cluster shapes
     int64_t oz_l2promo = 3;     // TMA L2 promotion of the digit-plane maps: 0 none, 1 64 B, 2 128 B, 3 256 B
     int64_t oz_min_n = 8192;    // below this size the native DMMA path is used
     // deferred (non-blocking) kernel timers: event pairs resolved at the next flush_timers()

@@ -21,69 +21,7 @@
 #include <limits.h>
 #include "qs_core.cuh"
 
-#define QS_CHUNK 64
-
-struct b200gp_qs {
-    b200gp_ctx* ctx = nullptr;
-    int64_t n = 0;
-    int J = 0;
-    QsModel model{};
-    double* t = nullptr;     // n
-    double* diag = nullptr;  // n
-    double* c = nullptr;     // n
-    double* w = nullptr;     // n x J
-    int info = 0;
-    double logdet_half = 0.0;
-    // fused log_probability: forward-solve chunk composites accumulated inside the Cholesky replay pass
-    double* fused_comp = nullptr;
-    size_t fused_comp_bytes = 0;
-};
-
-// up-sweep: parent[i] = fold of child[i*R .. i*R+R-1]
-template <class Op>
-__global__ void __launch_bounds__(QS_THREADS) tree_up_kernel(const double* child, int64_t nchild, double* parent, int64_t nparent) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nparent) return;
-    Op acc, e;
-    const int64_t b = i * TREE_R;
-    acc.load(child, nchild, b);
-    for (int64_t j = b + 1; j < b + TREE_R && j < nchild; ++j) {
-        e.load(child, nchild, j);
-        acc.combine(e);
-    }
-    acc.store(parent, nparent, i);
-}
-// top: a single thread walks the (<= TREE_R) top items and emits the state at each item's left edge
-template <class Op>
-__global__ void tree_top_kernel(const double* items, int64_t n, double* start) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    typename StateOf<Op>::type s;
-    state_zero(s);
-    Op e;
-    for (int64_t i = 0; i < n; ++i) {
-        state_store(s, start, n, i);
-        e.load(items, n, i);
-        e.apply(s);
-    }
-}
-// down-sweep: child start states from the parent's start state
-template <class Op>
-__global__ void __launch_bounds__(QS_THREADS) tree_down_kernel(const double* child, int64_t nchild, const double* pstart,
-                                                               int64_t nparent, double* cstart) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nparent) return;
-    typename StateOf<Op>::type s;
-    state_load(s, pstart, nparent, i);
-    Op e;
-    const int64_t b = i * TREE_R;
-    for (int64_t j = b; j < b + TREE_R && j < nchild; ++j) {
-        state_store(s, cstart, nchild, j);
-        if (j + 1 < b + TREE_R && j + 1 < nchild) {
-            e.load(child, nchild, j);
-            e.apply(s);
-        }
-    }
-}
+#include "qs_tree.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // scan kernels: thin wrappers over the __host__ __device__ bodies of qs_core.cuh (one thread = one chunk)
@@ -196,18 +134,6 @@ __global__ void general_gather_kernel(const __grid_constant__ QsModel m, const d
     }
     out[i * out_stride] = acc;
 }
-__global__ void sum_partials_kernel(const double* part, int64_t n, double* out) {
-    __shared__ double sh[1024];
-    double acc = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) acc += part[i];
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) out[0] = sh[0];
-}
 __global__ void add_const_kernel(const double* in, double c0, double* out, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] + c0;
@@ -232,141 +158,6 @@ __global__ void generators_kernel(const __grid_constant__ QsModel m, const doubl
         p[k * J + i] = pp[i];
         q[k * J + i] = m.q[i];
         for (int j = 0; j < J; ++j) a[(k * J + i) * J + j] = aa[i][j];
-    }
-}
-
-static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
-
-// ---------------------------------------------------------------------------------------------
-// warp-shuffle scan over the chunk composites (option "qs_tree" = 1): the alternative to the thread-sequential
-// fan-in-16 tree above.  One warp scans 32 consecutive composites with a Hillis-Steele inclusive scan
-// (5 x __shfl_up of the composite + combine), stores every item's EXCLUSIVE in-warp prefix and the warp total; the
-// totals are scanned the same way (fan-in 32: 156250 chunks -> 4883 -> 153 -> 5), and one fully parallel pass per level
-// turns "state at the left edge of my warp" + "my exclusive prefix" into "state at my left edge".  Critical path per
-// level: 5 combines + 1 apply instead of 15 combines + 16 applies.  The composites are SoA, so the warp's loads and
-// stores of one element are coalesced.
-// ---------------------------------------------------------------------------------------------
-template <class Op>
-__global__ void __launch_bounds__(QS_THREADS) warp_scan_kernel(const double* items, int64_t n, double* pre, double* totals,
-                                                               int64_t ntot) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= ntot) return;                                  // whole warps only: ntot = ceil(n / 32)
-    const int64_t i = w * 32 + lane;
-    Op cur;
-    if (i < n) cur.load(items, n, i);
-    else cur.identity();
-    Op left;                                                // one temporary: two composites live (register budget)
-#pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {
-        left.assign_map(cur, [d](double v) { return __shfl_up_sync(0xffffffffu, v, d); });
-        if (lane >= d) {                                    // prefix[i] = prefix[i - d] (applied first) then prefix-part[i]
-            left.combine(cur);
-            cur = left;
-        }
-    }
-    left.assign_map(cur, [](double v) { return __shfl_up_sync(0xffffffffu, v, 1); });   // exclusive prefix
-    if (lane == 0) left.identity();
-    if (i < n) left.store(pre, n, i);
-    const int64_t last = ((n - w * 32) < 32 ? (n - w * 32) : 32) - 1;     // last valid lane of this warp
-    if (totals != nullptr && lane == last) cur.store(totals, ntot, w);
-}
-
-// start[i] = pre[i] applied to the state at the left edge of i's warp (zero at the top level)
-template <class Op>
-__global__ void __launch_bounds__(QS_THREADS) warp_propagate_kernel(const double* pre, int64_t n, const double* pstart,
-                                                                    int64_t nparent, double* start) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    typename StateOf<Op>::type s;
-    if (pstart != nullptr) state_load(s, pstart, nparent, i >> 5);
-    else state_zero(s);
-    Op e;
-    e.load(pre, n, i);
-    e.apply(s);
-    state_store(s, start, n, i);
-}
-
-// ---------------------------------------------------------------------------------------------
-// host-side tree driver: chunk composites -> start state per chunk
-// ---------------------------------------------------------------------------------------------
-template <class Op>
-static void run_tree_warp(b200gp_ctx* ctx, double* comp0, int64_t n0, double* start0) {
-    std::vector<int64_t> counts{n0};
-    while (counts.back() > 32) counts.push_back((counts.back() + 31) / 32);
-    const int L = (int)counts.size();
-    std::vector<double*> items(L, nullptr), pre(L, nullptr), starts(L, nullptr);
-    items[0] = comp0;
-    starts[0] = start0;
-    for (int l = 0; l < L; ++l) {
-        pre[l] = (double*)ctx->alloc((size_t)Op::SIZE * counts[l] * 8);
-        if (l > 0) {
-            items[l] = (double*)ctx->alloc((size_t)Op::SIZE * counts[l] * 8);
-            starts[l] = (double*)ctx->alloc((size_t)Op::STATE * counts[l] * 8);
-        }
-    }
-    for (int l = 0; l < L; ++l) {                      // up: scan every level, totals feed the next one
-        const int64_t nw = (counts[l] + 31) / 32;
-        warp_scan_kernel<Op><<<nblk(nw * 32, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(
-            items[l], counts[l], pre[l], (l + 1 < L) ? items[l + 1] : nullptr, nw);
-        ctx->launches++;
-    }
-    for (int l = L - 1; l >= 0; --l) {                 // down: one parallel pass per level
-        warp_propagate_kernel<Op><<<nblk(counts[l], QS_THREADS), QS_THREADS, 0, ctx->stream>>>(
-            pre[l], counts[l], (l + 1 < L) ? starts[l + 1] : nullptr, (l + 1 < L) ? counts[l + 1] : 0, starts[l]);
-        ctx->launches++;
-    }
-    CUDA_CHECK(cudaGetLastError());
-    for (int l = 0; l < L; ++l) {
-        ctx->release(pre[l], (size_t)Op::SIZE * counts[l] * 8);
-        if (l > 0) {
-            ctx->release(items[l], (size_t)Op::SIZE * counts[l] * 8);
-            ctx->release(starts[l], (size_t)Op::STATE * counts[l] * 8);
-        }
-    }
-}
-
-template <class Op>
-static void run_tree(b200gp_ctx* ctx, double* comp0, int64_t n0, double* start0) {
-    if (ctx->qs_tree == 1) {
-        run_tree_warp<Op>(ctx, comp0, n0, start0);
-        return;
-    }
-    std::vector<double*> comps{comp0};
-    std::vector<int64_t> counts{n0};
-    std::vector<size_t> bytes{0};
-    while (counts.back() > TREE_R) {
-        const int64_t nc = counts.back(), np_ = (nc + TREE_R - 1) / TREE_R;
-        const size_t b = (size_t)Op::SIZE * np_ * 8;
-        double* parent = (double*)ctx->alloc(b);
-        tree_up_kernel<Op><<<nblk(np_, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(comps.back(), nc, parent, np_);
-        ctx->launches++;
-        comps.push_back(parent);
-        counts.push_back(np_);
-        bytes.push_back(b);
-    }
-    const int L = (int)counts.size();
-    std::vector<double*> starts(L, nullptr);
-    std::vector<size_t> sbytes(L, 0);
-    for (int l = 0; l < L; ++l) {
-        if (l == 0) {
-            starts[l] = start0;
-        } else {
-            sbytes[l] = (size_t)Op::STATE * counts[l] * 8;
-            starts[l] = (double*)ctx->alloc(sbytes[l]);
-        }
-    }
-    tree_top_kernel<Op><<<1, 32, 0, ctx->stream>>>(comps[L - 1], counts[L - 1], starts[L - 1]);
-    ctx->launches++;
-    for (int l = L - 2; l >= 0; --l) {
-        tree_down_kernel<Op><<<nblk(counts[l + 1], QS_THREADS), QS_THREADS, 0, ctx->stream>>>(
-            comps[l], counts[l], starts[l + 1], counts[l + 1], starts[l]);
-        ctx->launches++;
-    }
-    CUDA_CHECK(cudaGetLastError());
-    for (int l = 1; l < L; ++l) {
-        ctx->release(comps[l], bytes[l]);
-        ctx->release(starts[l], sbytes[l]);
     }
 }
 
@@ -471,8 +262,8 @@ static void qs_destroy(b200gp_qs* s) {
     if (!s) return;
     b200gp_ctx* ctx = s->ctx;
     const size_t nb = (size_t)s->n * 8;
-    if (s->t) ctx->release(s->t, nb);
-    if (s->diag) ctx->release(s->diag, nb);
+    if (s->t && s->owns_inputs) ctx->release(s->t, nb);
+    if (s->diag && s->owns_inputs) ctx->release(s->diag, nb);
     if (s->c) ctx->release(s->c, nb);
     if (s->w) ctx->release(s->w, nb * s->J);
     if (s->fused_comp) ctx->release(s->fused_comp, s->fused_comp_bytes);
@@ -495,7 +286,8 @@ static bool qs_is_unsorted(b200gp_ctx* ctx, const double* t_dev, int64_t n) {
 
 // t / diag may be host or device pointers
 static b200gp_qs* qs_create_impl(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n,
-                                 const double* diag, int assume_sorted, int* unsorted, const double* x_fuse_dev = nullptr) {
+                                 const double* diag, int assume_sorted, int* unsorted, const double* x_fuse_dev = nullptr,
+                                 bool borrow_device_inputs = false) {
     if (n <= 0) throw GpError("quasisep: n must be positive");
     QsModel model = build_model(comps, ncomp);
     b200gp_qs* s = new b200gp_qs();
@@ -506,10 +298,17 @@ static b200gp_qs* qs_create_impl(b200gp_ctx* ctx, const double* comps, int ncomp
     s->model.chunk = (int)ctx->qs_chunk;
     try {
         const size_t nb = (size_t)n * 8;
-        s->t = (double*)ctx->alloc(nb);
-        s->diag = (double*)ctx->alloc(nb);
-        CUDA_CHECK(cudaMemcpyAsync(s->t, t, nb, cudaMemcpyDefault, ctx->stream));
-        CUDA_CHECK(cudaMemcpyAsync(s->diag, diag, nb, cudaMemcpyDefault, ctx->stream));
+        if (borrow_device_inputs && qs_is_device_ptr(t) && qs_is_device_ptr(diag)) {
+            // transient object of the fused log-probability: read the caller's device buffers in place (no 16 B/point copy)
+            s->owns_inputs = false;
+            s->t = const_cast<double*>(t);
+            s->diag = const_cast<double*>(diag);
+        } else {
+            s->t = (double*)ctx->alloc(nb);
+            s->diag = (double*)ctx->alloc(nb);
+            CUDA_CHECK(cudaMemcpyAsync(s->t, t, nb, cudaMemcpyDefault, ctx->stream));
+            CUDA_CHECK(cudaMemcpyAsync(s->diag, diag, nb, cudaMemcpyDefault, ctx->stream));
+        }
         if (unsorted) *unsorted = 0;
         if (!assume_sorted && qs_is_unsorted(ctx, s->t, n)) {
             if (unsorted) *unsorted = 1;
@@ -526,7 +325,18 @@ static b200gp_qs* qs_create_impl(b200gp_ctx* ctx, const double* comps, int ncomp
             ProfTimer tm(ctx, &ctx->prof.qs_ms);
             ctx->prof.qs_launches++;
             ctx->prof.qs_bytes += 8.0 * (double)n * (2.0 * 2.0 + 1.0 + s->J);  // two passes read t,diag ; write c,w
-            QS_DISPATCH_J(s->J, (qs_factor_J<JJ>(s, info_dev, ld_dev, x_fuse_dev)))
+            Scratch ss_dev(ctx, 8);
+            bool fast = false;
+            if (ctx->qs_kernel != 0 && qsf_supported(s->model))
+                fast = qsf_factor(s, s->t, s->diag, info_dev, ld_dev, x_fuse_dev, ss_dev.f64());
+            if (fast) {
+                if (x_fuse_dev) {
+                    s->has_sumsq = true;
+                    CUDA_CHECK(cudaMemcpyAsync(&s->sumsq, ss_dev.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                }
+            } else {
+                QS_DISPATCH_J(s->J, (qs_factor_J<JJ>(s, info_dev, ld_dev, x_fuse_dev)))
+            }
         }
         CUDA_CHECK(cudaMemcpyAsync(&s->info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaMemcpyAsync(&s->logdet_half, ld_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -570,38 +380,46 @@ static void qs_apply_host(b200gp_qs* s, int op, double* Y, int64_t nrhs, int op2
 
 static double qs_logp_impl(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n,
                            const double* diag, const double* resid, int assume_sorted, int* unsorted) {
-    double* x = (double*)ctx->alloc((size_t)n * 8);
-    CUDA_CHECK(cudaMemcpyAsync(x, resid, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
+    // the right-hand side: used in place when it already lives on the device
+    const bool x_borrowed = qs_is_device_ptr(resid);
+    double* x = x_borrowed ? const_cast<double*>(resid) : (double*)ctx->alloc((size_t)n * 8);
+    auto release_x = [&]() { if (!x_borrowed) ctx->release(x, (size_t)n * 8); };
+    if (!x_borrowed) CUDA_CHECK(cudaMemcpyAsync(x, resid, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
     b200gp_qs* s = nullptr;
     try {
-        s = qs_create_impl(ctx, comps, ncomp, t, n, diag, assume_sorted, unsorted, x);
+        s = qs_create_impl(ctx, comps, ncomp, t, n, diag, assume_sorted, unsorted, x, /*borrow_device_inputs=*/true);
     } catch (...) {
-        ctx->release(x, (size_t)n * 8);
+        release_x();
         throw;
     }
     if (!s) {
-        ctx->release(x, (size_t)n * 8);
+        release_x();
         return NAN;
     }
     double logp;
     try {
-        double* o = (double*)ctx->alloc((size_t)n * 8);
-        double* ss_dev = (double*)ctx->alloc(8);
-        {   // tree + replay only: the chunk composites were accumulated inside the Cholesky replay
-            ProfTimer tm(ctx, &ctx->prof.qs_ms);
-            ctx->prof.qs_launches++;
-            ctx->prof.qs_bytes += 8.0 * (double)n * (4.0 + s->J);
-            QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_LOWER_SOLVE>(s, x, o, ss_dev, s->fused_comp)))
-        }
         double ss = 0.0;
-        CUDA_CHECK(cudaMemcpyAsync(&ss, ss_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (s->has_sumsq) {
+            ss = s->sumsq;   // structured path: forward substitution folded into the factorisation passes
+        } else {
+            double* o = (double*)ctx->alloc((size_t)n * 8);
+            double* ss_dev = (double*)ctx->alloc(8);
+            {   // tree + replay only: the chunk composites were accumulated inside the Cholesky replay
+                ProfTimer tm(ctx, &ctx->prof.qs_ms);
+                ctx->prof.qs_launches++;
+                ctx->prof.qs_bytes += 8.0 * (double)n * (4.0 + s->J);
+                QS_DISPATCH_J(s->J, (qs_affine_J<JJ, OP_LOWER_SOLVE>(s, x, o, ss_dev, s->fused_comp)))
+            }
+            CUDA_CHECK(cudaMemcpyAsync(&ss, ss_dev, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            ctx->release(o, (size_t)n * 8);
+            ctx->release(ss_dev, 8);
+        }
         logp = -0.5 * ss - (s->logdet_half + 0.5 * (double)n * log(2.0 * M_PI));  // gp.py:313-316 ; solver.py:90-93
         if (s->info != 0 || !isfinite(logp)) logp = -INFINITY;
-        ctx->release(x, (size_t)n * 8);
-        ctx->release(o, (size_t)n * 8);
-        ctx->release(ss_dev, 8);
+        release_x();
     } catch (...) {
+        release_x();
         qs_destroy(s);
         throw;
     }
@@ -637,6 +455,26 @@ int b200gp_qs_create(b200gp_ctx* ctx, const double* comps, int ncomp, const doub
 int b200gp_qs_create_dev(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t_dev, int64_t n,
                          const double* diag_dev, int assume_sorted, b200gp_qs** out, int* unsorted, int* info) {
     return b200gp_qs_create(ctx, comps, ncomp, t_dev, n, diag_dev, assume_sorted, out, unsorted, info);
+}
+
+/* sum of squares of L^-1 y (gp.py:313-316: -0.5 * sum(alpha^2)) without bringing alpha back to the host */
+int b200gp_qs_solve_sumsq(b200gp_qs* s, const double* y, double* out) {
+    API_BEGIN(s->ctx)
+    const int64_t n = s->n;
+    Scratch x(_ctx, (size_t)n * 8), ss(_ctx, 8);
+    CUDA_CHECK(cudaMemcpyAsync(x.p, y, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
+    bool done = false;
+    {
+        ProfTimer tm(_ctx, &_ctx->prof.qs_ms);
+        if (_ctx->qs_kernel != 0) done = qsf_solve_sumsq(s, x.f64(), ss.f64());
+    }
+    if (!done) {
+        Scratch o(_ctx, (size_t)n * 8);
+        qs_affine(s, OP_LOWER_SOLVE, x.f64(), o.f64(), ss.f64());
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out, ss.p, 8, cudaMemcpyDeviceToHost, _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    API_END
 }
 
 int b200gp_qs_free(b200gp_qs* s) {

@@ -88,6 +88,16 @@ class QuasisepSolver(Solver):
     def solve_triangular(self, y, *, transpose: bool = False):  # solver.py:95-99
         return self._apply(self._ctx.lib.b200gp_qs_solve_triangular, y, int(bool(transpose)))
 
+    def whitened_sumsq(self, y):
+        """``sum(solve_triangular(y) ** 2)`` (the data term of gp.py:313-316) reduced on the device: at N = 10^7 the
+        N-vector ``alpha`` is neither copied back nor squared on the host.  Optional hook read by GaussianProcess."""
+        y = _cabi.f64(y)
+        if y.shape != (self._n,):
+            raise ValueError("dimension mismatch")
+        out = c_double()
+        self._ctx.check(self._ctx.lib.b200gp_qs_solve_sumsq(self._h, _cabi.ptr(y), byref(out)))
+        return out.value
+
     def dot_triangular(self, y):  # solver.py:101-102
         return self._apply(self._ctx.lib.b200gp_qs_dot_triangular, y)
 

@@ -124,8 +124,12 @@ _USED_THREADS = [1]
 
 
 def oracle_dense_logp_seconds(n):
-    """One oracle log_probability on ALL host cores (torchrun exports OMP_NUM_THREADS=1; undo that here)."""
+    """One oracle log_probability on ALL host cores (torchrun exports OMP_NUM_THREADS=1; undo that here).
+    Returns (t_build, t_rest, logp): the O(N^2) kernel-matrix build (kernels/base.py:84-103 + noise.py:77-78) and the
+    O(N^3) rest (LAPACK dpotrf = direct.py:53, triangular solve, reductions) are timed SEPARATELY so that each can be
+    extrapolated with its own exponent."""
     from oracle import tinygp_np as o
+    import scipy.linalg as sla
     X, y, diag, scale = make_dense_problem(n)
     try:
         from threadpoolctl import threadpool_info, threadpool_limits
@@ -133,9 +137,15 @@ def oracle_dense_logp_seconds(n):
     except Exception:
         limiter = None
     try:
+        kernel = o.Constant(1.0) * o.ExpSquared(scale)
+        noise = o.Diagonal(diag)
         t0 = time.perf_counter()
-        lp = o.GaussianProcess(o.Constant(1.0) * o.ExpSquared(scale), X, diag=diag).log_probability(y)
-        dt = time.perf_counter() - t0
+        K = noise.add_to(kernel(X, X))                                            # direct.py:51
+        t1 = time.perf_counter()
+        L = sla.cholesky(K, lower=True, check_finite=False, overwrite_a=True)     # direct.py:53
+        alpha = sla.solve_triangular(L, y, lower=True, check_finite=False)        # gp.py:320
+        lp = -0.5 * np.sum(alpha ** 2) - (np.sum(np.log(np.diag(L))) + 0.5 * n * np.log(2 * np.pi))   # gp.py:313-316
+        t2 = time.perf_counter()
         try:
             _USED_THREADS[0] = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
         except Exception:
@@ -143,7 +153,7 @@ def oracle_dense_logp_seconds(n):
     finally:
         if limiter is not None:
             limiter.restore_original_limits()
-    return dt, lp
+    return t1 - t0, t2 - t1, float(lp)
 
 
 def cpu_threads():
@@ -151,18 +161,33 @@ def cpu_threads():
 
 
 def pick_sample_n(budget_s_per_step):
-    """Calibrate on N=4096 and pick the largest sample whose step fits the budget (time ~ N^3 + N^2 build)."""
-    t, _ = oracle_dense_logp_seconds(4096)
+    """Calibrate on N=4096 and pick the largest sample whose step fits the budget."""
+    tb, tr, _ = oracle_dense_logp_seconds(4096)
     for n in (16384, 12288, 8192):
-        if t * (n / 4096.0) ** 3 <= budget_s_per_step:
+        if tb * (n / 4096.0) ** 2 + tr * (n / 4096.0) ** 3 <= budget_s_per_step:
             return n
     return 8192
+
+
+def extrapolate(tb, tr, n_s, n):
+    """build ~ N^2, factor + solve ~ N^3"""
+    return tb * (n / n_s) ** 2 + tr * (n / n_s) ** 3
+
+
+def full_size_cpu_record():
+    """the one full-size CPU run on record (tests/golden/full_size.json, made by tests/golden/make_golden_full.py)"""
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "full_size.json")))["c2"]
+        return {"build_s": g.get("build_s"), "factor_s": g.get("dpotrf_s"), "source": g.get("lapack")}
+    except Exception:
+        return None
 
 
 def run_reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path: tinygp needs jax + equinox, neither of which is
     installed here or on the GPU box (no network), so this is the NumPy/SciPy/LAPACK oracle port
-    (oracle/tinygp_np.py: same formulas, LAPACK dpotrf = what XLA:CPU calls), all host threads."""
+    (oracle/tinygp_np.py: same formulas, LAPACK dpotrf = what XLA:CPU calls), all host threads, on a bounded sample of
+    the workload; the build and the factorisation are extrapolated separately (N^2 / N^3)."""
     if rank != 0:
         return
     np.random.seed(0)
@@ -170,24 +195,27 @@ def run_reference_arm(args, rank, world):
     n_s = pick_sample_n(total_budget / max(1, args.steps + args.warmup))
     for _ in range(args.warmup):
         oracle_dense_logp_seconds(n_s)
-    ts = []
+    tbs, trs = [], []
     for _ in range(args.steps):
-        t, lp = oracle_dense_logp_seconds(n_s)
-        ts.append(t)
-    t_step = float(np.sum(ts)) / max(1, len(ts))
-    scale_up = (N_DENSE / n_s) ** 3
-    value = 1.0 / (t_step * scale_up)
+        tb, tr, lp = oracle_dense_logp_seconds(n_s)
+        tbs.append(tb); trs.append(tr)
+    tb, tr = float(np.median(tbs)), float(np.median(trs))
+    t_full = extrapolate(tb, tr, n_s, N_DENSE)
+    value = 1.0 / t_full
     cores = cpu_threads()
-    sample = (f"N={n_s} of the same workload per step ({t_step:.2f} s measured), extrapolated x{scale_up:.0f} "
-              f"(N^3) to N={N_DENSE}")
+    sample = (f"N={n_s} of the same workload per step: build {tb:.2f} s (x{(N_DENSE / n_s) ** 2:.0f}, N^2) + "
+              f"dpotrf/solve {tr:.2f} s (x{(N_DENSE / n_s) ** 3:.0f}, N^3) -> {t_full:.0f} s at N={N_DENSE}")
     line = {
         "impl": "reference", "metric": "log_probability/sec", "value": value, "unit": "logp/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * scale_up * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"dense ExpSquared 3-D N={N_DENSE} log_probability (build + Cholesky + solve)",
-                   "kernel": "1.0*ExpSquared(scale=1.0), L2", "diag": 0.1, "seed": SEED},
-        "cpu_baseline": {"value": value, "unit": "logp/s", "cores": cores, "kind": "port", "sample": sample},
+                   "kernel": "1.0*ExpSquared(scale=1.0), L2", "diag": 0.1, "seed": SEED,
+                   "same_config": False, "note": "oracle port on a bounded sample, extrapolated (see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": value, "unit": "logp/s", "cores": cores, "kind": "port", "sample": sample,
+                         "full_size_run_on_record": full_size_cpu_record()},
         "e2e": {"value": value, "unit": "logp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "per_step_s_at_sample": [round(a + b, 3) for a, b in zip(tbs, trs)],
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -242,17 +270,21 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step_ms = []
+
+    def timed(fn, steps, record=None):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         barrier()
-        e0.record(stream)
+        evs[0].record(stream)
         out = None
-        for _ in range(steps):
+        for i in range(steps):
             out = fn()
-        e1.record(stream)
+            evs[i + 1].record(stream)
         barrier()
+        if record is not None:
+            record.extend(round(evs[i].elapsed_time(evs[i + 1]), 3) for i in range(steps))
         from tinygp_b200.parallel import max_over_ranks
-        return max_over_ranks(e0.elapsed_time(e1), device="cuda"), out
+        return max_over_ranks(evs[0].elapsed_time(evs[steps]), device="cuda"), out
 
     # fp64 tensor peak on this GPU: burst (short loop) and sustained (~2 s loop, the denominator for a kernel
     # timed inside a multi-second step)
@@ -273,7 +305,7 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms, logp = timed(step_device, args.steps)
+    ms, logp = timed(step_device, args.steps, per_step_ms)
     clocks = sampler.stop() if rank == 0 else None
     prof = ctx.profile(reset=True)
     ctx.set_option("profile", 0)
@@ -286,6 +318,25 @@ def run_ours(args, rank, local_rank, world):
     else:
         step_e2e()
         ms_e2e, logp_e2e = timed(step_e2e, e2e_steps)
+
+    # ---- the other BASELINE configs, attached to the one line the driver parses --------------------------------------
+    sub_records, sharded = {}, None
+    if not args.quick and not args.no_sub:
+        ctx.set_option("trim", 0)            # give the cached 34 GB matrix + digit planes back before the next workloads
+        if world > 1:
+            # BASELINE config 3: ONE factorisation sharded over all ranks (collective: every rank takes part)
+            try:
+                sharded = measure_sharded(args, ctx, rank, local_rank, world, steps=max(1, min(args.steps, 2)), warmup=1)
+            except Exception as e:  # noqa: BLE001
+                sharded = {"error": str(e)[:300]}
+        elif rank == 0:
+            for name, fn in (("c4_quasisep", measure_quasisep), ("c5_batched", measure_batched)):
+                try:
+                    ctx.reset_options()
+                    sub_records[name] = fn(args, ctx, local_rank)
+                except Exception as e:  # noqa: BLE001
+                    sub_records[name] = {"error": str(e)[:300]}
+                ctx.set_option("trim", 0)
 
     if rank != 0:
         if world > 1:
@@ -328,10 +379,12 @@ def run_ours(args, rank, local_rank, world):
     # CPU baseline on a bounded sample (rank 0 at N=1 only)
     if world == 1 and not args.quick:
         n_s = pick_sample_n(25.0)
-        t_cpu, lp_cpu = oracle_dense_logp_seconds(n_s)
-        cpu_value = 1.0 / (t_cpu * (n / n_s) ** 3)
-        cpu_baseline = {"value": cpu_value, "unit": "logp/s", "cores": cpu_threads(), "kind": "port",
-                        "sample": f"N={n_s} timed ({t_cpu:.2f} s), extrapolated x{(n / n_s) ** 3:.0f} (N^3) to N={n}"}
+        tb, tr, lp_cpu = oracle_dense_logp_seconds(n_s)
+        t_full = extrapolate(tb, tr, n_s, n)
+        cpu_baseline = {"value": 1.0 / t_full, "unit": "logp/s", "cores": cpu_threads(), "kind": "port",
+                        "sample": f"N={n_s} timed: build {tb:.2f} s (x{(n / n_s) ** 2:.0f}, N^2) + dpotrf/solve {tr:.2f} s "
+                                  f"(x{(n / n_s) ** 3:.0f}, N^3) -> {t_full:.0f} s at N={n}",
+                        "full_size_run_on_record": full_size_cpu_record()}
     else:
         cpu_baseline = None
 
@@ -354,28 +407,38 @@ def run_ours(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {"syrk": prof["syrk_ms"] / args.steps, "panel": prof["panel_ms"] / args.steps,
                                "build": prof["build_ms"] / args.steps, "solve": prof["solve_ms"] / args.steps},
+        "per_step_ms": per_step_ms,
     }
+    if sub_records:
+        line["configs"] = sub_records
+    if sharded is not None:
+        line["sharded"] = sharded
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_quasisep(args, rank, local_rank, world):
-    """BASELINE config 4: SHO + Matern-3/2 (J = 4) on a sorted 1-D series; non-default workload."""
+def _hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def measure_quasisep(args, ctx, local_rank, n=10_000_000, steps=None, warmup=3, opts=()):
+    """BASELINE config 4: SHO + Matern-3/2 (J = 4) on a sorted 1-D series of N = 1e7 points, one GPU.
+    `value`: device-resident inputs through b200gp_qs_log_probability_dev; `e2e`: GaussianProcess(...).log_probability(y)
+    with host buffers.  The C restatement of the sequential recursion (oracle/csrc) checks the FULL series."""
     import torch
     from ctypes import byref, c_double, c_int
     from tinygp_b200 import GaussianProcess, _cabi
     from tinygp_b200.kernels import quasisep as Q
 
-    from tinygp_b200 import multigpu
-    ctx = multigpu.make_context(local_rank)
+    steps = steps or max(3, min(args.steps, 10))
     stream = torch.cuda.current_stream()
-    if args.qs_chunk:
-        ctx.set_option("qs_chunk", args.qs_chunk)
-    for kv in args.opt:                            # tuning experiments, e.g. --opt qs_tree=1
+    for kv in opts:
         key, _, val = kv.partition("=")
         ctx.set_option(key, int(val))
-    n = args.n if args.n != N_DENSE else 10_000_000
     rng = np.random.default_rng(49384)
     t = np.sort(rng.uniform(0, n / 10.0, n))
     y = np.sin(t) + 0.1 * rng.normal(size=n)
@@ -393,91 +456,95 @@ def run_quasisep(args, rank, local_rank, world):
     def step_e2e():
         return GaussianProcess(kernel, t, diag=diag, assume_sorted=True).log_probability(y)
 
-    def timed(fn, steps):
+    def timed(fn, k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
-        for _ in range(steps):
+        for _ in range(k):
             out = fn()
         e1.record(stream)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), out
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
     ctx.set_option("profile", 1)
     ctx.profile(reset=True)
     l0 = ctx.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, logp = timed(step_device, args.steps)
+    reps = max(steps, 40)                     # a step is ~1 ms: take enough of them for nvidia-smi to sample the clocks
+    ms, logp = timed(step_device, reps)
     clocks = sampler.stop()
     prof = ctx.profile(reset=True)
     ctx.set_option("profile", 0)
     launches = ctx.launch_count() - l0
     step_e2e()
-    ms_e2e, logp_e2e = timed(step_e2e, max(1, min(args.steps, 3)))
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = 2
+    ms_e2e, logp_e2e = timed(step_e2e, e2e_steps)
     J = kernel.state_dim()
     alg_bytes = 8.0 * n * (3 + 1 + J)          # read t, diag, y ; write c, w   (64 B/point at J=4)
-    try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-        src = "MEASURED_PEAKS.json hbm_gbs (measured)"
-    except Exception:
-        hbm_peak, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    achieved = alg_bytes * args.steps / (prof["qs_ms"] * 1e-3) / 1e9
-    # CPU baseline: C restatement of the sequential recursion on a bounded sample (1 core, scalar port)
+    hbm_peak, src = _hbm_peak()
+    achieved = alg_bytes * reps / (prof["qs_ms"] * 1e-3) / 1e9
+    # parity at FULL size: the C restatement of ops.py:352-365,463-472 on all N points (1 core)
     from oracle import cref, tinygp_np as o
-    ns = min(n, 1_000_000)
     ko = o.qs.SHO(1.5, 3.0, 1.8) + o.qs.Matern32(1.5, 0.9)
-    d_, p_, q_, a_ = o.qs_generators_fast(ko, t[:ns])
+    d_, p_, q_, a_ = o.qs_generators_fast(ko, t)
     t0 = time.perf_counter()
-    lpo = cref.qs_log_probability(d_ + 0.1, p_, q_, a_, y[:ns])
+    lpo = cref.qs_log_probability(d_ + 0.1, p_, q_, a_, y)
     t_cpu = time.perf_counter() - t0
-    line = {
-        "metric": "log_probability/sec", "value": args.steps / (ms * 1e-3), "unit": "logp/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    del d_, p_, q_, a_
+    return {
+        "metric": "log_probability/sec", "value": reps / (ms * 1e-3), "unit": "logp/s", "n_gpus": 1,
+        "steps": reps, "warmup": warmup, "ms_per_step": ms / reps, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"quasisep SHO+Matern32 (J=4) N={n} log_probability", "diag": 0.1, "seed": 49384,
-                   "l2": "working set 0.64 GB > 126 MB L2"},
+                   "options": list(opts), "l2": "working set 0.64 GB > 126 MB L2"},
         "logp": logp, "logp_e2e": logp_e2e,
+        "parity": {"oracle_logp": lpo, "rel_err": abs(logp - lpo) / abs(lpo), "rel_err_e2e": abs(logp_e2e - lpo) / abs(lpo),
+                   "oracle": f"C restatement of the sequential recursion on all {n} points ({t_cpu:.2f} s, 1 core)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "peak_source": src, "traffic": None,
-                     "note": "kernel is fp64-ALU bound (Riccati composites), see DESIGN.md section 4"},
-        "cpu_baseline": {"value": 1.0 / (t_cpu * n / ns), "unit": "logp/s", "cores": 1, "kind": "port",
-                         "sample": f"first {ns} points, C restatement of ops.py:352-365,463-472 ({t_cpu:.2f} s; generators "
-                                   f"precomputed, not timed), scaled x{n / ns:.0f} (O(N))"},
+                     "peak_source": src, "traffic": None, "algorithmic_bytes_per_point": 8 * (3 + 1 + J),
+                     "note": "fp64-ALU bound (Riccati composites + exp/sincos per point), see DESIGN.md section 4"},
+        "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "logp/s", "cores": 1, "kind": "port",
+                         "sample": f"all {n} points, C restatement of ops.py:352-365,463-472 ({t_cpu:.2f} s; generators "
+                                   f"precomputed with NumPy, not timed)"},
         "clocks": clocks,
         "e2e": {"value": e2e_steps / (ms_e2e * 1e-3), "unit": "logp/s", "h2d_bytes_per_step": int(3 * 8 * n),
-                "d2h_bytes_per_step": int(8 * n + 8)},
-        "gpu_launches": int(launches), "kernel_ms_per_step": {"qs": prof["qs_ms"] / args.steps},
+                "d2h_bytes_per_step": 16,
+                "note": "host buffers are pageable NumPy arrays: 240 MB over PCIe per call bounds e2e at ~200 logp/s"},
+        "gpu_launches": int(launches), "kernel_ms_per_step": {"qs": prof["qs_ms"] / reps},
     }
+
+
+def run_quasisep(args, rank, local_rank, world):
+    """BASELINE config 4 as a stand-alone workload (python bench.py --workload quasisep)."""
+    from tinygp_b200 import multigpu
+    ctx = multigpu.make_context(local_rank)
+    if args.qs_chunk:
+        ctx.set_option("qs_chunk", args.qs_chunk)
+    n = args.n if args.n != N_DENSE else 10_000_000
+    line = measure_quasisep(args, ctx, local_rank, n=n, steps=args.steps, warmup=args.warmup, opts=args.opt)
+    line.update({"scaling": "weak", "vs_baseline": None})
     print(json.dumps(line), flush=True)
 
 
-def run_batched(args, rank, local_rank, world):
+def measure_batched(args, ctx, local_rank, rank=0, world=1, n=4096, steps=2, warmup=1):
     """BASELINE config 5: 1024 independent N=4096 ExpSquared problems (32 x 32 hyper-parameter grid), sharded
-    128 per GPU at 8 GPUs -- replicas only, no data-path collective.  Non-default workload."""
+    128 per GPU at 8 GPUs -- replicas only, no data-path collective."""
     import torch
     import torch.distributed as dist
     from tinygp_b200 import _cabi, kernels
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from tinygp_b200 import multigpu
-    ctx = multigpu.make_context(local_rank)
     stream = torch.cuda.current_stream()
-    n = 4096 if args.n == N_DENSE else args.n
     nprob = 1024
     rng = np.random.default_rng(49385)
     X = np.ascontiguousarray(rng.uniform(0, 8, (n, 3)))
     y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
     diag = np.full(n, 0.1)
-    grid = [(s, a) for s in np.logspace(-0.5, 0.5, 32) for a in np.logspace(-1, 1, 32)]
+    grid = [(sc, a) for sc in np.logspace(-0.5, 0.5, 32) for a in np.logspace(-1, 1, 32)]
     from tinygp_b200.parallel import shard_indices
     mine = [grid[i] for i in shard_indices(len(grid), rank, world)]
-    progs = np.ascontiguousarray(np.stack([(a * kernels.ExpSquared(scale=s)).program() for s, a in mine]))
+    progs = np.ascontiguousarray(np.stack([(a * kernels.ExpSquared(scale=sc)).program() for sc, a in mine]))
     out = np.empty(len(mine))
 
     def step():
@@ -485,49 +552,73 @@ def run_batched(args, rank, local_rank, world):
             ctx.handle, _cabi.ptr(progs), progs.shape[1], len(mine), _cabi.ptr(X), n, 3, _cabi.ptr(diag), _cabi.ptr(y),
             _cabi.ptr(out)))
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    t = float(ms.item()) * 1e-3
+    # parity on the corners of the grid this rank holds (oracle: LAPACK at N = 4096, ~1 s each)
+    from oracle import tinygp_np as o
+    checks = []
     if rank == 0:
-        t = float(ms.item()) * 1e-3
-        print(json.dumps({
-            "metric": "log_probability/sec", "value": nprob * args.steps / t, "unit": "logp/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True,
-            "scaling": "strong", "dtype": "f64", "data": "synthetic", "vs_baseline": None,
-            "config": {"workload": f"batched: {nprob} x (N={n}) ExpSquared log_probability, hyper-parameter grid, "
-                                   f"{len(mine)} problems per GPU (host buffers, end to end)"},
-            "tflops_n3_over_3": nprob * args.steps * n ** 3 / 3 / t / 1e12,
-            "logp_first": float(out[0]),
-        }), flush=True)
+        for idx in (0, len(mine) - 1):
+            sc, a = mine[idx]
+            lpo = o.GaussianProcess(o.Constant(a) * o.ExpSquared(sc), X, diag=0.1).log_probability(y)
+            checks.append(abs(out[idx] - lpo) / abs(lpo))
+    tf = nprob * steps * n ** 3 / 3 / t / 1e12
+    return {
+        "metric": "log_probability/sec", "value": nprob * steps / t, "unit": "logp/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3 / steps, "higher_is_better": True,
+        "scaling": "strong", "dtype": "f64", "data": "synthetic", "vs_baseline": None,
+        "config": {"workload": f"batched: {nprob} x (N={n}) ExpSquared log_probability, hyper-parameter grid, "
+                               f"{len(mine)} problems per GPU (host buffers, end to end)"},
+        "tflops_n3_over_3": tf,
+        "roofline": {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "peak": None,
+                     "note": "native fp64 DMMA path (N = 4096 < ozaki_min_n); DMMA peak measured by the dense line"},
+        "parity": {"max_rel_err_vs_oracle_on_grid_corners": max(checks) if checks else None},
+        "logp_first": float(out[0]), "clocks": clocks,
+    }
+
+
+def run_batched(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from tinygp_b200 import multigpu
+    ctx = multigpu.make_context(local_rank)
+    n = 4096 if args.n == N_DENSE else args.n
+    line = measure_batched(args, ctx, local_rank, rank, world, n=n, steps=args.steps, warmup=args.warmup)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_sharded(args, rank, local_rank, world):
-    """BASELINE config 3: ONE dense log_probability sharded over the GPUs (row-sharded int8 update, one NCCL
-    all-gather per block column, redundant panel factorisation).  Kernel 1.5*Matern52(2.0) + 0.7*RationalQuadratic(1.5,
-    alpha=1.5), both with the Euclidean metric (the L1 defaults are indefinite in 3-D),
-    N = 131072 by default.  Strong scaling."""
+def measure_sharded(args, ctx, rank, local_rank, world, n=131072, steps=2, warmup=1, slices=None):
+    """BASELINE config 3: ONE dense log_probability sharded over the GPUs.  Kernel 1.5*Matern52(2.0) +
+    0.7*RationalQuadratic(1.5, alpha=1.5), both with the Euclidean metric (the L1 defaults are indefinite in 3-D, see
+    DESIGN.md section 2), N = 131072 by default.  Strong scaling.  Collective: every rank must call this."""
     import torch
     import torch.distributed as dist
     from tinygp_b200 import kernels, multigpu
 
-    ctx = multigpu.make_context(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx.set_option("nb", args.nb)
-    n = 131072 if args.n == N_DENSE else args.n
     rng = np.random.default_rng(49383)
     side = 25.0 * (n / 131072.0) ** (1.0 / 3.0)
     X = np.ascontiguousarray(rng.uniform(0.0, side, (n, NDIM)))
@@ -536,51 +627,74 @@ def run_sharded(args, rank, local_rank, world):
     L2 = kernels.L2Distance()
     kernel = 1.5 * kernels.Matern52(2.0, L2) + 0.7 * kernels.RationalQuadratic(1.5, L2, alpha=1.5)
     dX, dy, dd = (torch.from_numpy(a).cuda() for a in (X, y, diag))
-    slices = args.slices or 8
+    slices = slices or args.slices or 7
+    stats = {}
 
     def step():
         return multigpu.log_probability_sharded(kernel, None, None, None, slices=slices, ctx=ctx, X_dev=dX, diag_dev=dd,
-                                                resid_dev=dy)
+                                                resid_dev=dy, stats=stats)
 
     from tinygp_b200.parallel import max_over_ranks
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     stream = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ctx.set_option("profile", 1)
     ctx.profile(reset=True)
+    if rank == 0:
+        sampler.start()
+    stats.clear()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         lp = step()
     e1.record(stream)
     torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     prof = ctx.profile(reset=True)
     ctx.set_option("profile", 0)
     ms = max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    t = ms * 1e-3
+    line = {
+        "metric": "log_probability/sec", "value": steps / t, "unit": "logp/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"dense Matern52+RationalQuadratic (L2) 3-D N={n}: ONE log_probability sharded over "
+                               f"{world} GPU(s), int8 fixed-point update ({slices} digit planes)",
+                   "diag": 0.1, "seed": 49383, "nb": args.nb, "exchange": stats.get("exchange", "all_gather_into_tensor per block column")},
+        "logp": lp, "golden": golden_check("c3", n, lp) or golden_check("c3s", n, lp),
+        "tflops_n3_over_3": n ** 3 / 3.0 * steps / t / 1e12,
+        "kernel_ms_per_step_rank0": {"i8_update": prof["syrk_ms"] / steps, "panel": prof["panel_ms"] / steps,
+                                     "build_cut": prof["build_ms"] / steps, "solve": prof["solve_ms"] / steps},
+        "exchange_bytes_per_step_per_rank": (stats["bytes"] // max(1, steps)) if stats.get("bytes") else 0,
+        "clocks": clocks,
+    }
+    if n <= 16384 and rank == 0:
+        from oracle import tinygp_np as o
+        ko = o.Constant(1.5) * o.Matern52(2.0, o.L2Distance()) + o.Constant(0.7) * o.RationalQuadratic(
+            1.5, o.L2Distance(), alpha=1.5)
+        lpo = o.GaussianProcess(ko, X, diag=0.1).log_probability(y)
+        line["oracle_logp"] = lpo
+        line["rel_err"] = abs(lp - lpo) / abs(lpo)
+    return line
+
+
+def run_sharded(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from tinygp_b200 import multigpu
+    ctx = multigpu.make_context(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    for kv in args.opt:
+        key, _, val = kv.partition("=")
+        ctx.set_option(key, int(val))
+    n = 131072 if args.n == N_DENSE else args.n
+    line = measure_sharded(args, ctx, rank, local_rank, world, n=n, steps=args.steps, warmup=args.warmup)
     if rank == 0:
-        t = ms * 1e-3
-        line = {
-            "metric": "log_probability/sec", "value": args.steps / t, "unit": "logp/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"dense Matern52+RationalQuadratic (L2) 3-D N={n}: ONE log_probability sharded over "
-                                   f"{world} GPU(s), int8 fixed-point update ({slices} digit planes), all-gather per block column",
-                       "diag": 0.1, "seed": 49383, "nb": args.nb},
-            "logp": lp, "golden": golden_check("c3s", n, lp), "tflops_n3_over_3": n ** 3 / 3.0 * args.steps / t / 1e12,
-            "kernel_ms_per_step_rank0": {"i8_update": prof["syrk_ms"] / args.steps, "panel": prof["panel_ms"] / args.steps,
-                                         "build_cut": prof["build_ms"] / args.steps, "solve": prof["solve_ms"] / args.steps},
-            "allgather_bytes_per_step": int(8 * n * (n + args.nb) / 2),
-        }
-        if n <= 16384:
-            from oracle import tinygp_np as o
-            ko = o.Constant(1.5) * o.Matern52(2.0, o.L2Distance()) + o.Constant(0.7) * o.RationalQuadratic(
-                1.5, o.L2Distance(), alpha=1.5)
-            lpo = o.GaussianProcess(ko, X, diag=0.1).log_probability(y)
-            line["oracle_logp"] = lpo
-            line["rel_err"] = abs(lp - lpo) / abs(lpo)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -610,6 +724,8 @@ def main():
                          "0 = native fp64 DMMA")
     ap.add_argument("--quick", action="store_true",
                     help="tuning sweeps: skip the e2e and cpu_baseline legs (the printed line is not a valid bench line)")
+    ap.add_argument("--no-sub", action="store_true",
+                    help="dense workload: skip the attached sub-records (C4 quasisep, C5 batched; sharded C3 when WORLD_SIZE > 1)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
                     help="library option for tuning runs (b200gp_set_option); dense and quasisep workloads")
     args = ap.parse_args()

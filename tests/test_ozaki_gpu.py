@@ -46,10 +46,11 @@ def test_i8_update_kernel_is_exact(ctx, rows, K, S, cluster, pairing, layout):
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
 
 
-@pytest.mark.parametrize("lookahead", [1, 0])
+@pytest.mark.parametrize("lookahead,subpanel", [(1, 256), (0, 256), (0, 0), (0, 512)])
 @pytest.mark.parametrize("slices", [8, 7, 6])
 @pytest.mark.parametrize("n,nb", [(1024, 256), (3000, 512), (6144, 1024)])
-def test_ozaki_factor_parity(ctx, n, nb, slices, lookahead):
+def test_ozaki_factor_parity(ctx, n, nb, slices, lookahead, subpanel):
+    """subpanel: fp64 panel width inside a block column (two-level blocking; 0 = one fp64 panel per block column)"""
     rng = np.random.default_rng(n)
     X = rng.uniform(0, 20.0 * (n / 65536.0) ** (1 / 3), (n, 3))
     y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
@@ -59,6 +60,7 @@ def test_ozaki_factor_parity(ctx, n, nb, slices, lookahead):
     ctx.set_option("ozaki_slices", slices)
     ctx.set_option("ozaki_min_n", 0)
     ctx.set_option("ozaki_lookahead", lookahead)
+    ctx.set_option("ozaki_subpanel", subpanel)
     try:
         s = solvers.DirectSolver(k, X, noise.Diagonal(diag))
         lp = GaussianProcess(k, X, diag=diag).log_probability(y)

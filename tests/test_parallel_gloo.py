@@ -73,3 +73,45 @@ def test_row_chunks_partition_every_block_column():
             for (a0, a1), (b0, b1) in zip(cover, cover[1:]):
                 assert a1 == b0 or (a1 == np_ and b0 == np_)
             assert max(r1 for _, r1 in cover) == np_
+
+
+def _inplace_worker(rank, world, port, np_, nb, q):
+    import torch
+    from tinygp_b200 import multigpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        col = torch.full(((np_ + world * multigpu.ALIGN) * nb,), -1.0, dtype=torch.float64)
+        ok = True
+        for c0 in range(0, np_, nb):
+            r0, r1 = multigpu.my_rows(np_, c0, world, rank)
+            rows = torch.arange(r0, r1, dtype=torch.float64)
+            col[r0 * nb:r1 * nb] = (rows[:, None] * 1000.0 + c0 + torch.arange(nb, dtype=torch.float64)[None, :]).reshape(-1)
+            o0, o1, i0, i1 = multigpu.inplace_slices(np_, nb, c0, world, rank)
+            ch = multigpu.row_chunk(np_, c0, world)
+            assert i0 == o0 + rank * ch * nb and i1 - i0 == ch * nb and o1 - o0 == world * ch * nb
+            out = col[o0:o1]
+            dist.all_gather_into_tensor(out, col[i0:i1].clone())    # gloo has no in-place path: same geometry, copied input
+            allrows = torch.arange(c0, np_, dtype=torch.float64)
+            want = (allrows[:, None] * 1000.0 + c0 + torch.arange(nb, dtype=torch.float64)[None, :]).reshape(-1)
+            ok = ok and bool(torch.equal(col[c0 * nb:np_ * nb], want))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_inplace_block_column_allgather_geometry_world2():
+    """the sharded path's exchange (multigpu.inplace_slices): every rank ends up with every row of the block column"""
+    world, np_, nb = 2, 1280, 256
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_inplace_worker, args=(r, world, port, np_, nb, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)

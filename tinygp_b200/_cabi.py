@@ -71,6 +71,7 @@ SIGNATURES = {
     "b200gp_dense_log_probability_batched": (c_int, [_V, _D, _I, _L, _D, _L, _I, _D, _D, _D]),
     "b200gp_mg_create": (c_int, [_V, _D, _I, _D, _L, _I, _D, _D, _I, _I, POINTER(c_void_p)]),
     "b200gp_mg_free": (c_int, [_V]),
+    "b200gp_mg_use_colbuf": (c_int, [_V, _D, _L]),
     "b200gp_mg_geometry": (c_int, [_V, POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]),
     "b200gp_mg_update_rows": (c_int, [_V, _I, _L, _L]),
     "b200gp_mg_pack": (c_int, [_V, _I, _L, _L, _D]),

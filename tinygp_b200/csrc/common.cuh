@@ -85,6 +85,7 @@ struct b200gp_ctx {
     int64_t oz_layout = 0;     // digit planes: 0 plane-major, 1 chunk-major (all planes of a K chunk adjacent)
     int64_t oz_cluster = 2;     // int8 update kernel: 2 = CTA pair with tcgen05 cta_group::2 (default: 256 x 256 tile per pair, B halves
                                 // shared through the peer's shared memory), 1 = wide 1-SM tile, CM*10 + CN = cta_group::1 cluster shapes
+    int64_t oz_subpanel = 256;  // two-level blocking of the int8 factorisation: fp64 panel width inside a block column (0 = off)
     int64_t oz_l2promo = 3;     // TMA L2 promotion of the digit-plane maps: 0 none, 1 64 B, 2 128 B, 3 256 B
     int64_t oz_min_n = 8192;    // below this size the native DMMA path is used
     // deferred (non-blocking) kernel timers: event pairs resolved at the next flush_timers()

@@ -183,6 +183,7 @@ static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kO
     {"ozaki_cluster", &b200gp_ctx::oz_cluster},
     {"ozaki_min_n", &b200gp_ctx::oz_min_n},
     {"ozaki_l2promo", &b200gp_ctx::oz_l2promo},
+    {"ozaki_subpanel", &b200gp_ctx::oz_subpanel},
     {"ozaki_persistent", &b200gp_ctx::oz_persistent},
 };
 

@@ -1413,7 +1413,12 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
     double* rs = (double*)ctx->alloc((size_t)np * 8);
     int* err = (int*)ctx->alloc(sizeof(int));
     CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), ctx->stream));
-    const int64_t slots_per_panel = (NB + 511) / 512;
+    // Two-level blocking (option "ozaki_subpanel" = SB, 0 = off): the fp64 panel factorisation works on SB-wide
+    // sub-panels; the update of sub-panel s by the sub-panels before it INSIDE the block column (K = s * SB <= NB - SB)
+    // also runs on the int8 pipe.  The DMMA work of a block column drops from ~NB^2/2 to ~SB^2/2 per row.
+    int64_t SB = lookahead ? 0 : ctx->oz_subpanel;
+    if (SB < 256 || SB >= NB || (NB % SB) != 0 || (SB % 256) != 0) SB = 0;
+    const int64_t slots_per_panel = SB ? (NB / SB) : ((NB + 511) / 512);
     const int64_t ncol_all = (np + NB - 1) / NB;
     const size_t corr_bytes = (size_t)ncol_all * slots_per_panel * np * 8;
     double* corr = (double*)ctx->alloc(corr_bytes);
@@ -1514,6 +1519,43 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
         }
         // ---- stream pan: factor the panel in fp64 (DMMA path), then cut the digits of the rows below it
         ctx->stream = pan;
+        if (SB) {
+            for (int64_t sp = 0; sp * SB < kb; ++sp) {
+                const int64_t cs = c0 + sp * SB;
+                const int64_t sw = (SB < c0 + kb - cs) ? SB : (c0 + kb - cs);
+                if (sp > 0) {   // C[cs:, cs:cs+sw] -= L[cs:, c0:cs] L[cs:cs+sw, c0:cs]^T with the digits cut a moment ago
+                    oz::Args a{};
+                    a.C = s->mat; a.ldc = ld; a.rs = rs;
+                    a.row0 = cs; a.col0 = cs; a.b_row0 = cs;
+                    a.tiles_m = (int)((np - cs) / oz::TM);
+                    a.tiles_n = (int)((sw + oz::TN - 1) / oz::TN);
+                    a.K = (int)(cs - c0); a.k_begin = (int)c0; a.S = S; a.n_rows = np; a.skip_upper = 1; a.error_flag = err;
+                    a.prefetch = 0; a.pg_single = (ctx->oz_pairing == 2); a.layout = layout;
+                    {
+                        ProfTimer t(ctx, &ctx->prof.syrk_ms);
+                        oz::launch_update(ctx, maps, a);
+                        ctx->prof.syrk_flop += 2.0 * (double)(np - cs) * (double)sw * (double)(cs - c0);
+                        ctx->prof.syrk_launches++;
+                    }
+                    oz::diag_correct_kernel<<<(unsigned)((sw + 255) / 256), 256, 0, pan>>>(
+                        s->mat, ld, corr + (size_t)J * slots_per_panel * np, sp, np, cs, sw);
+                    ctx->launches++;
+                }
+                {
+                    ProfTimer t(ctx, &ctx->prof.panel_ms);
+                    dense_panel_factor(s, cs, sw);
+                }
+                if (cs + sw < np) {
+                    const int64_t nrows = np - (cs + sw);
+                    const int64_t nthreads = nrows * (sw / 16);
+                    ProfTimer t(ctx, &ctx->prof.build_ms);
+                    oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, pan>>>(
+                        s->mat, ld, rs, cs + sw, nrows, cs, sw, planes, (int64_t)plane_stride, np, S,
+                        corr + ((size_t)J * slots_per_panel + sp) * np, np, layout);
+                    ctx->launches++;
+                }
+            }
+        } else {
         {
             ProfTimer t(ctx, &ctx->prof.panel_ms);
             dense_panel_factor(s, c0, kb);
@@ -1526,6 +1568,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
                 s->mat, ld, rs, c0 + kb, nrows, c0, kb, planes, (int64_t)plane_stride, np, S,
                 corr + (size_t)J * slots_per_panel * np, np, layout);
             ctx->launches++;
+        }
         }
         if (lookahead) CUDA_CHECK(cudaEventRecord(ev_cut[J], pan));
     }
@@ -1751,6 +1794,7 @@ struct b200gp_mg {
     // streaming mode: no full fp64 matrix; a rolling np x NB column buffer, forward solve + log-det per panel
     bool streaming = false;
     double* colbuf = nullptr;
+    bool colbuf_external = false;   // the rolling column buffer is the caller's (torch / NCCL-registered) memory
     double* y = nullptr;       // np, right-hand side being reduced
     double* x = nullptr;       // np, alpha
     double* logparts = nullptr;  // ncol partial sums of log L_ii
@@ -1830,11 +1874,24 @@ int b200gp_mg_free(b200gp_mg* m) {
     _ctx->release(m->y, (size_t)m->s->np * 8);
     _ctx->release(m->x, (size_t)m->s->np * 8);
     if (m->streaming) {
-        _ctx->release(m->colbuf, (size_t)m->s->np * m->NB * 8);
+        if (!m->colbuf_external) _ctx->release(m->colbuf, (size_t)m->s->np * m->NB * 8);
         m->s->mat = nullptr;
     }
     dense_destroy(m->s);
     delete m;
+    API_END
+}
+
+// streaming mode: use the caller's contiguous buffer of `rows` x nb doubles as the rolling block column (rows >= np), so
+// that a rank's row chunk of the column is ONE contiguous range and the block column can be all-gathered IN PLACE
+// (no pack / unpack copies around the collective)
+int b200gp_mg_use_colbuf(b200gp_mg* m, double* buf_dev, int64_t rows) {
+    API_BEGIN(m->ctx)
+    if (!m->streaming) throw GpError("mg_use_colbuf: only the streaming mode has a rolling column buffer");
+    if (!buf_dev || rows < m->s->np) throw GpError("mg_use_colbuf: the buffer must hold at least np rows");
+    if (!m->colbuf_external) _ctx->release(m->colbuf, (size_t)m->s->np * m->NB * 8);
+    m->colbuf = buf_dev;
+    m->colbuf_external = true;
     API_END
 }
 

@@ -30,6 +30,17 @@ def my_rows(np_: int, c0: int, world: int, rank: int) -> tuple[int, int]:
     return r0, min(np_, r0 + ch)
 
 
+def inplace_slices(np_: int, nb: int, c0: int, world: int, rank: int) -> tuple[int, int, int, int]:
+    """Element ranges (out_lo, out_hi, in_lo, in_hi) of the contiguous rolling block column (row r at r * nb) for the
+    in-place all-gather of block column c0: the output covers `world` equal chunks starting at row c0 and the input is this
+    rank's chunk INSIDE it (NCCL's in-place condition: in_lo == out_lo + rank * chunk).  The last chunks may reach past
+    np (the buffer has world * ALIGN spare rows)."""
+    ch = row_chunk(np_, c0, world)
+    out_lo = c0 * nb
+    in_lo = (c0 + rank * ch) * nb
+    return out_lo, (c0 + world * ch) * nb, in_lo, in_lo + ch * nb
+
+
 def make_context(local_rank: int = 0) -> _cabi.Context:
     """A library context on torch's current CUDA stream (so NCCL collectives order with our kernels).
     The legacy default stream has handle 0, which the C-ABI reads as "make a private stream", so a dedicated
@@ -47,7 +58,8 @@ def make_context(local_rank: int = 0) -> _cabi.Context:
 
 
 def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streaming: bool | None = None,
-                            ctx: _cabi.Context | None = None, X_dev=None, diag_dev=None, resid_dev=None) -> float:
+                            ctx: _cabi.Context | None = None, X_dev=None, diag_dev=None, resid_dev=None,
+                            stats: dict | None = None) -> float:
     """log N(resid | 0, k(X,X) + diag) with the factorisation sharded over the default process group.
     `*_dev` may be given as CUDA tensors (device-resident inputs, bench `value` leg).  `streaming=True` keeps no
     np x np fp64 matrix (forward solve and log-det are folded into the panel steps)."""
@@ -81,7 +93,14 @@ def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streamin
         np_, nb, ncol = c_int64(), c_int64(), c_int()
         ctx.check(lib.b200gp_mg_geometry(mg, byref(np_), byref(nb), byref(ncol)))
         np_, nb, ncol = np_.value, nb.value, ncol.value
-        if world > 1:
+        inplace = bool(streaming) and world > 1
+        if inplace:
+            # the rolling block column lives in a torch tensor: rank chunks are contiguous row ranges of it, so the
+            # collective runs IN PLACE (input = this rank's slice of the output) -- no pack / unpack copies
+            col_rows = np_ + world * ALIGN
+            colbuf = torch.empty(col_rows * nb, dtype=torch.float64, device="cuda")
+            ctx.check(lib.b200gp_mg_use_colbuf(mg, colbuf.data_ptr(), col_rows))
+        elif world > 1:
             chmax = row_chunk(np_, 0, world)
             mine_buf = torch.empty(chmax * nb, dtype=torch.float64, device="cuda")
             full_buf = torch.empty(world * chmax * nb, dtype=torch.float64, device="cuda")
@@ -90,11 +109,21 @@ def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streamin
             ch = row_chunk(np_, c0, world)
             r0, r1 = my_rows(np_, c0, world, rank)
             ctx.check(lib.b200gp_mg_update_rows(mg, J, r0, r1))
-            if world > 1:
+            if inplace:
+                o0, o1, i0, i1 = inplace_slices(np_, nb, c0, world, rank)
+                out = colbuf[o0:o1]
+                dist.all_gather_into_tensor(out, colbuf[i0:i1])
+                if stats is not None:
+                    stats["bytes"] = stats.get("bytes", 0) + int(out.numel() * 8)
+                    stats["exchange"] = "in-place dist.all_gather_into_tensor (NCCL) on the contiguous block column, one per block column"
+            elif world > 1:
                 mine = mine_buf[: ch * nb]
                 full = full_buf[: world * ch * nb]
                 ctx.check(lib.b200gp_mg_pack(mg, J, r0, r1, mine.data_ptr()))
                 dist.all_gather_into_tensor(full, mine)
+                if stats is not None:
+                    stats["bytes"] = stats.get("bytes", 0) + int(full.numel() * 8)
+                    stats["exchange"] = "pack -> dist.all_gather_into_tensor (NCCL) -> unpack, one per block column"
                 for r in range(world):
                     if r == rank:
                         continue

@@ -32,9 +32,11 @@ KERNELS = {
 }
 
 
+@pytest.mark.parametrize("build_fast", [1, 0])     # 1: sum-of-products normal form (default), 0: program interpreter
 @pytest.mark.parametrize("name", sorted(KERNELS))
 @pytest.mark.parametrize("ndim", [1, 3])
-def test_kernel_matrix_parity(name, ndim):
+def test_kernel_matrix_parity(name, ndim, build_fast, ctx):
+    ctx.set_option("build_fast", build_fast)          # restored by conftest's autouse fixture
     rng = np.random.default_rng(1234 + ndim)
     X1 = rng.uniform(-3, 3, (137, ndim)) if ndim > 1 else rng.uniform(-3, 3, 137)
     X2 = rng.uniform(-3, 3, (61, ndim)) if ndim > 1 else rng.uniform(-3, 3, 61)

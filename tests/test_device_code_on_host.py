@@ -132,6 +132,16 @@ def _kmat(klib, k, X1, X2):
     return out
 
 
+def _kmat_fast(klib, k, X1, X2):
+    prog, x1 = k.lower_for(X1)
+    _, x2 = k.lower_for(X2)
+    out, err = np.empty((x1.shape[0], x2.shape[0])), ctypes.create_string_buffer(256)
+    rc = klib.hostcheck_kernel_matrix_fast(_p(prog), prog.shape[0], _p(x1), ctypes.c_int64(x1.shape[0]), _p(x2),
+                                           ctypes.c_int64(x2.shape[0]), x1.shape[1], _p(out), err)
+    assert rc in (0, 4), err.value
+    return out if rc == 0 else None
+
+
 def _dense_cases():
     import sys
     sys.path.insert(0, os.path.join(HERE, "golden"))
@@ -154,6 +164,12 @@ def test_kernel_program_interpreter_reproduces_reference_kernel_values(klib, cas
     idx = np.arange(0, case["n"], max(1, case["n"] // 9))[:9]
     got = _kmat(klib, k, inp["X"][idx], inp["X_test"])
     np.testing.assert_allclose(got, np.array(gold["K_cross"]), rtol=1e-13, atol=1e-15)
+    fast = _kmat_fast(klib, k, inp["X"][idx], inp["X_test"])      # sum-of-products normal form (None: program has none)
+    if fast is not None:
+        np.testing.assert_allclose(fast, np.array(gold["K_cross"]), rtol=1e-13, atol=1e-15)
+    else:
+        assert "transforms" in case["kernel"] or "Subspace" in case["kernel"] or "Linear" in case["kernel"] \
+            or "Cholesky" in case["kernel"], case["kernel"]
     prog, x = k.lower_for(inp["X"][idx])
     d, err = ctypes.c_double(), ctypes.create_string_buffer(256)
     assert klib.hostcheck_kernel_diag(_p(prog), prog.shape[0], x.shape[1], ctypes.byref(d), err) == 0, err.value
@@ -384,3 +400,21 @@ def test_fast_factor_reports_the_first_bad_pivot(lib):
     assert lib.hostcheck_fast_factor(_p(comps), comps.shape[0], _p(t), _p(noise), ctypes.c_int64(n), 64, _p(c), _p(w),
                                      ctypes.byref(ld), ctypes.byref(info), _p(y), ctypes.byref(ss)) == 0
     assert info.value == 322                               # 1-based index of the first non-positive pivot
+
+
+def test_normal_form_covers_the_benchmark_kernels_and_refuses_what_it_cannot_represent(klib):
+    """kprog_to_fast: BASELINE configs 2 / 3 / 5 have a normal form; five leaves or five terms do not"""
+    from tinygp_b200 import kernels
+    rng = np.random.default_rng(5)
+    X1, X2 = rng.uniform(0, 4, (7, 3)), rng.uniform(0, 4, (5, 3))
+    L2 = kernels.L2Distance()
+    ok = [1.0 * kernels.ExpSquared(1.0), 1.5 * kernels.Matern52(2.0, L2) + 0.7 * kernels.RationalQuadratic(1.5, L2, alpha=1.5),
+          (kernels.Matern32(1.3, L2) + 0.2) * kernels.ExpSquared(0.8) * 2.5, kernels.Exp(1.1, L2) + kernels.Cosine(2.0, L2) * 0.3 + 0.01]
+    for k in ok:
+        fast = _kmat_fast(klib, k, X1, X2)
+        assert fast is not None
+        np.testing.assert_allclose(fast, _kmat(klib, k, X1, X2), rtol=2e-15, atol=0)
+    e = kernels.ExpSquared(0.8)
+    np.testing.assert_allclose(_kmat_fast(klib, e * e, X1, X2), _kmat(klib, e * e, X1, X2), rtol=2e-15, atol=0)
+    five = kernels.ExpSquared(0.5) + kernels.ExpSquared(0.6) + kernels.ExpSquared(0.7) + kernels.ExpSquared(0.8) + kernels.ExpSquared(0.9)
+    assert _kmat_fast(klib, five, X1, X2) is None

@@ -1,0 +1,81 @@
+"""One factorisation sharded over TWO GPUs (NCCL, one process per GPU): BASELINE config 3's path at a size the oracle
+can check.  Skipped when fewer than two CUDA devices are visible (the driver's 1-GPU test box)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, nb, streaming, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["LOCAL_RANK"] = str(rank)
+    torch.cuda.set_device(rank)
+    from tinygp_b200 import kernels, multigpu
+    ctx = multigpu.make_context(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ctx.set_option("nb", nb)
+        rng = np.random.default_rng(49383)
+        side = 25.0 * (n / 131072.0) ** (1.0 / 3.0)
+        X = np.ascontiguousarray(rng.uniform(0.0, side, (n, 3)))
+        y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+        diag = np.full(n, 0.1)
+        L2 = kernels.L2Distance()
+        k = 1.5 * kernels.Matern52(2.0, L2) + 0.7 * kernels.RationalQuadratic(1.5, L2, alpha=1.5)
+        stats = {}
+        lp = multigpu.log_probability_sharded(k, X, diag, y, slices=7, streaming=streaming, ctx=ctx, stats=stats)
+        q.put((rank, lp, stats.get("exchange", "")))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("streaming", [True, False])
+def test_sharded_two_ranks_matches_oracle_and_single_rank(streaming):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from oracle import tinygp_np as o
+    from tinygp_b200 import kernels, multigpu
+    n, nb, world = 5000, 512, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nb, streaming, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(49383)
+    side = 25.0 * (n / 131072.0) ** (1.0 / 3.0)
+    X = np.ascontiguousarray(rng.uniform(0.0, side, (n, 3)))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    ko = o.Constant(1.5) * o.Matern52(2.0, o.L2Distance()) + o.Constant(0.7) * o.RationalQuadratic(1.5, o.L2Distance(), alpha=1.5)
+    lpo = o.GaussianProcess(ko, X, diag=0.1).log_probability(y)
+    assert res[0][1] == res[1][1]                                  # every rank holds the same value
+    assert abs(res[0][1] - lpo) <= 1e-8 * abs(lpo), (res, lpo)
+    if streaming:
+        assert "in-place" in res[0][2]
+    # the same library, one rank: bit-identical (integer products are exact and the panel work is replicated)
+    from tinygp_b200 import _cabi
+    c = _cabi.get_context()
+    c.set_option("nb", nb)
+    L2 = kernels.L2Distance()
+    k = 1.5 * kernels.Matern52(2.0, L2) + 0.7 * kernels.RationalQuadratic(1.5, L2, alpha=1.5)
+    lp1 = multigpu.log_probability_sharded(k, X, np.full(n, 0.1), y, slices=7, streaming=streaming)
+    assert lp1 == res[0][1], (lp1, res)

@@ -66,6 +66,8 @@ struct b200gp_ctx {
     int64_t potf2_version = 2;  // 1: column-at-a-time diagonal-block kernel, 2: rank-8 blocked with register tiles
     int64_t qs_kernel = 1;      // quasiseparable factorisation: 1 = layout-specialised kernels (qs_fast.cuh) when the model's block
                                 // layout is compiled in, 0 = always the generic J x J kernels of qs_core.cuh
+    int64_t qs_occupancy = 1;   // structured quasisep kernels: 1 = register-capped variants (16 / 12 resident warps per SM), 0 = natural
+    int64_t build_fast = 1;     // kernel-matrix build: 1 = sum-of-products normal form when the program has one, 0 = interpreter
     int64_t panel_fused = 0;    // 1: one launch per 128-column step of the panel factorisation (potf2 + trtri + solve)
     int64_t oz_persistent = 0;  // int8 update: 1 = persistent tile scheduler (one CTA pair per SM pair, tiles by atomic counter)
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver

@@ -169,7 +169,9 @@ static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kO
     {"peak_iters", &b200gp_ctx::peak_iters},
     {"qs_tree", &b200gp_ctx::qs_tree},
     {"qs_chunk", &b200gp_ctx::qs_chunk},
+    {"build_fast", &b200gp_ctx::build_fast},
     {"qs_kernel", &b200gp_ctx::qs_kernel},
+    {"qs_occupancy", &b200gp_ctx::qs_occupancy},
     {"potf2_version", &b200gp_ctx::potf2_version},
     {"panel_fused", &b200gp_ctx::panel_fused},
     {"nb_batched", &b200gp_ctx::nb_batched},

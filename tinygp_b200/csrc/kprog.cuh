@@ -9,6 +9,136 @@
 #define SQRT5 2.23606797749979
 #define PI_D 3.141592653589793
 
+// one stationary leaf given the two distances of its metric (stationary.py:76-235 as cited per branch)
+__host__ __device__ __forceinline__ double kprog_leaf(const int op, const bool l2, const double p0, const double p1,
+                                                     const double l1, const double l2sq) {
+    if (op == B200GP_OP_EXPSQUARED || op == B200GP_OP_RATIONALQUADRATIC) {
+        // squared_distance / square(scale)   (stationary.py:105,234 ; distance.py:30-38,58-59)
+        const double sq = l2 ? l2sq : l1 * l1;
+        const double r2 = sq / (p0 * p0);
+        if (op == B200GP_OP_EXPSQUARED) return exp(-0.5 * r2);
+        return pow(1.0 + 0.5 * r2 / p1, -p1);
+    }
+    // distance (distance.py:44-45 / 51-56: sqrt with the r2==0 guard)
+    const double dist = l2 ? ((l2sq == 0.0) ? l1 : sqrt(l2sq)) : l1;
+    if (op == B200GP_OP_EXPCOS || op == B200GP_OP_EXPSIN) {
+        double sn, cs;
+        sincos(p1 * dist, &sn, &cs);
+        return exp(-p0 * dist) * ((op == B200GP_OP_EXPCOS) ? cs : sn);
+    }
+    const double r = dist / p0;
+    if (op == B200GP_OP_EXP) return exp(-r);
+    if (op == B200GP_OP_MATERN32) {
+        const double arg = SQRT3 * r;
+        return (1.0 + arg) * exp(-arg);
+    }
+    if (op == B200GP_OP_MATERN52) {
+        const double arg = SQRT5 * r;
+        return (1.0 + arg + arg * arg / 3.0) * exp(-arg);
+    }
+    if (op == B200GP_OP_COSINE) return cos(2.0 * PI_D * r);
+    const double s = sin(PI_D * r);   // EXPSINESQUARED
+    return exp(-p1 * (s * s));
+}
+
+// ---- sum-of-products normal form of a kernel program (no interpreter stack: everything stays in registers) -----------
+// K = sum_t coef[t] * prod_{i in mask[t]} leaf_i , at most 4 distinct identity-metric leaves and 4 terms; programs that do
+// not fit (input transforms, a leaf multiplied by itself, more leaves / terms) keep the generic interpreter below.
+#define KFAST_MAX 4
+struct KFast {
+    int nleaf, nterm;
+    int op[KFAST_MAX], l2[KFAST_MAX];
+    double p0[KFAST_MAX], p1[KFAST_MAX];
+    double coef[KFAST_MAX];
+    int mask[KFAST_MAX];
+};
+
+template <typename F>
+__host__ __device__ __forceinline__ double kfast_eval(const KFast& K, int ndim, F diff) {
+    double l1 = 0.0, l2sq = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+        const double df = diff(d);
+        l1 += fabs(df);
+        l2sq += df * df;
+    }
+    double v[KFAST_MAX];
+#pragma unroll
+    for (int i = 0; i < KFAST_MAX; ++i) {
+        v[i] = 1.0;
+        if (i < K.nleaf) v[i] = kprog_leaf(K.op[i], K.l2[i] != 0, K.p0[i], K.p1[i], l1, l2sq);
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < KFAST_MAX; ++t) {
+        if (t < K.nterm) {
+            double prod = K.coef[t];
+#pragma unroll
+            for (int i = 0; i < KFAST_MAX; ++i)
+                if ((K.mask[t] >> i) & 1) prod *= v[i];
+            acc += prod;
+        }
+    }
+    return acc;
+}
+
+// host: postfix program -> normal form by expanding the expression as a polynomial in its leaves
+static inline bool kprog_to_fast(const KProg& P, KFast& out) {
+    struct Poly { int n; double coef[KFAST_MAX]; int mask[KFAST_MAX]; };
+    Poly st[8];
+    int sp = 0;
+    KFast K{};
+    for (int i = 0; i < P.n; ++i) {
+        const int op = P.op[i];
+        if (op == B200GP_OP_ADD || op == B200GP_OP_MUL) {
+            if (sp < 2) return false;
+            const Poly b = st[--sp], a = st[sp - 1];
+            Poly r{};
+            if (op == B200GP_OP_ADD) {
+                r = a;
+                for (int j = 0; j < b.n; ++j) {
+                    int hit = -1;
+                    for (int k = 0; k < r.n; ++k) if (r.mask[k] == b.mask[j]) hit = k;
+                    if (hit >= 0) { r.coef[hit] += b.coef[j]; continue; }
+                    if (r.n >= KFAST_MAX) return false;
+                    r.coef[r.n] = b.coef[j]; r.mask[r.n] = b.mask[j]; ++r.n;
+                }
+            } else {
+                for (int j = 0; j < a.n; ++j)
+                    for (int k = 0; k < b.n; ++k) {
+                        if (a.mask[j] & b.mask[k]) return false;      // a leaf squared: not representable
+                        const int mk = a.mask[j] | b.mask[k];
+                        const double cf = a.coef[j] * b.coef[k];
+                        int hit = -1;
+                        for (int q = 0; q < r.n; ++q) if (r.mask[q] == mk) hit = q;
+                        if (hit >= 0) { r.coef[hit] += cf; continue; }
+                        if (r.n >= KFAST_MAX) return false;
+                        r.coef[r.n] = cf; r.mask[r.n] = mk; ++r.n;
+                    }
+            }
+            st[sp - 1] = r;
+            continue;
+        }
+        if (sp >= 8) return false;
+        Poly r{};
+        r.n = 1;
+        if (op == B200GP_OP_CONST) {
+            r.coef[0] = P.p0[i]; r.mask[0] = 0;
+        } else {
+            if (P.metric[i] != 0 || K.nleaf >= KFAST_MAX) return false;
+            K.op[K.nleaf] = op; K.l2[K.nleaf] = (P.dist[i] == B200GP_DIST_L2) ? 1 : 0;
+            K.p0[K.nleaf] = P.p0[i]; K.p1[K.nleaf] = P.p1[i];
+            r.coef[0] = 1.0; r.mask[0] = 1 << K.nleaf;
+            ++K.nleaf;
+        }
+        st[sp++] = r;
+    }
+    if (sp != 1) return false;
+    K.nterm = st[0].n;
+    for (int t = 0; t < K.nterm; ++t) { K.coef[t] = st[0].coef[t]; K.mask[t] = st[0].mask[t]; }
+    out = K;
+    return true;
+}
+
 // l1 = sum_d |x1_d - x2_d| ; l2sq = sum_d (x1_d - x2_d)^2   (explicit differences, distance.py:45,59)
 // `diff(d)` returns x1_d - x2_d; it is re-evaluated (not cached in a register array) so that the DMMA
 // GEMM epilogue, which inlines this, keeps its register budget.  Leaves that carry a linear input
@@ -53,40 +183,7 @@ __host__ __device__ __forceinline__ double kprog_eval(const KProg& P, int ndim, 
                     l2sq += z * z;
                 }
             }
-            const bool l2 = (P.dist[i] == B200GP_DIST_L2);
-            if (op == B200GP_OP_EXPSQUARED || op == B200GP_OP_RATIONALQUADRATIC) {
-                // squared_distance / square(scale)   (stationary.py:105,234 ; distance.py:30-38,58-59)
-                const double sq = l2 ? l2sq : l1 * l1;
-                const double r2 = sq / (p0 * p0);
-                if (op == B200GP_OP_EXPSQUARED)
-                    v = exp(-0.5 * r2);
-                else
-                    v = pow(1.0 + 0.5 * r2 / p1, -p1);
-            } else {
-                // distance (distance.py:44-45 / 51-56: sqrt with the r2==0 guard)
-                const double dist = l2 ? ((l2sq == 0.0) ? l1 : sqrt(l2sq)) : l1;
-                if (op == B200GP_OP_EXPCOS || op == B200GP_OP_EXPSIN) {
-                    double sn, cs;
-                    sincos(p1 * dist, &sn, &cs);
-                    st[sp++] = exp(-p0 * dist) * ((op == B200GP_OP_EXPCOS) ? cs : sn);
-                    continue;
-                }
-                const double r = dist / p0;
-                if (op == B200GP_OP_EXP) {
-                    v = exp(-r);
-                } else if (op == B200GP_OP_MATERN32) {
-                    const double arg = SQRT3 * r;
-                    v = (1.0 + arg) * exp(-arg);
-                } else if (op == B200GP_OP_MATERN52) {
-                    const double arg = SQRT5 * r;
-                    v = (1.0 + arg + arg * arg / 3.0) * exp(-arg);
-                } else if (op == B200GP_OP_COSINE) {
-                    v = cos(2.0 * PI_D * r);
-                } else {  // EXPSINESQUARED
-                    const double s = sin(PI_D * r);
-                    v = exp(-p1 * (s * s));
-                }
-            }
+            v = kprog_leaf(op, P.dist[i] == B200GP_DIST_L2, p0, p1, l1, l2sq);
         }
         st[sp++] = v;
     }

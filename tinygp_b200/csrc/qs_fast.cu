@@ -4,15 +4,18 @@
 #include "qs_tree.cuh"
 #include "qs_fast.cuh"
 
-template <int L>
-__global__ void __launch_bounds__(QS_THREADS) qsf_chunk_kernel(const __grid_constant__ QsModel m, const __grid_constant__ QsFastConst fc,
+// MINB: minimum resident blocks per SM asked of the compiler (register cap 65536 / (128 * MINB)): the fold / replay bodies
+// want ~154 / ~222 registers, i.e. 3 / 2 blocks = 12 / 8 warps per SM, and ncu shows the fp64 pipe only 57 % / 42 % busy at
+// that occupancy; MINB = 4 / 3 costs ~100 bytes of spills per thread and buys 16 / 12 warps.
+template <int L, int MINB>
+__global__ void __launch_bounds__(QS_THREADS, MINB) qsf_chunk_kernel(const __grid_constant__ QsModel m, const __grid_constant__ QsFastConst fc,
                                                                const double* __restrict__ t, const double* __restrict__ diag,
                                                                int64_t n, double* comp, int64_t nchunks) {
     const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch < nchunks) qsf_chunk_body<L>(m, fc, t, diag, n, comp, nchunks, ch);
 }
-template <int L>
-__global__ void __launch_bounds__(QS_THREADS) qsf_replay_kernel(const __grid_constant__ QsModel m, const __grid_constant__ QsFastConst fc,
+template <int L, int MINB>
+__global__ void __launch_bounds__(QS_THREADS, MINB) qsf_replay_kernel(const __grid_constant__ QsModel m, const __grid_constant__ QsFastConst fc,
                                                                 const double* __restrict__ t, const double* __restrict__ diag,
                                                                 int64_t n, const double* fstart, int64_t nchunks, double* c_out,
                                                                 double* w_out, double* logc_part, int* info,
@@ -43,14 +46,22 @@ static void qsf_run(b200gp_qs* s, const double* t, const double* diag, int* info
     const int64_t n = s->n, nch = (n + s->model.chunk - 1) / s->model.chunk;
     const QsFastConst fc = qsf_constants(s->model);
     Scratch comp(ctx, (size_t)Riccati<J>::SIZE * nch * 8), fstart(ctx, (size_t)J * J * nch * 8), part(ctx, (size_t)nch * 8);
-    qsf_chunk_kernel<L><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, fc, t, diag, n, comp.f64(), nch);
+    // option "qs_occupancy" = 1 (default): register-capped variants (more resident warps); compiled for the C4 layout only
+    const bool capped = (L == 10) && ctx->qs_occupancy != 0;
+    if (capped) qsf_chunk_kernel<L, (L == 10) ? 4 : 1><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, fc, t, diag, n, comp.f64(), nch);
+    else qsf_chunk_kernel<L, 1><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(s->model, fc, t, diag, n, comp.f64(), nch);
     ctx->launches++;
     run_tree<Riccati<J>>(ctx, comp.f64(), nch, fstart.f64());
     const bool fuse = (x_fuse != nullptr);
     Scratch acomp(ctx, fuse ? (size_t)Affine<J>::SIZE * nch * 8 : 8), quad(ctx, fuse ? (size_t)QsfQuad<J>::SIZE * nch * 8 : 8);
-    qsf_replay_kernel<L><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(
-        s->model, fc, t, diag, n, fstart.f64(), nch, s->c, s->w, part.f64(), info_dev, x_fuse, fuse ? acomp.f64() : nullptr,
-        fuse ? quad.f64() : nullptr);
+    if (capped)
+        qsf_replay_kernel<L, (L == 10) ? 3 : 1><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(
+            s->model, fc, t, diag, n, fstart.f64(), nch, s->c, s->w, part.f64(), info_dev, x_fuse, fuse ? acomp.f64() : nullptr,
+            fuse ? quad.f64() : nullptr);
+    else
+        qsf_replay_kernel<L, 1><<<nblk(nch, QS_THREADS), QS_THREADS, 0, ctx->stream>>>(
+            s->model, fc, t, diag, n, fstart.f64(), nch, s->c, s->w, part.f64(), info_dev, x_fuse, fuse ? acomp.f64() : nullptr,
+            fuse ? quad.f64() : nullptr);
     ctx->launches++;
     sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part.f64(), nch, logdet_dev);
     ctx->launches++;

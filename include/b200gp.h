@@ -190,6 +190,11 @@ typedef struct b200gp_mg b200gp_mg;
 int b200gp_mg_create(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
                      const double* diag, const double* resid, int slices, int streaming, b200gp_mg** out);
 int b200gp_mg_free(b200gp_mg* m);
+/* the panel step in two halves (sharded triangular solve): factor the diagonal block (its rows must be valid on every
+ * rank: the host broadcasts them) and solve this rank's rows [r0, r1) below it; after the host has all-gathered the
+ * finished column, _finish cuts the digits of all rows (and, streaming, folds the forward substitution / log-det). */
+int b200gp_mg_panel_factor(b200gp_mg* m, int J, int64_t r0, int64_t r1);
+int b200gp_mg_panel_finish(b200gp_mg* m, int J);
 /* streaming mode only: make a caller-owned contiguous device buffer (rows x nb doubles, rows >= np) the rolling block
  * column, so that rank chunks are contiguous and the column can be all-gathered in place by NCCL (no pack / unpack) */
 int b200gp_mg_use_colbuf(b200gp_mg* m, double* buf_dev, int64_t rows);

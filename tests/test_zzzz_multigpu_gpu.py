@@ -16,7 +16,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, nb, streaming, q):
+def _worker(rank, world, port, n, nb, streaming, split, q):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -36,14 +36,15 @@ def _worker(rank, world, port, n, nb, streaming, q):
         L2 = kernels.L2Distance()
         k = 1.5 * kernels.Matern52(2.0, L2) + 0.7 * kernels.RationalQuadratic(1.5, L2, alpha=1.5)
         stats = {}
-        lp = multigpu.log_probability_sharded(k, X, diag, y, slices=7, streaming=streaming, ctx=ctx, stats=stats)
+        lp = multigpu.log_probability_sharded(k, X, diag, y, slices=7, streaming=streaming, ctx=ctx, stats=stats,
+                                                split_panel=split)
         q.put((rank, lp, stats.get("exchange", "")))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("streaming", [True, False])
-def test_sharded_two_ranks_matches_oracle_and_single_rank(streaming):
+@pytest.mark.parametrize("streaming,split", [(True, True), (True, False), (False, False)])
+def test_sharded_two_ranks_matches_oracle_and_single_rank(streaming, split):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -54,7 +55,7 @@ def test_sharded_two_ranks_matches_oracle_and_single_rank(streaming):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nb, streaming, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nb, streaming, split, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=600) for _ in range(world))
@@ -71,6 +72,7 @@ def test_sharded_two_ranks_matches_oracle_and_single_rank(streaming):
     assert abs(res[0][1] - lpo) <= 1e-8 * abs(lpo), (res, lpo)
     if streaming:
         assert "in-place" in res[0][2]
+        assert ("broadcast" in res[0][2]) == split
     # the same library, one rank: bit-identical (integer products are exact and the panel work is replicated)
     from tinygp_b200 import _cabi
     c = _cabi.get_context()

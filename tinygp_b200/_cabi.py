@@ -77,6 +77,8 @@ SIGNATURES = {
     "b200gp_mg_pack": (c_int, [_V, _I, _L, _L, _D]),
     "b200gp_mg_unpack": (c_int, [_V, _I, _L, _L, _D]),
     "b200gp_mg_panel": (c_int, [_V, _I]),
+    "b200gp_mg_panel_factor": (c_int, [_V, _I, _L, _L]),
+    "b200gp_mg_panel_finish": (c_int, [_V, _I]),
     "b200gp_mg_finish": (c_int, [_V, c_double_p]),
     "b200gp_qs_check_sorted": (c_int, [_V, _D, _L, POINTER(c_int)]),
     "b200gp_qs_create": (c_int, [_V, _D, _I, _D, _L, _D, _I, POINTER(c_void_p), POINTER(c_int), POINTER(c_int)]),

@@ -735,6 +735,31 @@ void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb) {
     }
 }
 
+// Row-restricted panel factorisation for the sharded path: the diagonal block [k0, k0+kb) is factored (every rank does
+// this part redundantly) and the triangular solve is applied to the caller's rows [r0, r1) below the block only.  Tile
+// arithmetic is that of dense_panel_factor, so the rows a rank produces are bit-identical to the unsharded run.
+void dense_panel_factor_rows(b200gp_dense* s, int64_t k0, int64_t kb, int64_t r0, int64_t r1) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t np = s->np, ld = s->ld;
+    double* M = s->mat;
+    const int64_t bend = k0 + kb;
+    int64_t lo = (r0 > bend) ? r0 : bend, hi = (r1 < np) ? r1 : np;
+    if (lo % TILE || hi % TILE) throw GpError("panel_factor_rows: row range must be 128-aligned");
+    const int own = (hi > lo) ? (int)((hi - lo) / TILE) : 0;
+    for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
+        const int64_t c0 = k0 + j0;
+        const int blk = (int)((bend - c0) / TILE);          // block rows c0 .. bend
+        if (j0 > 0) {
+            gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld, blk, 1, (int)j0, -1.0, 1, 0);
+            if (own) gemm_nt(ctx, M + lo * ld + c0, ld, M + lo * ld + k0, ld, M + c0 * ld + k0, ld, own, 1, (int)j0, -1.0, 1, 0);
+        }
+        potf2(ctx, M + c0 * ld + c0, ld, s->linv + (c0 / TILE) * TILE * TILE, s->info_dev, (int)c0);
+        const double* li = s->linv + (c0 / TILE) * TILE * TILE;
+        if (blk > 1) gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld, li, TILE, blk - 1, 1, TILE, 1.0, 0, 0);
+        if (own) gemm_nt(ctx, M + lo * ld + c0, ld, M + lo * ld + c0, ld, li, TILE, own, 1, TILE, 1.0, 0, 0);
+    }
+}
+
 // generate K (+ diag, identity pad) for rows [r0, np), columns [c0, c0+ncols) straight into the matrix
 void dense_build_region(b200gp_dense* s, int64_t r0, int64_t c0, int64_t ncols) {
     b200gp_ctx* ctx = s->ctx;

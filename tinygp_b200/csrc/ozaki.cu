@@ -1390,6 +1390,7 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel_2sm(int iters, int* sin
 // left-looking factorisation driver
 // ================================================================================================
 void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb);                       // dense.cu
+void dense_panel_factor_rows(b200gp_dense* s, int64_t k0, int64_t kb, int64_t r0, int64_t r1);   // dense.cu
 struct BuildRegionArgs { int64_t r0, r1, c0, ncols; };
 void dense_build_rows(b200gp_dense* s, const BuildRegionArgs& a);                        // dense.cu
 void dense_build_region(b200gp_dense* s, int64_t r0, int64_t c0, int64_t ncols);          // dense.cu
@@ -1953,12 +1954,17 @@ int b200gp_mg_unpack(b200gp_mg* m, int J, int64_t r0, int64_t r1, const double* 
     API_END
 }
 
-// after the all-gather: diagonal correction, fp64 panel factorisation, digit cutting (identical on every rank)
-int b200gp_mg_panel(b200gp_mg* m, int J) {
+// ---- the panel step, in two halves so that the fp64 triangular solve is sharded by rows as well --------------------
+// mg_panel_factor: diagonal correction + factorisation of the diagonal block (every rank, redundantly: it needs the block's
+// rows, which the host broadcasts from their owner) + triangular solve of THIS rank's rows [r0, r1) below the block.
+// The host then all-gathers the finished column (in place) and calls mg_panel_finish: digit cutting of all rows and, in
+// streaming mode, the forward-substitution / log-det step that consumes the column before it is overwritten.
+int b200gp_mg_panel_factor(b200gp_mg* m, int J, int64_t r0, int64_t r1) {
     API_BEGIN(m->ctx)
     b200gp_dense* s = m->s;
     const int64_t np = s->np, c0 = (int64_t)J * m->NB;
     const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
+    if (m->streaming) s->mat = m->colbuf - c0;
     if (J >= 1) {
         oz::diag_correct_kernel<<<(unsigned)((kb + 255) / 256), 256, 0, _ctx->stream>>>(
             s->mat, s->ld, m->corr, (int64_t)J * m->slots_per_panel, np, c0, kb);
@@ -1966,8 +1972,17 @@ int b200gp_mg_panel(b200gp_mg* m, int J) {
     }
     {
         ProfTimer t(_ctx, &_ctx->prof.panel_ms);
-        dense_panel_factor(s, c0, kb);
+        dense_panel_factor_rows(s, c0, kb, r0, r1);
     }
+    CUDA_CHECK(cudaGetLastError());
+    API_END
+}
+
+static void mg_panel_tail(b200gp_mg* m, int J) {
+    b200gp_ctx* _ctx = m->ctx;
+    b200gp_dense* s = m->s;
+    const int64_t np = s->np, c0 = (int64_t)J * m->NB;
+    const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
     if (c0 + kb < np) {
         const int64_t nrows = np - (c0 + kb);
         const int64_t nthreads = nrows * (kb / 16);
@@ -1984,6 +1999,31 @@ int b200gp_mg_panel(b200gp_mg* m, int J) {
         dense_logdiag_partial(s, c0, valid, m->logparts + J);
     }
     CUDA_CHECK(cudaGetLastError());
+}
+
+int b200gp_mg_panel_finish(b200gp_mg* m, int J) {
+    API_BEGIN(m->ctx)
+    if (m->streaming) m->s->mat = m->colbuf - (int64_t)J * m->NB;
+    mg_panel_tail(m, J);
+    API_END
+}
+
+// after the all-gather: diagonal correction, fp64 panel factorisation, digit cutting (identical on every rank)
+int b200gp_mg_panel(b200gp_mg* m, int J) {
+    API_BEGIN(m->ctx)
+    b200gp_dense* s = m->s;
+    const int64_t np = s->np, c0 = (int64_t)J * m->NB;
+    const int64_t kb = (m->NB < np - c0) ? m->NB : (np - c0);
+    if (J >= 1) {
+        oz::diag_correct_kernel<<<(unsigned)((kb + 255) / 256), 256, 0, _ctx->stream>>>(
+            s->mat, s->ld, m->corr, (int64_t)J * m->slots_per_panel, np, c0, kb);
+        _ctx->launches++;
+    }
+    {
+        ProfTimer t(_ctx, &_ctx->prof.panel_ms);
+        dense_panel_factor(s, c0, kb);
+    }
+    mg_panel_tail(m, J);
     API_END
 }
 

@@ -59,7 +59,7 @@ def make_context(local_rank: int = 0) -> _cabi.Context:
 
 def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streaming: bool | None = None,
                             ctx: _cabi.Context | None = None, X_dev=None, diag_dev=None, resid_dev=None,
-                            stats: dict | None = None) -> float:
+                            stats: dict | None = None, split_panel: bool = True) -> float:
     """log N(resid | 0, k(X,X) + diag) with the factorisation sharded over the default process group.
     `*_dev` may be given as CUDA tensors (device-resident inputs, bench `value` leg).  `streaming=True` keeps no
     np x np fp64 matrix (forward solve and log-det are folded into the panel steps)."""
@@ -112,6 +112,19 @@ def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streamin
             if inplace:
                 o0, o1, i0, i1 = inplace_slices(np_, nb, c0, world, rank)
                 out = colbuf[o0:o1]
+                kbj = min(nb, np_ - c0)
+                if split_panel and ch >= kbj:
+                    # sharded triangular solve: the diagonal block's rows (all inside rank 0's chunk) go to everyone, each
+                    # rank factors the block and solves ITS rows, and the finished column is all-gathered in place
+                    dist.broadcast(colbuf[c0 * nb:(c0 + kbj) * nb], src=0)
+                    ctx.check(lib.b200gp_mg_panel_factor(mg, J, r0, r1))
+                    dist.all_gather_into_tensor(out, colbuf[i0:i1])
+                    ctx.check(lib.b200gp_mg_panel_finish(mg, J))
+                    if stats is not None:
+                        stats["bytes"] = stats.get("bytes", 0) + int(out.numel() * 8) + int(kbj * nb * 8)
+                        stats["exchange"] = ("NCCL broadcast of the diagonal block + in-place all_gather_into_tensor of the "
+                                             "factored block column (row-sharded update AND triangular solve)")
+                    continue
                 dist.all_gather_into_tensor(out, colbuf[i0:i1])
                 if stats is not None:
                     stats["bytes"] = stats.get("bytes", 0) + int(out.numel() * 8)

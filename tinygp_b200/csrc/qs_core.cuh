@@ -354,53 +354,60 @@ struct Riccati {
         }
     }
     // this <- this (left) combined with r (right)      (ops.py:376-383)
+    // M = I + F_l G_r is inverted ONCE (Gauss-Jordan with partial pivoting through solve_inplace on the identity) and
+    // the three solves of the reference become products with M^-1; with G_r symmetric, M^-T G_r = (G_r M^-1)^T.
     __host__ __device__ void combine(const Riccati& r) {
-        double M[J][J], X[J][J], T1[J][J], T2[J][J];
-        // M = I + F_l G_r
+        double M[J][J], Mi[J][J], X[J][J], T1[J][J], T2[J][J];
         matmul<J>(F, r.G, M);
-#pragma unroll
-        for (int i = 0; i < J; ++i) M[i][i] += 1.0;
-        // [M^-1 A_l | M^-1 F_l] share the factorisation: solve twice on copies
-        double Mc[J][J];
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) { Mc[i][j] = M[i][j]; X[i][j] = A[i][j]; }
-        solve_inplace<J>(Mc, X);        // X = M^-1 A_l
-        double newA[J][J];
-        matmul<J>(r.A, X, newA);        // A_r M^-1 A_l
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) { Mc[i][j] = M[i][j]; X[i][j] = F[i][j]; }
-        solve_inplace<J>(Mc, X);        // X = M^-1 F_l
-        matmul<J>(r.A, X, T1);          // A_r M^-1 F_l
-        matmul_nt<J>(T1, r.A, T2);      // ... A_r^T
-        double newF[J][J];
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) newF[i][j] = r.F[i][j] + T2[i][j];
-        // G_l + A_l^T M^-T G_r A_l : solve M^T Y = G_r
-#pragma unroll
-        for (int i = 0; i < J; ++i)
-#pragma unroll
-            for (int j = 0; j < J; ++j) { Mc[i][j] = M[j][i]; X[i][j] = r.G[i][j]; }
-        solve_inplace<J>(Mc, X);        // X = M^-T G_r
-        matmul<J>(X, A, T1);            // M^-T G_r A_l
 #pragma unroll
         for (int i = 0; i < J; ++i)
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                double s = 0.0;
+                if (i == j) M[i][j] += 1.0;
+                Mi[i][j] = (i == j) ? 1.0 : 0.0;
+            }
+        solve_inplace<J>(M, Mi);        // Mi = M^-1
+        matmul<J>(Mi, A, X);            // M^-1 A_l
+        double newA[J][J];
+        matmul<J>(r.A, X, newA);        // A_r M^-1 A_l
+        matmul<J>(Mi, F, X);            // M^-1 F_l
+        matmul<J>(r.A, X, T1);          // A_r M^-1 F_l
+        double newF[J][J];
 #pragma unroll
-                for (int k = 0; k < J; ++k) s += A[k][i] * T1[k][j];  // A_l^T (...)
-                T2[i][j] = s;
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = i; j < J; ++j) {   // F_r + (A_r M^-1 F_l) A_r^T is symmetric: upper triangle, mirrored
+                double acc = r.F[i][j];
+#pragma unroll
+                for (int k = 0; k < J; ++k) acc += T1[i][k] * r.A[j][k];
+                newF[i][j] = acc;
+                newF[j][i] = acc;
+            }
+        matmul<J>(r.G, Mi, X);          // G_r M^-1  = (M^-T G_r)^T
+        // T1 = (M^-T G_r) A_l = X^T A_l
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < J; ++k) acc += X[k][i] * A[k][j];
+                T1[i][j] = acc;
             }
 #pragma unroll
         for (int i = 0; i < J; ++i)
 #pragma unroll
-            for (int j = 0; j < J; ++j) { G[i][j] += T2[i][j]; A[i][j] = newA[i][j]; F[i][j] = newF[i][j]; }
+            for (int j = i; j < J; ++j) {   // G_l + A_l^T (M^-T G_r A_l): symmetric
+                double acc = G[i][j];
+#pragma unroll
+                for (int k = 0; k < J; ++k) acc += A[k][i] * T1[k][j];
+                T2[i][j] = acc;
+                T2[j][i] = acc;
+            }
+#pragma unroll
+        for (int i = 0; i < J; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) { G[i][j] = T2[i][j]; A[i][j] = newA[i][j]; F[i][j] = newF[i][j]; }
     }
     // f <- F + A (I + f G)^-1 f A^T
     __host__ __device__ void apply(double (&f)[J][J]) const {

@@ -149,17 +149,14 @@ def test_panel_overlap_option_gives_the_same_factorisation(ctx, slices):
     ctx.set_option("ozaki_slices", slices if slices else 7)
     out = []
     try:
-        for overlap, ahead in ((0, 0), (1, 0), (0, 1), (1, 1)):
-            ctx.set_option("panel_overlap", overlap)
+        ctx.set_option("ozaki_subpanel", 0)      # one fp64 panel per block column: 4 diagonal tiles per look-ahead chain
+        for overlap, ahead in ((0, 0), (1, 0), (0, 1), (1, 1), (2, 0), (2, 1)):
+            ctx.set_option("panel_overlap", overlap)   # 2 = look-ahead: diagonal block on the main stream, rows below on a side stream
             ctx.set_option("build_ahead", ahead)
             out.append(GaussianProcess(k, X, diag=0.1).log_probability(y))
     finally:
-        ctx.set_option("panel_overlap", 0)
-        ctx.set_option("build_ahead", 0)
-        ctx.set_option("ozaki_min_n", 8192)
-        ctx.set_option("ozaki_slices", 7)
-        ctx.set_option("nb", 1024)
-    assert out[0] == out[1] == out[2] == out[3], out
+        ctx.reset_options()
+    assert all(v == out[0] for v in out), out
     lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
     assert rel(out[0], lpo) < LOGP_RTOL
 

@@ -223,7 +223,8 @@ int b200gp_set_option(b200gp_ctx* ctx, const char* key, int64_t value) {
         if (strcmp(key, o.key)) continue;
         validate_option(key, value);
         if (!strcmp(key, "ozaki_pairing")) value = (value == 2) ? 2 : (value ? 1 : 0);
-        else if (!strcmp(key, "build_ahead") || !strcmp(key, "panel_overlap")) value = value ? 1 : 0;
+        else if (!strcmp(key, "build_ahead")) value = value ? 1 : 0;
+        else if (!strcmp(key, "panel_overlap")) value = (value == 2) ? 2 : (value ? 1 : 0);
         _ctx->*(o.field) = value;
         return 0;
     }

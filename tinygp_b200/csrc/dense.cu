@@ -679,14 +679,20 @@ static void potf2(b200gp_ctx* ctx, double* A, int64_t lda, double* linv, int* in
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
 
 // factor the panel of columns [k0, k0+kb) over all rows >= k0: inner 128-wide left-looking sweep
+static void dense_panel_factor_lookahead(b200gp_dense* s, int64_t k0, int64_t kb);
+
 void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb) {
     b200gp_ctx* ctx = s->ctx;
     const int64_t np = s->np, ld = s->ld;
     double* M = s->mat;
+    if (ctx->panel_overlap == 2 && kb > TILE) {
+        dense_panel_factor_lookahead(s, k0, kb);
+        return;
+    }
     // Option "panel_overlap": potf2 runs on ONE SM (a 128 x 128 Cholesky + inverse is a serial chain) while it only
     // needs the diagonal tile of the column-block update.  So that update is split: the diagonal tile then potf2 stay
     // on the main stream, the rows below go to a side stream and are joined before the triangular solve that needs both.
-    const bool overlap = ctx->panel_overlap != 0;
+    const bool overlap = ctx->panel_overlap == 1;
     cudaStream_t main_stream = ctx->stream;
     cudaEvent_t e_main = nullptr, e_side = nullptr;
     if (overlap) {
@@ -733,6 +739,50 @@ void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb) {
         ctx->event_pool.push_back(e_main);
         ctx->event_pool.push_back(e_side);
     }
+}
+
+// Look-ahead form of the panel factorisation (option "panel_overlap" = 2): the kb x kb DIAGONAL BLOCK is factored on the
+// main stream -- a chain of small kernels whose length is set by the serial 128 x 128 potf2 steps (~158 us each by ncu) --
+// while the rows BELOW the block are updated / solved on a side stream, column by column, as soon as the potf2 of that
+// column has produced inv(L_jj).  The wide GEMMs no longer wait for the next potf2 and vice versa; per panel the time
+// becomes ~max(potf2 chain, wide GEMMs) instead of their sum.  Same tiles, same arithmetic: bit-identical results.
+static void dense_panel_factor_lookahead(b200gp_dense* s, int64_t k0, int64_t kb) {
+    b200gp_ctx* ctx = s->ctx;
+    const int64_t np = s->np, ld = s->ld;
+    double* M = s->mat;
+    const int64_t bend = k0 + kb;
+    const int own = (np > bend) ? (int)((np - bend) / TILE) : 0;
+    cudaStream_t main_stream = ctx->stream;
+    if (!ctx->stream3) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+    cudaStream_t side = ctx->stream3;
+    cudaEvent_t ev = ctx->get_event();
+    struct Restore { b200gp_ctx* c; cudaStream_t st; ~Restore() { c->stream = st; } } restore{ctx, main_stream};
+    if (own) {   // the side stream must see the block column as the caller left it (int8 update, diagonal correction)
+        CUDA_CHECK(cudaEventRecord(ev, main_stream));
+        CUDA_CHECK(cudaStreamWaitEvent(side, ev, 0));
+    }
+    for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
+        const int64_t c0 = k0 + j0;
+        const int blk = (int)((bend - c0) / TILE);
+        const double* li = s->linv + (c0 / TILE) * TILE * TILE;
+        ctx->stream = main_stream;
+        if (j0 > 0) gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld, blk, 1, (int)j0, -1.0, 1, 0);
+        potf2(ctx, M + c0 * ld + c0, ld, s->linv + (c0 / TILE) * TILE * TILE, s->info_dev, (int)c0);
+        if (own) CUDA_CHECK(cudaEventRecord(ev, main_stream));      // L[c0 rows, k0..c0) and inv(L_jj) are final here
+        if (blk > 1) gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld, li, TILE, blk - 1, 1, TILE, 1.0, 0, 0);
+        if (own) {
+            CUDA_CHECK(cudaStreamWaitEvent(side, ev, 0));
+            ctx->stream = side;
+            if (j0 > 0) gemm_nt(ctx, M + bend * ld + c0, ld, M + bend * ld + k0, ld, M + c0 * ld + k0, ld, own, 1, (int)j0, -1.0, 1, 0);
+            gemm_nt(ctx, M + bend * ld + c0, ld, M + bend * ld + c0, ld, li, TILE, own, 1, TILE, 1.0, 0, 0);
+        }
+    }
+    ctx->stream = main_stream;
+    if (own) {
+        CUDA_CHECK(cudaEventRecord(ev, side));
+        CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev, 0));
+    }
+    ctx->event_pool.push_back(ev);
 }
 
 // Row-restricted panel factorisation for the sharded path: the diagonal block [k0, k0+kb) is factored (every rank does

@@ -197,7 +197,7 @@ static void validate_option(const char* key, int64_t value) {
     } else if (!strcmp(key, "qs_tree") || !strcmp(key, "ozaki_layout")) {
         if (value != 0 && value != 1) throw GpError(std::string("option ") + key + " must be 0 or 1");
     } else if (!strcmp(key, "qs_chunk")) {
-        if (value < 4 || value > 4096) throw GpError("option qs_chunk must be in [4, 4096]");
+        if (value != 0 && (value < 4 || value > 4096)) throw GpError("option qs_chunk must be 0 (auto) or in [4, 4096]");
     } else if (!strcmp(key, "ozaki_slices")) {
         if (value < 0 || value > 8) throw GpError("option ozaki_slices must be in [0, 8]");
     }

@@ -63,15 +63,13 @@ static void qsf_run(b200gp_qs* s, const double* t, const double* diag, int* info
             s->model, fc, t, diag, n, fstart.f64(), nch, s->c, s->w, part.f64(), info_dev, x_fuse, fuse ? acomp.f64() : nullptr,
             fuse ? quad.f64() : nullptr);
     ctx->launches++;
-    sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part.f64(), nch, logdet_dev);
-    ctx->launches++;
+    sum_partials(ctx, part.f64(), nch, logdet_dev);
     if (fuse) {
         Scratch gstart(ctx, (size_t)J * nch * 8);
         run_tree<Affine<J>>(ctx, acomp.f64(), nch, gstart.f64());
         qsf_finish_kernel<J><<<nblk(nch, 256), 256, 0, ctx->stream>>>(quad.f64(), gstart.f64(), nch, part.f64());
         ctx->launches++;
-        sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part.f64(), nch, sumsq_dev);
-        ctx->launches++;
+        sum_partials(ctx, part.f64(), nch, sumsq_dev);
     }
     CUDA_CHECK(cudaGetLastError());
 }
@@ -90,8 +88,7 @@ static void qsf_solvesq_run(b200gp_qs* s, const double* x, double* sumsq_dev) {
     run_tree<Affine<J>>(ctx, acomp.f64(), nch, gstart.f64());
     qsf_finish_kernel<J><<<nblk(nch, 256), 256, 0, ctx->stream>>>(quad.f64(), gstart.f64(), nch, part.f64());
     ctx->launches++;
-    sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part.f64(), nch, sumsq_dev);
-    ctx->launches++;
+    sum_partials(ctx, part.f64(), nch, sumsq_dev);
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -98,6 +98,34 @@ static __global__ void sum_partials_kernel(const double* part, int64_t n, double
 }
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// fixed-shape (deterministic) sum of n per-chunk partials: one block per slab of 8192 values, then one block over the
+// slab sums -- the single-block version took 18 us for the 156250 chunks of an N = 1e7 series (ncu launch list, round 2)
+static __global__ void sum_slabs_kernel(const double* part, int64_t n, double* slab_sums) {
+    __shared__ double sh[256];
+    const int64_t lo = (int64_t)blockIdx.x * 8192, hi = (lo + 8192 < n) ? lo + 8192 : n;
+    double acc = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) acc += part[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) slab_sums[blockIdx.x] = sh[0];
+}
+static void sum_partials(b200gp_ctx* ctx, const double* part, int64_t n, double* out) {
+    if (n <= 16384) {
+        sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part, n, out);
+        ctx->launches++;
+        return;
+    }
+    const int64_t nslab = (n + 8191) / 8192;
+    Scratch slabs(ctx, (size_t)nslab * 8);
+    sum_slabs_kernel<<<(unsigned)nslab, 256, 0, ctx->stream>>>(part, n, slabs.f64());
+    sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(slabs.f64(), nslab, out);
+    ctx->launches += 2;
+}
+
 // ---------------------------------------------------------------------------------------------
 // warp-shuffle scan over the chunk composites (option "qs_tree" = 1): the alternative to the thread-sequential
 // fan-in-16 tree above.  One warp scans 32 consecutive composites with a Hillis-Steele inclusive scan

@@ -180,8 +180,7 @@ static void qs_factor_J(b200gp_qs* s, int* info_dev, double* logdet_dev, const d
                                                                                  s->c, s->w, part, info_dev, x_fuse,
                                                                                  s->fused_comp);
     ctx->launches++;
-    sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part, nch, logdet_dev);
-    ctx->launches++;
+    sum_partials(ctx, part, nch, logdet_dev);
     CUDA_CHECK(cudaGetLastError());
     ctx->release(comp, cb);
     ctx->release(fstart, sb);
@@ -206,8 +205,7 @@ static void qs_affine_J(b200gp_qs* s, const double* x, double* out, double* sums
                                                                                        gstart, nch, out, part);
     ctx->launches++;
     if (sumsq_dev) {
-        sum_partials_kernel<<<1, 1024, 0, ctx->stream>>>(part, nch, sumsq_dev);
-        ctx->launches++;
+        sum_partials(ctx, part, nch, sumsq_dev);
         ctx->release(part, (size_t)nch * 8);
     }
     CUDA_CHECK(cudaGetLastError());
@@ -296,6 +294,19 @@ static b200gp_qs* qs_create_impl(b200gp_ctx* ctx, const double* comps, int ncomp
     s->J = model.J;
     s->model = model;
     s->model.chunk = (int)ctx->qs_chunk;
+    if (ctx->qs_chunk == 0) {
+        // auto: the scan kernels are chains of dependent fp64 work per thread, so a launch costs (number of waves) x (chunk
+        // length); pick the multiple of 4 in [48, 128] that minimises it for 3 resident 128-thread blocks per SM
+        const int64_t per_wave = 3 * (int64_t)ctx->num_sms;
+        int best = 64;
+        int64_t best_cost = INT64_MAX;
+        for (int c = 48; c <= 128; c += 4) {
+            const int64_t nblocks = ((n + c - 1) / c + QS_THREADS - 1) / QS_THREADS;
+            const int64_t cost = ((nblocks + per_wave - 1) / per_wave) * c;
+            if (cost < best_cost) { best_cost = cost; best = c; }
+        }
+        s->model.chunk = best;
+    }
     try {
         const size_t nb = (size_t)n * 8;
         if (borrow_device_inputs && qs_is_device_ptr(t) && qs_is_device_ptr(diag)) {
@@ -579,7 +590,7 @@ int b200gp_qs_kernel_matmul(b200gp_ctx* ctx, const double* comps, int ncomp, con
     s.ctx = _ctx;
     s.n = n;
     s.model = build_model(comps, ncomp);
-    s.model.chunk = _ctx->qs_chunk;
+    s.model.chunk = _ctx->qs_chunk ? (int)_ctx->qs_chunk : 64;
     s.J = s.model.J;
     const size_t nb8 = (size_t)n * 8, mb8 = (size_t)m * 8, sb = (size_t)n * s.J * 8;
     Scratch t2_buf(_ctx, nb8), t1_buf(_ctx, mb8), yh_buf(_ctx, nb8 * nrhs), x_buf(_ctx, nb8), F_buf(_ctx, sb), G_buf(_ctx, sb),

@@ -81,6 +81,7 @@ struct b200gp_ctx {
     int64_t build_ahead = 0;    // 1: generate block column J+1 on a side stream under the int8 update of column J
     int64_t panel_overlap = 0;  // 1: inside a panel, update the rows below the diagonal tile on a side stream while potf2 runs
     cudaStream_t stream3 = nullptr;
+    cudaStream_t stream_hi = nullptr;   // high-priority stream of the look-ahead panel chain (panel_overlap = 2)
     int64_t oz_prefetch = 0;    // L2 prefetch distance (K-chunks of 128) of the int8 update's TMA producer
     int64_t oz_pairing = 1;    // int8 update: 1 = accumulate two digit groups at once (default: 16 instead of 28 operand-stage loads
                                // per K chunk at 7 planes), 0 = one group per pass, 2 = diagnostic (paired loop order, single groups)

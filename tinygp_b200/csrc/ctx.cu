@@ -154,6 +154,7 @@ int b200gp_destroy(b200gp_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+    if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

@@ -502,6 +502,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel_v2(double* A
         if (owner) {
             const int r = tid;
             int firstbad = -1;
+            double invd[8];     // 1 / L_cc: the column is scaled by the reciprocal (as LAPACK's dpotf2 does with DSCAL), which
+                                // takes the 36 fp64 divisions per 8 x 8 block out of the serial chain (ncu: 158 us per call)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 double v = D[c][c];
@@ -509,13 +511,15 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel_v2(double* A
                 for (int k = 0; k < c; ++k) v -= D[c][k] * D[c][k];
                 if (!(v > 0.0) && firstbad < 0) firstbad = c;
                 const double sq = sqrt(v);
+                const double isq = 1.0 / sq;
                 D[c][c] = sq;
+                invd[c] = isq;
 #pragma unroll
                 for (int a = c + 1; a < 8; ++a) {
                     double w = D[a][c];
 #pragma unroll
                     for (int k = 0; k < c; ++k) w -= D[a][k] * D[c][k];
-                    D[a][c] = w / sq;
+                    D[a][c] = w * isq;
                 }
             }
             if (r == j0 && firstbad >= 0) atomicMin(info, global_off + j0 + firstbad + 1);
@@ -535,7 +539,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel_v2(double* A
                     double w = arow[c];
 #pragma unroll
                     for (int k = 0; k < c; ++k) w -= x[k] * D[c][k];
-                    x[c] = w / D[c][c];
+                    x[c] = w * invd[c];
                 }
 #pragma unroll
                 for (int c = 0; c < 8; ++c) S[r * PF_LD + j0 + c] = x[c];
@@ -610,16 +614,18 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_trtri_kernel_v2(double* A
         __syncthreads();
         if (part == 0 && i >= j0) {
             // inverse of the 8x8 lower diagonal block (rows j0..j0+7 of T), in registers
-            double Di[8][8];
+            double Di[8][8], rd[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) rd[c] = 1.0 / T[(j0 + c) * 8 + c];     // 8 independent reciprocals, then only FMAs
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                Di[c][c] = 1.0 / T[(j0 + c) * 8 + c];
+                Di[c][c] = rd[c];
 #pragma unroll
                 for (int a = c + 1; a < 8; ++a) {
                     double w = 0.0;
 #pragma unroll
                     for (int k = c; k < a; ++k) w += T[(j0 + a) * 8 + k] * Di[k][c];
-                    Di[a][c] = -w / T[(j0 + a) * 8 + a];
+                    Di[a][c] = -w * rd[a];
                 }
             }
             if (i < j0 + 8) {
@@ -752,36 +758,39 @@ static void dense_panel_factor_lookahead(b200gp_dense* s, int64_t k0, int64_t kb
     double* M = s->mat;
     const int64_t bend = k0 + kb;
     const int own = (np > bend) ? (int)((np - bend) / TILE) : 0;
-    cudaStream_t main_stream = ctx->stream;
-    if (!ctx->stream3) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
-    cudaStream_t side = ctx->stream3;
-    cudaEvent_t ev = ctx->get_event();
-    struct Restore { b200gp_ctx* c; cudaStream_t st; ~Restore() { c->stream = st; } } restore{ctx, main_stream};
-    if (own) {   // the side stream must see the block column as the caller left it (int8 update, diagonal correction)
-        CUDA_CHECK(cudaEventRecord(ev, main_stream));
-        CUDA_CHECK(cudaStreamWaitEvent(side, ev, 0));
+    cudaStream_t wide = ctx->stream;            // the caller's stream keeps the wide GEMMs (and the ProfTimer events)
+    // The chain of small kernels runs on a HIGH-PRIORITY stream: when an SM frees up, the block scheduler then places the
+    // chain's CTA before the pending CTAs of the wide GEMM grid.  (First attempt, chain on the default-priority stream and
+    // GEMMs on a side stream: no overlap at all -- the potf2 CTA queued behind every pending GEMM CTA: panel 212 vs 218 ms.)
+    if (!ctx->stream_hi) {
+        int lo = 0, hi = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi));
     }
+    cudaStream_t chain = ctx->stream_hi;
+    cudaEvent_t ev = ctx->get_event();
+    struct Restore { b200gp_ctx* c; cudaStream_t st; ~Restore() { c->stream = st; } } restore{ctx, wide};
+    CUDA_CHECK(cudaEventRecord(ev, wide));      // the chain must see the block column as the caller left it
+    CUDA_CHECK(cudaStreamWaitEvent(chain, ev, 0));
     for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
         const int64_t c0 = k0 + j0;
         const int blk = (int)((bend - c0) / TILE);
         const double* li = s->linv + (c0 / TILE) * TILE * TILE;
-        ctx->stream = main_stream;
+        ctx->stream = chain;
         if (j0 > 0) gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld, blk, 1, (int)j0, -1.0, 1, 0);
         potf2(ctx, M + c0 * ld + c0, ld, s->linv + (c0 / TILE) * TILE * TILE, s->info_dev, (int)c0);
-        if (own) CUDA_CHECK(cudaEventRecord(ev, main_stream));      // L[c0 rows, k0..c0) and inv(L_jj) are final here
+        if (own) CUDA_CHECK(cudaEventRecord(ev, chain));            // L[c0 rows, k0..c0) and inv(L_jj) are final here
         if (blk > 1) gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld, li, TILE, blk - 1, 1, TILE, 1.0, 0, 0);
         if (own) {
-            CUDA_CHECK(cudaStreamWaitEvent(side, ev, 0));
-            ctx->stream = side;
+            CUDA_CHECK(cudaStreamWaitEvent(wide, ev, 0));
+            ctx->stream = wide;
             if (j0 > 0) gemm_nt(ctx, M + bend * ld + c0, ld, M + bend * ld + k0, ld, M + c0 * ld + k0, ld, own, 1, (int)j0, -1.0, 1, 0);
             gemm_nt(ctx, M + bend * ld + c0, ld, M + bend * ld + c0, ld, li, TILE, own, 1, TILE, 1.0, 0, 0);
         }
     }
-    ctx->stream = main_stream;
-    if (own) {
-        CUDA_CHECK(cudaEventRecord(ev, side));
-        CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev, 0));
-    }
+    ctx->stream = wide;
+    CUDA_CHECK(cudaEventRecord(ev, chain));     // join: the last block-row solve
+    CUDA_CHECK(cudaStreamWaitEvent(wide, ev, 0));
     ctx->event_pool.push_back(ev);
 }
 

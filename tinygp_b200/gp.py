@@ -27,6 +27,7 @@ class GaussianProcess:
             raise ValueError("coordinates must be an array of shape (N,) or (N, D); pytree coordinates (gp.py:40-44) "
                              "are unsupported by the B200 solver backend")
         self.X = X
+        self._zero_mean = mean is None and mean_value is None      # default Mean(0.0): y - loc == y (skips an N-vector pass)
         if isinstance(mean, means.MeanBase):  # gp.py:81-86
             self.mean_function = mean
         elif mean is None:
@@ -65,7 +66,8 @@ class GaussianProcess:
         hook = getattr(self.solver, "whitened_sumsq", None)
         if hook is not None:     # same value as below with |alpha|^2 reduced on the device (no N-vector round trip)
             with np.errstate(all="ignore"):
-                loglike = -0.5 * hook(np.asarray(y, dtype=np.float64) - self.loc) - self.solver.normalization()
+                yv = np.asarray(y, dtype=np.float64)
+                loglike = -0.5 * hook(yv if self._zero_mean else yv - self.loc) - self.solver.normalization()
             return loglike if np.isfinite(loglike) else -np.inf
         return self._compute_log_prob(self._get_alpha(y))
 

@@ -685,7 +685,7 @@ static void potf2(b200gp_ctx* ctx, double* A, int64_t lda, double* linv, int* in
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
 
 // factor the panel of columns [k0, k0+kb) over all rows >= k0: inner 128-wide left-looking sweep
-static void dense_panel_factor_lookahead(b200gp_dense* s, int64_t k0, int64_t kb);
+static void dense_panel_factor_lookahead(b200gp_dense* s, int64_t k0, int64_t kb, int64_t lo = -1, int64_t hi = -1);
 
 void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb) {
     b200gp_ctx* ctx = s->ctx;
@@ -752,12 +752,14 @@ void dense_panel_factor(b200gp_dense* s, int64_t k0, int64_t kb) {
 // while the rows BELOW the block are updated / solved on a side stream, column by column, as soon as the potf2 of that
 // column has produced inv(L_jj).  The wide GEMMs no longer wait for the next potf2 and vice versa; per panel the time
 // becomes ~max(potf2 chain, wide GEMMs) instead of their sum.  Same tiles, same arithmetic: bit-identical results.
-static void dense_panel_factor_lookahead(b200gp_dense* s, int64_t k0, int64_t kb) {
+// [lo, hi): the rows below the block this call is responsible for (default: all of them; the sharded path passes its chunk)
+static void dense_panel_factor_lookahead(b200gp_dense* s, int64_t k0, int64_t kb, int64_t lo, int64_t hi) {
     b200gp_ctx* ctx = s->ctx;
     const int64_t np = s->np, ld = s->ld;
     double* M = s->mat;
     const int64_t bend = k0 + kb;
-    const int own = (np > bend) ? (int)((np - bend) / TILE) : 0;
+    if (lo < 0) { lo = bend; hi = np; }
+    const int own = (hi > lo) ? (int)((hi - lo) / TILE) : 0;
     cudaStream_t wide = ctx->stream;            // the caller's stream keeps the wide GEMMs (and the ProfTimer events)
     // The chain of small kernels runs on a HIGH-PRIORITY stream: when an SM frees up, the block scheduler then places the
     // chain's CTA before the pending CTAs of the wide GEMM grid.  (First attempt, chain on the default-priority stream and
@@ -784,8 +786,8 @@ static void dense_panel_factor_lookahead(b200gp_dense* s, int64_t k0, int64_t kb
         if (own) {
             CUDA_CHECK(cudaStreamWaitEvent(wide, ev, 0));
             ctx->stream = wide;
-            if (j0 > 0) gemm_nt(ctx, M + bend * ld + c0, ld, M + bend * ld + k0, ld, M + c0 * ld + k0, ld, own, 1, (int)j0, -1.0, 1, 0);
-            gemm_nt(ctx, M + bend * ld + c0, ld, M + bend * ld + c0, ld, li, TILE, own, 1, TILE, 1.0, 0, 0);
+            if (j0 > 0) gemm_nt(ctx, M + lo * ld + c0, ld, M + lo * ld + k0, ld, M + c0 * ld + k0, ld, own, 1, (int)j0, -1.0, 1, 0);
+            gemm_nt(ctx, M + lo * ld + c0, ld, M + lo * ld + c0, ld, li, TILE, own, 1, TILE, 1.0, 0, 0);
         }
     }
     ctx->stream = wide;
@@ -804,6 +806,10 @@ void dense_panel_factor_rows(b200gp_dense* s, int64_t k0, int64_t kb, int64_t r0
     const int64_t bend = k0 + kb;
     int64_t lo = (r0 > bend) ? r0 : bend, hi = (r1 < np) ? r1 : np;
     if (lo % TILE || hi % TILE) throw GpError("panel_factor_rows: row range must be 128-aligned");
+    if (ctx->panel_overlap == 2 && kb > TILE) {
+        dense_panel_factor_lookahead(s, k0, kb, lo, (hi > lo) ? hi : lo);
+        return;
+    }
     const int own = (hi > lo) ? (int)((hi - lo) / TILE) : 0;
     for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
         const int64_t c0 = k0 + j0;

@@ -128,7 +128,7 @@ def log_probability_sharded(kernel, X, diag, resid, *, slices: int = 8, streamin
                 dist.all_gather_into_tensor(out, colbuf[i0:i1])
                 if stats is not None:
                     stats["bytes"] = stats.get("bytes", 0) + int(out.numel() * 8)
-                    stats["exchange"] = "in-place dist.all_gather_into_tensor (NCCL) on the contiguous block column, one per block column"
+                    stats.setdefault("exchange", "in-place dist.all_gather_into_tensor (NCCL) on the contiguous block column, one per block column")
             elif world > 1:
                 mine = mine_buf[: ch * nb]
                 full = full_buf[: world * ch * nb]

@@ -147,7 +147,9 @@ def oracle_dense_logp_seconds(n):
         lp = -0.5 * np.sum(alpha ** 2) - (np.sum(np.log(np.diag(L))) + 0.5 * n * np.log(2 * np.pi))   # gp.py:313-316
         t2 = time.perf_counter()
         try:
-            _USED_THREADS[0] = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+            # the LAPACK / BLAS pool that actually ran dpotrf (not torch's OpenMP pool, which bench.py's own arm also loads)
+            blas = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+            _USED_THREADS[0] = max(blas or [p.get("num_threads", 1) for p in threadpool_info()] or [1])
         except Exception:
             pass
     finally:
@@ -473,7 +475,10 @@ def measure_quasisep(args, ctx, local_rank, n=10_000_000, steps=None, warmup=3, 
     l0 = ctx.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    reps = max(steps, 40)                     # a step is ~1 ms: take enough of them for nvidia-smi to sample the clocks
+    ms_cal, _ = timed(step_device, 10)
+    reps = max(steps, int(2000.0 / max(ms_cal / 10.0, 1e-3)))   # a step is ~1 ms: ~2 s of them so that nvidia-smi samples the clocks
+    ctx.profile(reset=True)
+    l0 = ctx.launch_count()
     ms, logp = timed(step_device, reps)
     clocks = sampler.stop()
     prof = ctx.profile(reset=True)

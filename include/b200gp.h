@@ -208,7 +208,9 @@ int b200gp_mg_finish(b200gp_mg* m, double* logp);
 /* ---- solvers.QuasisepSolver  (solvers/quasisep/solver.py:19-139) ------------------------- */
 /* Quasiseparable kernels (kernels/quasisep.py) are lowered to a list of `ncomp` components
  * (a Sum is block-diagonal, quasisep.py:241-295), each B200GP_QS_STRIDE doubles:
- * {kind, sigma_scale, p0, p1, p2, p3, 0, 0}.  sigma_scale multiplies Pinf (Scale, :334-340). */
+ * {kind, sigma_scale, p0, p1, p2, p3, mul_next, 0}.  sigma_scale multiplies Pinf (Scale, :334-340).  mul_next = 1
+ * chains the component with the next one into a Product term (quasisep.py:298-331: Kronecker-structured state, the
+ * first factor's index fastest as in _prod_helper :676-687; up to 3 factors, term size <= 6). */
 #define B200GP_QS_STRIDE 8
 #define B200GP_QS_MAX_COMP 8
 #define B200GP_QS_MAX_J 8

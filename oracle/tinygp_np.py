@@ -417,10 +417,13 @@ class qs:
 
         def __mul__(self, other):
             if isinstance(other, qs.Quasisep):
-                raise NotImplementedError("Product of quasisep kernels is out of scope")
+                return qs.Product(self, other)             # kernels/quasisep.py:181-190
             return qs.Scale(self, other)
 
-        __rmul__ = __mul__
+        def __rmul__(self, other):
+            if isinstance(other, qs.Quasisep):
+                return qs.Product(other, self)
+            return qs.Scale(self, other)
 
         def to_symm_qsm(self, X):
             """kernels/quasisep.py:102-116 -> (d, p, q, a)"""
@@ -478,6 +481,35 @@ class qs:
 
         def transition_matrix(self, X1, X2):
             return sla.block_diag(self.kernel1.transition_matrix(X1, X2), self.kernel2.transition_matrix(X1, X2))
+
+    class Product(Quasisep):
+        """kernels/quasisep.py:298-331 with `_prod_helper` (:676-687): Kronecker-structured state, the FIRST kernel's state
+        index running fastest (np.meshgrid's default "xy" indexing)."""
+
+        def __init__(self, kernel1, kernel2):
+            self.kernel1, self.kernel2 = kernel1, kernel2
+
+        @staticmethod
+        def _prod_helper(a1, a2):
+            a1, a2 = np.asarray(a1, dtype=np.float64), np.asarray(a2, dtype=np.float64)
+            i, j = np.meshgrid(np.arange(a1.shape[0]), np.arange(a2.shape[0]))
+            i, j = i.flatten(), j.flatten()
+            if a1.ndim == 1:
+                return a1[i] * a2[j]
+            return a1[i[:, None], i[None, :]] * a2[j[:, None], j[None, :]]
+
+        def design_matrix(self):
+            F1, F2 = self.kernel1.design_matrix(), self.kernel2.design_matrix()
+            return self._prod_helper(F1, np.eye(F2.shape[0])) + self._prod_helper(np.eye(F1.shape[0]), F2)
+
+        def stationary_covariance(self):
+            return self._prod_helper(self.kernel1.stationary_covariance(), self.kernel2.stationary_covariance())
+
+        def observation_model(self, X):
+            return self._prod_helper(self.kernel1.observation_model(X), self.kernel2.observation_model(X))
+
+        def transition_matrix(self, X1, X2):
+            return self._prod_helper(self.kernel1.transition_matrix(X1, X2), self.kernel2.transition_matrix(X1, X2))
 
     class Scale(Quasisep):
         """kernels/quasisep.py:334-340"""

@@ -119,15 +119,18 @@ def chol_or_nan(K):
 
 # ---- quasiseparable components -> oracle kernels (tinygp_b200/kernels/quasisep.py components()) --------------
 def qs_kernel(comps):
-    total = None
-    for kind, scale, p0, p1, p2, p3 in comps[:, :6]:
+    total, term = None, None
+    for kind, scale, p0, p1, p2, p3, mul_next in comps[:, :7]:
         kind = int(kind)
         k = {QS_EXP: lambda: o.qs.Exp(p0, p1), QS_MATERN32: lambda: o.qs.Matern32(p0, p1),
              QS_MATERN52: lambda: o.qs.Matern52(p0, p1), QS_SHO: lambda: o.qs.SHO(p0, p1, p2),
              QS_CELERITE: lambda: o.qs.Celerite(p0, p1, p2, p3), QS_COSINE: lambda: o.qs.Cosine(p0, p1)}[kind]()
         if scale != 1.0:
             k = o.qs.Scale(k, scale)
-        total = k if total is None else total + k
+        term = k if term is None else o.qs.Product(term, k)     # mul_next chains a Product term (quasisep.py:298-331)
+        if not mul_next:
+            total = term if total is None else total + term
+            term = None
     return total
 
 

@@ -76,8 +76,12 @@ def test_quasisep_components():
     assert k.state_dim() == 4
     with pytest.raises(ValueError):
         Q.Matern32(1.0) + kernels.Exp(1.0)
+    # Product (quasisep.py:298-331): one term of chained rows, scaled once; state dimension = product of the factors'
+    kp = 0.5 * (Q.Matern32(1.0) * Q.Exp(2.0)) + Q.Exp(3.0)
+    cp = kp.component_array()
+    assert cp[:, 6].tolist() == [1.0, 0.0, 0.0] and cp[:, 1].tolist() == [0.5, 1.0, 1.0] and kp.state_dim() == 3
     with pytest.raises(NotImplementedError):
-        (Q.Matern32(1.0) * Q.Exp(1.0)).components()
+        ((Q.Matern32(1.0) + Q.Exp(1.0)) * Q.Exp(1.0)).components()
 
 
 QS_PAIRS = [
@@ -89,6 +93,7 @@ QS_PAIRS = [
     (lambda: Q.Exp(1.3, 0.8), lambda o: o.qs.Exp(1.3, 0.8)),
     (lambda: Q.Cosine(1.3, 0.8), lambda o: o.qs.Cosine(1.3, 0.8)),
     (lambda: Q.Celerite(1.1, 0.8, 0.9, 0.1), lambda o: o.qs.Celerite(1.1, 0.8, 0.9, 0.1)),
+    (lambda: Q.SHO(1.5, 3.0, 1.8) * Q.Matern32(1.5, 0.9), lambda o: o.qs.SHO(1.5, 3.0, 1.8) * o.qs.Matern32(1.5, 0.9)),
 ]
 
 

@@ -287,6 +287,7 @@ QS_KERNELS = [
     lambda: 1.5 * quasisep.Matern52(1.5) + 0.3 * quasisep.Exp(1.5),
     lambda: quasisep.Cosine(sigma=1.8, scale=1.5),
     lambda: 1.8 * quasisep.Cosine(1.5),
+    lambda: quasisep.Matern52(1.5) * quasisep.SHO(omega=1.5, quality=0.1),      # test_quasisep.py's Product entry
 ]
 
 
@@ -305,9 +306,12 @@ def test_quasisep_kernels(which):                                    # test_quas
     assert_allclose(kernel.matmul(t, x, y), kernel(t, x) @ y)
 
 
-def test_quasisep_product_and_carma_are_refused():                   # the two kernels of the list the backend lacks
+def test_quasisep_carma_and_products_of_sums_are_refused():           # what the backend still lacks, refused loudly
     with pytest.raises(NotImplementedError, match="unsupported by the B200"):
-        QuasisepSolver(quasisep.Matern52(1.5) * quasisep.SHO(omega=1.5, quality=0.1), np.linspace(0, 1, 5),
+        QuasisepSolver((quasisep.Matern52(1.5) + quasisep.Exp(0.7)) * quasisep.SHO(omega=1.5, quality=0.1),
+                       np.linspace(0, 1, 5), noise.Diagonal(np.full(5, 0.1)))
+    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
+        QuasisepSolver(quasisep.Matern52(1.5) * quasisep.Matern52(0.5), np.linspace(0, 1, 5),      # 3 x 3 = 9 states
                        noise.Diagonal(np.full(5, 0.1)))
     with pytest.raises(NotImplementedError, match="unsupported by the B200"):
         quasisep.CARMA(alpha=np.array([1.4, 2.3, 1.5]), beta=np.array([0.1, 0.5]))

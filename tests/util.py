@@ -28,6 +28,8 @@ def to_oracle(k):
         return cls(k.scale, dist)
     if isinstance(k, Q.Sum):
         return o.qs.Sum(to_oracle(k.kernel1), to_oracle(k.kernel2))
+    if isinstance(k, Q.Product):
+        return o.qs.Product(to_oracle(k.kernel1), to_oracle(k.kernel2))
     if isinstance(k, Q.Scale):
         return o.qs.Scale(to_oracle(k.kernel), k.scale)
     if isinstance(k, Q.Celerite):

@@ -9,10 +9,12 @@
 #define QS_THREADS 128
 
 struct QsModel {
-    int ncomp, J;
+    int ncomp, J;   // ncomp = number of LEAVES; a term is a product of 1..3 consecutive leaves (kernels/quasisep.py:298-331)
     int chunk;   // points per thread (runtime tunable, option "qs_chunk")
+    int nterm;
+    int tfirst[B200GP_QS_MAX_COMP], tn[B200GP_QS_MAX_COMP], toff[B200GP_QS_MAX_COMP], tsize[B200GP_QS_MAX_COMP];
     int kind[B200GP_QS_MAX_COMP];
-    int off[B200GP_QS_MAX_COMP];
+    int off[B200GP_QS_MAX_COMP];   // state offset of leaf i when every term is a single leaf (the layout-specialised path)
     int mode[B200GP_QS_MAX_COMP];  // SHO: 0 critical, 1 underdamped, 2 overdamped
     double c0[B200GP_QS_MAX_COMP], c1[B200GP_QS_MAX_COMP], c2[B200GP_QS_MAX_COMP];
     double h[B200GP_QS_MAX_J];  // observation model (constant for all supported kernels)
@@ -29,10 +31,15 @@ static inline QsModel build_model(const double* comps, int ncomp) {
     m.ncomp = ncomp;
     int J = 0;
     double Pinf[B200GP_QS_MAX_J][B200GP_QS_MAX_J] = {};
+    // per-leaf constants, observation model and stationary covariance
+    double lP[B200GP_QS_MAX_COMP][3][3] = {}, lh[B200GP_QS_MAX_COMP][3] = {}, lps[B200GP_QS_MAX_COMP] = {};
+    int lsz[B200GP_QS_MAX_COMP] = {}, lmul[B200GP_QS_MAX_COMP] = {};
     for (int i = 0; i < ncomp; ++i) {
         const double* cc = comps + (size_t)i * B200GP_QS_STRIDE;
         const int kind = (int)cc[0];
         const double ps = cc[1], p0 = cc[2], p1 = cc[3], p2 = cc[4], p3 = cc[5];
+        lmul[i] = (cc[6] != 0.0) ? 1 : 0;
+        lps[i] = ps;
         int sz;
         switch (kind) {
             case B200GP_QS_EXP: sz = 1; break;
@@ -40,11 +47,10 @@ static inline QsModel build_model(const double* comps, int ncomp) {
             case B200GP_QS_MATERN32: case B200GP_QS_SHO: case B200GP_QS_CELERITE: case B200GP_QS_COSINE: sz = 2; break;
             default: throw GpError("quasisep: unknown component kind");
         }
-        if (J + sz > B200GP_QS_MAX_J) throw GpError("quasisep: state dimension exceeds 8");
+        lsz[i] = sz;
         m.kind[i] = kind;
-        m.off[i] = J;
-        double P[3][3] = {};
-        double h[3] = {0, 0, 0};
+        double (&P)[3][3] = lP[i];
+        double (&h)[3] = lh[i];
         switch (kind) {
             case B200GP_QS_EXP:  // quasisep.py:491-525
                 m.c0[i] = p0; h[0] = p1; P[0][0] = 1.0; break;
@@ -83,17 +89,47 @@ static inline QsModel build_model(const double* comps, int ncomp) {
             case B200GP_QS_COSINE:  // quasisep.py:636-673
                 m.c0[i] = 2.0 * M_PI / p0; h[0] = p1; P[0][0] = P[1][1] = 1.0; break;
         }
-        for (int r = 0; r < sz; ++r) {
-            m.h[J + r] = h[r];
-            for (int s = 0; s < sz; ++s) Pinf[J + r][J + s] = ps * P[r][s];  // Scale: quasisep.py:334-340
+    }
+    // terms: maximal runs of leaves chained by the mul_next flag; Kronecker structure with the FIRST leaf's index fastest
+    // (kernels/quasisep.py:298-331 and _prod_helper :676-687)
+    int i = 0;
+    while (i < ncomp) {
+        int n = 1;
+        while (lmul[i + n - 1]) {
+            if (i + n >= ncomp) throw GpError("quasisep: a product term runs past the last component");
+            ++n;
         }
-        J += sz;
+        if (n > 3) throw GpError("quasisep: a product of more than 3 state-space kernels is not supported");
+        int size = 1;
+        double ps = 1.0;
+        for (int l = 0; l < n; ++l) { size *= lsz[i + l]; ps *= lps[i + l]; }
+        if (J + size > B200GP_QS_MAX_J) throw GpError("quasisep: state dimension exceeds 8");
+        const int t = m.nterm++;
+        m.tfirst[t] = i; m.tn[t] = n; m.toff[t] = J; m.tsize[t] = size;
+        for (int l = 0; l < n; ++l) m.off[i + l] = J;   // meaningful for single-leaf terms only
+        for (int r = 0; r < size; ++r) {
+            double hv = 1.0;
+            int rr = r;
+            for (int l = 0; l < n; ++l) { hv *= lh[i + l][rr % lsz[i + l]]; rr /= lsz[i + l]; }
+            m.h[J + r] = hv;
+            for (int c = 0; c < size; ++c) {
+                double pv = ps;   // Scale: quasisep.py:334-340
+                int r2 = r, c2 = c;
+                for (int l = 0; l < n; ++l) {
+                    pv *= lP[i + l][r2 % lsz[i + l]][c2 % lsz[i + l]];
+                    r2 /= lsz[i + l]; c2 /= lsz[i + l];
+                }
+                Pinf[J + r][J + c] = pv;
+            }
+        }
+        J += size;
+        i += n;
     }
     m.J = J;
     m.d0 = 0.0;
     for (int j = 0; j < J; ++j) {  // q = h Pinf ; d = sum(hP * h)   (quasisep.py:109-111)
         double s = 0.0;
-        for (int i = 0; i < J; ++i) s += m.h[i] * Pinf[i][j];
+        for (int k = 0; k < J; ++k) s += m.h[k] * Pinf[k][j];
         m.q[j] = s;
     }
     for (int j = 0; j < J; ++j) m.d0 += m.q[j] * m.h[j];
@@ -103,81 +139,98 @@ static inline QsModel build_model(const double* comps, int ncomp) {
 // ---------------------------------------------------------------------------------------------
 // device: per-point generators  a = T(t_{k-1}, t_k)^T,  p = h a      (quasisep.py:102-116)
 // ---------------------------------------------------------------------------------------------
+// transition_matrix(X1, X2) of ONE leaf as written in the reference (T, not its transpose); returns the leaf's size
+__host__ __device__ __forceinline__ int qs_leaf_transition(const QsModel& m, const int ci, const double dt, double (&T)[3][3]) {
+    switch (m.kind[ci]) {
+        case B200GP_QS_EXP:
+            T[0][0] = exp(-dt / m.c0[ci]);
+            return 1;
+        case B200GP_QS_MATERN32: {
+            const double f = m.c0[ci], e = exp(-f * dt);
+            T[0][0] = e * (1.0 + f * dt); T[0][1] = e * (-m.c1[ci] * dt);
+            T[1][0] = e * dt;             T[1][1] = e * (1.0 - f * dt);
+            return 2;
+        }
+        case B200GP_QS_MATERN52: {
+            const double f = m.c0[ci], f2 = m.c1[ci], d2 = dt * dt, e = exp(-f * dt);
+            T[0][0] = e * (0.5 * f2 * d2 + f * dt + 1.0);
+            T[0][1] = e * (-0.5 * f * f2 * d2);
+            T[0][2] = e * (0.5 * f2 * f * dt * (f * dt - 2.0));
+            T[1][0] = e * (dt * (f * dt + 1.0));
+            T[1][1] = e * (-f2 * d2 + f * dt + 1.0);
+            T[1][2] = e * (f2 * dt * (f * dt - 3.0));
+            T[2][0] = e * (0.5 * d2);
+            T[2][1] = e * (0.5 * dt * (2.0 - f * dt));
+            T[2][2] = e * (0.5 * f2 * d2 - 2.0 * f * dt + 1.0);
+            return 3;
+        }
+        case B200GP_QS_SHO: {
+            const double w = m.c0[ci], q = m.c1[ci];
+            if (m.mode[ci] == 0) {
+                const double e = exp(-w * dt);
+                T[0][0] = e * (1.0 + w * dt); T[0][1] = e * (-(w * w) * dt);
+                T[1][0] = e * dt;             T[1][1] = e * (1.0 - w * dt);
+            } else {
+                const double f = m.c2[ci];
+                const double arg = 0.5 * f * w * dt / q;
+                const double e = exp(-0.5 * w * dt / q);
+                double sn, cs;
+                if (m.mode[ci] == 1) {
+                    sincos(arg, &sn, &cs);
+                } else {
+                    sn = sinh(arg);
+                    cs = cosh(arg);
+                }
+                T[0][0] = e * (cs + sn / f);           T[0][1] = e * (-2.0 * q * w * sn / f);
+                T[1][0] = e * (2.0 * q * sn / (w * f)); T[1][1] = e * (cs - sn / f);
+            }
+            return 2;
+        }
+        case B200GP_QS_CELERITE: {
+            double sn, cs;
+            sincos(m.c1[ci] * dt, &sn, &cs);
+            const double e = exp(-m.c0[ci] * dt);
+            // exp(-c dt) * [[cos, -sin], [sin, cos]].T
+            T[0][0] = e * cs; T[0][1] = e * sn;
+            T[1][0] = e * -sn; T[1][1] = e * cs;
+            return 2;
+        }
+        default: {  // COSINE
+            double sn, cs;
+            sincos(m.c0[ci] * dt, &sn, &cs);
+            T[0][0] = cs; T[0][1] = sn;
+            T[1][0] = -sn; T[1][1] = cs;
+            return 2;
+        }
+    }
+}
+
 template <int J>
 __host__ __device__ __forceinline__ void qs_gen(const QsModel& m, const double dt, double (&a)[J][J], double (&p)[J]) {
     double al[J * J];  // scratch with runtime offsets; copied to registers below
 #pragma unroll
     for (int i = 0; i < J * J; ++i) al[i] = 0.0;
-    for (int ci = 0; ci < m.ncomp; ++ci) {
-        const int o = m.off[ci];
-        double T[3][3];  // transition_matrix(X1, X2) as written in the reference
-        int sz = 2;
-        switch (m.kind[ci]) {
-            case B200GP_QS_EXP:
-                sz = 1;
-                T[0][0] = exp(-dt / m.c0[ci]);
-                break;
-            case B200GP_QS_MATERN32: {
-                const double f = m.c0[ci], e = exp(-f * dt);
-                T[0][0] = e * (1.0 + f * dt); T[0][1] = e * (-m.c1[ci] * dt);
-                T[1][0] = e * dt;             T[1][1] = e * (1.0 - f * dt);
-                break;
-            }
-            case B200GP_QS_MATERN52: {
-                sz = 3;
-                const double f = m.c0[ci], f2 = m.c1[ci], d2 = dt * dt, e = exp(-f * dt);
-                T[0][0] = e * (0.5 * f2 * d2 + f * dt + 1.0);
-                T[0][1] = e * (-0.5 * f * f2 * d2);
-                T[0][2] = e * (0.5 * f2 * f * dt * (f * dt - 2.0));
-                T[1][0] = e * (dt * (f * dt + 1.0));
-                T[1][1] = e * (-f2 * d2 + f * dt + 1.0);
-                T[1][2] = e * (f2 * dt * (f * dt - 3.0));
-                T[2][0] = e * (0.5 * d2);
-                T[2][1] = e * (0.5 * dt * (2.0 - f * dt));
-                T[2][2] = e * (0.5 * f2 * d2 - 2.0 * f * dt + 1.0);
-                break;
-            }
-            case B200GP_QS_SHO: {
-                const double w = m.c0[ci], q = m.c1[ci];
-                if (m.mode[ci] == 0) {
-                    const double e = exp(-w * dt);
-                    T[0][0] = e * (1.0 + w * dt); T[0][1] = e * (-(w * w) * dt);
-                    T[1][0] = e * dt;             T[1][1] = e * (1.0 - w * dt);
-                } else {
-                    const double f = m.c2[ci];
-                    const double arg = 0.5 * f * w * dt / q;
-                    const double e = exp(-0.5 * w * dt / q);
-                    double sn, cs;
-                    if (m.mode[ci] == 1) {
-                        sincos(arg, &sn, &cs);
-                    } else {
-                        sn = sinh(arg);
-                        cs = cosh(arg);
-                    }
-                    T[0][0] = e * (cs + sn / f);           T[0][1] = e * (-2.0 * q * w * sn / f);
-                    T[1][0] = e * (2.0 * q * sn / (w * f)); T[1][1] = e * (cs - sn / f);
+    for (int ti = 0; ti < m.nterm; ++ti) {
+        const int o = m.toff[ti], f0 = m.tfirst[ti];
+        double T[3][3];
+        const int sz = qs_leaf_transition(m, f0, dt, T);
+        if (m.tn[ti] == 1) {
+            for (int r = 0; r < sz; ++r)
+                for (int s = 0; s < sz; ++s) al[(o + r) * J + (o + s)] = T[s][r];  // a = T^T
+        } else {
+            // product term: T = kron-structured product of the leaves' transition matrices, first leaf's index fastest
+            double T1[3][3], T2[3][3];
+            const int s1 = qs_leaf_transition(m, f0 + 1, dt, T1);
+            int s2 = 1;
+            T2[0][0] = 1.0;
+            if (m.tn[ti] == 3) s2 = qs_leaf_transition(m, f0 + 2, dt, T2);
+            const int S = sz * s1 * s2;
+            for (int r = 0; r < S; ++r)
+                for (int s = 0; s < S; ++s) {
+                    const double v = T[s % sz][r % sz] * T1[(s / sz) % s1][(r / sz) % s1] * T2[s / (sz * s1)][r / (sz * s1)];
+                    al[(o + r) * J + (o + s)] = v;   // a[r][s] = T_term[s][r]
                 }
-                break;
-            }
-            case B200GP_QS_CELERITE: {
-                double sn, cs;
-                sincos(m.c1[ci] * dt, &sn, &cs);
-                const double e = exp(-m.c0[ci] * dt);
-                // exp(-c dt) * [[cos, -sin], [sin, cos]].T
-                T[0][0] = e * cs; T[0][1] = e * sn;
-                T[1][0] = e * -sn; T[1][1] = e * cs;
-                break;
-            }
-            default: {  // COSINE
-                double sn, cs;
-                sincos(m.c0[ci] * dt, &sn, &cs);
-                T[0][0] = cs; T[0][1] = sn;
-                T[1][0] = -sn; T[1][1] = cs;
-                break;
-            }
         }
-        for (int r = 0; r < sz; ++r)
-            for (int s = 0; s < sz; ++s) al[(o + r) * J + (o + s)] = T[s][r];  // a = T^T
     }
 #pragma unroll
     for (int i = 0; i < J; ++i)

@@ -40,7 +40,7 @@ __host__ __device__ constexpr bool lay_same(int L, int i, int j) { return lay_bl
 // host: layout code of a model, or 0 if a block does not fit the 2-bit encoding (never: sizes are 1..3) / too many blocks
 static inline int qsf_layout_of(const QsModel& m) {
     int L = 0;
-    if (m.ncomp > 8) return 0;
+    if (m.ncomp > 8 || m.nterm != m.ncomp) return 0;   // product terms (Kronecker-structured blocks): generic path only
     for (int i = 0; i < m.ncomp; ++i) {
         const int sz = (m.kind[i] == B200GP_QS_EXP) ? 1 : (m.kind[i] == B200GP_QS_MATERN52 ? 3 : 2);
         L |= sz << (2 * i);

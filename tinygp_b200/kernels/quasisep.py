@@ -28,7 +28,9 @@ class Quasisep(Kernel):
     """Base class (quasisep.py:47-215)."""
 
     def components(self) -> list[tuple]:
-        """[(kind, pinf_scale, p0, p1, p2, p3)] for the device."""
+        """Rows ``(kind, pinf_scale, p0, p1, p2, p3, mul_next)`` for the device.  A row with ``mul_next = 1`` is
+        multiplied (Kronecker-structured state, quasisep.py:298-331) with the row after it; a *term* is a maximal run of
+        such rows, and the model is the sum (block-diagonal state) of its terms."""
         raise NotImplementedError(
             f"{type(self).__name__} is unsupported by the B200 quasiseparable solver backend")
 
@@ -40,7 +42,13 @@ class Quasisep(Kernel):
         return out
 
     def state_dim(self) -> int:
-        return sum(STATE_DIM[int(c[0])] for c in self.components())
+        total, term = 0, 1
+        for c in self.components():
+            term *= STATE_DIM[int(c[0])]
+            if not (len(c) > 6 and c[6]):
+                total += term
+                term = 1
+        return total
 
     def coord_to_sortable(self, X):
         return X
@@ -145,17 +153,41 @@ class Scale(Quasisep):
 
     def components(self):
         s = float(self.scale)
-        return [(c[0], c[1] * s) + tuple(c[2:]) for c in self.kernel.components()]
+        out, term_start = [], True
+        for c in self.kernel.components():      # the stationary covariance of every TERM is scaled once (quasisep.py:339-340)
+            out.append(((c[0], c[1] * s) + tuple(c[2:])) if term_start else tuple(c))
+            term_start = not (len(c) > 6 and c[6])
+        return out
 
     def tau_program(self, dist):
         return self.kernel.tau_program(dist) + [(OP_CONST, 0, float(self.scale), 0.0), (OP_MUL, 0, 0.0, 0.0)]
 
 
 class Product(Quasisep):
-    """quasisep.py:298-331 -- Kronecker-product states: out of scope of the first B200 pass."""
+    """quasisep.py:298-331: the state of the product is Kronecker-structured (``_prod_helper``, :676-687, first kernel's
+    index fastest).  Supported for factors that are single terms (leaves, scaled leaves, products); a Sum inside a Product
+    would interleave the blocks of the reference's state ordering and is refused."""
 
     def __init__(self, kernel1, kernel2):
         self.kernel1, self.kernel2 = kernel1, kernel2
+
+    def components(self):
+        def single_term(rows):
+            return all(len(r) > 6 and r[6] for r in rows[:-1]) and not (len(rows[-1]) > 6 and rows[-1][6])
+        r1, r2 = self.kernel1.components(), self.kernel2.components()
+        if not (single_term(r1) and single_term(r2)):
+            raise NotImplementedError("a Product of quasiseparable Sums is unsupported by the B200 quasiseparable solver "
+                                      "backend (multiply the terms out: (a + b) * c == a * c + b * c)")
+        pad = lambda r: tuple(r) + (0.0,) * (7 - len(r))       # noqa: E731
+        rows = [pad(r) for r in r1] + [pad(r) for r in r2]
+        rows[len(r1) - 1] = rows[len(r1) - 1][:6] + (1.0,)
+        dim = 1
+        for r in rows:
+            dim *= STATE_DIM[int(r[0])]
+        if dim > 6 or len(rows) > 3:
+            raise NotImplementedError("a Product with more than 3 factors or a state dimension above 6 is unsupported by the "
+                                      "B200 quasiseparable solver backend")
+        return rows
 
     def tau_program(self, dist):
         return self.kernel1.tau_program(dist) + self.kernel2.tau_program(dist) + [(OP_MUL, 0, 0.0, 0.0)]

@@ -22,6 +22,8 @@ QS = {
     "cos+exp": lambda: Q.Cosine(2.5) + Q.Exp(0.7, 1.3),
     "j6": lambda: Q.SHO(1.5, 3.0, 1.8) + Q.Matern32(1.5, 0.9) + 0.5 * Q.SHO(0.4, 1.2),
     "exp": lambda: Q.Exp(2.0, 0.8),
+    "prod_sho_m32": lambda: Q.SHO(1.5, 3.0, 1.8) * Q.Matern32(1.5, 0.9),          # quasisep.py:298-331 (J = 4)
+    "prod3_plus_m52": lambda: 0.7 * (Q.Exp(2.0, 1.1) * Q.Celerite(1.1, 0.1, 0.3, 1.5)) + Q.Matern52(2.5, 1.3),   # J = 2 + 3
 }
 
 

@@ -87,3 +87,50 @@ def test_paired_cta_pair_kernel_is_exact(ctx, rows, K, S, pairing):
         for t in range(S - s):
             want -= 2.0 ** -(12 + 7 * (s + t)) * (rs[:, None] * rs[None, :]) * (P[s] @ P[t].T)
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
+
+
+@pytest.mark.parametrize("force", [2, 3, 5])
+@pytest.mark.parametrize("rows,K,S", [(512, 1024, 7), (768, 1920, 7), (1024, 4096, 8), (256, 640, 3)])
+def test_split_k_segments_are_exact(ctx, rows, K, S, force):
+    """CTA-pair kernel with the K range cut into segments inside one launch (segment 0 updates C, the others their own
+    zero-filled scratch tiles, added afterwards in a fixed order): same integer sums, one more fp64 addition per segment"""
+    from tinygp_b200 import _cabi
+    ctx.set_option("ozaki_cluster", 2)
+    ctx.set_option("ozaki_pairing", 1)
+    ctx.set_option("ozaki_splitk_force", force)
+    rng = np.random.default_rng(rows + K + S + force)
+    planes = rng.integers(-64, 65, size=(S, rows, K), dtype=np.int8)
+    rs = 2.0 ** rng.integers(-2, 3, size=rows).astype(np.float64)
+    C = rng.normal(size=(rows, rows))
+    got = C.copy()
+    pl = np.ascontiguousarray(planes)
+    try:
+        ctx.check(ctx.lib.b200gp_i8_update_test(ctx.handle, _cabi.ptr(pl), S, rows, K, _cabi.ptr(rs), _cabi.ptr(got)))
+    finally:
+        ctx.reset_options()
+    want = C.copy()
+    P = planes.astype(np.float64)
+    for s in range(S):
+        for t in range(S - s):
+            want -= 2.0 ** -(12 + 7 * (s + t)) * (rs[:, None] * rs[None, :]) * (P[s] @ P[t].T)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * max(1.0, np.abs(want).max()))
+
+
+@pytest.mark.parametrize("force", [0, 3])
+def test_factorisation_with_split_k(ctx, force):
+    """whole factorisation with the split-K policy on (default) and with three forced segments in every update launch"""
+    from tinygp_b200 import kernels
+    n = 6144
+    rng = np.random.default_rng(11)
+    X = rng.uniform(0, 20.0 * (n / 65536.0) ** (1 / 3), (n, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    k = 1.3 * kernels.ExpSquared(0.8)
+    ctx.set_option("nb", 512)
+    ctx.set_option("ozaki_min_n", 0)
+    ctx.set_option("ozaki_splitk_force", force)
+    try:
+        lp = GaussianProcess(k, X, diag=0.1).log_probability(y)
+    finally:
+        ctx.reset_options()
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+    assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)

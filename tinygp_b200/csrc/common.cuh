@@ -69,7 +69,9 @@ struct b200gp_ctx {
     int64_t qs_occupancy = 1;   // structured quasisep kernels: 1 = register-capped variants (16 / 12 resident warps per SM), 0 = natural
     int64_t build_fast = 1;     // kernel-matrix build: 1 = sum-of-products normal form when the program has one, 0 = interpreter
     int64_t panel_fused = 0;    // 1: one launch per 128-column step of the panel factorisation (potf2 + trtri + solve)
-    int64_t oz_persistent = 0;  // int8 update: 1 = persistent tile scheduler (one CTA pair per SM pair, tiles by atomic counter)
+    int64_t oz_splitk = 1024;   // int8 update (CTA-pair kernel): > 0 = split K over idle SM pairs, value = fixed cost of a tile in K
+                                // columns for the policy (ozaki.cu choose_splitk); 0 = one K range per tile
+    int64_t oz_splitk_force = 0; // > 1: that many K segments in every CTA-pair launch (tests)
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
     // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA.  7 planes = 48 bits under the
     // row scale: at N = 65536 the log-probability differs from the LAPACK golden by 4.7e-12 with 7 AND with 8 planes

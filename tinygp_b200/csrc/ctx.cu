@@ -187,7 +187,8 @@ static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kO
     {"ozaki_min_n", &b200gp_ctx::oz_min_n},
     {"ozaki_l2promo", &b200gp_ctx::oz_l2promo},
     {"ozaki_subpanel", &b200gp_ctx::oz_subpanel},
-    {"ozaki_persistent", &b200gp_ctx::oz_persistent},
+    {"ozaki_splitk", &b200gp_ctx::oz_splitk},
+    {"ozaki_splitk_force", &b200gp_ctx::oz_splitk_force},
 };
 
 static void validate_option(const char* key, int64_t value) {

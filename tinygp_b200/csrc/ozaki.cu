@@ -58,6 +58,13 @@ struct Args {
     int pg_single;                     // diagnostic: paired-group loop structure (kc outer) with ONE group per pass
     int* error_flag;
     unsigned long long* dbg;           // optional in-kernel cycle counters (see DBG_* below); nullptr = off
+    // split-K (CTA-pair kernel only; nseg <= 1 = off): the K range is cut into nseg segments of kseg columns that run as
+    // independent tiles of the SAME launch; segment 0 updates C, segment s >= 1 accumulates into its own zero-filled
+    // fp64 scratch tile set (virtual base Cseg + (s - 1) * seg_stride, row stride ldseg) that splitk_fixup_kernel adds
+    // to C afterwards in a fixed order.  Fills the SM pairs that a block column with few (long) tiles leaves idle.
+    int nseg, kseg;
+    double* Cseg; int64_t ldseg, seg_stride;
+    int no_split;                      // launcher hint: keep one K range per tile (sharded path: bit-identical for any rank count)
 };
 
 // in-kernel cycle counters (diagnostics, option-free: on when Args.dbg != nullptr).  Sums over CTAs of clock64() deltas.
@@ -636,10 +643,13 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
     int crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
     const bool leader = (crank == 0);
-    const int pair_id = (int)blockIdx.x >> 1;
+    int pair_id = (int)blockIdx.x >> 1;
     const int ptm = (g.tiles_m + 1) / 2;                     // row pairs
+    int seg = 0;
+    if (g.nseg > 1) { seg = pair_id / (ptm * g.tiles_n); pair_id -= seg * (ptm * g.tiles_n); }   // segment slowest
     const int pi = pair_id / g.tiles_n, tj = pair_id % g.tiles_n;   // tj fastest (L2 sharing of A panels)
-    (void)ptm;
+    const int seg_k0 = g.k_begin + seg * g.kseg;             // first K column of this tile's segment
+    const int seg_K = (g.nseg > 1) ? ((g.K - seg * g.kseg < g.kseg) ? (g.K - seg * g.kseg) : g.kseg) : g.K;
     const int64_t prow0 = g.row0 + (int64_t)pi * 2 * TM;     // first row of the 256-row pair tile
     const int64_t grow0 = prow0 + (int64_t)crank * TM;       // this CTA's 128 rows
     const int64_t gcol0 = g.col0 + (int64_t)tj * TN;
@@ -663,7 +673,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int KT = g.K / KC;
+    const int KT = seg_K / KC;
     const int64_t brow0 = g.b_row0 + (int64_t)tj * TN + (int64_t)crank * 128;  // this CTA's half of the B rows
 
     const bool prof = (g.dbg != nullptr);
@@ -689,7 +699,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                             uint8_t* b_dst = a_dst + A_BYTES;
                             if (leader) mbar_expect_tx(full + stage, 2 * STAGE2_BYTES);
                             const uint32_t lbar = mapa_rank0(smem_u32(full + stage));
-                            const int kx = g.k_begin + kc * KC;
+                            const int kx = seg_k0 + kc * KC;
 #pragma unroll
                             for (int bx = 0; bx < TM / BOXR; ++bx) {
                                 tma_load_3d_2sm(a_dst + bx * BOXR * KC, &maps.all, lbar, kx, (int)grow0 + bx * BOXR, i);
@@ -708,7 +718,7 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
                         uint8_t* b_dst = a_dst + A_BYTES;
                         if (leader) mbar_expect_tx(full + stage, 2 * STAGE2_BYTES);   // both CTAs' bytes
                         const uint32_t lbar = mapa_rank0(smem_u32(full + stage));
-                        const int kx = g.k_begin + kc * KC;
+                        const int kx = seg_k0 + kc * KC;
 #pragma unroll
                         for (int bx = 0; bx < TM / BOXR; ++bx) {
                             tma_load_3d_2sm(a_dst + bx * BOXR * KC, &maps.all, lbar, kx, (int)grow0 + bx * BOXR, s);
@@ -819,7 +829,8 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
         const int64_t gr = grow0 + row;
         const bool row_ok = gr < g.n_rows;
         const double rsi = row_ok ? g.rs[gr] : 0.0;
-        double* crow = g.C + (row_ok ? gr : 0) * g.ldc;
+        double* crow = (seg == 0) ? g.C + (row_ok ? gr : 0) * g.ldc
+                                   : g.Cseg + (int64_t)(seg - 1) * g.seg_stride + (row_ok ? gr : 0) * g.ldseg;
         const uint32_t tempty_leader0 = mapa_rank0(smem_u32(tempty + 0));
         const uint32_t tempty_leader1 = mapa_rank0(smem_u32(tempty + 1));
         bool ok = true;
@@ -1214,7 +1225,7 @@ static void launch_2sm(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     const int64_t npairs = (int64_t)ptm * a.tiles_n;
     if (npairs <= 0 || a.K <= 0) return;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(npairs * 2));
+    cfg.gridDim = dim3((unsigned)(npairs * 2 * (a.nseg > 1 ? a.nseg : 1)));
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM2_BYTES;
     cfg.stream = ctx->stream;
@@ -1290,10 +1301,102 @@ int max_exact_k(int S) {
     return (int)((k / KC) * KC);
 }
 
+// C[row0 + r, col0 + c] += sum_s scratch_s[r, c] in the fixed order s = 0, 1, ... (deterministic), 2 columns per thread
+__global__ void __launch_bounds__(256) splitk_fixup_kernel(double* __restrict__ C, int64_t ldc, int64_t row0, int64_t col0,
+                                                           int64_t rows, int64_t cols, const double* __restrict__ scr,
+                                                           int nextra, int64_t lds, int64_t seg_stride) {
+    const int64_t half = cols >> 1;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * half) return;
+    const int64_t r = idx / half, c = (idx - r * half) * 2;
+    double2* cp = reinterpret_cast<double2*>(C + (row0 + r) * ldc + col0 + c);
+    double2 v = *cp;
+    for (int s = 0; s < nextra; ++s) {
+        const double2 w = *reinterpret_cast<const double2*>(scr + (int64_t)s * seg_stride + r * lds + c);
+        v.x += w.x; v.y += w.y;
+    }
+    *cp = v;
+}
+
+// Split-K policy of the CTA-pair kernel (option "ozaki_splitk" = E > 0: on, E = cost of a tile's fixed part -- four
+// epilogue passes, pipeline fill -- in K columns; 0 = off).  A block-column launch has T active 256 x 256 tiles of EQUAL
+// duration for `slots` SM pairs, so it runs in ceil(T / slots) waves; the last block columns have the longest tiles and
+// the fewest of them (T = 10 at K = 64512 for the last column of N = 65536: 13 % of the chip busy).  Because every
+// segment's integer sums are exact, cutting K into s segments changes nothing but the order of s fp64 additions per
+// element.  s minimises  ceil(T s / slots) * (K / s + E)  + the scratch traffic (zero-fill + fix-up) in the same unit.
+static int choose_splitk(b200gp_ctx* ctx, const Args& a, int64_t active_tiles, int* kseg_out) {
+    const int64_t E = ctx->oz_splitk;
+    if (E <= 0 || ctx->oz_cluster != 2 || active_tiles <= 0 || a.no_split) return 1;
+    const int slots = ctx->num_sms / 2 > 0 ? ctx->num_sms / 2 : 1;
+    const int64_t rows = (int64_t)a.tiles_m * TM, cols = (int64_t)a.tiles_n * TN;
+    if (ctx->oz_splitk_force > 1) {   // tests: this many segments whatever the cost model says
+        int s = (int)ctx->oz_splitk_force;
+        if (s > a.K / KC) s = a.K / KC;
+        const int kseg = (int)((((int64_t)a.K + s - 1) / s + KC - 1) / KC) * KC;
+        *kseg_out = kseg;
+        return (a.K + kseg - 1) / kseg;
+    }
+    // one K column of one wave takes ~ S(S+1)/2 * 2*256*256 int8 op / (peak / slots): ~59 ns at 7 planes; the scratch
+    // costs 24 B per element and extra segment (memset write + fix-up read) + 16 B once (fix-up RMW of C) at ~5 TB/s
+    const double ns_per_k = 59.0 * (0.5 * a.S * (a.S + 1)) / 28.0;
+    double best = 0.0; int best_s = 1, best_kseg = a.K;
+    for (int s = 1; s <= 16; ++s) {
+        int kseg = (int)((((int64_t)a.K + s - 1) / s + KC - 1) / KC) * KC;
+        if (s > 1 && kseg < 1024) break;
+        const int ns = (a.K + kseg - 1) / kseg;
+        if (ns != s) continue;
+        const int64_t waves = (active_tiles * s + slots - 1) / slots;
+        double cost = (double)waves * ((double)kseg + (double)E) * ns_per_k;
+        if (s > 1) cost += ((double)(s - 1) * 24.0 + 16.0) * (double)rows * (double)cols / 5000.0;   // bytes / (5000 B/ns)
+        if ((size_t)(s - 1) * rows * cols * 8 > ((size_t)2 << 30)) break;
+        if (s == 1) best = cost;
+        else if (cost < 0.98 * best) { best = cost; best_s = s; best_kseg = kseg; }
+    }
+    *kseg_out = best_kseg;
+    return best_s;
+}
+
+static void launch_update_splitk(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
+    int64_t active = 0;
+    if (ctx->oz_cluster == 2 && ctx->oz_splitk > 0) {
+        const int ptm = (a.tiles_m + 1) / 2;
+        for (int pi = 0; pi < ptm; ++pi)
+            for (int tj = 0; tj < a.tiles_n; ++tj) {
+                const int64_t rlo = a.row0 + (int64_t)pi * 2 * TM, clo = a.col0 + (int64_t)tj * TN;
+                if (a.skip_upper && rlo + 2 * TM - 1 < clo) continue;
+                ++active;
+            }
+    }
+    int kseg = a.K;
+    const int nseg = choose_splitk(ctx, a, active, &kseg);
+    if (nseg <= 1) { launch_update_one(ctx, maps, a); return; }
+    const int64_t rows = (int64_t)a.tiles_m * TM;                       // rows the tiles may write (masked by n_rows)
+    const int64_t lds = (int64_t)a.tiles_n * TN;
+    const int64_t seg_stride = ((a.tiles_m + 1) / 2) * 2 * (int64_t)TM * lds;
+    size_t scr_bytes = (size_t)64 << 20;    // size classes (powers of two) so that the context's buffer cache hits
+    while (scr_bytes < (size_t)(nseg - 1) * seg_stride * 8) scr_bytes <<= 1;
+    Scratch scr(ctx, scr_bytes);
+    CUDA_CHECK(cudaMemsetAsync(scr.p, 0, (size_t)(nseg - 1) * seg_stride * 8, ctx->stream));
+    Args b = a;
+    b.nseg = nseg; b.kseg = kseg;
+    b.ldseg = lds; b.seg_stride = seg_stride;
+    b.Cseg = scr.f64() - a.row0 * lds - a.col0;                          // virtual base: indexed by GLOBAL row / column
+    launch_update_one(ctx, maps, b);
+    int64_t cols = lds;
+    if (a.col0 + cols > a.n_rows) cols = a.n_rows - a.col0;              // the kernel masks columns >= n_rows
+    int64_t rws = rows;
+    if (a.row0 + rws > a.n_rows) rws = a.n_rows - a.row0;
+    const int64_t nthr = rws * (cols / 2);
+    splitk_fixup_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(a.C, a.ldc, a.row0, a.col0, rws, cols, scr.f64(),
+                                                                                nseg - 1, lds, seg_stride);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
 void launch_update(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     const int kmax = max_exact_k(a.S);
     if (a.K <= kmax) {
-        launch_update_one(ctx, maps, a);
+        launch_update_splitk(ctx, maps, a);
         return;
     }
     for (int k0 = 0; k0 < a.K; k0 += kmax) {
@@ -1924,6 +2027,7 @@ int b200gp_mg_update_rows(b200gp_mg* m, int J, int64_t r0, int64_t r1) {
         a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
         a.K = (int)c0; a.k_begin = 0; a.S = m->S; a.n_rows = np; a.skip_upper = 1; a.error_flag = m->err;
         a.prefetch = (int)_ctx->oz_prefetch; a.pg_single = (_ctx->oz_pairing == 2);
+        a.no_split = 1;   // the split depends on the tile count of this rank's rows: keep the G-independent summation order
         ProfTimer t(_ctx, &_ctx->prof.syrk_ms);
         oz::launch_update(_ctx, m->maps, a);
         _ctx->prof.syrk_flop += 2.0 * (double)(r1 - r0) * (double)kb * (double)c0;

@@ -283,6 +283,61 @@ int b200gp_qs_condition(b200gp_qs* s, const double* prog, int n_instr, const dou
 int b200gp_searchsorted_right_m1(b200gp_ctx* ctx, const double* sorted, int64_t n,
                                  const double* query, int64_t m, int64_t* out);
 
+/* ---- quasiseparable-matrix algebra on generator arrays  (solvers/quasisep/core.py, ops.py) ---------------- */
+/* A b200gp_qsm holds DEVICE-resident generators of one of core.py's seven classes: d (n); strictly lower and / or
+ * strictly upper parts (p, q: n x m, a: n x m x m, row-major) of orders ml, mu.  StrictLowerTriQSM (core.py:168-236):
+ * M[i, j] = p_i . a_{i-1} ... a_{j+1} . q_j (i > j); StrictUpperTriQSM with the same (p, q, a) is its transpose
+ * (core.py:239-292).  Handles returned by the operations are new objects; parts and transposes share device arrays.
+ * Every operation is a chunked scan in O(n m^3) -- one warp per chunk, matrix state in shared memory -- nothing is
+ * densified.  This is what QuasisepSolver.condition's QSM branch (solver.py:124-129) is made of. */
+typedef struct b200gp_qsm b200gp_qsm;
+enum {
+    B200GP_QSM_DIAG = 0,         /* DiagQSM           core.py:134-165 */
+    B200GP_QSM_STRICT_LOWER = 1, /* StrictLowerTriQSM core.py:168-236 */
+    B200GP_QSM_STRICT_UPPER = 2, /* StrictUpperTriQSM core.py:239-292 */
+    B200GP_QSM_LOWER = 3,        /* LowerTriQSM       core.py:295-345 */
+    B200GP_QSM_UPPER = 4,        /* UpperTriQSM       core.py:348-393 */
+    B200GP_QSM_SQUARE = 5,       /* SquareQSM         core.py:396-481 */
+    B200GP_QSM_SYMM = 6          /* SymmQSM           core.py:484-540 */
+};
+/* constructors of core.py from host arrays (NULL for the parts the kind does not have; SYMM takes d + lower) */
+int b200gp_qsm_create(b200gp_ctx* ctx, int64_t n, int kind, int ml, int mu, const double* d, const double* lp,
+                      const double* lq, const double* la, const double* up, const double* uq, const double* ua,
+                      b200gp_qsm** out);
+int b200gp_qsm_free(b200gp_qsm* q);
+int b200gp_qsm_info(b200gp_qsm* q, int64_t* n, int* kind, int* ml, int* mu);
+/* download generator arrays (NULL = skip) */
+int b200gp_qsm_get(b200gp_qsm* q, double* d, double* lp, double* lq, double* la, double* up, double* uq, double* ua);
+/* `.diag` (which = 0), `.lower` (1), `.upper` (2) of the dataclasses of core.py, sharing the device arrays */
+int b200gp_qsm_part(b200gp_qsm* q, int which, b200gp_qsm** out);
+/* LowerTriQSM(diag=, lower=) / UpperTriQSM(diag=, upper=) / SquareQSM(diag=, lower=, upper=) / SymmQSM(diag=, lower=) */
+int b200gp_qsm_compose(b200gp_qsm* diag, b200gp_qsm* lower, b200gp_qsm* upper, int symm, b200gp_qsm** out);
+int b200gp_qsm_transpose(b200gp_qsm* q, b200gp_qsm** out);                       /* core.py transpose() */
+/* scale() of core.py:155-156, 196-197, 272-273: c is one scalar, or n per-row factors if is_vector */
+int b200gp_qsm_scale(b200gp_qsm* q, const double* c, int is_vector, b200gp_qsm** out);
+int b200gp_qsm_neg(b200gp_qsm* q, b200gp_qsm** out);                             /* __neg__ */
+int b200gp_qsm_add(b200gp_qsm* a, b200gp_qsm* b, b200gp_qsm** out);              /* elementwise_add  ops.py:24-35 */
+int b200gp_qsm_elementwise_mul(b200gp_qsm* a, b200gp_qsm* b, b200gp_qsm** out);  /* elementwise_mul  ops.py:38-49 */
+/* qsm_mul (ops.py:52-214): the phi / psi scans (:62-87) and the per-point assembly (:92-203).  Operand pairs for which
+ * the reference builds generators of unequal widths (it then fails) are refused with a message. */
+int b200gp_qsm_mul(b200gp_qsm* a, b200gp_qsm* b, b200gp_qsm** out);
+int b200gp_qsm_gram(b200gp_qsm* a, b200gp_qsm** out);                            /* SquareQSM.gram  core.py:424-434 */
+/* LowerTriQSM.inv (core.py:310-317), UpperTriQSM.inv (:362-363), SymmQSM.inv = symm_inv (ops.py:403-460);
+ * SquareQSM.inv (core.py:436-478) is refused */
+int b200gp_qsm_inv(b200gp_qsm* a, b200gp_qsm** out);
+/* SymmQSM.cholesky (core.py:522-537, ops.py:352-365).  *info = 1-based index of the first non-positive pivot (the
+ * generators are NaN from there on, like the reference's), 0 if none */
+int b200gp_qsm_cholesky(b200gp_qsm* a, b200gp_qsm** out, int64_t* info);
+/* matmul of every class (ops.py:308-349): Y (n x nrhs, host, row-major) <- A Y */
+int b200gp_qsm_matmul(b200gp_qsm* a, double* Y, int64_t nrhs);
+/* LowerTriQSM.solve / UpperTriQSM.solve (core.py:319-336, 366-383; ops.py:463-512): Y <- A^-1 Y */
+int b200gp_qsm_solve(b200gp_qsm* a, double* Y, int64_t nrhs);
+int b200gp_qsm_sum_log_diag(b200gp_qsm* a, double* out);                         /* solver.py:90-93 on a factor */
+/* Quasisep.to_symm_qsm(t) (kernels/quasisep.py:102-116) as a device SymmQSM, no noise; t: n sorted host values */
+int b200gp_qs_kernel_qsm(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n, b200gp_qsm** out);
+/* `solver.factor` (solver.py:82): LowerTriQSM(diag = c, lower = (p, w, a)) of a model-based solver */
+int b200gp_qs_factor_qsm(b200gp_qs* s, b200gp_qsm** out);
+
 #ifdef __cplusplus
 }
 #endif

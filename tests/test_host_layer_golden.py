@@ -109,22 +109,34 @@ def test_mean_only_predict_skips_the_conditioned_covariance(mocklib):
         gpd.predict(yd, Xd[0])
 
 
-def test_conditioning_a_quasisep_process_at_its_inputs_stays_linear_until_the_matrix_is_needed(mocklib):
+def test_conditioning_a_quasisep_process_at_its_inputs_is_qsm_valued(mocklib):
+    """solver.py:124-129: the conditioned covariance at the inputs is a SymmQSM, factored by QuasisepSolver(covariance=);
+    neither the N x N conditioning entry point nor a dense factorisation is called for anything but `.covariance`"""
     import tinygp_b200 as tg
     from tinygp_b200.kernels import quasisep
-    from tinygp_b200.solvers.lazy import LazyConditionedSolver
+    from tinygp_b200.solvers import QuasisepSolver
+    from tinygp_b200.solvers.quasisep.core import SymmQSM
     from oracle import tinygp_np as o
     rng = np.random.default_rng(6)
     t = np.sort(rng.uniform(0, 25, 120)); y = np.sin(t) + 0.1 * rng.normal(size=120)
     k, ko = quasisep.Matern52(2.5, 1.3) + quasisep.Exp(1.1, 0.4), o.qs.Matern52(2.5, 1.3) + o.qs.Exp(1.1, 0.4)
-    lp, cond = tg.GaussianProcess(k, t, diag=0.08).condition(y, diag=0.02)
+    gp = tg.GaussianProcess(k, t, diag=0.08)
+    lp, cond = gp.condition(y, diag=0.02)
     lpo, condo = o.GaussianProcess(ko, t, diag=0.08).condition(y, diag=0.02)
-    assert isinstance(cond.solver, LazyConditionedSolver)
+    assert isinstance(cond.solver, QuasisepSolver) and isinstance(cond.solver.matrix, SymmQSM)
+    assert cond.solver.matrix.lower.p.shape == (120, 16)                                   # order 4J, J = 4
     np.testing.assert_allclose(lp, lpo, rtol=1e-10)
     np.testing.assert_allclose(cond.loc, condo.loc, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(cond.variance, condo.variance, rtol=1e-8, atol=1e-12)
-    assert "qs_condition" not in mocklib.calls and "qs_conditioned_variance" in mocklib.calls     # no N x N so far
-    np.testing.assert_allclose(cond.covariance, condo.covariance, rtol=1e-8, atol=1e-11)
     np.testing.assert_allclose(cond.log_probability(y + 0.01), condo.log_probability(y + 0.01), rtol=1e-8)
-    assert "qs_condition" in mocklib.calls and "dense_create_from_cov" in mocklib.calls
-    np.testing.assert_allclose(cond.variance, condo.variance, rtol=1e-8, atol=1e-12)               # now from the matrix
+    z = rng.normal(size=(120, 3))
+    np.testing.assert_allclose(cond.solver.dot_triangular(z), np.linalg.cholesky(condo.covariance) @ z, rtol=1e-7, atol=1e-9)
+    assert "qs_condition" not in mocklib.calls and "dense_create_from_cov" not in mocklib.calls
+    assert {"qs_kernel_qsm", "qs_factor_qsm", "qsm_inv", "qsm_mul", "qsm_gram", "qsm_add", "qsm_cholesky"} <= set(mocklib.calls)
+    np.testing.assert_allclose(cond.covariance, condo.covariance, rtol=1e-8, atol=1e-11)
+    # predicting one component of a sum (kernel=): the QSM branch with a different predictive kernel
+    k1, k1o = quasisep.Exp(1.1, 0.4), o.qs.Exp(1.1, 0.4)
+    _, c1 = gp.condition(y, kernel=k1, diag=0.02)
+    _, c1o = o.GaussianProcess(ko, t, diag=0.08).condition(y, kernel=k1o, diag=0.02)
+    np.testing.assert_allclose(c1.loc, c1o.loc, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(c1.variance, c1o.variance, rtol=1e-8, atol=1e-12)

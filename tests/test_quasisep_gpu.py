@@ -47,7 +47,7 @@ def test_factor_and_ops_parity(name, n, qs_kernel, ctx):
     # generators (kernels/quasisep.py:102-116)
     for got, want in zip(s.generators(), (so.d, so.p, so.q, so.a)):
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
-    c, w = s.factor()
+    c, w = s.factor_arrays()
     np.testing.assert_allclose(c, so.c, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(w, so.w, rtol=1e-9, atol=1e-11)
     assert rel(s.normalization(), so.normalization()) < 1e-11

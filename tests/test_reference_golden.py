@@ -43,7 +43,7 @@ def product_namespace():
     from tinygp_b200.kernels import quasisep
 
     def qs_factor(gp):
-        return gp.solver.factor()
+        return gp.solver.factor_arrays()
 
     return refcases.Namespace("product", tg.GaussianProcess, kernels, quasisep, transforms, qs_factor)
 

@@ -173,7 +173,7 @@ def test_warp_shuffle_tree_option(ctx, name, n):
     ctx.set_option("qs_chunk", 4 if n <= 700 else 64)        # small chunks -> several tree levels at small n
     try:
         gp = GaussianProcess(k, t, diag=noise)
-        c, w = gp.solver.factor()
+        c, w = gp.solver.factor_arrays()
         lp = gp.log_probability(y)
         a = gp.solver.solve_triangular(y)
         at = gp.solver.solve_triangular(a, transpose=True)

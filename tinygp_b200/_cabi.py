@@ -100,6 +100,27 @@ SIGNATURES = {
     "b200gp_qs_conditioned_variance": (c_int, [_V, _D, _D]),
     "b200gp_qs_condition": (c_int, [_V, _D, _I, _D, _L, _D, _D]),
     "b200gp_searchsorted_right_m1": (c_int, [_V, _D, _L, _D, _L, _D]),
+    # quasiseparable-matrix algebra (qsm.cu)
+    "b200gp_qsm_create": (c_int, [_V, _L, _I, _I, _I, _D, _D, _D, _D, _D, _D, _D, POINTER(c_void_p)]),
+    "b200gp_qsm_free": (c_int, [_V]),
+    "b200gp_qsm_info": (c_int, [_V, POINTER(c_int64), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "b200gp_qsm_get": (c_int, [_V, _D, _D, _D, _D, _D, _D, _D]),
+    "b200gp_qsm_part": (c_int, [_V, _I, POINTER(c_void_p)]),
+    "b200gp_qsm_compose": (c_int, [_V, _V, _V, _I, POINTER(c_void_p)]),
+    "b200gp_qsm_transpose": (c_int, [_V, POINTER(c_void_p)]),
+    "b200gp_qsm_scale": (c_int, [_V, _D, _I, POINTER(c_void_p)]),
+    "b200gp_qsm_neg": (c_int, [_V, POINTER(c_void_p)]),
+    "b200gp_qsm_add": (c_int, [_V, _V, POINTER(c_void_p)]),
+    "b200gp_qsm_elementwise_mul": (c_int, [_V, _V, POINTER(c_void_p)]),
+    "b200gp_qsm_mul": (c_int, [_V, _V, POINTER(c_void_p)]),
+    "b200gp_qsm_gram": (c_int, [_V, POINTER(c_void_p)]),
+    "b200gp_qsm_inv": (c_int, [_V, POINTER(c_void_p)]),
+    "b200gp_qsm_cholesky": (c_int, [_V, POINTER(c_void_p), POINTER(c_int64)]),
+    "b200gp_qsm_matmul": (c_int, [_V, _D, _L]),
+    "b200gp_qsm_solve": (c_int, [_V, _D, _L]),
+    "b200gp_qsm_sum_log_diag": (c_int, [_V, c_double_p]),
+    "b200gp_qs_kernel_qsm": (c_int, [_V, _D, _I, _D, _L, POINTER(c_void_p)]),
+    "b200gp_qs_factor_qsm": (c_int, [_V, POINTER(c_void_p)]),
 }
 
 

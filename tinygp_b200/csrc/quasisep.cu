@@ -153,7 +153,7 @@ __global__ void generators_kernel(const __grid_constant__ QsModel m, const doubl
     if (k >= n) return;
     double aa[J][J], pp[J];
     qs_gen<J>(m, (k == 0) ? 0.0 : (t[k] - t[k - 1]), aa, pp);
-    d[k] = m.d0 + diag[k];
+    d[k] = m.d0 + (diag ? diag[k] : 0.0);
     for (int i = 0; i < J; ++i) {
         p[k * J + i] = pp[i];
         q[k * J + i] = m.q[i];
@@ -546,6 +546,53 @@ int b200gp_qs_get_generators(b200gp_qs* s, double* d, double* p, double* q, doub
     _ctx->release(pd, (size_t)n * J * 8);
     _ctx->release(qd, (size_t)n * J * 8);
     _ctx->release(ad, (size_t)n * J * J * 8);
+    API_END
+}
+
+// ---- bridges to the QSM algebra (qsm.cu) ------------------------------------------------------------------------------
+b200gp_qsm* qsm_alloc_for_solver(b200gp_ctx* ctx, int64_t n, int m, int symm, double** d, double** p, double** q, double** a);
+
+// Quasisep.to_symm_qsm (kernels/quasisep.py:102-116): the kernel's generators at t, on the device, no noise
+int b200gp_qs_kernel_qsm(b200gp_ctx* ctx, const double* comps, int ncomp, const double* t, int64_t n, b200gp_qsm** out) {
+    API_BEGIN(ctx)
+    if (n <= 0) throw GpError("qs_kernel_qsm: n must be positive");
+    const QsModel model = build_model(comps, ncomp);
+    const int J = model.J;
+    Scratch td(_ctx, (size_t)n * 8);
+    CUDA_CHECK(cudaMemcpyAsync(td.p, t, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
+    double *d, *p, *q, *a;
+    b200gp_qsm* r = qsm_alloc_for_solver(_ctx, n, J, 1, &d, &p, &q, &a);
+    try {
+        QS_DISPATCH_J(J, (generators_kernel<JJ><<<nblk(n, 128), 128, 0, _ctx->stream>>>(model, td.f64(), nullptr, n, d, p, q, a)))
+        _ctx->launches++;
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));   // t may be the caller's pageable buffer
+    } catch (...) {
+        b200gp_qsm_free(r);
+        throw;
+    }
+    *out = r;
+    API_END
+}
+
+// solver.factor (solver.py:82; core.py:524-539): LowerTriQSM(diag = c, lower = (p, w, a)) with p, a regenerated from t
+int b200gp_qs_factor_qsm(b200gp_qs* s, b200gp_qsm** out) {
+    API_BEGIN(s->ctx)
+    const int64_t n = s->n;
+    const int J = s->J;
+    double *d, *p, *q, *a;
+    b200gp_qsm* r = qsm_alloc_for_solver(_ctx, n, J, 0, &d, &p, &q, &a);
+    try {
+        QS_DISPATCH_J(J, (generators_kernel<JJ><<<nblk(n, 128), 128, 0, _ctx->stream>>>(s->model, s->t, nullptr, n, d, p, q, a)))
+        _ctx->launches++;
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(d, s->c, (size_t)n * 8, cudaMemcpyDeviceToDevice, _ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(q, s->w, (size_t)n * J * 8, cudaMemcpyDeviceToDevice, _ctx->stream));
+    } catch (...) {
+        b200gp_qsm_free(r);
+        throw;
+    }
+    *out = r;
     API_END
 }
 

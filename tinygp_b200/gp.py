@@ -16,7 +16,7 @@ from tinygp_b200 import kernels, means
 from tinygp_b200.kernels.quasisep import Quasisep
 from tinygp_b200.noise import Diagonal, Noise
 from tinygp_b200.solvers import DirectSolver, QuasisepSolver
-from tinygp_b200.solvers.lazy import LazyConditionedSolver
+from tinygp_b200.solvers.quasisep.core import SymmQSM
 
 
 class GaussianProcess:
@@ -47,7 +47,7 @@ class GaussianProcess:
             noise = Diagonal(diag=np.broadcast_to(np.asarray(diag, dtype=np.float64), self.mean.shape).copy())
         self.noise = noise
         if solver is None:  # gp.py:101-105
-            solver = QuasisepSolver if isinstance(kernel, Quasisep) else DirectSolver
+            solver = QuasisepSolver if (isinstance(covariance_value, SymmQSM) or isinstance(kernel, Quasisep)) else DirectSolver
         self.solver = solver(kernel, self.X, self.noise, covariance=covariance_value, **solver_kwargs)
 
     @property
@@ -83,15 +83,6 @@ class GaussianProcess:
             noise = Diagonal(diag=np.broadcast_to(np.asarray(diag, dtype=np.float64), mean_value.shape).copy())
         cond_kernel = kernels.Conditioned(self.X, self.solver, kernel)
         cond_mean = means.Conditioned(self.X, alpha, kernel, include_mean=include_mean, mean_function=self.mean_function)
-        if X_test is None and kernel is self.kernel and hasattr(self.solver, "conditioned_variance"):
-            # quasiseparable process conditioned at its own inputs (solver.py:124-129): linear in N until a caller
-            # asks for something that needs the matrix (solvers/lazy.py)
-            parent = self.solver
-            gp = GaussianProcess(
-                cond_kernel, self.X, noise=noise, mean=cond_mean, mean_value=mean_value,
-                solver=lambda k, X, n, covariance=None: LazyConditionedSolver(parent, k, kernel, X, n),
-            )
-            return ConditionResult(log_prob, gp)
         covariance_value = self.solver.condition(kernel, X_test, noise)  # gp.py:201
         if X_test is None:
             X_test = self.X
@@ -102,7 +93,8 @@ class GaussianProcess:
             mean=cond_mean,
             mean_value=mean_value,
             covariance_value=covariance_value,
-            solver=DirectSolver,
+            # a SymmQSM (solver.py:124-129) is factored in O(N) by QuasisepSolver(covariance=...), gp.py:101-103
+            solver=None if isinstance(covariance_value, SymmQSM) else DirectSolver,
         )
         return ConditionResult(log_prob, gp)
 
@@ -115,7 +107,7 @@ class GaussianProcess:
         if not (return_var or return_cov):
             self._check_X_test(X_test)
             return self._condition(y, X_test, include_mean, kernel)[2]
-        if return_var and X_test is None and kernel is None and hasattr(self.solver, "conditioned_variance"):
+        if return_var and X_test is None and kernel is None and getattr(self.solver, "conditioned_variance", None) is not None:
             # QuasisepSolver at the inputs: the reference's QSM branch (solver.py:124-129) keeps this O(N); so does the
             # backward scan behind conditioned_variance -- same values as cond.variance below
             mean_value = self._condition(y, None, include_mean, None)[2]

@@ -53,6 +53,23 @@ class Quasisep(Kernel):
     def coord_to_sortable(self, X):
         return X
 
+    def to_symm_qsm(self, X):
+        """quasisep.py:102-116: the SymmQSM of this kernel at the sorted coordinates X, generated on the device (d, p, q,
+        a never touch the host) -> ``tinygp_b200.solvers.quasisep.core.SymmQSM``."""
+        from ctypes import byref, c_void_p
+
+        from tinygp_b200 import _cabi
+        from tinygp_b200.solvers.quasisep import core
+        t = _cabi.f64(np.asarray(self.coord_to_sortable(X), dtype=np.float64))
+        if t.ndim != 1:
+            raise ValueError("quasiseparable kernels take 1-D sortable coordinates")
+        comps = self.component_array()
+        ctx = core._backend()
+        out = c_void_p()
+        ctx.check(ctx.lib.b200gp_qs_kernel_qsm(ctx.handle, _cabi.ptr(comps), comps.shape[0], _cabi.ptr(t), t.shape[0],
+                                               byref(out)))
+        return core.QSM._wrap(ctx, out)
+
     # Dense evaluation (quasisep.py:118-145 ``evaluate``; used by ``condition`` at test points,
     # solver.py:131-139): the closed form k(tau), tau = |t1 - t2|, lowered to the same device kernel program as
     # the stationary kernels and evaluated by the CUDA build kernel (Kernel.__call__).

@@ -43,6 +43,10 @@ class Diagonal(Noise):
         other = np.asarray(other, dtype=np.float64)
         return self.diag * other if other.ndim == 1 else self.diag[:, None] * other
 
+    def to_qsm(self):  # noise.py:92-95
+        from tinygp_b200.solvers.quasisep.core import DiagQSM
+        return DiagQSM(d=self.diag)
+
 
 class Dense(Noise):
     def __init__(self, *a, **k):

@@ -1,0 +1,5 @@
+"""Quasiseparable solver and matrix algebra (same layout as src/tinygp/solvers/quasisep/: solver, core, ops)."""
+
+from tinygp_b200.solvers.quasisep import core as core
+from tinygp_b200.solvers.quasisep import ops as ops
+from tinygp_b200.solvers.quasisep.solver import QuasisepSolver as QuasisepSolver

@@ -12,6 +12,7 @@ import numpy as np
 
 from tinygp_b200 import _cabi
 from tinygp_b200.kernels.quasisep import Quasisep
+from tinygp_b200.solvers.quasisep import core as qcore
 from tinygp_b200.solvers.solver import ConditionedCovariance, Solver
 
 _UNSORTED_MSG = "Input coordinates must be sorted in order to use the QuasisepSolver"  # solver.py:142-146
@@ -21,14 +22,29 @@ class QuasisepSolver(Solver):
     def __init__(self, kernel, X, noise, *, covariance: Any | None = None, assume_sorted: bool = False,
                  parallel: bool = False):
         """``parallel`` is accepted for API compatibility (solver.py:33,60-64); the device scans are
-        always the chunked parallel form, and give the sequential recursion's values."""
-        if covariance is not None:
-            raise NotImplementedError("QuasisepSolver(covariance=SymmQSM) is unsupported by the B200 backend")
-        if not isinstance(kernel, Quasisep):
-            raise ValueError("QuasisepSolver requires a tinygp_b200.kernels.quasisep.Quasisep kernel")
+        always the chunked parallel form, and give the sequential recursion's values.
+
+        ``covariance`` (solver.py:75-78): a precomputed ``core.SymmQSM`` -- what ``condition`` returns for a
+        quasiseparable predictive kernel at the inputs -- is factored as it is (generator arrays of any order, qsm.cu);
+        otherwise the kernel's state-space model is factored by the model-specialised scans (quasisep.cu / qs_fast.cu)."""
         self._ctx = _cabi.get_context()
         self._h = c_void_p()
         self.kernel, self.noise, self.parallel = kernel, noise, parallel
+        self._matrix = self._factor = None
+        if covariance is not None:
+            if not isinstance(covariance, qcore.SymmQSM):
+                raise ValueError("QuasisepSolver(covariance=...) takes a tinygp_b200.solvers.quasisep.core.SymmQSM")
+            self.X = X
+            self._n = covariance.shape[0]
+            self._matrix = covariance
+            self._factor = covariance.cholesky()                              # solver.py:82
+            self.info = int(self._factor.info)
+            self._J = covariance._ml
+            # model-specific shortcuts of the kernel-built solver do not exist for generator arrays
+            self.whitened_sumsq = self.conditioned_variance = self.inverse_diagonal = None
+            return
+        if not isinstance(kernel, Quasisep):
+            raise ValueError("QuasisepSolver requires a tinygp_b200.kernels.quasisep.Quasisep kernel")
         t = _cabi.f64(kernel.coord_to_sortable(X))
         if t.ndim != 1:
             raise ValueError("QuasisepSolver takes 1-D sortable coordinates")
@@ -59,18 +75,47 @@ class QuasisepSolver(Solver):
                 pass
             self._h = c_void_p()
 
+    @property
+    def _generic(self) -> bool:
+        """built from a precomputed SymmQSM (generator arrays) rather than from a kernel's state-space model"""
+        return not self._h
+
+    @property
+    def matrix(self):
+        """solver.py:81: the covariance incl. noise as a SymmQSM (device generators)"""
+        if self._matrix is None:
+            self._matrix = self.kernel.to_symm_qsm(self.X) + self.noise.to_qsm()      # solver.py:73-74
+        return self._matrix
+
+    @property
+    def factor(self):
+        """solver.py:82: LowerTriQSM(diag = c, lower = (p, w, a)) on the device"""
+        if self._factor is None:
+            out = c_void_p()
+            self._ctx.check(self._ctx.lib.b200gp_qs_factor_qsm(self._h, byref(out)))
+            self._factor = qcore.QSM._wrap(self._ctx, out)
+        return self._factor
+
     # -- Solver contract ------------------------------------------------------------------
     def variance(self):  # solver.py:84-85
+        if self._generic:
+            return self._matrix.diag.d
         out = np.empty(self._n)
         self._ctx.check(self._ctx.lib.b200gp_qs_variance(self._h, _cabi.ptr(out)))
         return out
 
     def covariance(self):  # solver.py:87-88: to_dense() = matmul with the identity (core.py:84-90)
+        if self._generic:
+            return self._matrix.to_dense()
         eye = np.eye(self._n)
         self._ctx.check(self._ctx.lib.b200gp_qs_matmul(self._h, _cabi.ptr(eye), self._n))
         return eye
 
     def normalization(self):  # solver.py:90-93
+        if self._generic:
+            if self.info != 0:
+                return np.nan
+            return qcore.sum_log_diag(self._factor) + 0.5 * self._n * np.log(2 * np.pi)
         ld = c_double()
         self._ctx.check(self._ctx.lib.b200gp_qs_logdet_half(self._h, byref(ld)))
         if getattr(self, "info", 0) != 0:     # failed factorisation: NaN like the reference's log of a NaN pivot
@@ -86,6 +131,8 @@ class QuasisepSolver(Solver):
         return buf.reshape(y.shape)
 
     def solve_triangular(self, y, *, transpose: bool = False):  # solver.py:95-99
+        if self._generic:
+            return (self._factor.transpose() if transpose else self._factor).solve(y)
         return self._apply(self._ctx.lib.b200gp_qs_solve_triangular, y, int(bool(transpose)))
 
     def whitened_sumsq(self, y):
@@ -94,19 +141,27 @@ class QuasisepSolver(Solver):
         y = _cabi.f64(y)
         if y.shape != (self._n,):
             raise ValueError("dimension mismatch")
+        if self._generic:
+            return float(np.sum(np.square(self._factor.solve(y))))
         out = c_double()
         self._ctx.check(self._ctx.lib.b200gp_qs_solve_sumsq(self._h, _cabi.ptr(y), byref(out)))
         return out.value
 
     def dot_triangular(self, y):  # solver.py:101-102
+        if self._generic:
+            return self._factor.matmul(y)
         return self._apply(self._ctx.lib.b200gp_qs_dot_triangular, y)
 
     def matmul(self, y):
         """covariance @ y without densifying (core.py:499-505)."""
+        if self._generic:
+            return self._matrix.matmul(y)
         return self._apply(self._ctx.lib.b200gp_qs_matmul, y)
 
-    def factor(self):
-        """(c, w) of the LowerTriQSM factor (core.py:524-539)."""
+    def factor_arrays(self):
+        """(c, w) of the LowerTriQSM factor (core.py:524-539) as host arrays."""
+        if self._generic:
+            return self._factor.diag.d, self._factor.lower.q
         c, w = np.empty(self._n), np.empty((self._n, self._J))
         self._ctx.check(self._ctx.lib.b200gp_qs_get_factor(self._h, _cabi.ptr(c), _cabi.ptr(w)))
         return c, w
@@ -114,6 +169,9 @@ class QuasisepSolver(Solver):
     def generators(self):
         """(d, p, q, a) of the SymmQSM incl. the noise diagonal (kernels/quasisep.py:102-116)."""
         n, J = self._n, self._J
+        if self._generic:
+            lo = self._matrix.lower
+            return self._matrix.diag.d, lo.p, lo.q, lo.a
         d, p, q, a = np.empty(n), np.empty((n, J)), np.empty((n, J)), np.empty((n, J, J))
         self._ctx.check(self._ctx.lib.b200gp_qs_get_generators(self._h, _cabi.ptr(d), _cabi.ptr(p), _cabi.ptr(q),
                                                                _cabi.ptr(a)))
@@ -136,22 +194,30 @@ class QuasisepSolver(Solver):
         return out
 
     def condition(self, kernel, X_test, noise) -> Any:
-        """solver.py:104-139: ``Kss [+ noise] - A^T A`` with ``A = factor.solve(Ks)`` -- computed entirely on the
-        device by ``b200gp_qs_condition`` (build kernel for ``Ks^T`` from the predictive kernel's program, one
-        forward-substitution scan per test point, NT GEMM on the tensor pipe with ``k(X*, X*)`` generated in its
-        epilogue).  The reference adds the predictive noise in its QSM branch (:124-129: ``X_test is None`` with a
-        quasiseparable kernel) and not in its dense branch (:131-139); the result is tagged accordingly
-        (``ConditionedCovariance.includes_noise``).  The QSM branch's *values* are returned as a dense matrix: a
-        QSM-valued result needs qsm_mul / inv / gram on the device and is a 'next' row."""
-        diag_ptr, with_noise = None, False
+        """solver.py:104-139.
+
+        *QSM branch* (:124-129; ``X_test is None`` and a quasiseparable predictive kernel): ``M - (factor.inv() @ M).gram()``
+        with ``M = kernel.to_symm_qsm(X) + noise`` as a ``core.SymmQSM`` of order up to 4J whose generators stay on the
+        device -- O(N), nothing densified; a GaussianProcess built on it factors it with QuasisepSolver(covariance=...).
+
+        *Dense branch* (:131-139): ``Kss - A^T A`` with ``A = factor.solve(Ks)`` computed entirely on the device by
+        ``b200gp_qs_condition`` (build kernel for ``Ks^T`` from the predictive kernel's program, one forward-substitution
+        scan per test point, NT GEMM on the tensor pipe with ``k(X*, X*)`` generated in its epilogue).  The reference
+        adds the predictive noise in the QSM branch and not in the dense one; the dense result is tagged accordingly
+        (``ConditionedCovariance.includes_noise``)."""
+        if X_test is None and isinstance(kernel, Quasisep):                       # solver.py:124-129
+            M = kernel.to_symm_qsm(self.X)
+            if M.shape[0] != self._n:
+                raise ValueError("dimension mismatch")
+            delta = (self.factor.inv() @ M).gram()
+            M = M + noise.to_qsm()
+            return M - delta
+        if self._generic:
+            raise NotImplementedError("the dense branch of QuasisepSolver.condition (solver.py:131-139) is not available "
+                                      "for a solver built from a precomputed SymmQSM")
         if X_test is None:
             prog, x = kernel.lower_for(self.X)
             xt_ptr, m = None, self._n
-            if isinstance(kernel, Quasisep):                                   # solver.py:124-129
-                diag = _cabi.f64(noise.diagonal())
-                if diag.shape != (m,):
-                    raise ValueError("noise diagonal must match the number of predicted points")
-                diag_ptr, with_noise = _cabi.ptr(diag), True
         else:
             xt = np.asarray(kernel.coord_to_sortable(X_test) if hasattr(kernel, "coord_to_sortable") else X_test,
                             dtype=np.float64)
@@ -164,5 +230,5 @@ class QuasisepSolver(Solver):
                                       "B200 QuasisepSolver.condition")
         out = np.empty((m, m))
         self._ctx.check(self._ctx.lib.b200gp_qs_condition(self._h, _cabi.ptr(prog), prog.shape[0], xt_ptr, m,
-                                                          diag_ptr, _cabi.ptr(out)))
-        return ConditionedCovariance.tag(out, with_noise)
+                                                          None, _cabi.ptr(out)))
+        return ConditionedCovariance.tag(out, False)

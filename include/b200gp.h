@@ -215,12 +215,17 @@ int b200gp_mg_finish(b200gp_mg* m, double* logp);
 #define B200GP_QS_MAX_COMP 8
 #define B200GP_QS_MAX_J 8
 enum {
-    B200GP_QS_EXP = 0,      /* p0 = scale, p1 = sigma                 quasisep.py:491-525 */
+    B200GP_QS_EXP = 0,      /* p0 = scale, p1 = sigma [, p2 = decay rate used instead of 1/scale]   quasisep.py:491-525 */
     B200GP_QS_MATERN32 = 1, /* p0 = scale, p1 = sigma                 quasisep.py:528-569 */
     B200GP_QS_MATERN52 = 2, /* p0 = scale, p1 = sigma                 quasisep.py:572-633 */
     B200GP_QS_SHO = 3,      /* p0 = omega, p1 = quality, p2 = sigma   quasisep.py:404-488 */
     B200GP_QS_CELERITE = 4, /* p0..p3 = a, b, c, d                    quasisep.py:343-401 */
-    B200GP_QS_COSINE = 5    /* p0 = scale, p1 = sigma                 quasisep.py:636-673 */
+    B200GP_QS_COSINE = 5,   /* p0 = scale, p1 = sigma                 quasisep.py:636-673 */
+    /* one complex-conjugate root pair -c -+ i d of a CARMA process (quasisep.py:690-900): p0 = c, p1 = d, p2, p3 = the two
+     * entries of its observation model (:770-792), slot 7 = sign of Re(acf) (:870); transition exp(-c dt) [[cos, sin],
+     * [-sin, cos]](d dt) (:886-900), Pinf = [[s, -c/d], [-c/d, s + 2 c^2/d^2]] (:866-882).  The real roots of a CARMA process
+     * are B200GP_QS_EXP components with sigma_scale = sign of Re(acf). */
+    B200GP_QS_CARMA2 = 6
 };
 /* _check_sorted (solver.py:142-146): *unsorted = any(diff(t) < 0), bit-exact boolean. */
 int b200gp_qs_check_sorted(b200gp_ctx* ctx, const double* t, int64_t n, int* unsorted);

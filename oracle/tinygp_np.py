@@ -681,6 +681,113 @@ class qs:
             cos, sin = np.cos(f * dt), np.sin(f * dt)
             return np.array([[cos, sin], [-sin, cos]])
 
+    class CARMA(Quasisep):
+        """kernels/quasisep.py:690-900 (CARMA(p, q) as a sum of real / complex exponential state blocks) with its helpers
+        carma_roots (:903-906), carma_quads2poly (:909-947) and carma_acvf (:989-1029), operation for operation -- incl.
+        the `ravel(om_complex)[::2]` selection of the complex observation model (:792)."""
+
+        def __init__(self, alpha, beta):
+            sigma = 1.0
+            alpha = np.atleast_1d(np.asarray(alpha, dtype=np.float64))
+            beta = np.atleast_1d(np.asarray(beta, dtype=np.float64))
+            assert alpha.ndim == 1 and beta.ndim == 1 and beta.shape[0] <= alpha.shape[0]
+            arroots = qs.carma_roots(np.append(alpha, 1.0))
+            acf = qs.carma_acvf(arroots, alpha, beta * sigma)
+            real_mask = np.abs(arroots.imag) < 10 * np.finfo(np.float64).eps
+            complex_mask = ~real_mask
+            complex_idx = np.cumsum(complex_mask) * complex_mask
+            complex_select = complex_mask * complex_idx % 2
+            with np.errstate(all="ignore"):
+                om_real = np.sqrt(np.abs(acf.real))
+                a, b, c, d = 2 * acf.real, 2 * acf.imag, -arroots.real, -arroots.imag
+                c2, d2 = np.square(c), np.square(d)
+                s2 = c2 + d2
+                denom = np.where(real_mask, 1.0, 2 * c * s2)
+                h2_2 = d2 * (a * c - b * d) / denom
+                h2 = np.sqrt(h2_2)
+                denom = np.where(real_mask, 1.0, d)
+                h1 = (c * h2 - np.sqrt(a * d2 - s2 * h2_2)) / denom
+            om_complex = np.array([h1, h2])
+            self.obsmodel = np.where(real_mask, om_real, np.ravel(om_complex)[::2])
+            self.alpha, self.beta, self.sigma, self.arroots, self.acf = alpha, beta, sigma, arroots, acf
+            self._real_mask, self._complex_mask, self._complex_select = real_mask, complex_mask, complex_select
+
+        @classmethod
+        def init(cls, alpha, beta):
+            return cls(alpha, beta)
+
+        @classmethod
+        def from_quads(cls, alpha_quads, beta_quads, beta_mult):
+            alpha_quads, beta_quads, beta_mult = (np.atleast_1d(np.asarray(v, dtype=np.float64))
+                                                  for v in (alpha_quads, beta_quads, beta_mult))
+            alpha = qs.carma_quads2poly(np.append(alpha_quads, 1.0))[:-1]
+            beta = qs.carma_quads2poly(np.append(beta_quads, beta_mult))
+            return cls(alpha, beta)
+
+        def design_matrix(self):
+            dm_real = np.diag(self.arroots.real * self._real_mask)
+            dm_complex_diag = np.diag(self.arroots.real * self._complex_mask)
+            dm_complex_u = np.diag((self.arroots.imag * self._complex_select)[:-1], k=1)
+            return dm_real + dm_complex_diag + -dm_complex_u.T + dm_complex_u
+
+        def stationary_covariance(self):
+            p = self.acf.shape[0]
+            diag = np.diag(np.where(self.acf.real > 0, np.ones(p), -np.ones(p)))
+            denom = np.where(self._real_mask, 1.0, self.arroots.imag)
+            diag_complex = np.diag(2 * np.square(self.arroots.real / denom * np.roll(self._complex_select, 1)
+                                                 * self._complex_mask))
+            c_over_d = self.arroots.real / denom
+            sc_complex_u = np.diag((-c_over_d * self._complex_select)[:-1], k=1)
+            return diag + diag_complex + sc_complex_u + sc_complex_u.T
+
+        def observation_model(self, X):
+            return self.obsmodel
+
+        def transition_matrix(self, X1, X2):
+            dt = X2 - X1
+            c, d = -self.arroots.real, -self.arroots.imag
+            decay = np.exp(-c * dt)
+            sin = np.sin(d * dt)
+            tm_real = np.diag(decay * self._real_mask)
+            tm_complex_diag = np.diag(decay * np.cos(d * dt) * self._complex_mask)
+            tm_complex_u = np.diag((decay * sin * self._complex_select)[:-1], k=1)
+            return tm_real + tm_complex_diag + -tm_complex_u.T + tm_complex_u
+
+    @staticmethod
+    def carma_roots(poly_coeffs):                                           # kernels/quasisep.py:903-906
+        roots = np.roots(np.asarray(poly_coeffs)[::-1]).astype(np.complex128)
+        return roots[np.argsort(roots.real, kind="stable")]
+
+    @staticmethod
+    def carma_quads2poly(quads_coeffs):                                     # kernels/quasisep.py:909-947
+        quads_coeffs = np.asarray(quads_coeffs, dtype=np.float64)
+        size = quads_coeffs.shape[0] - 1
+        remain, n_pair = size % 2, size // 2
+        mult_f = quads_coeffs[-1:]
+        poly = np.array([1.0, quads_coeffs[-2]]) if remain == 1 else np.array([0.0, 1.0])
+        poly = poly[-remain + 1:]
+        for p in range(n_pair):
+            poly = np.convolve(poly, np.append(np.array([quads_coeffs[p * 2], quads_coeffs[p * 2 + 1]]), np.ones(1))[::-1])
+        return poly[::-1] * mult_f
+
+    @staticmethod
+    def carma_acvf(arroots, arparam, maparam):                              # kernels/quasisep.py:989-1029
+        arparam, maparam = np.atleast_1d(arparam), np.atleast_1d(maparam)
+        p, q = arparam.shape[0], maparam.shape[0] - 1
+        sigma = maparam[0]
+        maparam = maparam / sigma
+        num_left = np.zeros(p, dtype=np.complex128)
+        num_right = np.zeros(p, dtype=np.complex128)
+        denom = -2 * arroots.real + np.zeros_like(arroots) * 1j
+        for k in range(q + 1):
+            num_left = num_left + maparam[k] * np.power(arroots, k)
+            num_right = num_right + maparam[k] * np.power(np.negative(arroots), k)
+        root_idx = np.arange(p)
+        for j in range(1, p):
+            root_k = arroots[np.roll(root_idx, j)]
+            denom = denom * ((root_k - arroots) * (np.conj(root_k) + arroots))
+        return sigma**2 * num_left * num_right / denom
+
 
 def qs_generators_fast(kernel, X):
     """Vectorised to_symm_qsm for the bench CPU baseline (same formulas, no Python loop per

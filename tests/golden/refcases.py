@@ -94,6 +94,12 @@ CASES = [
     dict(name="qs_scaled_sum3", kind="quasisep", kernel="2.0 * quasisep.Matern32(1.2) + quasisep.SHO(0.8, 4.0, 0.6) + 0.5 * quasisep.Exp(5.0)", n=120, span=30.0, diag=0.05, seed=28),
     dict(name="qs_product_sho_m32", kind="quasisep", kernel="quasisep.SHO(omega=1.5, quality=3.0, sigma=1.8) * quasisep.Matern32(scale=1.5, sigma=0.9)", n=120, span=30.0, diag=0.05, seed=29),
     dict(name="qs_scaled_product_plus_m52", kind="quasisep", kernel="0.7 * (quasisep.Exp(scale=2.0, sigma=1.1) * quasisep.Celerite(1.1, 0.1, 0.3, 1.5)) + quasisep.Matern52(scale=2.5, sigma=1.3)", n=120, span=30.0, diag=0.05, seed=30),
+    # CARMA (kernels/quasisep.py:690-900): one real root + a complex pair; a complex pair; two real roots; one real root; in a sum
+    dict(name="qs_carma31", kind="quasisep", kernel="quasisep.CARMA(alpha=np.array([1.4, 2.3, 1.5]), beta=np.array([0.1, 0.5]))", n=120, span=30.0, diag=0.05, seed=31),
+    dict(name="qs_carma21_complex", kind="quasisep", kernel="quasisep.CARMA(alpha=np.array([1.0, 1.2]), beta=np.array([1.0, 3.0]))", n=120, span=30.0, diag=0.05, seed=32),
+    dict(name="qs_carma21_real", kind="quasisep", kernel="quasisep.CARMA(alpha=np.array([0.1, 1.1]), beta=np.array([1.0, 3.0]))", n=120, span=30.0, diag=0.05, seed=33),
+    dict(name="qs_carma10", kind="quasisep", kernel="quasisep.CARMA(alpha=np.array([1.0 / 100]), beta=np.array([0.3]))", n=120, span=30.0, diag=0.05, seed=34),
+    dict(name="qs_carma_plus_m32", kind="quasisep", kernel="quasisep.CARMA.init(alpha=np.array([1.4, 2.3, 1.5]), beta=np.array([0.1, 0.5])) + 0.5 * quasisep.Matern32(1.5)", n=120, span=30.0, diag=0.05, seed=35),
     dict(name="qs_scaled_sum3_parallel", kind="quasisep", kernel="2.0 * quasisep.Matern32(1.2) + quasisep.SHO(0.8, 4.0, 0.6) + 0.5 * quasisep.Exp(5.0)", n=120, span=30.0, diag=0.05, seed=28, parallel=True),
 ]
 # fmt: on

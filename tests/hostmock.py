@@ -21,7 +21,7 @@ from oracle import tinygp_np as o
 
 OP_CONST, OP_EXP, OP_EXPSQ, OP_M32, OP_M52, OP_COS, OP_ESS, OP_RQ, OP_EXPCOS, OP_EXPSIN = range(10)
 OP_ADD, OP_MUL, OP_METRIC = 16, 17, 32
-QS_EXP, QS_MATERN32, QS_MATERN52, QS_SHO, QS_CELERITE, QS_COSINE = range(6)
+QS_EXP, QS_MATERN32, QS_MATERN52, QS_SHO, QS_CELERITE, QS_COSINE, QS_CARMA2 = range(7)
 
 
 def _addr(p):
@@ -118,13 +118,44 @@ def chol_or_nan(K):
 
 
 # ---- quasiseparable components -> oracle kernels (tinygp_b200/kernels/quasisep.py components()) --------------
+class _CarmaPair(o.qs.Quasisep):
+    """B200GP_QS_CARMA2 (include/b200gp.h): one complex root pair of a CARMA process as its own state-space block"""
+
+    def __init__(self, c, d, h1, h2, s):
+        self.c, self.d, self.h, self.s = c, d, np.array([h1, h2]), s
+
+    def stationary_covariance(self):
+        r = self.c / self.d
+        return np.array([[self.s, -r], [-r, self.s + 2 * r * r]])
+
+    def observation_model(self, X):
+        return self.h
+
+    def transition_matrix(self, X1, X2):
+        dt = X2 - X1
+        e, cs, sn = np.exp(-self.c * dt), np.cos(self.d * dt), np.sin(self.d * dt)
+        return e * np.array([[cs, sn], [-sn, cs]])
+
+
+class _RateExp(o.qs.Exp):
+    """B200GP_QS_EXP with the decay rate given directly (a real CARMA root): exp(-c dt), no division"""
+
+    def __init__(self, rate, sigma):
+        super().__init__(1.0 / rate, sigma)
+        self.rate = rate
+
+    def transition_matrix(self, X1, X2):
+        return np.array([[np.exp(-self.rate * (X2 - X1))]])
+
+
 def qs_kernel(comps):
     total, term = None, None
-    for kind, scale, p0, p1, p2, p3, mul_next in comps[:, :7]:
+    for kind, scale, p0, p1, p2, p3, mul_next, p4 in comps[:, :8]:
         kind = int(kind)
-        k = {QS_EXP: lambda: o.qs.Exp(p0, p1), QS_MATERN32: lambda: o.qs.Matern32(p0, p1),
+        k = {QS_EXP: lambda: (_RateExp(p2, p1) if p2 != 0.0 else o.qs.Exp(p0, p1)), QS_MATERN32: lambda: o.qs.Matern32(p0, p1),
              QS_MATERN52: lambda: o.qs.Matern52(p0, p1), QS_SHO: lambda: o.qs.SHO(p0, p1, p2),
-             QS_CELERITE: lambda: o.qs.Celerite(p0, p1, p2, p3), QS_COSINE: lambda: o.qs.Cosine(p0, p1)}[kind]()
+             QS_CELERITE: lambda: o.qs.Celerite(p0, p1, p2, p3), QS_COSINE: lambda: o.qs.Cosine(p0, p1),
+             QS_CARMA2: lambda: _CarmaPair(p0, p1, p2, p3, p4)}[kind]()
         if scale != 1.0:
             k = o.qs.Scale(k, scale)
         term = k if term is None else o.qs.Product(term, k)     # mul_next chains a Product term (quasisep.py:298-331)

@@ -32,6 +32,10 @@ KERNELS = {
     "product_sho_m32": (Q.SHO(1.5, 3.0, 1.8) * Q.Matern32(1.5, 0.9), o.qs.SHO(1.5, 3.0, 1.8) * o.qs.Matern32(1.5, 0.9)),
     "scaled_product_plus_m52": (0.7 * (Q.Exp(2.0, 1.1) * Q.Celerite(1.1, 0.1, 0.3, 1.5)) + Q.Matern52(2.5, 1.3),
                                 o.qs.Scale(o.qs.Exp(2.0, 1.1) * o.qs.Celerite(1.1, 0.1, 0.3, 1.5), 0.7) + o.qs.Matern52(2.5, 1.3)),
+    "carma31+m32": (Q.CARMA(np.array([1.4, 2.3, 1.5]), np.array([0.1, 0.5])) + 0.5 * Q.Matern32(1.5),
+                    o.qs.CARMA(np.array([1.4, 2.3, 1.5]), np.array([0.1, 0.5])) + o.qs.Scale(o.qs.Matern32(1.5, 1.0), 0.5)),
+    "carma21_complex": (Q.CARMA(np.array([1.0, 1.2]), np.array([1.0, 3.0])), o.qs.CARMA(np.array([1.0, 1.2]), np.array([1.0, 3.0]))),
+    "carma21_real": (Q.CARMA(np.array([0.1, 1.1]), np.array([1.0, 3.0])), o.qs.CARMA(np.array([0.1, 1.1]), np.array([1.0, 3.0]))),
     "scaled_sum3": (2.0 * Q.Matern32(1.2) + Q.SHO(0.8, 4.0, 0.6) + 0.5 * Q.Exp(5.0),
                     o.qs.Scale(o.qs.Matern32(1.2, 1.0), 2.0) + o.qs.SHO(0.8, 4.0, 0.6) + o.qs.Scale(o.qs.Exp(5.0, 1.0), 0.5)),
 }

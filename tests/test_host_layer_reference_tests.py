@@ -288,6 +288,10 @@ QS_KERNELS = [
     lambda: quasisep.Cosine(sigma=1.8, scale=1.5),
     lambda: 1.8 * quasisep.Cosine(1.5),
     lambda: quasisep.Matern52(1.5) * quasisep.SHO(omega=1.5, quality=0.1),      # test_quasisep.py's Product entry
+    lambda: quasisep.CARMA(alpha=np.array([1.4, 2.3, 1.5]), beta=np.array([0.1, 0.5])),      # test_quasisep.py:43-46
+    lambda: quasisep.CARMA(alpha=np.array([1, 1.2]), beta=np.array([1.0, 3.0])),
+    lambda: quasisep.CARMA(alpha=np.array([0.1, 1.1]), beta=np.array([1.0, 3.0])),
+    lambda: quasisep.CARMA(alpha=np.array([1.0 / 100]), beta=np.array([0.3])),
 ]
 
 
@@ -306,15 +310,47 @@ def test_quasisep_kernels(which):                                    # test_quas
     assert_allclose(kernel.matmul(t, x, y), kernel(t, x) @ y)
 
 
-def test_quasisep_carma_and_products_of_sums_are_refused():           # what the backend still lacks, refused loudly
+def test_products_of_sums_and_oversized_products_are_refused():       # what the backend still lacks, refused loudly
     with pytest.raises(NotImplementedError, match="unsupported by the B200"):
         QuasisepSolver((quasisep.Matern52(1.5) + quasisep.Exp(0.7)) * quasisep.SHO(omega=1.5, quality=0.1),
                        np.linspace(0, 1, 5), noise.Diagonal(np.full(5, 0.1)))
     with pytest.raises(NotImplementedError, match="unsupported by the B200"):
         QuasisepSolver(quasisep.Matern52(1.5) * quasisep.Matern52(0.5), np.linspace(0, 1, 5),      # 3 x 3 = 9 states
                        noise.Diagonal(np.full(5, 0.1)))
-    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
-        quasisep.CARMA(alpha=np.array([1.4, 2.3, 1.5]), beta=np.array([0.1, 0.5]))
+
+
+def test_carma():                                                    # test_quasisep.py:100-122
+    rng = np.random.default_rng(84930)
+    x = np.sort(rng.uniform(-3, 3, 50))
+    y = np.sin(x)
+    carma2_kernels = [
+        quasisep.CARMA(alpha=np.array([0.01]), beta=np.array([0.1])),
+        quasisep.CARMA(alpha=np.array([1.0, 1.2]), beta=np.array([1.0, 3.0])),
+        quasisep.CARMA(alpha=np.array([0.1, 1.1]), beta=np.array([1.0, 3.0])),
+    ]
+    validate_kernels = [                                             # equivalent Celerite + Exp kernels
+        quasisep.Exp(scale=100.0, sigma=np.sqrt(0.5)),
+        quasisep.Celerite(25.0 / 6, 2.5, 0.6, -0.8),
+        quasisep.Exp(1.0, np.sqrt(4.04040404)) + quasisep.Exp(10.0, np.sqrt(4.5959596)),
+    ]
+    for k1, k2 in zip(carma2_kernels, validate_kernels):
+        gp1 = GaussianProcess(k1, x, diag=0.1)
+        gp2 = GaussianProcess(k2, x, diag=0.1)
+        assert_allclose(gp1.log_probability(y), gp2.log_probability(y))
+        assert_allclose(gp1.solver.normalization(), gp2.solver.normalization())
+
+
+def test_carma_quads():                                              # test_quasisep.py:141-160
+    alpha = np.array([1.4, 2.3, 1.5])
+    beta = np.array([0.1, 0.5])
+    alpha_quads = quasisep.carma_poly2quads(np.append(alpha, 1.0))
+    beta_quads = quasisep.carma_poly2quads(beta)
+    alpha_quads, beta_mult, beta_quads = alpha_quads[:-1], beta_quads[-1], beta_quads[:-1]
+    carma31 = quasisep.CARMA.init(alpha=alpha, beta=beta)
+    carma31_quads = quasisep.CARMA.from_quads(alpha_quads=alpha_quads, beta_quads=beta_quads, beta_mult=beta_mult)
+    assert_allclose(carma31.arroots, carma31_quads.arroots)
+    assert_allclose(carma31.acf, carma31_quads.acf)
+    assert_allclose(carma31.obsmodel, carma31_quads.obsmodel)
 
 
 def test_celerite():                                                 # test_quasisep.py:83-97

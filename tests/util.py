@@ -32,6 +32,8 @@ def to_oracle(k):
         return o.qs.Product(to_oracle(k.kernel1), to_oracle(k.kernel2))
     if isinstance(k, Q.Scale):
         return o.qs.Scale(to_oracle(k.kernel), k.scale)
+    if isinstance(k, Q.CARMA):
+        return o.qs.CARMA(k.alpha, k.beta)
     if isinstance(k, Q.Celerite):
         return o.qs.Celerite(k.a, k.b, k.c, k.d)
     if isinstance(k, Q.SHO):

@@ -63,6 +63,7 @@ struct b200gp_ctx {
     int64_t peak_iters = 4096;  // loop length of the fp64 peak micro-benchmarks
     int64_t qs_chunk = 0;       // points per thread in the quasiseparable scans (0 = chosen per problem size, see qs_create_impl)
     int64_t qsm_chunk = 0;      // points per warp in the QSM-algebra scans (qsm.cu); 0 = chosen per problem size
+    int64_t qsm_sequential_redos = 0;   // read-only counter: Riccati scans redone sequentially after the consistency check (qsm.cu run_ric)
     int64_t qs_tree = 1;        // 1: warp-shuffle scan over the chunk composites (fan-in 32; default: 0.95 vs 1.37 ms at N = 1e7), 0: thread-sequential fan-in-16 tree
     int64_t potf2_version = 2;  // 1: column-at-a-time diagonal-block kernel, 2: rank-8 blocked with register tiles
     int64_t qs_kernel = 1;      // quasiseparable factorisation: 1 = layout-specialised kernels (qs_fast.cuh) when the model's block

@@ -171,6 +171,7 @@ static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kO
     {"qs_tree", &b200gp_ctx::qs_tree},
     {"qs_chunk", &b200gp_ctx::qs_chunk},
     {"qsm_chunk", &b200gp_ctx::qsm_chunk},
+    {"qsm_sequential_redos", &b200gp_ctx::qsm_sequential_redos},
     {"build_fast", &b200gp_ctx::build_fast},
     {"qs_kernel", &b200gp_ctx::qs_kernel},
     {"qs_occupancy", &b200gp_ctx::qs_occupancy},

@@ -58,12 +58,12 @@ struct Args {
     int pg_single;                     // diagnostic: paired-group loop structure (kc outer) with ONE group per pass
     int* error_flag;
     unsigned long long* dbg;           // optional in-kernel cycle counters (see DBG_* below); nullptr = off
-    // split-K (CTA-pair kernel only; nseg <= 1 = off): the K range is cut into nseg segments of kseg columns that run as
-    // independent tiles of the SAME launch; segment 0 updates C, segment s >= 1 accumulates into its own zero-filled
-    // fp64 scratch tile set (virtual base Cseg + (s - 1) * seg_stride, row stride ldseg) that splitk_fixup_kernel adds
-    // to C afterwards in a fixed order.  Fills the SM pairs that a block column with few (long) tiles leaves idle.
-    int nseg, kseg;
-    double* Cseg; int64_t ldseg, seg_stride;
+    // split-K of the tail tiles (CTA-pair kernel only; nseg <= 1 = off): pair indices >= split_from (ntail of them) are cut
+    // into nseg K segments of kseg columns that run as extra tiles of the SAME launch; segment 0 updates C, segment sg >= 1
+    // accumulates into its own zero-filled fp64 scratch tile Cseg[(sg - 1) * ntail + tail index][256][256] that
+    // splitk_fixup_kernel adds to C afterwards in a fixed order.
+    int nseg, kseg, split_from, ntail;
+    double* Cseg;
     int no_split;                      // launcher hint: keep one K range per tile (sharded path: bit-identical for any rank count)
 };
 
@@ -645,11 +645,17 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
     const bool leader = (crank == 0);
     int pair_id = (int)blockIdx.x >> 1;
     const int ptm = (g.tiles_m + 1) / 2;                     // row pairs
-    int seg = 0;
-    if (g.nseg > 1) { seg = pair_id / (ptm * g.tiles_n); pair_id -= seg * (ptm * g.tiles_n); }   // segment slowest
+    int seg = 0, tail_idx = 0;
+    const bool split = (g.nseg > 1 && pair_id >= g.split_from);
+    if (split) {                                             // tail tiles: segment slowest
+        const int idx = pair_id - g.split_from;
+        seg = idx / g.ntail; tail_idx = idx - seg * g.ntail;
+        pair_id = g.split_from + tail_idx;
+    }
+    (void)ptm;
     const int pi = pair_id / g.tiles_n, tj = pair_id % g.tiles_n;   // tj fastest (L2 sharing of A panels)
     const int seg_k0 = g.k_begin + seg * g.kseg;             // first K column of this tile's segment
-    const int seg_K = (g.nseg > 1) ? ((g.K - seg * g.kseg < g.kseg) ? (g.K - seg * g.kseg) : g.kseg) : g.K;
+    const int seg_K = split ? ((g.K - seg * g.kseg < g.kseg) ? (g.K - seg * g.kseg) : g.kseg) : g.K;
     const int64_t prow0 = g.row0 + (int64_t)pi * 2 * TM;     // first row of the 256-row pair tile
     const int64_t grow0 = prow0 + (int64_t)crank * TM;       // this CTA's 128 rows
     const int64_t gcol0 = g.col0 + (int64_t)tj * TN;
@@ -829,8 +835,10 @@ __global__ void __launch_bounds__(THREADS, 1) i8_update_kernel_2sm(const __grid_
         const int64_t gr = grow0 + row;
         const bool row_ok = gr < g.n_rows;
         const double rsi = row_ok ? g.rs[gr] : 0.0;
+        // segment >= 1: this pair's scratch tile, addressed like C through a virtual base (columns are GLOBAL indices)
         double* crow = (seg == 0) ? g.C + (row_ok ? gr : 0) * g.ldc
-                                   : g.Cseg + (int64_t)(seg - 1) * g.seg_stride + (row_ok ? gr : 0) * g.ldseg;
+                                   : g.Cseg + ((int64_t)(seg - 1) * g.ntail + tail_idx) * (2 * TM * TN)
+                                         + (int64_t)(crank * TM + row) * TN - gcol0;
         const uint32_t tempty_leader0 = mapa_rank0(smem_u32(tempty + 0));
         const uint32_t tempty_leader1 = mapa_rank0(smem_u32(tempty + 1));
         bool ok = true;
@@ -1225,7 +1233,7 @@ static void launch_2sm(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
     const int64_t npairs = (int64_t)ptm * a.tiles_n;
     if (npairs <= 0 || a.K <= 0) return;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(npairs * 2 * (a.nseg > 1 ? a.nseg : 1)));
+    cfg.gridDim = dim3((unsigned)(2 * (npairs + (a.nseg > 1 ? (int64_t)(a.nseg - 1) * a.ntail : 0))));
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM2_BYTES;
     cfg.stream = ctx->stream;
@@ -1301,94 +1309,97 @@ int max_exact_k(int S) {
     return (int)((k / KC) * KC);
 }
 
-// C[row0 + r, col0 + c] += sum_s scratch_s[r, c] in the fixed order s = 0, 1, ... (deterministic), 2 columns per thread
+// tail tile `ti` (pair index split_from + ti): C[tile] += sum_s scratch[s][ti] in the fixed order s = 0, 1, ... (deterministic)
 __global__ void __launch_bounds__(256) splitk_fixup_kernel(double* __restrict__ C, int64_t ldc, int64_t row0, int64_t col0,
-                                                           int64_t rows, int64_t cols, const double* __restrict__ scr,
-                                                           int nextra, int64_t lds, int64_t seg_stride) {
-    const int64_t half = cols >> 1;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * half) return;
-    const int64_t r = idx / half, c = (idx - r * half) * 2;
-    double2* cp = reinterpret_cast<double2*>(C + (row0 + r) * ldc + col0 + c);
+                                                           int tiles_n, int split_from, int ntail, int nextra,
+                                                           const double* __restrict__ scr, int64_t n_rows) {
+    const int ti = blockIdx.y;
+    const int pair = split_from + ti, pi = pair / tiles_n, tj = pair % tiles_n;
+    const int64_t prow0 = row0 + (int64_t)pi * 2 * TM, gcol0 = col0 + (int64_t)tj * TN;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // 2 columns per thread: 256 rows x 128 column pairs
+    const int r = idx >> 7, c = (idx & 127) * 2;
+    if (r >= 2 * TM || prow0 + r >= n_rows || gcol0 + c >= n_rows) return;
+    double2* cp = reinterpret_cast<double2*>(C + (prow0 + r) * ldc + gcol0 + c);
     double2 v = *cp;
-    for (int s = 0; s < nextra; ++s) {
-        const double2 w = *reinterpret_cast<const double2*>(scr + (int64_t)s * seg_stride + r * lds + c);
+    for (int sg = 0; sg < nextra; ++sg) {
+        const double2 w = *reinterpret_cast<const double2*>(scr + ((int64_t)sg * ntail + ti) * (2 * TM * TN) + r * TN + c);
         v.x += w.x; v.y += w.y;
     }
     *cp = v;
 }
 
-// Split-K policy of the CTA-pair kernel (option "ozaki_splitk" = E > 0: on, E = cost of a tile's fixed part -- four
-// epilogue passes, pipeline fill -- in K columns; 0 = off).  A block-column launch has T active 256 x 256 tiles of EQUAL
-// duration for `slots` SM pairs, so it runs in ceil(T / slots) waves; the last block columns have the longest tiles and
-// the fewest of them (T = 10 at K = 64512 for the last column of N = 65536: 13 % of the chip busy).  Because every
-// segment's integer sums are exact, cutting K into s segments changes nothing but the order of s fp64 additions per
-// element.  s minimises  ceil(T s / slots) * (K / s + E)  + the scratch traffic (zero-fill + fix-up) in the same unit.
-static int choose_splitk(b200gp_ctx* ctx, const Args& a, int64_t active_tiles, int* kseg_out) {
+// Split-K of the CTA-pair kernel's LAST, partially filled wave (option "ozaki_splitk" = E > 0: on, E = cost of a tile's
+// fixed part -- four epilogue passes, pipeline fill -- in K columns; 0 = off).  A block-column launch has T active
+// 256 x 256 tiles of EQUAL duration for `slots` SM pairs: floor(T / slots) full waves and a last wave of r = T mod slots
+// tiles that leaves slots - r SM pairs idle for a whole tile time; the last block columns have the longest tiles and the
+// fewest of them (T = 10 at K = 64512 for the last column of N = 65536: 13 % of the chip busy).  The r tail tiles -- the
+// last pair indices of the launch, scheduled last -- are cut into s = floor(slots / r) K segments that run as s r <= slots
+// short tiles of the SAME launch: segment 0 updates C, segment sg >= 1 accumulates into its own zero-filled fp64 scratch
+// tile, added to C afterwards in a fixed order.  Every segment's integer sums are exact, so the only change is the order
+// of s fp64 additions per element of a tail tile.  Scratch: r (s - 1) x 512 KB <= 37 MB.
+struct SplitPlan { int nseg = 1, kseg = 0, split_from = 0, ntail = 0; };
+static SplitPlan choose_splitk(b200gp_ctx* ctx, const Args& a) {
+    SplitPlan p;
+    p.kseg = a.K;
     const int64_t E = ctx->oz_splitk;
-    if (E <= 0 || ctx->oz_cluster != 2 || active_tiles <= 0 || a.no_split) return 1;
-    const int slots = ctx->num_sms / 2 > 0 ? ctx->num_sms / 2 : 1;
-    const int64_t rows = (int64_t)a.tiles_m * TM, cols = (int64_t)a.tiles_n * TN;
-    if (ctx->oz_splitk_force > 1) {   // tests: this many segments whatever the cost model says
+    if (ctx->oz_cluster != 2 || a.no_split || a.K < 2 * KC) return p;
+    const int ptm = (a.tiles_m + 1) / 2, npairs = ptm * a.tiles_n;
+    auto seg_len = [&](int s) { return (int)((((int64_t)a.K + s - 1) / s + KC - 1) / KC) * KC; };
+    if (ctx->oz_splitk_force > 1) {   // tests: every tile, this many segments whatever the cost model says
         int s = (int)ctx->oz_splitk_force;
         if (s > a.K / KC) s = a.K / KC;
-        const int kseg = (int)((((int64_t)a.K + s - 1) / s + KC - 1) / KC) * KC;
-        *kseg_out = kseg;
-        return (a.K + kseg - 1) / kseg;
+        p.kseg = seg_len(s);
+        p.nseg = (a.K + p.kseg - 1) / p.kseg;
+        p.split_from = 0; p.ntail = npairs;
+        return p;
     }
-    // one K column of one wave takes ~ S(S+1)/2 * 2*256*256 int8 op / (peak / slots): ~59 ns at 7 planes; the scratch
-    // costs 24 B per element and extra segment (memset write + fix-up read) + 16 B once (fix-up RMW of C) at ~5 TB/s
-    const double ns_per_k = 59.0 * (0.5 * a.S * (a.S + 1)) / 28.0;
-    double best = 0.0; int best_s = 1, best_kseg = a.K;
-    for (int s = 1; s <= 16; ++s) {
-        int kseg = (int)((((int64_t)a.K + s - 1) / s + KC - 1) / KC) * KC;
-        if (s > 1 && kseg < 1024) break;
-        const int ns = (a.K + kseg - 1) / kseg;
-        if (ns != s) continue;
-        const int64_t waves = (active_tiles * s + slots - 1) / slots;
-        double cost = (double)waves * ((double)kseg + (double)E) * ns_per_k;
-        if (s > 1) cost += ((double)(s - 1) * 24.0 + 16.0) * (double)rows * (double)cols / 5000.0;   // bytes / (5000 B/ns)
-        if ((size_t)(s - 1) * rows * cols * 8 > ((size_t)2 << 30)) break;
-        if (s == 1) best = cost;
-        else if (cost < 0.98 * best) { best = cost; best_s = s; best_kseg = kseg; }
+    if (E <= 0) return p;
+    const int slots = ctx->num_sms / 2 > 0 ? ctx->num_sms / 2 : 1;
+    // active tiles in launch order (pair index = pi * tiles_n + tj); the tail starts at the (full waves * slots)-th one
+    int64_t active = 0;
+    for (int pr = 0; pr < npairs; ++pr) {
+        const int pi = pr / a.tiles_n, tj = pr % a.tiles_n;
+        if (a.skip_upper && a.row0 + (int64_t)pi * 2 * TM + 2 * TM - 1 < a.col0 + (int64_t)tj * TN) continue;
+        ++active;
     }
-    *kseg_out = best_kseg;
-    return best_s;
+    const int64_t r = active % slots, full = active - r;
+    if (r == 0) return p;
+    int s = (int)(slots / r);
+    while (s > 1 && seg_len(s) < 1024) --s;          // segments shorter than ~8 K chunks are all epilogue
+    if (s > 16) s = 16;
+    if (s < 2) return p;
+    const int kseg = seg_len(s), nseg = (a.K + kseg - 1) / kseg;
+    // worth it?  tail wave (K + E) against (kseg + E) + scratch traffic (zero-fill, fix-up) ~ 0.02 K-columns per tile-segment
+    if ((double)kseg + (double)E > 0.9 * ((double)a.K + (double)E) || nseg < 2) return p;
+    int64_t seen = 0;
+    int split_from = npairs;
+    for (int pr = 0; pr < npairs; ++pr) {
+        const int pi = pr / a.tiles_n, tj = pr % a.tiles_n;
+        if (a.skip_upper && a.row0 + (int64_t)pi * 2 * TM + 2 * TM - 1 < a.col0 + (int64_t)tj * TN) continue;
+        if (seen == full) { split_from = pr; break; }
+        ++seen;
+    }
+    if (split_from >= npairs) return p;
+    p.nseg = nseg; p.kseg = kseg; p.split_from = split_from; p.ntail = npairs - split_from;
+    return p;
 }
 
 static void launch_update_splitk(b200gp_ctx* ctx, const Maps& maps, const Args& a) {
-    int64_t active = 0;
-    if (ctx->oz_cluster == 2 && ctx->oz_splitk > 0) {
-        const int ptm = (a.tiles_m + 1) / 2;
-        for (int pi = 0; pi < ptm; ++pi)
-            for (int tj = 0; tj < a.tiles_n; ++tj) {
-                const int64_t rlo = a.row0 + (int64_t)pi * 2 * TM, clo = a.col0 + (int64_t)tj * TN;
-                if (a.skip_upper && rlo + 2 * TM - 1 < clo) continue;
-                ++active;
-            }
-    }
-    int kseg = a.K;
-    const int nseg = choose_splitk(ctx, a, active, &kseg);
-    if (nseg <= 1) { launch_update_one(ctx, maps, a); return; }
-    const int64_t rows = (int64_t)a.tiles_m * TM;                       // rows the tiles may write (masked by n_rows)
-    const int64_t lds = (int64_t)a.tiles_n * TN;
-    const int64_t seg_stride = ((a.tiles_m + 1) / 2) * 2 * (int64_t)TM * lds;
+    const SplitPlan p = choose_splitk(ctx, a);
+    if (p.nseg <= 1) { launch_update_one(ctx, maps, a); return; }
+    const size_t tile_doubles = (size_t)2 * TM * TN;
+    const size_t need = (size_t)(p.nseg - 1) * p.ntail * tile_doubles * 8;
     size_t scr_bytes = (size_t)64 << 20;    // size classes (powers of two) so that the context's buffer cache hits
-    while (scr_bytes < (size_t)(nseg - 1) * seg_stride * 8) scr_bytes <<= 1;
+    while (scr_bytes < need) scr_bytes <<= 1;
     Scratch scr(ctx, scr_bytes);
-    CUDA_CHECK(cudaMemsetAsync(scr.p, 0, (size_t)(nseg - 1) * seg_stride * 8, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(scr.p, 0, need, ctx->stream));
     Args b = a;
-    b.nseg = nseg; b.kseg = kseg;
-    b.ldseg = lds; b.seg_stride = seg_stride;
-    b.Cseg = scr.f64() - a.row0 * lds - a.col0;                          // virtual base: indexed by GLOBAL row / column
+    b.nseg = p.nseg; b.kseg = p.kseg; b.split_from = p.split_from; b.ntail = p.ntail;
+    b.Cseg = scr.f64();
     launch_update_one(ctx, maps, b);
-    int64_t cols = lds;
-    if (a.col0 + cols > a.n_rows) cols = a.n_rows - a.col0;              // the kernel masks columns >= n_rows
-    int64_t rws = rows;
-    if (a.row0 + rws > a.n_rows) rws = a.n_rows - a.row0;
-    const int64_t nthr = rws * (cols / 2);
-    splitk_fixup_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(a.C, a.ldc, a.row0, a.col0, rws, cols, scr.f64(),
-                                                                                nseg - 1, lds, seg_stride);
+    dim3 grid((unsigned)((2 * TM * (TN / 2) + 255) / 256), (unsigned)p.ntail);
+    splitk_fixup_kernel<<<grid, 256, 0, ctx->stream>>>(a.C, a.ldc, a.row0, a.col0, a.tiles_n, p.split_from, p.ntail, p.nseg - 1,
+                                                      scr.f64(), a.n_rows);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }

@@ -44,7 +44,8 @@ static inline QsModel build_model(const double* comps, int ncomp) {
         switch (kind) {
             case B200GP_QS_EXP: sz = 1; break;
             case B200GP_QS_MATERN52: sz = 3; break;
-            case B200GP_QS_MATERN32: case B200GP_QS_SHO: case B200GP_QS_CELERITE: case B200GP_QS_COSINE: sz = 2; break;
+            case B200GP_QS_MATERN32: case B200GP_QS_SHO: case B200GP_QS_CELERITE: case B200GP_QS_COSINE:
+            case B200GP_QS_CARMA2: sz = 2; break;
             default: throw GpError("quasisep: unknown component kind");
         }
         lsz[i] = sz;
@@ -52,8 +53,9 @@ static inline QsModel build_model(const double* comps, int ncomp) {
         double (&P)[3][3] = lP[i];
         double (&h)[3] = lh[i];
         switch (kind) {
-            case B200GP_QS_EXP:  // quasisep.py:491-525
-                m.c0[i] = p0; h[0] = p1; P[0][0] = 1.0; break;
+            case B200GP_QS_EXP:  // quasisep.py:491-525; c1 = -1/scale, or minus the decay RATE itself when the host
+                                 // gives one in p2 (a real CARMA root, quasisep.py:886-892: exp(-c dt) with no division)
+                m.c0[i] = p0; m.c1[i] = (p2 != 0.0) ? -p2 : -1.0 / p0; h[0] = p1; P[0][0] = 1.0; break;
             case B200GP_QS_MATERN32: {  // quasisep.py:528-569
                 const double f = sqrt(3.0) / p0;
                 m.c0[i] = f; m.c1[i] = f * f; h[0] = p1;
@@ -88,6 +90,13 @@ static inline QsModel build_model(const double* comps, int ncomp) {
             }
             case B200GP_QS_COSINE:  // quasisep.py:636-673
                 m.c0[i] = 2.0 * M_PI / p0; h[0] = p1; P[0][0] = P[1][1] = 1.0; break;
+            case B200GP_QS_CARMA2: {  // one complex root pair of CARMA (quasisep.py:770-792, 866-900)
+                const double c = p0, d = p1, sgn = cc[7];
+                m.c0[i] = c; m.c1[i] = d; h[0] = p2; h[1] = p3;
+                P[0][0] = sgn; P[0][1] = P[1][0] = -c / d; P[1][1] = sgn + 2.0 * (c / d) * (c / d);
+                m.kind[i] = B200GP_QS_CELERITE;   // same transition matrix: the per-point code needs no new case
+                break;
+            }
         }
     }
     // terms: maximal runs of leaves chained by the mul_next flag; Kronecker structure with the FIRST leaf's index fastest
@@ -143,7 +152,7 @@ static inline QsModel build_model(const double* comps, int ncomp) {
 __host__ __device__ __forceinline__ int qs_leaf_transition(const QsModel& m, const int ci, const double dt, double (&T)[3][3]) {
     switch (m.kind[ci]) {
         case B200GP_QS_EXP:
-            T[0][0] = exp(-dt / m.c0[ci]);
+            T[0][0] = exp(dt * m.c1[ci]);
             return 1;
         case B200GP_QS_MATERN32: {
             const double f = m.c0[ci], e = exp(-f * dt);

@@ -56,7 +56,7 @@ static inline QsFastConst qsf_constants(const QsModel& m) {
     QsFastConst c{};
     for (int i = 0; i < m.ncomp; ++i) {
         switch (m.kind[i]) {
-            case B200GP_QS_EXP: c.k0[i] = -1.0 / m.c0[i]; break;
+            case B200GP_QS_EXP: c.k0[i] = m.c1[i]; break;
             case B200GP_QS_SHO:
                 if (m.mode[i] != 0) {
                     const double w = m.c0[i], q = m.c1[i], f = m.c2[i];

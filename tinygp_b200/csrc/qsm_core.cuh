@@ -331,6 +331,7 @@ struct RicArgs {
     double* o_c; double* o_w; double* o_ell;
     double* comp;   // nchunks x 3 m^2
     double* fin;    // nchunks x m^2
+    double* fend;   // nchunks x m^2 or null: the state LEAVING each chunk as the replay found it (consistency check)
     long long* info;      // first k (1-based) with a non-positive / non-finite pivot (atomic min); LLONG_MAX = none
 };
 QHD int ric_smem_doubles(int m) { return 7 * m * m + 6 * m; }
@@ -459,6 +460,7 @@ QHD void ric_phase3(Lane L, const RicArgs& a, int64_t c, double* ws) {
             QSYNC();
         }
     }
+    if (a.fend) vcopy(L, a.fend + c * (int64_t)mm2, f, mm2);
 }
 
 }  // namespace qsm

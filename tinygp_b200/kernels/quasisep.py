@@ -11,7 +11,7 @@ are computed on the device in registers from t[k] - t[k-1]; they are never mater
 from __future__ import annotations
 
 __all__ = ["Quasisep", "Sum", "Product", "Scale", "Celerite", "SHO", "Exp", "Matern32", "Matern52",
-           "Cosine", "CARMA"]
+           "Cosine", "CARMA", "carma_roots", "carma_quads2poly", "carma_poly2quads", "carma_acvf"]
 
 import numpy as np
 
@@ -20,8 +20,8 @@ from tinygp_b200.kernels.base import Kernel
 # dense kernel-program opcodes (include/b200gp.h)
 OP_CONST, OP_EXP, OP_MATERN32, OP_MATERN52, OP_COSINE, OP_EXPCOS, OP_EXPSIN, OP_ADD, OP_MUL = 0, 1, 3, 4, 5, 8, 9, 16, 17
 
-QS_EXP, QS_MATERN32, QS_MATERN52, QS_SHO, QS_CELERITE, QS_COSINE = range(6)
-STATE_DIM = {QS_EXP: 1, QS_MATERN32: 2, QS_MATERN52: 3, QS_SHO: 2, QS_CELERITE: 2, QS_COSINE: 2}
+QS_EXP, QS_MATERN32, QS_MATERN52, QS_SHO, QS_CELERITE, QS_COSINE, QS_CARMA2 = range(7)
+STATE_DIM = {QS_EXP: 1, QS_MATERN32: 2, QS_MATERN52: 3, QS_SHO: 2, QS_CELERITE: 2, QS_COSINE: 2, QS_CARMA2: 2}
 
 
 class Quasisep(Kernel):
@@ -308,7 +308,159 @@ class Cosine(Quasisep):
 
 
 class CARMA(Quasisep):
-    """quasisep.py:695-1030 -- complex-root state space: out of scope of the first B200 pass."""
+    """CARMA(p, q) process (quasisep.py:690-900).  The host finds the roots of the autoregressive polynomial and the
+    autocovariance coefficients once (O(p^2), `carma_roots` :903-906, `carma_acvf` :989-1029) and lowers the process to
+    the device's block-diagonal state-space model: one ``Exp`` component per real root (stationary variance +-1 = the
+    sign of Re(acf), :870) and one ``B200GP_QS_CARMA2`` component per complex pair (Celerite-type transition :886-900,
+    Pinf of :866-882, observation model of :770-792 incl. its ``ravel(om_complex)[::2]`` selection).  Per-point work
+    then runs in the model-specialised CUDA scans like every other quasiseparable kernel."""
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("CARMA is unsupported by the B200 quasiseparable solver backend")
+    def __init__(self, alpha, beta):
+        sigma = 1.0
+        alpha = np.atleast_1d(np.asarray(alpha, dtype=np.float64))
+        beta = np.atleast_1d(np.asarray(beta, dtype=np.float64))
+        assert alpha.ndim == 1
+        assert beta.ndim == 1
+        p = alpha.shape[0]
+        assert beta.shape[0] <= p
+        arroots = carma_roots(np.append(alpha, 1.0))
+        acf = carma_acvf(arroots, alpha, beta * sigma)
+        real_mask = np.abs(arroots.imag) < 10 * np.finfo(np.float64).eps        # :758
+        complex_mask = ~real_mask
+        complex_idx = np.cumsum(complex_mask) * complex_mask
+        complex_select = complex_mask * complex_idx % 2
+        with np.errstate(all="ignore"):
+            om_real = np.sqrt(np.abs(acf.real))
+            a, b, c, d = 2 * acf.real, 2 * acf.imag, -arroots.real, -arroots.imag
+            c2, d2 = np.square(c), np.square(d)
+            s2 = c2 + d2
+            denom = np.where(real_mask, 1.0, 2 * c * s2)
+            h2_2 = d2 * (a * c - b * d) / denom
+            h2 = np.sqrt(h2_2)
+            denom = np.where(real_mask, 1.0, d)
+            h1 = (c * h2 - np.sqrt(a * d2 - s2 * h2_2)) / denom
+        om_complex = np.array([h1, h2])
+        self.obsmodel = np.where(real_mask, om_real, np.ravel(om_complex)[::2])  # :792
+        self.alpha, self.beta, self.sigma, self.arroots, self.acf = alpha, beta, sigma, arroots, acf
+        self._real_mask, self._complex_mask, self._complex_select = real_mask, complex_mask, complex_select
+
+    @classmethod
+    def init(cls, alpha, beta):
+        return cls(alpha, beta)
+
+    @classmethod
+    def from_quads(cls, alpha_quads, beta_quads, beta_mult):
+        """quasisep.py:806-838"""
+        alpha_quads, beta_quads, beta_mult = (np.atleast_1d(np.asarray(v, dtype=np.float64))
+                                              for v in (alpha_quads, beta_quads, beta_mult))
+        alpha = carma_quads2poly(np.append(alpha_quads, 1.0))[:-1]
+        beta = carma_quads2poly(np.append(beta_quads, beta_mult))
+        return cls(alpha, beta)
+
+    def _blocks(self):
+        """[(kind, params...)] in state order: real roots and complex pairs as the roots are sorted (:903-906)"""
+        out, i, p = [], 0, self.arroots.shape[0]
+        sgn = np.where(self.acf.real > 0, 1.0, -1.0)
+        while i < p:
+            if self._real_mask[i]:
+                out.append(("real", -self.arroots.real[i], self.obsmodel[i], sgn[i]))
+                i += 1
+                continue
+            if not (self._complex_select[i] == 1 and i + 1 < p and self._complex_mask[i + 1] and self._complex_select[i + 1] == 0):
+                raise ValueError("CARMA: the complex roots do not come in adjacent conjugate pairs")
+            if sgn[i + 1] != sgn[i]:
+                raise ValueError("CARMA: Re(acf) changes sign inside a conjugate pair")
+            out.append(("pair", -self.arroots.real[i], -self.arroots.imag[i], self.obsmodel[i], self.obsmodel[i + 1], sgn[i]))
+            i += 2
+        return out
+
+    def components(self):
+        comps = []
+        for blk in self._blocks():
+            if blk[0] == "real":
+                _, c, h, s = blk
+                comps.append((QS_EXP, float(s), float(1.0 / c), float(h), float(c), 0.0, 0.0, 0.0))   # p2 = the rate itself
+            else:
+                _, c, d, h1, h2, s = blk
+                comps.append((QS_CARMA2, 1.0, float(c), float(d), float(h1), float(h2), 0.0, float(s)))
+        return comps
+
+    def tau_program(self, dist):
+        """k(tau) = h^T T(tau)^T Pinf h block by block (quasisep.py:201-210): s h^2 exp(-c tau) per real root and
+        exp(-c tau) [A cos(d tau) + B sin(d tau)], A = h^T P h, B = h^T J P h with J = [[0, -1], [1, 0]], per pair."""
+        prog, first = [], True
+        for blk in self._blocks():
+            if blk[0] == "real":
+                _, c, h, s = blk
+                term = [(OP_EXP, dist, float(1.0 / c), 0.0), (OP_CONST, 0, float(s * h * h), 0.0), (OP_MUL, 0, 0.0, 0.0)]
+            else:
+                _, c, d, h1, h2, s = blk
+                P = np.array([[s, -c / d], [-c / d, s + 2.0 * (c / d) ** 2]])
+                h = np.array([h1, h2])
+                A = float(h @ P @ h)
+                B = float(h @ np.array([[0.0, -1.0], [1.0, 0.0]]) @ P @ h)
+                term = [(OP_EXPCOS, dist, float(c), float(d)), (OP_CONST, 0, A, 0.0), (OP_MUL, 0, 0.0, 0.0),
+                        (OP_EXPSIN, dist, float(c), float(d)), (OP_CONST, 0, B, 0.0), (OP_MUL, 0, 0.0, 0.0), (OP_ADD, 0, 0.0, 0.0)]
+            prog += term
+            if not first:
+                prog.append((OP_ADD, 0, 0.0, 0.0))
+            first = False
+        return prog
+
+
+def carma_roots(poly_coeffs):
+    """quasisep.py:903-906"""
+    roots = np.roots(np.asarray(poly_coeffs, dtype=np.float64)[::-1]).astype(np.complex128)
+    return roots[np.argsort(roots.real, kind="stable")]
+
+
+def carma_quads2poly(quads_coeffs):
+    """quasisep.py:909-947"""
+    quads_coeffs = np.asarray(quads_coeffs, dtype=np.float64)
+    size = quads_coeffs.shape[0] - 1
+    remain, n_pair = size % 2, size // 2
+    mult_f = quads_coeffs[-1:]
+    poly = np.array([1.0, quads_coeffs[-2]]) if remain == 1 else np.array([0.0, 1.0])
+    poly = poly[-remain + 1:]
+    for p in range(n_pair):
+        poly = np.convolve(poly, np.append(np.array([quads_coeffs[p * 2], quads_coeffs[p * 2 + 1]]), np.ones(1))[::-1])
+    return poly[::-1] * mult_f
+
+
+def carma_poly2quads(poly_coeffs):
+    """quasisep.py:950-986"""
+    poly_coeffs = np.asarray(poly_coeffs, dtype=np.float64)
+    quads = np.empty(0)
+    mult_f = poly_coeffs[-1]
+    roots = carma_roots(poly_coeffs / mult_f)
+    odd = bool(len(roots) & 0x1)
+    roots_comp = roots[roots.imag != 0]
+    roots_real = roots[roots.imag == 0]
+    for i in range(len(roots_comp) // 2):
+        r1, r2 = roots_comp[i], roots_comp[i + 1]
+        quads = np.append(quads, [(r1 * r2).real, -(r1.real + r2.real)])
+    for i in range(len(roots_real) // 2):
+        r1, r2 = roots_real[i], roots_real[i + 1]
+        quads = np.append(quads, [(r1 * r2).real, -(r1.real + r2.real)])
+    if odd:
+        quads = np.append(quads, -roots_real[-1].real)
+    return np.append(quads, mult_f)
+
+
+def carma_acvf(arroots, arparam, maparam):
+    """quasisep.py:989-1029: the autocovariance coefficient of every root (Kelly et al. 2014, eq. 4)"""
+    arparam, maparam = np.atleast_1d(arparam), np.atleast_1d(maparam)
+    p, q = arparam.shape[0], maparam.shape[0] - 1
+    sigma = maparam[0]
+    maparam = maparam / sigma
+    num_left = np.zeros(p, dtype=np.complex128)
+    num_right = np.zeros(p, dtype=np.complex128)
+    denom = -2 * arroots.real + np.zeros_like(arroots) * 1j
+    for k in range(q + 1):
+        num_left = num_left + maparam[k] * np.power(arroots, k)
+        num_right = num_right + maparam[k] * np.power(np.negative(arroots), k)
+    root_idx = np.arange(p)
+    for j in range(1, p):
+        root_k = arroots[np.roll(root_idx, j)]
+        denom = denom * ((root_k - arroots) * (np.conj(root_k) + arroots))
+    return sigma**2 * num_left * num_right / denom

@@ -69,7 +69,8 @@ struct b200gp_ctx {
     int64_t qs_kernel = 1;      // quasiseparable factorisation: 1 = layout-specialised kernels (qs_fast.cuh) when the model's block
                                 // layout is compiled in, 0 = always the generic J x J kernels of qs_core.cuh
     int64_t qs_occupancy = 1;   // structured quasisep kernels: 1 = register-capped variants (16 / 12 resident warps per SM), 0 = natural
-    int64_t build_fast = 1;     // kernel-matrix build: 1 = sum-of-products normal form when the program has one, 0 = interpreter
+    int64_t build_fast = 2;     // kernel-matrix build: 2 = + compile-time single-leaf kernels (coef * one stationary leaf, <= 3-D),
+                                // 1 = sum-of-products normal form when the program has one, 0 = interpreter
     int64_t panel_fused = 0;    // 1: one launch per 128-column step of the panel factorisation (potf2 + trtri + solve)
     int64_t oz_splitk = 1024;   // int8 update (CTA-pair kernel): > 0 = split K over idle SM pairs, value = fixed cost of a tile in K
                                 // columns for the policy (ozaki.cu choose_splitk); 0 = one K range per tile

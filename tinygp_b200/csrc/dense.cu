@@ -105,13 +105,131 @@ __global__ void __launch_bounds__(256, 3) build_rect_kernel_t(const __grid_const
     }
 }
 
-// normal form when the program has one (and option "build_fast" is on), the interpreter otherwise / for batched programs
+// SINGLE: coef * one stationary leaf, identity metric, 1-3 dimensions, everything about the program a template parameter --
+// the shape of BASELINE configs 1, 2, 5 (`amp * ExpSquared(scale)`) and of most hyper-parameter searches.  ncu of the
+// normal-form kernel above (profiles/r2_ncu_build.md): ~230 instructions per element, issue-bound at 12 % of the HBM write
+// peak, most of them loop / predicate / runtime-dispatch overhead around one fp64 exp.  Here a thread keeps its two columns'
+// coordinates in registers, the row coordinates come from shared memory as broadcasts, model constants are folded on the
+// host (1 / scale^2: one rounding in the argument, within the 1e-13 parity tolerance), and tiles that touch neither the
+// diagonal nor the padding run without a single predicate.  Boundary / diagonal tiles take the general element path.
+template <int OP, bool L2, int ND>
+__device__ __forceinline__ double single_leaf(const double (&xa)[ND], const double (&xb)[ND], const double c0, const double c1) {
+    double l1 = 0.0, l2sq = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double df = xa[d] - xb[d];
+        if (L2) l2sq = fma(df, df, l2sq);
+        else l1 += fabs(df);
+    }
+    if (OP == B200GP_OP_EXPSQUARED) return exp((L2 ? l2sq : l1 * l1) * c0);            // c0 = -0.5 / scale^2
+    const double dist = L2 ? sqrt(l2sq) : l1;                                          // sqrt(0) = 0 = the reference's guard value
+    const double r = dist * c0;                                                        // c0 = sqrt3|sqrt5|1 / scale
+    if (OP == B200GP_OP_EXP) return exp(-r);
+    if (OP == B200GP_OP_MATERN32) return (1.0 + r) * exp(-r);
+    return (1.0 + r + r * r * c1) * exp(-r);                                           // MATERN52, c1 = 1/3
+}
+
+template <int OP, bool L2, int ND>
+__global__ void __launch_bounds__(256, 3) build_rect_kernel_single(const BuildArgs a, const double coef, const double c0, const double c1) {
+    __shared__ double x1s[BUILD_ROWS * ND];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * BUILD_ROWS;
+    const int64_t c0g = (int64_t)blockIdx.x * BUILD_COLS;
+    for (int i = tid; i < BUILD_ROWS * ND; i += 256) {
+        const int64_t r = r0 + i / ND;
+        x1s[i] = (r < a.n1) ? a.X1[r * ND + (i % ND)] : 0.0;
+    }
+    const int cl = (tid & 63) * 2;  // two consecutive columns per thread -> 16-byte stores, 512 B per warp
+    const int rl0 = tid >> 6;       // 0..3
+    double xb[2][ND];
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const int64_t c = c0g + cl + e;
+            xb[e][d] = (c < a.n2) ? a.X2[c * ND + d] : 0.0;
+        }
+    __syncthreads();
+    // interior tile: all rows / columns valid, not on the diagonal of the global matrix, 16-byte aligned rows
+    const int64_t gr0 = r0 + a.row_off, gc0 = c0g + a.col_off;
+    const bool interior = (r0 + BUILD_ROWS <= a.n1) && (c0g + BUILD_COLS <= a.n2) && (r0 + BUILD_ROWS <= a.rows_pad) &&
+                          (c0g + BUILD_COLS <= a.cols_pad) && (gr0 + BUILD_ROWS <= gc0 || gc0 + BUILD_COLS <= gr0) &&
+                          ((reinterpret_cast<uintptr_t>(a.out + r0 * a.ld + c0g) | (uintptr_t)(a.ld * 8)) & 15) == 0;
+    if (interior) {
+        double* dst = a.out + (r0 + rl0) * a.ld + c0g + cl;
+        const int64_t step = 4 * a.ld;
+#pragma unroll 4
+        for (int rr = 0; rr < BUILD_ROWS / 4; ++rr) {
+            double xa[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) xa[d] = x1s[(rl0 + rr * 4) * ND + d];
+            const double v0 = coef * single_leaf<OP, L2, ND>(xa, xb[0], c0, c1);
+            const double v1 = coef * single_leaf<OP, L2, ND>(xa, xb[1], c0, c1);
+            *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            dst += step;
+        }
+        return;
+    }
+    for (int rr = 0; rr < BUILD_ROWS / 4; ++rr) {
+        const int rl = rl0 + rr * 4;
+        const int64_t r = r0 + rl;
+        if (r >= a.rows_pad) break;
+        double xa[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) xa[d] = x1s[rl * ND + d];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int64_t c = c0g + cl + e;
+            if (c >= a.cols_pad) continue;
+            const int64_t gr = r + a.row_off, gc = c + a.col_off;
+            double v;
+            if (r < a.n1 && c < a.n2) {
+                v = coef * single_leaf<OP, L2, ND>(xa, xb[e], c0, c1);
+                if (a.diag != nullptr && gr == gc) v += a.diag[gr];
+            } else {
+                v = (a.pad_identity && gr == gc) ? 1.0 : 0.0;
+            }
+            a.out[r * a.ld + c] = v;
+        }
+    }
+}
+
+template <int OP, bool L2>
+static void launch_single_nd(cudaStream_t st, dim3 grid, const BuildArgs& a, double coef, double c0, double c1) {
+    switch (a.ndim) {
+        case 1: build_rect_kernel_single<OP, L2, 1><<<grid, 256, 0, st>>>(a, coef, c0, c1); break;
+        case 2: build_rect_kernel_single<OP, L2, 2><<<grid, 256, 0, st>>>(a, coef, c0, c1); break;
+        default: build_rect_kernel_single<OP, L2, 3><<<grid, 256, 0, st>>>(a, coef, c0, c1); break;
+    }
+}
+// true if the program is coef * (one stationary leaf) of a kind compiled above and the launch was made
+static bool launch_build_single(b200gp_ctx* ctx, dim3 grid, const KFast& F, const BuildArgs& a) {
+    if (ctx->build_fast < 2 || F.nleaf != 1 || F.nterm != 1 || F.mask[0] != 1 || a.ndim < 1 || a.ndim > 3 || grid.z != 1) return false;
+    const double coef = F.coef[0], p0 = F.p0[0];
+    const bool l2 = F.l2[0] != 0;
+    cudaStream_t st = ctx->stream;
+#define SINGLE(OPv, C0, C1) \
+    do { if (l2) launch_single_nd<OPv, true>(st, grid, a, coef, (C0), (C1)); else launch_single_nd<OPv, false>(st, grid, a, coef, (C0), (C1)); return true; } while (0)
+    switch (F.op[0]) {
+        case B200GP_OP_EXPSQUARED: SINGLE(B200GP_OP_EXPSQUARED, -0.5 / (p0 * p0), 0.0);
+        case B200GP_OP_EXP: SINGLE(B200GP_OP_EXP, 1.0 / p0, 0.0);
+        case B200GP_OP_MATERN32: SINGLE(B200GP_OP_MATERN32, SQRT3 / p0, 0.0);
+        case B200GP_OP_MATERN52: SINGLE(B200GP_OP_MATERN52, SQRT5 / p0, 1.0 / 3.0);
+        default: return false;
+    }
+#undef SINGLE
+}
+
+// single-leaf specialisation (option "build_fast" = 2, default), else the normal form when the program has one
+// ("build_fast" >= 1), else the interpreter (also for batched programs)
 static void launch_build_rect(b200gp_ctx* ctx, dim3 grid, const KProg& prog, const BuildArgs& a) {
     KFast F{};
-    if (a.progs == nullptr && ctx->build_fast != 0 && kprog_to_fast(prog, F))
+    if (a.progs == nullptr && ctx->build_fast != 0 && kprog_to_fast(prog, F)) {
+        if (launch_build_single(ctx, grid, F, a)) return;
         build_rect_kernel_t<true><<<grid, 256, 0, ctx->stream>>>(prog, F, a);
-    else
+    } else {
         build_rect_kernel_t<false><<<grid, 256, 0, ctx->stream>>>(prog, F, a);
+    }
 }
 
 // diag: out[i] = k(x_i, x_i)

@@ -1022,11 +1022,16 @@ __global__ void __launch_bounds__(THREADS_W, 1) i8_update_kernel_wide(const __gr
 // planes[s][row * ldq + col] for rows [r0, np), cols [c0, c0 + ncols); 16 columns per thread.
 // Also accumulates, per row, the dropped diagonal pairs  sum_{s+t>=S} 2^-(12+7(s+t)) sum_k q_s q_t  (exact integer
 // sums, fp64 weights) into corr[slot][row] with slot = 512-column group: two warps -> two commutative adds.
-__global__ void __launch_bounds__(256) cut_digits_kernel(const double* __restrict__ mat, int64_t ld, const double* __restrict__ rs,
-                                                         int64_t r0, int64_t nrows, int64_t c0, int64_t ncols,
-                                                         int8_t* planes, int64_t plane_stride, int64_t ldq, int S,
-                                                         double* corr /* [ncols/512 slots][np] for this panel */, int64_t np,
-                                                         int layout = 0) {
+// ST > 0: the plane count is a compile-time constant, so the digit table q[ST][16] lives in registers and every loop over
+// planes / digit pairs is unrolled; ST = 0 keeps the run-time count (q in local memory: 512 B of stack per thread, the
+// reason this kernel took 24 ms per factorisation at N = 65536 -- 5x its HBM time).
+template <int ST>
+__global__ void __launch_bounds__(256) cut_digits_kernel_t(const double* __restrict__ mat, int64_t ld, const double* __restrict__ rs,
+                                                           int64_t r0, int64_t nrows, int64_t c0, int64_t ncols,
+                                                           int8_t* planes, int64_t plane_stride, int64_t ldq, int S_rt,
+                                                           double* corr /* [ncols/512 slots][np] for this panel */, int64_t np,
+                                                           int layout) {
+    const int S = (ST > 0) ? ST : S_rt;
     const int64_t groups_per_row = ncols / 16;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = idx < nrows * groups_per_row;
@@ -1043,8 +1048,10 @@ __global__ void __launch_bounds__(256) cut_digits_kernel(const double* __restric
             x[4 * v + 0] = d.x * inv * 64.0; x[4 * v + 1] = d.y * inv * 64.0;
             x[4 * v + 2] = d.z * inv * 64.0; x[4 * v + 3] = d.w * inv * 64.0;
         }
-        int q[8][16];
-        for (int s = 0; s < S; ++s) {
+        int q[(ST > 0) ? ST : 8][16];
+#pragma unroll
+        for (int s = 0; s < ((ST > 0) ? ST : 8); ++s) {
+            if (ST == 0 && s >= S) break;
             uint32_t packed[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
@@ -1067,14 +1074,27 @@ __global__ void __launch_bounds__(256) cut_digits_kernel(const double* __restric
             *reinterpret_cast<uint4*>(planes + off) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
         // dropped pairs (s + t >= S), grouped by g = s + t so each group is one exact integer sum
-        for (int gsum = S; gsum <= 2 * (S - 1); ++gsum) {
-            int acc = 0;
-            for (int sdig = gsum - (S - 1); sdig <= S - 1; ++sdig) {
-                const int tdig = gsum - sdig;
+        if (ST > 0) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) acc += q[sdig][e] * q[tdig][e];
+            for (int gsum = ST; gsum <= 2 * (ST - 1); ++gsum) {
+                int acc = 0;
+#pragma unroll
+                for (int sdig = gsum - (ST - 1); sdig <= ST - 1; ++sdig) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc += q[sdig][e] * q[gsum - sdig][e];
+                }
+                dropped += (double)acc * __longlong_as_double((long long)(1023 - (12 + 7 * gsum)) << 52);
             }
-            dropped += (double)acc * __longlong_as_double((long long)(1023 - (12 + 7 * gsum)) << 52);
+        } else {
+            for (int gsum = S; gsum <= 2 * (S - 1); ++gsum) {
+                int acc = 0;
+                for (int sdig = gsum - (S - 1); sdig <= S - 1; ++sdig) {
+                    const int tdig = gsum - sdig;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc += q[sdig][e] * q[tdig][e];
+                }
+                dropped += (double)acc * __longlong_as_double((long long)(1023 - (12 + 7 * gsum)) << 52);
+            }
         }
     }
     // 32 threads (one warp) cover 512 columns of one row when ncols >= 512; reduce and add once per warp
@@ -1088,6 +1108,20 @@ __global__ void __launch_bounds__(256) cut_digits_kernel(const double* __restric
 }
 
 // test helper: plane-major [s][row][k] -> chunk-major [k / 128][row][s][128], 16 bytes per thread
+static void launch_cut_digits(cudaStream_t st, int64_t nthreads, const double* mat, int64_t ld, const double* rs, int64_t r0,
+                              int64_t nrows, int64_t c0, int64_t ncols, int8_t* planes, int64_t plane_stride, int64_t ldq, int S,
+                              double* corr, int64_t np, int layout) {
+    const unsigned grid = (unsigned)((nthreads + 255) / 256);
+#define CUT(STv) cut_digits_kernel_t<STv><<<grid, 256, 0, st>>>(mat, ld, rs, r0, nrows, c0, ncols, planes, plane_stride, ldq, S, corr, np, layout)
+    switch (S) {
+        case 8: CUT(8); break;
+        case 7: CUT(7); break;
+        case 6: CUT(6); break;
+        default: CUT(0); break;
+    }
+#undef CUT
+}
+
 __global__ void relayout_chunk_major_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst, int64_t rows, int64_t K, int S) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t per_plane = rows * (K / 16);
@@ -1664,8 +1698,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
                     const int64_t nrows = np - (cs + sw);
                     const int64_t nthreads = nrows * (sw / 16);
                     ProfTimer t(ctx, &ctx->prof.build_ms);
-                    oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, pan>>>(
-                        s->mat, ld, rs, cs + sw, nrows, cs, sw, planes, (int64_t)plane_stride, np, S,
+                    oz::launch_cut_digits(pan, nthreads, s->mat, ld, rs, cs + sw, nrows, cs, sw, planes, (int64_t)plane_stride, np, S,
                         corr + ((size_t)J * slots_per_panel + sp) * np, np, layout);
                     ctx->launches++;
                 }
@@ -1679,8 +1712,7 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
             const int64_t nrows = np - (c0 + kb);
             const int64_t nthreads = nrows * (kb / 16);
             ProfTimer t(ctx, &ctx->prof.build_ms);
-            oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, pan>>>(
-                s->mat, ld, rs, c0 + kb, nrows, c0, kb, planes, (int64_t)plane_stride, np, S,
+            oz::launch_cut_digits(pan, nthreads, s->mat, ld, rs, c0 + kb, nrows, c0, kb, planes, (int64_t)plane_stride, np, S,
                 corr + (size_t)J * slots_per_panel * np, np, layout);
             ctx->launches++;
         }
@@ -2102,9 +2134,8 @@ static void mg_panel_tail(b200gp_mg* m, int J) {
         const int64_t nrows = np - (c0 + kb);
         const int64_t nthreads = nrows * (kb / 16);
         ProfTimer t(_ctx, &_ctx->prof.build_ms);
-        oz::cut_digits_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, _ctx->stream>>>(
-            s->mat, s->ld, m->rs, c0 + kb, nrows, c0, kb, m->planes, (int64_t)m->plane_stride, np, m->S,
-            m->corr + (size_t)J * m->slots_per_panel * np, np);
+        oz::launch_cut_digits(_ctx->stream, nthreads, s->mat, s->ld, m->rs, c0 + kb, nrows, c0, kb, m->planes,
+                              (int64_t)m->plane_stride, np, m->S, m->corr + (size_t)J * m->slots_per_panel * np, np, 0);
         _ctx->launches++;
     }
     if (m->streaming) {

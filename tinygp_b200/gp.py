@@ -44,7 +44,7 @@ class GaussianProcess:
         self.mean = mean_value
         if noise is None:  # gp.py:96-99
             diag = _default_diag(self.mean) if diag is None else diag
-            noise = Diagonal(diag=np.broadcast_to(np.asarray(diag, dtype=np.float64), self.mean.shape).copy())
+            noise = Diagonal(diag=_as_full_diag(diag, self.mean.shape))
         self.noise = noise
         if solver is None:  # gp.py:101-105
             solver = QuasisepSolver if (isinstance(covariance_value, SymmQSM) or isinstance(kernel, Quasisep)) else DirectSolver
@@ -174,6 +174,15 @@ class ConditionResult(NamedTuple):
     """gp.py:364-385"""
     log_probability: Any
     gp: GaussianProcess
+
+
+def _as_full_diag(diag, shape):
+    """jnp.broadcast_to(diag, shape) of gp.py:98; an array that already has the full shape is passed through as it is (no
+    copy: a caller's page-locked buffer stays page-locked all the way to the device copy)"""
+    d = np.asarray(diag, dtype=np.float64)
+    if d.shape == tuple(shape) and d.flags.c_contiguous:
+        return d
+    return np.broadcast_to(d, shape).copy()
 
 
 def _default_diag(reference):  # gp.py:388-393

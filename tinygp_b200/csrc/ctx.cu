@@ -190,6 +190,7 @@ static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kO
     {"ozaki_l2promo", &b200gp_ctx::oz_l2promo},
     {"ozaki_subpanel", &b200gp_ctx::oz_subpanel},
     {"ozaki_splitk", &b200gp_ctx::oz_splitk},
+    {"mg_splitk", &b200gp_ctx::mg_splitk},
     {"ozaki_splitk_force", &b200gp_ctx::oz_splitk_force},
 };
 

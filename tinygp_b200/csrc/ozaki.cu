@@ -2070,7 +2070,9 @@ int b200gp_mg_update_rows(b200gp_mg* m, int J, int64_t r0, int64_t r1) {
         a.tiles_n = (int)((kb + oz::TN - 1) / oz::TN);
         a.K = (int)c0; a.k_begin = 0; a.S = m->S; a.n_rows = np; a.skip_upper = 1; a.error_flag = m->err;
         a.prefetch = (int)_ctx->oz_prefetch; a.pg_single = (_ctx->oz_pairing == 2);
-        a.no_split = 1;   // the split depends on the tile count of this rank's rows: keep the G-independent summation order
+        // the tail split depends on the tile count of THIS rank's rows, so with it the last bits of the result depend on the
+        // rank count (option "mg_splitk" = 0 restores the rank-count-independent summation order: bit-identical for any G)
+        a.no_split = (_ctx->mg_splitk == 0) ? 1 : 0;
         ProfTimer t(_ctx, &_ctx->prof.syrk_ms);
         oz::launch_update(_ctx, m->maps, a);
         _ctx->prof.syrk_flop += 2.0 * (double)(r1 - r0) * (double)kb * (double)c0;

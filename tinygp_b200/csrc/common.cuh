@@ -61,6 +61,7 @@ struct b200gp_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int num_sms = 148;
     int64_t peak_iters = 4096;  // loop length of the fp64 peak micro-benchmarks
+    int64_t qs_chunk_max = 128; // upper end of the automatic chunk-length search of the quasiseparable scans
     int64_t qs_chunk = 0;       // points per thread in the quasiseparable scans (0 = chosen per problem size, see qs_create_impl)
     int64_t qsm_chunk = 0;      // points per warp in the QSM-algebra scans (qsm.cu); 0 = chosen per problem size
     int64_t qsm_sequential_redos = 0;   // read-only counter: Riccati scans redone sequentially after the consistency check (qsm.cu run_ric)

@@ -170,6 +170,7 @@ static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kO
     {"peak_iters", &b200gp_ctx::peak_iters},
     {"qs_tree", &b200gp_ctx::qs_tree},
     {"qs_chunk", &b200gp_ctx::qs_chunk},
+    {"qs_chunk_max", &b200gp_ctx::qs_chunk_max},
     {"qsm_chunk", &b200gp_ctx::qsm_chunk},
     {"qsm_sequential_redos", &b200gp_ctx::qsm_sequential_redos},
     {"build_fast", &b200gp_ctx::build_fast},

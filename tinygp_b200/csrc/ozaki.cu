@@ -1026,7 +1026,7 @@ __global__ void __launch_bounds__(THREADS_W, 1) i8_update_kernel_wide(const __gr
 // planes / digit pairs is unrolled; ST = 0 keeps the run-time count (q in local memory: 512 B of stack per thread, the
 // reason this kernel took 24 ms per factorisation at N = 65536 -- 5x its HBM time).
 template <int ST>
-__global__ void __launch_bounds__(256) cut_digits_kernel_t(const double* __restrict__ mat, int64_t ld, const double* __restrict__ rs,
+__global__ void __launch_bounds__(256, 2) cut_digits_kernel_t(const double* __restrict__ mat, int64_t ld, const double* __restrict__ rs,
                                                            int64_t r0, int64_t nrows, int64_t c0, int64_t ncols,
                                                            int8_t* planes, int64_t plane_stride, int64_t ldq, int S_rt,
                                                            double* corr /* [ncols/512 slots][np] for this panel */, int64_t np,
@@ -1038,7 +1038,65 @@ __global__ void __launch_bounds__(256) cut_digits_kernel_t(const double* __restr
     const int64_t row = r0 + (active ? idx / groups_per_row : 0);
     const int64_t col = c0 + (active ? (idx % groups_per_row) * 16 : 0);
     double dropped = 0.0;
-    if (active) {
+    if (active && ST > 0) {
+        // two halves of 8 columns: the digit table of a half (ST x 8 ints) and the packed words of the first half are all
+        // that stays live, the dropped-pair sums are carried across the halves as ST - 1 exact integer accumulators
+        const double inv = 1.0 / rs[row];  // power of two: exact
+        const double4* src = reinterpret_cast<const double4*>(mat + row * ld + col);
+        constexpr int SS = (ST > 0) ? ST : 1;
+        uint32_t pk[SS][4];
+        int acc[SS];                       // acc[g - ST] for g = ST .. 2 ST - 2 (last entry unused)
+#pragma unroll
+        for (int g = 0; g < SS; ++g) acc[g] = 0;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            double x[8];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const double4 d = src[2 * hf + v];
+                x[4 * v + 0] = d.x * inv * 64.0; x[4 * v + 1] = d.y * inv * 64.0;
+                x[4 * v + 2] = d.z * inv * 64.0; x[4 * v + 3] = d.w * inv * 64.0;
+            }
+            int q[SS][8];
+#pragma unroll
+            for (int sd = 0; sd < SS; ++sd) {
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    uint32_t wv = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        double& xx = x[4 * v + e];
+                        double qd = rint(xx);
+                        qd = fmin(fmax(qd, -127.0), 127.0);   // |x| <= 64 (+ rounding) by construction
+                        xx = (xx - qd) * 128.0;               // exact
+                        const int qi = (int)qd;
+                        q[sd][4 * v + e] = qi;
+                        wv |= ((uint32_t)(uint8_t)(int8_t)qi) << (8 * e);
+                    }
+                    pk[sd][2 * hf + v] = wv;
+                }
+            }
+            // dropped pairs (s + t >= S), grouped by g = s + t so each group is one exact integer sum
+#pragma unroll
+            for (int gsum = SS; gsum <= 2 * (SS - 1); ++gsum) {
+#pragma unroll
+                for (int sdig = gsum - (SS - 1); sdig <= SS - 1; ++sdig) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[gsum - SS] += q[sdig][e] * q[gsum - sdig][e];
+                }
+            }
+        }
+#pragma unroll
+        for (int sd = 0; sd < SS; ++sd) {
+            // plane-major [s][row][k], or chunk-major [k / 128][row][s][128] (np rows per chunk slab)
+            const int64_t off = (layout == 1) ? (((col >> 7) * np + row) * S + sd) * 128 + (col & 127)
+                                              : (int64_t)sd * plane_stride + row * ldq + col;
+            *reinterpret_cast<uint4*>(planes + off) = make_uint4(pk[sd][0], pk[sd][1], pk[sd][2], pk[sd][3]);
+        }
+#pragma unroll
+        for (int gsum = SS; gsum <= 2 * (SS - 1); ++gsum)
+            dropped += (double)acc[gsum - SS] * __longlong_as_double((long long)(1023 - (12 + 7 * gsum)) << 52);
+    } else if (active) {
         const double inv = 1.0 / rs[row];  // power of two: exact
         double x[16];
         const double4* src = reinterpret_cast<const double4*>(mat + row * ld + col);
@@ -1048,10 +1106,8 @@ __global__ void __launch_bounds__(256) cut_digits_kernel_t(const double* __restr
             x[4 * v + 0] = d.x * inv * 64.0; x[4 * v + 1] = d.y * inv * 64.0;
             x[4 * v + 2] = d.z * inv * 64.0; x[4 * v + 3] = d.w * inv * 64.0;
         }
-        int q[(ST > 0) ? ST : 8][16];
-#pragma unroll
-        for (int s = 0; s < ((ST > 0) ? ST : 8); ++s) {
-            if (ST == 0 && s >= S) break;
+        int q[8][16];
+        for (int s = 0; s < S; ++s) {
             uint32_t packed[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
@@ -1068,33 +1124,18 @@ __global__ void __launch_bounds__(256) cut_digits_kernel_t(const double* __restr
                 }
                 packed[v] = wv;
             }
-            // plane-major [s][row][k], or chunk-major [k / 128][row][s][128] (np rows per chunk slab)
             const int64_t off = (layout == 1) ? (((col >> 7) * np + row) * S + s) * 128 + (col & 127)
                                               : (int64_t)s * plane_stride + row * ldq + col;
             *reinterpret_cast<uint4*>(planes + off) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
-        // dropped pairs (s + t >= S), grouped by g = s + t so each group is one exact integer sum
-        if (ST > 0) {
+        for (int gsum = S; gsum <= 2 * (S - 1); ++gsum) {
+            int acc = 0;
+            for (int sdig = gsum - (S - 1); sdig <= S - 1; ++sdig) {
+                const int tdig = gsum - sdig;
 #pragma unroll
-            for (int gsum = ST; gsum <= 2 * (ST - 1); ++gsum) {
-                int acc = 0;
-#pragma unroll
-                for (int sdig = gsum - (ST - 1); sdig <= ST - 1; ++sdig) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) acc += q[sdig][e] * q[gsum - sdig][e];
-                }
-                dropped += (double)acc * __longlong_as_double((long long)(1023 - (12 + 7 * gsum)) << 52);
+                for (int e = 0; e < 16; ++e) acc += q[sdig][e] * q[tdig][e];
             }
-        } else {
-            for (int gsum = S; gsum <= 2 * (S - 1); ++gsum) {
-                int acc = 0;
-                for (int sdig = gsum - (S - 1); sdig <= S - 1; ++sdig) {
-                    const int tdig = gsum - sdig;
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) acc += q[sdig][e] * q[tdig][e];
-                }
-                dropped += (double)acc * __longlong_as_double((long long)(1023 - (12 + 7 * gsum)) << 52);
-            }
+            dropped += (double)acc * __longlong_as_double((long long)(1023 - (12 + 7 * gsum)) << 52);
         }
     }
     // 32 threads (one warp) cover 512 columns of one row when ncols >= 512; reduce and add once per warp

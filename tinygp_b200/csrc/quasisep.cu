@@ -296,14 +296,16 @@ static b200gp_qs* qs_create_impl(b200gp_ctx* ctx, const double* comps, int ncomp
     s->model.chunk = (int)ctx->qs_chunk;
     if (ctx->qs_chunk == 0) {
         // auto: the scan kernels are chains of dependent fp64 work per thread, so a launch costs (number of waves) x (chunk
-        // length); pick the multiple of 4 in [48, 128] that minimises it for 3 resident 128-thread blocks per SM
+        // length); pick the multiple of 4 in [48, qs_chunk_max] that minimises it for 3 resident 128-thread blocks per SM.
+        // On ties the LONGER chunk wins: same point-wise time, fewer chunk composites for the scan over them.
         const int64_t per_wave = 3 * (int64_t)ctx->num_sms;
         int best = 64;
         int64_t best_cost = INT64_MAX;
-        for (int c = 48; c <= 128; c += 4) {
+        const int cmax = (int)((ctx->qs_chunk_max >= 48) ? ctx->qs_chunk_max : 128);
+        for (int c = 48; c <= cmax; c += 4) {
             const int64_t nblocks = ((n + c - 1) / c + QS_THREADS - 1) / QS_THREADS;
             const int64_t cost = ((nblocks + per_wave - 1) / per_wave) * c;
-            if (cost < best_cost) { best_cost = cost; best = c; }
+            if (cost <= best_cost) { best_cost = cost; best = c; }
         }
         s->model.chunk = best;
     }

@@ -61,7 +61,7 @@ struct b200gp_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int num_sms = 148;
     int64_t peak_iters = 4096;  // loop length of the fp64 peak micro-benchmarks
-    int64_t qs_chunk_max = 128; // upper end of the automatic chunk-length search of the quasiseparable scans
+    int64_t qs_chunk_max = 256; // upper end of the automatic chunk-length search of the quasiseparable scans
     int64_t qs_chunk = 0;       // points per thread in the quasiseparable scans (0 = chosen per problem size, see qs_create_impl)
     int64_t qsm_chunk = 0;      // points per warp in the QSM-algebra scans (qsm.cu); 0 = chosen per problem size
     int64_t qsm_sequential_redos = 0;   // read-only counter: Riccati scans redone sequentially after the consistency check (qsm.cu run_ric)
@@ -90,6 +90,14 @@ struct b200gp_ctx {
     int64_t panel_overlap = 2;  // 2 (default): look-ahead, diagonal-block chain on a high-priority stream; 1: rows below the diagonal
                                 // tile on a side stream while potf2 runs; 0: serial
     cudaStream_t stream3 = nullptr;
+    // fused log_probability: residual whose forward substitution dense_factor_ozaki runs panel by panel on a side stream,
+    // under the int8 update of the NEXT block column (set by dense_logp_impl, consumed by the factorisation)
+    const double* fuse_resid = nullptr;   // n values, host or device
+    int64_t fuse_n = 0;
+    double* fuse_y = nullptr;             // np, owned by the caller of the factorisation afterwards (ctx->alloc)
+    double* fuse_x = nullptr;             // np: L^-1 resid once the factorisation has returned
+    int64_t solve_overlap = 1;            // option: 1 = hide the forward substitution of log_probability under the factorisation
+    cudaStream_t stream_solve = nullptr;
     cudaStream_t stream_hi = nullptr;   // high-priority stream of the look-ahead panel chain (panel_overlap = 2)
     int64_t oz_prefetch = 0;    // L2 prefetch distance (K-chunks of 128) of the int8 update's TMA producer
     int64_t oz_pairing = 1;    // int8 update: 1 = accumulate two digit groups at once (default: 16 instead of 28 operand-stage loads

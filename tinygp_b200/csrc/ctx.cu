@@ -154,6 +154,7 @@ int b200gp_destroy(b200gp_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+    if (ctx->stream_solve) cudaStreamDestroy(ctx->stream_solve);
     if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -191,6 +192,7 @@ static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kO
     {"ozaki_l2promo", &b200gp_ctx::oz_l2promo},
     {"ozaki_subpanel", &b200gp_ctx::oz_subpanel},
     {"ozaki_splitk", &b200gp_ctx::oz_splitk},
+    {"solve_overlap", &b200gp_ctx::solve_overlap},
     {"mg_splitk", &b200gp_ctx::mg_splitk},
     {"ozaki_splitk_force", &b200gp_ctx::oz_splitk_force},
 };

@@ -1611,15 +1611,32 @@ static double dense_logp_impl(b200gp_ctx* ctx, const KProg& P, const double* X, 
         if (ctx->oz_slices > 0 && npad >= ctx->oz_min_n && need > 150e9)
             return ozaki_logp_streaming(ctx, P, X, n, ndim, diag, resid, (int)ctx->oz_slices);
     }
-    b200gp_dense* s = dense_factor_from_prog(ctx, P, X, n, ndim, diag, true);
+    // the int8 factorisation runs the forward substitution itself, panel by panel on a side stream under the update of
+    // the next block column (option "solve_overlap"); it leaves L^-1 resid in ctx->fuse_x
+    ctx->fuse_resid = (ctx->solve_overlap != 0) ? resid : nullptr;
+    ctx->fuse_n = n;
+    ctx->fuse_y = ctx->fuse_x = nullptr;
+    b200gp_dense* s = nullptr;
+    try {
+        s = dense_factor_from_prog(ctx, P, X, n, ndim, diag, true);
+    } catch (...) {
+        ctx->fuse_resid = nullptr;
+        throw;
+    }
+    ctx->fuse_resid = nullptr;
     double logp;
     try {
         const int64_t np = s->np;
-        double* y = (double*)ctx->alloc((size_t)np * 8);
-        double* x = (double*)ctx->alloc((size_t)np * 8);
-        CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)np * 8, ctx->stream));
-        CUDA_CHECK(cudaMemcpyAsync(y, resid, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
-        dense_solve_vec_dev(s, y, x, false);
+        double* y = ctx->fuse_y;
+        double* x = ctx->fuse_x;
+        ctx->fuse_y = ctx->fuse_x = nullptr;
+        if (x == nullptr) {     // native fp64 path (or the overlap is off): substitute now
+            y = (double*)ctx->alloc((size_t)np * 8);
+            x = (double*)ctx->alloc((size_t)np * 8);
+            CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)np * 8, ctx->stream));
+            CUDA_CHECK(cudaMemcpyAsync(y, resid, (size_t)n * 8, cudaMemcpyDefault, ctx->stream));
+            dense_solve_vec_dev(s, y, x, false);
+        }
         const double ss = dense_sumsq_dev(ctx, x, n);
         const double ld = dense_logdet_half(s);
         logp = -0.5 * ss - (ld + 0.5 * (double)n * log(2.0 * M_PI));   // gp.py:313-316, direct.py:61-64

@@ -1584,6 +1584,7 @@ struct BuildRegionArgs { int64_t r0, r1, c0, ncols; };
 void dense_build_rows(b200gp_dense* s, const BuildRegionArgs& a);                        // dense.cu
 void dense_build_region(b200gp_dense* s, int64_t r0, int64_t c0, int64_t ncols);          // dense.cu
 double dense_kernel_diag_value(const KProg& P);                                           // dense.cu
+void dense_trsv_fwd_blocks(b200gp_dense* s, double* y_dev, double* x_dev, int j_begin, int j_end);   // dense.cu
 
 void dense_factor_ozaki(b200gp_dense* s, int S) {
     b200gp_ctx* ctx = s->ctx;
@@ -1634,6 +1635,22 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
         pan = ctx->stream2;
     }
     const int ncol = (int)((np + NB - 1) / NB);
+    // fused forward substitution (log_probability): y <- resid; after panel J is final its 128-blocks are substituted on a
+    // side stream while the int8 update of column J + 1 runs (the substitution kernels fit beside the update's CTAs)
+    cudaStream_t sol = nullptr;
+    cudaEvent_t ev_panel = nullptr;
+    double *fy = nullptr, *fx = nullptr;
+    if (ctx->fuse_resid != nullptr && !lookahead) {
+        if (!ctx->stream_solve) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream_solve, cudaStreamNonBlocking));
+        sol = ctx->stream_solve;
+        fy = (double*)ctx->alloc((size_t)np * 8);
+        fx = (double*)ctx->alloc((size_t)np * 8);
+        CUDA_CHECK(cudaMemsetAsync(fy, 0, (size_t)np * 8, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(fy, ctx->fuse_resid, (size_t)ctx->fuse_n * 8, cudaMemcpyDefault, ctx->stream));
+        ev_panel = ctx->get_event();
+        CUDA_CHECK(cudaEventRecord(ev_panel, ctx->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(sol, ev_panel, 0));
+    }
     std::vector<cudaEvent_t> ev_upd(ncol), ev_cut(ncol);
     if (lookahead) {
         for (int j = 0; j < ncol; ++j) { ev_upd[j] = ctx->get_event(); ev_cut[j] = ctx->get_event(); }
@@ -1759,8 +1776,26 @@ void dense_factor_ozaki(b200gp_dense* s, int S) {
         }
         }
         if (lookahead) CUDA_CHECK(cudaEventRecord(ev_cut[J], pan));
+        if (sol) {   // columns [c0, c0 + kb) of L and their inverted diagonal blocks are final on `pan`
+            CUDA_CHECK(cudaEventRecord(ev_panel, pan));
+            CUDA_CHECK(cudaStreamWaitEvent(sol, ev_panel, 0));
+            ctx->stream = sol;
+            try {
+                dense_trsv_fwd_blocks(s, fy, fx, (int)(c0 / TILE), (int)((c0 + kb) / TILE));
+            } catch (...) {
+                ctx->stream = upd;
+                throw;
+            }
+            ctx->stream = pan;
+        }
     }
     ctx->stream = upd;
+    if (sol) {   // join
+        CUDA_CHECK(cudaEventRecord(ev_panel, sol));
+        CUDA_CHECK(cudaStreamWaitEvent(upd, ev_panel, 0));
+        ctx->event_pool.push_back(ev_panel);
+        ctx->fuse_y = fy; ctx->fuse_x = fx;
+    }
     CUDA_CHECK(cudaGetLastError());
     if (ev_build) ctx->event_pool.push_back(ev_build);
     if (lookahead) {

@@ -411,9 +411,13 @@ def run_ours(args, rank, local_rank, world):
                 "d2h_bytes_per_step": int(n * 8 + n * 8 + 8 + 4)},
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {"syrk": prof["syrk_ms"] / args.steps, "panel": prof["panel_ms"] / args.steps,
-                               "build": prof["build_ms"] / args.steps, "solve": prof["solve_ms"] / args.steps},
+                               "build": prof["build_ms"] / args.steps},
         "per_step_ms": per_step_ms,
     }
+    # the forward substitution: a serial phase of its own (13 ms at N = 65536), or -- option solve_overlap, default -- launches
+    # on a side stream that are IN FLIGHT under the int8 update of the next block column (event time = residence, not cost)
+    solve_key = "solve_in_flight_under_update" if (args.slices > 0 and ctx.get_option("solve_overlap")) else "solve"
+    line["kernel_ms_per_step"][solve_key] = prof["solve_ms"] / args.steps
     if sub_records:
         line["configs"] = sub_records
     if sharded is not None:

@@ -328,7 +328,7 @@ int b200gp_qsm_elementwise_mul(b200gp_qsm* a, b200gp_qsm* b, b200gp_qsm** out); 
 int b200gp_qsm_mul(b200gp_qsm* a, b200gp_qsm* b, b200gp_qsm** out);
 int b200gp_qsm_gram(b200gp_qsm* a, b200gp_qsm** out);                            /* SquareQSM.gram  core.py:424-434 */
 /* LowerTriQSM.inv (core.py:310-317), UpperTriQSM.inv (:362-363), SymmQSM.inv = symm_inv (ops.py:403-460);
- * SquareQSM.inv (core.py:436-478) is refused */
+ * SquareQSM.inv (core.py:436-478: sequential, one warp) */
 int b200gp_qsm_inv(b200gp_qsm* a, b200gp_qsm** out);
 /* SymmQSM.cholesky (core.py:522-537, ops.py:352-365).  *info = 1-based index of the first non-positive pivot (the
  * generators are NaN from there on, like the reference's), 0 if none */

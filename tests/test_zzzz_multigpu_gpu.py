@@ -16,7 +16,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, nb, streaming, split, q, mg_splitk=1):
+def _worker(rank, world, port, n, nb, streaming, split, q, mg_splitk=0):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -75,7 +75,7 @@ def test_sharded_two_ranks_matches_oracle_and_single_rank(streaming, split, mg_s
         assert "in-place" in res[0][2]
         assert ("broadcast" in res[0][2]) == split
     # the same library, one rank: bit-identical when every tile keeps one K range (integer products are exact and the panel
-    # work is replicated); with the tail split-K on (default) the last bits depend on how many tiles a rank has
+    # work is replicated); with the tail split-K on (option mg_splitk) the last bits depend on how many tiles a rank has
     from tinygp_b200 import _cabi
     c = _cabi.get_context()
     c.set_option("nb", nb)

@@ -75,8 +75,8 @@ struct b200gp_ctx {
     int64_t panel_fused = 0;    // 1: one launch per 128-column step of the panel factorisation (potf2 + trtri + solve)
     int64_t oz_splitk = 1024;   // int8 update (CTA-pair kernel): > 0 = split K over idle SM pairs, value = fixed cost of a tile in K
                                 // columns for the policy (ozaki.cu choose_splitk); 0 = one K range per tile
-    int64_t mg_splitk = 1;       // sharded path: 1 = tail split-K on every rank's rows too (a rank has 1/G of the tiles: the last wave
-                                 // matters G times more), 0 = one K range per tile (bit-identical results for every rank count)
+    int64_t mg_splitk = 0;       // sharded path: 0 (default) = one K range per tile: bit-identical results for every rank count;
+                                 // 1 = tail split-K on every rank's rows too (2 GPUs, N = 131072: update 2791 -> 2738 ms, step not faster)
     int64_t oz_splitk_force = 0; // > 1: that many K segments in every CTA-pair launch (tests)
     int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
     // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA.  7 planes = 48 bits under the

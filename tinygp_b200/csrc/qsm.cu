@@ -542,6 +542,25 @@ static b200gp_qsm* op_symm_inv(const b200gp_qsm* S) {
     return r.release();
 }
 
+// core.py:436-478 (sequential, one warp)
+static b200gp_qsm* op_square_inv(const b200gp_qsm* M) {
+    b200gp_ctx* c = M->ctx; const int64_t n = M->n; const int ml = M->lo.m, mu = M->up.m;
+    BufP ig = qnew(c, (size_t)n);
+    QTri lo = tri_new(c, n, ml), up = tri_new(c, n, mu);          // lower = (t, s, ell), upper = (u, v, del)
+    BufP lam = qnew(c, (size_t)n);
+    qsm::SqInvArgs a{};
+    a.n = n; a.ml = ml; a.mu = mu; a.d = M->d->p;
+    a.p = M->lo.p->p; a.q = M->lo.q->p; a.a = M->lo.a->p; a.h = M->up.p->p; a.g = M->up.q->p; a.b = M->up.a->p;
+    a.ig = ig->p; a.s = lo.q->p; a.ell = lo.a->p; a.v = up.q->p; a.del = up.a->p;
+    a.lam = lam->p; a.t = lo.p->p; a.u = up.p->p;
+    const int wsd = qsm::sqinv_smem_doubles(ml, mu);
+    run_single<qsm::SqInvArgs, qsm::sqinv_forward>(c, a, wsd);
+    run_single<qsm::SqInvArgs, qsm::sqinv_backward>(c, a, wsd);
+    std::unique_ptr<b200gp_qsm> r(q_new(c, n));
+    r->d = lam; r->lo = lo; r->up = up;
+    return r.release();
+}
+
 // =========================================================================================================================
 extern "C" {
 
@@ -718,8 +737,7 @@ int b200gp_qsm_inv(b200gp_qsm* a, b200gp_qsm** out) {
             r->d = vec_new(_ctx, a->n, a->d->p, nullptr, 0, 0, 2);
             *out = r.release();
         } break;
-        case B200GP_QSM_SQUARE:
-            throw GpError("qsm_inv: SquareQSM.inv (core.py:436-478) is not implemented by the B200 backend");
+        case B200GP_QSM_SQUARE: *out = op_square_inv(a); break;
         default: throw GpError("qsm_inv: a strictly triangular QSM has no inverse");
     }
     API_END

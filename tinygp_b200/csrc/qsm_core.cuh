@@ -463,4 +463,101 @@ QHD void ric_phase3(Lane L, const RicArgs& a, int64_t c, double* ws) {
     if (a.fend) vcopy(L, a.fend + c * (int64_t)mm2, f, mm2);
 }
 
+// =====================================================================================================================
+// 4. SquareQSM.inv (core.py:436-478): a forward pass with a NON-symmetric Riccati carry f (ml x mu) and a backward pass
+//    with carry z (mu x ml), both written exactly as the reference's scans and run by ONE warp over the whole series
+//    (no chunk decomposition: nothing on the GP path calls it; it completes the class).
+//    lower = (p, q, a) of order ml; upper = (h, g, b) = (upper.p, upper.q, upper.a) of order mu.
+// =====================================================================================================================
+struct SqInvArgs {
+    int64_t n; int ml, mu;
+    const double *d, *p, *q, *a, *h, *g, *b;
+    double *ig, *s, *ell, *v, *del;        // forward outputs: n, n x ml, n x ml x ml, n x mu, n x mu x mu
+    double *lam, *t, *u;                   // backward outputs: n, n x ml, n x mu
+};
+QHD int sqinv_smem_doubles(int ml, int mu) { return 4 * ml * mu + ml * ml + mu * mu + 6 * (ml + mu); }
+
+QHD void sqinv_forward(Lane L, const SqInvArgs& a, double* ws) {
+    const int ml = a.ml, mu = a.mu;
+    double* f = ws; double* fbk = f + ml * mu; double* T = fbk + ml * mu; double* am = T + 2 * ml * mu; double* bm = am + ml * ml;
+    double* pv = bm + mu * mu; double* qv = pv + ml; double* left = qv + ml; double* fhk = left + ml;
+    double* hv = fhk + ml; double* gv = hv + mu; double* right = gv + mu;
+    vzero(L, f, ml * mu);
+    QSYNC();
+    for (int64_t k = 0; k < a.n; ++k) {
+        vcopy(L, am, a.a + k * ml * ml, ml * ml); vcopy(L, bm, a.b + k * mu * mu, mu * mu);
+        vcopy(L, pv, a.p + k * ml, ml); vcopy(L, qv, a.q + k * ml, ml);
+        vcopy(L, hv, a.h + k * mu, mu); vcopy(L, gv, a.g + k * mu, mu);
+        QSYNC();
+        mv(L, fhk, f, mu, 1, hv, ml, mu);                                     // fhk = f h
+        mm(L, fbk, mu, f, mu, 1, bm, 1, mu, ml, mu, mu, 1.0, false);          // fbk = f b^T
+        const double igk = 1.0 / (a.d[k] - dot_all(pv, fhk, ml));
+        for (int i = L.lane; i < ml; i += L.nl) {                             // left = q - a fhk
+            double t2 = qv[i];
+            for (int l = 0; l < ml; ++l) t2 -= am[i * ml + l] * fhk[l];
+            left[i] = t2;
+            a.s[k * ml + i] = igk * t2;
+        }
+        for (int j = L.lane; j < mu; j += L.nl) {                             // right = g - p fbk
+            double t2 = gv[j];
+            for (int l = 0; l < ml; ++l) t2 -= pv[l] * fbk[l * mu + j];
+            right[j] = t2;
+            a.v[k * mu + j] = igk * t2;
+        }
+        if (L.lane == 0) a.ig[k] = igk;
+        QSYNC();
+        for (int e = L.lane; e < ml * ml; e += L.nl) a.ell[k * ml * ml + e] = am[e] - igk * left[e / ml] * pv[e % ml];
+        for (int e = L.lane; e < mu * mu; e += L.nl) a.del[k * mu * mu + e] = bm[e] - igk * right[e / mu] * hv[e % mu];
+        for (int e = L.lane; e < ml * mu; e += L.nl) {                        // f <- a fbk + ig left (x) right
+            const int i = e / mu, j = e - i * mu;
+            double t2 = igk * left[i] * right[j];
+            for (int l = 0; l < ml; ++l) t2 += am[i * ml + l] * fbk[l * mu + j];
+            T[e] = t2;
+        }
+        QSYNC();
+        vcopy(L, f, T, ml * mu);
+        QSYNC();
+    }
+}
+QHD void sqinv_backward(Lane L, const SqInvArgs& a, double* ws) {
+    const int ml = a.ml, mu = a.mu;
+    double* z = ws; double* zak = z + ml * mu; double* T = zak + ml * mu; double* am = T + 2 * ml * mu; double* bm = am + ml * ml;
+    double* pv = bm + mu * mu; double* sv = pv + ml; double* tk = sv + ml; double* spare = tk + ml;
+    double* hv = spare + ml; double* vv = hv + mu; double* zsk = vv + mu; double* uk = zsk + mu;
+    vzero(L, z, mu * ml);
+    QSYNC();
+    for (int64_t k = a.n - 1; k >= 0; --k) {
+        vcopy(L, am, a.a + k * ml * ml, ml * ml); vcopy(L, bm, a.b + k * mu * mu, mu * mu);
+        vcopy(L, pv, a.p + k * ml, ml); vcopy(L, sv, a.s + k * ml, ml);
+        vcopy(L, hv, a.h + k * mu, mu); vcopy(L, vv, a.v + k * mu, mu);
+        QSYNC();
+        mv(L, zsk, z, ml, 1, sv, mu, ml);                                     // zsk = z s      (z: mu x ml)
+        mm(L, zak, ml, z, ml, 1, am, ml, 1, mu, ml, ml, 1.0, false);          // zak = z a
+        const double lk = a.ig[k] + dot_all(vv, zsk, mu);
+        for (int i = L.lane; i < ml; i += L.nl) {                             // t = v zak - l p
+            double t2 = -lk * pv[i];
+            for (int l = 0; l < mu; ++l) t2 += vv[l] * zak[l * ml + i];
+            tk[i] = t2;
+            a.t[k * ml + i] = t2;
+        }
+        for (int j = L.lane; j < mu; j += L.nl) {                             // u = b^T zsk - l h
+            double t2 = -lk * hv[j];
+            for (int l = 0; l < mu; ++l) t2 += bm[l * mu + j] * zsk[l];
+            uk[j] = t2;
+            a.u[k * mu + j] = t2;
+        }
+        if (L.lane == 0) a.lam[k] = lk;
+        QSYNC();
+        for (int e = L.lane; e < mu * ml; e += L.nl) {                        // z <- b^T zak - (u + l h) (x) p - h (x) t
+            const int i = e / ml, j = e - i * ml;
+            double t2 = -(uk[i] + lk * hv[i]) * pv[j] - hv[i] * tk[j];
+            for (int l = 0; l < mu; ++l) t2 += bm[l * mu + i] * zak[l * ml + j];
+            T[e] = t2;
+        }
+        QSYNC();
+        vcopy(L, z, T, mu * ml);
+        QSYNC();
+    }
+}
+
 }  // namespace qsm

@@ -312,7 +312,7 @@ class SquareQSM(_WithDiag):
         return self._unary(self._ctx.lib.b200gp_qsm_gram)             # core.py:424-434
 
     def inv(self):
-        return self._unary(self._ctx.lib.b200gp_qsm_inv)              # core.py:436-478: refused by the backend
+        return self._unary(self._ctx.lib.b200gp_qsm_inv)              # core.py:436-478 (sequential on the device)
 
     def __iter__(self):
         return iter((self.diag, self.lower, self.upper))

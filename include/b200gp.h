@@ -149,6 +149,10 @@ int b200gp_dense_create_dev(b200gp_ctx* ctx, const double* prog, int n_instr,
                             const double* X_dev, int64_t n, int ndim, const double* diag_dev,
                             b200gp_dense** out, int* info);
 /* __init__ with covariance= given (direct.py:50-53): factor a host n x n matrix. */
+/* DirectSolver.__init__ fused with the data term of log_probability (gp.py:313-316): *sumsq = sum((L^-1 resid)^2); the
+ * forward substitution runs panel by panel under the factorisation (resid: n values, host or device) */
+int b200gp_dense_create_with_resid(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
+                                   const double* diag, const double* resid, b200gp_dense** out, int* info, double* sumsq);
 int b200gp_dense_create_from_cov(b200gp_ctx* ctx, const double* cov, int64_t n,
                                  b200gp_dense** out, int* info);
 int b200gp_dense_free(b200gp_dense* s);

@@ -264,6 +264,19 @@ class MockLib:
         self._new(d, href)
         return 0
 
+    def b200gp_dense_create_with_resid(self, ctx, prog, n_instr, X, n, ndim, diag, resid, href, info, sumsq):
+        rc = self.b200gp_dense_create(ctx, prog, n_instr, X, n, ndim, diag, href, info)
+        self.calls[-1] = "dense_create_with_resid"
+        d = self.objects[out(href).value]
+        r = arr(resid, (n,)).copy()
+        with np.errstate(all="ignore"):
+            if np.all(np.isfinite(d.L)):
+                a = sla.solve_triangular(d.L, r, lower=True, check_finite=False)
+                out(sumsq).value = float(np.sum(a * a))
+            else:
+                out(sumsq).value = float("nan")
+        return rc
+
     def b200gp_dense_create_from_cov(self, ctx, cov, n, href, info):
         self.calls.append("dense_create_from_cov")
         d = _Dense()

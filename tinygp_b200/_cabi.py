@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200gp_kernel_diag": (c_int, [_V, _D, _I, _D, _L, _I, _D]),
     "b200gp_kernel_matvec": (c_int, [_V, _D, _I, _D, _L, _D, _L, _I, _D, _D]),
     "b200gp_dense_create": (c_int, [_V, _D, _I, _D, _L, _I, _D, POINTER(c_void_p), POINTER(c_int)]),
+    "b200gp_dense_create_with_resid": (c_int, [_V, _D, _I, _D, _L, _I, _D, _D, POINTER(c_void_p), POINTER(c_int), c_double_p]),
     "b200gp_dense_create_dev": (c_int, [_V, _D, _I, _D, _L, _I, _D, POINTER(c_void_p), POINTER(c_int)]),
     "b200gp_dense_create_from_cov": (c_int, [_V, _D, _L, POINTER(c_void_p), POINTER(c_int)]),
     "b200gp_dense_free": (c_int, [_V]),

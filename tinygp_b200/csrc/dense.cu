@@ -1431,6 +1431,48 @@ int b200gp_dense_create(b200gp_ctx* ctx, const double* prog, int n_instr, const 
     API_END
 }
 
+// DirectSolver.__init__ (direct.py:30-53) and, in the same pass, sum((L^-1 resid)^2) -- the data term of
+// gp.py:313-316: the int8 factorisation substitutes panel by panel on a side stream under the update of the next block
+// column (option "solve_overlap"), so `GaussianProcess(...).log_probability(y)` pays no separate triangular solve.
+int b200gp_dense_create_with_resid(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X, int64_t n, int ndim,
+                                   const double* diag, const double* resid, b200gp_dense** out, int* info, double* sumsq) {
+    API_BEGIN(ctx)
+    KProg P = parse_prog(prog, n_instr, ndim);
+    _ctx->fuse_resid = (_ctx->solve_overlap != 0) ? resid : nullptr;
+    _ctx->fuse_n = n;
+    _ctx->fuse_y = _ctx->fuse_x = nullptr;
+    b200gp_dense* s = nullptr;
+    try {
+        s = dense_factor_from_prog(_ctx, P, X, n, ndim, diag, true);
+    } catch (...) {
+        _ctx->fuse_resid = nullptr;
+        throw;
+    }
+    _ctx->fuse_resid = nullptr;
+    try {
+        const int64_t np = s->np;
+        double* y = _ctx->fuse_y;
+        double* x = _ctx->fuse_x;
+        _ctx->fuse_y = _ctx->fuse_x = nullptr;
+        if (x == nullptr) {
+            y = (double*)_ctx->alloc((size_t)np * 8);
+            x = (double*)_ctx->alloc((size_t)np * 8);
+            CUDA_CHECK(cudaMemsetAsync(y, 0, (size_t)np * 8, _ctx->stream));
+            CUDA_CHECK(cudaMemcpyAsync(y, resid, (size_t)n * 8, cudaMemcpyDefault, _ctx->stream));
+            dense_solve_vec_dev(s, y, x, false);
+        }
+        *sumsq = dense_sumsq_dev(_ctx, x, n);
+        _ctx->release(y, (size_t)np * 8);
+        _ctx->release(x, (size_t)np * 8);
+    } catch (...) {
+        dense_destroy(s);
+        throw;
+    }
+    *out = s;
+    if (info) *info = s->info;
+    API_END
+}
+
 int b200gp_dense_create_dev(b200gp_ctx* ctx, const double* prog, int n_instr, const double* X_dev, int64_t n,
                             int ndim, const double* diag_dev, b200gp_dense** out, int* info) {
     return b200gp_dense_create(ctx, prog, n_instr, X_dev, n, ndim, diag_dev, out, info);  // cudaMemcpyDefault

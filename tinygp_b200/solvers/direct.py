@@ -24,6 +24,8 @@ class DirectSolver(Solver):
         self.X = X
         self.kernel = kernel
         self.noise = noise
+        self._pending = None
+        self._info = 0
         info = c_int(0)
         lib = self._ctx.lib
         if covariance is None:
@@ -35,9 +37,12 @@ class DirectSolver(Solver):
             self._x = x                      # the lowered (possibly transform-augmented) coordinates held on the device
             self.variance_value = kernel(X) + diag                              # direct.py:49
             self._cov = None
-            self._ctx.check(lib.b200gp_dense_create(self._ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(x),
-                                                    x.shape[0], x.shape[1], _cabi.ptr(diag), byref(self._h),
-                                                    byref(info)))
+            # The factorisation (direct.py:53) is issued by the first method that needs it.  When that method is
+            # `whitened_sumsq` -- GaussianProcess(...).log_probability(y), the benchmark's end-to-end path -- it runs as ONE
+            # call that also substitutes the residual, panel by panel under the int8 update (b200gp_dense_create_with_resid);
+            # any other first use factors alone (b200gp_dense_create).  Results are the same either way.
+            self._pending = (prog, diag)
+            return
         else:
             cov = _cabi.f64(covariance)
             if cov.ndim != 2 or cov.shape[0] != cov.shape[1]:
@@ -54,7 +59,45 @@ class DirectSolver(Solver):
                 self.variance_value = self.variance_value + _cabi.f64(noise.diagonal())
             self._ctx.check(lib.b200gp_dense_create_from_cov(self._ctx.handle, _cabi.ptr(cov), cov.shape[0],
                                                              byref(self._h), byref(info)))
-        self.info = info.value
+        self._info = info.value
+
+    @property
+    def info(self):
+        """0, or the 1-based index of the first non-positive pivot (the factor is NaN from there on, like
+        jnp.linalg.cholesky's)"""
+        self._ensure()
+        return self._info
+
+    def _ensure(self, resid=None):
+        """factor now if that has not happened yet; with `resid` also return sum((L^-1 resid)^2) from the same pass"""
+        if self._pending is None:
+            return None
+        prog, diag = self._pending
+        x, info, lib = self._x, c_int(0), self._ctx.lib
+        out = None
+        if resid is None:
+            self._ctx.check(lib.b200gp_dense_create(self._ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(x),
+                                                    x.shape[0], x.shape[1], _cabi.ptr(diag), byref(self._h), byref(info)))
+        else:
+            ss = c_double()
+            self._ctx.check(lib.b200gp_dense_create_with_resid(self._ctx.handle, _cabi.ptr(prog), prog.shape[0], _cabi.ptr(x),
+                                                               x.shape[0], x.shape[1], _cabi.ptr(diag), _cabi.ptr(resid),
+                                                               byref(self._h), byref(info), byref(ss)))
+            out = ss.value
+        self._pending = None
+        self._info = info.value
+        return out
+
+    def whitened_sumsq(self, y):
+        """``sum(solve_triangular(y) ** 2)`` (the data term of gp.py:313-316).  Optional hook read by
+        GaussianProcess.log_probability: on a solver that has not factored yet, factorisation and forward substitution are one
+        device pass; afterwards it is the ordinary triangular solve."""
+        y = _cabi.f64(y)
+        if y.shape != (self._n,):
+            raise ValueError("dimension mismatch")
+        if self._pending is not None:
+            return self._ensure(resid=y)
+        return float(np.sum(np.square(self.solve_triangular(y))))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -71,6 +114,7 @@ class DirectSolver(Solver):
 
     def covariance(self):  # direct.py:58-59, regenerated lazily by the build kernel
         if self._cov is None:
+            self._ensure()
             out = np.empty((self._n, self._n))
             self._ctx.check(self._ctx.lib.b200gp_dense_covariance(self._h, _cabi.ptr(out)))
             self._cov = out
@@ -78,14 +122,16 @@ class DirectSolver(Solver):
 
     @property
     def scale_tril(self):
+        self._ensure()
         out = np.empty((self._n, self._n))
         self._ctx.check(self._ctx.lib.b200gp_dense_get_factor(self._h, _cabi.ptr(out)))
         return out
 
     def normalization(self):  # direct.py:61-64
+        self._ensure()
         ld = c_double()
         self._ctx.check(self._ctx.lib.b200gp_dense_logdet_half(self._h, byref(ld)))
-        if self.info != 0:
+        if self._info != 0:
             return np.nan
         return ld.value + 0.5 * self._n * np.log(2 * np.pi)
 
@@ -93,6 +139,7 @@ class DirectSolver(Solver):
         y = np.asarray(y, dtype=np.float64)
         if y.shape[0] != self._n:
             raise ValueError("dimension mismatch")
+        self._ensure()
         buf = np.array(y.reshape(self._n, -1), dtype=np.float64, order="C", copy=True)
         self._ctx.check(self._ctx.lib.b200gp_dense_solve_triangular(self._h, _cabi.ptr(buf), buf.shape[1],
                                                                     int(bool(transpose))))
@@ -102,6 +149,7 @@ class DirectSolver(Solver):
         y = np.asarray(y, dtype=np.float64)
         if y.shape[0] != self._n:
             raise ValueError("dimension mismatch")
+        self._ensure()
         buf = np.array(y.reshape(self._n, -1), dtype=np.float64, order="C", copy=True)
         self._ctx.check(self._ctx.lib.b200gp_dense_dot_triangular(self._h, _cabi.ptr(buf), buf.shape[1]))
         return buf.reshape(y.shape)
@@ -115,6 +163,7 @@ class DirectSolver(Solver):
         # the training kernel's lowered layout (raw columns + the host-computed columns of any transforms.Transform).
         # A predictive kernel that lowers the training inputs differently (other width, other transform outputs) would
         # read those columns wrongly -- or past the test-point buffer -- so it is refused instead of silently mis-evaluated.
+        self._ensure()
         prog, x_train = kernel.lower_for(self.X)
         if x_train.shape != self._x.shape or not np.array_equal(x_train, self._x):
             raise NotImplementedError(

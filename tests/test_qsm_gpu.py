@@ -108,3 +108,41 @@ def test_conditioning_a_long_series_never_densifies():
     _, co = o.GaussianProcess(ko, t[:m], diag=0.1).condition(y[:m], diag=0.05)
     np.testing.assert_allclose(cs.variance, co.variance, rtol=1e-7, atol=1e-10)
     assert abs(cs.log_probability(y[:m]) - co.log_probability(y[:m])) < 1e-7 * abs(co.log_probability(y[:m]))
+
+
+# ---- the reference's own test_core.py (tests/qsm_reference_tests.py) on the GPU ---------------------------------------
+import qsm_reference_tests as R  # noqa: E402
+
+
+def test_reference_quasisep_def():
+    R.check_quasisep_def()
+
+
+@pytest.mark.parametrize("parallel", [False, True])
+@pytest.mark.parametrize("name", ["random", "celerite"])
+def test_reference_matmuls(name, parallel):
+    R.check_strict_tri_matmul(name, parallel)
+    R.check_tri_matmul(name, parallel)
+    R.check_square_matmul(True, name, parallel)
+    R.check_square_matmul(False, name, parallel)
+
+
+@pytest.mark.parametrize("chunk", [0, 5])
+def test_reference_inverses_solves_gram_cholesky(ctx, chunk):
+    ctx.set_option("qsm_chunk", chunk)
+    R.check_tri_inv()
+    for parallel in (False, True):
+        R.check_tri_solve(parallel)
+        R.check_cholesky(parallel)
+    for name in ("random", "celerite"):
+        R.check_gram(name)
+        for symm in (True, False):
+            R.check_square_inv(symm, name)
+
+
+@pytest.mark.parametrize("chunk", [0, 5])
+def test_reference_products_and_ops(ctx, chunk):
+    ctx.set_option("qsm_chunk", chunk)
+    R.check_tri_qsmul()
+    R.check_square_qsmul()
+    R.check_ops()

@@ -269,3 +269,26 @@ def test_batched_hyperparameter_grid(ctx):
     ctx.check(ctx.lib.b200gp_dense_log_probability_batched(
         ctx.handle, _cabi.ptr(bad), bad.shape[1], 2, _cabi.ptr(X), n, 3, _cabi.ptr(diag), _cabi.ptr(y), _cabi.ptr(out2)))
     assert out2[1] == -np.inf and rel(out2[0], out[0]) < 1e-12
+    # a batch whose members are NOT one common single-leaf kernel: the interpreter builds it (lower triangle only)
+    L2 = kernels.L2Distance()
+    mixed = [1.3 * kernels.ExpSquared(0.8), 0.7 * kernels.Matern32(1.5, L2), 1.1 * kernels.Matern52(2.0, L2)]
+    pm = np.ascontiguousarray(np.stack([k.program() for k in mixed]))
+    out3 = np.empty(3)
+    ctx.check(ctx.lib.b200gp_dense_log_probability_batched(
+        ctx.handle, _cabi.ptr(pm), pm.shape[1], 3, _cabi.ptr(X), n, 3, _cabi.ptr(diag), _cabi.ptr(y), _cabi.ptr(out3)))
+    for k, got in zip(mixed, out3):
+        want = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+        assert rel(got, want) < LOGP_RTOL, (got, want)
+    # larger problems (interior build tiles, several panels): Matern-5/2 grid on the specialised batched build
+    n2 = 2304
+    X2 = np.ascontiguousarray(rng.uniform(0, 10, (n2, 2)))
+    y2 = np.cos(X2[:, 1]) + 0.1 * rng.normal(size=n2)
+    d2 = np.full(n2, 0.05)
+    ks2 = [a * kernels.Matern52(s, L2) for s, a in ((0.7, 0.5), (1.5, 2.0))]
+    p2 = np.ascontiguousarray(np.stack([k.program() for k in ks2]))
+    out4 = np.empty(2)
+    ctx.check(ctx.lib.b200gp_dense_log_probability_batched(
+        ctx.handle, _cabi.ptr(p2), p2.shape[1], 2, _cabi.ptr(X2), n2, 2, _cabi.ptr(d2), _cabi.ptr(y2), _cabi.ptr(out4)))
+    for k, got in zip(ks2, out4):
+        want = o.GaussianProcess(to_oracle(k), X2, diag=0.05).log_probability(y2)
+        assert rel(got, want) < LOGP_RTOL, (got, want)

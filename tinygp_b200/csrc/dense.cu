@@ -37,6 +37,12 @@ struct BuildArgs {
     // batched build (blockIdx.z = problem): one program per problem, outputs batch_stride apart
     const KProg* progs;
     int64_t batch_stride;
+    // batched single-leaf build: per-problem (coef, c0, c1) of build_rect_kernel_single (3 doubles per problem, device), the
+    // common leaf's opcode and metric; lower_only: skip the tiles strictly right of the row's 128-wide diagonal tile column
+    // (a factorisation reads the lower triangle only)
+    const double* batch_consts;
+    int batch_op, batch_l2;
+    int lower_only;
 };
 
 #define BUILD_ROWS 32
@@ -60,6 +66,7 @@ __global__ void __launch_bounds__(256, 3) build_rect_kernel_t(const __grid_const
     double* const outb = a.out + (int64_t)blockIdx.z * a.batch_stride;
     const int64_t r0 = (int64_t)blockIdx.y * BUILD_ROWS;
     const int64_t c0 = (int64_t)blockIdx.x * BUILD_COLS;
+    if (a.lower_only && (c0 + a.col_off) / TILE > (r0 + a.row_off) / TILE) return;   // block-uniform
     const int nd = a.ndim;
     for (int i = tid; i < BUILD_ROWS * nd; i += 256) {
         const int64_t r = r0 + i / nd;
@@ -130,11 +137,20 @@ __device__ __forceinline__ double single_leaf(const double (&xa)[ND], const doub
 }
 
 template <int OP, bool L2, int ND>
-__global__ void __launch_bounds__(256, 3) build_rect_kernel_single(const BuildArgs a, const double coef, const double c0, const double c1) {
+__global__ void __launch_bounds__(256, 3) build_rect_kernel_single(const BuildArgs a_in, const double coef_in, const double c0_in,
+                                                                   const double c1_in) {
     __shared__ double x1s[BUILD_ROWS * ND];
     const int tid = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * BUILD_ROWS;
     const int64_t c0g = (int64_t)blockIdx.x * BUILD_COLS;
+    BuildArgs a = a_in;
+    if (a.lower_only && (c0g + a.col_off) / TILE > (r0 + a.row_off) / TILE) return;   // block-uniform
+    double coef = coef_in, c0 = c0_in, c1 = c1_in;
+    if (a.batch_consts != nullptr) {     // blockIdx.z = problem: its own amplitude / scale, its own output matrix
+        const double* bc = a.batch_consts + 3 * (int64_t)blockIdx.z;
+        coef = bc[0]; c0 = bc[1]; c1 = bc[2];
+        a.out += (int64_t)blockIdx.z * a.batch_stride;
+    }
     for (int i = tid; i < BUILD_ROWS * ND; i += 256) {
         const int64_t r = r0 + i / ND;
         x1s[i] = (r < a.n1) ? a.X1[r * ND + (i % ND)] : 0.0;
@@ -202,9 +218,24 @@ static void launch_single_nd(cudaStream_t st, dim3 grid, const BuildArgs& a, dou
         default: build_rect_kernel_single<OP, L2, 3><<<grid, 256, 0, st>>>(a, coef, c0, c1); break;
     }
 }
+// (coef, c0, c1) of build_rect_kernel_single for a single-leaf normal form; false if the leaf has no compiled kernel
+static bool single_constants(const KFast& F, double* out3) {
+    if (F.nleaf != 1 || F.nterm != 1 || F.mask[0] != 1) return false;
+    const double p0 = F.p0[0];
+    out3[0] = F.coef[0]; out3[2] = 0.0;
+    switch (F.op[0]) {
+        case B200GP_OP_EXPSQUARED: out3[1] = -0.5 / (p0 * p0); return true;
+        case B200GP_OP_EXP: out3[1] = 1.0 / p0; return true;
+        case B200GP_OP_MATERN32: out3[1] = SQRT3 / p0; return true;
+        case B200GP_OP_MATERN52: out3[1] = SQRT5 / p0; out3[2] = 1.0 / 3.0; return true;
+        default: return false;
+    }
+}
+
 // true if the program is coef * (one stationary leaf) of a kind compiled above and the launch was made
 static bool launch_build_single(b200gp_ctx* ctx, dim3 grid, const KFast& F, const BuildArgs& a) {
-    if (ctx->build_fast < 2 || F.nleaf != 1 || F.nterm != 1 || F.mask[0] != 1 || a.ndim < 1 || a.ndim > 3 || grid.z != 1) return false;
+    if (ctx->build_fast < 2 || F.nleaf != 1 || F.nterm != 1 || F.mask[0] != 1 || a.ndim < 1 || a.ndim > 3) return false;
+    if (grid.z != 1 && a.batch_consts == nullptr) return false;
     const double coef = F.coef[0], p0 = F.p0[0];
     const bool l2 = F.l2[0] != 0;
     cudaStream_t st = ctx->stream;
@@ -224,6 +255,10 @@ static bool launch_build_single(b200gp_ctx* ctx, dim3 grid, const KFast& F, cons
 // ("build_fast" >= 1), else the interpreter (also for batched programs)
 static void launch_build_rect(b200gp_ctx* ctx, dim3 grid, const KProg& prog, const BuildArgs& a) {
     KFast F{};
+    if (a.progs != nullptr && a.batch_consts != nullptr) {   // batched hyper-parameter grid of one single-leaf kernel
+        F.nleaf = F.nterm = 1; F.mask[0] = 1; F.op[0] = a.batch_op; F.l2[0] = a.batch_l2; F.p0[0] = 1.0; F.coef[0] = 1.0;
+        if (launch_build_single(ctx, grid, F, a)) return;
+    }
     if (a.progs == nullptr && ctx->build_fast != 0 && kprog_to_fast(prog, F)) {
         if (launch_build_single(ctx, grid, F, a)) return;
         build_rect_kernel_t<true><<<grid, 256, 0, ctx->stream>>>(prog, F, a);
@@ -1734,7 +1769,8 @@ __global__ void replicate_pad_kernel(const double* src, int64_t n, double* dst, 
 }
 
 static void dense_logp_batched_chunk(b200gp_ctx* ctx, const KProg* progs_dev, int64_t B, const double* X_dev, int64_t n,
-                                     int ndim, const double* diag_dev, const double* resid_dev, double* logp_dev) {
+                                     int ndim, const double* diag_dev, const double* resid_dev, double* logp_dev,
+                                     const double* consts_dev, int batch_op, int batch_l2) {
     const int64_t np = ((n + TILE - 1) / TILE) * TILE, ld = np;
     const int nblk = (int)(np / TILE);
     const int64_t smat = np * np, slinv = (int64_t)nblk * TILE * TILE;
@@ -1751,6 +1787,8 @@ static void dense_logp_batched_chunk(b200gp_ctx* ctx, const KProg* progs_dev, in
         a.X1 = X_dev; a.X2 = X_dev; a.diag = diag_dev; a.out = M; a.ld = ld;
         a.n1 = n; a.n2 = n; a.rows_pad = np; a.cols_pad = np; a.ndim = ndim; a.pad_identity = 1;
         a.progs = progs_dev; a.batch_stride = smat;
+        a.batch_consts = consts_dev; a.batch_op = batch_op; a.batch_l2 = batch_l2;
+        a.lower_only = 1;      // the blocked factorisation below reads (and writes) lower-triangle 128-tiles only
         dim3 grid((unsigned)((np + BUILD_COLS - 1) / BUILD_COLS), (unsigned)((np + BUILD_ROWS - 1) / BUILD_ROWS), (unsigned)B);
         ProfTimer t(ctx, &ctx->prof.build_ms);
         launch_build_rect(ctx, grid, empty_prog(), a);
@@ -1818,6 +1856,19 @@ extern "C" int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const doubl
     if (ndim < 1 || ndim > MAX_NDIM) throw GpError("batched log_probability: ndim must be in [1, 16]");
     std::vector<KProg> hp((size_t)nbatch);
     for (int64_t b = 0; b < nbatch; ++b) hp[b] = parse_prog(progs + (size_t)b * n_instr * B200GP_PROG_STRIDE, n_instr, ndim);
+    // a hyper-parameter grid of ONE single-leaf kernel (amp * ExpSquared(scale), ...: BASELINE config 5) runs the build in the
+    // compile-time specialised kernel with per-problem constants instead of the interpreter
+    std::vector<double> hc((size_t)nbatch * 3);
+    int batch_op = -1, batch_l2 = 0;
+    bool single = (_ctx->build_fast >= 2 && ndim <= 3);
+    for (int64_t b = 0; b < nbatch && single; ++b) {
+        KFast F{};
+        if (!kprog_to_fast(hp[b], F) || !single_constants(F, &hc[(size_t)b * 3])) { single = false; break; }
+        if (b == 0) { batch_op = F.op[0]; batch_l2 = F.l2[0]; }
+        else if (F.op[0] != batch_op || F.l2[0] != batch_l2) single = false;
+    }
+    double* dc = single ? (double*)_ctx->alloc((size_t)nbatch * 3 * 8) : nullptr;
+    if (dc) CUDA_CHECK(cudaMemcpyAsync(dc, hc.data(), (size_t)nbatch * 3 * 8, cudaMemcpyHostToDevice, _ctx->stream));
     KProg* dp = (KProg*)_ctx->alloc((size_t)nbatch * sizeof(KProg));
     double* dX = (double*)_ctx->alloc((size_t)n * ndim * 8);
     double* dd = (double*)_ctx->alloc((size_t)n * 8);
@@ -1834,11 +1885,12 @@ extern "C" int b200gp_dense_log_probability_batched(b200gp_ctx* ctx, const doubl
     if (chunk > 4096) chunk = 4096;
     for (int64_t b0 = 0; b0 < nbatch; b0 += chunk) {
         const int64_t B = (chunk < nbatch - b0) ? chunk : (nbatch - b0);
-        dense_logp_batched_chunk(_ctx, dp + b0, B, dX, n, ndim, dd, dr, dl + b0);
+        dense_logp_batched_chunk(_ctx, dp + b0, B, dX, n, ndim, dd, dr, dl + b0, dc ? dc + 3 * b0 : nullptr, batch_op, batch_l2);
     }
     CUDA_CHECK(cudaMemcpyAsync(logp, dl, (size_t)nbatch * 8, cudaMemcpyDeviceToHost, _ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
     _ctx->release(dp, (size_t)nbatch * sizeof(KProg));
+    if (dc) _ctx->release(dc, (size_t)nbatch * 3 * 8);
     _ctx->release(dX, (size_t)n * ndim * 8);
     _ctx->release(dd, (size_t)n * 8);
     _ctx->release(dr, (size_t)n * 8);

@@ -620,7 +620,12 @@ def run_batched(args, rank, local_rank, world):
     from tinygp_b200 import multigpu
     ctx = multigpu.make_context(local_rank)
     n = 4096 if args.n == N_DENSE else args.n
+    for kv in args.opt:                            # tuning experiments: --opt nb_batched=1024 ...
+        key, _, val = kv.partition("=")
+        ctx.set_option(key, int(val))
     line = measure_batched(args, ctx, local_rank, rank, world, n=n, steps=args.steps, warmup=args.warmup)
+    if args.opt:
+        line["config"]["options"] = list(args.opt)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

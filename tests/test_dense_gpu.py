@@ -254,7 +254,7 @@ def test_batched_hyperparameter_grid(ctx):
     ks = [a * kernels.ExpSquared(scale=s) for s, a in grid]
     progs = np.ascontiguousarray(np.stack([k.program() for k in ks]))
     out = np.empty(len(ks))
-    for nb in (128, 512):
+    for nb in (128, 512, 4096):
         ctx.set_option("nb_batched", nb)
         ctx.check(ctx.lib.b200gp_dense_log_probability_batched(
             ctx.handle, _cabi.ptr(progs), progs.shape[1], len(ks), _cabi.ptr(X), n, 3, _cabi.ptr(diag), _cabi.ptr(y),
@@ -262,7 +262,7 @@ def test_batched_hyperparameter_grid(ctx):
         for k, got in zip(ks, out):
             want = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
             assert rel(got, want) < LOGP_RTOL, (got, want)
-    ctx.set_option("nb_batched", 512)
+    ctx.set_option("nb_batched", 4096)       # the library default
     # a non-PD member of the batch gives -inf without disturbing the others
     bad = np.ascontiguousarray(np.stack([ks[0].program(), (-1.0 * kernels.ExpSquared(1.0)).program()]))
     out2 = np.empty(2)

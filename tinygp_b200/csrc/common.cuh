@@ -78,7 +78,8 @@ struct b200gp_ctx {
     int64_t mg_splitk = 0;       // sharded path: 0 (default) = one K range per tile: bit-identical results for every rank count;
                                  // 1 = tail split-K on every rank's rows too (2 GPUs, N = 131072: update 2791 -> 2738 ms, step not faster)
     int64_t oz_splitk_force = 0; // > 1: that many K segments in every CTA-pair launch (tests)
-    int64_t nb_batched = 512;   // outer panel width of the batched small-N driver
+    int64_t nb_batched = 4096;  // outer panel width of the batched small-N driver: 4096 = N of config 5, i.e. one left-looking sweep (reads C
+                                // once per 128-column block); measured 843 / 956 / 1025 / 1055 / 1061 logp/s for 256 / 512 / 1024 / 2048 / 4096
     // > 0: int8 fixed-point trailing update with this many digit planes (ozaki.cu); 0 = DMMA.  7 planes = 48 bits under the
     // row scale: at N = 65536 the log-probability differs from the LAPACK golden by 4.7e-12 with 7 AND with 8 planes
     // (profiles/r1_bench_dense_int8x{7,8}.json vs tests/golden/full_size.json) -- the digit truncation is below the fp64

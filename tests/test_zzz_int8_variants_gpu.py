@@ -134,3 +134,24 @@ def test_factorisation_with_split_k(ctx, force):
         ctx.reset_options()
     lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
     assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+
+
+@pytest.mark.parametrize("slices", [0, 7])
+def test_right_looking_diagonal_block_chain(ctx, slices):
+    """option panel_chain = 1: right-looking order inside the diagonal block of the look-ahead panel (other summation order
+    than the left-looking chain: parity with the oracle, not bit-identity)"""
+    from tinygp_b200 import kernels
+    n = 6144
+    rng = np.random.default_rng(23)
+    X = rng.uniform(0, 20.0 * (n / 65536.0) ** (1 / 3), (n, 3))
+    y = np.sin(X[:, 0]) + 0.1 * rng.normal(size=n)
+    k = 1.3 * kernels.ExpSquared(0.8)
+    ctx.set_option("nb", 1024)
+    ctx.set_option("ozaki_min_n", 0 if slices else 1 << 40)
+    ctx.set_option("panel_chain", 1)
+    try:
+        lp = GaussianProcess(k, X, diag=0.1).log_probability(y)
+    finally:
+        ctx.reset_options()
+    lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
+    assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)

@@ -99,6 +99,7 @@ struct b200gp_ctx {
     double* fuse_x = nullptr;             // np: L^-1 resid once the factorisation has returned
     int64_t solve_overlap = 1;            // option: 1 = hide the forward substitution of log_probability under the factorisation
     cudaStream_t stream_solve = nullptr;
+    int64_t panel_chain = 0;    // look-ahead panel: 1 = right-looking order inside the diagonal block (shorter chain, other summation order)
     cudaStream_t stream_hi = nullptr;   // high-priority stream of the look-ahead panel chain (panel_overlap = 2)
     int64_t oz_prefetch = 0;    // L2 prefetch distance (K-chunks of 128) of the int8 update's TMA producer
     int64_t oz_pairing = 1;    // int8 update: 1 = accumulate two digit groups at once (default: 16 instead of 28 operand-stage loads

@@ -186,6 +186,7 @@ static const struct OptEntry { const char* key; int64_t b200gp_ctx::*field; } kO
     {"ozaki_pairing", &b200gp_ctx::oz_pairing},
     {"build_ahead", &b200gp_ctx::build_ahead},
     {"panel_overlap", &b200gp_ctx::panel_overlap},
+    {"panel_chain", &b200gp_ctx::panel_chain},
     {"ozaki_lookahead", &b200gp_ctx::oz_lookahead},
     {"ozaki_cluster", &b200gp_ctx::oz_cluster},
     {"ozaki_min_n", &b200gp_ctx::oz_min_n},

@@ -927,15 +927,25 @@ static void dense_panel_factor_lookahead(b200gp_dense* s, int64_t k0, int64_t kb
     struct Restore { b200gp_ctx* c; cudaStream_t st; ~Restore() { c->stream = st; } } restore{ctx, wide};
     CUDA_CHECK(cudaEventRecord(ev, wide));      // the chain must see the block column as the caller left it
     CUDA_CHECK(cudaStreamWaitEvent(chain, ev, 0));
+    // chain_right (option "panel_chain" = 1): RIGHT-looking order inside the diagonal block -- after the block column is
+    // solved, the remaining (blk - 1) x (blk - 1) lower tiles of the block are updated with K = 128 (up to 28 tiles in
+    // parallel) instead of updating each block column just before its potf2 with K = j0 (1-7 tiles, a single CTA running
+    // K = 896 takes 164 us).  Shorter chain per panel (1.8 -> ~1.3 ms by the launch list), different summation order of the
+    // diagonal block (not bit-identical to the left-looking orders).
+    const bool chain_right = (ctx->panel_chain == 1);
     for (int64_t j0 = 0; j0 < kb; j0 += TILE) {
         const int64_t c0 = k0 + j0;
         const int blk = (int)((bend - c0) / TILE);
         const double* li = s->linv + (c0 / TILE) * TILE * TILE;
         ctx->stream = chain;
-        if (j0 > 0) gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld, blk, 1, (int)j0, -1.0, 1, 0);
+        if (j0 > 0 && !chain_right)
+            gemm_nt(ctx, M + c0 * ld + c0, ld, M + c0 * ld + k0, ld, M + c0 * ld + k0, ld, blk, 1, (int)j0, -1.0, 1, 0);
         potf2(ctx, M + c0 * ld + c0, ld, s->linv + (c0 / TILE) * TILE * TILE, s->info_dev, (int)c0);
         if (own) CUDA_CHECK(cudaEventRecord(ev, chain));            // L[c0 rows, k0..c0) and inv(L_jj) are final here
         if (blk > 1) gemm_nt(ctx, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld, li, TILE, blk - 1, 1, TILE, 1.0, 0, 0);
+        if (chain_right && blk > 1)      // trailing tiles of the diagonal block: C -= X X^T, X = the block column just solved
+            gemm_nt(ctx, M + (c0 + TILE) * ld + (c0 + TILE), ld, M + (c0 + TILE) * ld + c0, ld, M + (c0 + TILE) * ld + c0, ld,
+                    blk - 1, blk - 1, TILE, -1.0, 1, 1);
         if (own) {
             CUDA_CHECK(cudaStreamWaitEvent(wide, ev, 0));
             ctx->stream = wide;

@@ -148,10 +148,13 @@ def test_right_looking_diagonal_block_chain(ctx, slices):
     k = 1.3 * kernels.ExpSquared(0.8)
     ctx.set_option("nb", 1024)
     ctx.set_option("ozaki_min_n", 0 if slices else 1 << 40)
-    ctx.set_option("panel_chain", 1)
+    lps = []
     try:
-        lp = GaussianProcess(k, X, diag=0.1).log_probability(y)
+        for chain in (1, 0):
+            ctx.set_option("panel_chain", chain)
+            lps.append(GaussianProcess(k, X, diag=0.1).log_probability(y))
     finally:
         ctx.reset_options()
     lpo = o.GaussianProcess(to_oracle(k), X, diag=0.1).log_probability(y)
-    assert rel(lp, lpo) < LOGP_RTOL, (lp, lpo)
+    assert rel(lps[0], lpo) < LOGP_RTOL and rel(lps[1], lpo) < LOGP_RTOL, (lps, lpo)
+    assert rel(lps[0], lps[1]) < 1e-11

@@ -2,6 +2,8 @@
 The data path itself has no collective (replicas); see DESIGN.md section 5."""
 
 import os
+
+import pytest
 import socket
 
 import numpy as np
@@ -101,9 +103,31 @@ def _inplace_worker(rank, world, port, np_, nb, q):
         dist.destroy_process_group()
 
 
-def test_inplace_block_column_allgather_geometry_world2():
+def test_inplace_slices_stay_inside_the_column_buffer():
+    """the in-place all-gather's output covers `world` equal chunks from row c0 on and may reach past np: never past the
+    world * ALIGN spare rows the column buffer has, for every block column of the bench sizes on 2 / 4 / 8 ranks"""
+    from tinygp_b200 import multigpu
+    for np_, nb in [(131072, 1024), (65536, 1024), (65664, 1024), (5120, 512), (1280, 256)]:
+        for world in (2, 4, 8):
+            limit = (np_ + world * multigpu.ALIGN) * nb
+            for c0 in range(0, np_, nb):
+                ch = multigpu.row_chunk(np_, c0, world)
+                prev_hi = None
+                for rank in range(world):
+                    o0, o1, i0, i1 = multigpu.inplace_slices(np_, nb, c0, world, rank)
+                    assert o0 == c0 * nb and o1 - o0 == world * ch * nb and o1 <= limit
+                    assert i0 == o0 + rank * ch * nb and i1 - i0 == ch * nb and o0 <= i0 < i1 <= o1
+                    assert prev_hi is None or i0 == prev_hi
+                    prev_hi = i1
+                    r0, r1 = multigpu.my_rows(np_, c0, world, rank)
+                    assert r0 * nb >= i0 or r0 == np_                 # a rank's rows start inside its own chunk ...
+                    assert r1 * nb <= i1 or r1 == np_                 # ... and end inside it
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_inplace_block_column_allgather_geometry(world):
     """the sharded path's exchange (multigpu.inplace_slices): every rank ends up with every row of the block column"""
-    world, np_, nb = 2, 1280, 256
+    np_, nb = 1280, 256
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

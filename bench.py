@@ -520,7 +520,8 @@ def measure_quasisep(args, ctx, local_rank, n=10_000_000, steps=None, warmup=3, 
         "parity": {"oracle_logp": lpo, "rel_err": abs(logp - lpo) / abs(lpo), "rel_err_e2e": abs(logp_e2e - lpo) / abs(lpo),
                    "oracle": f"C restatement of the sequential recursion on all {n} points ({t_cpu:.2f} s, 1 core)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "peak_source": src, "traffic": None, "algorithmic_bytes_per_point": 8 * (3 + 1 + J),
+                     "peak_source": src, "traffic": _read_traffic("qs_traffic.json", "dram_bytes_per_step") if n == 10_000_000 else None,
+                     "algorithmic_bytes_per_point": 8 * (3 + 1 + J),
                      "note": "fp64-ALU bound (Riccati composites + exp/sincos per point), see DESIGN.md section 4"},
         "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "logp/s", "cores": 1, "kind": "port",
                          "sample": f"all {n} points, C restatement of ops.py:352-365,463-472 ({t_cpu:.2f} s; generators "
@@ -722,10 +723,12 @@ def run_sharded(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def _read_traffic():
-    p = os.path.join(ROOT, "profiles", "syrk_traffic.json")
+def _read_traffic(name="syrk_traffic.json", key="dram_bytes_per_launch"):
+    """DRAM read + write bytes of the dominant kernel(s) from the committed ncu capture (profiles/): per launch for the int8
+    update, per step for the two point-wise quasiseparable passes"""
+    p = os.path.join(ROOT, "profiles", name)
     try:
-        return json.load(open(p)).get("dram_bytes_per_launch")
+        return json.load(open(p)).get(key)
     except Exception:
         return None
 

@@ -205,6 +205,47 @@ static void vec(b200gp_ctx* c, int64_t n, double* dst, const double* x, const do
 enum { B200GP_QSM_DIAG = 0, B200GP_QSM_STRICT_LOWER = 1, B200GP_QSM_STRICT_UPPER = 2, B200GP_QSM_LOWER = 3,
        B200GP_QSM_UPPER = 4, B200GP_QSM_SQUARE = 5, B200GP_QSM_SYMM = 6 };
 #endif
+// ---- sum of logs: slab i of QSM_LOGSUM_SLABS covers [i * len, (i + 1) * len); one block per slab, fixed reduction tree ----
+#define QSM_LOGSUM_SLABS 256
+#ifndef QSM_HOSTCHECK
+__global__ void __launch_bounds__(256) qsm_logsum_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ part) {
+    __shared__ double sh[256];
+    const int64_t len = (n + QSM_LOGSUM_SLABS - 1) / QSM_LOGSUM_SLABS;
+    const int64_t lo = (int64_t)blockIdx.x * len, hi = (lo + len < n) ? (lo + len) : n;
+    double s = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) s += log(x[i]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+#endif
+static void qsm_logsum(b200gp_ctx* ctx, const double* x, int64_t n, double* part) {
+#ifdef QSM_HOSTCHECK
+    const int64_t len = (n + QSM_LOGSUM_SLABS - 1) / QSM_LOGSUM_SLABS;
+    for (int b = 0; b < QSM_LOGSUM_SLABS; ++b) {     // the kernel's summation tree, thread by thread
+        double sh[256];
+        const int64_t lo = (int64_t)b * len, hi = (lo + len < n) ? (lo + len) : n;
+        for (int t = 0; t < 256; ++t) {
+            double s = 0.0;
+            for (int64_t i = lo + t; i < hi; i += 256) s += log(x[i]);
+            sh[t] = s;
+        }
+        for (int o = 128; o > 0; o >>= 1)
+            for (int t = 0; t < o; ++t) sh[t] += sh[t + o];
+        part[b] = sh[0];
+    }
+    ctx->launches++;
+#else
+    qsm_logsum_kernel<<<QSM_LOGSUM_SLABS, 256, 0, ctx->stream>>>(x, n, part);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+#endif
+}
+
 // ---- the object --------------------------------------------------------------------------------------------------------
 struct QTri {
     int m = 0; BufP p, q, a;
@@ -790,14 +831,17 @@ int b200gp_qsm_solve(b200gp_qsm* a, double* Y, int64_t nrhs) {
     API_END
 }
 
-// sum_k log d_k (solver.py:90-93 on a LowerTriQSM factor), accumulated in index order on the host side of the boundary
+// sum_k log d_k (solver.py:90-93 on a LowerTriQSM factor): fixed-shape two-stage reduction on the device (deterministic:
+// QSM_LOGSUM_SLABS contiguous slabs, each summed by one block's fixed tree; the 256 slab sums are added in index order)
 int b200gp_qsm_sum_log_diag(b200gp_qsm* a, double* out) {
     API_BEGIN(a->ctx)
     if (!a->d) throw GpError("qsm_sum_log_diag: no diagonal");
-    std::vector<double> h((size_t)a->n);
-    q_d2h(_ctx, h.data(), a->d->p, (size_t)a->n);
+    BufP part = qnew(_ctx, QSM_LOGSUM_SLABS);
+    qsm_logsum(_ctx, a->d->p, a->n, part->p);
+    double h[QSM_LOGSUM_SLABS];
+    q_d2h(_ctx, h, part->p, QSM_LOGSUM_SLABS);
     double s = 0.0;
-    for (int64_t i = 0; i < a->n; ++i) s += log(h[(size_t)i]);
+    for (int i = 0; i < QSM_LOGSUM_SLABS; ++i) s += h[i];
     *out = s;
     API_END
 }

@@ -421,6 +421,10 @@ class MockLib:
         arr(outp, (m, m))[:] = res
         return 0
 
+    def b200gp_searchsorted_right_m1(self, ctx, sorted_, n, query, m, outp):      # kernels/quasisep.py:121
+        arr(outp, (m,), np.int64)[:] = np.searchsorted(arr(sorted_, (n,)), arr(query, (m,)), side="right") - 1
+        return 0
+
     def b200gp_qs_kernel_matmul(self, ctx, comps, ncomp, t_test, m, t_train, n, Y, nrhs, outp):
         self.calls.append("qs_kernel_matmul")
         k = qs_kernel(arr(comps, (ncomp, 8)).copy())

@@ -306,8 +306,13 @@ def test_quasisep_kernels(which):                                    # test_quas
     diag = np.full(50, 0.3)
     dense = QuasisepSolver(kernel, x, noise.Diagonal(diag)).covariance()      # to_symm_qsm(x).to_dense() + noise
     assert_allclose(dense - np.diag(diag), K)
+    assert_allclose(kernel.to_symm_qsm(x).to_dense(), K)                       # test_quasisep.py:58 as written
     assert_allclose(kernel.matmul(x, y), K @ y)
     assert_allclose(kernel.matmul(t, x, y), kernel(t, x) @ y)
+    gq = kernel.to_general_qsm(t, x)                                           # kernels/quasisep.py:118-145, general.py
+    assert gq.shape == (12, 50)
+    assert_allclose(gq @ y, kernel(t, x) @ y)
+    assert np.array_equal(gq.idx, np.searchsorted(x, t, side="right") - 1)
 
 
 def test_products_of_sums_and_oversized_products_are_refused():       # what the backend still lacks, refused loudly

@@ -86,6 +86,11 @@ class Quasisep(Kernel):
             raise ValueError("quasiseparable kernels take 1-D sortable coordinates")
         return super().__call__(X1, X2)
 
+    def to_general_qsm(self, X1, X2):
+        """quasisep.py:118-145: the rectangular cross-covariance as a handle whose ``@ y`` runs on the device"""
+        from tinygp_b200.solvers.quasisep.general import GeneralQSM
+        return GeneralQSM(self, X1, X2)
+
     def evaluate(self, X1, X2):
         """Scalar evaluation k(t1, t2) (kernels/quasisep.py:118-145): 1-element 1-D coordinates, not the (1, 1) arrays the
         stationary base class builds."""

@@ -1,5 +1,6 @@
-"""Quasiseparable solver and matrix algebra (same layout as src/tinygp/solvers/quasisep/: solver, core, ops)."""
+"""Quasiseparable solver and matrix algebra (same layout as src/tinygp/solvers/quasisep/: solver, core, ops, general)."""
 
 from tinygp_b200.solvers.quasisep import core as core
+from tinygp_b200.solvers.quasisep import general as general
 from tinygp_b200.solvers.quasisep import ops as ops
 from tinygp_b200.solvers.quasisep.solver import QuasisepSolver as QuasisepSolver

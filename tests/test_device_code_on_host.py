@@ -36,6 +36,12 @@ KERNELS = {
                     o.qs.CARMA(np.array([1.4, 2.3, 1.5]), np.array([0.1, 0.5])) + o.qs.Scale(o.qs.Matern32(1.5, 1.0), 0.5)),
     "carma21_complex": (Q.CARMA(np.array([1.0, 1.2]), np.array([1.0, 3.0])), o.qs.CARMA(np.array([1.0, 1.2]), np.array([1.0, 3.0]))),
     "carma21_real": (Q.CARMA(np.array([0.1, 1.1]), np.array([1.0, 3.0])), o.qs.CARMA(np.array([0.1, 1.1]), np.array([1.0, 3.0]))),
+    # a Sum inside a Product is multiplied out by the host layer: two Kronecker-structured terms, block after block
+    "product_of_sum_multiplied_out": ((Q.Matern32(1.5, 0.9) + 0.4 * Q.Exp(0.7)) * Q.SHO(1.5, 3.0, 1.8),
+                                      o.qs.Matern32(1.5, 0.9) * o.qs.SHO(1.5, 3.0, 1.8)
+                                      + o.qs.Scale(o.qs.Exp(0.7, 1.0), 0.4) * o.qs.SHO(1.5, 3.0, 1.8)),
+    "product_carma_pair_first": (Q.CARMA(np.array([1.0, 1.2]), np.array([1.0, 3.0])) * Q.Exp(2.0, 1.1),
+                                 o.qs.CARMA(np.array([1.0, 1.2]), np.array([1.0, 3.0])) * o.qs.Exp(2.0, 1.1)),
     "scaled_sum3": (2.0 * Q.Matern32(1.2) + Q.SHO(0.8, 4.0, 0.6) + 0.5 * Q.Exp(5.0),
                     o.qs.Scale(o.qs.Matern32(1.2, 1.0), 2.0) + o.qs.SHO(0.8, 4.0, 0.6) + o.qs.Scale(o.qs.Exp(5.0, 1.0), 0.5)),
 }

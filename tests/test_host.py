@@ -80,8 +80,12 @@ def test_quasisep_components():
     kp = 0.5 * (Q.Matern32(1.0) * Q.Exp(2.0)) + Q.Exp(3.0)
     cp = kp.component_array()
     assert cp[:, 6].tolist() == [1.0, 0.0, 0.0] and cp[:, 1].tolist() == [0.5, 1.0, 1.0] and kp.state_dim() == 3
-    with pytest.raises(NotImplementedError):
-        ((Q.Matern32(1.0) + Q.Exp(1.0)) * Q.Exp(1.0)).components()
+    # a Sum inside a Product is multiplied out: (a + b) * c -> a * c + b * c, two chained terms
+    cs = ((Q.Matern32(1.0) + 0.3 * Q.Exp(1.0)) * Q.Exp(2.0)).component_array()
+    assert cs[:, 0].tolist() == [Q.QS_MATERN32, Q.QS_EXP, Q.QS_EXP, Q.QS_EXP]
+    assert cs[:, 6].tolist() == [1.0, 0.0, 1.0, 0.0] and cs[:, 1].tolist() == [1.0, 1.0, 0.3, 1.0]
+    with pytest.raises(NotImplementedError):      # ... unless that needs more than 8 states (3 * 2 + 2 * 2 = 10)
+        ((Q.Matern52(1.0) + Q.Matern32(1.0)) * Q.SHO(1.0, 2.0)).component_array()
 
 
 QS_PAIRS = [

@@ -292,6 +292,9 @@ QS_KERNELS = [
     lambda: quasisep.CARMA(alpha=np.array([1, 1.2]), beta=np.array([1.0, 3.0])),
     lambda: quasisep.CARMA(alpha=np.array([0.1, 1.1]), beta=np.array([1.0, 3.0])),
     lambda: quasisep.CARMA(alpha=np.array([1.0 / 100]), beta=np.array([0.3])),
+    lambda: (quasisep.Matern52(1.5) + 0.4 * quasisep.Exp(0.7)) * quasisep.SHO(omega=1.5, quality=0.1),      # multiplied out
+    lambda: (quasisep.Exp(1.5) + quasisep.Exp(0.7)) * (quasisep.Cosine(2.5) + 0.5 * quasisep.Exp(1.1)),
+    lambda: quasisep.CARMA(alpha=np.array([1, 1.2]), beta=np.array([1.0, 3.0])) * quasisep.Exp(2.0),       # CARMA2 row first
 ]
 
 
@@ -313,11 +316,19 @@ def test_quasisep_kernels(which):                                    # test_quas
     assert gq.shape == (12, 50)
     assert_allclose(gq @ y, kernel(t, x) @ y)
     assert np.array_equal(gq.idx, np.searchsorted(x, t, side="right") - 1)
+    # the state-space model itself (test_quasisep.py:66-72): the kernel value from (h, Pinf, A), and "F is defined
+    # consistently with the transition matrix"
+    from scipy.linalg import expm
+    F, Pinf = kernel.design_matrix(), kernel.stationary_covariance()
+    for x1, x2 in ((x[3], x[9]), (x[0], x[0]), (x[7], x[41])):
+        A = kernel.transition_matrix(x1, x2)
+        assert_allclose(expm(F.T * (x2 - x1)), A)
+        assert_allclose(kernel.observation_model(x2) @ A.T @ Pinf @ kernel.observation_model(x1), kernel.evaluate(x1, x2))
 
 
-def test_products_of_sums_and_oversized_products_are_refused():       # what the backend still lacks, refused loudly
-    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
-        QuasisepSolver((quasisep.Matern52(1.5) + quasisep.Exp(0.7)) * quasisep.SHO(omega=1.5, quality=0.1),
+def test_oversized_products_are_refused():                           # what the backend still lacks, refused loudly
+    with pytest.raises(NotImplementedError, match="unsupported by the B200"):      # a sum multiplied out past 8 states
+        QuasisepSolver((quasisep.Matern52(1.5) + quasisep.Matern32(0.7)) * quasisep.SHO(omega=1.5, quality=0.1),
                        np.linspace(0, 1, 5), noise.Diagonal(np.full(5, 0.1)))
     with pytest.raises(NotImplementedError, match="unsupported by the B200"):
         QuasisepSolver(quasisep.Matern52(1.5) * quasisep.Matern52(0.5), np.linspace(0, 1, 5),      # 3 x 3 = 9 states

@@ -36,6 +36,9 @@ class Quasisep(Kernel):
 
     def component_array(self) -> np.ndarray:
         comps = self.components()
+        if len(comps) > 8 or self.state_dim() > 8:      # B200GP_QS_MAX_COMP / B200GP_QS_MAX_J (include/b200gp.h)
+            raise NotImplementedError(f"a quasiseparable model with {len(comps)} component rows and {self.state_dim()} states "
+                                      "(more than 8 of either) is unsupported by the B200 quasiseparable solver backend")
         out = np.zeros((len(comps), 8))
         for i, c in enumerate(comps):
             out[i, : len(c)] = c
@@ -52,6 +55,53 @@ class Quasisep(Kernel):
 
     def coord_to_sortable(self, X):
         return X
+
+    # ---- the state-space model on the host (quasisep.py:60-100: design_matrix, stationary_covariance, observation_model,
+    # transition_matrix).  Small J x J NumPy matrices assembled from the SAME component rows the device lowers
+    # (`_leaf_state_space` restates qs_core.cuh's build_model / qs_leaf_transition); nothing on the solver path calls them.
+    def _terms(self):
+        """[[leaf rows of one term], ...]: a term is a run of rows chained by mul_next (a Product); terms are summed"""
+        terms, cur = [], []
+        for r in self.components():
+            r = tuple(r) + (0.0,) * (8 - len(r))
+            cur.append(r)
+            if not r[6]:
+                terms.append(cur)
+                cur = []
+        return terms
+
+    def _assemble(self, what, *args):
+        blocks = []
+        for term in self._terms():
+            mats = [_leaf_state_space(r, what, *args) for r in term]
+            m = mats[0]
+            for nxt in mats[1:]:
+                if what == "F":      # F = F1 (x) I + I (x) F2 in the product's state order (quasisep.py:307-311)
+                    m = _prod(m, np.eye(nxt.shape[0])) + _prod(np.eye(m.shape[0]), nxt)
+                else:
+                    m = _prod(m, nxt)
+            blocks.append(m)
+        if blocks[0].ndim == 1:
+            return np.concatenate(blocks)
+        n = sum(b.shape[0] for b in blocks)
+        out, o = np.zeros((n, n)), 0
+        for b in blocks:
+            out[o:o + b.shape[0], o:o + b.shape[0]] = b
+            o += b.shape[0]
+        return out
+
+    def design_matrix(self):
+        return self._assemble("F")
+
+    def stationary_covariance(self):
+        return self._assemble("P")
+
+    def observation_model(self, X):
+        return self._assemble("h")
+
+    def transition_matrix(self, X1, X2):
+        """the ADJOINT transition matrix between two coordinates, as in the reference (quasisep.py:88-95)"""
+        return self._assemble("T", float(X2) - float(X1))
 
     def to_symm_qsm(self, X):
         """quasisep.py:102-116: the SymmQSM of this kernel at the sorted coordinates X, generated on the device (d, p, q,
@@ -154,6 +204,90 @@ class Quasisep(Kernel):
         return Scale(kernel=self, scale=other)
 
 
+def _prod(a1, a2):
+    """`_prod_helper` (quasisep.py:676-687): Kronecker structure with the FIRST factor's index running fastest"""
+    a1, a2 = np.asarray(a1, dtype=np.float64), np.asarray(a2, dtype=np.float64)
+    i, j = np.meshgrid(np.arange(a1.shape[0]), np.arange(a2.shape[0]))
+    i, j = i.flatten(), j.flatten()
+    if a1.ndim == 1:
+        return a1[i] * a2[j]
+    return a1[i[:, None], i[None, :]] * a2[j[:, None], j[None, :]]
+
+
+def _leaf_state_space(row, what, dt=None):
+    """F (design matrix), P (stationary covariance incl. the row's Pinf scale), h (observation model) or T(dt) (adjoint
+    transition matrix) of ONE component row -- the host twin of build_model / qs_leaf_transition in csrc/qs_core.cuh"""
+    kind, ps, p0, p1, p2, p3, _, p4 = row[:8]
+    kind = int(kind)
+    if kind == QS_EXP:                                          # quasisep.py:491-525 (p2: a CARMA real root's rate)
+        rate = p2 if p2 != 0.0 else 1.0 / p0
+        return {"F": lambda: np.array([[-rate]]), "P": lambda: ps * np.ones((1, 1)), "h": lambda: np.array([p1]),
+                "T": lambda: np.array([[np.exp(-rate * dt)]])}[what]()
+    if kind == QS_MATERN32:                                     # quasisep.py:528-569
+        f = np.sqrt(3.0) / p0
+        return {"F": lambda: np.array([[0.0, 1.0], [-f * f, -2 * f]]), "P": lambda: ps * np.diag([1.0, 3.0 / (p0 * p0)]),
+                "h": lambda: np.array([p1, 0.0]),
+                "T": lambda: np.exp(-f * dt) * np.array([[1 + f * dt, -f * f * dt], [dt, 1 - f * dt]])}[what]()
+    if kind == QS_MATERN52:                                     # quasisep.py:572-633
+        f = np.sqrt(5.0) / p0
+        f2 = f * f
+        if what == "F":
+            return np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [-f2 * f, -3 * f2, -3 * f]])
+        if what == "P":
+            return ps * np.array([[1.0, 0.0, -f2 / 3], [0.0, f2 / 3, 0.0], [-f2 / 3, 0.0, f2 * f2]])
+        if what == "h":
+            return np.array([p1, 0.0, 0.0])
+        d2 = dt * dt
+        return np.exp(-f * dt) * np.array([
+            [0.5 * f2 * d2 + f * dt + 1, -0.5 * f * f2 * d2, 0.5 * f2 * f * dt * (f * dt - 2)],
+            [dt * (f * dt + 1), -f2 * d2 + f * dt + 1, f2 * dt * (f * dt - 3)],
+            [0.5 * d2, 0.5 * dt * (2 - f * dt), 0.5 * f2 * d2 - 2 * f * dt + 1]])
+    if kind == QS_SHO:                                          # quasisep.py:404-488: p0 = omega, p1 = quality, p2 = sigma
+        w, q = p0, p1
+        if what == "F":
+            return np.array([[0.0, 1.0], [-w * w, -w / q]])
+        if what == "P":
+            return ps * np.diag([1.0, w * w])
+        if what == "h":
+            return np.array([p2, 0.0])
+        if np.allclose(q, 0.5):
+            return np.exp(-w * dt) * np.array([[1 + w * dt, -w * w * dt], [dt, 1 - w * dt]])
+        under = q > 0.5
+        f = np.sqrt(max(4 * q * q - 1, 0.0)) if under else np.sqrt(max(1 - 4 * q * q, 0.0))
+        arg = 0.5 * f * w * dt / q
+        sn, cs = (np.sin(arg), np.cos(arg)) if under else (np.sinh(arg), np.cosh(arg))
+        return np.exp(-0.5 * w * dt / q) * np.array([[cs + sn / f, -2 * q * w * sn / f], [2 * q * sn / (w * f), cs - sn / f]])
+    if kind in (QS_CELERITE, QS_CARMA2):                        # quasisep.py:343-401 / one complex CARMA pair (:770-900)
+        if kind == QS_CELERITE:
+            a, b, c, d = p0, p1, p2, p3
+            c2, d2 = c * c, d * d
+            h2_2 = d2 * (a * c - b * d) / (2 * c * (c2 + d2))
+            h2 = np.sqrt(h2_2)
+            h = np.array([(c * h2 - np.sqrt(a * d2 - (c2 + d2) * h2_2)) / d, h2])
+            sgn = 1.0
+        else:
+            c, d, h, sgn = p0, p1, np.array([p2, p3]), p4
+        if what == "F":
+            return np.array([[-c, -d], [d, -c]])
+        if what == "P":
+            return ps * np.array([[sgn, -c / d], [-c / d, sgn + 2 * (c / d) ** 2]])
+        if what == "h":
+            return h
+        cs, sn = np.cos(d * dt), np.sin(d * dt)
+        return np.exp(-c * dt) * np.array([[cs, sn], [-sn, cs]])
+    if kind == QS_COSINE:                                       # quasisep.py:636-673
+        f = 2 * np.pi / p0
+        if what == "F":
+            return np.array([[0.0, -f], [f, 0.0]])
+        if what == "P":
+            return ps * np.eye(2)
+        if what == "h":
+            return np.array([p1, 0.0])
+        cs, sn = np.cos(f * dt), np.sin(f * dt)
+        return np.array([[cs, sn], [-sn, cs]])
+    raise ValueError(f"unknown quasiseparable component kind {kind}")
+
+
 class Sum(Quasisep):
     """quasisep.py:241-295"""
 
@@ -187,28 +321,35 @@ class Scale(Quasisep):
 
 class Product(Quasisep):
     """quasisep.py:298-331: the state of the product is Kronecker-structured (``_prod_helper``, :676-687, first kernel's
-    index fastest).  Supported for factors that are single terms (leaves, scaled leaves, products); a Sum inside a Product
-    would interleave the blocks of the reference's state ordering and is refused."""
+    index fastest).  The device model chains the leaves of ONE term; a Sum inside a Product is multiplied out on the host,
+    (a + b) * c == a * c + b * c, which gives the same kernel with the reference's state vector permuted (block of a * c,
+    then block of b * c, instead of the interleaved Kronecker order) -- every solver result is unchanged by that."""
 
     def __init__(self, kernel1, kernel2):
         self.kernel1, self.kernel2 = kernel1, kernel2
 
     def components(self):
-        def single_term(rows):
-            return all(len(r) > 6 and r[6] for r in rows[:-1]) and not (len(rows[-1]) > 6 and rows[-1][6])
-        r1, r2 = self.kernel1.components(), self.kernel2.components()
-        if not (single_term(r1) and single_term(r2)):
-            raise NotImplementedError("a Product of quasiseparable Sums is unsupported by the B200 quasiseparable solver "
-                                      "backend (multiply the terms out: (a + b) * c == a * c + b * c)")
-        pad = lambda r: tuple(r) + (0.0,) * (7 - len(r))       # noqa: E731
-        rows = [pad(r) for r in r1] + [pad(r) for r in r2]
-        rows[len(r1) - 1] = rows[len(r1) - 1][:6] + (1.0,)
-        dim = 1
-        for r in rows:
-            dim *= STATE_DIM[int(r[0])]
-        if dim > 6 or len(rows) > 3:
-            raise NotImplementedError("a Product with more than 3 factors or a state dimension above 6 is unsupported by the "
-                                      "B200 quasiseparable solver backend")
+        def terms(rows):
+            out, cur = [], []
+            for r in rows:
+                r = tuple(r) + (0.0,) * (7 - len(r))
+                cur.append(r)
+                if not r[6]:
+                    out.append(cur)
+                    cur = []
+            return out
+        rows = []
+        for t1 in terms(self.kernel1.components()):
+            for t2 in terms(self.kernel2.components()):
+                term = list(t1) + list(t2)
+                term[len(t1) - 1] = term[len(t1) - 1][:6] + (1.0,) + term[len(t1) - 1][7:]      # mul_next; slot 7 (CARMA2's sign) kept
+                dim = 1
+                for r in term:
+                    dim *= STATE_DIM[int(r[0])]
+                if dim > 6 or len(term) > 3:
+                    raise NotImplementedError("a Product with more than 3 factors or a state dimension above 6 is "
+                                              "unsupported by the B200 quasiseparable solver backend")
+                rows += term
         return rows
 
     def tau_program(self, dist):

@@ -208,6 +208,8 @@ void generators_host(const QsModel& m, const double* t, int64_t n, double* a_out
         case 4: { constexpr int JJ = 4; CALL; } break; \
         case 5: { constexpr int JJ = 5; CALL; } break; \
         case 6: { constexpr int JJ = 6; CALL; } break; \
+        case 7: { constexpr int JJ = 7; CALL; } break; \
+        case 8: { constexpr int JJ = 8; CALL; } break; \
         default: return 3;                          \
     }
 

@@ -221,7 +221,9 @@ static void qs_affine_J(b200gp_qs* s, const double* x, double* out, double* sums
         case 4: { constexpr int JJ = 4; CALL; } break;                   \
         case 5: { constexpr int JJ = 5; CALL; } break;                   \
         case 6: { constexpr int JJ = 6; CALL; } break;                   \
-        default: throw GpError("quasisep: state dimension > 6 is not compiled in"); \
+        case 7: { constexpr int JJ = 7; CALL; } break;                   \
+        case 8: { constexpr int JJ = 8; CALL; } break;                   \
+        default: throw GpError("quasisep: state dimension > 8 is not compiled in"); \
     }
 
 static void qs_affine(b200gp_qs* s, int op, const double* x, double* out, double* sumsq_dev) {

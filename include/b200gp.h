@@ -165,6 +165,10 @@ int b200gp_dense_dot_triangular(b200gp_dense* s, double* Y, int64_t nrhs);
 /* condition (direct.py:75-95): out (m, m) = Kss - A^T A, A = L^-1 Ks; Xtest NULL => X. */
 int b200gp_dense_condition(b200gp_dense* s, const double* prog, int n_instr,
                            const double* Xtest, int64_t m, const double* diag_test, double* out);
+/* C (m, m) <- C - At At^T, At (m, k) row-major, host operands: "Kss - A.T @ A" (direct.py:93-95; quasisep solver.py:137-139)
+ * for solvers without a kernel program on the device (a factor of a precomputed covariance -- noise.Dense / noise.Banded,
+ * noise.py:98-240 -- or of generator arrays); the host passes A^T from its own solve_triangular call. */
+int b200gp_gram_downdate(b200gp_ctx* ctx, const double* At, int64_t m, int64_t k, double* C);
 /* covariance() (direct.py:58-59): regenerated by the build kernel; only valid for objects
  * created from a program.  out (n, n). */
 int b200gp_dense_covariance(b200gp_dense* s, double* out);

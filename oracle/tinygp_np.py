@@ -343,6 +343,57 @@ class Diagonal:
         return self.diag * other if other.ndim == 1 else self.diag[:, None] * other
 
 
+class Dense:
+    """noise.py:98-123: a full-rank N x N observation model"""
+
+    def __init__(self, value):
+        self.value = np.asarray(value, dtype=np.float64)
+
+    def diagonal(self):
+        return np.diag(self.value)
+
+    def add_to(self, other):  # noise.py:109-113
+        return self.value + np.asarray(other, dtype=np.float64)
+
+    def matmul(self, other):  # noise.py:115-116
+        return self.value @ np.asarray(other, dtype=np.float64)
+
+
+class Banded:
+    """noise.py:126-240: diag (N,) and J symmetric off-diagonals, off_diags[n, j] = N[n, n + j + 1]"""
+
+    def __init__(self, diag, off_diags):
+        self.diag = np.asarray(diag, dtype=np.float64)
+        self.off_diags = np.asarray(off_diags, dtype=np.float64)
+
+    def diagonal(self):
+        return self.diag
+
+    def add_to(self, other):  # noise.py:196-215
+        out = np.array(other, dtype=np.float64, copy=True)
+        N, J = self.off_diags.shape
+        for n in range(N):
+            out[n, n] += self.diag[n]
+            for j in range(J):
+                if n + j + 1 < N:
+                    out[n, n + j + 1] += self.off_diags[n, j]
+                    out[n + j + 1, n] += self.off_diags[n, j]
+        return out
+
+    def matmul(self, other):  # noise.py:223-224 (to_qsm() @ other: the same banded matrix)
+        N = self.diag.shape[0]
+        return self.add_to(np.zeros((N, N))) @ np.asarray(other, dtype=np.float64)
+
+    def to_qsm_arrays(self):  # noise.py:226-240: (d, p, q, a) with p = e_1, q = off_diags, a = the upper shift
+        N, J = self.off_diags.shape
+        p = np.zeros((N, J))
+        p[:, 0] = 1.0
+        a = np.zeros((N, J, J))
+        for j in range(J - 1):
+            a[:, j, j + 1] = 1.0
+        return self.diag, p, self.off_diags, a
+
+
 # ----------------------------------------------------------------------------
 # solvers/direct.py
 # ----------------------------------------------------------------------------
@@ -912,7 +963,16 @@ class QuasisepSolver:
         if not assume_sorted and np.any(np.diff(X) < 0.0):              # solver.py:142-146
             raise ValueError("Input coordinates must be sorted in order to use the QuasisepSolver")
         d, p, q, a = kernel.to_symm_qsm(X)                               # solver.py:73
-        d = d + noise.diagonal()                                         # solver.py:74 ; core.py:161-163
+        if hasattr(noise, "to_qsm_arrays"):
+            # noise.Banded: SymmQSM + SymmQSM (core.py:161-163 -> StrictLowerTriQSM.self_add, core.py:208-214: p and q are
+            # concatenated, a is block-diagonal)
+            dn, pn, qn, an = noise.to_qsm_arrays()
+            J1, J2 = p.shape[1], pn.shape[1]
+            aa = np.zeros((X.shape[0], J1 + J2, J1 + J2))
+            aa[:, :J1, :J1], aa[:, J1:, J1:] = a, an
+            d, p, q, a = d + dn, np.concatenate((p, pn), axis=1), np.concatenate((q, qn), axis=1), aa
+        else:
+            d = d + noise.diagonal()                                     # solver.py:74 ; core.py:161-163
         self.X, self.kernel = X, kernel
         self.d, self.p, self.q, self.a = d, p, q, a
         self.c, self.w = qs_cholesky(d, p, q, a)                         # solver.py:82 ; core.py:524-539

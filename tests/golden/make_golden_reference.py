@@ -20,7 +20,7 @@ import refimport  # noqa: E402
 
 def reference_namespace():
     tinygp = refimport.install()
-    from tinygp import GaussianProcess, kernels, transforms
+    from tinygp import GaussianProcess, kernels, noise, transforms
     from tinygp.kernels import quasisep
 
     def qs_factor(gp):
@@ -28,7 +28,7 @@ def reference_namespace():
         return np.asarray(f.diag.d), np.asarray(f.lower.q)
 
     assert tinygp.__file__.startswith(refimport.REFERENCE_SRC)
-    return refcases.Namespace("reference", GaussianProcess, kernels, quasisep, transforms, qs_factor)
+    return refcases.Namespace("reference", GaussianProcess, kernels, quasisep, transforms, qs_factor, noise=noise)
 
 
 def main():

@@ -18,8 +18,8 @@ import numpy as np
 class Namespace:
     """what a case may use: GaussianProcess, kernels, quasisep, transforms + three accessors that differ by backend"""
 
-    def __init__(self, name, GaussianProcess, kernels, quasisep, transforms, qs_factor, to_np=np.asarray):
-        self.name, self.GaussianProcess = name, GaussianProcess
+    def __init__(self, name, GaussianProcess, kernels, quasisep, transforms, qs_factor, to_np=np.asarray, noise=None):
+        self.name, self.GaussianProcess, self.noise = name, GaussianProcess, noise
         self.kernels, self.quasisep, self.transforms = kernels, quasisep, transforms
         self.qs_factor, self.to_np = qs_factor, to_np
 
@@ -100,9 +100,24 @@ CASES = [
     dict(name="qs_carma21_real", kind="quasisep", kernel="quasisep.CARMA(alpha=np.array([0.1, 1.1]), beta=np.array([1.0, 3.0]))", n=120, span=30.0, diag=0.05, seed=33),
     dict(name="qs_carma10", kind="quasisep", kernel="quasisep.CARMA(alpha=np.array([1.0 / 100]), beta=np.array([0.3]))", n=120, span=30.0, diag=0.05, seed=34),
     dict(name="qs_carma_plus_m32", kind="quasisep", kernel="quasisep.CARMA.init(alpha=np.array([1.4, 2.3, 1.5]), beta=np.array([0.1, 0.5])) + 0.5 * quasisep.Matern32(1.5)", n=120, span=30.0, diag=0.05, seed=35),
+    # noise.Banded / noise.Dense (noise.py:98-240): the precomputed-covariance paths of both solvers
+    dict(name="qs_m32_sho_noise_banded2", kind="quasisep", kernel="quasisep.Matern32(scale=1.5, sigma=1.8) + quasisep.SHO(omega=1.2, quality=2.0, sigma=0.7)", n=120, span=30.0, seed=41, noise="banded", band=2),
+    dict(name="qs_exp_noise_banded5", kind="quasisep", kernel="quasisep.Exp(scale=1.7, sigma=0.8)", n=120, span=30.0, seed=42, noise="banded", band=5),
+    dict(name="m52_3d_noise_dense", kind="dense", kernel="0.8 * kernels.Matern52(1.1)", n=90, d=3, span=4.0, seed=43, noise="dense"),
+    dict(name="expsq_1d_noise_banded3", kind="dense", kernel="1.2 * kernels.ExpSquared(0.7)", n=90, d=1, span=8.0, seed=44, noise="banded", band=3),
     dict(name="qs_scaled_sum3_parallel", kind="quasisep", kernel="2.0 * quasisep.Matern32(1.2) + quasisep.SHO(0.8, 4.0, 0.6) + 0.5 * quasisep.Exp(5.0)", n=120, span=30.0, diag=0.05, seed=28, parallel=True),
 ]
 # fmt: on
+
+
+def _noise(ns, case, n):
+    """noise.Banded / noise.Dense (noise.py:98-240) instead of a diagonal: seeded, diagonally dominant"""
+    rng = np.random.default_rng(case["seed"] + 7)
+    diag = rng.uniform(0.1, 0.2, n)
+    if case["noise"] == "banded":
+        return ns.noise.Banded(diag=diag, off_diags=0.02 * rng.normal(size=(n, case.get("band", 2))))
+    R = rng.normal(size=(n, 3))
+    return ns.noise.Dense(value=np.diag(diag) + 0.02 * (R @ R.T))
 
 
 def run_case(ns, case):
@@ -117,6 +132,8 @@ def run_case(ns, case):
         kw["mean"] = case["mean"]
     if case.get("parallel"):
         kw["parallel"] = True
+    if "noise" in case:
+        kw["noise"] = _noise(ns, case, case["n"])
     to_np = ns.to_np
     out = {}
     gp = ns.GaussianProcess(k, X, **kw)

@@ -321,6 +321,12 @@ class MockLib:
         arr(outp, (m, m))[:] = kmat(P, Xt, Xt) + np.diag(arr(diag, (m,))) - A.T @ A       # direct.py:88-95
         return 0
 
+    def b200gp_gram_downdate(self, ctx, At, m, k, C):
+        self.calls.append("gram_downdate")
+        a = arr(At, (m, k))
+        arr(C, (m, m))[:] -= a @ a.T
+        return 0
+
     def b200gp_dense_covariance(self, h, outp):
         d = self._get(h)
         arr(outp, (d.n, d.n))[:] = d.K
@@ -332,6 +338,10 @@ class MockLib:
         return 0
 
     # -- quasisep -----------------------------------------------------------------------------
+    def b200gp_qs_check_sorted(self, ctx, t, n, unsorted):
+        out(unsorted).value = int(np.any(np.diff(arr(t, (n,))) < 0.0))      # solver.py:142-146
+        return 0
+
     def b200gp_qs_create(self, ctx, comps, ncomp, t, n, diag, assume_sorted, href, unsorted, info):
         self.calls.append("qs_create")
         tt = arr(t, (n,)).copy()

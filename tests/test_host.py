@@ -63,8 +63,8 @@ def test_unsupported_kernels_raise():
         kernels.ExpSineSquared()
     with pytest.raises(ValueError):
         kernels.Constant(np.ones(3))
-    with pytest.raises(NotImplementedError):
-        noise.Dense(np.eye(3))
+    with pytest.raises(NotImplementedError):      # noise.py:121-123: no quasiseparable form
+        noise.Dense(np.eye(3)).to_qsm()
 
 
 def test_quasisep_components():

@@ -42,7 +42,11 @@ def test_host_layer_reproduces_reference_goldens(mocklib, case):
     compare(got, GOLD["cases"][case["name"]], case["name"], tol=1e-9)
     if not np.isfinite(got["log_probability"]):
         return                                  # non-PD: the reference says -inf and nothing else is defined
-    if case["kind"] == "quasisep":
+    if "noise" in case:
+        # noise.Banded / noise.Dense: a factor of a precomputed covariance; Kss - A^T A is the device GEMM entry point
+        assert "gram_downdate" in mocklib.calls
+        assert ("qsm_cholesky" if case["kind"] == "quasisep" else "dense_create_from_cov") in mocklib.calls
+    elif case["kind"] == "quasisep":
         # conditioning goes through the device entry point, never through host linear algebra
         assert "qs_condition" in mocklib.calls and "qs_kernel_matmul" in mocklib.calls
     else:

@@ -87,12 +87,7 @@ def test_condition_shape_error(gp_data):                             # test_gp.p
 
 
 # ---- tests/test_noise.py ------------------------------------------------------------------------------------
-def test_diagonal():                                                 # test_noise.py:10-46
-    N = 50
-    rng = np.random.default_rng(9432)
-    diag = rng.normal(size=N)
-    nz = tinygp.noise.Diagonal(diag=diag)
-    dense = np.diag(diag)
+def check_noise_model(nz, dense):                                    # test_noise.py:10-37
     rng = np.random.default_rng(6675)
     assert_allclose(nz.diagonal(), np.diag(dense))
     assert_allclose(nz + np.zeros_like(dense), dense)
@@ -100,19 +95,68 @@ def test_diagonal():                                                 # test_nois
     assert_allclose(nz + y1, dense + y1)
     assert_allclose(y1 + nz, y1 + dense)
     assert_allclose(nz @ y1, dense @ y1)
-    y2 = rng.normal(size=(N, 3))
+    y2 = rng.normal(size=(dense.shape[1], 3))
     assert_allclose(nz @ y2, dense @ y2)
-    y3 = rng.normal(size=N)
+    y3 = rng.normal(size=dense.shape[1])
     assert_allclose(nz @ y3, dense @ y3)
+    try:
+        qsm = nz.to_qsm()
+    except NotImplementedError:
+        pass
+    else:
+        assert_allclose(qsm @ y1, dense @ y1)
+        assert_allclose(qsm @ y2, dense @ y2)
+        assert_allclose(qsm @ y3, dense @ y3)
+
+
+def test_diagonal():                                                 # test_noise.py:40-45
+    N = 50
+    diag = np.random.default_rng(9432).normal(size=N)
+    check_noise_model(tinygp.noise.Diagonal(diag=diag), np.diag(diag))
     with pytest.raises(ValueError):                                  # noise.py:67-72
         tinygp.noise.Diagonal(diag=np.float64(0.1))
 
 
-def test_banded_and_dense_are_refused():                             # test_noise.py:49-71: unsupported, loudly
-    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
-        tinygp.noise.Dense(value=np.eye(3))
-    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
-        tinygp.noise.Banded(diag=np.ones(3), off_diags=np.zeros((3, 1)))
+def test_banded():                                                   # test_noise.py:48-65
+    N, J = 50, 5
+    R = np.random.default_rng(9432).normal(size=(N, N))
+    R[np.triu_indices(N, J + 1)] = 0
+    R[np.tril_indices(N)] = R.T[np.tril_indices(N)]
+    off_diags = np.zeros((N, J))
+    for j in range(J):
+        off_diags[: N - j - 1, j] = R[(np.arange(0, N - j - 1), np.arange(j + 1, N))]
+    check_noise_model(tinygp.noise.Banded(diag=np.diag(R), off_diags=off_diags), R)
+
+
+def test_dense():                                                    # test_noise.py:68-73
+    M = np.random.default_rng(9432).normal(size=(50, 50))
+    check_noise_model(tinygp.noise.Dense(value=M), M)
+
+
+def test_gp_with_banded_and_dense_noise_on_both_solvers():
+    """noise.Banded on the QuasisepSolver (solver.py:73-74: a SymmQSM sum) equals the same model on the DirectSolver
+    (direct.py:47-48), which equals noise.Dense of the dense band -- log_probability, conditioning at new points, at the inputs"""
+    rng = np.random.default_rng(5)
+    x = np.sort(rng.uniform(0, 10, 60))
+    y, xs = np.sin(x), np.linspace(-1, 11, 9)
+    banded = tinygp.noise.Banded(diag=rng.uniform(0.1, 0.2, 60), off_diags=0.02 * rng.normal(size=(60, 2)))
+    dense = tinygp.noise.Dense(value=banded + np.zeros((60, 60)))
+    kq = quasisep.Matern32(1.5) + quasisep.SHO(omega=1.2, quality=2.0, sigma=0.7)
+    gps = [GaussianProcess(kq, x, noise=banded), GaussianProcess(kq, x, noise=banded, solver=DirectSolver),
+           GaussianProcess(kq, x, noise=dense, solver=DirectSolver)]
+    assert isinstance(gps[0].solver, QuasisepSolver) and gps[0].solver._generic
+    ref = gps[2]
+    for gp in gps[:2]:
+        assert_allclose(gp.log_probability(y), ref.log_probability(y))
+        assert_allclose(gp.covariance, ref.covariance)
+        for kw in (dict(X_test=xs), dict()):
+            a, b = gp.condition(y, **kw).gp, ref.condition(y, **kw).gp
+            assert_allclose(a.loc, b.loc)
+            assert_allclose(a.covariance, b.covariance)
+    with pytest.raises(NotImplementedError):                         # noise.py:121-123
+        GaussianProcess(kq, x, noise=dense)                          # -> QuasisepSolver -> dense.to_qsm()
+    with pytest.raises(ValueError, match="Input coordinates must be sorted"):
+        GaussianProcess(kq, x[::-1], noise=banded)
 
 
 # ---- tests/test_kernels/test_kernels.py -----------------------------------------------------------------------

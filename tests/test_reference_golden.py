@@ -34,7 +34,7 @@ def oracle_namespace():
     def qs_factor(gp):
         return gp.solver.c, gp.solver.w
 
-    return refcases.Namespace("oracle", o.GaussianProcess, o, o.qs, o, qs_factor)
+    return refcases.Namespace("oracle", o.GaussianProcess, o, o.qs, o, qs_factor, noise=o)
 
 
 def product_namespace():
@@ -45,7 +45,7 @@ def product_namespace():
     def qs_factor(gp):
         return gp.solver.factor_arrays()
 
-    return refcases.Namespace("product", tg.GaussianProcess, kernels, quasisep, transforms, qs_factor)
+    return refcases.Namespace("product", tg.GaussianProcess, kernels, quasisep, transforms, qs_factor, noise=tg.noise)
 
 
 def compare(got, want, name, tol=None):

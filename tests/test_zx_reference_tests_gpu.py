@@ -19,9 +19,9 @@ def _clone(fn):
     return wrapper
 
 
-# every test of the CPU module except the ones that only assert refusals / pure host behaviour
+# every test of the CPU module except the ones that only assert pure host behaviour
 # test_consistent_with_direct needs first-run device code (b200gp_qs_condition, GramBack): it runs in test_zzy_*
-_SKIP = {"test_banded_and_dense_are_refused", "test_diagonal", "test_consistent_with_direct"}
+_SKIP = {"test_diagonal", "test_dense", "test_consistent_with_direct"}
 for _name in dir(_cpu):
     if _name.startswith("test_") and _name not in _SKIP:
         globals()[_name] = _clone(getattr(_cpu, _name))

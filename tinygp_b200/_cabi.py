@@ -65,6 +65,7 @@ SIGNATURES = {
     "b200gp_dense_solve_triangular": (c_int, [_V, _D, _L, _I]),
     "b200gp_dense_dot_triangular": (c_int, [_V, _D, _L]),
     "b200gp_dense_condition": (c_int, [_V, _D, _I, _D, _L, _D, _D]),
+    "b200gp_gram_downdate": (c_int, [_V, _D, _L, _L, _D]),
     "b200gp_dense_covariance": (c_int, [_V, _D]),
     "b200gp_dense_get_factor": (c_int, [_V, _D]),
     "b200gp_dense_log_probability": (c_int, [_V, _D, _I, _D, _L, _I, _D, _D, c_double_p]),

@@ -1648,6 +1648,30 @@ int b200gp_dense_condition(b200gp_dense* s, const double* prog, int n_instr, con
     API_END
 }
 
+// C (m, m) <- C - At At^T for host operands, At (m, k) row-major: the Kss - A^T A of direct.py:93-95 / quasisep solver.py:131-139
+// for solvers that have no kernel program on the device (a factor of a precomputed covariance, i.e. noise.Dense / noise.Banded,
+// or of generator arrays): the host passes A^T = (L^-1 Ks)^T from its own triangular solve.  fp64 DMMA GEMM, operands zero
+// padded to the 128-tile.
+int b200gp_gram_downdate(b200gp_ctx* ctx, const double* At, int64_t m, int64_t k, double* C) {
+    API_BEGIN(ctx)
+    if (m <= 0 || k <= 0) throw GpError("gram_downdate: empty operand");
+    const int64_t mp = ((m + TILE - 1) / TILE) * TILE, kp = ((k + TILE - 1) / TILE) * TILE;
+    Scratch a_buf(_ctx, (size_t)mp * kp * 8), c_buf(_ctx, (size_t)mp * mp * 8);
+    double* const a = a_buf.f64();
+    double* const c = c_buf.f64();
+    CUDA_CHECK(cudaMemsetAsync(a, 0, (size_t)mp * kp * 8, _ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(c, 0, (size_t)mp * mp * 8, _ctx->stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(a, (size_t)kp * 8, At, (size_t)k * 8, (size_t)k * 8, (size_t)m, cudaMemcpyHostToDevice,
+                                 _ctx->stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(c, (size_t)mp * 8, C, (size_t)m * 8, (size_t)m * 8, (size_t)m, cudaMemcpyHostToDevice,
+                                 _ctx->stream));
+    gemm_nt(_ctx, c, mp, a, kp, a, kp, (int)(mp / TILE), (int)(mp / TILE), (int)kp, -1.0, 1, 0);
+    CUDA_CHECK(cudaMemcpy2DAsync(C, (size_t)m * 8, c, (size_t)mp * 8, (size_t)m * 8, (size_t)m, cudaMemcpyDeviceToHost,
+                                 _ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(_ctx->stream));
+    API_END
+}
+
 int b200gp_dense_covariance(b200gp_dense* s, double* out) {
     API_BEGIN(s->ctx)
     if (!s->has_prog) throw GpError("covariance: solver was built from a precomputed covariance; the host keeps it");

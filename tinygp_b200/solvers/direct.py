@@ -12,6 +12,7 @@ import numpy as np
 
 from tinygp_b200 import _cabi
 from tinygp_b200.kernels.base import Kernel, _as_coords
+from tinygp_b200.noise import Diagonal
 from tinygp_b200.solvers.solver import ConditionedCovariance, Solver
 
 
@@ -28,6 +29,10 @@ class DirectSolver(Solver):
         self._info = 0
         info = c_int(0)
         lib = self._ctx.lib
+        if covariance is None and not isinstance(noise, Diagonal):
+            # noise.Dense / noise.Banded (direct.py:47-48: covariance = kernel(X, X) + noise): the kernel matrix is built on
+            # the device, the noise matrix joins it on its way to the device factorisation of a precomputed covariance
+            covariance = noise + kernel(X, X)
         if covariance is None:
             prog, x = kernel.lower_for(X)   # x = X, plus host-computed columns of any transforms.Transform
             diag = _cabi.f64(noise.diagonal())
@@ -157,8 +162,16 @@ class DirectSolver(Solver):
     def condition(self, kernel: Kernel, X_test, noise) -> Any:  # direct.py:75-95
         diag = _cabi.f64(noise.diagonal())
         if self._x is None:
-            raise NotImplementedError("condition() of a solver built from a precomputed covariance is unsupported by the "
-                                      "B200 solver backend (there are no training coordinates on the device)")
+            # a factor of a precomputed covariance (noise.Dense / noise.Banded, or a conditioned process) has no kernel
+            # program on the device: direct.py:75-95 call by call -- Ks and Kss from the build kernel, A from the blocked
+            # substitution, Kss - A^T A from the fp64 GEMM behind b200gp_gram_downdate
+            Xs = self.X if X_test is None else X_test
+            A = self.solve_triangular(kernel(self.X, Xs))
+            out = np.ascontiguousarray(noise + kernel(Xs, Xs))
+            At = np.ascontiguousarray(A.T)
+            self._ctx.check(self._ctx.lib.b200gp_gram_downdate(self._ctx.handle, _cabi.ptr(At), At.shape[0], At.shape[1],
+                                                               _cabi.ptr(out)))
+            return ConditionedCovariance.tag(out, True)
         # b200gp_dense_condition evaluates the predictive kernel on the TRAINING coordinates kept on the device, i.e. in
         # the training kernel's lowered layout (raw columns + the host-computed columns of any transforms.Transform).
         # A predictive kernel that lowers the training inputs differently (other width, other transform outputs) would

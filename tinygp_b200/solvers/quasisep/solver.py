@@ -12,6 +12,7 @@ import numpy as np
 
 from tinygp_b200 import _cabi
 from tinygp_b200.kernels.quasisep import Quasisep
+from tinygp_b200.noise import Diagonal
 from tinygp_b200.solvers.quasisep import core as qcore
 from tinygp_b200.solvers.solver import ConditionedCovariance, Solver
 
@@ -31,6 +32,20 @@ class QuasisepSolver(Solver):
         self._h = c_void_p()
         self.kernel, self.noise, self.parallel = kernel, noise, parallel
         self._matrix = self._factor = None
+        if covariance is None and not isinstance(noise, Diagonal):
+            # noise.Banded (noise.py:226-240): solver.py:73-74 as written -- the kernel's SymmQSM plus the noise's, a device
+            # SymmQSM of order J + J_band, factored from its generator arrays
+            if not isinstance(kernel, Quasisep):
+                raise ValueError("QuasisepSolver requires a tinygp_b200.kernels.quasisep.Quasisep kernel")
+            X = _cabi.f64(kernel.coord_to_sortable(X))
+            if X.ndim != 1:
+                raise ValueError("QuasisepSolver takes 1-D sortable coordinates")
+            if not assume_sorted:
+                unsorted = c_int(0)
+                self._ctx.check(self._ctx.lib.b200gp_qs_check_sorted(self._ctx.handle, _cabi.ptr(X), X.shape[0], byref(unsorted)))
+                if unsorted.value:
+                    raise ValueError(_UNSORTED_MSG)
+            covariance = kernel.to_symm_qsm(X) + noise.to_qsm()
         if covariance is not None:
             if not isinstance(covariance, qcore.SymmQSM):
                 raise ValueError("QuasisepSolver(covariance=...) takes a tinygp_b200.solvers.quasisep.core.SymmQSM")
@@ -234,8 +249,15 @@ class QuasisepSolver(Solver):
             M = M + noise.to_qsm()
             return M - delta
         if self._generic:
-            raise NotImplementedError("the dense branch of QuasisepSolver.condition (solver.py:131-139) is not available "
-                                      "for a solver built from a precomputed SymmQSM")
+            # generator arrays (noise.Banded, or a conditioned process): solver.py:131-139 call by call -- Ks and Kss from the
+            # build kernel, A = factor.solve(Ks) by the QSM scans, Kss - A^T A from the fp64 GEMM (b200gp_gram_downdate)
+            Xs = self.X if X_test is None else X_test
+            A = self._factor.solve(kernel(self.X, Xs))
+            out = np.ascontiguousarray(kernel(Xs, Xs))
+            At = np.ascontiguousarray(A.T)
+            self._ctx.check(self._ctx.lib.b200gp_gram_downdate(self._ctx.handle, _cabi.ptr(At), At.shape[0], At.shape[1],
+                                                               _cabi.ptr(out)))
+            return ConditionedCovariance.tag(out, False)
         if X_test is None:
             prog, x = kernel.lower_for(self.X)
             xt_ptr, m = None, self._n

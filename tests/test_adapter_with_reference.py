@@ -122,5 +122,26 @@ def test_unsupported_objects_are_refused_loudly(tinygp):
     X = np.linspace(0, 1, 5)
     with pytest.raises(NotImplementedError, match="unsupported by the B200"):
         GaussianProcess(kernels.DotProduct(), X, diag=0.1, solver=adapter.DirectSolver)
-    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
-        GaussianProcess(kernels.ExpSquared(), X, noise=noise.Dense(np.eye(5)), solver=adapter.DirectSolver)
+
+
+def test_reference_gaussian_process_with_banded_and_dense_noise(tinygp):
+    """the reference's own noise.Banded / noise.Dense objects (noise.py:98-240) through the adapter's solvers"""
+    from tinygp import GaussianProcess, kernels, noise
+    from tinygp.kernels import quasisep
+    rng = np.random.default_rng(8)
+    t = np.sort(rng.uniform(0, 12, 50))
+    tt, y = rng.uniform(-1, 13, 5), np.sin(t)
+    banded = noise.Banded(diag=rng.uniform(0.1, 0.2, 50), off_diags=0.02 * rng.normal(size=(50, 2)))
+    dense = noise.Dense(value=np.asarray(banded + np.zeros((50, 50))))
+    kq = quasisep.Matern32(scale=1.5, sigma=1.8) + quasisep.Exp(scale=0.7)
+    from tinygp.solvers import DirectSolver, QuasisepSolver
+    for k, nz, theirs, solver in ((kq, banded, QuasisepSolver, adapter.QuasisepSolver),
+                                  (kq, banded, DirectSolver, adapter.DirectSolver),
+                                  (kernels.Matern52(1.1), dense, DirectSolver, adapter.DirectSolver)):
+        ref, ours = GaussianProcess(k, t, noise=nz, solver=theirs), GaussianProcess(k, t, noise=nz, solver=solver)
+        _close(ours.log_probability(y), ref.log_probability(y))
+        _close(ours.covariance, ref.covariance)
+        (lp_o, cond_o), (lp_r, cond_r) = ours.condition(y, tt, diag=1e-3), ref.condition(y, tt, diag=1e-3)
+        _close(lp_o, lp_r)
+        _close(cond_o.loc, cond_r.loc)
+        _close(cond_o.covariance, cond_r.covariance)

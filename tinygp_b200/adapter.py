@@ -90,11 +90,15 @@ def translate_kernel(k) -> K.Kernel:
 
 
 def translate_noise(noise) -> N.Noise:
-    """src/tinygp/noise.py:55-95"""
+    """src/tinygp/noise.py:55-240"""
     if isinstance(noise, N.Noise):
         return noise
     if type(noise).__name__ == "Diagonal":
         return N.Diagonal(np.asarray(noise.diag, dtype=np.float64))
+    if type(noise).__name__ == "Banded":      # noise.py:126-240
+        return N.Banded(np.asarray(noise.diag, dtype=np.float64), np.asarray(noise.off_diags, dtype=np.float64))
+    if type(noise).__name__ == "Dense":       # noise.py:98-123
+        return N.Dense(np.asarray(noise.value, dtype=np.float64))
     raise NotImplementedError(f"noise model {type(noise).__name__} is unsupported by the B200 solver backend")
 
 

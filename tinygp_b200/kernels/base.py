@@ -259,9 +259,16 @@ class Conditioned(Kernel):
         if X2 is None:
             K = self.solver.solve_triangular(self.kernel(self.X, X1))
             return self.kernel(X1) - np.sum(K * K, axis=0)
-        K1 = self.solver.solve_triangular(self.kernel(self.X, X1))
-        K2 = self.solver.solve_triangular(self.kernel(self.X, X2))
-        return self.kernel(X1, X2) - K1.T @ K2
+        # the rectangular block of the joint conditioned covariance of [X1; X2]: kernel values from the build kernel, one
+        # triangular solve, and Kss - A^T A by the device GEMM (b200gp_gram_downdate) -- no host matrix product
+        X1, X2 = np.asarray(X1, dtype=np.float64), np.asarray(X2, dtype=np.float64)
+        m1 = X1.shape[0]
+        XX = np.concatenate((X1, X2), axis=0)
+        At = np.ascontiguousarray(self.solver.solve_triangular(self.kernel(self.X, XX)).T)
+        C = np.ascontiguousarray(self.kernel(XX, XX))
+        ctx = _cabi.get_context()
+        ctx.check(ctx.lib.b200gp_gram_downdate(ctx.handle, _cabi.ptr(At), At.shape[0], At.shape[1], _cabi.ptr(C)))
+        return C[:m1, m1:]
 
     def matmul(self, X1, X2=None, y=None):
         if y is None:

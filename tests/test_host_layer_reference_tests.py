@@ -363,11 +363,48 @@ def test_quasisep_kernels(which):                                    # test_quas
     # the state-space model itself (test_quasisep.py:66-72): the kernel value from (h, Pinf, A), and "F is defined
     # consistently with the transition matrix"
     from scipy.linalg import expm
+    from tinygp_b200.solvers.quasisep.block import ensure_dense
     F, Pinf = kernel.design_matrix(), kernel.stationary_covariance()
     for x1, x2 in ((x[3], x[9]), (x[0], x[0]), (x[7], x[41])):
-        A = kernel.transition_matrix(x1, x2)
-        assert_allclose(expm(F.T * (x2 - x1)), A)
+        A = kernel.transition_matrix(x1, x2)                  # a Block for a Sum (quasisep.py:262-270)
+        assert_allclose(expm(ensure_dense(F).T * (x2 - x1)), ensure_dense(A))
         assert_allclose(kernel.observation_model(x2) @ A.T @ Pinf @ kernel.observation_model(x1), kernel.evaluate(x1, x2))
+        assert_allclose(kernel.observation_model(x2) @ ensure_dense(A).T @ ensure_dense(Pinf) @ kernel.observation_model(x1),
+                        kernel.evaluate(x1, x2))
+
+
+# ---- tests/test_solvers/test_quasisep/test_block.py ------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(10,), (10, 3), (4, 10, 3), (2, 4, 10, 3)])
+def test_block(shape):                                               # test_block.py:13-33
+    from scipy.linalg import block_diag
+    from tinygp_b200.solvers.quasisep.block import Block
+    rng = np.random.default_rng(1234)
+    block = Block(*(rng.uniform(size=(s, s)) for s in [1, 3, 2, 4]))
+    x = rng.uniform(size=shape)
+    xt = x if x.ndim == 1 else np.swapaxes(x, -1, -2)
+    block_ = block_diag(*block.blocks)
+    assert len(block) == len(block_)
+    assert block.shape == block_.shape
+    assert_allclose(block @ x, block_ @ x)
+    assert_allclose(xt @ block, xt @ block_)
+    assert_allclose(block.T @ x, block_.T @ x)
+    assert_allclose(xt @ block.T, xt @ block_.T)
+    assert_allclose(block.to_dense(), block_)
+    assert_allclose((block @ block.T).to_dense(), block_ @ block_.T)
+    assert_allclose((2.0 * block + block).to_dense(), 3.0 * block_)
+    assert_allclose(block - block_, np.zeros_like(block_))
+
+
+def test_sum_state_space_is_blocked_like_the_reference():            # kernels/quasisep.py:241-295
+    from tinygp_b200.solvers.quasisep.block import Block
+    k = quasisep.Matern32(1.5) + quasisep.SHO(omega=1.5, quality=0.7) + quasisep.Exp(0.4)
+    T = k.transition_matrix(0.1, 0.9)
+    assert isinstance(T, Block) and [b.shape for b in T.blocks] == [(2, 2), (2, 2), (1, 1)]      # not nested (issue 265)
+    assert isinstance(k.design_matrix(), Block) and isinstance(k.stationary_covariance(), Block)
+    dense = quasisep.Sum(quasisep.Matern32(1.5) + quasisep.SHO(omega=1.5, quality=0.7), quasisep.Exp(0.4), use_block=False)
+    assert isinstance(dense.transition_matrix(0.1, 0.9), np.ndarray)
+    assert_allclose(dense.transition_matrix(0.1, 0.9), T.to_dense())
+    assert_allclose(dense.transition_matrix(0.1, 0.9), quasisep.Quasisep.transition_matrix(k, 0.1, 0.9))   # from the device rows
 
 
 def test_oversized_products_are_refused():                           # what the backend still lacks, refused loudly

@@ -289,10 +289,26 @@ def _leaf_state_space(row, what, dt=None):
 
 
 class Sum(Quasisep):
-    """quasisep.py:241-295"""
+    """quasisep.py:241-295.  ``use_block`` (:247-257): the host-side state-space matrices of a sum come back as
+    ``solvers.quasisep.block.Block`` (default) or dense; the device always works on the block structure."""
 
     def __init__(self, kernel1: Quasisep, kernel2: Quasisep, use_block: bool = True):
         self.kernel1, self.kernel2, self.use_block = kernel1, kernel2, use_block
+
+    def _blocked(self, m1, m2):      # quasisep.py:262-270 (Block objects are not nested)
+        from tinygp_b200.solvers.quasisep.block import Block, ensure_dense
+        if not self.use_block:
+            return Block(ensure_dense(m1), ensure_dense(m2)).to_dense()
+        return Block(*(m1.blocks if isinstance(m1, Block) else (m1,)), *(m2.blocks if isinstance(m2, Block) else (m2,)))
+
+    def design_matrix(self):
+        return self._blocked(self.kernel1.design_matrix(), self.kernel2.design_matrix())
+
+    def stationary_covariance(self):
+        return self._blocked(self.kernel1.stationary_covariance(), self.kernel2.stationary_covariance())
+
+    def transition_matrix(self, X1, X2):
+        return self._blocked(self.kernel1.transition_matrix(X1, X2), self.kernel2.transition_matrix(X1, X2))
 
     def components(self):
         return self.kernel1.components() + self.kernel2.components()

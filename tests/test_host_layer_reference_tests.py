@@ -407,6 +407,42 @@ def test_sum_state_space_is_blocked_like_the_reference():            # kernels/q
     assert_allclose(dense.transition_matrix(0.1, 0.9), quasisep.Quasisep.transition_matrix(k, 0.1, 0.9))   # from the device rows
 
 
+def test_wrapper_kernels():                                          # kernels/quasisep.py:218-238
+    class TimeColumn(quasisep.Wrapper):                              # structured inputs (t, band): the process lives on t
+        def coord_to_sortable(self, X):
+            return np.asarray(X)[..., 0]
+
+    rng = np.random.default_rng(11)
+    t = np.sort(rng.uniform(0, 10, 40))
+    X = np.stack((t, rng.integers(0, 2, 40).astype(float)), axis=1)
+    tt = rng.uniform(-1, 11, 6)
+    Xt = np.stack((tt, np.zeros(6)), axis=1)
+    y = np.sin(t)
+    base = quasisep.Matern32(1.5) + 0.5 * quasisep.SHO(omega=1.2, quality=2.0)
+    wrapped = TimeColumn(base)
+    assert_allclose(wrapped(X, Xt), base(t, tt))
+    assert_allclose(wrapped.to_symm_qsm(X).to_dense(), base(t, t))
+    assert_allclose(wrapped.matmul(Xt, X, y), base(tt, t) @ y)
+    assert_allclose(wrapped.to_general_qsm(Xt, X) @ y, base(tt, t) @ y)
+    assert_allclose(wrapped.transition_matrix(X[3], X[8]).to_dense(), base.transition_matrix(t[3], t[8]).to_dense())
+    g1, g2 = GaussianProcess(wrapped, X, diag=0.1), GaussianProcess(base, t, diag=0.1)
+    assert isinstance(g1.solver, QuasisepSolver)
+    assert_allclose(g1.log_probability(y), g2.log_probability(y))
+    for kw1, kw2 in ((dict(X_test=Xt), dict(X_test=tt)), (dict(), dict())):
+        c1, c2 = g1.condition(y, **kw1).gp, g2.condition(y, **kw2).gp
+        assert_allclose(c1.loc, c2.loc)
+        assert_allclose(c1.covariance, c2.covariance)
+    with pytest.raises(ValueError, match="Input coordinates must be sorted"):
+        GaussianProcess(wrapped, X[::-1], diag=0.1)
+
+    class Multiband(TimeColumn):                                     # a coordinate-dependent observation model: refused
+        def observation_model(self, X):
+            return np.asarray(X)[1] * self.kernel.observation_model(X[0])
+
+    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
+        GaussianProcess(Multiband(base), X, diag=0.1)
+
+
 def test_oversized_products_are_refused():                           # what the backend still lacks, refused loudly
     with pytest.raises(NotImplementedError, match="unsupported by the B200"):      # a sum multiplied out past 8 states
         QuasisepSolver((quasisep.Matern52(1.5) + quasisep.Matern32(0.7)) * quasisep.SHO(omega=1.5, quality=0.1),

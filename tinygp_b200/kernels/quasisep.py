@@ -10,7 +10,7 @@ are computed on the device in registers from t[k] - t[k-1]; they are never mater
 
 from __future__ import annotations
 
-__all__ = ["Quasisep", "Sum", "Product", "Scale", "Celerite", "SHO", "Exp", "Matern32", "Matern52",
+__all__ = ["Quasisep", "Wrapper", "Sum", "Product", "Scale", "Celerite", "SHO", "Exp", "Matern32", "Matern52",
            "Cosine", "CARMA", "carma_roots", "carma_quads2poly", "carma_poly2quads", "carma_acvf"]
 
 import numpy as np
@@ -131,10 +131,14 @@ class Quasisep(Kernel):
         return self.tau_program(lc.metric_code())   # distance code 0 = L1 = |t1 - t2| in one dimension
 
     def __call__(self, X1, X2=None):
-        X1 = np.asarray(X1, dtype=np.float64)
-        if X1.ndim != 1 or (X2 is not None and np.ndim(X2) != 1):
+        return self._dense(self.coord_to_sortable(X1), None if X2 is None else self.coord_to_sortable(X2))
+
+    def _dense(self, t1, t2=None):
+        """k(t1, t2) for coordinates that are already sortable (coord_to_sortable applied): the CUDA build kernel"""
+        t1 = np.asarray(t1, dtype=np.float64)
+        if t1.ndim != 1 or (t2 is not None and np.ndim(t2) != 1):
             raise ValueError("quasiseparable kernels take 1-D sortable coordinates")
-        return super().__call__(X1, X2)
+        return super().__call__(t1, t2)
 
     def to_general_qsm(self, X1, X2):
         """quasisep.py:118-145: the rectangular cross-covariance as a handle whose ``@ y`` runs on the device"""
@@ -317,11 +321,48 @@ class Sum(Quasisep):
         return self.kernel1.tau_program(dist) + self.kernel2.tau_program(dist) + [(OP_ADD, 0, 0.0, 0.0)]
 
 
-class Scale(Quasisep):
+class Wrapper(Quasisep):
+    """quasisep.py:218-238: a base class for kernels that wrap another quasiseparable kernel.  Everything is forwarded to
+    ``self.kernel``; a subclass may override ``coord_to_sortable`` (e.g. to pick the time column of structured inputs).  An
+    overridden ``observation_model`` -- a coordinate-dependent h, as in the reference's multiband tutorial -- cannot be lowered
+    to the device model (its h is a constant of the kernel) and is refused."""
+
+    def __init__(self, kernel: Quasisep):
+        self.kernel = kernel
+
+    def coord_to_sortable(self, X):
+        return self.kernel.coord_to_sortable(X)
+
+    def components(self):
+        if type(self).observation_model is not Wrapper.observation_model:
+            raise NotImplementedError(f"{type(self).__name__} overrides observation_model: a coordinate-dependent observation "
+                                      "model is unsupported by the B200 quasiseparable solver backend")
+        return self.kernel.components()
+
+    def tau_program(self, dist):
+        return self.kernel.tau_program(dist)
+
+    def design_matrix(self):
+        return self.kernel.design_matrix()
+
+    def stationary_covariance(self):
+        return self.kernel.stationary_covariance()
+
+    def observation_model(self, X):
+        return self.kernel.observation_model(self.coord_to_sortable(X))
+
+    def transition_matrix(self, X1, X2):
+        return self.kernel.transition_matrix(self.coord_to_sortable(X1), self.coord_to_sortable(X2))
+
+
+class Scale(Wrapper):
     """quasisep.py:334-340"""
 
     def __init__(self, kernel: Quasisep, scale):
         self.kernel, self.scale = kernel, scale
+
+    def stationary_covariance(self):
+        return self.scale * self.kernel.stationary_covariance()
 
     def components(self):
         s = float(self.scale)

@@ -17,6 +17,7 @@ import numpy as np
 class GeneralQSM:
     def __init__(self, kernel, X1, X2):
         self.kernel = kernel
+        self._raw = (X1, X2)                      # kernel.matmul applies coord_to_sortable itself
         self.X1 = np.asarray(kernel.coord_to_sortable(X1), dtype=np.float64)
         self.X2 = np.asarray(kernel.coord_to_sortable(X2), dtype=np.float64)
         if self.X1.ndim != 1 or self.X2.ndim != 1:
@@ -39,7 +40,7 @@ class GeneralQSM:
 
     def matmul(self, x):
         """general.py:66-103: (n2, ...) -> (n1, ...)"""
-        return self.kernel.matmul(self.X1, self.X2, x)
+        return self.kernel.matmul(self._raw[0], self._raw[1], x)
 
     def __matmul__(self, other):
         return self.matmul(other)

@@ -37,12 +37,12 @@ class QuasisepSolver(Solver):
             # SymmQSM of order J + J_band, factored from its generator arrays
             if not isinstance(kernel, Quasisep):
                 raise ValueError("QuasisepSolver requires a tinygp_b200.kernels.quasisep.Quasisep kernel")
-            X = _cabi.f64(kernel.coord_to_sortable(X))
-            if X.ndim != 1:
+            t = _cabi.f64(kernel.coord_to_sortable(X))
+            if t.ndim != 1:
                 raise ValueError("QuasisepSolver takes 1-D sortable coordinates")
             if not assume_sorted:
                 unsorted = c_int(0)
-                self._ctx.check(self._ctx.lib.b200gp_qs_check_sorted(self._ctx.handle, _cabi.ptr(X), X.shape[0], byref(unsorted)))
+                self._ctx.check(self._ctx.lib.b200gp_qs_check_sorted(self._ctx.handle, _cabi.ptr(t), t.shape[0], byref(unsorted)))
                 if unsorted.value:
                     raise ValueError(_UNSORTED_MSG)
             covariance = kernel.to_symm_qsm(X) + noise.to_qsm()
@@ -63,7 +63,7 @@ class QuasisepSolver(Solver):
         t = _cabi.f64(kernel.coord_to_sortable(X))
         if t.ndim != 1:
             raise ValueError("QuasisepSolver takes 1-D sortable coordinates")
-        self.X = t
+        self.X = X                     # as given (solver.py:66); the kernel's coord_to_sortable is applied where it is used
         self._n = t.shape[0]
         diag = _cabi.f64(noise.diagonal())
         if diag.shape != t.shape:
@@ -259,7 +259,7 @@ class QuasisepSolver(Solver):
                                                                _cabi.ptr(out)))
             return ConditionedCovariance.tag(out, False)
         if X_test is None:
-            prog, x = kernel.lower_for(self.X)
+            prog, x = kernel.lower_for(kernel.coord_to_sortable(self.X) if hasattr(kernel, "coord_to_sortable") else self.X)
             xt_ptr, m = None, self._n
         else:
             xt = np.asarray(kernel.coord_to_sortable(X_test) if hasattr(kernel, "coord_to_sortable") else X_test,

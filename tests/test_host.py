@@ -84,7 +84,7 @@ def test_quasisep_components():
     cs = ((Q.Matern32(1.0) + 0.3 * Q.Exp(1.0)) * Q.Exp(2.0)).component_array()
     assert cs[:, 0].tolist() == [Q.QS_MATERN32, Q.QS_EXP, Q.QS_EXP, Q.QS_EXP]
     assert cs[:, 6].tolist() == [1.0, 0.0, 1.0, 0.0] and cs[:, 1].tolist() == [1.0, 1.0, 0.3, 1.0]
-    with pytest.raises(NotImplementedError):      # ... unless that needs more than 8 states (3 * 2 + 2 * 2 = 10)
+    with pytest.raises(NotImplementedError):      # ... more than 8 states (3 * 2 + 2 * 2 = 10): no device rows (generator arrays instead)
         ((Q.Matern52(1.0) + Q.Matern32(1.0)) * Q.SHO(1.0, 2.0)).component_array()
 
 

@@ -435,21 +435,134 @@ def test_wrapper_kernels():                                          # kernels/q
     with pytest.raises(ValueError, match="Input coordinates must be sorted"):
         GaussianProcess(wrapped, X[::-1], diag=0.1)
 
-    class Multiband(TimeColumn):                                     # a coordinate-dependent observation model: refused
+    class Multiband(TimeColumn):     # a coordinate-dependent observation model (the reference's multiband tutorial): no device
+        amp = np.array([1.0, 0.6])   # state-space rows for that -> generators from these Python methods, device QSM algebra
         def observation_model(self, X):
-            return np.asarray(X)[1] * self.kernel.observation_model(X[0])
+            return self.amp[int(X[1])] * self.kernel.observation_model(X[0])
 
-    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
-        GaussianProcess(Multiband(base), X, diag=0.1)
+    mb = Multiband(base)
+    assert not mb._on_device() and not mb._has_closed_form()
+    band = X[:, 1].astype(int)
+    want = np.outer(mb.amp[band], mb.amp[band]) * base(t, t)
+    assert_allclose(mb(X, X), want)
+    assert_allclose(mb(X), np.diag(want))
+    assert_allclose(mb.to_symm_qsm(X).to_dense(), want)
+    cross = mb.amp[0] * mb.amp[band][None, :] * base(tt, t)
+    assert_allclose(mb(Xt, X), cross)
+    assert_allclose(mb.matmul(Xt, X, y), cross @ y)
+    assert_allclose(mb.evaluate(X[3], X[9]), want[3, 9])
+    assert_allclose(mb.evaluate(X[9], X[3]), want[3, 9])
+    g3 = GaussianProcess(mb, X, diag=0.1)
+    g4 = GaussianProcess(mb, X, diag=0.1, solver=DirectSolver)
+    assert isinstance(g3.solver, QuasisepSolver) and g3.solver._generic
+    Sigma = want + 0.1 * np.eye(40)
+    sign, logdet = np.linalg.slogdet(Sigma)
+    lp = -0.5 * y @ np.linalg.solve(Sigma, y) - 0.5 * logdet - 20 * np.log(2 * np.pi)
+    assert_allclose(g3.log_probability(y), lp)
+    assert_allclose(g4.log_probability(y), lp)
+    for kw in (dict(X_test=Xt), dict()):
+        c3, c4 = g3.condition(y, **kw).gp, g4.condition(y, **kw).gp
+        assert_allclose(c3.loc, c4.loc)
+        assert_allclose(c3.covariance, c4.covariance)
+    assert_allclose(g3.condition(y, Xt).gp.loc, cross @ np.linalg.solve(Sigma, y))
 
 
-def test_oversized_products_are_refused():                           # what the backend still lacks, refused loudly
-    with pytest.raises(NotImplementedError, match="unsupported by the B200"):      # a sum multiplied out past 8 states
-        QuasisepSolver((quasisep.Matern52(1.5) + quasisep.Matern32(0.7)) * quasisep.SHO(omega=1.5, quality=0.1),
-                       np.linspace(0, 1, 5), noise.Diagonal(np.full(5, 0.1)))
-    with pytest.raises(NotImplementedError, match="unsupported by the B200"):
-        QuasisepSolver(quasisep.Matern52(1.5) * quasisep.Matern52(0.5), np.linspace(0, 1, 5),      # 3 x 3 = 9 states
-                       noise.Diagonal(np.full(5, 0.1)))
+# ---- tests/test_kernels/test_quasisep_nonreversible.py (structured (N, 2) arrays instead of pytree coordinates) ----------
+class CausalFilter(quasisep.Quasisep):
+    """A minimal non-reversible two-state process: driver -> response."""
+
+    def design_matrix(self):
+        return np.array([[-1.0, 0.0], [0.8, -2.0]])
+
+    def stationary_covariance(self):
+        return np.array([[0.5, 2.0 / 15.0], [2.0 / 15.0, 91.0 / 300.0]])
+
+    def observation_model(self, X):
+        return np.eye(2)[int(X[1])]
+
+    def coord_to_sortable(self, X):
+        return X[0]
+
+    def transition_matrix(self, X1, X2):
+        from scipy.linalg import expm
+        return expm(self.design_matrix().T * (X2[0] - X1[0]))
+
+
+def _direct_covariance(kernel, X1, X2):                               # test_quasisep_nonreversible.py:36-50
+    Pinf = kernel.stationary_covariance()
+    out = np.empty((len(X1), len(X2)))
+    for i, x1 in enumerate(X1):
+        for j, x2 in enumerate(X2):
+            h1, h2 = kernel.observation_model(x1), kernel.observation_model(x2)
+            out[i, j] = (h2 @ kernel.transition_matrix(x1, x2).T @ Pinf @ h1 if x1[0] < x2[0]
+                         else h1 @ kernel.transition_matrix(x2, x1).T @ Pinf @ h2)
+    return out
+
+
+_NR_X = np.stack(([0.0, 0.3, 0.8, 1.4, 2.2, 3.1], [0, 1, 0, 1, 1, 0]), axis=1)
+_NR_XT = np.stack(([0.1, 0.9, 1.8, 2.8], [1, 0, 1, 0]), axis=1)
+
+
+def test_nonreversible_covariance_and_cross_matmul():                # test_quasisep_nonreversible.py:53-78
+    kernel = CausalFilter()
+    expected = _direct_covariance(kernel, _NR_X, _NR_X)
+    assert_allclose(kernel(_NR_X, _NR_X), expected)
+    assert_allclose(kernel.to_symm_qsm(_NR_X).to_dense(), expected)
+    cross = _direct_covariance(kernel, _NR_XT, _NR_X)
+    y = np.linspace(-0.5, 0.7, 6)
+    assert_allclose(kernel.matmul(_NR_XT, _NR_X, y), cross @ y)
+    a = _direct_covariance(kernel, np.array([[1.0, 1]]), np.array([[0.0, 0]]))[0, 0]
+    b = _direct_covariance(kernel, np.array([[1.0, 0]]), np.array([[0.0, 1]]))[0, 0]
+    assert not np.isclose(a, b)
+    assert_allclose(kernel.evaluate(np.array([1.0, 1]), np.array([0.0, 0])), a)
+
+
+def test_nonreversible_solvers_and_conditioning_agree():             # test_quasisep_nonreversible.py:81-106
+    kernel = CausalFilter()
+    y = np.array([0.2, -0.1, 0.3, 0.15, -0.2, 0.05])
+    diag = np.full(6, 0.05)
+    gp_direct = GaussianProcess(kernel, _NR_X, diag=diag, solver=DirectSolver)
+    gp_quasisep = GaussianProcess(kernel, _NR_X, diag=diag, solver=QuasisepSolver)
+    assert_allclose(gp_quasisep.covariance, gp_direct.covariance)
+    assert_allclose(gp_quasisep.log_probability(y), gp_direct.log_probability(y))
+    Sigma = _direct_covariance(kernel, _NR_X, _NR_X) + np.diag(diag)
+    sign, logdet = np.linalg.slogdet(Sigma)
+    assert_allclose(gp_direct.log_probability(y), -0.5 * y @ np.linalg.solve(Sigma, y) - 0.5 * logdet - 3 * np.log(2 * np.pi))
+    for kw in (dict(), dict(X_test=_NR_XT)):
+        cd, cq = gp_direct.condition(y, **kw), gp_quasisep.condition(y, **kw)
+        assert_allclose(cq.gp.loc, cd.gp.loc)
+        assert_allclose(cq.gp.covariance, cd.gp.covariance)
+
+
+def test_models_with_more_than_eight_states_use_generator_arrays():
+    """Matern52 + Matern52 + SHO + SHO = 10 states: above the 8 the model-specialised kernels compile, so the generators are
+    evaluated on the host and the device works on generator arrays of order 10 (QuasisepSolver's generic mode)"""
+    rng = np.random.default_rng(2)
+    t = np.sort(rng.uniform(0, 10, 50))
+    y, tt = np.sin(t), rng.uniform(-1, 11, 5)
+    k = (quasisep.Matern52(1.5) + 0.5 * quasisep.Matern52(0.4) + quasisep.SHO(omega=1.2, quality=2.0, sigma=0.7)
+         + quasisep.SHO(omega=3.0, quality=0.3, sigma=0.4))
+    assert not k._on_device() and k._has_closed_form()
+    gq, gd = GaussianProcess(k, t, diag=0.1), GaussianProcess(k, t, diag=0.1, solver=DirectSolver)
+    assert isinstance(gq.solver, QuasisepSolver) and gq.solver._generic
+    assert_allclose(gq.log_probability(y), gd.log_probability(y))
+    assert_allclose(k.to_symm_qsm(t).to_dense(), k(t, t))
+    assert_allclose(k.matmul(tt, t, y), k(tt, t) @ y)
+    cq, cd = gq.condition(y, tt).gp, gd.condition(y, tt).gp
+    assert_allclose(cq.loc, cd.loc)
+    assert_allclose(cq.covariance, cd.covariance + 0.0)
+
+
+def test_oversized_products_use_generator_arrays():                  # more states than the model-specialised kernels compile
+    t = np.linspace(0, 4, 30)
+    y = np.cos(t)
+    for k in ((quasisep.Matern52(1.5) + quasisep.Matern32(0.7)) * quasisep.SHO(omega=1.5, quality=0.1),      # 6 + 4 states
+              quasisep.Matern52(1.5) * quasisep.Matern52(0.5)):                                              # 3 x 3 = 9 states
+        assert not k._on_device()
+        gq = GaussianProcess(k, t, diag=0.1)
+        assert gq.solver._generic
+        assert_allclose(gq.log_probability(y), GaussianProcess(k, t, diag=0.1, solver=DirectSolver).log_probability(y))
+        assert_allclose(k.to_symm_qsm(t).to_dense(), k(t, t))
 
 
 def test_carma():                                                    # test_quasisep.py:100-122

@@ -21,7 +21,14 @@ def _clone(fn):
 
 # every test of the CPU module except the ones that only assert pure host behaviour
 # test_consistent_with_direct needs first-run device code (b200gp_qs_condition, GramBack): it runs in test_zzy_*
-_SKIP = {"test_diagonal", "test_dense", "test_consistent_with_direct"}
+_SKIP = {"test_diagonal", "test_dense", "test_block", "test_sum_state_space_is_blocked_like_the_reference",
+         "test_consistent_with_direct"}
+# written after the round's last GPU minute was spent (CPU-checked through the mock and the host build of the device code only):
+# they run from test_zzzzz_late_additions_gpu.py, the LAST file, so that under `pytest -x` a first-run surprise there cannot
+# hide the results of the files in between
+LATE = {"test_wrapper_kernels", "test_nonreversible_covariance_and_cross_matmul",
+        "test_nonreversible_solvers_and_conditioning_agree", "test_models_with_more_than_eight_states_use_generator_arrays",
+        "test_oversized_products_use_generator_arrays", "test_conditioned"}
 for _name in dir(_cpu):
-    if _name.startswith("test_") and _name not in _SKIP:
+    if _name.startswith("test_") and _name not in _SKIP and _name not in LATE:
         globals()[_name] = _clone(getattr(_cpu, _name))

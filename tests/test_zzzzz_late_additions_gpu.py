@@ -1,0 +1,15 @@
+"""The restated reference tests that were added after the round's GPU minutes were spent (user-defined state-space kernels,
+models with more than 8 states, the Conditioned kernel through the device GEMM), run with the real backend.  On the CPU they
+pass over the mock C-ABI and the host build of the device QSM source (tests/test_host_layer_reference_tests.py); this file sorts
+last so that under `pytest -x` nothing else is hidden if one of them meets a first-run surprise on the GPU."""
+
+import pytest
+
+import test_host_layer_reference_tests as _cpu
+from test_host_layer_reference_tests import gp_data, kdata, random  # noqa: F401  (fixtures)
+from test_zx_reference_tests_gpu import LATE, _clone
+
+pytestmark = pytest.mark.gpu
+
+for _name in sorted(LATE):
+    globals()[_name] = _clone(getattr(_cpu, _name))

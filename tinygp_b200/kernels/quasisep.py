@@ -54,7 +54,70 @@ class Quasisep(Kernel):
         return total
 
     def coord_to_sortable(self, X):
+        """quasisep.py:88-100: the sortable (time) coordinate of ONE input point; the identity unless a subclass overrides it"""
         return X
+
+    def _sortable(self, X):
+        """coord_to_sortable over all points of X (the reference vmaps it): the array itself for the default identity -- also
+        through Sum / Product / Scale, which forward to their first kernel --, a per-point call of a user's override otherwise"""
+        fn = type(self).coord_to_sortable
+        if fn is Quasisep.coord_to_sortable:
+            return X
+        if fn in _FORWARDED_COORDS:
+            return (self.kernel1 if hasattr(self, "kernel1") else self.kernel)._sortable(X)
+        return np.asarray([self.coord_to_sortable(x) for x in np.asarray(X)], dtype=np.float64)
+
+    def _on_device(self) -> bool:
+        """does the state-space model lower to the device's component rows (a built-in model with at most 8 states)?  If not --
+        a user-defined subclass that writes design_matrix / stationary_covariance / observation_model / transition_matrix in
+        Python (quasisep.py:60-100), or a model with more states -- the generators are evaluated point by point on the host
+        and uploaded, and the device works on them as generator arrays of any order (solvers/quasisep/core.py, csrc/qsm.cu)."""
+        try:
+            self.component_array()
+        except NotImplementedError:
+            return False
+        return True
+
+    def _has_closed_form(self) -> bool:
+        try:
+            self.tau_program(0)
+        except NotImplementedError:
+            return False
+        return True
+
+    def _host_symm_qsm(self, X):
+        """quasisep.py:102-116 as written, with the model's own Python methods per point (X sorted by coord_to_sortable)"""
+        from tinygp_b200.solvers.quasisep import core
+        from tinygp_b200.solvers.quasisep.block import ensure_dense
+        X = np.asarray(X, dtype=np.float64)
+        n = X.shape[0]
+        Pinf = np.asarray(ensure_dense(self.stationary_covariance()), dtype=np.float64)
+        h = np.stack([np.asarray(self.observation_model(X[k]), dtype=np.float64) for k in range(n)])
+        a = np.stack([np.asarray(ensure_dense(self.transition_matrix(X[max(k - 1, 0)], X[k])), dtype=np.float64).T
+                      for k in range(n)])                                        # a_0 = T(x_0, x_0)^T
+        hP = h @ Pinf
+        return core.SymmQSM(diag=core.DiagQSM(d=np.sum(hP * h, axis=1)),
+                            lower=core.StrictLowerTriQSM(p=np.einsum("ni,nij->nj", h, a), q=hP, a=a))
+
+    def _host_joint(self, X1, X2):
+        """the SymmQSM of the union of two coordinate sets in sorted order + where each set sits in it: cross-covariances and
+        their products with vectors (quasisep.py:118-163) for models without a device lowering, by the symmetric device algebra"""
+        X1, X2 = np.asarray(X1, dtype=np.float64), np.asarray(X2, dtype=np.float64)
+        joint = np.concatenate((X1, X2), axis=0)
+        order = np.argsort(np.asarray(self._sortable(joint), dtype=np.float64), kind="stable")
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        return self._host_symm_qsm(joint[order]), order, rank[: X1.shape[0]], rank[X1.shape[0]:]
+
+    def _host_dense(self, X1, X2=None):
+        from tinygp_b200.solvers.quasisep.block import ensure_dense
+        X1 = np.asarray(X1, dtype=np.float64)
+        if X2 is None:                                                           # evaluate_diag, quasisep.py:212-215
+            Pinf = np.asarray(ensure_dense(self.stationary_covariance()), dtype=np.float64)
+            h = np.stack([np.asarray(self.observation_model(x), dtype=np.float64) for x in X1])
+            return np.sum((h @ Pinf) * h, axis=1)
+        S, _, r1, r2 = self._host_joint(X1, X2)
+        return S.to_dense()[np.ix_(r1, r2)]
 
     # ---- the state-space model on the host (quasisep.py:60-100: design_matrix, stationary_covariance, observation_model,
     # transition_matrix).  Small J x J NumPy matrices assembled from the SAME component rows the device lowers
@@ -110,7 +173,9 @@ class Quasisep(Kernel):
 
         from tinygp_b200 import _cabi
         from tinygp_b200.solvers.quasisep import core
-        t = _cabi.f64(np.asarray(self.coord_to_sortable(X), dtype=np.float64))
+        if not self._on_device():
+            return self._host_symm_qsm(X)
+        t = _cabi.f64(np.asarray(self._sortable(X), dtype=np.float64))
         if t.ndim != 1:
             raise ValueError("quasiseparable kernels take 1-D sortable coordinates")
         comps = self.component_array()
@@ -131,7 +196,9 @@ class Quasisep(Kernel):
         return self.tau_program(lc.metric_code())   # distance code 0 = L1 = |t1 - t2| in one dimension
 
     def __call__(self, X1, X2=None):
-        return self._dense(self.coord_to_sortable(X1), None if X2 is None else self.coord_to_sortable(X2))
+        if not self._has_closed_form():
+            return self._host_dense(X1, X2)
+        return self._dense(self._sortable(X1), None if X2 is None else self._sortable(X2))
 
     def _dense(self, t1, t2=None):
         """k(t1, t2) for coordinates that are already sortable (coord_to_sortable applied): the CUDA build kernel"""
@@ -148,6 +215,12 @@ class Quasisep(Kernel):
     def evaluate(self, X1, X2):
         """Scalar evaluation k(t1, t2) (kernels/quasisep.py:118-145): 1-element 1-D coordinates, not the (1, 1) arrays the
         stationary base class builds."""
+        if not self._has_closed_form():                                          # quasisep.py:201-210 as written
+            from tinygp_b200.solvers.quasisep.block import ensure_dense
+            if self.coord_to_sortable(X1) >= self.coord_to_sortable(X2):
+                X1, X2 = X2, X1
+            h1, h2 = self.observation_model(X1), self.observation_model(X2)
+            return float(h2 @ ensure_dense(self.transition_matrix(X1, X2)).T @ ensure_dense(self.stationary_covariance()) @ h1)
         t1 = np.atleast_1d(np.asarray(X1, dtype=np.float64)).reshape(-1)[:1]
         t2 = np.atleast_1d(np.asarray(X2, dtype=np.float64)).reshape(-1)[:1]
         return self(t1, t2)[0, 0]
@@ -164,8 +237,18 @@ class Quasisep(Kernel):
             y, X2 = X2, None
         if X2 is None:
             X2 = X1
-        t1 = _cabi.f64(np.asarray(self.coord_to_sortable(X1), dtype=np.float64))
-        t2 = _cabi.f64(np.asarray(self.coord_to_sortable(X2), dtype=np.float64))
+        if not self._on_device():
+            # no device model: K(X1, X2) y = rows X1 of  S [y at X2; 0 at X1]  with S the SymmQSM of the sorted union --
+            # O((n + m) J^2) in the device's symmetric QSM product, nothing densified
+            y = np.asarray(y, dtype=np.float64)
+            S, order, r1, r2 = self._host_joint(X1, X2)
+            if y.shape[0] != r2.shape[0]:
+                raise ValueError("dimension mismatch")
+            v = np.zeros((order.size,) + y.shape[1:])
+            v[r2] = y
+            return (S @ v)[r1]
+        t1 = _cabi.f64(np.asarray(self._sortable(X1), dtype=np.float64))
+        t2 = _cabi.f64(np.asarray(self._sortable(X2), dtype=np.float64))
         y = np.asarray(y, dtype=np.float64)
         if t1.ndim != 1 or t2.ndim != 1:
             raise ValueError("quasiseparable kernels take 1-D sortable coordinates")
@@ -314,6 +397,12 @@ class Sum(Quasisep):
     def transition_matrix(self, X1, X2):
         return self._blocked(self.kernel1.transition_matrix(X1, X2), self.kernel2.transition_matrix(X1, X2))
 
+    def observation_model(self, X):  # quasisep.py:283-289
+        return np.concatenate((self.kernel1.observation_model(X), self.kernel2.observation_model(X)))
+
+    def coord_to_sortable(self, X):  # quasisep.py:259-260
+        return self.kernel1.coord_to_sortable(X)
+
     def components(self):
         return self.kernel1.components() + self.kernel2.components()
 
@@ -323,9 +412,10 @@ class Sum(Quasisep):
 
 class Wrapper(Quasisep):
     """quasisep.py:218-238: a base class for kernels that wrap another quasiseparable kernel.  Everything is forwarded to
-    ``self.kernel``; a subclass may override ``coord_to_sortable`` (e.g. to pick the time column of structured inputs).  An
-    overridden ``observation_model`` -- a coordinate-dependent h, as in the reference's multiband tutorial -- cannot be lowered
-    to the device model (its h is a constant of the kernel) and is refused."""
+    ``self.kernel``; a subclass may override ``coord_to_sortable`` (e.g. to pick the time column of structured inputs) and keep
+    the device model.  A subclass that overrides a state-space method -- e.g. a coordinate-dependent ``observation_model``, the
+    reference's multiband tutorial -- has no device rows (their h is a constant of the kernel): its generators are evaluated by
+    its Python methods and the device works on them as generator arrays (Quasisep._on_device)."""
 
     def __init__(self, kernel: Quasisep):
         self.kernel = kernel
@@ -333,13 +423,21 @@ class Wrapper(Quasisep):
     def coord_to_sortable(self, X):
         return self.kernel.coord_to_sortable(X)
 
+    def _plain(self):
+        """does the wrapper leave the wrapped model as it is (only the coordinate mapping may differ)?  A subclass that
+        overrides one of the state-space methods has no device rows and no closed form: Quasisep._on_device() is then False
+        and the generators come from its Python methods"""
+        for m in ("design_matrix", "stationary_covariance", "observation_model", "transition_matrix"):
+            if getattr(type(self), m) is not getattr(Wrapper, m):
+                raise NotImplementedError(f"{type(self).__name__} overrides {m}: no device lowering for a user-defined "
+                                          "state-space method")
+
     def components(self):
-        if type(self).observation_model is not Wrapper.observation_model:
-            raise NotImplementedError(f"{type(self).__name__} overrides observation_model: a coordinate-dependent observation "
-                                      "model is unsupported by the B200 quasiseparable solver backend")
+        self._plain()
         return self.kernel.components()
 
     def tau_program(self, dist):
+        self._plain()
         return self.kernel.tau_program(dist)
 
     def design_matrix(self):
@@ -360,6 +458,9 @@ class Scale(Wrapper):
 
     def __init__(self, kernel: Quasisep, scale):
         self.kernel, self.scale = kernel, scale
+
+    def _plain(self):
+        pass
 
     def stationary_covariance(self):
         return self.scale * self.kernel.stationary_covariance()
@@ -411,6 +512,26 @@ class Product(Quasisep):
 
     def tau_program(self, dist):
         return self.kernel1.tau_program(dist) + self.kernel2.tau_program(dist) + [(OP_MUL, 0, 0.0, 0.0)]
+
+    # the product's state-space model in the reference's (interleaved Kronecker) state order, quasisep.py:304-331
+    def coord_to_sortable(self, X):
+        return self.kernel1.coord_to_sortable(X)
+
+    def design_matrix(self):
+        from tinygp_b200.solvers.quasisep.block import ensure_dense
+        F1, F2 = ensure_dense(self.kernel1.design_matrix()), ensure_dense(self.kernel2.design_matrix())
+        return _prod(F1, np.eye(F2.shape[0])) + _prod(np.eye(F1.shape[0]), F2)
+
+    def stationary_covariance(self):
+        from tinygp_b200.solvers.quasisep.block import ensure_dense
+        return _prod(ensure_dense(self.kernel1.stationary_covariance()), ensure_dense(self.kernel2.stationary_covariance()))
+
+    def observation_model(self, X):
+        return _prod(self.kernel1.observation_model(X), self.kernel2.observation_model(X))
+
+    def transition_matrix(self, X1, X2):
+        from tinygp_b200.solvers.quasisep.block import ensure_dense
+        return _prod(ensure_dense(self.kernel1.transition_matrix(X1, X2)), ensure_dense(self.kernel2.transition_matrix(X1, X2)))
 
 
 class Celerite(Quasisep):
@@ -667,3 +788,7 @@ def carma_acvf(arroots, arparam, maparam):
         root_k = arroots[np.roll(root_idx, j)]
         denom = denom * ((root_k - arroots) * (np.conj(root_k) + arroots))
     return sigma**2 * num_left * num_right / denom
+
+
+# coord_to_sortable implementations that only forward to a wrapped kernel (Quasisep._sortable sees through them)
+_FORWARDED_COORDS = (Sum.coord_to_sortable, Product.coord_to_sortable, Wrapper.coord_to_sortable)

@@ -33,6 +33,10 @@ class DirectSolver(Solver):
             # noise.Dense / noise.Banded (direct.py:47-48: covariance = kernel(X, X) + noise): the kernel matrix is built on
             # the device, the noise matrix joins it on its way to the device factorisation of a precomputed covariance
             covariance = noise + kernel(X, X)
+        if covariance is None and hasattr(kernel, "_has_closed_form") and not kernel._has_closed_form():
+            # a user-defined quasiseparable model (kernels/quasisep.py:60-100 written in Python) has no kernel program: its
+            # covariance comes from the device QSM algebra over host-evaluated generators (Quasisep._host_dense)
+            covariance = noise + kernel(X, X)
         if covariance is None:
             prog, x = kernel.lower_for(X)   # x = X, plus host-computed columns of any transforms.Transform
             diag = _cabi.f64(noise.diagonal())

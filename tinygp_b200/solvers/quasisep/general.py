@@ -18,8 +18,8 @@ class GeneralQSM:
     def __init__(self, kernel, X1, X2):
         self.kernel = kernel
         self._raw = (X1, X2)                      # kernel.matmul applies coord_to_sortable itself
-        self.X1 = np.asarray(kernel.coord_to_sortable(X1), dtype=np.float64)
-        self.X2 = np.asarray(kernel.coord_to_sortable(X2), dtype=np.float64)
+        self.X1 = np.asarray(kernel._sortable(X1), dtype=np.float64)
+        self.X2 = np.asarray(kernel._sortable(X2), dtype=np.float64)
         if self.X1.ndim != 1 or self.X2.ndim != 1:
             raise ValueError("quasiseparable kernels take 1-D sortable coordinates")
 

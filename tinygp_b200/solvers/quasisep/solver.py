@@ -32,12 +32,12 @@ class QuasisepSolver(Solver):
         self._h = c_void_p()
         self.kernel, self.noise, self.parallel = kernel, noise, parallel
         self._matrix = self._factor = None
-        if covariance is None and not isinstance(noise, Diagonal):
-            # noise.Banded (noise.py:226-240): solver.py:73-74 as written -- the kernel's SymmQSM plus the noise's, a device
-            # SymmQSM of order J + J_band, factored from its generator arrays
-            if not isinstance(kernel, Quasisep):
-                raise ValueError("QuasisepSolver requires a tinygp_b200.kernels.quasisep.Quasisep kernel")
-            t = _cabi.f64(kernel.coord_to_sortable(X))
+        if covariance is None and isinstance(kernel, Quasisep) and not (isinstance(noise, Diagonal) and kernel._on_device()):
+            # solver.py:73-74 as written -- the kernel's SymmQSM plus the noise's, factored from generator arrays -- for
+            #  * noise.Banded (noise.py:226-240): a device SymmQSM of order J + J_band;
+            #  * kernels without a device model (a user-defined state-space subclass, or more than 8 states): their
+            #    generators are evaluated by the kernel's own Python methods on the host and uploaded (any order J)
+            t = _cabi.f64(kernel._sortable(X))
             if t.ndim != 1:
                 raise ValueError("QuasisepSolver takes 1-D sortable coordinates")
             if not assume_sorted:
@@ -60,7 +60,7 @@ class QuasisepSolver(Solver):
             return
         if not isinstance(kernel, Quasisep):
             raise ValueError("QuasisepSolver requires a tinygp_b200.kernels.quasisep.Quasisep kernel")
-        t = _cabi.f64(kernel.coord_to_sortable(X))
+        t = _cabi.f64(kernel._sortable(X))
         if t.ndim != 1:
             raise ValueError("QuasisepSolver takes 1-D sortable coordinates")
         self.X = X                     # as given (solver.py:66); the kernel's coord_to_sortable is applied where it is used
@@ -259,10 +259,10 @@ class QuasisepSolver(Solver):
                                                                _cabi.ptr(out)))
             return ConditionedCovariance.tag(out, False)
         if X_test is None:
-            prog, x = kernel.lower_for(kernel.coord_to_sortable(self.X) if hasattr(kernel, "coord_to_sortable") else self.X)
+            prog, x = kernel.lower_for(kernel._sortable(self.X) if isinstance(kernel, Quasisep) else self.X)
             xt_ptr, m = None, self._n
         else:
-            xt = np.asarray(kernel.coord_to_sortable(X_test) if hasattr(kernel, "coord_to_sortable") else X_test,
+            xt = np.asarray(kernel._sortable(X_test) if isinstance(kernel, Quasisep) else X_test,
                             dtype=np.float64)
             if xt.ndim != 1:
                 raise ValueError("QuasisepSolver.condition takes 1-D test coordinates")

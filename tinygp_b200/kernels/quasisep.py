@@ -91,6 +91,20 @@ class Quasisep(Kernel):
         from tinygp_b200.solvers.quasisep.block import ensure_dense
         X = np.asarray(X, dtype=np.float64)
         n = X.shape[0]
+        try:
+            self.components()
+        except NotImplementedError:
+            pass
+        else:
+            # a built-in model (just more states than the model-specialised kernels compile): the same formulas for all points
+            # at once -- the component rows' closed-form transition matrices over the array of time steps
+            t = np.asarray(self._sortable(X), dtype=np.float64)
+            a = np.transpose(self._assemble("T", np.diff(t, prepend=t[:1])), (2, 1, 0))     # a_k = T(t_k - t_{k-1})^T, a_0 = I
+            h = self._assemble("h")
+            hP = h @ self._assemble("P")
+            return core.SymmQSM(diag=core.DiagQSM(d=np.full(n, hP @ h)),
+                                lower=core.StrictLowerTriQSM(p=np.einsum("i,nij->nj", h, a), q=np.tile(hP, (n, 1)),
+                                                             a=np.ascontiguousarray(a)))
         Pinf = np.asarray(ensure_dense(self.stationary_covariance()), dtype=np.float64)
         h = np.stack([np.asarray(self.observation_model(X[k]), dtype=np.float64) for k in range(n)])
         a = np.stack([np.asarray(ensure_dense(self.transition_matrix(X[max(k - 1, 0)], X[k])), dtype=np.float64).T
@@ -147,7 +161,7 @@ class Quasisep(Kernel):
         if blocks[0].ndim == 1:
             return np.concatenate(blocks)
         n = sum(b.shape[0] for b in blocks)
-        out, o = np.zeros((n, n)), 0
+        out, o = np.zeros((n, n) + blocks[0].shape[2:]), 0      # trailing axis: "T" for an array of time steps
         for b in blocks:
             out[o:o + b.shape[0], o:o + b.shape[0]] = b
             o += b.shape[0]

@@ -553,6 +553,29 @@ def test_models_with_more_than_eight_states_use_generator_arrays():
     assert_allclose(cq.covariance, cd.covariance + 0.0)
 
 
+def test_vectorised_generators_equal_the_per_point_formulas():
+    """models with more than 8 states: `_host_symm_qsm` evaluates the component rows' closed forms for all time steps at once;
+    the per-point path (quasisep.py:102-116 through the kernel's methods, what a user-defined subclass gets) gives the same arrays"""
+    t = np.sort(np.random.default_rng(3).uniform(0, 60, 400))
+    t[7] = t[6]
+    k = (quasisep.Celerite(1.1, 0.1, 0.3, 1.5) + quasisep.Cosine(3.0, 0.7) * quasisep.Exp(2.0) + quasisep.SHO(1.2, 0.5, 1.1)
+         + quasisep.SHO(1.2, 0.2, 1.1) + 0.3 * quasisep.Exp(0.5)
+         + quasisep.CARMA(alpha=np.array([1.4, 2.3, 1.5]), beta=np.array([0.1, 0.5])))
+    assert k.state_dim() == 12 and not k._on_device()
+    fast = k._host_symm_qsm(t)
+
+    def no_rows():
+        raise NotImplementedError
+    k.components = no_rows                       # the Sum's own state-space methods still work (its leaves keep their rows)
+    try:
+        slow = k._host_symm_qsm(t)
+    finally:
+        del k.components
+    assert_allclose(fast.diag.d, slow.diag.d, atol=1e-13, rtol=1e-12)
+    for part in ("p", "q", "a"):
+        assert_allclose(getattr(fast.lower, part), getattr(slow.lower, part), atol=1e-13, rtol=1e-12)
+
+
 def test_oversized_products_use_generator_arrays():                  # more states than the model-specialised kernels compile
     t = np.linspace(0, 4, 30)
     y = np.cos(t)

@@ -100,6 +100,11 @@ CASES = [
     dict(name="qs_carma21_real", kind="quasisep", kernel="quasisep.CARMA(alpha=np.array([0.1, 1.1]), beta=np.array([1.0, 3.0]))", n=120, span=30.0, diag=0.05, seed=33),
     dict(name="qs_carma10", kind="quasisep", kernel="quasisep.CARMA(alpha=np.array([1.0 / 100]), beta=np.array([0.3]))", n=120, span=30.0, diag=0.05, seed=34),
     dict(name="qs_carma_plus_m32", kind="quasisep", kernel="quasisep.CARMA.init(alpha=np.array([1.4, 2.3, 1.5]), beta=np.array([0.1, 0.5])) + 0.5 * quasisep.Matern32(1.5)", n=120, span=30.0, diag=0.05, seed=35),
+    # 7 and 8 states; a Sum inside a Product (multiplied out by the host lowering: the state vector is a permutation of the
+    # reference's, so only permutation-invariant outputs are recorded: small=False)
+    dict(name="qs_product_m52_cosine_plus_exp_7", kind="quasisep", kernel="quasisep.Matern52(scale=2.5, sigma=1.3) * quasisep.Cosine(scale=3.0, sigma=0.7) + quasisep.Exp(scale=2.0, sigma=0.5)", n=120, span=30.0, diag=0.05, seed=51),
+    dict(name="qs_m52_m52_sho_8", kind="quasisep", kernel="quasisep.Matern52(scale=2.5, sigma=1.3) + quasisep.Matern52(scale=0.6, sigma=0.4) + quasisep.SHO(omega=1.5, quality=3.0, sigma=0.8)", n=120, span=30.0, diag=0.05, seed=52),
+    dict(name="qs_product_of_sum_8", kind="quasisep", kernel="(quasisep.Matern52(1.5) + 0.4 * quasisep.Exp(0.7)) * quasisep.SHO(omega=1.5, quality=0.1)", n=120, span=30.0, diag=0.05, seed=53, small=False),
     # noise.Banded / noise.Dense (noise.py:98-240): the precomputed-covariance paths of both solvers
     dict(name="qs_m32_sho_noise_banded2", kind="quasisep", kernel="quasisep.Matern32(scale=1.5, sigma=1.8) + quasisep.SHO(omega=1.2, quality=2.0, sigma=0.7)", n=120, span=30.0, seed=41, noise="banded", band=2),
     dict(name="qs_exp_noise_banded5", kind="quasisep", kernel="quasisep.Exp(scale=1.7, sigma=0.8)", n=120, span=30.0, seed=42, noise="banded", band=5),

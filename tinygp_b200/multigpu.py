@@ -10,10 +10,7 @@ from __future__ import annotations
 
 from ctypes import byref, c_double, c_int, c_int64, c_void_p
 
-import numpy as np
-
 from tinygp_b200 import _cabi
-from tinygp_b200.kernels.base import _as_coords
 
 ALIGN = 256  # row chunks are whole 256-row tile pairs
 

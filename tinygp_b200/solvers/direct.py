@@ -11,7 +11,7 @@ from typing import Any
 import numpy as np
 
 from tinygp_b200 import _cabi
-from tinygp_b200.kernels.base import Kernel, _as_coords
+from tinygp_b200.kernels.base import Kernel
 from tinygp_b200.noise import Diagonal
 from tinygp_b200.solvers.solver import ConditionedCovariance, Solver
 

@@ -45,6 +45,8 @@ class QuasisepSolver(Solver):
                 self._ctx.check(self._ctx.lib.b200gp_qs_check_sorted(self._ctx.handle, _cabi.ptr(t), t.shape[0], byref(unsorted)))
                 if unsorted.value:
                     raise ValueError(_UNSORTED_MSG)
+            if np.shape(noise.diagonal()) != t.shape:
+                raise ValueError("noise diagonal must have shape (N,)")
             covariance = kernel.to_symm_qsm(X) + noise.to_qsm()
         if covariance is not None:
             if not isinstance(covariance, qcore.SymmQSM):

@@ -534,6 +534,32 @@ def test_nonreversible_solvers_and_conditioning_agree():             # test_quas
         assert_allclose(cq.gp.covariance, cd.gp.covariance)
 
 
+def test_user_defined_kernel_reproduces_the_reference():
+    """the same CausalFilter run by the UNMODIFIED reference (tests/golden/make_golden_custom.py -> custom_kernel_vectors.json,
+    pytree coordinates there, (N, 2) arrays here): kernel values, QSM, cross product, both solvers, conditioning"""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "custom_kernel_vectors.json")) as f:
+        g = json.load(f)
+    X = np.stack((g["time"], g["channel"]), axis=1).astype(float)
+    Xt = np.stack((g["time_test"], g["channel_test"]), axis=1).astype(float)
+    y, diag = np.array(g["y"]), np.full(len(g["time"]), g["diag"])
+    kernel = CausalFilter()
+    tol = dict(atol=1e-12, rtol=1e-10)
+    assert_allclose(kernel(X, X), g["K"], **tol)
+    assert_allclose(kernel(Xt, X), g["K_cross"], **tol)
+    assert_allclose(kernel.to_symm_qsm(X).to_dense(), g["symm_qsm_dense"], **tol)
+    assert_allclose(kernel.matmul(Xt, X, y), g["cross_matmul"], **tol)
+    for name, solver in (("quasisep", QuasisepSolver), ("direct", DirectSolver)):
+        gp, want = GaussianProcess(kernel, X, diag=diag, solver=solver), g[name]
+        assert_allclose(gp.log_probability(y), want["log_probability"], **tol)
+        assert_allclose(gp.covariance, want["covariance"], **tol)
+        c_in, c_test = gp.condition(y), gp.condition(y, X_test=Xt)
+        assert_allclose(c_in.gp.loc, want["cond_in_loc"], atol=1e-10, rtol=1e-9)
+        assert_allclose(c_in.gp.covariance, want["cond_in_cov"], atol=1e-10, rtol=1e-9)
+        assert_allclose(c_test.gp.loc, want["cond_test_loc"], atol=1e-10, rtol=1e-9)
+        assert_allclose(c_test.gp.covariance, want["cond_test_cov"], atol=1e-10, rtol=1e-9)
+
+
 def test_models_with_more_than_eight_states_use_generator_arrays():
     """Matern52 + Matern52 + SHO + SHO = 10 states: above the 8 the model-specialised kernels compile, so the generators are
     evaluated on the host and the device works on generator arrays of order 10 (QuasisepSolver's generic mode)"""

@@ -72,6 +72,35 @@ def main():
         rec["cond_test_cov"] = np.asarray(c_test.gp.covariance).tolist()
         out[name] = rec
         print(name, rec["log_probability"])
+    # a Wrapper with a coordinate-dependent observation model (quasisep.py:218-238; the multiband construction of the
+    # reference's documentation): amplitude per band times the wrapped kernel's observation model
+    class Multiband(quasisep.Wrapper):
+        amplitudes: jnp.ndarray
+
+        def coord_to_sortable(self, X):
+            return X[0]
+
+        def observation_model(self, X):
+            return self.amplitudes[X[1]] * self.kernel.observation_model(X[0])
+
+    rng = np.random.default_rng(11)
+    t = np.sort(rng.uniform(0, 10, 40))
+    band = rng.integers(0, 2, 40)
+    tt = rng.uniform(-1, 11, 6)
+    band_t = np.array([0, 1, 1, 0, 1, 0])
+    ym = np.sin(t)
+    base = quasisep.Matern32(1.5) + 0.5 * quasisep.SHO(omega=1.2, quality=2.0)
+    mb = Multiband(kernel=base, amplitudes=jnp.array([1.0, 0.6]))
+    Xm, Xmt = (jnp.asarray(t), jnp.asarray(band)), (jnp.asarray(tt), jnp.asarray(band_t))
+    rec = {"t": t.tolist(), "band": band.tolist(), "t_test": tt.tolist(), "band_test": band_t.tolist(), "y": ym.tolist(),
+           "amplitudes": [1.0, 0.6], "K": np.asarray(mb(Xm, Xm)).tolist(), "K_cross": np.asarray(mb(Xmt, Xm)).tolist()}
+    gp = GaussianProcess(mb, Xm, diag=0.1)
+    rec["log_probability"] = float(gp.log_probability(ym))
+    c_in, c_test = gp.condition(ym), gp.condition(ym, X_test=Xmt)
+    rec["cond_in_loc"], rec["cond_in_var"] = np.asarray(c_in.gp.loc).tolist(), np.asarray(c_in.gp.variance).tolist()
+    rec["cond_test_loc"], rec["cond_test_cov"] = np.asarray(c_test.gp.loc).tolist(), np.asarray(c_test.gp.covariance).tolist()
+    out["multiband"] = rec
+    print("multiband", rec["log_probability"])
     with open(os.path.join(HERE, "custom_kernel_vectors.json"), "w") as f:
         json.dump(out, f, indent=0)
     print("wrote custom_kernel_vectors.json")

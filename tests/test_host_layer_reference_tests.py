@@ -560,6 +560,38 @@ def test_user_defined_kernel_reproduces_the_reference():
         assert_allclose(c_test.gp.covariance, want["cond_test_cov"], atol=1e-10, rtol=1e-9)
 
 
+def test_multiband_wrapper_reproduces_the_reference():
+    """a Wrapper whose observation model depends on the band column, run by the unmodified reference (make_golden_custom.py)"""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "custom_kernel_vectors.json")) as f:
+        g = json.load(f)["multiband"]
+
+    class Multiband(quasisep.Wrapper):
+        def __init__(self, kernel, amplitudes):
+            self.kernel, self.amplitudes = kernel, np.asarray(amplitudes)
+
+        def coord_to_sortable(self, X):
+            return X[0]
+
+        def observation_model(self, X):
+            return self.amplitudes[int(X[1])] * self.kernel.observation_model(X[0])
+
+    X = np.stack((g["t"], g["band"]), axis=1).astype(float)
+    Xt = np.stack((g["t_test"], g["band_test"]), axis=1).astype(float)
+    y = np.array(g["y"])
+    mb = Multiband(quasisep.Matern32(1.5) + 0.5 * quasisep.SHO(omega=1.2, quality=2.0), g["amplitudes"])
+    tol = dict(atol=1e-11, rtol=1e-9)
+    assert_allclose(mb(X, X), g["K"], **tol)
+    assert_allclose(mb(Xt, X), g["K_cross"], **tol)
+    gp = GaussianProcess(mb, X, diag=0.1)
+    assert_allclose(gp.log_probability(y), g["log_probability"], **tol)
+    c_in, c_test = gp.condition(y), gp.condition(y, X_test=Xt)
+    assert_allclose(c_in.gp.loc, g["cond_in_loc"], **tol)
+    assert_allclose(c_in.gp.variance, g["cond_in_var"], **tol)
+    assert_allclose(c_test.gp.loc, g["cond_test_loc"], **tol)
+    assert_allclose(c_test.gp.covariance, g["cond_test_cov"], **tol)
+
+
 def test_models_with_more_than_eight_states_use_generator_arrays():
     """Matern52 + Matern52 + SHO + SHO = 10 states: above the 8 the model-specialised kernels compile, so the generators are
     evaluated on the host and the device works on generator arrays of order 10 (QuasisepSolver's generic mode)"""
